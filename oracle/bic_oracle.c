@@ -1,0 +1,464 @@
+/*
+ * TEST INFRASTRUCTURE -- the CPU oracle. NOT part of the product. See bic_oracle.h for the
+ * pinning statement and the layout convention. Every function cites the reference
+ * file:line (relative to /root/reference/) whose behaviour it restates.
+ */
+#include "bic_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#define BO_MSB ((bo_word)1 << 63)
+
+uint64_t bo_wpr(uint64_t cols) { return (cols + 63) / 64; } /* src/binmat.cpp:143 */
+
+static inline int popc64(bo_word v) { return __builtin_popcountll(v); } /* = block_weight, src/binmat.cpp:22-37 */
+
+static inline int get_bit(const bo_word* row, uint64_t j) { /* src/binmat.h:114-116 */
+  return (int)((row[j >> 6] >> (63 - (j & 63))) & 1u);
+}
+static inline void put_bit(bo_word* row, uint64_t j, int v) { /* src/binmat.h:121-141 */
+  const bo_word mask = BO_MSB >> (j & 63);
+  if (v) row[j >> 6] |= mask; else row[j >> 6] &= ~mask;
+}
+
+/* src/binmat.cpp:57-67 (pad bits are zero by convention, so no trail mask is needed) */
+uint64_t bo_weight(const bo_word* M, uint64_t rows, uint64_t cols) {
+  const uint64_t total = rows * bo_wpr(cols);
+  uint64_t w = 0;
+  for (uint64_t i = 0; i < total; ++i) w += (uint64_t)popc64(M[i]);
+  return w;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Patch extraction. src/bsvd_test.cpp:80-99.
+ *
+ * copy_submatrix_to (src/binmat.cpp:267-298) reads the raster through LINEAR word indices
+ * k = i0*bpr + j0/64 + di*bpr + dj (and k+1 for unaligned tiles), substituting 0 only when
+ * k >= data_blocks. So pixel (r, c) is the bit at linear position r*bpr*64 + c of the padded
+ * raster: columns cols..bpr*64-1 read the (zero) pad, and a column >= bpr*64 -- which only an
+ * edge tile with W not dividing 64 can ask for -- falls through into the next raster row.
+ * That is reproduced here on purpose. Tile rows are then masked to W bits (get_block,
+ * src/binmat.h:188-190) and concatenated row-major, MSB first (copy_vectorized_to, :306-320;
+ * well defined for W < 64, which is all the reference's drivers use).
+ * ------------------------------------------------------------------------------------------ */
+static inline int raster_bit(const bo_word* I, uint64_t data_blocks, uint64_t bpr, uint64_t r, uint64_t c) {
+  const uint64_t k = r * bpr + (c >> 6);
+  if (k >= data_blocks) return 0;
+  return (int)((I[k] >> (63 - (c & 63))) & 1u);
+}
+
+void bo_extract_patches(const bo_word* I, uint64_t rows, uint64_t cols, uint64_t W, bo_word* X) {
+  const uint64_t bpr = bo_wpr(cols);
+  const uint64_t data_blocks = bpr * rows;
+  const uint64_t Ny = (W - 1 + rows) / W, Nx = (W - 1 + cols) / W; /* bsvd_test.cpp:82-83 */
+  const uint64_t m = W * W, xw = bo_wpr(m);
+  memset(X, 0, sizeof(bo_word) * Nx * Ny * xw);
+  uint64_t li = 0;
+  for (uint64_t i = 0; i < Ny; ++i) {
+    for (uint64_t j = 0; j < Nx; ++j, ++li) { /* row-major patch order, bsvd_test.cpp:92-93 */
+      bo_word* xr = X + li * xw;
+      for (uint64_t pr = 0; pr < W; ++pr)
+        for (uint64_t pc = 0; pc < W; ++pc)
+          if (raster_bit(I, data_blocks, bpr, i * W + pr, j * W + pc)) put_bit(xr, pr * W + pc, 1);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * RNG: GSL's rand48 and gsl_rng_uniform_int (un-vendored dependency; call sites
+ * src/bsvd.cpp:8-15, :241). Restated from GSL's published rng/rand48.c and rng/rng.c.
+ * ------------------------------------------------------------------------------------------ */
+void bo_rand48_seed(bo_rand48* r, unsigned long s) {
+  if (s == 0) { r->x0 = 0x330E; r->x1 = 0xABCD; r->x2 = 0x1234; }
+  else { r->x0 = 0x330E; r->x1 = (uint16_t)(s & 0xFFFF); r->x2 = (uint16_t)((s >> 16) & 0xFFFF); }
+}
+
+uint32_t bo_rand48_next(bo_rand48* r) {
+  /* one 48-bit multiply-add instead of GSL's three 16-bit limbs; same recurrence */
+  uint64_t x = ((uint64_t)r->x2 << 32) | ((uint64_t)r->x1 << 16) | (uint64_t)r->x0;
+  x = (x * 0x5DEECE66DULL + 0xBULL) & 0xFFFFFFFFFFFFULL;
+  r->x0 = (uint16_t)(x & 0xFFFF);
+  r->x1 = (uint16_t)((x >> 16) & 0xFFFF);
+  r->x2 = (uint16_t)((x >> 32) & 0xFFFF);
+  return (uint32_t)(x >> 16);
+}
+
+uint64_t bo_uniform_int(bo_rand48* r, uint64_t n) {
+  const uint64_t range = 0xFFFFFFFFULL;
+  if (n == 0 || n > range) return 0;
+  const uint64_t scale = range / n;
+  uint64_t k;
+  do { k = (uint64_t)bo_rand48_next(r) / scale; } while (k >= n);
+  return k;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * initialize_model_neighbor. src/bsvd.cpp:227-267.
+ * ------------------------------------------------------------------------------------------ */
+uint64_t bo_draw_pivots(const bo_word* X, uint64_t n, uint64_t m, uint64_t p, bo_rand48* rng,
+                        uint64_t* pivots) {
+  const uint64_t wpr = bo_wpr(m);
+  uint64_t draws = 0;
+  for (uint64_t k = 0; k < p;) {            /* :239 */
+    const uint64_t i = bo_uniform_int(rng, n); /* :241 */
+    ++draws;
+    const bo_word* Ei = X + i * wpr;
+    uint64_t w = 0;
+    for (uint64_t b = 0; b < wpr; ++b) w += (uint64_t)popc64(Ei[b]);
+    if (w == 0) continue;                   /* :243  rejected draw is consumed */
+    /* a non-zero pivot intersects itself, so u > 0 (:258) always holds and k advances */
+    pivots[k++] = i;
+  }
+  return draws;
+}
+
+void bo_init_neighbor_pivots(const bo_word* X, uint64_t n, uint64_t m, uint64_t p,
+                             const uint64_t* pivots, bo_word* D, bo_word* A) {
+  const uint64_t wpr = bo_wpr(m), apr = bo_wpr(p);
+  memset(A, 0, sizeof(bo_word) * n * apr); /* A.clear(), :237 */
+  memset(D, 0, sizeof(bo_word) * p * wpr); /* D.clear(), :238 */
+  uint64_t* s = (uint64_t*)malloc(sizeof(uint64_t) * (m ? m : 1));
+  bo_word* Ej = (bo_word*)malloc(sizeof(bo_word) * (wpr ? wpr : 1));
+  for (uint64_t k = 0; k < p; ++k) {
+    const bo_word* Ei = X + pivots[k] * wpr;
+    uint64_t u = 0;
+    for (uint64_t b = 0; b < m; ++b) s[b] = 0; /* :246 */
+    for (uint64_t j = 0; j < n; ++j) {         /* :247 */
+      uint64_t w = 0;
+      for (uint64_t b = 0; b < wpr; ++b) {     /* Ej = E[j] & Ei, :248-249 */
+        Ej[b] = X[j * wpr + b] & Ei[b];
+        w += (uint64_t)popc64(Ej[b]);
+      }
+      if (w > 0) {                             /* :250 */
+        u++;
+        for (uint64_t b = 0; b < m; ++b)       /* counts the AND, not E[j]; :252-255 */
+          if (get_bit(Ej, b)) s[b]++;
+      }
+    }
+    if (u > 0) {                               /* :258 */
+      for (uint64_t b = 0; b < m; ++b) put_bit(D + k * wpr, b, s[b] >= u / 2); /* ">=" and integer u/2, :259-260 */
+    }
+  }
+  free(s);
+  free(Ej);
+}
+
+void bo_init_neighbor(const bo_word* X, uint64_t n, uint64_t m, uint64_t p, bo_rand48* rng,
+                      bo_word* D, bo_word* A) {
+  uint64_t* pivots = (uint64_t*)malloc(sizeof(uint64_t) * (p ? p : 1));
+  bo_draw_pivots(X, n, m, p, rng, pivots);
+  bo_init_neighbor_pivots(X, n, m, p, pivots, D, A);
+  free(pivots);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * update_coefficients_omp (src/bsvd.cpp:1029-1107) == update_coefficients_basic (:399-460):
+ * greedy matching pursuit over GF(2), one row at a time, rows independent given D.
+ * ------------------------------------------------------------------------------------------ */
+uint64_t bo_update_coefficients(bo_word* E, const bo_word* D, bo_word* A,
+                                uint64_t n, uint64_t m, uint64_t p) {
+  const uint64_t wpr = bo_wpr(m), apr = bo_wpr(p);
+  uint64_t changed = 0;
+  if (p == 0) return 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    bo_word* Ei = E + i * wpr;
+    bo_word* Ai = A + i * apr;
+    int ichanged = 0;
+    for (;;) {
+      uint64_t w = 0;                                   /* w = Ei.weight(), :1065 */
+      for (uint64_t b = 0; b < wpr; ++b) w += (uint64_t)popc64(Ei[b]);
+      uint64_t bestk = 0, bestd = 0;                    /* :1067 */
+      for (uint64_t b = 0; b < wpr; ++b) bestd += (uint64_t)popc64(Ei[b] ^ D[b]);
+      for (uint64_t k = 1; k < p; ++k) {                /* :1071-1082 */
+        uint64_t dk = 0;
+        for (uint64_t b = 0; b < wpr; ++b) dk += (uint64_t)popc64(Ei[b] ^ D[k * wpr + b]);
+        if (dk < bestd) { bestd = dk; bestk = k; }      /* strict <: lowest k wins ties */
+      }
+      if (bestd < w) {                                  /* strict <, :1084 */
+        Ai[bestk >> 6] ^= BO_MSB >> (bestk & 63);       /* Ai.flip(0,bestk), :1086 */
+        for (uint64_t b = 0; b < wpr; ++b) Ei[b] ^= D[bestk * wpr + b]; /* :1087 */
+        ichanged = 1;
+      } else {
+        break;                                          /* :1090-1092 */
+      }
+    }
+    if (ichanged) changed++;                            /* :1095-1096 */
+  }
+  return changed;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * update_dictionary_steepest. src/bsvd.cpp:463-527. Atoms strictly in order; E is patched
+ * after each changed atom, so atom k+1 sees atom k's outcome.
+ * ------------------------------------------------------------------------------------------ */
+uint64_t bo_update_dictionary(bo_word* E, bo_word* D, const bo_word* A,
+                              uint64_t n, uint64_t m, uint64_t p) {
+  const uint64_t wpr = bo_wpr(m), apr = bo_wpr(p);
+  uint64_t* weights = (uint64_t*)malloc(sizeof(uint64_t) * (m ? m : 1));
+  bo_word* newDk = (bo_word*)malloc(sizeof(bo_word) * (wpr ? wpr : 1));
+  uint64_t changed = 0;
+  for (uint64_t k = 0; k < p; ++k) {
+    bo_word* Dk = D + k * wpr;
+    uint64_t usage = 0;
+    for (uint64_t j = 0; j < m; ++j) weights[j] = 0;
+    for (uint64_t i = 0; i < n; ++i) {                  /* :486-498 */
+      if (!get_bit(A + i * apr, k)) continue;
+      usage++;
+      for (uint64_t j = 0; j < m; ++j)                  /* bits of E[i] ^ Dk */
+        if (get_bit(E + i * wpr, j) ^ get_bit(Dk, j)) weights[j]++;
+    }
+    if (!usage) continue;                               /* :499-500 */
+    const uint64_t u = usage / 2;                       /* :502 */
+    memcpy(newDk, Dk, sizeof(bo_word) * wpr);           /* :503 */
+    for (uint64_t j = 0; j < m; ++j) put_bit(newDk, j, weights[j] > u); /* strict >, :504-506 */
+    uint64_t d = 0;
+    for (uint64_t b = 0; b < wpr; ++b) d += (uint64_t)popc64(newDk[b] ^ Dk[b]);
+    if (d > 0) {                                        /* :507 */
+      changed++;
+      for (uint64_t i = 0; i < n; ++i) {                /* :512-520 */
+        if (!get_bit(A + i * apr, k)) continue;
+        for (uint64_t b = 0; b < wpr; ++b) E[i * wpr + b] ^= Dk[b] ^ newDk[b];
+      }
+      memcpy(Dk, newDk, sizeof(bo_word) * wpr);         /* D.set_row(k,newDk), :510 */
+    }
+  }
+  free(weights);
+  free(newDk);
+  return changed;
+}
+
+/* mul_AB (src/binmat.cpp:516-543) then add (:463-478) */
+void bo_residual(const bo_word* X, const bo_word* A, const bo_word* D, bo_word* E,
+                 uint64_t n, uint64_t m, uint64_t p) {
+  const uint64_t wpr = bo_wpr(m), apr = bo_wpr(p);
+  for (uint64_t i = 0; i < n; ++i) {
+    bo_word* Ei = E + i * wpr;
+    for (uint64_t b = 0; b < wpr; ++b) Ei[b] = 0;
+    for (uint64_t k = 0; k < p; ++k)
+      if (get_bit(A + i * apr, k))
+        for (uint64_t b = 0; b < wpr; ++b) Ei[b] ^= D[k * wpr + b];
+    for (uint64_t b = 0; b < wpr; ++b) Ei[b] ^= X[i * wpr + b];
+  }
+}
+
+/* src/bsvd.cpp:1215-1244 */
+uint64_t bo_learn_traditional(const bo_word* X, bo_word* E, bo_word* D, bo_word* A,
+                              uint64_t n, uint64_t m, uint64_t p,
+                              uint64_t* trace, uint64_t trace_cap) {
+  bo_residual(X, A, D, E, n, m, p);                     /* :1219-1220 */
+  uint64_t changed = 1, iter = 0;
+  while (changed > 0) {                                 /* :1227 */
+    iter++;
+    const uint64_t cc = bo_update_coefficients(E, D, A, n, m, p); /* :1229 */
+    const uint64_t ca = bo_update_dictionary(E, D, A, n, m, p);   /* :1235 */
+    changed = cc + ca;
+    if (trace && iter <= trace_cap) { trace[2 * (iter - 1)] = cc; trace[2 * (iter - 1) + 1] = ca; }
+  }
+  return iter;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Bit I/O
+ * ------------------------------------------------------------------------------------------ */
+static void bw_put_bit(bo_bitwriter* bw, int bit) {
+  if (bw->nbits < bw->cap_bits) {
+    if (bit) bw->buf[bw->nbits >> 3] |= (uint8_t)(0x80u >> (bw->nbits & 7));
+  }
+  bw->nbits++;
+}
+static void bw_put_bits(bo_bitwriter* bw, uint32_t value, unsigned nbits) { /* writeBits(value, nbits): MSB of the field first */
+  for (unsigned i = nbits; i-- > 0;) bw_put_bit(bw, (int)((value >> i) & 1u));
+}
+static void bw_put_zeros(bo_bitwriter* bw, uint64_t n) { bw->nbits += n; } /* buffer is pre-zeroed */
+
+static int br_get_bit(bo_bitreader* br) {
+  int b = 0;
+  if (br->pos < br->nbits) b = (br->buf[br->pos >> 3] >> (7 - (br->pos & 7))) & 1;
+  br->pos++;
+  return b;
+}
+static uint32_t br_get_bits(bo_bitreader* br, unsigned nbits) {
+  uint32_t v = 0;
+  for (unsigned i = 0; i < nbits; ++i) v = (v << 1) | (uint32_t)br_get_bit(br);
+  return v;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Golomb. src/Golomb.h:12-29, src/GolombCoder.cpp:13-34, src/GolombDecoder.cpp:15-23.
+ * ------------------------------------------------------------------------------------------ */
+void bo_golomb_init(bo_golomb* g) { g->accumulatedError = 0; g->samples = 0; g->k = 1; g->bitcount = 0; } /* Golomb.h:14-19 */
+
+static void golomb_adapt(bo_golomb* g, uint32_t sample) {
+  g->samples++;                                         /* GolombCoder.cpp:31 */
+  g->accumulatedError += sample;                        /* :32, uint32 wrap-around */
+  uint32_t k;
+  /* :33  for(k=0; (samples<<k) < accumulatedError; k++);  in unsigned 32-bit arithmetic.
+   * k >= 32 would be an out-of-range shift there and trips the assert at :14 on the next
+   * sample; the search stops at 31 so the state stays inside the reference's domain. */
+  for (k = 0; k < 31 && (uint32_t)(g->samples << k) < g->accumulatedError; k++) {}
+  g->k = k;
+}
+
+void bo_golomb_code_sample(bo_golomb* g, bo_bitwriter* bw, uint32_t sample) {
+  const uint32_t k = g->k;
+  const uint32_t unary = sample >> k;                   /* GolombCoder.cpp:19 */
+  if (bw) {
+    const uint32_t binary = k ? (sample & (0xFFFFFFFFu >> (32 - k))) : 0u; /* :18 */
+    bw_put_bits(bw, binary, k);                         /* :22  file->writeBits(binary, k)   */
+    bw_put_zeros(bw, unary);                            /* :24  file->writeZeros(unary)      */
+    bw_put_bit(bw, 1);                                  /* :25  file->writeBits(1, 1)        */
+  }
+  g->bitcount += (int64_t)k + (int64_t)unary + 1;       /* :26 */
+  golomb_adapt(g, sample);
+}
+
+uint32_t bo_golomb_decode_sample(bo_golomb* g, bo_bitreader* br) {
+  const uint32_t k = g->k;
+  const uint32_t binary = br_get_bits(br, k);           /* GolombDecoder.cpp:17 readBits(k)   */
+  uint32_t unary = 0;                                   /* :18 countZeros()                   */
+  while (br->pos < br->nbits && !br_get_bit(br)) unary++; /* consumes the terminating one (:19) */
+  const uint32_t sample = (unary << k) | binary;        /* :21 */
+  g->bitcount += (int64_t)k + (int64_t)unary + 1;
+  golomb_adapt(g, sample);                              /* :36-37 */
+  return sample;
+}
+
+uint64_t bo_zero_runs(const bo_word* M, uint64_t rows, uint64_t cols, uint32_t* samples, uint64_t cap) {
+  const uint64_t wpr = bo_wpr(cols);
+  uint64_t count = 0, run = 0;
+  for (uint64_t i = 0; i < rows; ++i)
+    for (uint64_t j = 0; j < cols; ++j) {
+      if (get_bit(M + i * wpr, j)) {
+        if (samples && count < cap) samples[count] = (uint32_t)run;
+        count++;
+        run = 0;
+      } else {
+        run++;
+      }
+    }
+  if (samples && count < cap) samples[count] = (uint32_t)run; /* run closed by the virtual one */
+  count++;
+  return count;
+}
+
+uint64_t bo_golomb_encode_matrix(const bo_word* M, uint64_t rows, uint64_t cols,
+                                 uint8_t* out, uint64_t cap_bytes, uint64_t* nsamples) {
+  const uint64_t wpr = bo_wpr(cols);
+  bo_golomb g;
+  bo_golomb_init(&g);
+  bo_bitwriter bw = {out, cap_bytes * 8, 0};
+  if (out) memset(out, 0, cap_bytes);
+  uint64_t count = 0, run = 0;
+  for (uint64_t i = 0; i < rows; ++i)
+    for (uint64_t j = 0; j < cols; ++j) {
+      if (get_bit(M + i * wpr, j)) {
+        bo_golomb_code_sample(&g, out ? &bw : NULL, (uint32_t)run);
+        count++;
+        run = 0;
+      } else {
+        run++;
+      }
+    }
+  bo_golomb_code_sample(&g, out ? &bw : NULL, (uint32_t)run);
+  count++;
+  if (nsamples) *nsamples = count;
+  return (uint64_t)g.bitcount;
+}
+
+int bo_golomb_decode_matrix(const uint8_t* in, uint64_t nbits_in, uint64_t rows, uint64_t cols, bo_word* M) {
+  const uint64_t wpr = bo_wpr(cols), N = rows * cols;
+  memset(M, 0, sizeof(bo_word) * rows * wpr);
+  bo_golomb g;
+  bo_golomb_init(&g);
+  bo_bitreader br = {in, nbits_in, 0};
+  uint64_t pos = 0; /* next undecided bit of the row-major stream */
+  while (pos <= N) {
+    if (br.pos >= br.nbits) return -1;
+    const uint64_t x = bo_golomb_decode_sample(&g, &br);
+    pos += x;
+    if (pos > N) return -2;
+    if (pos == N) break; /* the virtual terminating one */
+    put_bit(M + (pos / cols) * wpr, pos % cols, 1);
+    pos++;
+  }
+  return br.pos == nbits_in ? 0 : -3;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * EG. src/eg.h:6-27, src/eg.cpp:2-37 (coder), :41-55 (decoder sketch, `#if 0` there).
+ * ------------------------------------------------------------------------------------------ */
+static const short BO_EGLUT[32] = {0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3,
+                                   4, 4, 5, 5, 6, 6, 7, 7, 8, 9, 10, 11, 12, 13, 14, 15}; /* eg.cpp:2 */
+
+void bo_eg_init(bo_eg* e) { e->g = 1; e->blockSize = 1; e->lutIndex = 0; e->bitcount = 0; } /* eg.h:9 */
+
+static void eg_dec_block(bo_eg* e) { /* eg.cpp:12-18 */
+  if (e->lutIndex > 0) e->lutIndex--;
+  e->g = (uint32_t)BO_EGLUT[e->lutIndex];
+  e->blockSize = 1u << e->g;
+}
+
+void bo_eg_code_run(bo_eg* e, bo_bitwriter* bw, int len, int eol) {
+  /* eg.cpp:22 compares int len with unsigned blockSize: len is converted to unsigned */
+  while ((unsigned)len >= e->blockSize) {               /* :22-27 (incBlockSize disabled, :25) */
+    len -= (int)e->blockSize;
+    if (bw) bw_put_bit(bw, 1);                          /* :24 */
+    e->bitcount++;
+  }
+  if (eol) {                                            /* :28-30 */
+    if (bw) bw_put_bit(bw, 1);
+    e->bitcount++;
+  } else {                                              /* :31-36 */
+    if (bw) { bw_put_bit(bw, 0); bw_put_bits(bw, (uint32_t)len, e->g); }
+    e->bitcount += e->g + 1;
+    eg_dec_block(e);
+  }
+}
+
+uint64_t bo_eg_encode_matrix(const bo_word* M, uint64_t rows, uint64_t cols, uint8_t* out, uint64_t cap_bytes) {
+  const uint64_t wpr = bo_wpr(cols);
+  bo_eg e;
+  bo_eg_init(&e);
+  bo_bitwriter bw = {out, cap_bytes * 8, 0};
+  if (out) memset(out, 0, cap_bytes);
+  for (uint64_t i = 0; i < rows; ++i) {
+    int run = 0;
+    for (uint64_t j = 0; j < cols; ++j) {
+      if (get_bit(M + i * wpr, j)) { bo_eg_code_run(&e, out ? &bw : NULL, run, 0); run = 0; }
+      else run++;
+    }
+    bo_eg_code_run(&e, out ? &bw : NULL, run, 1);
+  }
+  return e.bitcount;
+}
+
+int bo_eg_decode_matrix(const uint8_t* in, uint64_t nbits_in, uint64_t rows, uint64_t cols, bo_word* M) {
+  const uint64_t wpr = bo_wpr(cols);
+  memset(M, 0, sizeof(bo_word) * rows * wpr);
+  bo_eg e;
+  bo_eg_init(&e);
+  bo_bitreader br = {in, nbits_in, 0};
+  for (uint64_t i = 0; i < rows; ++i) {
+    uint64_t col = 0;
+    for (;;) {
+      const uint64_t maxlen = cols - col;
+      uint64_t len = 0;
+      int eol = 0;
+      /* eg.cpp:44-50: a one per full block; running past maxlen means the row ended */
+      while (br_get_bit(&br)) {
+        len += e.blockSize;
+        if (len > maxlen) { eol = 1; break; }
+        if (br.pos > br.nbits) return -1;
+      }
+      if (eol) break;
+      len += br_get_bits(&br, e.g);                     /* :52 */
+      eg_dec_block(&e);                                 /* :53 */
+      col += len;
+      if (col >= cols) return -2;
+      put_bit(M + i * wpr, col, 1);
+      col++;
+    }
+  }
+  return br.pos == nbits_in ? 0 : -3;
+}
