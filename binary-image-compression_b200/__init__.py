@@ -1,0 +1,390 @@
+"""binary-image-compression_b200: B200 (sm_100a) implementation of the encoder hot path of
+nacho-pancho/binary-image-compression -- bsvd fit (patch extraction, neighbour init, greedy
+coefficient update, ordered majority-vote dictionary update) + Golomb/EG coding.
+
+The product is the C-ABI shared library `libbic_b200.so` (CUDA kernels, include/bic_b200.h) and
+the C++ shim in host/ that keeps the reference's names. This Python module is only a ctypes
+binding over that C ABI for tests/, bench.py and __graft_entry__.py. There is no CPU fallback:
+loading fails loudly when the library is missing and every call fails when no GPU is present.
+
+The directory name has a hyphen, so import it with
+    importlib.import_module("binary-image-compression_b200")      (or `import bic_b200`)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from . import synth  # noqa: F401
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libbic_b200.so"
+
+BIC_OK = 0
+STATUS_NAMES = {0: "ok", 1: "invalid", 2: "cuda", 3: "nomem", 4: "capacity", 5: "no_device", 6: "corrupt", 7: "unsupported"}
+CODER_GOLOMB, CODER_EG = 1, 2
+
+_u64 = C.c_uint64
+_u64p = C.POINTER(C.c_uint64)
+_u8p = C.POINTER(C.c_uint8)
+_vp = C.c_void_p
+
+
+class BicError(RuntimeError):
+    def __init__(self, status, msg=""):
+        super().__init__(f"libbic_b200: {STATUS_NAMES.get(status, status)} {msg}")
+        self.status = status
+
+
+class StreamInfo(C.Structure):
+    _fields_ = [("coder", C.c_uint32), ("chunk_samples", C.c_uint32), ("rows", _u64), ("cols", _u64),
+                ("bitcount", _u64), ("nsamples", _u64), ("nchunks", _u64)]
+
+
+class EncodeInfo(C.Structure):
+    _fields_ = [(n, _u64) for n in ("rows", "cols", "W", "K", "n", "m", "iterations", "weight_E", "weight_A",
+                                    "weight_D", "bits_D", "bits_A", "bits_E", "container_bytes")]
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile libbic_b200.so in-tree with nvcc for sm_100a (no GPU needed)."""
+    r = subprocess.run(["make", "-C", str(PKG_DIR / "csrc"), "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libbic_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout[-2000:])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the C-ABI library. Raises if it has not been built -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
+                          "There is no CPU fallback for this path.")
+    L = C.CDLL(str(LIB_PATH))
+    sig = {
+        "bic_ctx_create": [C.c_int, C.POINTER(_vp)],
+        "bic_ctx_create_on_stream": [C.c_int, _vp, C.POINTER(_vp)],
+        "bic_ctx_destroy": [_vp],
+        "bic_ctx_sync": [_vp],
+        "bic_timer_start": [_vp],
+        "bic_timer_stop": [_vp, C.POINTER(C.c_float)],
+        "bic_host_alloc": [C.c_size_t, C.POINTER(_vp)],
+        "bic_host_free": [_vp],
+        "bic_mat_create": [_vp, _u64, _u64, C.POINTER(_vp)],
+        "bic_mat_destroy": [_vp, _vp],
+        "bic_mat_upload_words64": [_vp, _vp, _u64p],
+        "bic_mat_download_words64": [_vp, _vp, _u64p],
+        "bic_mat_upload_pbm": [_vp, _vp, _u8p],
+        "bic_mat_download_pbm": [_vp, _vp, _u8p],
+        "bic_mat_clear": [_vp, _vp],
+        "bic_mat_copy": [_vp, _vp, _vp],
+        "bic_mat_weight": [_vp, _vp, _u64p],
+        "bic_mat_dist": [_vp, _vp, _vp, _u64p],
+        "bic_mat_xor": [_vp, _vp, _vp, _vp],
+        "bic_extract_patches": [_vp, _vp, _u64, _vp],
+        "bic_assemble_patches": [_vp, _vp, _u64, _vp],
+        "bic_draw_pivots": [_vp, _vp, _u64, _u64p, _u64p, _u64p],
+        "bic_initialize_model_neighbor_pivots": [_vp, _vp, _u64p, _u64, _vp, _vp],
+        "bic_initialize_model_neighbor": [_vp, _vp, _vp, _vp, _u64p],
+        "bic_update_coefficients": [_vp, _vp, _vp, _vp, _u64p],
+        "bic_update_dictionary_steepest": [_vp, _vp, _vp, _vp, _u64p],
+        "bic_residual": [_vp, _vp, _vp, _vp, _vp],
+        "bic_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
+        "bic_stream_create": [_vp, C.POINTER(_vp)],
+        "bic_stream_destroy": [_vp, _vp],
+        "bic_stream_get_info": [_vp, C.POINTER(StreamInfo)],
+        "bic_stream_download": [_vp, _vp, _u8p, _u64, _u64p, _u64],
+        "bic_stream_upload": [_vp, _vp, C.POINTER(StreamInfo), _u8p, _u64p],
+        "bic_golomb_encode": [_vp, _vp, C.c_uint32, _vp],
+        "bic_golomb_bitcount": [_vp, _vp, _u64p, _u64p],
+        "bic_golomb_decode": [_vp, _vp, _vp],
+        "bic_eg_encode": [_vp, _vp, _vp],
+        "bic_eg_decode": [_vp, _vp, _vp],
+        "bic_encode_raster": [_vp, _u8p, _u64, _u64, _u64, _u64, C.c_ulong, _u8p, _u64, C.POINTER(EncodeInfo)],
+        "bic_decode_raster": [_vp, _u8p, _u64, _u8p, _u64, _u64p, _u64p],
+    }
+    for name, args in sig.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = C.c_int
+    L.bic_ctx_last_error.argtypes = [_vp]
+    L.bic_ctx_last_error.restype = C.c_char_p
+    L.bic_status_string.argtypes = [C.c_int]
+    L.bic_status_string.restype = C.c_char_p
+    L.bic_ctx_cuda_stream.argtypes = [_vp]
+    L.bic_ctx_cuda_stream.restype = _vp
+    L.bic_ctx_sm_count.argtypes = [_vp]
+    L.bic_ctx_sm_count.restype = C.c_int
+    L.bic_ctx_launch_count.argtypes = [_vp]
+    L.bic_ctx_launch_count.restype = _u64
+    for n in ("bic_mat_rows", "bic_mat_cols", "bic_mat_stride_words32"):
+        getattr(L, n).argtypes = [_vp]
+        getattr(L, n).restype = _u64
+    L.bic_mat_device_ptr.argtypes = [_vp]
+    L.bic_mat_device_ptr.restype = _vp
+    L.bic_rand48_seed.argtypes = [_u64p, C.c_ulong]
+    L.bic_rand48_seed.restype = None
+    L.bic_rand48_uniform_int.argtypes = [_u64p, _u64]
+    L.bic_rand48_uniform_int.restype = _u64
+    _lib = L
+    return L
+
+
+def exported_symbols_declared_in_header():
+    """names declared in include/bic_b200.h (used by the CPU test that checks the .so exports them)"""
+    import re
+    text = (PKG_DIR.parent / "include" / "bic_b200.h").read_text()
+    return sorted(set(re.findall(r"\b(bic_[a-z0-9_]+)\s*\(", text)))
+
+
+def _wpr64(cols):
+    return (cols + 63) // 64
+
+
+class Matrix:
+    """Device bit matrix handle (stands in for binary_matrix, src/binmat.h:29)."""
+
+    def __init__(self, ctx: "Context", rows: int, cols: int):
+        self.ctx, self.rows, self.cols = ctx, int(rows), int(cols)
+        h = _vp()
+        ctx._ck(ctx.L.bic_mat_create(ctx.h, self.rows, self.cols, C.byref(h)))
+        self.h = h
+
+    def upload(self, words64: np.ndarray) -> "Matrix":
+        w = np.ascontiguousarray(words64, np.uint64)
+        assert w.size == self.rows * _wpr64(self.cols), (w.shape, self.rows, self.cols)
+        self.ctx._ck(self.ctx.L.bic_mat_upload_words64(self.ctx.h, self.h, w.ctypes.data_as(_u64p)))
+        self.ctx.sync()  # w may be a temporary
+        return self
+
+    def download(self) -> np.ndarray:
+        out = np.zeros((self.rows, _wpr64(self.cols)), np.uint64)
+        self.ctx._ck(self.ctx.L.bic_mat_download_words64(self.ctx.h, self.h, out.ctypes.data_as(_u64p)))
+        return out
+
+    def upload_pbm(self, payload: np.ndarray) -> "Matrix":
+        b = np.ascontiguousarray(payload, np.uint8)
+        assert b.size == self.rows * ((self.cols + 7) // 8)
+        self.ctx._ck(self.ctx.L.bic_mat_upload_pbm(self.ctx.h, self.h, b.ctypes.data_as(_u8p)))
+        self.ctx.sync()
+        return self
+
+    def download_pbm(self) -> np.ndarray:
+        out = np.zeros((self.rows, (self.cols + 7) // 8), np.uint8)
+        self.ctx._ck(self.ctx.L.bic_mat_download_pbm(self.ctx.h, self.h, out.ctypes.data_as(_u8p)))
+        return out
+
+    def clear(self):
+        self.ctx._ck(self.ctx.L.bic_mat_clear(self.ctx.h, self.h))
+
+    def copy_from(self, other: "Matrix"):
+        self.ctx._ck(self.ctx.L.bic_mat_copy(self.ctx.h, other.h, self.h))
+
+    def weight(self) -> int:
+        w = _u64(0)
+        self.ctx._ck(self.ctx.L.bic_mat_weight(self.ctx.h, self.h, C.byref(w)))
+        return int(w.value)
+
+    def destroy(self):
+        if self.h:
+            self.ctx.L.bic_mat_destroy(self.ctx.h, self.h)
+            self.h = None
+
+
+class Stream:
+    def __init__(self, ctx: "Context"):
+        self.ctx = ctx
+        h = _vp()
+        ctx._ck(ctx.L.bic_stream_create(ctx.h, C.byref(h)))
+        self.h = h
+
+    @property
+    def info(self) -> StreamInfo:
+        si = StreamInfo()
+        self.ctx._ck(self.ctx.L.bic_stream_get_info(self.h, C.byref(si)))
+        return si
+
+    def download(self):
+        si = self.info
+        nb = (si.bitcount + 7) // 8
+        by = np.zeros(max(nb, 1), np.uint8)
+        idx = np.zeros(max(2 * si.nchunks, 2), np.uint64)
+        self.ctx._ck(self.ctx.L.bic_stream_download(self.ctx.h, self.h, by.ctypes.data_as(_u8p), by.size,
+                                                    idx.ctypes.data_as(_u64p), idx.size // 2))
+        return by[:nb], idx[: 2 * si.nchunks].reshape(-1, 2)
+
+    def upload(self, info: StreamInfo, by: np.ndarray, idx: np.ndarray):
+        by = np.ascontiguousarray(by, np.uint8)
+        idx = np.ascontiguousarray(idx, np.uint64)
+        self.ctx._ck(self.ctx.L.bic_stream_upload(self.ctx.h, self.h, C.byref(info), by.ctypes.data_as(_u8p),
+                                                  idx.ctypes.data_as(_u64p)))
+        self.ctx.sync()
+
+    def destroy(self):
+        if self.h:
+            self.ctx.L.bic_stream_destroy(self.ctx.h, self.h)
+            self.h = None
+
+
+class Context:
+    """One device context (one CUDA stream). Method names follow the reference's plug points."""
+
+    def __init__(self, device: int = 0, cuda_stream: int | None = None):
+        self.L = lib()
+        h = _vp()
+        if cuda_stream is None:
+            st = self.L.bic_ctx_create(device, C.byref(h))
+        else:
+            st = self.L.bic_ctx_create_on_stream(device, _vp(cuda_stream), C.byref(h))
+        if st != BIC_OK:
+            raise BicError(st, self.L.bic_status_string(st).decode())
+        self.h = h
+
+    def _ck(self, st):
+        if st != BIC_OK:
+            raise BicError(st, self.L.bic_ctx_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.bic_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        self._ck(self.L.bic_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.bic_ctx_launch_count(self.h))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.L.bic_ctx_sm_count(self.h))
+
+    def timer_start(self):
+        self._ck(self.L.bic_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        self._ck(self.L.bic_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    # ---- matrices
+    def matrix(self, rows, cols, words64=None) -> Matrix:
+        m = Matrix(self, rows, cols)
+        if words64 is not None:
+            m.upload(words64)
+        return m
+
+    def stream(self) -> Stream:
+        return Stream(self)
+
+    # ---- bsvd path (names as in src/bsvd.h / src/bsvd_test.cpp)
+    def extract_patches(self, raster: Matrix, W: int) -> Matrix:
+        n = ((raster.rows + W - 1) // W) * ((raster.cols + W - 1) // W)
+        X = Matrix(self, n, W * W)
+        self._ck(self.L.bic_extract_patches(self.h, raster.h, W, X.h))
+        return X
+
+    def assemble_patches(self, X: Matrix, W: int, rows: int, cols: int) -> Matrix:
+        R = Matrix(self, rows, cols)
+        self._ck(self.L.bic_assemble_patches(self.h, X.h, W, R.h))
+        return R
+
+    def rand48(self, seed: int):
+        s = _u64(0)
+        self.L.bic_rand48_seed(C.byref(s), seed)
+        return s
+
+    def draw_pivots(self, X: Matrix, p: int, rng_state) -> tuple[np.ndarray, int]:
+        piv = np.zeros(max(p, 1), np.uint64)
+        nd = _u64(0)
+        self._ck(self.L.bic_draw_pivots(self.h, X.h, p, C.byref(rng_state), piv.ctypes.data_as(_u64p), C.byref(nd)))
+        return piv[:p], int(nd.value)
+
+    def initialize_model_neighbor_pivots(self, X: Matrix, pivots, D: Matrix, A: Matrix):
+        piv = np.ascontiguousarray(pivots, np.uint64)
+        self._ck(self.L.bic_initialize_model_neighbor_pivots(self.h, X.h, piv.ctypes.data_as(_u64p), piv.size, D.h, A.h))
+        self.sync()
+
+    def initialize_model_neighbor(self, X: Matrix, D: Matrix, A: Matrix, rng_state):
+        self._ck(self.L.bic_initialize_model_neighbor(self.h, X.h, D.h, A.h, C.byref(rng_state)))
+
+    def update_coefficients(self, E: Matrix, D: Matrix, A: Matrix) -> int:
+        ch = _u64(0)
+        self._ck(self.L.bic_update_coefficients(self.h, E.h, D.h, A.h, C.byref(ch)))
+        return int(ch.value)
+
+    def update_dictionary(self, E: Matrix, D: Matrix, A: Matrix) -> int:
+        ch = _u64(0)
+        self._ck(self.L.bic_update_dictionary_steepest(self.h, E.h, D.h, A.h, C.byref(ch)))
+        return int(ch.value)
+
+    def residual(self, X: Matrix, A: Matrix, D: Matrix, E: Matrix):
+        self._ck(self.L.bic_residual(self.h, X.h, A.h, D.h, E.h))
+
+    def learn_model_traditional(self, X: Matrix, E: Matrix, D: Matrix, A: Matrix, trace_cap: int = 256):
+        it = _u64(0)
+        tr = np.zeros(2 * trace_cap, np.uint64)
+        self._ck(self.L.bic_learn_model_traditional(self.h, X.h, E.h, D.h, A.h, C.byref(it),
+                                                    tr.ctypes.data_as(_u64p), trace_cap))
+        n = int(it.value)
+        return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
+
+    # ---- coding
+    def golomb_encode(self, M: Matrix, out: Stream | None = None, chunk_samples: int = 256) -> Stream:
+        out = out or Stream(self)
+        self._ck(self.L.bic_golomb_encode(self.h, M.h, chunk_samples, out.h))
+        return out
+
+    def golomb_bitcount(self, M: Matrix):
+        b, s = _u64(0), _u64(0)
+        self._ck(self.L.bic_golomb_bitcount(self.h, M.h, C.byref(b), C.byref(s)))
+        return int(b.value), int(s.value)
+
+    def golomb_decode(self, s: Stream, M: Matrix):
+        self._ck(self.L.bic_golomb_decode(self.h, s.h, M.h))
+
+    def eg_encode(self, M: Matrix, out: Stream | None = None) -> Stream:
+        out = out or Stream(self)
+        self._ck(self.L.bic_eg_encode(self.h, M.h, out.h))
+        return out
+
+    def eg_decode(self, s: Stream, M: Matrix):
+        self._ck(self.L.bic_eg_decode(self.h, s.h, M.h))
+
+    # ---- whole encoder
+    def encode_raster(self, payload: np.ndarray, rows: int, cols: int, W: int, K: int, seed: int = 34503498,
+                      out: np.ndarray | None = None):
+        """payload: P4 rows (uint8). Returns (container bytes ndarray, EncodeInfo)."""
+        b = np.ascontiguousarray(payload, np.uint8)
+        info = EncodeInfo()
+        if out is None:
+            out = np.zeros(max(64 * 1024, 2 * b.size + 64 * 1024), np.uint8)
+        st = self.L.bic_encode_raster(self.h, b.ctypes.data_as(_u8p), rows, cols, W, K, seed,
+                                      out.ctypes.data_as(_u8p), out.size, C.byref(info))
+        if st == 4:  # capacity: retry once with the size the library reported
+            out = np.zeros(int(info.container_bytes) + 64, np.uint8)
+            st = self.L.bic_encode_raster(self.h, b.ctypes.data_as(_u8p), rows, cols, W, K, seed,
+                                          out.ctypes.data_as(_u8p), out.size, C.byref(info))
+        self._ck(st)
+        return out[: int(info.container_bytes)], info
+
+    def decode_raster(self, container: np.ndarray):
+        cbuf = np.ascontiguousarray(container, np.uint8)
+        r, c_ = _u64(0), _u64(0)
+        self._ck(self.L.bic_decode_raster(self.h, cbuf.ctypes.data_as(_u8p), cbuf.size, None, 0, C.byref(r), C.byref(c_)))
+        rows, cols = int(r.value), int(c_.value)
+        out = np.zeros((rows, (cols + 7) // 8), np.uint8)
+        self._ck(self.L.bic_decode_raster(self.h, cbuf.ctypes.data_as(_u8p), cbuf.size, out.ctypes.data_as(_u8p),
+                                          out.size, C.byref(r), C.byref(c_)))
+        return out, rows, cols

@@ -1,0 +1,125 @@
+// Internal declarations shared by the translation units of libbic_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "bic_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// Device layout of a bit matrix: uint32 words, MSB first (bit j of a row is bit 31-(j&31) of
+// word j>>5), stride = ceil(cols/32) words, pad bits zero. The allocation is rounded up to a
+// multiple of 256 B and zero filled so 128-bit loads may run past the last row harmlessly.
+// ---------------------------------------------------------------------------------------------
+struct bic_mat {
+  uint64_t rows = 0, cols = 0;
+  uint64_t wpr = 0;         // 32-bit words per row
+  uint32_t* d = nullptr;    // device words
+  size_t alloc_bytes = 0;
+  bool owns = true;
+  uint64_t words() const { return rows * wpr; }
+};
+
+struct bic_scratch {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct bic_stream {
+  bic_stream_info info{};
+  uint8_t* d_bytes = nullptr;   // device byte stream
+  size_t cap_bytes = 0;
+  uint64_t* d_index = nullptr;  // 2 * nchunks
+  size_t cap_index = 0;         // in uint64 entries
+};
+
+struct bic_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  uint64_t launches = 0;
+  std::string err;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // pinned host scalars for results read back after a kernel
+  uint64_t* h_scalars = nullptr;  // 64 entries
+  uint64_t* d_scalars = nullptr;  // 64 entries
+  // grow-only scratch areas
+  bic_scratch staging;    // host-layout staging for uploads/downloads
+  bic_scratch work[6];    // per-algorithm work buffers
+};
+
+#define BIC_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                   \
+      return BIC_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define BIC_TRY(expr)                 \
+  do {                                \
+    bic_status _s = (expr);           \
+    if (_s != BIC_OK) return _s;      \
+  } while (0)
+
+#define BIC_LAUNCH_CHECK(ctx)                                   \
+  do {                                                          \
+    (ctx)->launches++;                                          \
+    BIC_CUDA(ctx, cudaGetLastError());                          \
+  } while (0)
+
+static inline bic_status bic_fail(bic_ctx* ctx, bic_status s, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return s;
+}
+
+// grow-only scratch; contents are undefined after growth
+bic_status bic_scratch_reserve(bic_ctx* ctx, bic_scratch* s, size_t bytes);
+// D2H of the first n scalar slots after the stream drained
+bic_status bic_read_scalars(bic_ctx* ctx, int n);
+bic_status bic_zero_scalars(bic_ctx* ctx);
+
+#ifdef __CUDACC__
+#define BIC_HD __host__ __device__
+#else
+#define BIC_HD
+#endif
+BIC_HD static inline uint64_t div_up_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// persistent-grid sizing: a multiple of the SM count
+static inline int bic_grid_for(const bic_ctx* ctx, uint64_t work_items, int per_block, int blocks_per_sm) {
+  uint64_t need = div_up_u64(work_items ? work_items : 1, (uint64_t)per_block);
+  uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)blocks_per_sm;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---- cross-TU entry points (implemented next to their kernels) -------------------------------
+bic_status bic_k_row_nonzero_bitmap(bic_ctx* ctx, const bic_mat* X, uint32_t* d_bitmap);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// mask of the valid bits of the last word of a row with `cols` columns
+__host__ __device__ __forceinline__ uint32_t tail_mask32(uint64_t cols) {
+  const unsigned r = (unsigned)(cols & 31);
+  return r ? (0xFFFFFFFFu << (32 - r)) : 0xFFFFFFFFu;
+}
+#endif

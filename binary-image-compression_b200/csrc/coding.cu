@@ -1,0 +1,687 @@
+// Parallel Golomb / EG coding of a bit matrix and the chunk-parallel decoders.
+// Reference semantics: Golomb state src/Golomb.h:12-29; GolombCoder::codeSample
+// src/GolombCoder.cpp:13-34 (bit layout from its commented writer calls :22-25 and from
+// GolombDecoder::binaryDecode src/GolombDecoder.cpp:15-23); EGCoder::codeRun src/eg.cpp:20-37.
+//
+// Golomb. The samples are the zero-run lengths of the matrix read row-major; a virtual one after
+// the last bit closes the last run, so there are popcount+1 samples. With pos_t the stream
+// position of the t-th one, sample x_t = pos_t - pos_{t-1} - 1 and the coder state before sample
+// t is a closed form of (t, pos_{t-1}): samples = t, accumulatedError = pos_{t-1} + 1 - t
+// (mod 2^32), k_t = min{k : (t << k) >= accumulatedError} (k_0 = 1). So the serial adaptive coder
+// becomes: rank of every one (prefix sum of word popcounts) + position of the previous one
+// (prefix max) -> k_t and codeword length per one -> prefix sum of lengths = bit offsets ->
+// scatter of the k remainder bits and the closing one of each codeword into a zeroed buffer.
+#include "bic_internal.cuh"
+
+#define TILE_THREADS 256
+#define TILE_WORDS_PER_THREAD 4
+#define TILE_WORDS (TILE_THREADS * TILE_WORDS_PER_THREAD)
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+// k after t samples whose sum is acc (uint32 arithmetic, GolombCoder.cpp:33; the search is
+// capped at 31 because k >= 32 trips the reference's own assert, GolombCoder.cpp:14)
+__device__ __forceinline__ uint32_t golomb_k(uint64_t t64, uint64_t bits_consumed) {
+  if (t64 == 0) return 1;  // Golomb.h:18
+  const uint32_t t = (uint32_t)t64;
+  const uint32_t acc = (uint32_t)(bits_consumed - t64);  // sum of the first t samples, mod 2^32
+  if (acc <= t) return 0;
+  if (acc < 0x80000000u && t != 0) {
+    // no shift below the answer can wrap: t << k has the bit length of acc
+    int k = __clz(t) - __clz(acc);
+    if ((t << k) < acc) k++;
+    return (uint32_t)k;
+  }
+  uint32_t k = 0;
+  while (k < 31 && (uint32_t)(t << k) < acc) k++;
+  return k;
+}
+
+__device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long* total,
+                                                                  unsigned long long* s_warp /* 8 */) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[wib] = inc;
+  __syncthreads();
+  unsigned long long base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < TILE_THREADS / 32; ++w) {
+    const unsigned long long x = s_warp[w];
+    if (w < wib) base += x;
+    tot += x;
+  }
+  if (total) *total = tot;
+  return base + inc - v;
+}
+
+// exclusive prefix max of "position of my last one" (-1 = none)
+__device__ __forceinline__ long long block_excl_scan_max(long long v, long long* total, long long* s_warp /* 8 */) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = inc > y ? inc : y;
+  }
+  long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) excl = -1;
+  __syncthreads();
+  if (lane == 31) s_warp[wib] = inc;
+  __syncthreads();
+  long long base = -1, tot = -1;
+#pragma unroll
+  for (int w = 0; w < TILE_THREADS / 32; ++w) {
+    const long long x = s_warp[w];
+    if (w < wib) base = base > x ? base : x;
+    tot = tot > x ? tot : x;
+  }
+  if (total) *total = tot;
+  return base > excl ? base : excl;
+}
+
+// ------------------------------------------------------------------ dense row-major bit stream
+// When cols is not a multiple of 32 the rows carry pad bits; the coders work on a compacted copy.
+__global__ void k_compact_rows(const uint32_t* __restrict__ M, uint64_t cols, uint64_t wpr, uint64_t N,
+                               uint32_t* __restrict__ S, uint64_t T) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t s = t * 32;
+    const uint64_t send = (s + 32 < N) ? s + 32 : N;
+    uint32_t out = 0;
+    unsigned filled = 0;
+    while (s < send) {
+      const uint64_t r = s / cols, cc = s - r * cols;
+      uint64_t len = cols - cc;
+      if (len > send - s) len = send - s;
+      const uint64_t wi = cc >> 5;
+      const unsigned off = (unsigned)(cc & 31);
+      const uint32_t* row = M + r * wpr;
+      const uint32_t hi = row[wi];
+      const uint32_t lo = (off + len > 32 && wi + 1 < wpr) ? row[wi + 1] : 0u;
+      const uint32_t v = __funnelshift_l(lo, hi, off) >> (32 - (unsigned)len);
+      out |= v << (32 - filled - (unsigned)len);
+      filled += (unsigned)len;
+      s += len;
+    }
+    S[t] = out;
+  }
+}
+
+__global__ void k_expand_rows(const uint32_t* __restrict__ S, uint64_t cols, uint64_t wpr, uint64_t rows,
+                              uint32_t* __restrict__ M) {
+  const uint64_t total = rows * wpr;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = i / wpr, w = i - r * wpr;
+    const uint64_t c0 = w * 32;
+    const unsigned len = (unsigned)((cols - c0 < 32) ? cols - c0 : 32);
+    const uint64_t s = r * cols + c0;
+    const uint64_t wi = s >> 5;
+    const unsigned off = (unsigned)(s & 31);
+    const uint32_t hi = S[wi];
+    const uint32_t lo = (off + len > 32) ? S[wi + 1] : 0u;
+    M[i] = (__funnelshift_l(lo, hi, off) >> (32 - len)) << (32 - len);
+  }
+}
+
+// ------------------------------------------------------------------ Golomb encoder
+struct GolTile {           // per 1024-word tile
+  uint32_t* ones;          // ones in the tile
+  long long* last;         // stream position of the tile's last one, -1 if none
+  unsigned long long* ones_before;  // exclusive prefix of ones
+  long long* last_before;  // last one before the tile, -1 if none
+  unsigned long long* bits;         // code bits produced by the tile's ones
+  unsigned long long* bits_before;  // exclusive prefix
+};
+
+__device__ __forceinline__ void load_tile_words(const uint32_t* __restrict__ S, uint64_t T, uint64_t w0, uint32_t (&v)[4]) {
+  if (w0 + 4 <= T) {
+    const uint4 q = *reinterpret_cast<const uint4*>(S + w0);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (w0 + i < T) ? S[w0 + i] : 0u;
+  }
+}
+
+__global__ void __launch_bounds__(TILE_THREADS) k_gol_tile_counts(const uint32_t* __restrict__ S, uint64_t T, GolTile g) {
+  __shared__ unsigned long long s_a[8];
+  __shared__ long long s_b[8];
+  const uint64_t w0 = (uint64_t)blockIdx.x * TILE_WORDS + threadIdx.x * TILE_WORDS_PER_THREAD;
+  uint32_t v[4];
+  load_tile_words(S, T, w0, v);
+  unsigned long long c = 0;
+  long long last = -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    c += __popc(v[i]);
+    if (v[i]) last = (long long)((w0 + i) * 32 + (32 - __ffs(v[i])));
+  }
+  unsigned long long tot;
+  long long tlast;
+  block_excl_scan_u64(c, &tot, s_a);
+  block_excl_scan_max(last, &tlast, s_b);
+  if (threadIdx.x == 0) { g.ones[blockIdx.x] = (uint32_t)tot; g.last[blockIdx.x] = tlast; }
+}
+
+// single CTA: exclusive scans over the tiles
+__global__ void __launch_bounds__(TILE_THREADS) k_gol_scan_tiles_a(GolTile g, uint64_t ntiles) {
+  __shared__ unsigned long long s_a[8];
+  __shared__ long long s_b[8];
+  unsigned long long carry = 0;
+  long long carry_last = -1;
+  for (uint64_t base = 0; base < ntiles; base += TILE_THREADS) {
+    const uint64_t i = base + threadIdx.x;
+    const unsigned long long c = (i < ntiles) ? g.ones[i] : 0ull;
+    const long long l = (i < ntiles) ? g.last[i] : -1;
+    unsigned long long tot;
+    long long tlast;
+    const unsigned long long ex = block_excl_scan_u64(c, &tot, s_a);
+    const long long exl = block_excl_scan_max(l, &tlast, s_b);
+    if (i < ntiles) {
+      g.ones_before[i] = carry + ex;
+      g.last_before[i] = carry_last > exl ? carry_last : exl;
+    }
+    carry += tot;
+    carry_last = carry_last > tlast ? carry_last : tlast;
+    __syncthreads();
+  }
+}
+
+// scalars: [0] bitcount, [1] nsamples, [2] offset of the closing sample, [3] last one + 1
+__global__ void __launch_bounds__(TILE_THREADS) k_gol_scan_tiles_b(GolTile g, uint64_t ntiles, uint64_t N,
+                                                                   unsigned long long* scalars) {
+  __shared__ unsigned long long s_a[8];
+  unsigned long long carry = 0;
+  for (uint64_t base = 0; base < ntiles; base += TILE_THREADS) {
+    const uint64_t i = base + threadIdx.x;
+    const unsigned long long c = (i < ntiles) ? g.bits[i] : 0ull;
+    unsigned long long tot;
+    const unsigned long long ex = block_excl_scan_u64(c, &tot, s_a);
+    if (i < ntiles) g.bits_before[i] = carry + ex;
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long ones = 0;
+    long long last = -1;
+    if (ntiles) {
+      ones = g.ones_before[ntiles - 1] + g.ones[ntiles - 1];
+      last = g.last_before[ntiles - 1] > g.last[ntiles - 1] ? g.last_before[ntiles - 1] : g.last[ntiles - 1];
+    }
+    // the run closed by the virtual one at position N
+    const unsigned long long consumed = (unsigned long long)(last + 1);
+    const unsigned long long x = N - consumed;
+    const uint32_t k = golomb_k(ones, consumed);
+    scalars[0] = carry + k + (x >> k) + 1;
+    scalars[1] = ones + 1;
+    scalars[2] = carry;
+    scalars[3] = consumed;
+  }
+}
+
+__device__ __forceinline__ void put_bits(uint32_t* __restrict__ out, unsigned long long o, uint32_t value, uint32_t nb) {
+  if (nb == 0 || value == 0) return;
+  const unsigned long long wi = o >> 5;
+  const unsigned off = (unsigned)(o & 31);
+  const unsigned long long v64 = (unsigned long long)value << (64 - off - nb);
+  const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
+  if (hi) atomicOr(out + wi, bswap32(hi));
+  if (lo) atomicOr(out + wi + 1, bswap32(lo));
+}
+__device__ __forceinline__ void put_one(uint32_t* __restrict__ out, unsigned long long o) {
+  atomicOr(out + (o >> 5), bswap32(0x80000000u >> (unsigned)(o & 31)));
+}
+
+// MODE 0: code lengths per tile; MODE 1: scatter codewords (+ chunk index)
+template <int MODE>
+__global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __restrict__ S, uint64_t T, uint64_t N, GolTile g,
+                                                           uint32_t* __restrict__ out, unsigned long long* __restrict__ index,
+                                                           uint32_t chunk, const unsigned long long* __restrict__ scalars) {
+  __shared__ unsigned long long s_a[8];
+  __shared__ long long s_b[8];
+  const uint64_t w0 = (uint64_t)blockIdx.x * TILE_WORDS + threadIdx.x * TILE_WORDS_PER_THREAD;
+  uint32_t v[4];
+  load_tile_words(S, T, w0, v);
+  unsigned long long c = 0;
+  long long last = -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    c += __popc(v[i]);
+    if (v[i]) last = (long long)((w0 + i) * 32 + (32 - __ffs(v[i])));
+  }
+  const unsigned long long rank0 = g.ones_before[blockIdx.x] + block_excl_scan_u64(c, nullptr, s_a);
+  const long long pl = block_excl_scan_max(last, nullptr, s_b);
+  const long long lb = g.last_before[blockIdx.x];
+  long long prev = pl > lb ? pl : lb;  // position of the previous one, -1 if none
+
+  // pass 1: my code bits
+  unsigned long long mybits = 0;
+  {
+    unsigned long long t = rank0;
+    long long pv = prev;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t b = v[i];
+      while (b) {
+        const int p = __clz(b);
+        b &= ~(0x80000000u >> p);
+        const long long pos = (long long)((w0 + i) * 32 + p);
+        const unsigned long long x = (unsigned long long)(pos - pv - 1);
+        const uint32_t k = golomb_k(t, (unsigned long long)(pv + 1));
+        mybits += k + (x >> k) + 1;
+        pv = pos;
+        ++t;
+      }
+    }
+  }
+  unsigned long long tot;
+  const unsigned long long ex = block_excl_scan_u64(mybits, &tot, s_a);
+  if (MODE == 0) {
+    if (threadIdx.x == 0) g.bits[blockIdx.x] = tot;
+    return;
+  }
+  // pass 2: scatter
+  unsigned long long o = g.bits_before[blockIdx.x] + ex;
+  unsigned long long t = rank0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t b = v[i];
+    while (b) {
+      const int p = __clz(b);
+      b &= ~(0x80000000u >> p);
+      const long long pos = (long long)((w0 + i) * 32 + p);
+      const unsigned long long x = (unsigned long long)(pos - prev - 1);
+      const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+      if (t % chunk == 0) { index[2 * (t / chunk)] = o; index[2 * (t / chunk) + 1] = (unsigned long long)(prev + 1); }
+      put_bits(out, o, (uint32_t)(x & ((1ull << k) - 1)), k);  // k-bit remainder, MSB first
+      o += k + (x >> k);                                       // x>>k zeros (the buffer is zeroed)
+      put_one(out, o);                                         // closing one
+      o += 1;
+      prev = pos;
+      ++t;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // the run closed by the virtual one
+    const unsigned long long tt = scalars[1] - 1, consumed = scalars[3];
+    unsigned long long oo = scalars[2];
+    const unsigned long long x = N - consumed;
+    const uint32_t k = golomb_k(tt, consumed);
+    if (tt % chunk == 0) { index[2 * (tt / chunk)] = oo; index[2 * (tt / chunk) + 1] = consumed; }
+    put_bits(out, oo, (uint32_t)(x & ((1ull << k) - 1)), k);
+    oo += k + (x >> k);
+    put_one(out, oo);
+  }
+}
+
+// ------------------------------------------------------------------ Golomb decoder: a thread per chunk
+__device__ __forceinline__ uint32_t peek32(const uint32_t* __restrict__ in, unsigned long long o) {
+  const unsigned long long wi = o >> 5;
+  const unsigned off = (unsigned)(o & 31);
+  const uint32_t a = bswap32(__ldg(in + wi)), b = bswap32(__ldg(in + wi + 1));
+  return __funnelshift_l(b, a, off);
+}
+
+__global__ void k_gol_decode(const uint32_t* __restrict__ in, unsigned long long bitcount,
+                             const unsigned long long* __restrict__ index, uint64_t nchunks, uint32_t chunk,
+                             uint64_t nsamples, uint64_t N, uint32_t* __restrict__ S, unsigned long long* __restrict__ err) {
+  for (uint64_t ch = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; ch < nchunks; ch += (uint64_t)gridDim.x * blockDim.x) {
+    unsigned long long o = index[2 * ch], pos = index[2 * ch + 1];
+    unsigned long long t = ch * chunk;
+    const unsigned long long tend = (t + chunk < nsamples) ? t + chunk : nsamples;
+    bool bad = (o > bitcount) || (pos > N);
+    for (; t < tend && !bad; ++t) {
+      const uint32_t k = golomb_k(t, pos);
+      const uint32_t rem = k ? (peek32(in, o) >> (32 - k)) : 0u;  // readBits(k), GolombDecoder.cpp:17
+      o += k;
+      unsigned long long unary = 0;                               // countZeros(), :18
+      for (;;) {
+        if (o >= bitcount) { bad = true; break; }
+        const uint32_t w = peek32(in, o);
+        if (w == 0) { unary += 32; o += 32; continue; }
+        const int z = __clz(w);
+        unary += z;
+        o += z + 1;                                               // the closing one, :19
+        break;
+      }
+      if (bad) break;
+      pos += (unary << k) | rem;                                  // :21
+      if (pos < N) {
+        atomicOr(S + (pos >> 5), 0x80000000u >> (unsigned)(pos & 31));
+        pos++;
+      } else if (pos > N || t + 1 != nsamples) {
+        bad = true;
+      }
+    }
+    if (!bad && tend == nsamples && pos != N) bad = true;  // the closing run must end exactly at N
+    if (bad) atomicAdd(err, 1ull);
+  }
+}
+
+// ------------------------------------------------------------------ EG
+// codeRun (eg.cpp:20-37) with the coder's block growth disabled (:25) keeps blockSize = 1, and g
+// drops from 1 to 0 after the first run that ends in a one. The stream is therefore: a one per
+// zero of the input, a zero per one of the input, a one at every end of row, and a single extra
+// zero (the one-bit remainder, g = 1) right after the first input one's zero.
+__global__ void k_first_one(const uint32_t* __restrict__ S, uint64_t T, unsigned long long* __restrict__ first) {
+  unsigned long long best = ~0ull;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = S[t];
+    if (v) { const unsigned long long p = t * 32 + __clz(v); best = p < best ? p : best; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
+    best = y < best ? y : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(first, best);
+}
+
+__global__ void k_fill_ones(uint32_t* __restrict__ out, unsigned long long nbits) {
+  const unsigned long long nw = (nbits + 31) >> 5;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nw;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    uint32_t v = 0xFFFFFFFFu;
+    if (i == nw - 1 && (nbits & 31)) v <<= (32 - (unsigned)(nbits & 31));
+    out[i] = bswap32(v);
+  }
+}
+
+__global__ void k_eg_encode(const uint32_t* __restrict__ S, uint64_t T, uint64_t cols, const unsigned long long* __restrict__ first,
+                            uint32_t* __restrict__ out) {
+  const unsigned long long f = *first;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t b = S[t];
+    while (b) {
+      const int p = __clz(b);
+      b &= ~(0x80000000u >> p);
+      const unsigned long long s = t * 32 + p;
+      const unsigned long long o = s + s / cols + (s > f ? 1 : 0);
+      atomicAnd(out + (o >> 5), ~bswap32(0x80000000u >> (unsigned)(o & 31)));
+      if (s == f) atomicAnd(out + ((o + 1) >> 5), ~bswap32(0x80000000u >> (unsigned)((o + 1) & 31)));
+    }
+  }
+}
+
+// first zero of the code = the first input one's terminator
+__global__ void k_first_zero(const uint32_t* __restrict__ in, unsigned long long nbits, unsigned long long* __restrict__ first) {
+  const unsigned long long nw = (nbits + 31) >> 5;
+  unsigned long long best = ~0ull;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nw;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t v = ~bswap32(in[i]);
+    if (v) { const unsigned long long p = i * 32 + __clz(v); if (p < nbits && p < best) best = p; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
+    best = y < best ? y : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(first, best);
+}
+
+__global__ void k_eg_decode(const uint32_t* __restrict__ in, uint64_t rows, uint64_t cols, uint64_t wpr,
+                            const unsigned long long* __restrict__ first_zero, uint32_t* __restrict__ M) {
+  const unsigned long long z = *first_zero;  // code position; ~0 if the matrix is all zero
+  const uint64_t total = rows * wpr;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = i / wpr, w = i - r * wpr;
+    uint32_t v = 0;
+    for (int b = 0; b < 32; ++b) {
+      const uint64_t cc = w * 32 + b;
+      if (cc >= cols) break;
+      unsigned long long o = r * (cols + 1) + cc;  // position without the extra bit
+      if (o > z) o += 1;
+      const uint32_t word = bswap32(__ldg(in + (o >> 5)));
+      if (!((word >> (31 - (unsigned)(o & 31))) & 1u)) v |= 0x80000000u >> b;
+    }
+    M[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+extern "C" bic_status bic_stream_create(bic_ctx* c, bic_stream** out) {
+  if (!c || !out) return BIC_ERR_INVALID;
+  *out = new (std::nothrow) bic_stream();
+  return *out ? BIC_OK : BIC_ERR_NOMEM;
+}
+
+extern "C" bic_status bic_stream_destroy(bic_ctx* c, bic_stream* s) {
+  if (!c || !s) return BIC_ERR_INVALID;
+  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (s->d_bytes) cudaFree(s->d_bytes);
+  if (s->d_index) cudaFree(s->d_index);
+  delete s;
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_stream_get_info(const bic_stream* s, bic_stream_info* info) {
+  if (!s || !info) return BIC_ERR_INVALID;
+  *info = s->info;
+  return BIC_OK;
+}
+
+static bic_status stream_reserve(bic_ctx* c, bic_stream* s, uint64_t bitcount, uint64_t nchunks) {
+  // whole 32-bit words plus slack so peek32 / put_bits may touch one word past the end
+  const size_t need = (size_t)(div_up_u64(bitcount, 32) * 4 + 16);
+  if (need > s->cap_bytes) {
+    BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (s->d_bytes) cudaFree(s->d_bytes);
+    s->d_bytes = nullptr; s->cap_bytes = 0;
+    const size_t want = (need + (need >> 3) + 255) & ~(size_t)255;
+    if (cudaMalloc(&s->d_bytes, want) != cudaSuccess) { cudaGetLastError(); c->err = "stream allocation failed"; return BIC_ERR_NOMEM; }
+    s->cap_bytes = want;
+  }
+  const size_t needi = (size_t)(nchunks ? nchunks : 1) * 2;
+  if (needi > s->cap_index) {
+    BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (s->d_index) cudaFree(s->d_index);
+    s->d_index = nullptr; s->cap_index = 0;
+    if (cudaMalloc(&s->d_index, needi * 8) != cudaSuccess) { cudaGetLastError(); c->err = "index allocation failed"; return BIC_ERR_NOMEM; }
+    s->cap_index = needi;
+  }
+  return BIC_OK;
+}
+
+// dense stream view of a matrix: the matrix itself when cols % 32 == 0, else a compacted copy
+static bic_status dense_stream(bic_ctx* c, const bic_mat* M, const uint32_t** S, uint64_t* T) {
+  const uint64_t N = M->rows * M->cols;
+  *T = div_up_u64(N, 32);
+  if ((M->cols & 31) == 0) { *S = M->d; return BIC_OK; }
+  BIC_TRY(bic_scratch_reserve(c, &c->work[4], (size_t)(*T) * 4 + 16));
+  if (*T) {
+    k_compact_rows<<<bic_grid_for(c, *T, 256, 8), 256, 0, c->stream>>>(M->d, M->cols, M->wpr, N, (uint32_t*)c->work[4].p, *T);
+    BIC_LAUNCH_CHECK(c);
+  }
+  *S = (const uint32_t*)c->work[4].p;
+  return BIC_OK;
+}
+
+static bic_status golomb_prepare(bic_ctx* c, const bic_mat* M, const uint32_t** S_out, uint64_t* T_out, GolTile* g,
+                                 uint64_t* ntiles_out) {
+  const uint64_t N = M->rows * M->cols;
+  const uint32_t* S;
+  uint64_t T;
+  BIC_TRY(dense_stream(c, M, &S, &T));
+  const uint64_t ntiles = div_up_u64(T, TILE_WORDS);
+  // work[5]: per-tile arrays
+  const size_t per = (size_t)(ntiles ? ntiles : 1);
+  const size_t bytes = per * (8 * 5 + 8);  // ones kept in a u64 slot for alignment
+  BIC_TRY(bic_scratch_reserve(c, &c->work[5], bytes));
+  uint8_t* base = (uint8_t*)c->work[5].p;
+  g->last = (long long*)base;
+  g->ones_before = (unsigned long long*)(base + per * 8);
+  g->last_before = (long long*)(base + per * 16);
+  g->bits = (unsigned long long*)(base + per * 24);
+  g->bits_before = (unsigned long long*)(base + per * 32);
+  g->ones = (uint32_t*)(base + per * 40);
+  if (ntiles) {
+    k_gol_tile_counts<<<(unsigned)ntiles, TILE_THREADS, 0, c->stream>>>(S, T, *g);
+    BIC_LAUNCH_CHECK(c);
+    k_gol_scan_tiles_a<<<1, TILE_THREADS, 0, c->stream>>>(*g, ntiles);
+    BIC_LAUNCH_CHECK(c);
+    k_gol_walk<0><<<(unsigned)ntiles, TILE_THREADS, 0, c->stream>>>(S, T, N, *g, nullptr, nullptr, 1, nullptr);
+    BIC_LAUNCH_CHECK(c);
+  }
+  k_gol_scan_tiles_b<<<1, TILE_THREADS, 0, c->stream>>>(*g, ntiles, N, (unsigned long long*)c->d_scalars);
+  BIC_LAUNCH_CHECK(c);
+  BIC_TRY(bic_read_scalars(c, 4));
+  *S_out = S; *T_out = T; *ntiles_out = ntiles;
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_golomb_bitcount(bic_ctx* c, const bic_mat* M, uint64_t* bitcount, uint64_t* nsamples) {
+  if (!c || !M) return BIC_ERR_INVALID;
+  const uint32_t* S; uint64_t T, ntiles; GolTile g;
+  BIC_TRY(golomb_prepare(c, M, &S, &T, &g, &ntiles));
+  if (bitcount) *bitcount = c->h_scalars[0];
+  if (nsamples) *nsamples = c->h_scalars[1];
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t chunk_samples, bic_stream* out) {
+  if (!c || !M || !out) return BIC_ERR_INVALID;
+  if (chunk_samples == 0) chunk_samples = 256;
+  const uint64_t N = M->rows * M->cols;
+  const uint32_t* S; uint64_t T, ntiles; GolTile g;
+  BIC_TRY(golomb_prepare(c, M, &S, &T, &g, &ntiles));
+  const uint64_t bitcount = c->h_scalars[0], nsamples = c->h_scalars[1];
+  const uint64_t nchunks = div_up_u64(nsamples, chunk_samples);
+  BIC_TRY(stream_reserve(c, out, bitcount, nchunks));
+  BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, out->cap_bytes, c->stream));
+  // with no tile (empty matrix) one CTA still has to write the closing sample
+  const unsigned grid = (unsigned)(ntiles ? ntiles : 1);
+  k_gol_walk<1><<<grid, TILE_THREADS, 0, c->stream>>>(S, ntiles ? T : 0, N, g, (uint32_t*)out->d_bytes,
+                                                     (unsigned long long*)out->d_index, chunk_samples,
+                                                     (const unsigned long long*)c->d_scalars);
+  BIC_LAUNCH_CHECK(c);
+  out->info.coder = BIC_CODER_GOLOMB;
+  out->info.chunk_samples = chunk_samples;
+  out->info.rows = M->rows;
+  out->info.cols = M->cols;
+  out->info.bitcount = bitcount;
+  out->info.nsamples = nsamples;
+  out->info.nchunks = nchunks;
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_golomb_decode(bic_ctx* c, const bic_stream* s, bic_mat* M) {
+  if (!c || !s || !M) return BIC_ERR_INVALID;
+  if (s->info.coder != BIC_CODER_GOLOMB) return bic_fail(c, BIC_ERR_INVALID, "golomb_decode: not a Golomb stream");
+  if (M->rows != s->info.rows || M->cols != s->info.cols) return bic_fail(c, BIC_ERR_INVALID, "golomb_decode: shape mismatch");
+  const uint64_t N = M->rows * M->cols, T = div_up_u64(N, 32);
+  if (s->info.chunk_samples == 0 || s->info.nchunks != div_up_u64(s->info.nsamples, s->info.chunk_samples))
+    return bic_fail(c, BIC_ERR_CORRUPT, "golomb_decode: inconsistent chunk index");
+  uint32_t* S;
+  const bool dense = (M->cols & 31) == 0;
+  if (dense) {
+    S = M->d;
+    BIC_TRY(bic_mat_clear(c, M));
+  } else {
+    BIC_TRY(bic_scratch_reserve(c, &c->work[4], (size_t)T * 4 + 16));
+    S = (uint32_t*)c->work[4].p;
+    BIC_CUDA(c, cudaMemsetAsync(S, 0, (size_t)T * 4 + 16, c->stream));
+  }
+  BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, 8, c->stream));
+  k_gol_decode<<<bic_grid_for(c, s->info.nchunks, 128, 16), 128, 0, c->stream>>>(
+      (const uint32_t*)s->d_bytes, s->info.bitcount, (const unsigned long long*)s->d_index, s->info.nchunks,
+      s->info.chunk_samples, s->info.nsamples, N, S, (unsigned long long*)c->d_scalars);
+  BIC_LAUNCH_CHECK(c);
+  if (!dense && M->words()) {
+    k_expand_rows<<<bic_grid_for(c, M->words(), 256, 8), 256, 0, c->stream>>>(S, M->cols, M->wpr, M->rows, M->d);
+    BIC_LAUNCH_CHECK(c);
+  }
+  BIC_TRY(bic_read_scalars(c, 1));
+  if (c->h_scalars[0]) return bic_fail(c, BIC_ERR_CORRUPT, "golomb_decode: stream does not decode to the stated shape");
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_eg_encode(bic_ctx* c, const bic_mat* M, bic_stream* out) {
+  if (!c || !M || !out) return BIC_ERR_INVALID;
+  const uint64_t N = M->rows * M->cols;
+  const uint32_t* S; uint64_t T;
+  BIC_TRY(dense_stream(c, M, &S, &T));
+  BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0xFF, 8, c->stream));
+  if (T) {
+    k_first_one<<<bic_grid_for(c, T, 256, 8), 256, 0, c->stream>>>(S, T, (unsigned long long*)c->d_scalars);
+    BIC_LAUNCH_CHECK(c);
+  }
+  BIC_TRY(bic_read_scalars(c, 1));
+  const bool any = c->h_scalars[0] != ~0ull;
+  const uint64_t bitcount = N + M->rows + (any ? 1 : 0);
+  BIC_TRY(stream_reserve(c, out, bitcount, 0));
+  BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, out->cap_bytes, c->stream));
+  if (bitcount) {
+    k_fill_ones<<<bic_grid_for(c, div_up_u64(bitcount, 32), 256, 8), 256, 0, c->stream>>>((uint32_t*)out->d_bytes, bitcount);
+    BIC_LAUNCH_CHECK(c);
+  }
+  if (any) {
+    k_eg_encode<<<bic_grid_for(c, T, 256, 8), 256, 0, c->stream>>>(S, T, M->cols, (const unsigned long long*)c->d_scalars,
+                                                                  (uint32_t*)out->d_bytes);
+    BIC_LAUNCH_CHECK(c);
+  }
+  out->info.coder = BIC_CODER_EG;
+  out->info.chunk_samples = 0;
+  out->info.rows = M->rows;
+  out->info.cols = M->cols;
+  out->info.bitcount = bitcount;
+  out->info.nsamples = 0;
+  out->info.nchunks = 0;
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_eg_decode(bic_ctx* c, const bic_stream* s, bic_mat* M) {
+  if (!c || !s || !M) return BIC_ERR_INVALID;
+  if (s->info.coder != BIC_CODER_EG) return bic_fail(c, BIC_ERR_INVALID, "eg_decode: not an EG stream");
+  if (M->rows != s->info.rows || M->cols != s->info.cols) return bic_fail(c, BIC_ERR_INVALID, "eg_decode: shape mismatch");
+  const uint64_t N = M->rows * M->cols;
+  if (s->info.bitcount != N + M->rows && s->info.bitcount != N + M->rows + 1)
+    return bic_fail(c, BIC_ERR_CORRUPT, "eg_decode: bit count does not match the shape");
+  BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0xFF, 8, c->stream));
+  if (s->info.bitcount) {
+    k_first_zero<<<bic_grid_for(c, div_up_u64(s->info.bitcount, 32), 256, 8), 256, 0, c->stream>>>(
+        (const uint32_t*)s->d_bytes, s->info.bitcount, (unsigned long long*)c->d_scalars);
+    BIC_LAUNCH_CHECK(c);
+  }
+  if (M->words()) {
+    k_eg_decode<<<bic_grid_for(c, M->words(), 256, 8), 256, 0, c->stream>>>((const uint32_t*)s->d_bytes, M->rows, M->cols,
+                                                                          M->wpr, (const unsigned long long*)c->d_scalars, M->d);
+    BIC_LAUNCH_CHECK(c);
+  }
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_stream_download(bic_ctx* c, const bic_stream* s, uint8_t* bytes, uint64_t cap_bytes,
+                                          uint64_t* index, uint64_t cap_index_entries) {
+  if (!c || !s) return BIC_ERR_INVALID;
+  const uint64_t nb = div_up_u64(s->info.bitcount, 8);
+  if (bytes) {
+    if (cap_bytes < nb) return BIC_ERR_CAPACITY;
+    if (nb) BIC_CUDA(c, cudaMemcpyAsync(bytes, s->d_bytes, nb, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (index) {
+    if (cap_index_entries < s->info.nchunks) return BIC_ERR_CAPACITY;
+    if (s->info.nchunks)
+      BIC_CUDA(c, cudaMemcpyAsync(index, s->d_index, s->info.nchunks * 16, cudaMemcpyDeviceToHost, c->stream));
+  }
+  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_stream_upload(bic_ctx* c, bic_stream* s, const bic_stream_info* info, const uint8_t* bytes,
+                                        const uint64_t* index) {
+  if (!c || !s || !info) return BIC_ERR_INVALID;
+  const uint64_t nb = div_up_u64(info->bitcount, 8);
+  if ((nb && !bytes) || (info->nchunks && !index)) return BIC_ERR_INVALID;
+  BIC_TRY(stream_reserve(c, s, info->bitcount, info->nchunks));
+  BIC_CUDA(c, cudaMemsetAsync(s->d_bytes, 0, s->cap_bytes, c->stream));
+  if (nb) BIC_CUDA(c, cudaMemcpyAsync(s->d_bytes, bytes, nb, cudaMemcpyHostToDevice, c->stream));
+  if (info->nchunks) BIC_CUDA(c, cudaMemcpyAsync(s->d_index, index, info->nchunks * 16, cudaMemcpyHostToDevice, c->stream));
+  s->info = *info;
+  return BIC_OK;
+}

@@ -1,0 +1,259 @@
+// update_coefficients (greedy matching pursuit over GF(2)) and the GF(2) residual product.
+// Reference: update_coefficients_omp src/bsvd.cpp:1029-1107 (serial twin :399-460);
+// mul_AB src/binmat.cpp:516-543 + add :463-478.
+//
+// Per row i, repeat: w = |E_i|; pick k minimising |E_i xor D_k| (strict <, so the lowest k wins
+// ties); if that distance is strictly below w flip A[i,k] and E_i ^= D_k, else stop.
+// Rows are independent given D, so this is one thread per row with the row in registers and D
+// staged in shared memory as [atom][word] (every lane of a warp reads the same atom word, a
+// broadcast). The work is XOR + POPC: it is bound by the popcount pipe, not by HBM.
+#include "bic_internal.cuh"
+
+// distance and atom index packed in one key so the argmin with the reference's tie-break is a
+// plain min: key = dist << 16 | k  (dist <= 32*32 = 1024 bits, k < 65536)
+template <int WORDS>
+__device__ __forceinline__ uint32_t best_atom_key(const uint32_t (&e)[WORDS], const uint32_t* __restrict__ Ds, uint32_t p) {
+  uint32_t best = 0xFFFFFFFFu;
+  for (uint32_t k = 0; k < p; ++k) {
+    const uint32_t* dk = Ds + k * WORDS;
+    uint32_t d = 0;
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) d += __popc(e[w] ^ dk[w]);
+    best = min(best, (d << 16) | k);
+  }
+  return best;
+}
+
+template <int WORDS>
+__global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restrict__ E, const uint32_t* __restrict__ D,
+                                                             uint32_t* __restrict__ A, uint64_t n, uint64_t wprE,
+                                                             uint32_t p, uint64_t wprA,
+                                                             unsigned long long* __restrict__ changed) {
+  extern __shared__ uint32_t Ds[];  // p * WORDS, rows zero padded to WORDS
+  for (uint32_t i = threadIdx.x; i < p * WORDS; i += blockDim.x) {
+    const uint32_t k = i / WORDS, w = i - k * WORDS;
+    Ds[i] = (w < wprE) ? D[(uint64_t)k * wprE + w] : 0u;
+  }
+  __syncthreads();
+  uint32_t nchanged = 0;
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t e[WORDS];
+    uint32_t* erow = E + r * wprE;
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) e[w] = ((uint64_t)w < wprE) ? erow[w] : 0u;
+    bool row_changed = false;
+    for (;;) {
+      uint32_t wt = 0;  // w = Ei.weight(), src/bsvd.cpp:1065
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) wt += __popc(e[w]);
+      if (wt == 0) break;  // no distance can be < 0
+      const uint32_t key = best_atom_key<WORDS>(e, Ds, p);  // :1067-1082
+      const uint32_t bestd = key >> 16, bestk = key & 0xFFFFu;
+      if (bestd >= wt) break;  // :1084, strict <
+      A[r * wprA + (bestk >> 5)] ^= 0x80000000u >> (bestk & 31);  // Ai.flip(0,bestk), :1086
+      const uint32_t* dk = Ds + bestk * WORDS;
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) e[w] ^= dk[w];  // :1087
+      row_changed = true;
+    }
+    if (row_changed) {  // :1095-1099
+      nchanged++;
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w)
+        if ((uint64_t)w < wprE) erow[w] = e[w];
+    }
+  }
+  nchanged = warp_sum_u32(nchanged);
+  if ((threadIdx.x & 31) == 0 && nchanged) atomicAdd(changed, (unsigned long long)nchanged);
+}
+
+// Fallback for rows wider than 32 words (m > 1024) or a dictionary that does not fit in shared
+// memory: one warp per row, the row staged in shared memory, D read through L1/L2.
+__global__ void __launch_bounds__(256) k_update_coefficients_wide(uint32_t* __restrict__ E, const uint32_t* __restrict__ D,
+                                                                  uint32_t* __restrict__ A, uint64_t n, uint64_t wprE,
+                                                                  uint32_t p, uint64_t wprA,
+                                                                  unsigned long long* __restrict__ changed) {
+  extern __shared__ uint32_t es_all[];  // (blockDim/32) * wprE
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t* es = es_all + (size_t)wib * wprE;
+  const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  uint32_t nchanged = 0;
+  for (uint64_t r = gw; r < n; r += nwarps) {
+    uint32_t* erow = E + r * wprE;
+    for (uint64_t w = lane; w < wprE; w += 32) es[w] = erow[w];
+    __syncwarp();
+    bool row_changed = false;
+    for (;;) {
+      uint32_t wt = 0;
+      for (uint64_t w = lane; w < wprE; w += 32) wt += __popc(es[w]);
+      wt = warp_sum_u32(wt);
+      if (wt == 0) break;
+      unsigned long long best = ~0ull;  // dist << 32 | k
+      for (uint32_t k = 0; k < p; ++k) {
+        const uint32_t* dk = D + (uint64_t)k * wprE;
+        uint32_t d = 0;
+        for (uint64_t w = lane; w < wprE; w += 32) d += __popc(es[w] ^ __ldg(dk + w));
+        d = warp_sum_u32(d);
+        const unsigned long long key = ((unsigned long long)d << 32) | k;
+        best = key < best ? key : best;
+      }
+      const uint32_t bestd = (uint32_t)(best >> 32), bestk = (uint32_t)best;
+      if (bestd >= wt) break;
+      if (lane == 0) A[r * wprA + (bestk >> 5)] ^= 0x80000000u >> (bestk & 31);
+      const uint32_t* dk = D + (uint64_t)bestk * wprE;
+      for (uint64_t w = lane; w < wprE; w += 32) es[w] ^= __ldg(dk + w);
+      __syncwarp();
+      row_changed = true;
+    }
+    if (row_changed) {
+      if (lane == 0) nchanged++;
+      for (uint64_t w = lane; w < wprE; w += 32) erow[w] = es[w];
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && nchanged) atomicAdd(changed, (unsigned long long)nchanged);
+}
+
+template <int WORDS>
+static bic_status launch_coef(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, unsigned long long* d_changed) {
+  const size_t smem = (size_t)D->rows * WORDS * 4;
+  if (smem > 48 * 1024)
+    BIC_CUDA(c, cudaFuncSetAttribute(k_update_coefficients<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // persistent grid: a multiple of the SM count, as many CTAs per SM as the dictionary allows
+  int per_sm = smem ? (int)((200 * 1024) / smem) : 8;
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  const int grid = bic_grid_for(c, E->rows, 256, per_sm);
+  k_update_coefficients<WORDS><<<grid, 256, smem, c->stream>>>(E->d, D->d, A->d, E->rows, E->wpr, (uint32_t)D->rows,
+                                                              A->wpr, d_changed);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+// device-side entry used by the learner too: adds the changed-row count to *d_changed
+bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, unsigned long long* d_changed) {
+  if (E->rows != A->rows || E->cols != D->cols || A->cols != D->rows)
+    return bic_fail(c, BIC_ERR_INVALID, "update_coefficients: shapes must be E n x m, D p x m, A n x p");
+  if (E->rows == 0 || D->rows == 0) return BIC_OK;
+  if (D->rows > 65535) return bic_fail(c, BIC_ERR_UNSUPPORTED, "update_coefficients: more than 65535 atoms");
+  const uint64_t wpr = E->wpr;
+  const int WORDS = wpr <= 1 ? 1 : wpr <= 2 ? 2 : wpr <= 4 ? 4 : wpr <= 8 ? 8 : wpr <= 16 ? 16 : wpr <= 32 ? 32 : 0;
+  if (WORDS && (size_t)D->rows * WORDS * 4 <= 200 * 1024) {
+    switch (WORDS) {
+      case 1: return launch_coef<1>(c, E, D, A, d_changed);
+      case 2: return launch_coef<2>(c, E, D, A, d_changed);
+      case 4: return launch_coef<4>(c, E, D, A, d_changed);
+      case 8: return launch_coef<8>(c, E, D, A, d_changed);
+      case 16: return launch_coef<16>(c, E, D, A, d_changed);
+      default: return launch_coef<32>(c, E, D, A, d_changed);
+    }
+  }
+  const size_t smem = (size_t)8 * wpr * 4;
+  if (smem > 200 * 1024) return bic_fail(c, BIC_ERR_UNSUPPORTED, "update_coefficients: rows wider than 200 KB");
+  if (smem > 48 * 1024)
+    BIC_CUDA(c, cudaFuncSetAttribute(k_update_coefficients_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_update_coefficients_wide<<<bic_grid_for(c, E->rows * 32, 256, 4), 256, smem, c->stream>>>(
+      E->d, D->d, A->d, E->rows, wpr, (uint32_t)D->rows, A->wpr, d_changed);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, uint64_t* changed) {
+  if (!c || !E || !D || !A) return BIC_ERR_INVALID;
+  BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, sizeof(uint64_t), c->stream));
+  BIC_TRY(bic_k_update_coefficients(c, E, D, A, (unsigned long long*)c->d_scalars));
+  BIC_TRY(bic_read_scalars(c, 1));
+  if (changed) *changed = c->h_scalars[0];
+  return BIC_OK;
+}
+
+// ------------------------------------------------------------------ E = A*D xor X
+template <int WORDS>
+__global__ void __launch_bounds__(256) k_residual(const uint32_t* __restrict__ X, const uint32_t* __restrict__ A,
+                                                  const uint32_t* __restrict__ D, uint32_t* __restrict__ E, uint64_t n,
+                                                  uint64_t wprE, uint32_t p, uint64_t wprA, bool d_in_smem) {
+  extern __shared__ uint32_t Ds[];
+  if (d_in_smem) {
+    for (uint32_t i = threadIdx.x; i < p * WORDS; i += blockDim.x) {
+      const uint32_t k = i / WORDS, w = i - k * WORDS;
+      Ds[i] = (w < wprE) ? D[(uint64_t)k * wprE + w] : 0u;
+    }
+    __syncthreads();
+  }
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t e[WORDS];
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) e[w] = ((uint64_t)w < wprE) ? X[r * wprE + w] : 0u;
+    for (uint64_t aw = 0; aw < wprA; ++aw) {
+      uint32_t bits = A[r * wprA + aw];
+      while (bits) {
+        const int pos = __clz(bits);
+        bits &= ~(0x80000000u >> pos);
+        const uint32_t k = (uint32_t)aw * 32 + pos;
+        if (d_in_smem) {
+#pragma unroll
+          for (int w = 0; w < WORDS; ++w) e[w] ^= Ds[k * WORDS + w];
+        } else {
+#pragma unroll
+          for (int w = 0; w < WORDS; ++w)
+            if ((uint64_t)w < wprE) e[w] ^= __ldg(D + (uint64_t)k * wprE + w);
+        }
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w)
+      if ((uint64_t)w < wprE) E[r * wprE + w] = e[w];
+  }
+}
+
+// generic: a thread per word of E
+__global__ void k_residual_wide(const uint32_t* __restrict__ X, const uint32_t* __restrict__ A,
+                                const uint32_t* __restrict__ D, uint32_t* __restrict__ E, uint64_t n, uint64_t wprE,
+                                uint64_t wprA) {
+  const uint64_t total = n * wprE;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = i / wprE, w = i - r * wprE;
+    uint32_t e = X[i];
+    for (uint64_t aw = 0; aw < wprA; ++aw) {
+      uint32_t bits = __ldg(A + r * wprA + aw);
+      while (bits) {
+        const int pos = __clz(bits);
+        bits &= ~(0x80000000u >> pos);
+        e ^= __ldg(D + (aw * 32 + pos) * wprE + w);
+      }
+    }
+    E[i] = e;
+  }
+}
+
+template <int WORDS>
+static bic_status launch_residual(bic_ctx* c, const bic_mat* X, const bic_mat* A, const bic_mat* D, bic_mat* E) {
+  size_t smem = (size_t)D->rows * WORDS * 4;
+  const bool in_smem = smem <= 200 * 1024;
+  if (!in_smem) smem = 0;
+  if (smem > 48 * 1024)
+    BIC_CUDA(c, cudaFuncSetAttribute(k_residual<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = smem ? (int)((200 * 1024) / smem) : 8;
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  k_residual<WORDS><<<bic_grid_for(c, X->rows, 256, per_sm), 256, smem, c->stream>>>(
+      X->d, A->d, D->d, E->d, X->rows, X->wpr, (uint32_t)D->rows, A->wpr, in_smem);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_residual(bic_ctx* c, const bic_mat* X, const bic_mat* A, const bic_mat* D, bic_mat* E) {
+  if (!c || !X || !A || !D || !E) return BIC_ERR_INVALID;
+  if (X->rows != A->rows || X->cols != D->cols || A->cols != D->rows || E->rows != X->rows || E->cols != X->cols)
+    return bic_fail(c, BIC_ERR_INVALID, "residual: shapes must be X,E n x m, D p x m, A n x p");
+  if (X->words() == 0) return BIC_OK;
+  const uint64_t wpr = X->wpr;
+  if (wpr <= 1) return launch_residual<1>(c, X, A, D, E);
+  if (wpr <= 2) return launch_residual<2>(c, X, A, D, E);
+  if (wpr <= 4) return launch_residual<4>(c, X, A, D, E);
+  if (wpr <= 8) return launch_residual<8>(c, X, A, D, E);
+  if (wpr <= 16) return launch_residual<16>(c, X, A, D, E);
+  if (wpr <= 32) return launch_residual<32>(c, X, A, D, E);
+  k_residual_wide<<<bic_grid_for(c, X->words(), 256, 8), 256, 0, c->stream>>>(X->d, A->d, D->d, E->d, X->rows, wpr, A->wpr);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}

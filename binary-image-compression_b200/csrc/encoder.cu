@@ -1,0 +1,172 @@
+// learn_model_traditional and the whole-page encoder / decoder.
+// Reference: learn_model_traditional src/bsvd.cpp:1215-1244; driver src/bsvd_test.cpp:56-155.
+#include "bic_internal.cuh"
+
+#include <vector>
+
+bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, unsigned long long* d_changed);
+bic_status bic_k_update_dictionary(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed);
+
+extern "C" bic_status bic_learn_model_traditional(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat* D, bic_mat* A,
+                                                  uint64_t* iterations, uint64_t* trace, uint64_t trace_cap) {
+  if (!c || !X || !E || !D || !A) return BIC_ERR_INVALID;
+  BIC_TRY(bic_residual(c, X, A, D, E));  // mul(A,false,D,false,E); add(E,X,E)  src/bsvd.cpp:1219-1220
+  uint64_t changed = 1, iter = 0;
+  unsigned long long* d_cc = (unsigned long long*)c->d_scalars;
+  while (changed > 0) {  // :1227
+    iter++;
+    BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, 2 * sizeof(uint64_t), c->stream));
+    BIC_TRY(bic_k_update_coefficients(c, E, D, A, d_cc));      // :1229
+    BIC_TRY(bic_k_update_dictionary(c, E, D, A, d_cc + 1));    // :1235
+    BIC_TRY(bic_read_scalars(c, 2));                           // the loop condition needs the counts
+    changed = c->h_scalars[0] + c->h_scalars[1];
+    if (trace && iter <= trace_cap) { trace[2 * (iter - 1)] = c->h_scalars[0]; trace[2 * (iter - 1) + 1] = c->h_scalars[1]; }
+  }
+  if (iterations) *iterations = iter;
+  return BIC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// container: little-endian u64 fields
+//   [0] magic "BICB200\0"  [1] version  [2] rows [3] cols [4] W [5] K [6] n [7] m [8] iterations [9] seed
+//   then per stream (D, A, E) 7 fields: coder, chunk_samples, rows, cols, bitcount, nsamples, nchunks
+//   then per stream: code bytes padded to 8, chunk index (nchunks * 2 u64)
+// ---------------------------------------------------------------------------------------------
+static const uint64_t BIC_MAGIC = 0x0030303242434942ull;  // "BICB200\0"
+static const uint64_t HDR_FIELDS = 10, STREAM_FIELDS = 7;
+
+struct EncWorkspace {
+  uint64_t rows = 0, cols = 0, W = 0, K = 0;
+  bic_mat *raster = nullptr, *X = nullptr, *E = nullptr, *D = nullptr, *A = nullptr;
+  bic_stream* st[3] = {nullptr, nullptr, nullptr};
+};
+
+static EncWorkspace* ws_of(bic_ctx* c);
+
+// one workspace per context, kept in a side table so bic_ctx stays a plain struct
+#include <map>
+#include <mutex>
+static std::map<bic_ctx*, EncWorkspace> g_ws;
+static std::mutex g_ws_mu;
+static EncWorkspace* ws_of(bic_ctx* c) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  return &g_ws[c];
+}
+
+static void ws_release(bic_ctx* c, EncWorkspace* w) {
+  bic_mat** ms[] = {&w->raster, &w->X, &w->E, &w->D, &w->A};
+  for (auto pm : ms) if (*pm) { bic_mat_destroy(c, *pm); *pm = nullptr; }
+}
+
+extern "C" void bic_internal_drop_workspace(bic_ctx* c) {
+  EncWorkspace* w = ws_of(c);
+  ws_release(c, w);
+  for (auto& s : w->st) if (s) { bic_stream_destroy(c, s); s = nullptr; }
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  g_ws.erase(c);
+}
+
+static bic_status ws_prepare(bic_ctx* c, EncWorkspace* w, uint64_t rows, uint64_t cols, uint64_t W, uint64_t K) {
+  if (w->raster && w->rows == rows && w->cols == cols && w->W == W && w->K == K) return BIC_OK;
+  ws_release(c, w);
+  const uint64_t Ny = (W - 1 + rows) / W, Nx = (W - 1 + cols) / W, n = Nx * Ny, m = W * W;
+  BIC_TRY(bic_mat_create(c, rows, cols, &w->raster));
+  BIC_TRY(bic_mat_create(c, n, m, &w->X));
+  BIC_TRY(bic_mat_create(c, n, m, &w->E));
+  BIC_TRY(bic_mat_create(c, K, m, &w->D));
+  BIC_TRY(bic_mat_create(c, n, K, &w->A));
+  for (auto& s : w->st) if (!s) BIC_TRY(bic_stream_create(c, &s));
+  w->rows = rows; w->cols = cols; w->W = W; w->K = K;
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_encode_raster(bic_ctx* c, const uint8_t* pbm_payload, uint64_t rows, uint64_t cols, uint64_t W,
+                                        uint64_t K, unsigned long seed, uint8_t* out, uint64_t cap_bytes,
+                                        bic_encode_info* info) {
+  if (!c || !pbm_payload || W == 0 || K == 0 || rows == 0 || cols == 0) return BIC_ERR_INVALID;
+  EncWorkspace* w = ws_of(c);
+  BIC_TRY(ws_prepare(c, w, rows, cols, W, K));
+  BIC_TRY(bic_mat_upload_pbm(c, w->raster, pbm_payload));
+  BIC_TRY(bic_extract_patches(c, w->raster, W, w->X));       // src/bsvd_test.cpp:80-99
+  uint64_t rng;
+  bic_rand48_seed(&rng, seed);                               // -r / random_seed, src/bsvd.cpp:12
+  BIC_TRY(bic_initialize_model_neighbor(c, w->X, w->D, w->A, &rng));  // :114
+  uint64_t iters = 0;
+  BIC_TRY(bic_learn_model_traditional(c, w->X, w->E, w->D, w->A, &iters, nullptr, 0));  // :119
+  const bic_mat* mats[3] = {w->D, w->A, w->E};
+  for (int i = 0; i < 3; ++i) BIC_TRY(bic_golomb_encode(c, mats[i], 256, w->st[i]));
+  // lay out the container
+  uint64_t need = (HDR_FIELDS + 3 * STREAM_FIELDS) * 8;
+  for (int i = 0; i < 3; ++i) need += div_up_u64(div_up_u64(w->st[i]->info.bitcount, 8), 8) * 8 + w->st[i]->info.nchunks * 16;
+  if (info) {
+    memset(info, 0, sizeof(*info));
+    info->rows = rows; info->cols = cols; info->W = W; info->K = K;
+    info->n = w->X->rows; info->m = w->X->cols; info->iterations = iters;
+    info->bits_D = w->st[0]->info.bitcount; info->bits_A = w->st[1]->info.bitcount; info->bits_E = w->st[2]->info.bitcount;
+    info->weight_D = w->st[0]->info.nsamples - 1; info->weight_A = w->st[1]->info.nsamples - 1;
+    info->weight_E = w->st[2]->info.nsamples - 1;  // samples = ones + 1
+    info->container_bytes = need;
+  }
+  if (!out) return BIC_OK;
+  if (cap_bytes < need) return BIC_ERR_CAPACITY;
+  if (((uintptr_t)out & 7) != 0) return bic_fail(c, BIC_ERR_INVALID, "encode_raster: out must be 8-byte aligned");
+  uint64_t* h = (uint64_t*)out;
+  h[0] = BIC_MAGIC; h[1] = 1; h[2] = rows; h[3] = cols; h[4] = W; h[5] = K; h[6] = w->X->rows; h[7] = w->X->cols;
+  h[8] = iters; h[9] = (uint64_t)seed;
+  uint64_t off = (HDR_FIELDS + 3 * STREAM_FIELDS) * 8;
+  for (int i = 0; i < 3; ++i) {
+    const bic_stream_info& si = w->st[i]->info;
+    uint64_t* f = h + HDR_FIELDS + i * STREAM_FIELDS;
+    f[0] = si.coder; f[1] = si.chunk_samples; f[2] = si.rows; f[3] = si.cols; f[4] = si.bitcount; f[5] = si.nsamples; f[6] = si.nchunks;
+    const uint64_t nb = div_up_u64(si.bitcount, 8), nbp = div_up_u64(nb, 8) * 8;
+    memset(out + off + nb, 0, nbp - nb);
+    BIC_TRY(bic_stream_download(c, w->st[i], out + off, nb, (uint64_t*)(out + off + nbp), si.nchunks));
+    off += nbp + si.nchunks * 16;
+  }
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_decode_raster(bic_ctx* c, const uint8_t* cont, uint64_t nbytes, uint8_t* pbm_payload,
+                                        uint64_t cap_bytes, uint64_t* rows_out, uint64_t* cols_out) {
+  if (!c || !cont) return BIC_ERR_INVALID;
+  const uint64_t hdr = (HDR_FIELDS + 3 * STREAM_FIELDS) * 8;
+  if (nbytes < hdr) return bic_fail(c, BIC_ERR_CORRUPT, "container: truncated header");
+  std::vector<uint64_t> h((HDR_FIELDS + 3 * STREAM_FIELDS));
+  memcpy(h.data(), cont, hdr);
+  if (h[0] != BIC_MAGIC || h[1] != 1) return bic_fail(c, BIC_ERR_CORRUPT, "container: bad magic/version");
+  const uint64_t rows = h[2], cols = h[3], W = h[4], K = h[5], n = h[6], m = h[7];
+  if (W == 0 || rows == 0 || cols == 0 || m != W * W || n != ((W - 1 + rows) / W) * ((W - 1 + cols) / W))
+    return bic_fail(c, BIC_ERR_CORRUPT, "container: inconsistent shape");
+  if (rows_out) *rows_out = rows;
+  if (cols_out) *cols_out = cols;
+  const uint64_t payload = rows * div_up_u64(cols, 8);
+  if (!pbm_payload) return BIC_OK;
+  if (cap_bytes < payload) return BIC_ERR_CAPACITY;
+  EncWorkspace* w = ws_of(c);
+  BIC_TRY(ws_prepare(c, w, rows, cols, W, K));
+  bic_mat* mats[3] = {w->D, w->A, w->E};
+  const uint64_t shp[3][2] = {{K, m}, {n, K}, {n, m}};
+  uint64_t off = hdr;
+  for (int i = 0; i < 3; ++i) {
+    const uint64_t* f = h.data() + HDR_FIELDS + i * STREAM_FIELDS;
+    bic_stream_info si;
+    si.coder = (uint32_t)f[0]; si.chunk_samples = (uint32_t)f[1]; si.rows = f[2]; si.cols = f[3];
+    si.bitcount = f[4]; si.nsamples = f[5]; si.nchunks = f[6];
+    if (si.rows != shp[i][0] || si.cols != shp[i][1]) return bic_fail(c, BIC_ERR_CORRUPT, "container: stream shape mismatch");
+    const uint64_t nb = div_up_u64(si.bitcount, 8), nbp = div_up_u64(nb, 8) * 8;
+    if (off + nbp + si.nchunks * 16 > nbytes) return bic_fail(c, BIC_ERR_CORRUPT, "container: truncated stream");
+    std::vector<uint64_t> idx(si.nchunks * 2 + 1);
+    memcpy(idx.data(), cont + off + nbp, si.nchunks * 16);
+    BIC_TRY(bic_stream_upload(c, w->st[i], &si, cont + off, idx.data()));
+    BIC_CUDA(c, cudaStreamSynchronize(c->stream));  // idx is a local
+    if (si.coder == BIC_CODER_GOLOMB) BIC_TRY(bic_golomb_decode(c, w->st[i], mats[i]));
+    else if (si.coder == BIC_CODER_EG) BIC_TRY(bic_eg_decode(c, w->st[i], mats[i]));
+    else return bic_fail(c, BIC_ERR_CORRUPT, "container: unknown coder");
+    off += nbp + si.nchunks * 16;
+  }
+  // X = A*D xor E  (the residual identity read backwards), then patches -> raster
+  BIC_TRY(bic_residual(c, w->E, w->A, w->D, w->X));
+  BIC_TRY(bic_assemble_patches(c, w->X, W, w->raster));
+  BIC_TRY(bic_mat_download_pbm(c, w->raster, pbm_payload));
+  return BIC_OK;
+}

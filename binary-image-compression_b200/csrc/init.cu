@@ -1,0 +1,244 @@
+// initialize_model_neighbor on the device. Reference: src/bsvd.cpp:227-267.
+//
+// The reference, per pivot row P (a random non-zero row of X), scans all rows j, forms
+// Ej = X[j] & P, and if Ej != 0 counts u++ and s[b] += Ej[b]; then D[k][b] = (s[b] >= u/2).
+// Two observations make this one pass over X instead of p bit-serial passes, with identical
+// results:
+//   (1) Ej[b] = 1 already implies Ej != 0, so s[b] = P[b] ? c[b] : 0 where c[b] is the plain
+//       column count of X (independent of the pivot);
+//   (2) only u = #{j : X[j] & P != 0} depends on the pivot.
+// So: one column histogram of X, one "does row j meet pivot k" count per pivot, one threshold.
+// The RNG draw (rand48 + rejection of all-zero rows, :241-243) is serial and stays on the host;
+// the device only supplies the zero-row bitmap.
+#include "bic_internal.cuh"
+
+#include <vector>
+
+// ------------------------------------------------------------------ zero-row bitmap
+__global__ void k_row_nonzero(const uint32_t* __restrict__ X, uint64_t n, uint64_t wpr, uint32_t* __restrict__ bitmap) {
+  const uint64_t nround = (n + 31) & ~(uint64_t)31;
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < nround; r += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t any = 0;
+    if (r < n) {
+      const uint32_t* row = X + r * wpr;
+      for (uint64_t w = 0; w < wpr; ++w) any |= __ldg(row + w);
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, any != 0);
+    if ((threadIdx.x & 31) == 0) bitmap[r >> 5] = b;  // bit (r & 31), LSB first
+  }
+}
+
+bic_status bic_k_row_nonzero_bitmap(bic_ctx* c, const bic_mat* X, uint32_t* d_bitmap) {
+  if (X->rows == 0) return BIC_OK;
+  k_row_nonzero<<<bic_grid_for(c, X->rows, 256, 8), 256, 0, c->stream>>>(X->d, X->rows, X->wpr, d_bitmap);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_draw_pivots(bic_ctx* c, const bic_mat* X, uint64_t p, uint64_t* rng_state,
+                                      uint64_t* pivots_out, uint64_t* ndraws_out) {
+  if (!c || !X || !rng_state || (!pivots_out && p)) return BIC_ERR_INVALID;
+  const uint64_t n = X->rows;
+  if (p == 0) { if (ndraws_out) *ndraws_out = 0; return BIC_OK; }
+  if (n == 0) return bic_fail(c, BIC_ERR_INVALID, "draw_pivots: empty X");
+  const uint64_t nw = div_up_u64(n, 32);
+  BIC_TRY(bic_scratch_reserve(c, &c->work[0], nw * 4));
+  BIC_TRY(bic_k_row_nonzero_bitmap(c, X, (uint32_t*)c->work[0].p));
+  std::vector<uint32_t> bm(nw);
+  BIC_CUDA(c, cudaMemcpyAsync(bm.data(), c->work[0].p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  bool any = false;
+  for (uint64_t i = 0; i < nw && !any; ++i) any = bm[i] != 0;
+  if (!any) return bic_fail(c, BIC_ERR_INVALID, "draw_pivots: X is all zero (the reference's draw loop never ends)");
+  uint64_t draws = 0;
+  for (uint64_t k = 0; k < p;) {                     // src/bsvd.cpp:239
+    const uint64_t i = bic_rand48_uniform_int(rng_state, n);  // :241
+    ++draws;
+    if (!((bm[i >> 5] >> (i & 31)) & 1u)) continue;  // :243 (a rejected draw is consumed)
+    pivots_out[k++] = i;                             // u > 0 always holds for a non-zero pivot (:258)
+  }
+  if (ndraws_out) *ndraws_out = draws;
+  return BIC_OK;
+}
+
+// ------------------------------------------------------------------ column histogram c[b]
+// A warp walks rows; every lane loads the same word (broadcast) and counts its own bit.
+// WORDS = words of a row handled per launch (registers), word0 = first word.
+template <int WORDS>
+__global__ void k_col_hist(const uint32_t* __restrict__ X, uint64_t n, uint64_t wpr, uint64_t word0, uint64_t nwords,
+                           uint32_t* __restrict__ hist /* [wpr*32] */) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  uint32_t cnt[WORDS];
+#pragma unroll
+  for (int w = 0; w < WORDS; ++w) cnt[w] = 0;
+  for (uint64_t r = gw; r < n; r += nwarps) {
+    const uint32_t* row = X + r * wpr + word0;
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) {
+      if ((uint64_t)w < nwords) cnt[w] += (__ldg(row + w) >> (31 - lane)) & 1u;
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < WORDS; ++w)
+    if ((uint64_t)w < nwords && cnt[w]) atomicAdd(&hist[(word0 + w) * 32 + lane], cnt[w]);
+}
+
+// ------------------------------------------------------------------ u[k] = #{j : X[j] & P_k != 0}
+// Thread per row (row words in registers), pivot rows staged in shared memory (broadcast reads).
+template <int WORDS>
+__global__ void k_pivot_usage(const uint32_t* __restrict__ X, uint64_t n, uint64_t wpr,
+                              const uint32_t* __restrict__ P /* [np][wpr] */, uint32_t np, uint32_t* __restrict__ usage) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* Ps = sm;             // np * WORDS
+  uint32_t* us = sm + (size_t)np * WORDS;  // np
+  for (uint32_t i = threadIdx.x; i < np * WORDS; i += blockDim.x) {
+    const uint32_t k = i / WORDS, w = i - k * WORDS;
+    Ps[i] = (w < wpr) ? P[(uint64_t)k * wpr + w] : 0u;
+  }
+  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) us[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint64_t nround = (n + 31) & ~(uint64_t)31;
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < nround; r += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t x[WORDS];
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) x[w] = (r < n && (uint64_t)w < wpr) ? __ldg(X + r * wpr + w) : 0u;
+    for (uint32_t k = 0; k < np; ++k) {
+      uint32_t any = 0;
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) any |= x[w] & Ps[k * WORDS + w];
+      const uint32_t b = __ballot_sync(0xffffffffu, any != 0);
+      if (lane == 0 && b) atomicAdd(&us[k], (uint32_t)__popc(b));
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x)
+    if (us[i]) atomicAdd(&usage[i], us[i]);
+}
+
+// slow path for rows wider than 32 words: a warp per row, lanes stride the words
+__global__ void k_pivot_usage_wide(const uint32_t* __restrict__ X, uint64_t n, uint64_t wpr,
+                                   const uint32_t* __restrict__ P, uint32_t np, uint32_t* __restrict__ usage) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t r = gw; r < n; r += nwarps) {
+    for (uint32_t k = 0; k < np; ++k) {
+      uint32_t any = 0;
+      for (uint64_t w = lane; w < wpr; w += 32) any |= __ldg(X + r * wpr + w) & __ldg(P + (uint64_t)k * wpr + w);
+      if (__any_sync(0xffffffffu, any != 0) && lane == 0) atomicAdd(&usage[k], 1u);
+    }
+  }
+}
+
+__global__ void k_gather_rows(const uint32_t* __restrict__ X, uint64_t wpr, const uint64_t* __restrict__ pivots,
+                              uint32_t np, uint32_t* __restrict__ P) {
+  const uint64_t total = (uint64_t)np * wpr;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = i / wpr, w = i - k * wpr;
+    P[i] = X[pivots[k] * wpr + w];
+  }
+}
+
+// D[k][b] = (P_k[b] ? c[b] : 0) >= u_k / 2     (src/bsvd.cpp:258-262; ">=" and integer u/2)
+__global__ void k_init_finalize(const uint32_t* __restrict__ P, const uint32_t* __restrict__ hist,
+                                const uint32_t* __restrict__ usage, uint32_t np, uint64_t wpr, uint64_t m,
+                                uint32_t* __restrict__ D) {
+  const uint64_t total = (uint64_t)np * wpr;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = i / wpr, w = i - k * wpr;
+    const uint32_t pw = P[i];
+    const uint32_t half = usage[k] >> 1;
+    uint32_t out = 0;
+    for (int b = 0; b < 32; ++b) {
+      const uint64_t j = w * 32 + b;
+      if (j >= m) break;
+      const uint32_t s = ((pw >> (31 - b)) & 1u) ? hist[j] : 0u;
+      if (s >= half) out |= 0x80000000u >> b;
+    }
+    D[i] = out;
+  }
+}
+
+template <int WORDS>
+static bic_status launch_usage(bic_ctx* c, const bic_mat* X, const uint32_t* P, uint32_t np, uint32_t* usage) {
+  const size_t smem = ((size_t)np * WORDS + np) * 4;
+  if (smem > 48 * 1024)
+    BIC_CUDA(c, cudaFuncSetAttribute(k_pivot_usage<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_pivot_usage<WORDS><<<bic_grid_for(c, X->rows, 256, 4), 256, smem, c->stream>>>(X->d, X->rows, X->wpr, P, np, usage);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_initialize_model_neighbor_pivots(bic_ctx* c, const bic_mat* X, const uint64_t* pivots,
+                                                           uint64_t p, bic_mat* D, bic_mat* A) {
+  if (!c || !X || !D || !A || (!pivots && p)) return BIC_ERR_INVALID;
+  if (D->rows != p || D->cols != X->cols || A->rows != X->rows || A->cols != p)
+    return bic_fail(c, BIC_ERR_INVALID, "init: shapes must be X n x m, D p x m, A n x p");
+  for (uint64_t k = 0; k < p; ++k)
+    if (pivots[k] >= X->rows) return bic_fail(c, BIC_ERR_INVALID, "init: pivot out of range");
+  BIC_TRY(bic_mat_clear(c, A));  // A.clear(), src/bsvd.cpp:237
+  BIC_TRY(bic_mat_clear(c, D));  // D.clear(), :238
+  if (p == 0 || X->rows == 0 || X->cols == 0) return BIC_OK;
+  const uint64_t wpr = X->wpr, m = X->cols;
+  // work[1]: pivots (u64 p) | P rows (p*wpr u32) | hist (wpr*32 u32) | usage (p u32)
+  const size_t off_P = (size_t)p * 8;
+  const size_t off_h = off_P + (size_t)p * wpr * 4;
+  const size_t off_u = off_h + (size_t)wpr * 32 * 4;
+  const size_t total = off_u + (size_t)p * 4;
+  BIC_TRY(bic_scratch_reserve(c, &c->work[1], total));
+  uint8_t* base = (uint8_t*)c->work[1].p;
+  uint64_t* d_piv = (uint64_t*)base;
+  uint32_t* d_P = (uint32_t*)(base + off_P);
+  uint32_t* d_hist = (uint32_t*)(base + off_h);
+  uint32_t* d_usage = (uint32_t*)(base + off_u);
+  BIC_CUDA(c, cudaMemcpyAsync(d_piv, pivots, (size_t)p * 8, cudaMemcpyHostToDevice, c->stream));
+  BIC_CUDA(c, cudaMemsetAsync(d_hist, 0, (size_t)wpr * 32 * 4 + (size_t)p * 4, c->stream));
+  k_gather_rows<<<bic_grid_for(c, p * wpr, 256, 4), 256, 0, c->stream>>>(X->d, wpr, d_piv, (uint32_t)p, d_P);
+  BIC_LAUNCH_CHECK(c);
+  // column histogram, 32 words of the row per launch
+  for (uint64_t w0 = 0; w0 < wpr; w0 += 32) {
+    const uint64_t nw = (wpr - w0 < 32) ? wpr - w0 : 32;
+    const int grid = bic_grid_for(c, X->rows * 32, 256, 8);
+    if (nw <= 2) k_col_hist<2><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist);
+    else if (nw <= 8) k_col_hist<8><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist);
+    else k_col_hist<32><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist);
+    BIC_LAUNCH_CHECK(c);
+  }
+  // pivot usage, in chunks of pivots whose rows fit in shared memory
+  if (wpr <= 32) {
+    const int WORDS = wpr <= 1 ? 1 : wpr <= 2 ? 2 : wpr <= 4 ? 4 : wpr <= 8 ? 8 : wpr <= 16 ? 16 : 32;
+    const uint64_t max_np = (96 * 1024 / 4) / (WORDS + 1);
+    for (uint64_t k0 = 0; k0 < p; k0 += max_np) {
+      const uint32_t np = (uint32_t)((p - k0 < max_np) ? p - k0 : max_np);
+      const uint32_t* Pk = d_P + k0 * wpr;
+      uint32_t* uk = d_usage + k0;
+      switch (WORDS) {
+        case 1: BIC_TRY(launch_usage<1>(c, X, Pk, np, uk)); break;
+        case 2: BIC_TRY(launch_usage<2>(c, X, Pk, np, uk)); break;
+        case 4: BIC_TRY(launch_usage<4>(c, X, Pk, np, uk)); break;
+        case 8: BIC_TRY(launch_usage<8>(c, X, Pk, np, uk)); break;
+        case 16: BIC_TRY(launch_usage<16>(c, X, Pk, np, uk)); break;
+        default: BIC_TRY(launch_usage<32>(c, X, Pk, np, uk)); break;
+      }
+    }
+  } else {
+    k_pivot_usage_wide<<<bic_grid_for(c, X->rows * 32, 256, 8), 256, 0, c->stream>>>(X->d, X->rows, wpr, d_P,
+                                                                                   (uint32_t)p, d_usage);
+    BIC_LAUNCH_CHECK(c);
+  }
+  k_init_finalize<<<bic_grid_for(c, p * wpr, 256, 4), 256, 0, c->stream>>>(d_P, d_hist, d_usage, (uint32_t)p, wpr, m, D->d);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_initialize_model_neighbor(bic_ctx* c, const bic_mat* X, bic_mat* D, bic_mat* A,
+                                                    uint64_t* rng_state) {
+  if (!c || !X || !D || !A || !rng_state) return BIC_ERR_INVALID;
+  const uint64_t p = D->rows;
+  std::vector<uint64_t> piv(p ? p : 1);
+  BIC_TRY(bic_draw_pivots(c, X, p, rng_state, piv.data(), nullptr));
+  return bic_initialize_model_neighbor_pivots(c, X, piv.data(), p, D, A);
+}

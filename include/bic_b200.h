@@ -1,0 +1,197 @@
+/*
+ * bic_b200.h -- C ABI of libbic_b200.so: the B200 (sm_100a) implementation of the encoder hot
+ * path of nacho-pancho/binary-image-compression (bit-packed binary matrix factorisation
+ * "bsvd" + Golomb / EG coding of the factors and the residual).
+ *
+ * The reference has no FFI (it is one C++ program): its plug points are the global
+ * function pointers of src/bsvd.h:104-125 and the classes of src/binmat.h, src/GolombCoder.h,
+ * src/eg.h. The host-side C++ shim that keeps those names (binary-image-compression_b200/host/)
+ * is a thin layer over the entry points below; each entry point cites the reference interface
+ * it stands in for (paths relative to /root/reference/).
+ *
+ * Conventions
+ *   - plain C: opaque handles, pointers and sizes; every call returns a bic_status.
+ *   - one caller thread per context; a context owns one CUDA stream; calls are ordered on it.
+ *     Calls that return values to the host synchronise that stream, the others are async.
+ *   - host matrices use the reference's word layout (src/binmat.h:114-116, src/binmat.cpp:140-149):
+ *     row-major uint64 words, ceil(cols/64) per row, bit j of a row at (1<<63) >> (j % 64).
+ *     Pad bits are ignored on upload and zero on download.
+ *   - device layout (private): row-major uint32 words, ceil(cols/32) per row, MSB first, pad
+ *     bits zero; 8x8/16x16/32x32 patches therefore occupy 8/32/128 contiguous bytes and a
+ *     32-atom coefficient row 4 bytes (the reference pads it to 8).
+ *   - there is NO CPU fallback: without a CUDA device bic_ctx_create fails with
+ *     BIC_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef BIC_B200_H
+#define BIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int bic_status;
+enum {
+  BIC_OK = 0,
+  BIC_ERR_INVALID = 1,   /* bad argument / shape mismatch (the reference asserts, src/binmat.cpp:465-469) */
+  BIC_ERR_CUDA = 2,      /* a CUDA runtime call failed; see bic_ctx_last_error */
+  BIC_ERR_NOMEM = 3,
+  BIC_ERR_CAPACITY = 4,  /* caller buffer too small; the needed size is still reported */
+  BIC_ERR_NO_DEVICE = 5,
+  BIC_ERR_CORRUPT = 6,   /* undecodable stream / container */
+  BIC_ERR_UNSUPPORTED = 7
+};
+
+typedef struct bic_ctx bic_ctx;       /* device + stream + scratch */
+typedef struct bic_mat bic_mat;       /* device bit matrix (stands in for binary_matrix, src/binmat.h:29) */
+typedef struct bic_stream bic_stream; /* device-resident coded bit stream + chunk index */
+
+/* ---------------------------------------------------------------- context */
+bic_status bic_ctx_create(int device, bic_ctx** out);
+/* same, but enqueue on a stream the caller owns (a cudaStream_t), e.g. torch's current stream */
+bic_status bic_ctx_create_on_stream(int device, void* cuda_stream, bic_ctx** out);
+bic_status bic_ctx_destroy(bic_ctx* ctx);
+bic_status bic_ctx_sync(bic_ctx* ctx);
+const char* bic_ctx_last_error(bic_ctx* ctx);
+const char* bic_status_string(bic_status s);
+void* bic_ctx_cuda_stream(bic_ctx* ctx);
+int bic_ctx_sm_count(bic_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t bic_ctx_launch_count(bic_ctx* ctx);
+/* device timers on the context's stream (cudaEvent pairs): ms between start and stop */
+bic_status bic_timer_start(bic_ctx* ctx);
+bic_status bic_timer_stop(bic_ctx* ctx, float* ms);
+/* pinned host memory for callers that want async H2D/D2H */
+bic_status bic_host_alloc(size_t bytes, void** out);
+bic_status bic_host_free(void* p);
+
+/* ---------------------------------------------------------------- matrices
+ * binary_matrix(rows, cols) / allocate / destroy: src/binmat.cpp:140-163, src/binmat.h:178.
+ * Unlike the reference (uninitialised words) a new matrix is all zero. */
+bic_status bic_mat_create(bic_ctx* ctx, uint64_t rows, uint64_t cols, bic_mat** out);
+bic_status bic_mat_destroy(bic_ctx* ctx, bic_mat* m);
+uint64_t bic_mat_rows(const bic_mat* m);   /* get_rows, src/binmat.h:84 */
+uint64_t bic_mat_cols(const bic_mat* m);   /* get_cols, src/binmat.h:87 */
+void* bic_mat_device_ptr(const bic_mat* m);
+uint64_t bic_mat_stride_words32(const bic_mat* m);
+/* host words in the reference layout <-> device */
+bic_status bic_mat_upload_words64(bic_ctx* ctx, bic_mat* m, const uint64_t* host_words);
+bic_status bic_mat_download_words64(bic_ctx* ctx, const bic_mat* m, uint64_t* host_words);
+/* P4 payload (rows of ceil(cols/8) bytes, MSB first; src/pbm.cpp:29-77) <-> device */
+bic_status bic_mat_upload_pbm(bic_ctx* ctx, bic_mat* m, const uint8_t* payload);
+bic_status bic_mat_download_pbm(bic_ctx* ctx, const bic_mat* m, uint8_t* payload);
+bic_status bic_mat_clear(bic_ctx* ctx, bic_mat* m);                       /* clear(), src/binmat.cpp:165-168 */
+bic_status bic_mat_copy(bic_ctx* ctx, const bic_mat* src, bic_mat* dst);  /* copy_to, src/binmat.cpp:195-197 */
+bic_status bic_mat_weight(bic_ctx* ctx, const bic_mat* m, uint64_t* w);   /* weight(), src/binmat.cpp:57-67 */
+bic_status bic_mat_dist(bic_ctx* ctx, const bic_mat* a, const bic_mat* b, uint64_t* d); /* dist, :499-512 */
+bic_status bic_mat_xor(bic_ctx* ctx, const bic_mat* a, const bic_mat* b, bic_mat* c);   /* add, :463-478 */
+
+/* ---------------------------------------------------------------- bsvd hot path */
+
+/* Patch extraction loop of the driver, src/bsvd_test.cpp:80-99 (copy_submatrix_to
+ * src/binmat.cpp:267-298, copy_vectorized_to :306-320, set_row :362-371).
+ * X must be ceil(rows/W)*ceil(cols/W) x W*W. Row-major patch order, zero padding, and the
+ * reference's read-through into the next raster row for edge tiles when W does not divide 64. */
+bic_status bic_extract_patches(bic_ctx* ctx, const bic_mat* raster, uint64_t W, bic_mat* X);
+/* inverse (set_vectorized + set_submatrix, src/bsvd_test.cpp:128-139): patches -> raster */
+bic_status bic_assemble_patches(bic_ctx* ctx, const bic_mat* X, uint64_t W, bic_mat* raster);
+
+/* GSL rand48 + gsl_rng_uniform_int as used by get_rng / initialize_model_neighbor,
+ * src/bsvd.cpp:8-15, :241. The 48-bit state lives in one uint64 owned by the caller. */
+void bic_rand48_seed(uint64_t* state, unsigned long seed);
+uint64_t bic_rand48_uniform_int(uint64_t* state, uint64_t n);
+
+/* Pivot draw of initialize_model_neighbor (src/bsvd.cpp:239-243): draws until p non-zero rows
+ * of X were accepted; consumes the generator exactly like the reference. The zero-row test
+ * runs on the device, the (serial) draw on the host. BIC_ERR_INVALID if X is all zero (the
+ * reference would never return). */
+bic_status bic_draw_pivots(bic_ctx* ctx, const bic_mat* X, uint64_t p, uint64_t* rng_state,
+                           uint64_t* pivots_out, uint64_t* ndraws_out);
+/* Body of initialize_model_neighbor for a given pivot list (src/bsvd.cpp:237-238, :244-262). */
+bic_status bic_initialize_model_neighbor_pivots(bic_ctx* ctx, const bic_mat* X, const uint64_t* pivots,
+                                                uint64_t p, bic_mat* D, bic_mat* A);
+/* initialize_model_neighbor(E, D, A), src/bsvd.cpp:227-267 (mi_algorithm_t, src/bsvd.h:104-106). */
+bic_status bic_initialize_model_neighbor(bic_ctx* ctx, const bic_mat* X, bic_mat* D, bic_mat* A,
+                                         uint64_t* rng_state);
+
+/* update_coefficients_omp / _basic (cu_algorithm_t, src/bsvd.h:108-110; src/bsvd.cpp:1029-1107,
+ * :399-460). E and A are updated in place; *changed = rows that changed (the exact count of the
+ * serial variant; the OpenMP variant's own count is racy, src/bsvd.cpp:1096). */
+bic_status bic_update_coefficients(bic_ctx* ctx, bic_mat* E, const bic_mat* D, bic_mat* A, uint64_t* changed);
+
+/* update_dictionary_steepest (du_algorithm_t, src/bsvd.h:112-114; src/bsvd.cpp:463-527): atoms
+ * strictly in order, E patched after every changed atom. *changed = atoms that changed. */
+bic_status bic_update_dictionary_steepest(bic_ctx* ctx, bic_mat* E, bic_mat* D, const bic_mat* A, uint64_t* changed);
+
+/* E = A*D xor X: mul(A,false,D,false,E); add(E,X,E)  (src/binmat.cpp:516-543, :463-478), as in
+ * src/bsvd.cpp:1219-1220 and src/bsvd_test.cpp:153-154. */
+bic_status bic_residual(bic_ctx* ctx, const bic_mat* X, const bic_mat* A, const bic_mat* D, bic_mat* E);
+
+/* learn_model_traditional(X, E, D, A) (ml_algorithm_t, src/bsvd.h:116-119; src/bsvd.cpp:1215-1244).
+ * trace (optional) receives {changed_coefs, changed_atoms} per iteration, up to trace_cap. */
+bic_status bic_learn_model_traditional(bic_ctx* ctx, const bic_mat* X, bic_mat* E, bic_mat* D, bic_mat* A,
+                                       uint64_t* iterations, uint64_t* trace, uint64_t trace_cap);
+
+/* ---------------------------------------------------------------- entropy coding
+ * A coded stream is a byte string: stream bit t is in byte t/8 at mask 0x80 >> (t%8)
+ * (writeBits / readBits order, src/GolombCoder.cpp:22-25, src/GolombDecoder.cpp:15-23). */
+enum { BIC_CODER_GOLOMB = 1, BIC_CODER_EG = 2 };
+
+bic_status bic_stream_create(bic_ctx* ctx, bic_stream** out);
+bic_status bic_stream_destroy(bic_ctx* ctx, bic_stream* s);
+typedef struct {
+  uint32_t coder;         /* BIC_CODER_* */
+  uint32_t chunk_samples; /* samples per decoder chunk (Golomb) */
+  uint64_t rows, cols;    /* shape of the coded matrix */
+  uint64_t bitcount;      /* == GolombCoder::bitcount / EGCoder::bitcount over the same input */
+  uint64_t nsamples;      /* Golomb: popcount + 1 */
+  uint64_t nchunks;       /* entries of the chunk index (2 uint64 each) */
+} bic_stream_info;
+bic_status bic_stream_get_info(const bic_stream* s, bic_stream_info* info);
+/* bytes: ceil(bitcount/8); index: 2*nchunks uint64 {code bit offset, decoded bit position} */
+bic_status bic_stream_download(bic_ctx* ctx, const bic_stream* s, uint8_t* bytes, uint64_t cap_bytes,
+                               uint64_t* index, uint64_t cap_index_entries);
+bic_status bic_stream_upload(bic_ctx* ctx, bic_stream* s, const bic_stream_info* info,
+                             const uint8_t* bytes, const uint64_t* index);
+
+/* GolombCoder (src/GolombCoder.h:19-28, src/GolombCoder.cpp:13-34, state src/Golomb.h:12-29)
+ * applied to the zero-run lengths of M read row-major (a virtual one closes the last run):
+ * run-length extraction -> adaptive k per sample -> codeword lengths -> device-wide prefix sum
+ * of bit offsets -> bit scatter. Byte-identical to the serial coder writing k remainder bits,
+ * (x>>k) zeros and a one per sample. */
+bic_status bic_golomb_encode(bic_ctx* ctx, const bic_mat* M, uint32_t chunk_samples, bic_stream* out);
+/* count only: the reference's GolombCoder::bitcount for the same samples */
+bic_status bic_golomb_bitcount(bic_ctx* ctx, const bic_mat* M, uint64_t* bitcount, uint64_t* nsamples);
+/* chunk-parallel decoder (GolombDecoder::decodeSample, src/GolombDecoder.cpp:15-40, unsigned samples) */
+bic_status bic_golomb_decode(bic_ctx* ctx, const bic_stream* s, bic_mat* M);
+
+/* EGCoder::codeRun (src/eg.h:19-27, src/eg.cpp:20-37) over each row's zero runs: a run broken
+ * by a one has eol=false, the row's last run eol=true. */
+bic_status bic_eg_encode(bic_ctx* ctx, const bic_mat* M, bic_stream* out);
+bic_status bic_eg_decode(bic_ctx* ctx, const bic_stream* s, bic_mat* M);
+
+/* ---------------------------------------------------------------- whole encoder (what bsvd_test's main does,
+ * src/bsvd_test.cpp:56-125, with the three PBM dumps replaced by Golomb streams) */
+typedef struct {
+  uint64_t rows, cols, W, K;  /* raster shape, patch width, atoms */
+  uint64_t n, m;              /* patches, bits per patch */
+  uint64_t iterations;        /* learn_model_traditional's return value */
+  uint64_t weight_E, weight_A, weight_D;
+  uint64_t bits_D, bits_A, bits_E; /* Golomb bit counts */
+  uint64_t container_bytes;
+} bic_encode_info;
+
+/* raster: P4 payload on the host. out: container (header + 3 streams + chunk indexes). */
+bic_status bic_encode_raster(bic_ctx* ctx, const uint8_t* pbm_payload, uint64_t rows, uint64_t cols,
+                             uint64_t W, uint64_t K, unsigned long seed,
+                             uint8_t* out, uint64_t cap_bytes, bic_encode_info* info);
+/* inverse: container -> P4 payload (decode D, A, E; X = A*D xor E; patches -> raster) */
+bic_status bic_decode_raster(bic_ctx* ctx, const uint8_t* container, uint64_t container_bytes,
+                             uint8_t* pbm_payload, uint64_t cap_bytes, uint64_t* rows, uint64_t* cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIC_B200_H */

@@ -1,0 +1,276 @@
+"""GPU parity tests: every call goes through the C ABI (libbic_b200.so) and is compared, bit for
+bit, with the oracle (oracle/bic_oracle.c) on the same seeded inputs and with the golden vectors
+generated from the compiled reference (tests/golden/)."""
+import importlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+FIT_CASES = sorted(p.stem for p in GOLDEN.glob("fit_*.npz"))
+
+
+@pytest.fixture(scope="module")
+def bic():
+    return importlib.import_module("binary-image-compression_b200")
+
+
+@pytest.fixture(scope="module")
+def ctx(bic):
+    c = bic.Context(0)
+    yield c
+    c.close()
+
+
+def wpr(c):
+    return (c + 63) // 64
+
+
+# ---------------------------------------------------------------- layout
+@pytest.mark.parametrize("rows,cols", [(1, 1), (5, 31), (7, 32), (9, 33), (3, 64), (11, 100), (64, 256), (17, 1024), (2, 2481)])
+def test_upload_download_roundtrip(ctx, synth, rows, cols):
+    rng = np.random.default_rng(rows * 7 + cols)
+    bits = (rng.random((rows, cols)) < 0.4).astype(np.uint8)
+    w = synth.pack_rows(bits)
+    dirty = w.copy()
+    if cols % 64:
+        dirty[:, -1] |= np.uint64((1 << (64 - cols % 64)) - 1)  # stale pad bits must be ignored
+    m = ctx.matrix(rows, cols, dirty)
+    assert np.array_equal(m.download(), w)
+    assert m.weight() == int(bits.sum())
+    p = synth.pbm_bytes(bits)
+    m2 = ctx.matrix(rows, cols)
+    m2.upload_pbm(p)
+    assert np.array_equal(m2.download(), w)
+    assert np.array_equal(m2.download_pbm(), p)
+    m.destroy(); m2.destroy()
+
+
+# ---------------------------------------------------------------- golden vectors from the compiled reference
+@pytest.mark.parametrize("name", FIT_CASES)
+def test_fit_matches_reference_golden(ctx, name):
+    g = np.load(GOLDEN / f"{name}.npz")
+    rows, cols, W, K = int(g["rows"]), int(g["cols"]), int(g["W"]), int(g["K"])
+    m = W * W
+    I = ctx.matrix(rows, cols, g["raster"])
+    X = ctx.extract_patches(I, W)
+    assert np.array_equal(X.download(), g["X"])
+    n = X.rows
+    rng = ctx.rand48(int(g["rseed"]))
+    piv, ndraws = ctx.draw_pivots(X, K, rng)
+    assert ndraws == len(g["draws"])
+    D, A, E = ctx.matrix(K, m), ctx.matrix(n, K), ctx.matrix(n, m)
+    ctx.initialize_model_neighbor_pivots(X, piv, D, A)
+    assert np.array_equal(D.download(), g["D0"])
+    assert A.weight() == 0
+    ctx.residual(X, A, D, E)
+    assert np.array_equal(E.download(), g["X"])
+    cc1 = ctx.update_coefficients(E, D, A)
+    assert cc1 == int(g["cc1"])
+    assert np.array_equal(E.download(), g["E1"]) and np.array_equal(A.download(), g["A1"])
+    ca1 = ctx.update_dictionary(E, D, A)
+    assert ca1 == int(g["ca1"])
+    assert np.array_equal(E.download(), g["E2"]) and np.array_equal(D.download(), g["D2"])
+    # whole learner from the initial model
+    D.upload(g["D0"]); A.clear()
+    iters, trace = ctx.learn_model_traditional(X, E, D, A)
+    assert iters == int(g["iters"])
+    assert np.array_equal(D.download(), g["D"])
+    assert np.array_equal(A.download(), g["A"])
+    assert np.array_equal(E.download(), g["E"])
+    assert E.weight() == int(g["weightE"])
+    for mm in (I, X, D, A, E):
+        mm.destroy()
+
+
+# ---------------------------------------------------------------- seeded inputs vs the oracle
+FIT_SHAPES = [  # rows, cols, W, K, seed
+    (400, 300, 8, 32, 1),
+    (333, 257, 8, 7, 2),
+    (512, 384, 16, 64, 3),
+    (260, 200, 16, 256, 4),
+    (384, 512, 32, 32, 5),
+    (200, 190, 12, 10, 6),      # W does not divide 64
+    (130, 128, 24, 6, 7),       # edge tiles read through into the next raster row
+    (64, 64, 4, 3, 8),
+    (97, 45, 5, 4, 9),
+]
+
+
+@pytest.mark.parametrize("rows,cols,W,K,seed", FIT_SHAPES)
+def test_fit_vs_oracle(ctx, oracle, synth, rows, cols, W, K, seed):
+    page = synth.structured_page(rows, cols, seed=seed, salt=0.01)
+    Iw = synth.pack_rows(page)
+    m = W * W
+    Xo = oracle.extract_patches(Iw, rows, cols, W)
+    I = ctx.matrix(rows, cols, Iw)
+    X = ctx.extract_patches(I, W)
+    assert np.array_equal(X.download(), Xo)
+    n = X.rows
+    # pivots: same RNG stream on both sides
+    r = oracle.rng(1234 + seed)
+    piv_o, nd_o = oracle.draw_pivots(Xo, m, K, r)
+    rng = ctx.rand48(1234 + seed)
+    piv, nd = ctx.draw_pivots(X, K, rng)
+    assert nd == nd_o and np.array_equal(piv, piv_o)
+    Do, Ao = oracle.init_neighbor_pivots(Xo, m, K, piv_o)
+    D, A, E = ctx.matrix(K, m), ctx.matrix(n, K), ctx.matrix(n, m)
+    ctx.initialize_model_neighbor_pivots(X, piv, D, A)
+    assert np.array_equal(D.download(), Do)
+    # step by step, comparing after every call
+    Eo = oracle.residual(Xo, Ao, Do, m, K)
+    ctx.residual(X, A, D, E)
+    assert np.array_equal(E.download(), Eo)
+    for it in range(3):
+        cco = oracle.update_coefficients(Eo, Do, Ao, m, K)
+        cc = ctx.update_coefficients(E, D, A)
+        assert cc == cco, f"iteration {it}"
+        assert np.array_equal(E.download(), Eo) and np.array_equal(A.download(), Ao)
+        cao = oracle.update_dictionary(Eo, Do, Ao, m, K)
+        ca = ctx.update_dictionary(E, D, A)
+        assert ca == cao, f"iteration {it}"
+        assert np.array_equal(E.download(), Eo) and np.array_equal(D.download(), Do)
+    # whole learner
+    Do2, Ao2 = oracle.init_neighbor_pivots(Xo, m, K, piv_o)
+    Eo2, ito, tro = oracle.learn_traditional(Xo, Do2, Ao2, m, K)
+    ctx.initialize_model_neighbor_pivots(X, piv, D, A)
+    it, tr = ctx.learn_model_traditional(X, E, D, A)
+    assert it == ito
+    assert np.array_equal(tr, tro)
+    assert np.array_equal(D.download(), Do2) and np.array_equal(A.download(), Ao2) and np.array_equal(E.download(), Eo2)
+    # patches -> raster is the inverse of extraction on the in-bounds pixels
+    R = ctx.assemble_patches(X, W, rows, cols)
+    assert np.array_equal(R.download(), Iw)
+    for mm in (I, X, D, A, E, R):
+        mm.destroy()
+
+
+def test_matrix_mode_wide_rows(ctx, oracle, synth):
+    """-I 0 (rows are the samples, bsvd_test.cpp:101-106) with m = 1100 > 1024: wide-row kernels"""
+    page = synth.structured_page(300, 1100, seed=31, salt=0.01)
+    Xo = synth.pack_rows(page)
+    m, K = 1100, 9
+    piv, _ = oracle.draw_pivots(Xo, m, K, oracle.rng(5))
+    Do, Ao = oracle.init_neighbor_pivots(Xo, m, K, piv)
+    X = ctx.matrix(300, m, Xo)
+    D, A, E = ctx.matrix(K, m), ctx.matrix(300, K), ctx.matrix(300, m)
+    ctx.initialize_model_neighbor_pivots(X, piv, D, A)
+    assert np.array_equal(D.download(), Do)
+    Eo, ito, tro = oracle.learn_traditional(Xo, Do, Ao, m, K)
+    it, tr = ctx.learn_model_traditional(X, E, D, A)
+    assert it == ito and np.array_equal(tr, tro)
+    assert np.array_equal(D.download(), Do) and np.array_equal(A.download(), Ao) and np.array_equal(E.download(), Eo)
+
+
+# ---------------------------------------------------------------- coders
+CODER_SHAPES = [(1, 1, 0.0), (1, 1, 1.0), (1, 32, 0.0), (3, 64, 0.5), (17, 100, 0.05), (64, 32, 0.5), (5, 333, 0.0),
+                (3, 70, 1.0), (300, 256, 0.005), (1000, 64, 0.02), (2000, 1024, 0.1), (1, 200000, 0.001), (4096, 32, 0.3)]
+
+
+@pytest.mark.parametrize("rows,cols,rho", CODER_SHAPES)
+def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho):
+    rng = np.random.default_rng(rows * 31 + cols)
+    bits = (rng.random((rows, cols)) < rho).astype(np.uint8)
+    Mw = synth.pack_rows(bits)
+    so, nbits_o, ns_o = oracle.golomb_encode(Mw, cols)
+    M = ctx.matrix(rows, cols, Mw)
+    bc, ns = ctx.golomb_bitcount(M)
+    assert (bc, ns) == (nbits_o, ns_o)
+    for chunk in (256, 7):
+        s = ctx.golomb_encode(M, chunk_samples=chunk)
+        si = s.info
+        assert si.bitcount == nbits_o and si.nsamples == ns_o
+        by, idx = s.download()
+        assert np.array_equal(by, so)
+        # the serial decoder reads the parallel encoder's stream
+        assert np.array_equal(oracle.golomb_decode(by, si.bitcount, rows, cols), Mw)
+        # the chunk-parallel decoder reads it too
+        M2 = ctx.matrix(rows, cols)
+        ctx.golomb_decode(s, M2)
+        assert np.array_equal(M2.download(), Mw)
+        M2.destroy(); s.destroy()
+    M.destroy()
+
+
+@pytest.mark.parametrize("rows,cols,rho", CODER_SHAPES[:11])
+def test_eg_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho):
+    rng = np.random.default_rng(rows * 17 + cols)
+    bits = (rng.random((rows, cols)) < rho).astype(np.uint8)
+    Mw = synth.pack_rows(bits)
+    so, nbits_o = oracle.eg_encode(Mw, cols)
+    M = ctx.matrix(rows, cols, Mw)
+    s = ctx.eg_encode(M)
+    assert s.info.bitcount == nbits_o
+    by, _ = s.download()
+    assert np.array_equal(by, so)
+    M2 = ctx.matrix(rows, cols)
+    ctx.eg_decode(s, M2)
+    assert np.array_equal(M2.download(), Mw)
+    for x in (M, M2, s):
+        x.destroy()
+
+
+def test_golomb_decode_rejects_corrupt_stream(ctx, bic, synth):
+    rng = np.random.default_rng(3)
+    bits = (rng.random((50, 64)) < 0.1).astype(np.uint8)
+    M = ctx.matrix(50, 64, synth.pack_rows(bits))
+    s = ctx.golomb_encode(M)
+    by, idx = s.download()
+    info = s.info
+    bad = by.copy()
+    bad[: len(bad) // 2] = 0
+    s2 = ctx.stream()
+    s2.upload(info, bad, idx)
+    with pytest.raises(bic.BicError):
+        ctx.golomb_decode(s2, ctx.matrix(50, 64))
+
+
+# ---------------------------------------------------------------- whole encoder: lossless round trip
+@pytest.mark.parametrize("rows,cols,W,K", [(300, 200, 8, 16), (256, 256, 16, 32), (100, 90, 12, 5)])
+def test_encode_decode_raster_roundtrip(ctx, oracle, synth, rows, cols, W, K):
+    page = synth.structured_page(rows, cols, seed=rows + W, salt=0.01)
+    payload = synth.pbm_bytes(page)
+    cont, info = ctx.encode_raster(payload, rows, cols, W, K, seed=34503498)
+    # same fit as the oracle, same Golomb bit counts
+    Iw = synth.pack_rows(page)
+    Xo = oracle.extract_patches(Iw, rows, cols, W)
+    Do, Ao, _ = oracle.init_neighbor(Xo, W * W, K, 34503498)
+    Eo, ito, _ = oracle.learn_traditional(Xo, Do, Ao, W * W, K)
+    assert info.iterations == ito
+    assert info.weight_E == oracle.weight(Eo, W * W)
+    assert info.bits_D == oracle.golomb_encode(Do, W * W)[1]
+    assert info.bits_A == oracle.golomb_encode(Ao, K)[1]
+    assert info.bits_E == oracle.golomb_encode(Eo, W * W)[1]
+    out, r, c = ctx.decode_raster(cont)
+    assert (r, c) == (rows, cols)
+    assert np.array_equal(out, payload)
+
+
+# ---------------------------------------------------------------- full-size properties (no oracle at this size)
+def test_a4_page_properties(ctx, synth):
+    """config 1 shape: A4 @300dpi, 8x8 patches, 32 atoms. Size-independent checks: the learner's
+    fixed point (a further pass changes nothing), E == A*D xor X, monotone residual weight,
+    and the lossless container round trip."""
+    rows, cols, W, K = 3508, 2480, 8, 32
+    page = synth.structured_page(rows, cols, seed=7)
+    payload = synth.pbm_bytes(page)
+    I = ctx.matrix(rows, cols)
+    I.upload_pbm(payload)
+    X = ctx.extract_patches(I, W)
+    n, m = X.rows, W * W
+    assert n == 136090
+    D, A, E, E2 = ctx.matrix(K, m), ctx.matrix(n, K), ctx.matrix(n, m), ctx.matrix(n, m)
+    rng = ctx.rand48(34503498)
+    ctx.initialize_model_neighbor(X, D, A, rng)
+    iters, tr = ctx.learn_model_traditional(X, E, D, A)
+    assert iters >= 2 and tr[-1].sum() == 0
+    assert ctx.update_coefficients(E, D, A) == 0 and ctx.update_dictionary(E, D, A) == 0
+    ctx.residual(X, A, D, E2)
+    assert np.array_equal(E2.download(), E.download())
+    assert E.weight() < X.weight()
+    cont, info = ctx.encode_raster(payload, rows, cols, W, K)
+    assert info.iterations == iters and info.weight_E == E.weight()
+    out, r, c = ctx.decode_raster(cont)
+    assert np.array_equal(out, payload)
