@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixel/s encoded (bsvd fit + Golomb coding of D, A, E), BASELINE.json's metric.
+
+Workload (config.workload): BASELINE.json configs[1] -- a synthetic 16-bit 8192x8192 PGM split into
+its 16 bitplanes (src/bitplane_tool.cpp:24-39, host side), each plane patch-factorised
+(extract -> initialize_model_neighbor -> learn_model_traditional to convergence) and its D, A, E
+Golomb coded. One step = all 16 planes = 16 * 8192 * 8192 pixels. The config does not fix the
+patch size / atom count; the default is 8x8 / 32 atoms (configs[0]'s), `--patch-width 16 --atoms 256`
+runs the other pair SURVEY 8 names.
+
+  value : planes already resident in HBM (device rasters) when the timed region starts
+  e2e   : through bic_encode_raster with HOST buffers -- pinned P4 payloads in, container bytes out,
+          H2D and D2H inside the timed region
+  roofline : dominant kernel, timed live with CUDA events on the library's stream (bic_prof_*)
+  cpu_baseline / --impl reference : the reference's own code (oracle/_ref, compiled from
+          /root/reference by oracle/Makefile) on this box's host cores, on a bounded crop
+
+Multi-GPU (torchrun, one rank per GPU): every rank encodes its own 16-plane image (planes are
+independent fits: no data-path collective), weak scaling; timing is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "Mpixel/s encoded (bsvd fit+Golomb/EG)"
+UNIT = "Mpixel/s"
+SEED = 34503498  # the reference's default random_seed, src/bsvd.cpp:23
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=8192)
+    ap.add_argument("--planes", type=int, default=16)
+    ap.add_argument("--patch-width", type=int, default=8)
+    ap.add_argument("--atoms", type=int, default=32)
+    ap.add_argument("--cpu-crop", type=int, default=2048, help="crop edge for the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks (nvidia-smi sampled DURING the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, ln in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample fell inside the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm (oracle/_ref = the reference's own code)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(synth, args, planes, crop, seed_img, budget_s=30.0):
+    """Runs the reference fit (bsvd_test.cpp's sequence via ref_fit_timed) + its serial GolombCoder
+    over D, A, E on `crop` x `crop` crops of the given planes. Returns (Mpixel/s, dict)."""
+    from oracle_bindings import load_reference, Oracle
+    ref = load_reference()
+    kind = "reference"
+    if ref is None:
+        kind = "port"
+        orc = Oracle()
+    W, K = args.patch_width, args.atoms
+    cores = ref.max_threads() if ref is not None else 1
+    img = synth.smooth_pgm16(crop, crop, seed=seed_img)
+    t_total, px, done = 0.0, 0, 0
+    phases = np.zeros(6)
+    for b in planes:
+        I = synth.pack_rows(synth.bitplane(img, b))
+        t0 = time.perf_counter()
+        if ref is not None:
+            it, times, (D, A, E) = ref.fit_timed(I, crop, crop, W, K, SEED, want_outputs=True)
+            phases += np.array(times)
+            for M, c in ((D, W * W), (A, K), (E, W * W)):
+                ref.golomb_matrix(M, c)
+        else:
+            X = orc.extract_patches(I, crop, crop, W)
+            D, A, _ = orc.init_neighbor(X, W * W, K, SEED)
+            E, it, _ = orc.learn_traditional(X, D, A, W * W, K)
+            for M, c in ((D, W * W), (A, K), (E, W * W)):
+                orc.golomb_encode(M, c)
+        t_total += time.perf_counter() - t0
+        px += crop * crop
+        done += 1
+        if t_total > budget_s:
+            break
+    return px / 1e6 / t_total, {
+        "kind": kind, "cores": cores,
+        "sample": f"{done} bitplanes of a {crop}x{crop} crop of the same synthetic PGM, {W}x{W} patches, {K} atoms, "
+                  f"fit to convergence + serial GolombCoder over D,A,E ({t_total:.1f} s of CPU)",
+        "seconds": t_total,
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bic = importlib.import_module("binary-image-compression_b200")
+    synth = bic.synth
+    planes = list(range(args.planes))
+    vals = []
+    info = None
+    for s in range(args.warmup + args.steps):
+        v, info = cpu_reference_sample(synth, args, planes, args.cpu_crop, 2, budget_s=1e9)
+        if s >= args.warmup:
+            vals.append((v, info["seconds"]))
+        if sum(x[1] for x in vals) > 150:
+            break
+    px = len(planes) * args.cpu_crop * args.cpu_crop / 1e6
+    secs = float(np.mean([x[1] for x in vals]))
+    value = px / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "patch_width": args.patch_width, "atoms": args.atoms,
+                   "note": "CPU reference arm: each step is a bounded sample of the workload (see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return (f"configs[1]: 16-bit {args.size}x{args.size} synthetic PGM -> {args.planes} bitplanes, each "
+            f"{args.patch_width}x{args.patch_width}-patch / {args.atoms}-atom bsvd fit to convergence + Golomb coding of D, A, E")
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic bytes per launch, for the roofline of whichever kernel dominates
+# ---------------------------------------------------------------------------------------------
+def algorithmic_bytes(kernel: str, rows, cols, n, m, p):
+    t = {
+        "k_update_dictionary": n * (2 * m + p) / 8,        # read E, A once + write E once
+        "k_update_coefficients": n * 2 * (m + p) / 8,      # read + write E row and A row
+        "k_transpose_bits": 2 * n * p / 8,
+        "k_extract": 2 * rows * cols / 8,
+        "k_residual": n * (2 * m + p) / 8,
+        "k_col_hist": n * m / 8,
+        "k_pivot_usage": n * m / 8,
+        "k_row_nonzero": n * m / 8,
+        "k_pbm_to_dev": 2 * rows * cols / 8,
+    }
+    return t.get(kernel)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    bic = importlib.import_module("binary-image-compression_b200")
+    synth = bic.synth
+    ctx = bic.Context(local_rank)
+    S, P, W, K = args.size, args.planes, args.patch_width, args.atoms
+    rows = cols = S
+    n = ((rows + W - 1) // W) * ((cols + W - 1) // W)
+    m = W * W
+    bpr = (cols + 7) // 8
+    plane_bytes = rows * bpr
+
+    # ---- synthetic data: rank r owns its own image (rows offset by r * S in the infinite field)
+    dev = torch.device("cuda", local_rank)
+    img = synth.smooth_pgm16(rows, cols, seed=2, y0=rank * S, device=dev)
+    host_planes = ctx.pinned(P * plane_bytes).reshape(P, rows, bpr)
+    rasters = []
+    for b in range(P):
+        pay = synth.pbm_bytes_torch(synth.bitplane(img, b)).cpu().numpy()
+        host_planes[b] = pay
+        r = ctx.matrix(rows, cols)
+        r.upload_pbm(host_planes[b])
+        rasters.append(r)
+    del img
+    torch.cuda.empty_cache()
+
+    X, E = ctx.matrix(n, m), ctx.matrix(n, m)
+    D, A = ctx.matrix(K, m), ctx.matrix(n, K)
+    streams = [ctx.stream() for _ in range(3)]
+    L = ctx.L
+    import ctypes as C
+    stats = {"iters": [], "bits": 0}
+
+    def step_resident(record=False):
+        total_bits = 0
+        its = []
+        for b in range(P):
+            ctx._ck(L.bic_extract_patches(ctx.h, rasters[b].h, W, X.h))
+            rng = ctx.rand48(SEED)
+            ctx._ck(L.bic_initialize_model_neighbor(ctx.h, X.h, D.h, A.h, C.byref(rng)))
+            it = C.c_uint64(0)
+            ctx._ck(L.bic_learn_model_traditional(ctx.h, X.h, E.h, D.h, A.h, C.byref(it), None, 0))
+            its.append(int(it.value))
+            for M, s in zip((D, A, E), streams):
+                ctx._ck(L.bic_golomb_encode(ctx.h, M.h, 256, s.h))
+                if record:
+                    total_bits += s.info.bitcount
+        if record:
+            stats["iters"], stats["bits"] = its, total_bits
+
+    out_buf = ctx.pinned(2 * plane_bytes + (1 << 20))
+    e2e_stats = {"d2h": 0}
+
+    def step_e2e():
+        d2h = 0
+        for b in range(P):
+            _, info = ctx.encode_raster(host_planes[b], rows, cols, W, K, seed=SEED, out=out_buf)
+            d2h += int(info.container_bytes)
+        e2e_stats["d2h"] = d2h
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident timing
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_resident(record=True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = ctx.launches
+    barrier()
+    t_wall0 = time.time()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_resident()
+    ms = ctx.timer_stop()
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms_per_step = max_over_ranks(ms / args.steps)
+    px_step = P * rows * cols / 1e6  # Mpixel per rank per step
+    value = world * px_step / (ms_per_step / 1e3)
+
+    # ---- e2e timing (host buffers, H2D + D2H inside)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_e2e()
+    ms_e2e = ctx.timer_stop()
+    barrier()
+    ms_e2e_step = max_over_ranks(ms_e2e / args.steps)
+    e2e_value = world * px_step / (ms_e2e_step / 1e3)
+
+    # ---- per-kernel device times over the same steps -> roofline of the dominant kernel
+    ctx.prof_reset()
+    ctx.prof_enable(True)
+    for _ in range(args.steps):
+        step_resident()
+    ctx.prof_enable(False)
+    prof = ctx.prof_stats()
+    tot_ms = sum(v[1] for v in prof.values()) or 1.0
+    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    dom_name, (dom_n, dom_ms) = dom
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ab = algorithmic_bytes(dom_name, rows, cols, n, m, K)
+    avg_ms = dom_ms / dom_n
+    achieved = (ab / (avg_ms / 1e3)) / 1e9 if ab else None
+    traffic = None
+    tfile = ROOT / "profiles" / "dominant_kernel_traffic.json"
+    if tfile.exists():
+        try:
+            tj = json.loads(tfile.read_text())
+            if tj.get("kernel") == dom_name and tj.get("workload") == f"{S}x{S}/{W}/{K}":
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {
+        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": avg_ms,
+        "launches_per_step": dom_n / args.steps, "share_of_kernel_time": dom_ms / tot_ms,
+        "kernel_time_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+    }
+
+    # ---- CPU baseline (rank 0, N == 1): the reference's own code on a bounded crop
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = cpu_reference_sample(synth, args, list(range(P)), args.cpu_crop, 2)
+            cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+        except Exception as ex:  # the checker missing must not void the GPU number
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"{type(ex).__name__}: {ex}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "patch_width": W, "atoms": K, "patches_per_plane": n,
+                       "parallelism": f"{world} rank(s), one 16-plane image per rank, no data-path collective",
+                       "l2_policy": f"inputs larger than L2: {P} planes x {plane_bytes >> 20} MiB rasters + X/E/A "
+                                    f"({(2 * n * m + n * K) // 8 >> 20} MiB per plane) cycle through a 126 MB L2",
+                       "iterations_per_plane": stats["iters"], "golomb_bits_per_step": stats["bits"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e_step,
+                    "h2d_bytes_per_step": P * plane_bytes, "d2h_bytes_per_step": e2e_stats["d2h"]},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,9 @@ def lib() -> C.CDLL:
         "bic_ctx_sync": [_vp],
         "bic_timer_start": [_vp],
         "bic_timer_stop": [_vp, C.POINTER(C.c_float)],
+        "bic_prof_enable": [_vp, C.c_int],
+        "bic_prof_reset": [_vp],
+        "bic_prof_get": [_vp, C.c_int, C.POINTER(C.c_char_p), _u64p, C.POINTER(C.c_double)],
         "bic_host_alloc": [C.c_size_t, C.POINTER(_vp)],
         "bic_host_free": [_vp],
         "bic_mat_create": [_vp, _u64, _u64, C.POINTER(_vp)],
@@ -117,6 +120,8 @@ def lib() -> C.CDLL:
         f = getattr(L, name)
         f.argtypes = args
         f.restype = C.c_int
+    L.bic_prof_kernel_count.argtypes = []
+    L.bic_prof_kernel_count.restype = C.c_int
     L.bic_ctx_last_error.argtypes = [_vp]
     L.bic_ctx_last_error.restype = C.c_char_p
     L.bic_status_string.argtypes = [C.c_int]
@@ -277,6 +282,36 @@ class Context:
         ms = C.c_float(0)
         self._ck(self.L.bic_timer_stop(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def prof_enable(self, on: bool):
+        self._ck(self.L.bic_prof_enable(self.h, 1 if on else 0))
+
+    def prof_reset(self):
+        self._ck(self.L.bic_prof_reset(self.h))
+
+    def prof_stats(self) -> dict:
+        """{kernel name: (launches, total device ms)} for kernels launched while profiling was on"""
+        out = {}
+        for k in range(self.L.bic_prof_kernel_count()):
+            name, n, ms = C.c_char_p(), _u64(0), C.c_double(0)
+            self._ck(self.L.bic_prof_get(self.h, k, C.byref(name), C.byref(n), C.byref(ms)))
+            if n.value:
+                key = name.value.decode()
+                pn, pms = out.get(key, (0, 0.0))
+                out[key] = (pn + int(n.value), pms + float(ms.value))
+        return out
+
+    def pinned(self, nbytes: int) -> np.ndarray:
+        """uint8 array backed by page-locked host memory (kept alive by the context)"""
+        p = _vp()
+        st = self.L.bic_host_alloc(nbytes, C.byref(p))
+        if st != BIC_OK:
+            raise BicError(st, "pinned allocation")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append((p, buf))
+        return arr
 
     # ---- matrices
     def matrix(self, rows, cols, words64=None) -> Matrix:

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "bic_b200.h"
 
@@ -37,6 +38,18 @@ struct bic_stream {
   size_t cap_index = 0;         // in uint64 entries
 };
 
+// kernels of the library, for the per-kernel device timers (bic_prof_*)
+enum bic_kernel_id {
+  KID_WORDS64_TO_DEV = 0, KID_DEV_TO_WORDS64, KID_PBM_TO_DEV, KID_DEV_TO_PBM, KID_WEIGHT, KID_XOR,
+  KID_EXTRACT, KID_ASSEMBLE, KID_ROW_NONZERO, KID_GATHER_ROWS, KID_COL_HIST, KID_PIVOT_USAGE, KID_INIT_FINALIZE,
+  KID_UPDATE_COEF, KID_RESIDUAL, KID_TRANSPOSE_BITS, KID_UPDATE_DICT,
+  KID_COMPACT_ROWS, KID_EXPAND_ROWS, KID_GOL_TILE_COUNTS, KID_GOL_SCAN_A, KID_GOL_LENGTHS, KID_GOL_SCAN_B,
+  KID_GOL_SCATTER, KID_GOL_DECODE, KID_EG_FIRST, KID_EG_FILL, KID_EG_ENCODE, KID_EG_DECODE,
+  KID_COUNT
+};
+
+struct bic_prof_rec { int kid; cudaEvent_t e0, e1; };
+
 struct bic_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -52,7 +65,17 @@ struct bic_ctx {
   // grow-only scratch areas
   bic_scratch staging;    // host-layout staging for uploads/downloads
   bic_scratch work[6];    // per-algorithm work buffers
+  // optional per-launch device timers
+  bool prof_on = false;
+  std::vector<bic_prof_rec> prof_recs;
+  std::vector<cudaEvent_t> prof_free;
+  double prof_ms[KID_COUNT] = {0};
+  uint64_t prof_n[KID_COUNT] = {0};
 };
+
+void bic_prof_begin(bic_ctx* c, int kid);
+void bic_prof_end(bic_ctx* c);
+#define BIC_PROF(ctx, kid) do { if ((ctx)->prof_on) bic_prof_begin((ctx), (kid)); } while (0)
 
 #define BIC_CUDA(ctx, expr)                                                              \
   do {                                                                                   \
@@ -72,6 +95,7 @@ struct bic_ctx {
 #define BIC_LAUNCH_CHECK(ctx)                                   \
   do {                                                          \
     (ctx)->launches++;                                          \
+    if ((ctx)->prof_on) bic_prof_end(ctx);                      \
     BIC_CUDA(ctx, cudaGetLastError());                          \
   } while (0)
 

@@ -495,6 +495,7 @@ static bic_status dense_stream(bic_ctx* c, const bic_mat* M, const uint32_t** S,
   if ((M->cols & 31) == 0) { *S = M->d; return BIC_OK; }
   BIC_TRY(bic_scratch_reserve(c, &c->work[4], (size_t)(*T) * 4 + 16));
   if (*T) {
+    BIC_PROF(c, KID_COMPACT_ROWS);
     k_compact_rows<<<bic_grid_for(c, *T, 256, 8), 256, 0, c->stream>>>(M->d, M->cols, M->wpr, N, (uint32_t*)c->work[4].p, *T);
     BIC_LAUNCH_CHECK(c);
   }
@@ -521,13 +522,17 @@ static bic_status golomb_prepare(bic_ctx* c, const bic_mat* M, const uint32_t** 
   g->bits_before = (unsigned long long*)(base + per * 32);
   g->ones = (uint32_t*)(base + per * 40);
   if (ntiles) {
+    BIC_PROF(c, KID_GOL_TILE_COUNTS);
     k_gol_tile_counts<<<(unsigned)ntiles, TILE_THREADS, 0, c->stream>>>(S, T, *g);
     BIC_LAUNCH_CHECK(c);
+    BIC_PROF(c, KID_GOL_SCAN_A);
     k_gol_scan_tiles_a<<<1, TILE_THREADS, 0, c->stream>>>(*g, ntiles);
     BIC_LAUNCH_CHECK(c);
+    BIC_PROF(c, KID_GOL_LENGTHS);
     k_gol_walk<0><<<(unsigned)ntiles, TILE_THREADS, 0, c->stream>>>(S, T, N, *g, nullptr, nullptr, 1, nullptr);
     BIC_LAUNCH_CHECK(c);
   }
+  BIC_PROF(c, KID_GOL_SCAN_B);
   k_gol_scan_tiles_b<<<1, TILE_THREADS, 0, c->stream>>>(*g, ntiles, N, (unsigned long long*)c->d_scalars);
   BIC_LAUNCH_CHECK(c);
   BIC_TRY(bic_read_scalars(c, 4));
@@ -556,6 +561,7 @@ extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t c
   BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, out->cap_bytes, c->stream));
   // with no tile (empty matrix) one CTA still has to write the closing sample
   const unsigned grid = (unsigned)(ntiles ? ntiles : 1);
+  BIC_PROF(c, KID_GOL_SCATTER);
   k_gol_walk<1><<<grid, TILE_THREADS, 0, c->stream>>>(S, ntiles ? T : 0, N, g, (uint32_t*)out->d_bytes,
                                                      (unsigned long long*)out->d_index, chunk_samples,
                                                      (const unsigned long long*)c->d_scalars);
@@ -588,11 +594,13 @@ extern "C" bic_status bic_golomb_decode(bic_ctx* c, const bic_stream* s, bic_mat
     BIC_CUDA(c, cudaMemsetAsync(S, 0, (size_t)T * 4 + 16, c->stream));
   }
   BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, 8, c->stream));
+  BIC_PROF(c, KID_GOL_DECODE);
   k_gol_decode<<<bic_grid_for(c, s->info.nchunks, 128, 16), 128, 0, c->stream>>>(
       (const uint32_t*)s->d_bytes, s->info.bitcount, (const unsigned long long*)s->d_index, s->info.nchunks,
       s->info.chunk_samples, s->info.nsamples, N, S, (unsigned long long*)c->d_scalars);
   BIC_LAUNCH_CHECK(c);
   if (!dense && M->words()) {
+    BIC_PROF(c, KID_EXPAND_ROWS);
     k_expand_rows<<<bic_grid_for(c, M->words(), 256, 8), 256, 0, c->stream>>>(S, M->cols, M->wpr, M->rows, M->d);
     BIC_LAUNCH_CHECK(c);
   }
@@ -608,6 +616,7 @@ extern "C" bic_status bic_eg_encode(bic_ctx* c, const bic_mat* M, bic_stream* ou
   BIC_TRY(dense_stream(c, M, &S, &T));
   BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0xFF, 8, c->stream));
   if (T) {
+    BIC_PROF(c, KID_EG_FIRST);
     k_first_one<<<bic_grid_for(c, T, 256, 8), 256, 0, c->stream>>>(S, T, (unsigned long long*)c->d_scalars);
     BIC_LAUNCH_CHECK(c);
   }
@@ -617,10 +626,12 @@ extern "C" bic_status bic_eg_encode(bic_ctx* c, const bic_mat* M, bic_stream* ou
   BIC_TRY(stream_reserve(c, out, bitcount, 0));
   BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, out->cap_bytes, c->stream));
   if (bitcount) {
+    BIC_PROF(c, KID_EG_FILL);
     k_fill_ones<<<bic_grid_for(c, div_up_u64(bitcount, 32), 256, 8), 256, 0, c->stream>>>((uint32_t*)out->d_bytes, bitcount);
     BIC_LAUNCH_CHECK(c);
   }
   if (any) {
+    BIC_PROF(c, KID_EG_ENCODE);
     k_eg_encode<<<bic_grid_for(c, T, 256, 8), 256, 0, c->stream>>>(S, T, M->cols, (const unsigned long long*)c->d_scalars,
                                                                   (uint32_t*)out->d_bytes);
     BIC_LAUNCH_CHECK(c);
@@ -644,11 +655,13 @@ extern "C" bic_status bic_eg_decode(bic_ctx* c, const bic_stream* s, bic_mat* M)
     return bic_fail(c, BIC_ERR_CORRUPT, "eg_decode: bit count does not match the shape");
   BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0xFF, 8, c->stream));
   if (s->info.bitcount) {
+    BIC_PROF(c, KID_EG_FIRST);
     k_first_zero<<<bic_grid_for(c, div_up_u64(s->info.bitcount, 32), 256, 8), 256, 0, c->stream>>>(
         (const uint32_t*)s->d_bytes, s->info.bitcount, (unsigned long long*)c->d_scalars);
     BIC_LAUNCH_CHECK(c);
   }
   if (M->words()) {
+    BIC_PROF(c, KID_EG_DECODE);
     k_eg_decode<<<bic_grid_for(c, M->words(), 256, 8), 256, 0, c->stream>>>((const uint32_t*)s->d_bytes, M->rows, M->cols,
                                                                           M->wpr, (const unsigned long long*)c->d_scalars, M->d);
     BIC_LAUNCH_CHECK(c);

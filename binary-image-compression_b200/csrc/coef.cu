@@ -124,6 +124,7 @@ static bic_status launch_coef(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat*
   int per_sm = smem ? (int)((200 * 1024) / smem) : 8;
   per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
   const int grid = bic_grid_for(c, E->rows, 256, per_sm);
+  BIC_PROF(c, KID_UPDATE_COEF);
   k_update_coefficients<WORDS><<<grid, 256, smem, c->stream>>>(E->d, D->d, A->d, E->rows, E->wpr, (uint32_t)D->rows,
                                                               A->wpr, d_changed);
   BIC_LAUNCH_CHECK(c);
@@ -152,6 +153,7 @@ bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, b
   if (smem > 200 * 1024) return bic_fail(c, BIC_ERR_UNSUPPORTED, "update_coefficients: rows wider than 200 KB");
   if (smem > 48 * 1024)
     BIC_CUDA(c, cudaFuncSetAttribute(k_update_coefficients_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BIC_PROF(c, KID_UPDATE_COEF);
   k_update_coefficients_wide<<<bic_grid_for(c, E->rows * 32, 256, 4), 256, smem, c->stream>>>(
       E->d, D->d, A->d, E->rows, wpr, (uint32_t)D->rows, A->wpr, d_changed);
   BIC_LAUNCH_CHECK(c);
@@ -235,6 +237,7 @@ static bic_status launch_residual(bic_ctx* c, const bic_mat* X, const bic_mat* A
     BIC_CUDA(c, cudaFuncSetAttribute(k_residual<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = smem ? (int)((200 * 1024) / smem) : 8;
   per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  BIC_PROF(c, KID_RESIDUAL);
   k_residual<WORDS><<<bic_grid_for(c, X->rows, 256, per_sm), 256, smem, c->stream>>>(
       X->d, A->d, D->d, E->d, X->rows, X->wpr, (uint32_t)D->rows, A->wpr, in_smem);
   BIC_LAUNCH_CHECK(c);
@@ -253,6 +256,7 @@ extern "C" bic_status bic_residual(bic_ctx* c, const bic_mat* X, const bic_mat* 
   if (wpr <= 8) return launch_residual<8>(c, X, A, D, E);
   if (wpr <= 16) return launch_residual<16>(c, X, A, D, E);
   if (wpr <= 32) return launch_residual<32>(c, X, A, D, E);
+  BIC_PROF(c, KID_RESIDUAL);
   k_residual_wide<<<bic_grid_for(c, X->words(), 256, 8), 256, 0, c->stream>>>(X->d, A->d, D->d, E->d, X->rows, wpr, A->wpr);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;

@@ -54,12 +54,20 @@ extern "C" bic_status bic_ctx_create_on_stream(int device, void* cuda_stream, bi
 }
 
 extern "C" void bic_internal_drop_workspace(bic_ctx* c);
+static void prof_collect_for_destroy(bic_ctx* c) {
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : c->prof_recs) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
+  c->prof_recs.clear();
+  for (auto e : c->prof_free) cudaEventDestroy(e);
+  c->prof_free.clear();
+}
 
 extern "C" bic_status bic_ctx_destroy(bic_ctx* c) {
   if (!c) return BIC_ERR_INVALID;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   bic_internal_drop_workspace(c);
+  prof_collect_for_destroy(c);
   if (c->staging.p) cudaFree(c->staging.p);
   for (auto& w : c->work) if (w.p) cudaFree(w.p);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -245,6 +253,7 @@ extern "C" bic_status bic_mat_upload_words64(bic_ctx* c, bic_mat* m, const uint6
   const size_t bytes = (size_t)(m->rows * wpr64) * 8;
   BIC_TRY(bic_scratch_reserve(c, &c->staging, bytes));
   BIC_CUDA(c, cudaMemcpyAsync(c->staging.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  BIC_PROF(c, KID_WORDS64_TO_DEV);
   k_words64_to_dev<<<copy_grid(c, m->words()), 256, 0, c->stream>>>((const uint64_t*)c->staging.p, m->d, m->rows,
                                                                    m->wpr, wpr64, tail_mask32(m->cols));
   BIC_LAUNCH_CHECK(c);
@@ -257,6 +266,7 @@ extern "C" bic_status bic_mat_download_words64(bic_ctx* c, const bic_mat* m, uin
   const uint64_t wpr64 = div_up_u64(m->cols, 64);
   const size_t bytes = (size_t)(m->rows * wpr64) * 8;
   BIC_TRY(bic_scratch_reserve(c, &c->staging, bytes));
+  BIC_PROF(c, KID_DEV_TO_WORDS64);
   k_dev_to_words64<<<copy_grid(c, m->rows * wpr64), 256, 0, c->stream>>>(m->d, (uint64_t*)c->staging.p, m->rows,
                                                                          m->wpr, wpr64);
   BIC_LAUNCH_CHECK(c);
@@ -272,6 +282,7 @@ extern "C" bic_status bic_mat_upload_pbm(bic_ctx* c, bic_mat* m, const uint8_t* 
   const size_t bytes = (size_t)(m->rows * bpr);
   BIC_TRY(bic_scratch_reserve(c, &c->staging, bytes + 16));
   BIC_CUDA(c, cudaMemcpyAsync(c->staging.p, payload, bytes, cudaMemcpyHostToDevice, c->stream));
+  BIC_PROF(c, KID_PBM_TO_DEV);
   k_pbm_to_dev<<<copy_grid(c, m->words()), 256, 0, c->stream>>>((const uint8_t*)c->staging.p, m->d, m->rows, m->wpr,
                                                                bpr, tail_mask32(m->cols));
   BIC_LAUNCH_CHECK(c);
@@ -284,6 +295,7 @@ extern "C" bic_status bic_mat_download_pbm(bic_ctx* c, const bic_mat* m, uint8_t
   const uint64_t bpr = div_up_u64(m->cols, 8);
   const size_t bytes = (size_t)(m->rows * bpr);
   BIC_TRY(bic_scratch_reserve(c, &c->staging, bytes + 16));
+  BIC_PROF(c, KID_DEV_TO_PBM);
   k_dev_to_pbm<<<copy_grid(c, bytes), 256, 0, c->stream>>>(m->d, (uint8_t*)c->staging.p, m->rows, m->wpr, bpr);
   BIC_LAUNCH_CHECK(c);
   BIC_CUDA(c, cudaMemcpyAsync(payload, c->staging.p, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -326,6 +338,7 @@ __global__ void k_weight(const uint32_t* __restrict__ a, const uint32_t* __restr
 static bic_status weight_impl(bic_ctx* c, const bic_mat* a, const bic_mat* b, uint64_t* w) {
   BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, sizeof(uint64_t), c->stream));
   if (a->words()) {
+    BIC_PROF(c, KID_WEIGHT);
     k_weight<<<bic_grid_for(c, a->words() / 4 + 1, 256, 8), 256, 0, c->stream>>>(
         a->d, b ? b->d : nullptr, a->words(), (unsigned long long*)c->d_scalars);
     BIC_LAUNCH_CHECK(c);
@@ -361,6 +374,7 @@ extern "C" bic_status bic_mat_xor(bic_ctx* c, const bic_mat* a, const bic_mat* b
   // allocations are padded to 16 B multiples with zero words, so whole uint4s are safe
   const uint64_t nv = div_up_u64(a->words(), 4);
   if (nv) {
+    BIC_PROF(c, KID_XOR);
     k_xor<<<bic_grid_for(c, nv, 256, 8), 256, 0, c->stream>>>(a->d, b->d, o->d, nv);
     BIC_LAUNCH_CHECK(c);
   }
@@ -387,4 +401,75 @@ extern "C" uint64_t bic_rand48_uniform_int(uint64_t* state, uint64_t n) {
     k = (*state >> 16) / scale;
   } while (k >= n);
   return k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-launch device timers: an event pair around every kernel of this context's stream
+// ---------------------------------------------------------------------------------------------
+static const char* const kKernelNames[KID_COUNT] = {
+  "k_words64_to_dev", "k_dev_to_words64", "k_pbm_to_dev", "k_dev_to_pbm", "k_weight", "k_xor",
+  "k_extract", "k_assemble", "k_row_nonzero", "k_gather_rows", "k_col_hist", "k_pivot_usage", "k_init_finalize",
+  "k_update_coefficients", "k_residual", "k_transpose_bits", "k_update_dictionary",
+  "k_compact_rows", "k_expand_rows", "k_gol_tile_counts", "k_gol_scan_tiles_a", "k_gol_walk<0>", "k_gol_scan_tiles_b",
+  "k_gol_walk<1>", "k_gol_decode", "k_first_one/zero", "k_fill_ones", "k_eg_encode", "k_eg_decode"};
+
+static cudaEvent_t prof_event(bic_ctx* c) {
+  if (!c->prof_free.empty()) { cudaEvent_t e = c->prof_free.back(); c->prof_free.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void bic_prof_begin(bic_ctx* c, int kid) {
+  bic_prof_rec r;
+  r.kid = kid;
+  r.e0 = prof_event(c);
+  r.e1 = nullptr;
+  cudaEventRecord(r.e0, c->stream);
+  c->prof_recs.push_back(r);
+}
+
+void bic_prof_end(bic_ctx* c) {
+  if (c->prof_recs.empty() || c->prof_recs.back().e1) return;
+  bic_prof_rec& r = c->prof_recs.back();
+  r.e1 = prof_event(c);
+  cudaEventRecord(r.e1, c->stream);
+}
+
+static void prof_collect(bic_ctx* c) {
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : c->prof_recs) {
+    if (r.e1) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { c->prof_ms[r.kid] += ms; c->prof_n[r.kid]++; }
+      c->prof_free.push_back(r.e1);
+    }
+    c->prof_free.push_back(r.e0);
+  }
+  c->prof_recs.clear();
+}
+
+extern "C" bic_status bic_prof_enable(bic_ctx* c, int on) {
+  if (!c) return BIC_ERR_INVALID;
+  if (!on && c->prof_on) prof_collect(c);
+  c->prof_on = on != 0;
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_prof_reset(bic_ctx* c) {
+  if (!c) return BIC_ERR_INVALID;
+  prof_collect(c);
+  for (int i = 0; i < KID_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+  return BIC_OK;
+}
+
+extern "C" int bic_prof_kernel_count(void) { return KID_COUNT; }
+
+extern "C" bic_status bic_prof_get(bic_ctx* c, int kid, const char** name, uint64_t* launches, double* total_ms) {
+  if (!c || kid < 0 || kid >= KID_COUNT) return BIC_ERR_INVALID;
+  prof_collect(c);
+  if (name) *name = kKernelNames[kid];
+  if (launches) *launches = c->prof_n[kid];
+  if (total_ms) *total_ms = c->prof_ms[kid];
+  return BIC_OK;
 }

@@ -188,8 +188,10 @@ static bic_status launch_dict(bic_ctx* c, DictParams& P) {
   uint64_t cap = (uint64_t)c->sm_count * per_sm;
   int grid = (int)(want < cap ? (want ? want : 1) : cap);
   void* args[] = {&P};
+  BIC_PROF(c, KID_UPDATE_DICT);
   BIC_CUDA(c, cudaLaunchCooperativeKernel((void*)k_update_dictionary<WORDS>, dim3(grid), dim3(256), args, smem, c->stream));
   c->launches++;
+  if (c->prof_on) bic_prof_end(c);
   return BIC_OK;
 }
 
@@ -211,6 +213,7 @@ bic_status bic_k_update_dictionary(bic_ctx* c, bic_mat* E, bic_mat* D, const bic
     const uint64_t nblk = div_up_u64(n, 1024);
     const uint64_t gx = nblk < (uint64_t)c->sm_count * 2 ? nblk : (uint64_t)c->sm_count * 2;
     dim3 grid((unsigned)gx, (unsigned)A->wpr);
+    BIC_PROF(c, KID_TRANSPOSE_BITS);
     k_transpose_bits<<<grid, 1024, 0, c->stream>>>(A->d, n, A->wpr, AT, wprN, p);
     BIC_LAUNCH_CHECK(c);
   }

@@ -87,6 +87,7 @@ extern "C" bic_status bic_extract_patches(bic_ctx* c, const bic_mat* raster, uin
   const uint64_t Ny = (W - 1 + raster->rows) / W, Nx = (W - 1 + raster->cols) / W;  // bsvd_test.cpp:82-83
   if (X->rows != Nx * Ny || X->cols != W * W) return bic_fail(c, BIC_ERR_INVALID, "extract: X must be Nx*Ny x W*W");
   if (X->rows == 0) return BIC_OK;
+  BIC_PROF(c, KID_EXTRACT);
   k_extract<<<bic_grid_for(c, X->words(), 256, 16), 256, 0, c->stream>>>(raster->d, X->d, raster->rows, raster->cols,
                                                                         raster->wpr, W, Nx, X->rows, X->wpr, X->cols);
   BIC_LAUNCH_CHECK(c);
@@ -98,6 +99,7 @@ extern "C" bic_status bic_assemble_patches(bic_ctx* c, const bic_mat* X, uint64_
   const uint64_t Ny = (W - 1 + raster->rows) / W, Nx = (W - 1 + raster->cols) / W;
   if (X->rows != Nx * Ny || X->cols != W * W) return bic_fail(c, BIC_ERR_INVALID, "assemble: X must be Nx*Ny x W*W");
   if (raster->words() == 0) return BIC_OK;
+  BIC_PROF(c, KID_ASSEMBLE);
   k_assemble<<<bic_grid_for(c, raster->words(), 256, 16), 256, 0, c->stream>>>(X->d, raster->d, raster->rows,
                                                                               raster->cols, raster->wpr, W, Nx, X->wpr);
   BIC_LAUNCH_CHECK(c);

@@ -30,6 +30,7 @@ __global__ void k_row_nonzero(const uint32_t* __restrict__ X, uint64_t n, uint64
 
 bic_status bic_k_row_nonzero_bitmap(bic_ctx* c, const bic_mat* X, uint32_t* d_bitmap) {
   if (X->rows == 0) return BIC_OK;
+  BIC_PROF(c, KID_ROW_NONZERO);
   k_row_nonzero<<<bic_grid_for(c, X->rows, 256, 8), 256, 0, c->stream>>>(X->d, X->rows, X->wpr, d_bitmap);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
@@ -167,6 +168,7 @@ static bic_status launch_usage(bic_ctx* c, const bic_mat* X, const uint32_t* P, 
   const size_t smem = ((size_t)np * WORDS + np) * 4;
   if (smem > 48 * 1024)
     BIC_CUDA(c, cudaFuncSetAttribute(k_pivot_usage<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BIC_PROF(c, KID_PIVOT_USAGE);
   k_pivot_usage<WORDS><<<bic_grid_for(c, X->rows, 256, 4), 256, smem, c->stream>>>(X->d, X->rows, X->wpr, P, np, usage);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
@@ -196,15 +198,16 @@ extern "C" bic_status bic_initialize_model_neighbor_pivots(bic_ctx* c, const bic
   uint32_t* d_usage = (uint32_t*)(base + off_u);
   BIC_CUDA(c, cudaMemcpyAsync(d_piv, pivots, (size_t)p * 8, cudaMemcpyHostToDevice, c->stream));
   BIC_CUDA(c, cudaMemsetAsync(d_hist, 0, (size_t)wpr * 32 * 4 + (size_t)p * 4, c->stream));
+  BIC_PROF(c, KID_GATHER_ROWS);
   k_gather_rows<<<bic_grid_for(c, p * wpr, 256, 4), 256, 0, c->stream>>>(X->d, wpr, d_piv, (uint32_t)p, d_P);
   BIC_LAUNCH_CHECK(c);
   // column histogram, 32 words of the row per launch
   for (uint64_t w0 = 0; w0 < wpr; w0 += 32) {
     const uint64_t nw = (wpr - w0 < 32) ? wpr - w0 : 32;
     const int grid = bic_grid_for(c, X->rows * 32, 256, 8);
-    if (nw <= 2) k_col_hist<2><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist);
-    else if (nw <= 8) k_col_hist<8><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist);
-    else k_col_hist<32><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist);
+    if (nw <= 2) { BIC_PROF(c, KID_COL_HIST); k_col_hist<2><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist); }
+    else if (nw <= 8) { BIC_PROF(c, KID_COL_HIST); k_col_hist<8><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist); }
+    else { BIC_PROF(c, KID_COL_HIST); k_col_hist<32><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist); }
     BIC_LAUNCH_CHECK(c);
   }
   // pivot usage, in chunks of pivots whose rows fit in shared memory
@@ -225,10 +228,12 @@ extern "C" bic_status bic_initialize_model_neighbor_pivots(bic_ctx* c, const bic
       }
     }
   } else {
+    BIC_PROF(c, KID_PIVOT_USAGE);
     k_pivot_usage_wide<<<bic_grid_for(c, X->rows * 32, 256, 8), 256, 0, c->stream>>>(X->d, X->rows, wpr, d_P,
                                                                                    (uint32_t)p, d_usage);
     BIC_LAUNCH_CHECK(c);
   }
+  BIC_PROF(c, KID_INIT_FINALIZE);
   k_init_finalize<<<bic_grid_for(c, p * wpr, 256, 4), 256, 0, c->stream>>>(d_P, d_hist, d_usage, (uint32_t)p, wpr, m, D->d);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;

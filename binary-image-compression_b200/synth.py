@@ -91,28 +91,80 @@ def structured_canvas(rows: int, cols: int, seed: int = 4) -> np.ndarray:
     return out
 
 
-def smooth_pgm16(rows: int = 8192, cols: int = 8192, seed: int = 2, noise_bits: int = 6) -> np.ndarray:
-    """16-bit grey image: sum of 64 low-frequency cosines + uniform noise in the low bits
-    (config 2). Planes run from structured (MSBs) to ~50 % density (LSBs)."""
+_COS_TABLE = None
+
+
+def _cos_table() -> np.ndarray:
+    global _COS_TABLE
+    if _COS_TABLE is None:
+        k = np.arange(65536, dtype=np.float64)
+        _COS_TABLE = np.round(32767.0 * np.cos(2.0 * np.pi * k / 65536.0)).astype(np.int64)
+    return _COS_TABLE
+
+
+def _pgm16_params(seed: int):
     rng = np.random.default_rng(seed)
-    y = np.arange(rows, dtype=np.float32)[:, None] / max(rows, 1)
-    x = np.arange(cols, dtype=np.float32)[None, :] / max(cols, 1)
-    f = np.zeros((rows, cols), np.float32)
-    for _ in range(64):
-        fy, fx = rng.uniform(0, 6, size=2)
-        ph = rng.uniform(0, 2 * np.pi)
-        amp = rng.uniform(0.2, 1.0)
-        f += np.float32(amp) * np.cos(np.float32(2 * np.pi) * (np.float32(fy) * y + np.float32(fx) * x) + np.float32(ph))
-    f -= f.min()
-    f /= max(float(f.max()), 1e-9)
-    img = (f * np.float32(65535 - (1 << noise_bits))).astype(np.uint32)
-    img += rng.integers(0, 1 << noise_bits, size=(rows, cols), dtype=np.uint32)
-    return np.minimum(img, 65535).astype(np.uint16)
+    u = rng.integers(0, 49, size=64).astype(np.int64)      # cycles per 65536 rows
+    v = rng.integers(0, 49, size=64).astype(np.int64)
+    w = rng.integers(0, 65536, size=64).astype(np.int64)   # phase
+    a = rng.integers(50, 256, size=64).astype(np.int64)    # amplitude
+    return u, v, w, a
 
 
-def bitplane(img: np.ndarray, b: int) -> np.ndarray:
+def smooth_pgm16(rows: int = 8192, cols: int = 8192, seed: int = 2, noise_bits: int = 6,
+                 y0: int = 0, x0: int = 0, device=None):
+    """16-bit grey image (config 2): a smooth field (sum of 64 low-frequency cosines) with hashed
+    uniform noise in the low `noise_bits` bits, so planes run from structured (MSBs) to ~50 %
+    density (LSBs). All integer arithmetic (cosine through a 65536-entry table, noise through an
+    integer hash of the pixel coordinates), so any crop (y0, x0, rows, cols) of the infinite image
+    is bit-identical whether it is produced by numpy (device=None) or by torch on a GPU."""
+    u, v, w, a = _pgm16_params(seed)
+    T = _cos_table()
+    if device is None:
+        y = (np.arange(rows, dtype=np.int64) + y0)[:, None]
+        x = (np.arange(cols, dtype=np.int64) + x0)[None, :]
+        acc = np.zeros((rows, cols), np.int64)
+        for i in range(64):
+            acc += a[i] * T[(u[i] * y * 8 + v[i] * x * 8 + w[i]) & 0xFFFF]
+        S = int(a.sum()) * 32767
+        img = np.clip(((3 * acc + S) * 65535) // (2 * S), 0, 65535)  # gain 3: the sum of 64 random phases rarely leaves +-S/3
+        h = (y * 73856093) ^ (x * 19349663) ^ (seed * 83492791)
+        h = ((h ^ (h >> 13)) * 1540483477) & 0xFFFFFFFF
+        h = (h ^ (h >> 15)) & ((1 << noise_bits) - 1)
+        img = (img & ~((1 << noise_bits) - 1)) | h
+        return img.astype(np.uint16)
+    import torch
+    y = (torch.arange(rows, dtype=torch.int64, device=device) + y0)[:, None]
+    x = (torch.arange(cols, dtype=torch.int64, device=device) + x0)[None, :]
+    Tt = torch.from_numpy(T).to(device)
+    acc = torch.zeros((rows, cols), dtype=torch.int64, device=device)
+    for i in range(64):
+        acc += int(a[i]) * Tt[(int(u[i]) * 8 * y + int(v[i]) * 8 * x + int(w[i])) & 0xFFFF]
+    S = int(a.sum()) * 32767
+    img = torch.clamp(torch.div((3 * acc + S) * 65535, 2 * S, rounding_mode="floor"), 0, 65535)
+    h = (y * 73856093) ^ (x * 19349663) ^ (seed * 83492791)
+    h = ((h ^ (h >> 13)) * 1540483477) & 0xFFFFFFFF
+    h = (h ^ (h >> 15)) & ((1 << noise_bits) - 1)
+    img = (img & ~((1 << noise_bits) - 1)) | h
+    return img  # int64 tensor with values in [0, 65535]
+
+
+def bitplane(img, b: int):
     """plane b (0 = LSB) exactly as bitplane_tool does it (src/bitplane_tool.cpp:24-39)."""
-    return ((img >> np.uint16(b)) & np.uint16(1)).astype(np.uint8)
+    if isinstance(img, np.ndarray):
+        return ((img >> np.uint16(b)) & np.uint16(1)).astype(np.uint8)
+    return ((img >> b) & 1).to(dtype=__import__("torch").uint8)
+
+
+def pbm_bytes_torch(bits):
+    """torch twin of pbm_bytes: dense {0,1} uint8 (rows, cols) -> P4 payload rows (uint8)"""
+    import torch
+    rows, cols = bits.shape
+    pad = (-cols) % 8
+    if pad:
+        bits = torch.nn.functional.pad(bits, (0, pad))
+    w = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.int32, device=bits.device)
+    return (bits.reshape(rows, -1, 8).to(torch.int32) * w).sum(dim=2).to(torch.uint8)
 
 
 def bernoulli_bits(nbits: int, rho: float, seed: int = 5) -> np.ndarray:

@@ -63,6 +63,12 @@ uint64_t bic_ctx_launch_count(bic_ctx* ctx);
 /* device timers on the context's stream (cudaEvent pairs): ms between start and stop */
 bic_status bic_timer_start(bic_ctx* ctx);
 bic_status bic_timer_stop(bic_ctx* ctx, float* ms);
+/* optional per-launch device timers: an event pair around every kernel this context launches,
+ * accumulated per kernel (used by bench.py for the live roofline; off by default) */
+bic_status bic_prof_enable(bic_ctx* ctx, int on);
+bic_status bic_prof_reset(bic_ctx* ctx);
+int bic_prof_kernel_count(void);
+bic_status bic_prof_get(bic_ctx* ctx, int kernel, const char** name, uint64_t* launches, double* total_ms);
 /* pinned host memory for callers that want async H2D/D2H */
 bic_status bic_host_alloc(size_t bytes, void** out);
 bic_status bic_host_free(void* p);

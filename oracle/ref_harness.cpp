@@ -196,6 +196,24 @@ long ref_golomb(const unsigned* samples, u64 n, unsigned* k_used, long* bits_add
   return gc.bitcount;
 }
 
+/* The reference's GolombCoder (GolombCoder.cpp:29-34) fed with the zero-run lengths of M read
+ * row-major through binary_matrix::get (binmat.h:114-116); a virtual one closes the last run.
+ * This is the serial coding baseline (single core: the state machine cannot be threaded). */
+long ref_golomb_matrix(const u64* words, u64 rows, u64 cols) {
+  binary_matrix M(rows, cols);
+  load(M, words);
+  GolombCoder gc;
+  unsigned run = 0;
+  for (u64 i = 0; i < rows; ++i)
+    for (u64 j = 0; j < cols; ++j) {
+      if (M.get(i, j)) { gc.codeSample(run); run = 0; }
+      else run++;
+    }
+  gc.codeSample(run);
+  M.destroy();
+  return gc.bitcount;
+}
+
 /* EGCoder::codeRun: eg.cpp:20-37. Returns the final bitcount. */
 u64 ref_eg(const int* lens, const unsigned char* eols, u64 n, u64* bits_added) {
   EGCoder ec;

@@ -212,6 +212,8 @@ class Reference:
         L.ref_weight.argtypes = [u64p, u64, u64]
         L.ref_golomb.restype = C.c_long
         L.ref_golomb.argtypes = [u32p, u64, u32p, C.POINTER(C.c_long)]
+        L.ref_golomb_matrix.restype = C.c_long
+        L.ref_golomb_matrix.argtypes = [u64p, u64, u64]
         L.ref_eg.restype = u64
         L.ref_eg.argtypes = [C.POINTER(C.c_int), u8p, u64, u64p]
         L.ref_fit_timed.restype = u64
@@ -271,6 +273,10 @@ class Reference:
         total = int(self.lib.ref_golomb(s.ctypes.data_as(u32p), s.size, k.ctypes.data_as(u32p),
                                         b.ctypes.data_as(C.POINTER(C.c_long))))
         return total, k, b
+
+    def golomb_matrix(self, M, cols):
+        M = np.ascontiguousarray(M, np.uint64)
+        return int(self.lib.ref_golomb_matrix(_p64(M), M.shape[0], cols))
 
     def eg(self, lens, eols):
         l = np.ascontiguousarray(lens, np.int32)
