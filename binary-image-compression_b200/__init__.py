@@ -78,6 +78,8 @@ def lib() -> C.CDLL:
         "bic_ctx_sync": [_vp],
         "bic_timer_start": [_vp],
         "bic_timer_stop": [_vp, C.POINTER(C.c_float)],
+        "bic_ctx_set_option": [_vp, C.c_char_p, C.c_int64],
+        "bic_ctx_wait_ctx": [_vp, _vp],
         "bic_prof_enable": [_vp, C.c_int],
         "bic_prof_reset": [_vp],
         "bic_prof_get": [_vp, C.c_int, C.POINTER(C.c_char_p), _u64p, C.POINTER(C.c_double)],
@@ -282,6 +284,13 @@ class Context:
         ms = C.c_float(0)
         self._ck(self.L.bic_timer_stop(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def wait_for(self, other: "Context"):
+        """order this context's stream after everything queued so far on `other`'s stream"""
+        self._ck(self.L.bic_ctx_wait_ctx(self.h, other.h))
+
+    def set_option(self, name: str, value: int):
+        self._ck(self.L.bic_ctx_set_option(self.h, name.encode(), int(value)))
 
     def prof_enable(self, on: bool):
         self._ck(self.L.bic_prof_enable(self.h, 1 if on else 0))

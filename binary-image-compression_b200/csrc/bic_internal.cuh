@@ -42,7 +42,7 @@ struct bic_stream {
 enum bic_kernel_id {
   KID_WORDS64_TO_DEV = 0, KID_DEV_TO_WORDS64, KID_PBM_TO_DEV, KID_DEV_TO_PBM, KID_WEIGHT, KID_XOR,
   KID_EXTRACT, KID_ASSEMBLE, KID_ROW_NONZERO, KID_GATHER_ROWS, KID_COL_HIST, KID_PIVOT_USAGE, KID_INIT_FINALIZE,
-  KID_UPDATE_COEF, KID_RESIDUAL, KID_TRANSPOSE_BITS, KID_UPDATE_DICT,
+  KID_UPDATE_COEF, KID_RESIDUAL, KID_TRANSPOSE_BITS, KID_UPDATE_DICT, KID_DICT_HIST, KID_DICT_RESOLVE,
   KID_COMPACT_ROWS, KID_EXPAND_ROWS, KID_GOL_TILE_COUNTS, KID_GOL_SCAN_A, KID_GOL_LENGTHS, KID_GOL_SCAN_B,
   KID_GOL_SCATTER, KID_GOL_DECODE, KID_EG_FIRST, KID_EG_FILL, KID_EG_ENCODE, KID_EG_DECODE,
   KID_COUNT
@@ -66,6 +66,7 @@ struct bic_ctx {
   bic_scratch staging;    // host-layout staging for uploads/downloads
   bic_scratch work[6];    // per-algorithm work buffers
   // optional per-launch device timers
+  int dict_algo = 1;  // 0: per-atom walk (dict.cu), 1: histogram first, resolve in order (dict2.cu)
   bool prof_on = false;
   std::vector<bic_prof_rec> prof_recs;
   std::vector<cudaEvent_t> prof_free;

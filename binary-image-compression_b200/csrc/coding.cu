@@ -446,12 +446,14 @@ __global__ void k_eg_decode(const uint32_t* __restrict__ in, uint64_t rows, uint
 
 // ------------------------------------------------------------------ host side
 extern "C" bic_status bic_stream_create(bic_ctx* c, bic_stream** out) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !out) return BIC_ERR_INVALID;
   *out = new (std::nothrow) bic_stream();
   return *out ? BIC_OK : BIC_ERR_NOMEM;
 }
 
 extern "C" bic_status bic_stream_destroy(bic_ctx* c, bic_stream* s) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !s) return BIC_ERR_INVALID;
   BIC_CUDA(c, cudaStreamSynchronize(c->stream));
   if (s->d_bytes) cudaFree(s->d_bytes);
@@ -466,9 +468,13 @@ extern "C" bic_status bic_stream_get_info(const bic_stream* s, bic_stream_info* 
   return BIC_OK;
 }
 
-static bic_status stream_reserve(bic_ctx* c, bic_stream* s, uint64_t bitcount, uint64_t nchunks) {
+static bic_status stream_reserve(bic_ctx* c, bic_stream* s, uint64_t bitcount, uint64_t nchunks, uint64_t src_bits = 0) {
   // whole 32-bit words plus slack so peek32 / put_bits may touch one word past the end
-  const size_t need = (size_t)(div_up_u64(bitcount, 32) * 4 + 16);
+  size_t need = (size_t)(div_up_u64(bitcount, 32) * 4 + 16);
+  // cudaMalloc/cudaFree stall every stream of the device, so a stream object is sized once for
+  // what its source can plausibly produce (1.25 bits per input bit) instead of growing plane by plane
+  const size_t typical = (size_t)(src_bits / 8 + src_bits / 32) + 4096;
+  if (need > s->cap_bytes && typical > need) need = typical;
   if (need > s->cap_bytes) {
     BIC_CUDA(c, cudaStreamSynchronize(c->stream));
     if (s->d_bytes) cudaFree(s->d_bytes);
@@ -477,7 +483,9 @@ static bic_status stream_reserve(bic_ctx* c, bic_stream* s, uint64_t bitcount, u
     if (cudaMalloc(&s->d_bytes, want) != cudaSuccess) { cudaGetLastError(); c->err = "stream allocation failed"; return BIC_ERR_NOMEM; }
     s->cap_bytes = want;
   }
-  const size_t needi = (size_t)(nchunks ? nchunks : 1) * 2;
+  size_t needi = (size_t)(nchunks ? nchunks : 1) * 2;
+  const size_t typicali = (size_t)(src_bits / 256 + 64) * 2;  // one chunk per 256 samples, <= 1 sample per bit... /2 on average
+  if (needi > s->cap_index && typicali > needi) needi = typicali;
   if (needi > s->cap_index) {
     BIC_CUDA(c, cudaStreamSynchronize(c->stream));
     if (s->d_index) cudaFree(s->d_index);
@@ -541,6 +549,7 @@ static bic_status golomb_prepare(bic_ctx* c, const bic_mat* M, const uint32_t** 
 }
 
 extern "C" bic_status bic_golomb_bitcount(bic_ctx* c, const bic_mat* M, uint64_t* bitcount, uint64_t* nsamples) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !M) return BIC_ERR_INVALID;
   const uint32_t* S; uint64_t T, ntiles; GolTile g;
   BIC_TRY(golomb_prepare(c, M, &S, &T, &g, &ntiles));
@@ -550,6 +559,7 @@ extern "C" bic_status bic_golomb_bitcount(bic_ctx* c, const bic_mat* M, uint64_t
 }
 
 extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t chunk_samples, bic_stream* out) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !M || !out) return BIC_ERR_INVALID;
   if (chunk_samples == 0) chunk_samples = 256;
   const uint64_t N = M->rows * M->cols;
@@ -557,8 +567,8 @@ extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t c
   BIC_TRY(golomb_prepare(c, M, &S, &T, &g, &ntiles));
   const uint64_t bitcount = c->h_scalars[0], nsamples = c->h_scalars[1];
   const uint64_t nchunks = div_up_u64(nsamples, chunk_samples);
-  BIC_TRY(stream_reserve(c, out, bitcount, nchunks));
-  BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, out->cap_bytes, c->stream));
+  BIC_TRY(stream_reserve(c, out, bitcount, nchunks, N));
+  BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, (size_t)(div_up_u64(bitcount, 32) * 4 + 16), c->stream));
   // with no tile (empty matrix) one CTA still has to write the closing sample
   const unsigned grid = (unsigned)(ntiles ? ntiles : 1);
   BIC_PROF(c, KID_GOL_SCATTER);
@@ -577,6 +587,7 @@ extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t c
 }
 
 extern "C" bic_status bic_golomb_decode(bic_ctx* c, const bic_stream* s, bic_mat* M) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !s || !M) return BIC_ERR_INVALID;
   if (s->info.coder != BIC_CODER_GOLOMB) return bic_fail(c, BIC_ERR_INVALID, "golomb_decode: not a Golomb stream");
   if (M->rows != s->info.rows || M->cols != s->info.cols) return bic_fail(c, BIC_ERR_INVALID, "golomb_decode: shape mismatch");
@@ -610,6 +621,7 @@ extern "C" bic_status bic_golomb_decode(bic_ctx* c, const bic_stream* s, bic_mat
 }
 
 extern "C" bic_status bic_eg_encode(bic_ctx* c, const bic_mat* M, bic_stream* out) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !M || !out) return BIC_ERR_INVALID;
   const uint64_t N = M->rows * M->cols;
   const uint32_t* S; uint64_t T;
@@ -647,6 +659,7 @@ extern "C" bic_status bic_eg_encode(bic_ctx* c, const bic_mat* M, bic_stream* ou
 }
 
 extern "C" bic_status bic_eg_decode(bic_ctx* c, const bic_stream* s, bic_mat* M) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !s || !M) return BIC_ERR_INVALID;
   if (s->info.coder != BIC_CODER_EG) return bic_fail(c, BIC_ERR_INVALID, "eg_decode: not an EG stream");
   if (M->rows != s->info.rows || M->cols != s->info.cols) return bic_fail(c, BIC_ERR_INVALID, "eg_decode: shape mismatch");
@@ -671,6 +684,7 @@ extern "C" bic_status bic_eg_decode(bic_ctx* c, const bic_stream* s, bic_mat* M)
 
 extern "C" bic_status bic_stream_download(bic_ctx* c, const bic_stream* s, uint8_t* bytes, uint64_t cap_bytes,
                                           uint64_t* index, uint64_t cap_index_entries) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !s) return BIC_ERR_INVALID;
   const uint64_t nb = div_up_u64(s->info.bitcount, 8);
   if (bytes) {
@@ -688,6 +702,7 @@ extern "C" bic_status bic_stream_download(bic_ctx* c, const bic_stream* s, uint8
 
 extern "C" bic_status bic_stream_upload(bic_ctx* c, bic_stream* s, const bic_stream_info* info, const uint8_t* bytes,
                                         const uint64_t* index) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !s || !info) return BIC_ERR_INVALID;
   const uint64_t nb = div_up_u64(info->bitcount, 8);
   if ((nb && !bytes) || (info->nchunks && !index)) return BIC_ERR_INVALID;

@@ -161,6 +161,7 @@ bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, b
 }
 
 extern "C" bic_status bic_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, uint64_t* changed) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !E || !D || !A) return BIC_ERR_INVALID;
   BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, sizeof(uint64_t), c->stream));
   BIC_TRY(bic_k_update_coefficients(c, E, D, A, (unsigned long long*)c->d_scalars));
@@ -245,6 +246,7 @@ static bic_status launch_residual(bic_ctx* c, const bic_mat* X, const bic_mat* A
 }
 
 extern "C" bic_status bic_residual(bic_ctx* c, const bic_mat* X, const bic_mat* A, const bic_mat* D, bic_mat* E) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !X || !A || !D || !E) return BIC_ERR_INVALID;
   if (X->rows != A->rows || X->cols != D->cols || A->cols != D->rows || E->rows != X->rows || E->cols != X->cols)
     return bic_fail(c, BIC_ERR_INVALID, "residual: shapes must be X,E n x m, D p x m, A n x p");

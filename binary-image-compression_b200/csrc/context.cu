@@ -80,6 +80,7 @@ extern "C" bic_status bic_ctx_destroy(bic_ctx* c) {
 }
 
 extern "C" bic_status bic_ctx_sync(bic_ctx* c) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c) return BIC_ERR_INVALID;
   BIC_CUDA(c, cudaStreamSynchronize(c->stream));
   return BIC_OK;
@@ -106,11 +107,13 @@ extern "C" int bic_ctx_sm_count(bic_ctx* c) { return c ? c->sm_count : 0; }
 extern "C" uint64_t bic_ctx_launch_count(bic_ctx* c) { return c ? c->launches : 0; }
 
 extern "C" bic_status bic_timer_start(bic_ctx* c) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c) return BIC_ERR_INVALID;
   BIC_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   return BIC_OK;
 }
 extern "C" bic_status bic_timer_stop(bic_ctx* c, float* ms) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !ms) return BIC_ERR_INVALID;
   BIC_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   BIC_CUDA(c, cudaEventSynchronize(c->ev1));
@@ -157,6 +160,7 @@ bic_status bic_zero_scalars(bic_ctx* c) {
 // matrices
 // ---------------------------------------------------------------------------------------------
 extern "C" bic_status bic_mat_create(bic_ctx* c, uint64_t rows, uint64_t cols, bic_mat** out) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !out) return BIC_ERR_INVALID;
   *out = nullptr;
   bic_mat* m = new (std::nothrow) bic_mat();
@@ -180,6 +184,7 @@ extern "C" bic_status bic_mat_create(bic_ctx* c, uint64_t rows, uint64_t cols, b
 }
 
 extern "C" bic_status bic_mat_destroy(bic_ctx* c, bic_mat* m) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !m) return BIC_ERR_INVALID;
   BIC_CUDA(c, cudaStreamSynchronize(c->stream));
   if (m->owns && m->d) cudaFree(m->d);
@@ -247,6 +252,7 @@ __global__ void k_dev_to_pbm(const uint32_t* __restrict__ src, uint8_t* __restri
 static int copy_grid(const bic_ctx* c, uint64_t items) { return bic_grid_for(c, items, 256, 16); }
 
 extern "C" bic_status bic_mat_upload_words64(bic_ctx* c, bic_mat* m, const uint64_t* host) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !m || (!host && m->rows * m->cols)) return BIC_ERR_INVALID;
   if (m->rows * m->cols == 0) return BIC_OK;
   const uint64_t wpr64 = div_up_u64(m->cols, 64);
@@ -261,6 +267,7 @@ extern "C" bic_status bic_mat_upload_words64(bic_ctx* c, bic_mat* m, const uint6
 }
 
 extern "C" bic_status bic_mat_download_words64(bic_ctx* c, const bic_mat* m, uint64_t* host) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !m || (!host && m->rows * m->cols)) return BIC_ERR_INVALID;
   if (m->rows * m->cols == 0) return BIC_OK;
   const uint64_t wpr64 = div_up_u64(m->cols, 64);
@@ -276,6 +283,7 @@ extern "C" bic_status bic_mat_download_words64(bic_ctx* c, const bic_mat* m, uin
 }
 
 extern "C" bic_status bic_mat_upload_pbm(bic_ctx* c, bic_mat* m, const uint8_t* payload) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !m || (!payload && m->rows * m->cols)) return BIC_ERR_INVALID;
   if (m->rows * m->cols == 0) return BIC_OK;
   const uint64_t bpr = div_up_u64(m->cols, 8);
@@ -290,6 +298,7 @@ extern "C" bic_status bic_mat_upload_pbm(bic_ctx* c, bic_mat* m, const uint8_t* 
 }
 
 extern "C" bic_status bic_mat_download_pbm(bic_ctx* c, const bic_mat* m, uint8_t* payload) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !m || (!payload && m->rows * m->cols)) return BIC_ERR_INVALID;
   if (m->rows * m->cols == 0) return BIC_OK;
   const uint64_t bpr = div_up_u64(m->cols, 8);
@@ -304,12 +313,14 @@ extern "C" bic_status bic_mat_download_pbm(bic_ctx* c, const bic_mat* m, uint8_t
 }
 
 extern "C" bic_status bic_mat_clear(bic_ctx* c, bic_mat* m) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !m) return BIC_ERR_INVALID;
   BIC_CUDA(c, cudaMemsetAsync(m->d, 0, m->alloc_bytes, c->stream));
   return BIC_OK;
 }
 
 extern "C" bic_status bic_mat_copy(bic_ctx* c, const bic_mat* src, bic_mat* dst) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !src || !dst || src->rows != dst->rows || src->cols != dst->cols) return BIC_ERR_INVALID;
   BIC_CUDA(c, cudaMemcpyAsync(dst->d, src->d, (size_t)src->words() * 4, cudaMemcpyDeviceToDevice, c->stream));
   return BIC_OK;
@@ -349,11 +360,13 @@ static bic_status weight_impl(bic_ctx* c, const bic_mat* a, const bic_mat* b, ui
 }
 
 extern "C" bic_status bic_mat_weight(bic_ctx* c, const bic_mat* m, uint64_t* w) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !m || !w) return BIC_ERR_INVALID;
   return weight_impl(c, m, nullptr, w);
 }
 
 extern "C" bic_status bic_mat_dist(bic_ctx* c, const bic_mat* a, const bic_mat* b, uint64_t* d) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !a || !b || !d || a->rows != b->rows || a->cols != b->cols) return BIC_ERR_INVALID;
   return weight_impl(c, a, b, d);
 }
@@ -369,6 +382,7 @@ __global__ void k_xor(const uint32_t* __restrict__ a, const uint32_t* __restrict
 }
 
 extern "C" bic_status bic_mat_xor(bic_ctx* c, const bic_mat* a, const bic_mat* b, bic_mat* o) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !a || !b || !o || a->rows != b->rows || a->cols != b->cols || a->rows != o->rows || a->cols != o->cols)
     return BIC_ERR_INVALID;
   // allocations are padded to 16 B multiples with zero words, so whole uint4s are safe
@@ -409,7 +423,7 @@ extern "C" uint64_t bic_rand48_uniform_int(uint64_t* state, uint64_t n) {
 static const char* const kKernelNames[KID_COUNT] = {
   "k_words64_to_dev", "k_dev_to_words64", "k_pbm_to_dev", "k_dev_to_pbm", "k_weight", "k_xor",
   "k_extract", "k_assemble", "k_row_nonzero", "k_gather_rows", "k_col_hist", "k_pivot_usage", "k_init_finalize",
-  "k_update_coefficients", "k_residual", "k_transpose_bits", "k_update_dictionary",
+  "k_update_coefficients", "k_residual", "k_transpose_bits", "k_update_dictionary", "k_dict_hist_all", "k_dict_resolve",
   "k_compact_rows", "k_expand_rows", "k_gol_tile_counts", "k_gol_scan_tiles_a", "k_gol_walk<0>", "k_gol_scan_tiles_b",
   "k_gol_walk<1>", "k_gol_decode", "k_first_one/zero", "k_fill_ones", "k_eg_encode", "k_eg_decode"};
 
@@ -450,6 +464,7 @@ static void prof_collect(bic_ctx* c) {
 }
 
 extern "C" bic_status bic_prof_enable(bic_ctx* c, int on) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c) return BIC_ERR_INVALID;
   if (!on && c->prof_on) prof_collect(c);
   c->prof_on = on != 0;
@@ -457,6 +472,7 @@ extern "C" bic_status bic_prof_enable(bic_ctx* c, int on) {
 }
 
 extern "C" bic_status bic_prof_reset(bic_ctx* c) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c) return BIC_ERR_INVALID;
   prof_collect(c);
   for (int i = 0; i < KID_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
@@ -466,10 +482,31 @@ extern "C" bic_status bic_prof_reset(bic_ctx* c) {
 extern "C" int bic_prof_kernel_count(void) { return KID_COUNT; }
 
 extern "C" bic_status bic_prof_get(bic_ctx* c, int kid, const char** name, uint64_t* launches, double* total_ms) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || kid < 0 || kid >= KID_COUNT) return BIC_ERR_INVALID;
   prof_collect(c);
   if (name) *name = kKernelNames[kid];
   if (launches) *launches = c->prof_n[kid];
   if (total_ms) *total_ms = c->prof_ms[kid];
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_ctx_set_option(bic_ctx* c, const char* name, int64_t value) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
+  if (!c || !name) return BIC_ERR_INVALID;
+  if (!strcmp(name, "dict_algo")) { if (value < 0 || value > 1) return BIC_ERR_INVALID; c->dict_algo = (int)value; return BIC_OK; }
+  return bic_fail(c, BIC_ERR_INVALID, "unknown option");
+}
+
+// Order `waiter`'s stream after everything queued so far on `signal`'s stream (cross-context
+// dependency for callers that drive several contexts at once).
+extern "C" bic_status bic_ctx_wait_ctx(bic_ctx* waiter, bic_ctx* signal) {
+  if (!waiter || !signal) return BIC_ERR_INVALID;
+  cudaSetDevice(signal->device);
+  cudaEvent_t e = nullptr;
+  BIC_CUDA(waiter, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  BIC_CUDA(waiter, cudaEventRecord(e, signal->stream));
+  BIC_CUDA(waiter, cudaStreamWaitEvent(waiter->stream, e, 0));
+  BIC_CUDA(waiter, cudaEventDestroy(e));
   return BIC_OK;
 }

@@ -195,9 +195,23 @@ static bic_status launch_dict(bic_ctx* c, DictParams& P) {
   return BIC_OK;
 }
 
+bic_status bic_k_transpose_A(bic_ctx* c, const bic_mat* A, uint32_t* AT, uint64_t wprN) {
+  const uint64_t n = A->rows;
+  const uint64_t nblk = div_up_u64(n, 1024);
+  const uint64_t gx = nblk < (uint64_t)c->sm_count * 2 ? nblk : (uint64_t)c->sm_count * 2;
+  dim3 grid((unsigned)gx, (unsigned)A->wpr);
+  BIC_PROF(c, KID_TRANSPOSE_BITS);
+  k_transpose_bits<<<grid, 1024, 0, c->stream>>>(A->d, n, A->wpr, AT, wprN, A->cols);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+bic_status bic_k_update_dictionary_v2(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed);
+
 bic_status bic_k_update_dictionary(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
   if (E->rows != A->rows || E->cols != D->cols || A->cols != D->rows)
     return bic_fail(c, BIC_ERR_INVALID, "update_dictionary: shapes must be E n x m, D p x m, A n x p");
+  if (c->dict_algo != 0) return bic_k_update_dictionary_v2(c, E, D, A, d_changed);
   const uint64_t n = E->rows, p = D->rows, m = E->cols;
   if (n == 0 || p == 0 || m == 0) return BIC_OK;
   if (E->wpr > 128) return bic_fail(c, BIC_ERR_UNSUPPORTED, "update_dictionary: rows wider than 4096 bits");
@@ -209,14 +223,7 @@ bic_status bic_k_update_dictionary(bic_ctx* c, bic_mat* E, bic_mat* D, const bic
   uint32_t* AT = (uint32_t*)c->work[2].p;
   uint32_t* hist = (uint32_t*)c->work[3].p;
   BIC_CUDA(c, cudaMemsetAsync(hist, 0, (size_t)3 * hist_stride * 4, c->stream));
-  {
-    const uint64_t nblk = div_up_u64(n, 1024);
-    const uint64_t gx = nblk < (uint64_t)c->sm_count * 2 ? nblk : (uint64_t)c->sm_count * 2;
-    dim3 grid((unsigned)gx, (unsigned)A->wpr);
-    BIC_PROF(c, KID_TRANSPOSE_BITS);
-    k_transpose_bits<<<grid, 1024, 0, c->stream>>>(A->d, n, A->wpr, AT, wprN, p);
-    BIC_LAUNCH_CHECK(c);
-  }
+  BIC_TRY(bic_k_transpose_A(c, A, AT, wprN));
   DictParams P;
   P.E = E->d; P.D = D->d; P.AT = AT; P.hist = hist; P.changed = d_changed;
   P.n = n; P.wprE = E->wpr; P.wprN = wprN; P.m = m; P.hist_stride = hist_stride; P.p = (uint32_t)p;
@@ -228,6 +235,7 @@ bic_status bic_k_update_dictionary(bic_ctx* c, bic_mat* E, bic_mat* D, const bic
 }
 
 extern "C" bic_status bic_update_dictionary_steepest(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, uint64_t* changed) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !E || !D || !A) return BIC_ERR_INVALID;
   BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, sizeof(uint64_t), c->stream));
   BIC_TRY(bic_k_update_dictionary(c, E, D, A, (unsigned long long*)c->d_scalars));

@@ -1,0 +1,290 @@
+// update_dictionary_steepest, second formulation ("histogram first, resolve in order").
+// Reference: src/bsvd.cpp:463-527. Same results as dict.cu, far fewer dependent steps.
+//
+// dict.cu walks the atoms with one grid barrier (and one latency-bound gather) per atom. But the
+// vote of atom l only differs from what the iteration-start residual gives when an EARLIER atom
+// k < l changed AND some row uses both. So:
+//   pass 1 (one ordinary launch, all atoms at once): H[l][j] = sum over users i of atom l of E_i[j],
+//           usage[l] = number of users -- read from the bit-transposed coefficient matrix AT.
+//   pass 2 (one cooperative launch): for k = 0..p-1 in order, every CTA derives newD_k from H[k]
+//           (weights[j] = D_k[j] ? usage - H[k][j] : H[k][j]; bit = weights[j] > usage/2). If the atom
+//           does not change nothing else happens -- no barrier. If it changes by delta = D_k ^ newD_k,
+//           the grid patches E_i ^= delta for the users i of k and, for every later atom l > k that
+//           row i also uses and every bit j of delta, corrects H[l][j] by +1 (E_i[j] was 0) or -1
+//           (it was 1); then ONE grid barrier. The invariant "H[l] is the column count of atom l's
+//           users in the CURRENT E" therefore holds whenever atom l is resolved: exactly the
+//           Gauss-Seidel order of the reference, with barriers only for atoms that change.
+// Integer atomics are order independent, so the result is deterministic and bit exact.
+#include "bic_internal.cuh"
+
+
+// ------------------------------------------------------------------ pass 1
+// Work item = (atom, chunk of 32 AT words = 1024 rows). Each warp owns a contiguous run of items.
+// For a chunk, lane l holds AT word l; in rounds every lane takes its next user row, loads that
+// row's words (32 independent gathers in flight per warp), and the 32x32 bit tile is transposed
+// with ballots so lane b accumulates the count of bit b.
+template <int WORDS>
+__global__ void __launch_bounds__(256) k_dict_hist_all(const uint32_t* __restrict__ E, const uint32_t* __restrict__ AT,
+                                                       uint32_t* __restrict__ H, uint32_t* __restrict__ U, uint64_t wprE,
+                                                       uint64_t wprN, uint64_t hs, uint32_t p) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t nchunks = div_up_u64(wprN, 32);
+  const uint64_t total = (uint64_t)p * nchunks;
+  const uint64_t per = div_up_u64(total, nwarps);
+  uint64_t it = gw * per;
+  const uint64_t it_end = (it + per < total) ? it + per : total;
+  uint32_t cnt[WORDS];
+#pragma unroll
+  for (int w = 0; w < WORDS; ++w) cnt[w] = 0;
+  uint32_t ucnt = 0;
+  uint64_t cur_k = ~0ull;
+  for (; it < it_end; ++it) {
+    const uint64_t k = it / nchunks, ch = it - k * nchunks;
+    if (k != cur_k) {
+      if (cur_k != ~0ull) {
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) {
+          if (cnt[w]) atomicAdd(&H[cur_k * hs + w * 32 + lane], cnt[w]);
+          cnt[w] = 0;
+        }
+        ucnt = warp_sum_u32(ucnt);
+        if (lane == 0 && ucnt) atomicAdd(&U[cur_k], ucnt);
+        ucnt = 0;
+      }
+      cur_k = k;
+    }
+    const uint64_t wi = ch * 32 + lane;
+    uint32_t bits = (wi < wprN) ? __ldg(AT + k * wprN + wi) : 0u;
+    ucnt += __popc(bits);
+    const uint64_t row0 = wi * 32;
+    while (__any_sync(0xffffffffu, bits != 0)) {
+      uint32_t x[WORDS];
+      if (bits) {
+        const int pos = __clz(bits);
+        bits &= ~(0x80000000u >> pos);
+        const uint32_t* erow = E + (row0 + pos) * wprE;
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) x[w] = ((uint64_t)w < wprE) ? __ldg(erow + w) : 0u;
+      } else {
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) x[w] = 0u;
+      }
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) {
+        if (__any_sync(0xffffffffu, x[w] != 0)) {
+#pragma unroll
+          for (int b = 0; b < 32; ++b) {
+            const uint32_t t = __ballot_sync(0xffffffffu, (x[w] >> (31 - b)) & 1u);
+            if (lane == b) cnt[w] += __popc(t);
+          }
+        }
+      }
+    }
+  }
+  if (cur_k != ~0ull) {
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w)
+      if (cnt[w]) atomicAdd(&H[cur_k * hs + w * 32 + lane], cnt[w]);
+    ucnt = warp_sum_u32(ucnt);
+    if (lane == 0 && ucnt) atomicAdd(&U[cur_k], ucnt);
+  }
+}
+
+// ------------------------------------------------------------------ pass 2
+// One ordinary launch resolves atoms in order from a device-side cursor up to and including the
+// FIRST atom that changes, applies that atom's corrections, and stores the next cursor. Launches
+// of one stream run in order, so the next launch sees the corrected histograms: the grid barrier
+// of a cooperative kernel is replaced by the launch boundary (cooperative launches from several
+// streams -- one per page in flight -- serialise against everything else on the GPU).
+// A launch whose cursor already reached p returns at once, so the host may queue a few launches
+// ahead without knowing how many atoms will change.
+struct ResolveParams {
+  uint32_t* E;
+  const uint32_t* D;     // the dictionary as it was when the update started (never written here)
+  uint32_t* Dnew;        // receives the changed atoms
+  const uint32_t* A;
+  const uint32_t* AT;
+  uint32_t* H;
+  const uint32_t* U;
+  unsigned long long* changed;
+  uint32_t* cursor;      // [2]: this launch reads [parity], writes [parity ^ 1]
+  uint64_t n, wprE, wprA, wprN, m, hs;
+  uint32_t p, parity, win;  // win: histogram rows cached in shared memory per refill
+};
+
+__global__ void __launch_bounds__(256) k_dict_resolve_step(ResolveParams P) {
+  extern __shared__ uint32_t s_mem[];
+  uint32_t* s_delta = s_mem;              // wprE
+  uint32_t* s_U = s_delta + P.wprE;       // win
+  uint32_t* s_H = s_U + P.win;            // win * hs
+  __shared__ int s_any;
+  const int lane = threadIdx.x & 31;
+  const uint32_t start = __ldcg(P.cursor + P.parity);
+  if (start >= P.p) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.cursor[P.parity ^ 1] = P.p;
+    return;
+  }
+  uint32_t k = start;
+  uint32_t win0 = start, win1 = start;    // cached rows [win0, win1)
+  int any = 0;
+  for (; k < P.p; ++k) {
+    if (k >= win1) {                      // refill: rows <= the first changing atom are stable
+      __syncthreads();
+      win0 = k;
+      win1 = (k + P.win < P.p) ? k + P.win : P.p;
+      for (uint64_t i = threadIdx.x; i < (uint64_t)(win1 - win0) * P.hs; i += blockDim.x)
+        s_H[i] = __ldcg(P.H + (uint64_t)win0 * P.hs + i);
+      for (uint32_t i = threadIdx.x; i < win1 - win0; i += blockDim.x) s_U[i] = __ldcg(P.U + win0 + i);
+      __syncthreads();
+    }
+    const uint32_t usage = s_U[k - win0];
+    if (usage == 0) continue;             // src/bsvd.cpp:499-500
+    const uint32_t half = usage >> 1;     // :502
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    const uint32_t* hk = s_H + (uint64_t)(k - win0) * P.hs;
+    for (uint64_t w = threadIdx.x >> 5; w < P.wprE; w += blockDim.x >> 5) {
+      const uint64_t j = w * 32 + lane;
+      const uint32_t dk = __ldg(P.D + (uint64_t)k * P.wprE + w);
+      uint32_t bit = 0;
+      if (j < P.m) {
+        const uint32_t ce = hk[j];
+        const uint32_t weight = ((dk >> (31 - lane)) & 1u) ? usage - ce : ce;  // sum of (E_i ^ D_k)[j] over users
+        bit = weight > half;              // strict >, :504-506
+      }
+      const uint32_t nd = __brev(__ballot_sync(0xffffffffu, bit));
+      if (lane == 0) {
+        s_delta[w] = nd ^ dk;
+        if (nd != dk) s_any = 1;
+      }
+    }
+    __syncthreads();
+    any = s_any;
+    __syncthreads();                      // s_any / s_delta are rewritten at the next atom
+    if (any) break;                       // dist(newDk, Dk) > 0, :507 (same decision in every CTA)
+  }
+  if (!any) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.cursor[P.parity ^ 1] = P.p;
+    return;
+  }
+  // ---- atom k changes: patch its users' residuals and the histograms of the later atoms they use
+  const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t nchunks = div_up_u64(P.wprN, 32);
+  const uint32_t* at = P.AT + (uint64_t)k * P.wprN;
+  for (uint64_t ch = gw; ch < nchunks; ch += nwarps) {
+    const uint64_t wi = ch * 32 + lane;
+    uint32_t bits = (wi < P.wprN) ? __ldg(at + wi) : 0u;
+    const uint64_t row0 = wi * 32;
+    while (bits) {
+      const int pos = __clz(bits);
+      bits &= ~(0x80000000u >> pos);
+      const uint64_t i = row0 + pos;
+      uint32_t* erow = P.E + i * P.wprE;
+      const uint32_t* arow = P.A + i * P.wprA;
+      for (uint64_t aw = k >> 5; aw < P.wprA; ++aw) {   // later atoms used by this row
+        uint32_t ab = __ldg(arow + aw);
+        if (aw == (k >> 5)) ab &= (0x7FFFFFFFu >> (k & 31));  // strictly after k
+        while (ab) {
+          const int ap = __clz(ab);
+          ab &= ~(0x80000000u >> ap);
+          uint32_t* hl = P.H + (aw * 32 + ap) * P.hs;
+          for (uint64_t w = 0; w < P.wprE; ++w) {
+            uint32_t dl = s_delta[w];
+            if (!dl) continue;
+            const uint32_t e = erow[w];
+            while (dl) {
+              const int bp = __clz(dl);
+              dl &= ~(0x80000000u >> bp);
+              atomicAdd(hl + w * 32 + bp, ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u);
+            }
+          }
+        }
+      }
+      for (uint64_t w = 0; w < P.wprE; ++w) {           // E_i ^= Dk ^ newDk, :512-520
+        const uint32_t dl = s_delta[w];
+        if (dl) erow[w] ^= dl;
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (uint64_t w = threadIdx.x; w < P.wprE; w += blockDim.x)
+      P.Dnew[(uint64_t)k * P.wprE + w] = __ldg(P.D + (uint64_t)k * P.wprE + w) ^ s_delta[w];  // :510
+    if (threadIdx.x == 0) {
+      atomicAdd(P.changed, 1ull);                       // :509
+      P.cursor[P.parity ^ 1] = k + 1;
+    }
+  }
+}
+
+template <int WORDS>
+static bic_status launch_hist_all(bic_ctx* c, const bic_mat* E, const uint32_t* AT, uint32_t* H, uint32_t* U, uint64_t wprN,
+                                  uint64_t hs, uint32_t p) {
+  const uint64_t items = (uint64_t)p * div_up_u64(wprN, 32);
+  const int grid = bic_grid_for(c, items * 32, 256, WORDS >= 32 ? 4 : 8);
+  BIC_PROF(c, KID_DICT_HIST);
+  k_dict_hist_all<WORDS><<<grid, 256, 0, c->stream>>>(E->d, AT, H, U, E->wpr, wprN, hs, p);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+bic_status bic_k_transpose_A(bic_ctx* c, const bic_mat* A, uint32_t* AT, uint64_t wprN);
+
+bic_status bic_k_update_dictionary_v2(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
+  if (E->rows != A->rows || E->cols != D->cols || A->cols != D->rows)
+    return bic_fail(c, BIC_ERR_INVALID, "update_dictionary: shapes must be E n x m, D p x m, A n x p");
+  const uint64_t n = E->rows, p = D->rows, m = E->cols;
+  if (n == 0 || p == 0 || m == 0) return BIC_OK;
+  if (E->wpr > 128) return bic_fail(c, BIC_ERR_UNSUPPORTED, "update_dictionary: rows wider than 4096 bits");
+  const uint64_t wprN = div_up_u64(n, 32);
+  const uint64_t hs = E->wpr * 32;
+  // work[2]: AT (p * wprN u32) ; work[3]: H (p * hs u32) + U (p u32)
+  BIC_TRY(bic_scratch_reserve(c, &c->work[2], (size_t)p * wprN * 4));
+  BIC_TRY(bic_scratch_reserve(c, &c->work[3], (size_t)(p * hs + p) * 4));
+  uint32_t* AT = (uint32_t*)c->work[2].p;
+  uint32_t* H = (uint32_t*)c->work[3].p;
+  uint32_t* U = H + p * hs;
+  BIC_CUDA(c, cudaMemsetAsync(H, 0, (size_t)(p * hs + p) * 4, c->stream));
+  BIC_TRY(bic_k_transpose_A(c, A, AT, wprN));
+  const uint64_t wpr = E->wpr;
+  if (wpr <= 2) BIC_TRY(launch_hist_all<2>(c, E, AT, H, U, wprN, hs, (uint32_t)p));
+  else if (wpr <= 8) BIC_TRY(launch_hist_all<8>(c, E, AT, H, U, wprN, hs, (uint32_t)p));
+  else if (wpr <= 32) BIC_TRY(launch_hist_all<32>(c, E, AT, H, U, wprN, hs, (uint32_t)p));
+  else BIC_TRY(launch_hist_all<128>(c, E, AT, H, U, wprN, hs, (uint32_t)p));
+
+  // work[1] tail is free here (init is over): Dnew (p * wpr u32) + cursor (2 u32) live in work[0]
+  BIC_TRY(bic_scratch_reserve(c, &c->work[0], (size_t)p * wpr * 4 + 64));
+  uint32_t* Dnew = (uint32_t*)c->work[0].p;
+  uint32_t* cursor = Dnew + p * wpr;
+  BIC_CUDA(c, cudaMemcpyAsync(Dnew, D->d, (size_t)p * wpr * 4, cudaMemcpyDeviceToDevice, c->stream));
+  BIC_CUDA(c, cudaMemsetAsync(cursor, 0, 8, c->stream));
+  ResolveParams P;
+  P.E = E->d; P.D = D->d; P.Dnew = Dnew; P.A = A->d; P.AT = AT; P.H = H; P.U = U; P.changed = d_changed; P.cursor = cursor;
+  P.n = n; P.wprE = wpr; P.wprA = A->wpr; P.wprN = wprN; P.m = m; P.hs = hs; P.p = (uint32_t)p;
+  uint64_t win = (32 * 1024 / 4) / (hs + 1);
+  if (win < 1) win = 1;
+  if (win > p) win = p;
+  P.win = (uint32_t)win;
+  const size_t smem = (size_t)(wpr + win * (hs + 1)) * 4;
+  const int grid = bic_grid_for(c, div_up_u64(wprN, 32) * 32, 256, 4);
+  // Queue launches ahead; each returns at once when the cursor is already at p. The cursor is read
+  // back together with the change counter; more launches follow only if atoms are still pending.
+  uint32_t launched = 0, batch = 8;
+  uint32_t* h_cursor = (uint32_t*)(c->h_scalars + 32);
+  for (;;) {
+    for (uint32_t i = 0; i < batch && launched < p; ++i, ++launched) {
+      P.parity = launched & 1;
+      BIC_PROF(c, KID_DICT_RESOLVE);
+      k_dict_resolve_step<<<grid, 256, smem, c->stream>>>(P);
+      BIC_LAUNCH_CHECK(c);
+    }
+    BIC_CUDA(c, cudaMemcpyAsync(h_cursor, cursor + (launched & 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (*h_cursor >= p || launched >= p) break;
+    batch = (batch * 2 < 64) ? batch * 2 : 64;
+  }
+  BIC_CUDA(c, cudaMemcpyAsync(D->d, Dnew, (size_t)p * wpr * 4, cudaMemcpyDeviceToDevice, c->stream));
+  return BIC_OK;
+}

@@ -9,6 +9,7 @@ bic_status bic_k_update_dictionary(bic_ctx* c, bic_mat* E, bic_mat* D, const bic
 
 extern "C" bic_status bic_learn_model_traditional(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat* D, bic_mat* A,
                                                   uint64_t* iterations, uint64_t* trace, uint64_t trace_cap) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !X || !E || !D || !A) return BIC_ERR_INVALID;
   BIC_TRY(bic_residual(c, X, A, D, E));  // mul(A,false,D,false,E); add(E,X,E)  src/bsvd.cpp:1219-1220
   uint64_t changed = 1, iter = 0;
@@ -83,6 +84,7 @@ static bic_status ws_prepare(bic_ctx* c, EncWorkspace* w, uint64_t rows, uint64_
 extern "C" bic_status bic_encode_raster(bic_ctx* c, const uint8_t* pbm_payload, uint64_t rows, uint64_t cols, uint64_t W,
                                         uint64_t K, unsigned long seed, uint8_t* out, uint64_t cap_bytes,
                                         bic_encode_info* info) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !pbm_payload || W == 0 || K == 0 || rows == 0 || cols == 0) return BIC_ERR_INVALID;
   EncWorkspace* w = ws_of(c);
   BIC_TRY(ws_prepare(c, w, rows, cols, W, K));
@@ -128,6 +130,7 @@ extern "C" bic_status bic_encode_raster(bic_ctx* c, const uint8_t* pbm_payload, 
 
 extern "C" bic_status bic_decode_raster(bic_ctx* c, const uint8_t* cont, uint64_t nbytes, uint8_t* pbm_payload,
                                         uint64_t cap_bytes, uint64_t* rows_out, uint64_t* cols_out) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !cont) return BIC_ERR_INVALID;
   const uint64_t hdr = (HDR_FIELDS + 3 * STREAM_FIELDS) * 8;
   if (nbytes < hdr) return bic_fail(c, BIC_ERR_CORRUPT, "container: truncated header");

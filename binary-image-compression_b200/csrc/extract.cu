@@ -83,6 +83,7 @@ __global__ void k_assemble(const uint32_t* __restrict__ X, uint32_t* __restrict_
 }
 
 extern "C" bic_status bic_extract_patches(bic_ctx* c, const bic_mat* raster, uint64_t W, bic_mat* X) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !raster || !X || W == 0) return BIC_ERR_INVALID;
   const uint64_t Ny = (W - 1 + raster->rows) / W, Nx = (W - 1 + raster->cols) / W;  // bsvd_test.cpp:82-83
   if (X->rows != Nx * Ny || X->cols != W * W) return bic_fail(c, BIC_ERR_INVALID, "extract: X must be Nx*Ny x W*W");
@@ -95,6 +96,7 @@ extern "C" bic_status bic_extract_patches(bic_ctx* c, const bic_mat* raster, uin
 }
 
 extern "C" bic_status bic_assemble_patches(bic_ctx* c, const bic_mat* X, uint64_t W, bic_mat* raster) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !raster || !X || W == 0) return BIC_ERR_INVALID;
   const uint64_t Ny = (W - 1 + raster->rows) / W, Nx = (W - 1 + raster->cols) / W;
   if (X->rows != Nx * Ny || X->cols != W * W) return bic_fail(c, BIC_ERR_INVALID, "assemble: X must be Nx*Ny x W*W");

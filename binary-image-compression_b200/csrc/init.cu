@@ -38,6 +38,7 @@ bic_status bic_k_row_nonzero_bitmap(bic_ctx* c, const bic_mat* X, uint32_t* d_bi
 
 extern "C" bic_status bic_draw_pivots(bic_ctx* c, const bic_mat* X, uint64_t p, uint64_t* rng_state,
                                       uint64_t* pivots_out, uint64_t* ndraws_out) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !X || !rng_state || (!pivots_out && p)) return BIC_ERR_INVALID;
   const uint64_t n = X->rows;
   if (p == 0) { if (ndraws_out) *ndraws_out = 0; return BIC_OK; }
@@ -176,6 +177,7 @@ static bic_status launch_usage(bic_ctx* c, const bic_mat* X, const uint32_t* P, 
 
 extern "C" bic_status bic_initialize_model_neighbor_pivots(bic_ctx* c, const bic_mat* X, const uint64_t* pivots,
                                                            uint64_t p, bic_mat* D, bic_mat* A) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !X || !D || !A || (!pivots && p)) return BIC_ERR_INVALID;
   if (D->rows != p || D->cols != X->cols || A->rows != X->rows || A->cols != p)
     return bic_fail(c, BIC_ERR_INVALID, "init: shapes must be X n x m, D p x m, A n x p");
@@ -241,6 +243,7 @@ extern "C" bic_status bic_initialize_model_neighbor_pivots(bic_ctx* c, const bic
 
 extern "C" bic_status bic_initialize_model_neighbor(bic_ctx* c, const bic_mat* X, bic_mat* D, bic_mat* A,
                                                     uint64_t* rng_state) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !X || !D || !A || !rng_state) return BIC_ERR_INVALID;
   const uint64_t p = D->rows;
   std::vector<uint64_t> piv(p ? p : 1);

@@ -58,6 +58,12 @@ const char* bic_ctx_last_error(bic_ctx* ctx);
 const char* bic_status_string(bic_status s);
 void* bic_ctx_cuda_stream(bic_ctx* ctx);
 int bic_ctx_sm_count(bic_ctx* ctx);
+/* make `waiter`'s stream wait for everything queued so far on `signal`'s stream (for callers
+ * that run several contexts -- one per independent page -- concurrently) */
+bic_status bic_ctx_wait_ctx(bic_ctx* waiter, bic_ctx* signal);
+/* tuning switches. "dict_algo": 1 (default) = all atom histograms in one pass, then an in-order
+ * resolve with a grid barrier only for atoms that change; 0 = one barrier per atom. Same results. */
+bic_status bic_ctx_set_option(bic_ctx* ctx, const char* name, int64_t value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t bic_ctx_launch_count(bic_ctx* ctx);
 /* device timers on the context's stream (cudaEvent pairs): ms between start and stop */

@@ -99,8 +99,10 @@ FIT_SHAPES = [  # rows, cols, W, K, seed
 ]
 
 
+@pytest.mark.parametrize("dict_algo", [1, 0])
 @pytest.mark.parametrize("rows,cols,W,K,seed", FIT_SHAPES)
-def test_fit_vs_oracle(ctx, oracle, synth, rows, cols, W, K, seed):
+def test_fit_vs_oracle(ctx, oracle, synth, rows, cols, W, K, seed, dict_algo):
+    ctx.set_option("dict_algo", dict_algo)  # 1: histogram-first resolve (default), 0: per-atom walk
     page = synth.structured_page(rows, cols, seed=seed, salt=0.01)
     Iw = synth.pack_rows(page)
     m = W * W
@@ -145,10 +147,13 @@ def test_fit_vs_oracle(ctx, oracle, synth, rows, cols, W, K, seed):
     assert np.array_equal(R.download(), Iw)
     for mm in (I, X, D, A, E, R):
         mm.destroy()
+    ctx.set_option("dict_algo", 1)
 
 
-def test_matrix_mode_wide_rows(ctx, oracle, synth):
+@pytest.mark.parametrize("dict_algo", [1, 0])
+def test_matrix_mode_wide_rows(ctx, oracle, synth, dict_algo):
     """-I 0 (rows are the samples, bsvd_test.cpp:101-106) with m = 1100 > 1024: wide-row kernels"""
+    ctx.set_option("dict_algo", dict_algo)
     page = synth.structured_page(300, 1100, seed=31, salt=0.01)
     Xo = synth.pack_rows(page)
     m, K = 1100, 9
@@ -162,6 +167,29 @@ def test_matrix_mode_wide_rows(ctx, oracle, synth):
     it, tr = ctx.learn_model_traditional(X, E, D, A)
     assert it == ito and np.array_equal(tr, tro)
     assert np.array_equal(D.download(), Do) and np.array_equal(A.download(), Ao) and np.array_equal(E.download(), Eo)
+    ctx.set_option("dict_algo", 1)
+
+
+def test_dense_coefficients_many_shared_rows(ctx, oracle, synth):
+    """noise input with few atoms: most rows use several atoms, so a changed atom has to correct
+    the histograms of many later atoms (the cross-atom path of the dictionary update)"""
+    rng = np.random.default_rng(11)
+    bits = (rng.random((4000, 64)) < 0.35).astype(np.uint8)
+    bits[:, :16] |= (rng.random((4000, 1)) < 0.5).astype(np.uint8)
+    Xo = synth.pack_rows(bits)
+    m, K = 64, 6
+    piv, _ = oracle.draw_pivots(Xo, m, K, oracle.rng(3))
+    for algo in (1, 0):
+        ctx.set_option("dict_algo", algo)
+        Do, Ao = oracle.init_neighbor_pivots(Xo, m, K, piv)
+        X = ctx.matrix(4000, m, Xo)
+        D, A, E = ctx.matrix(K, m), ctx.matrix(4000, K), ctx.matrix(4000, m)
+        ctx.initialize_model_neighbor_pivots(X, piv, D, A)
+        Eo, ito, tro = oracle.learn_traditional(Xo, Do, Ao, m, K)
+        it, tr = ctx.learn_model_traditional(X, E, D, A)
+        assert it == ito and np.array_equal(tr, tro)
+        assert np.array_equal(D.download(), Do) and np.array_equal(A.download(), Ao) and np.array_equal(E.download(), Eo)
+    ctx.set_option("dict_algo", 1)
 
 
 # ---------------------------------------------------------------- coders
