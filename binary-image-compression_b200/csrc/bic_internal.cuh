@@ -142,6 +142,24 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// 32x32 bit-matrix transpose across a warp. In: lane r holds row r (bit c of the row at bit
+// 31-c of the word, MSB first). Out: lane c holds column c (row r at bit 31-r). Five butterfly
+// stages, each one shuffle + a masked merge.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
+  const unsigned lane = threadIdx.x & 31;
+#define BIC_T32_STAGE(S, HI)                                                         \
+  {                                                                                   \
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, S);                            \
+    x = (lane & S) ? (((y << S) & (HI)) | (x & ~(HI))) : ((x & (HI)) | ((y >> S) & ~(HI))); \
+  }
+  BIC_T32_STAGE(16, 0xFFFF0000u)
+  BIC_T32_STAGE(8, 0xFF00FF00u)
+  BIC_T32_STAGE(4, 0xF0F0F0F0u)
+  BIC_T32_STAGE(2, 0xCCCCCCCCu)
+  BIC_T32_STAGE(1, 0xAAAAAAAAu)
+#undef BIC_T32_STAGE
+  return x;
+}
 // mask of the valid bits of the last word of a row with `cols` columns
 __host__ __device__ __forceinline__ uint32_t tail_mask32(uint64_t cols) {
   const unsigned r = (unsigned)(cols & 31);

@@ -35,12 +35,7 @@ __global__ void __launch_bounds__(1024) k_transpose_bits(const uint32_t* __restr
   for (uint64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     const uint64_t r = blk * 1024 + (uint64_t)wib * 32 + lane;
     const uint32_t v = (r < n) ? A[r * wprA + cw] : 0u;
-    uint32_t mine = 0;
-#pragma unroll
-    for (int b = 0; b < 32; ++b) {
-      const uint32_t t = __ballot_sync(0xffffffffu, (v >> (31 - b)) & 1u);  // bit l = row l of the tile
-      if (lane == b) mine = __brev(t);                                      // MSB first along rows
-    }
+    const uint32_t mine = warp_transpose32(v);  // lane b: atom b of the slab, rows of this warp
     tile[lane][wib] = mine;  // atom `lane` of the slab, row-word `wib` of the block
     __syncthreads();
     const uint64_t atom = cw * 32 + wib;

@@ -19,77 +19,69 @@
 
 
 // ------------------------------------------------------------------ pass 1
-// Work item = (atom, chunk of 32 AT words = 1024 rows). Each warp owns a contiguous run of items.
-// For a chunk, lane l holds AT word l; in rounds every lane takes its next user row, loads that
-// row's words (32 independent gathers in flight per warp), and the 32x32 bit tile is transposed
-// with ballots so lane b accumulates the count of bit b.
-template <int WORDS>
-__global__ void __launch_bounds__(256) k_dict_hist_all(const uint32_t* __restrict__ E, const uint32_t* __restrict__ AT,
-                                                       uint32_t* __restrict__ H, uint32_t* __restrict__ U, uint64_t wprE,
-                                                       uint64_t wprN, uint64_t hs, uint32_t p) {
+// H = A^T * E as integer counts: H[k][j] = sum_i A[i][k] * E[i][j] = popc(column k of A AND column j
+// of E). A warp takes a block of 32 consecutive rows: lane r loads A word kw and JW words of E of
+// row r (coalesced), both 32x32 bit tiles are transposed in registers (shuffle butterfly), so lane
+// l then holds, for atom kw*32+l, the 32 rows' usage bits, and for bit column l of every E word the
+// 32 rows' residual bits. Atom words are broadcast with shuffles and every lane accumulates
+// popc(users_k & column_j) for its 32 x JW (k, j) pairs: AND + POPC on the XU pipe, no divergence,
+// no gather. Tiles (kw, JW-word group of E) are spread over blockIdx.y for larger p and m.
+template <int JW>
+__global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restrict__ E, const uint32_t* __restrict__ A,
+                                                        uint32_t* __restrict__ H, uint32_t* __restrict__ U, uint64_t n,
+                                                        uint64_t wprE, uint64_t wprA, uint64_t hs, uint32_t ntile_j) {
+  __shared__ uint32_t s_acc[32 * JW * 32];
+  __shared__ uint32_t s_u[32];
   const int lane = threadIdx.x & 31;
+  const uint32_t kw = blockIdx.y / ntile_j, jt = blockIdx.y - kw * ntile_j;
+  const uint64_t jw0 = (uint64_t)jt * JW;
+  for (int i = threadIdx.x; i < 32 * JW * 32; i += blockDim.x) s_acc[i] = 0;
+  if (threadIdx.x < 32) s_u[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t acc[32][JW];
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+#pragma unroll
+    for (int w = 0; w < JW; ++w) acc[k][w] = 0;
+  uint32_t ucnt = 0;
   const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint64_t nchunks = div_up_u64(wprN, 32);
-  const uint64_t total = (uint64_t)p * nchunks;
-  const uint64_t per = div_up_u64(total, nwarps);
-  uint64_t it = gw * per;
-  const uint64_t it_end = (it + per < total) ? it + per : total;
-  uint32_t cnt[WORDS];
+  const uint64_t nblocks = div_up_u64(n, 32);
+  for (uint64_t blk = gw; blk < nblocks; blk += nwarps) {
+    const uint64_t row = blk * 32 + lane;
+    const uint32_t a = (row < n) ? __ldg(A + row * wprA + kw) : 0u;
+    if (!__any_sync(0xffffffffu, a != 0)) continue;  // none of these 32 rows uses these 32 atoms
+    uint32_t et[JW];
 #pragma unroll
-  for (int w = 0; w < WORDS; ++w) cnt[w] = 0;
-  uint32_t ucnt = 0;
-  uint64_t cur_k = ~0ull;
-  for (; it < it_end; ++it) {
-    const uint64_t k = it / nchunks, ch = it - k * nchunks;
-    if (k != cur_k) {
-      if (cur_k != ~0ull) {
-#pragma unroll
-        for (int w = 0; w < WORDS; ++w) {
-          if (cnt[w]) atomicAdd(&H[cur_k * hs + w * 32 + lane], cnt[w]);
-          cnt[w] = 0;
-        }
-        ucnt = warp_sum_u32(ucnt);
-        if (lane == 0 && ucnt) atomicAdd(&U[cur_k], ucnt);
-        ucnt = 0;
-      }
-      cur_k = k;
+    for (int w = 0; w < JW; ++w) {
+      const uint32_t e = (row < n && jw0 + w < wprE) ? __ldg(E + row * wprE + jw0 + w) : 0u;
+      et[w] = warp_transpose32(e);
     }
-    const uint64_t wi = ch * 32 + lane;
-    uint32_t bits = (wi < wprN) ? __ldg(AT + k * wprN + wi) : 0u;
-    ucnt += __popc(bits);
-    const uint64_t row0 = wi * 32;
-    while (__any_sync(0xffffffffu, bits != 0)) {
-      uint32_t x[WORDS];
-      if (bits) {
-        const int pos = __clz(bits);
-        bits &= ~(0x80000000u >> pos);
-        const uint32_t* erow = E + (row0 + pos) * wprE;
+    const uint32_t at = warp_transpose32(a);
+    ucnt += __popc(at);
 #pragma unroll
-        for (int w = 0; w < WORDS; ++w) x[w] = ((uint64_t)w < wprE) ? __ldg(erow + w) : 0u;
-      } else {
+    for (int k = 0; k < 32; ++k) {
+      const uint32_t ak = __shfl_sync(0xffffffffu, at, k);
 #pragma unroll
-        for (int w = 0; w < WORDS; ++w) x[w] = 0u;
-      }
-#pragma unroll
-      for (int w = 0; w < WORDS; ++w) {
-        if (__any_sync(0xffffffffu, x[w] != 0)) {
-#pragma unroll
-          for (int b = 0; b < 32; ++b) {
-            const uint32_t t = __ballot_sync(0xffffffffu, (x[w] >> (31 - b)) & 1u);
-            if (lane == b) cnt[w] += __popc(t);
-          }
-        }
-      }
+      for (int w = 0; w < JW; ++w) acc[k][w] += __popc(ak & et[w]);
     }
   }
-  if (cur_k != ~0ull) {
+  // CTA reduction in shared memory (lane-distinct banks), then one global atomic per nonzero count
 #pragma unroll
-    for (int w = 0; w < WORDS; ++w)
-      if (cnt[w]) atomicAdd(&H[cur_k * hs + w * 32 + lane], cnt[w]);
-    ucnt = warp_sum_u32(ucnt);
-    if (lane == 0 && ucnt) atomicAdd(&U[cur_k], ucnt);
+  for (int k = 0; k < 32; ++k)
+#pragma unroll
+    for (int w = 0; w < JW; ++w)
+      if (acc[k][w]) atomicAdd(&s_acc[(k * JW + w) * 32 + lane], acc[k][w]);
+  if (jt == 0 && ucnt) atomicAdd(&s_u[lane], ucnt);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * JW * 32; i += blockDim.x) {
+    const uint32_t v = s_acc[i];
+    if (v) {
+      const int l = i & 31, kwv = i >> 5, w = kwv % JW, k = kwv / JW;
+      atomicAdd(&H[((uint64_t)kw * 32 + k) * hs + (jw0 + w) * 32 + l], v);
+    }
   }
+  if (jt == 0 && threadIdx.x < 32 && s_u[threadIdx.x]) atomicAdd(&U[kw * 32 + threadIdx.x], s_u[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------ pass 2
@@ -219,13 +211,20 @@ __global__ void __launch_bounds__(256) k_dict_resolve_step(ResolveParams P) {
   }
 }
 
-template <int WORDS>
-static bic_status launch_hist_all(bic_ctx* c, const bic_mat* E, const uint32_t* AT, uint32_t* H, uint32_t* U, uint64_t wprN,
-                                  uint64_t hs, uint32_t p) {
-  const uint64_t items = (uint64_t)p * div_up_u64(wprN, 32);
-  const int grid = bic_grid_for(c, items * 32, 256, WORDS >= 32 ? 4 : 8);
+static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs) {
+  const uint64_t n = E->rows;
+  const bool two = E->wpr >= 2;
+  const uint32_t ntile_j = (uint32_t)(two ? div_up_u64(E->wpr, 2) : 1);
+  const uint32_t ntiles = (uint32_t)A->wpr * ntile_j;
+  // persistent in x: about two CTAs per SM overall, at least one block of rows per warp
+  uint64_t gx = div_up_u64((uint64_t)c->sm_count * 2, ntiles);
+  const uint64_t need = div_up_u64(div_up_u64(n, 32), 8);
+  if (gx > need) gx = need;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, ntiles);
   BIC_PROF(c, KID_DICT_HIST);
-  k_dict_hist_all<WORDS><<<grid, 256, 0, c->stream>>>(E->d, AT, H, U, E->wpr, wprN, hs, p);
+  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j);
+  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }
@@ -237,7 +236,6 @@ bic_status bic_k_update_dictionary_v2(bic_ctx* c, bic_mat* E, bic_mat* D, const 
     return bic_fail(c, BIC_ERR_INVALID, "update_dictionary: shapes must be E n x m, D p x m, A n x p");
   const uint64_t n = E->rows, p = D->rows, m = E->cols;
   if (n == 0 || p == 0 || m == 0) return BIC_OK;
-  if (E->wpr > 128) return bic_fail(c, BIC_ERR_UNSUPPORTED, "update_dictionary: rows wider than 4096 bits");
   const uint64_t wprN = div_up_u64(n, 32);
   const uint64_t hs = E->wpr * 32;
   // work[2]: AT (p * wprN u32) ; work[3]: H (p * hs u32) + U (p u32)
@@ -249,10 +247,7 @@ bic_status bic_k_update_dictionary_v2(bic_ctx* c, bic_mat* E, bic_mat* D, const 
   BIC_CUDA(c, cudaMemsetAsync(H, 0, (size_t)(p * hs + p) * 4, c->stream));
   BIC_TRY(bic_k_transpose_A(c, A, AT, wprN));
   const uint64_t wpr = E->wpr;
-  if (wpr <= 2) BIC_TRY(launch_hist_all<2>(c, E, AT, H, U, wprN, hs, (uint32_t)p));
-  else if (wpr <= 8) BIC_TRY(launch_hist_all<8>(c, E, AT, H, U, wprN, hs, (uint32_t)p));
-  else if (wpr <= 32) BIC_TRY(launch_hist_all<32>(c, E, AT, H, U, wprN, hs, (uint32_t)p));
-  else BIC_TRY(launch_hist_all<128>(c, E, AT, H, U, wprN, hs, (uint32_t)p));
+  BIC_TRY(launch_hist(c, E, A, H, U, hs));
 
   // work[1] tail is free here (init is over): Dnew (p * wpr u32) + cursor (2 u32) live in work[0]
   BIC_TRY(bic_scratch_reserve(c, &c->work[0], (size_t)p * wpr * 4 + 64));
