@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--atoms", type=int, default=32)
     ap.add_argument("--cpu-crop", type=int, default=2048, help="crop edge for the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=8, help="contexts (CUDA streams) per GPU")
+    ap.add_argument("--streams", type=int, default=16, help="contexts (CUDA streams) per GPU")
     return ap.parse_args()
 
 
