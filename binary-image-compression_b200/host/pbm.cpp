@@ -19,9 +19,12 @@ ErrorCode read_pbm_data(FILE* f, binary_matrix& A) {
   const idx_t bpr = (A.get_cols() + 7) / 8;
   std::vector<unsigned char> line(bpr ? bpr : 1);
   for (idx_t i = 0; i < A.get_rows(); ++i) {
-    if (fread(line.data(), 1, bpr, f) != bpr) return PBM_INVALID_DATA;
-    for (idx_t j = 0; j < A.get_cols(); ++j)
+    // like the reference (src/pbm.cpp:37-47) a short read keeps the pixels that did arrive: its
+    // header parser (" %d ", :18) also swallows leading data bytes that happen to be white space
+    const size_t got = fread(line.data(), 1, bpr, f);
+    for (idx_t j = 0; j < A.get_cols() && (j >> 3) < got; ++j)
       if (line[j >> 3] & (0x80u >> (j & 7))) A.set(i, j);
+    if (got != bpr) return PBM_INVALID_DATA;
   }
   return PBM_OK;
 }
