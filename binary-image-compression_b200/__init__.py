@@ -105,6 +105,12 @@ def lib() -> C.CDLL:
         "bic_update_dictionary_steepest": [_vp, _vp, _vp, _vp, _u64p],
         "bic_residual": [_vp, _vp, _vp, _vp, _vp],
         "bic_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
+        "bic_comm_unique_id": [_u8p],
+        "bic_comm_create": [_vp, C.c_int, C.c_int, _u8p, C.POINTER(_vp)],
+        "bic_comm_destroy": [_vp, _vp],
+        "bic_dist_initialize_model_neighbor": [_vp, _vp, _vp, _vp, _vp, _u64p],
+        "bic_dist_update_dictionary_steepest": [_vp, _vp, _vp, _vp, _vp, _u64p],
+        "bic_dist_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
         "bic_stream_create": [_vp, C.POINTER(_vp)],
         "bic_stream_destroy": [_vp, _vp],
         "bic_stream_get_info": [_vp, C.POINTER(StreamInfo)],
@@ -124,6 +130,8 @@ def lib() -> C.CDLL:
         f.restype = C.c_int
     L.bic_prof_kernel_count.argtypes = []
     L.bic_prof_kernel_count.restype = C.c_int
+    L.bic_comm_collective_count.argtypes = [_vp]
+    L.bic_comm_collective_count.restype = _u64
     L.bic_ctx_last_error.argtypes = [_vp]
     L.bic_ctx_last_error.restype = C.c_char_p
     L.bic_status_string.argtypes = [C.c_int]
@@ -381,6 +389,40 @@ class Context:
         tr = np.zeros(2 * trace_cap, np.uint64)
         self._ck(self.L.bic_learn_model_traditional(self.h, X.h, E.h, D.h, A.h, C.byref(it),
                                                     tr.ctypes.data_as(_u64p), trace_cap))
+        n = int(it.value)
+        return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
+
+    # ---- several GPUs (rows sharded, D replicated)
+    def comm_unique_id(self) -> np.ndarray:
+        uid = np.zeros(128, np.uint8)
+        self._ck(self.L.bic_comm_unique_id(uid.ctypes.data_as(_u8p)))
+        return uid
+
+    def comm_create(self, rank: int, nranks: int, uid: np.ndarray):
+        h = _vp()
+        u = np.ascontiguousarray(uid, np.uint8)
+        self._ck(self.L.bic_comm_create(self.h, rank, nranks, u.ctypes.data_as(_u8p), C.byref(h)))
+        return h
+
+    def comm_destroy(self, comm):
+        self._ck(self.L.bic_comm_destroy(self.h, comm))
+
+    def comm_collectives(self, comm) -> int:
+        return int(self.L.bic_comm_collective_count(comm))
+
+    def dist_initialize_model_neighbor(self, comm, X: Matrix, D: Matrix, A: Matrix, rng_state):
+        self._ck(self.L.bic_dist_initialize_model_neighbor(self.h, comm, X.h, D.h, A.h, C.byref(rng_state)))
+
+    def dist_update_dictionary(self, comm, E: Matrix, D: Matrix, A: Matrix) -> int:
+        ch = _u64(0)
+        self._ck(self.L.bic_dist_update_dictionary_steepest(self.h, comm, E.h, D.h, A.h, C.byref(ch)))
+        return int(ch.value)
+
+    def dist_learn_model_traditional(self, comm, X: Matrix, E: Matrix, D: Matrix, A: Matrix, trace_cap: int = 256):
+        it = _u64(0)
+        tr = np.zeros(2 * trace_cap, np.uint64)
+        self._ck(self.L.bic_dist_learn_model_traditional(self.h, comm, X.h, E.h, D.h, A.h, C.byref(it),
+                                                         tr.ctypes.data_as(_u64p), trace_cap))
         n = int(it.value)
         return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
 

@@ -125,6 +125,20 @@ static inline int bic_grid_for(const bic_ctx* ctx, uint64_t work_items, int per_
   return (int)(need < cap ? need : cap);
 }
 
+// scratch layout of one dictionary update (dict2.cu), shared with the row-sharded driver (dist.cu)
+struct DictWork {
+  uint64_t n, p, wpr, hs, wprN;
+  uint32_t *AT, *H, *U, *extra, *Hd, *Dnew, *cursor;
+  uint32_t launched;
+};
+
+// scratch layout of one neighbour initialisation (init.cu), shared with dist.cu
+struct InitWork {
+  uint64_t p, wpr;
+  uint64_t* piv;
+  uint32_t *P, *hist, *usage;
+};
+
 // ---- cross-TU entry points (implemented next to their kernels) -------------------------------
 bic_status bic_k_row_nonzero_bitmap(bic_ctx* ctx, const bic_mat* X, uint32_t* d_bitmap);
 

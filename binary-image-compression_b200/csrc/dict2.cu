@@ -99,6 +99,7 @@ struct ResolveParams {
   const uint32_t* A;
   const uint32_t* AT;
   uint32_t* H;
+  uint32_t* Hc;          // where corrections for later atoms are accumulated (H itself, or a per-rank delta buffer)
   const uint32_t* U;
   unsigned long long* changed;
   uint32_t* cursor;      // [2]: this launch reads [parity], writes [parity ^ 1]
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256) k_dict_resolve_step(ResolveParams P) {
         while (ab) {
           const int ap = __clz(ab);
           ab &= ~(0x80000000u >> ap);
-          uint32_t* hl = P.H + (aw * 32 + ap) * P.hs;
+          uint32_t* hl = P.Hc + (aw * 32 + ap) * P.hs;
           for (uint64_t w = 0; w < P.wprE; ++w) {
             uint32_t dl = s_delta[w];
             if (!dl) continue;
@@ -231,55 +232,82 @@ static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, ui
 
 bic_status bic_k_transpose_A(bic_ctx* c, const bic_mat* A, uint32_t* AT, uint64_t wprN);
 
-bic_status bic_k_update_dictionary_v2(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
+// The update as three reusable stages, so the row-sharded driver (dist.cu) can put its collectives
+// between them: (1) prepare: AT, local H/U; (2) resolve steps; (3) commit Dnew -> D.
+bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, DictWork* w) {
   if (E->rows != A->rows || E->cols != D->cols || A->cols != D->rows)
     return bic_fail(c, BIC_ERR_INVALID, "update_dictionary: shapes must be E n x m, D p x m, A n x p");
-  const uint64_t n = E->rows, p = D->rows, m = E->cols;
-  if (n == 0 || p == 0 || m == 0) return BIC_OK;
-  const uint64_t wprN = div_up_u64(n, 32);
-  const uint64_t hs = E->wpr * 32;
-  // work[2]: AT (p * wprN u32) ; work[3]: H (p * hs u32) + U (p u32)
-  BIC_TRY(bic_scratch_reserve(c, &c->work[2], (size_t)p * wprN * 4));
-  BIC_TRY(bic_scratch_reserve(c, &c->work[3], (size_t)(p * hs + p) * 4));
-  uint32_t* AT = (uint32_t*)c->work[2].p;
-  uint32_t* H = (uint32_t*)c->work[3].p;
-  uint32_t* U = H + p * hs;
-  BIC_CUDA(c, cudaMemsetAsync(H, 0, (size_t)(p * hs + p) * 4, c->stream));
-  BIC_TRY(bic_k_transpose_A(c, A, AT, wprN));
-  const uint64_t wpr = E->wpr;
-  BIC_TRY(launch_hist(c, E, A, H, U, hs));
-
-  // work[1] tail is free here (init is over): Dnew (p * wpr u32) + cursor (2 u32) live in work[0]
+  const uint64_t n = E->rows, p = D->rows, wpr = E->wpr;
+  w->n = n; w->p = p; w->wpr = wpr; w->hs = wpr * 32; w->wprN = div_up_u64(n, 32);
+  // work[2]: AT (p * wprN u32) ; work[3]: H (p*hs) | U (p) | extra (64) | Hd (p*hs) ; work[0]: Dnew (p*wpr) | cursor
+  BIC_TRY(bic_scratch_reserve(c, &c->work[2], (size_t)p * w->wprN * 4 + 16));
+  BIC_TRY(bic_scratch_reserve(c, &c->work[3], (size_t)(2 * p * w->hs + p + 64) * 4));
   BIC_TRY(bic_scratch_reserve(c, &c->work[0], (size_t)p * wpr * 4 + 64));
-  uint32_t* Dnew = (uint32_t*)c->work[0].p;
-  uint32_t* cursor = Dnew + p * wpr;
-  BIC_CUDA(c, cudaMemcpyAsync(Dnew, D->d, (size_t)p * wpr * 4, cudaMemcpyDeviceToDevice, c->stream));
-  BIC_CUDA(c, cudaMemsetAsync(cursor, 0, 8, c->stream));
+  w->AT = (uint32_t*)c->work[2].p;
+  w->H = (uint32_t*)c->work[3].p;
+  w->U = w->H + p * w->hs;
+  w->extra = w->U + p;
+  w->Hd = w->extra + 64;
+  w->Dnew = (uint32_t*)c->work[0].p;
+  w->cursor = w->Dnew + p * wpr;
+  w->launched = 0;
+  BIC_CUDA(c, cudaMemsetAsync(w->H, 0, (size_t)(2 * p * w->hs + p + 64) * 4, c->stream));
+  BIC_CUDA(c, cudaMemcpyAsync(w->Dnew, D->d, (size_t)p * wpr * 4, cudaMemcpyDeviceToDevice, c->stream));
+  BIC_CUDA(c, cudaMemsetAsync(w->cursor, 0, 8, c->stream));
+  if (n) {
+    BIC_TRY(bic_k_transpose_A(c, A, w->AT, w->wprN));
+    BIC_TRY(launch_hist(c, E, A, w->H, w->U, w->hs));
+  }
+  return BIC_OK;
+}
+
+// one resolve launch; corrections go to `Hc` (w->H in place, or w->Hd for the sharded driver)
+bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_mat* A, DictWork* w, uint32_t* Hc,
+                           unsigned long long* d_changed) {
   ResolveParams P;
-  P.E = E->d; P.D = D->d; P.Dnew = Dnew; P.A = A->d; P.AT = AT; P.H = H; P.U = U; P.changed = d_changed; P.cursor = cursor;
-  P.n = n; P.wprE = wpr; P.wprA = A->wpr; P.wprN = wprN; P.m = m; P.hs = hs; P.p = (uint32_t)p;
-  uint64_t win = (32 * 1024 / 4) / (hs + 1);
+  P.E = E->d; P.D = D->d; P.Dnew = w->Dnew; P.A = A->d; P.AT = w->AT; P.H = w->H; P.Hc = Hc; P.U = w->U;
+  P.changed = d_changed; P.cursor = w->cursor;
+  P.n = w->n; P.wprE = w->wpr; P.wprA = A->wpr; P.wprN = w->wprN; P.m = E->cols; P.hs = w->hs; P.p = (uint32_t)w->p;
+  uint64_t win = (32 * 1024 / 4) / (w->hs + 1);
   if (win < 1) win = 1;
-  if (win > p) win = p;
+  if (win > w->p) win = w->p;
   P.win = (uint32_t)win;
-  const size_t smem = (size_t)(wpr + win * (hs + 1)) * 4;
-  const int grid = bic_grid_for(c, div_up_u64(wprN, 32) * 32, 256, 4);
-  // Queue launches ahead; each returns at once when the cursor is already at p. The cursor is read
-  // back together with the change counter; more launches follow only if atoms are still pending.
-  uint32_t launched = 0, batch = 8;
+  const size_t smem = (size_t)(w->wpr + win * (w->hs + 1)) * 4;
+  const int grid = bic_grid_for(c, div_up_u64(w->wprN ? w->wprN : 1, 32) * 32, 256, 4);
+  P.parity = w->launched & 1;
+  BIC_PROF(c, KID_DICT_RESOLVE);
+  k_dict_resolve_step<<<grid, 256, smem, c->stream>>>(P);
+  BIC_LAUNCH_CHECK(c);
+  w->launched++;
+  return BIC_OK;
+}
+
+// cursor after the launches queued so far (synchronises the stream)
+bic_status bic_k_dict_cursor(bic_ctx* c, DictWork* w, uint32_t* cursor_out) {
   uint32_t* h_cursor = (uint32_t*)(c->h_scalars + 32);
+  BIC_CUDA(c, cudaMemcpyAsync(h_cursor, w->cursor + (w->launched & 1), 4, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  *cursor_out = *h_cursor;
+  return BIC_OK;
+}
+
+bic_status bic_k_dict_commit(bic_ctx* c, bic_mat* D, DictWork* w) {
+  BIC_CUDA(c, cudaMemcpyAsync(D->d, w->Dnew, (size_t)w->p * w->wpr * 4, cudaMemcpyDeviceToDevice, c->stream));
+  return BIC_OK;
+}
+
+bic_status bic_k_update_dictionary_v2(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
+  if (E->rows == 0 || D->rows == 0 || E->cols == 0) return BIC_OK;
+  DictWork w;
+  BIC_TRY(bic_k_dict_prepare(c, E, D, A, &w));
+  // Queue launches ahead; each returns at once when the cursor is already at p. The cursor is read
+  // back and more launches follow only if atoms are still pending.
+  uint32_t batch = 8, cursor = 0;
   for (;;) {
-    for (uint32_t i = 0; i < batch && launched < p; ++i, ++launched) {
-      P.parity = launched & 1;
-      BIC_PROF(c, KID_DICT_RESOLVE);
-      k_dict_resolve_step<<<grid, 256, smem, c->stream>>>(P);
-      BIC_LAUNCH_CHECK(c);
-    }
-    BIC_CUDA(c, cudaMemcpyAsync(h_cursor, cursor + (launched & 1), 4, cudaMemcpyDeviceToHost, c->stream));
-    BIC_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (*h_cursor >= p || launched >= p) break;
+    for (uint32_t i = 0; i < batch && w.launched < w.p; ++i) BIC_TRY(bic_k_dict_step(c, E, D, A, &w, w.H, d_changed));
+    BIC_TRY(bic_k_dict_cursor(c, &w, &cursor));
+    if (cursor >= w.p || w.launched >= w.p) break;
     batch = (batch * 2 < 64) ? batch * 2 : 64;
   }
-  BIC_CUDA(c, cudaMemcpyAsync(D->d, Dnew, (size_t)p * wpr * 4, cudaMemcpyDeviceToDevice, c->stream));
-  return BIC_OK;
+  return bic_k_dict_commit(c, D, &w);
 }

@@ -1,0 +1,277 @@
+// Row-sharded fit over several GPUs: every rank holds a contiguous block of patch rows
+// (its X, E, A), the dictionary D is replicated, and the integer statistics are combined with NCCL
+// over NVLink. Integer sums are order independent, so the result is bit-identical to the single-GPU
+// (and to the reference's serial) fit of the concatenated rows.
+//
+//   init   : allgather of the per-rank zero-row bitmaps (the rand48 accept/reject needs "is global row i
+//            zero"), every rank replays the same draw; pivot rows are contributed by their owners through
+//            one allreduce; one allreduce of [column histogram | per-pivot intersect counts].
+//   coef   : local (rows are independent given D).
+//   dict   : one allreduce of [H | U | changed-rows] per iteration, then the in-order resolve runs
+//            replicated on every rank; only an atom that CHANGES costs another (small) allreduce of the
+//            histogram corrections its users produced (dict2.cu).
+//
+// NCCL is loaded at run time (the copy torch already loaded if there is one, else the system
+// libnccl.so.2); nccl.h is only used for its types.
+#include "bic_internal.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <vector>
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok = false;
+};
+
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return nullptr;
+#define LOAD(name) *(void**)(&api.name) = dlsym(h, "nccl" #name); if (!api.name) return nullptr
+  LOAD(GetUniqueId); LOAD(CommInitRank); LOAD(CommDestroy); LOAD(AllReduce); LOAD(AllGather); LOAD(GetErrorString);
+#undef LOAD
+  api.ok = true;
+  return &api;
+}
+
+struct bic_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  std::vector<uint64_t> nrows;    // rows per rank (set by the first collective that needs them)
+  uint64_t row0 = 0, nglobal = 0;
+  uint64_t collectives = 0;
+};
+
+#define BIC_NCCL(ctx, expr)                                                                   \
+  do {                                                                                        \
+    ncclResult_t _r = (expr);                                                                 \
+    if (_r != ncclSuccess) {                                                                  \
+      (ctx)->err = std::string(#expr) + ": " + nccl_api()->GetErrorString(_r);                \
+      return BIC_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+extern "C" bic_status bic_comm_unique_id(uint8_t id[128]) {
+  NcclApi* n = nccl_api();
+  if (!n || !id) return BIC_ERR_UNSUPPORTED;
+  ncclUniqueId u;
+  if (n->GetUniqueId(&u) != ncclSuccess) return BIC_ERR_CUDA;
+  memcpy(id, u.internal, 128);
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_comm_create(bic_ctx* c, int rank, int nranks, const uint8_t id[128], bic_comm** out) {
+  if (!c || !out || !id || nranks < 1 || rank < 0 || rank >= nranks) return BIC_ERR_INVALID;
+  cudaSetDevice(c->device);
+  NcclApi* n = nccl_api();
+  if (!n) return bic_fail(c, BIC_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  bic_comm* m = new bic_comm();
+  m->rank = rank;
+  m->nranks = nranks;
+  ncclUniqueId u;
+  memcpy(u.internal, id, 128);
+  ncclResult_t r = n->CommInitRank(&m->comm, nranks, u, rank);
+  if (r != ncclSuccess) { c->err = std::string("ncclCommInitRank: ") + n->GetErrorString(r); delete m; return BIC_ERR_CUDA; }
+  *out = m;
+  return BIC_OK;
+}
+
+extern "C" bic_status bic_comm_destroy(bic_ctx* c, bic_comm* m) {
+  if (!c || !m) return BIC_ERR_INVALID;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (m->comm) nccl_api()->CommDestroy(m->comm);
+  delete m;
+  return BIC_OK;
+}
+
+extern "C" uint64_t bic_comm_collective_count(const bic_comm* m) { return m ? m->collectives : 0; }
+
+static bic_status allreduce_u32(bic_ctx* c, bic_comm* m, uint32_t* buf, size_t count) {
+  if (m->nranks == 1 || count == 0) return BIC_OK;
+  BIC_NCCL(c, nccl_api()->AllReduce(buf, buf, count, ncclUint32, ncclSum, m->comm, c->stream));
+  m->collectives++;
+  return BIC_OK;
+}
+
+// rows per rank -> offsets (one tiny allgather, repeated when the local row count changes)
+static bic_status share_rows(bic_ctx* c, bic_comm* m, uint64_t n_local) {
+  if ((int)m->nrows.size() == m->nranks && m->nrows[m->rank] == n_local) return BIC_OK;
+  m->nrows.assign(m->nranks, 0);
+  uint64_t* d = c->d_scalars + 40;  // [40, 40+nranks)
+  if (m->nranks > 16) return bic_fail(c, BIC_ERR_UNSUPPORTED, "more than 16 ranks");
+  BIC_CUDA(c, cudaMemcpyAsync(d + m->rank, &n_local, 8, cudaMemcpyHostToDevice, c->stream));
+  if (m->nranks > 1) {
+    BIC_NCCL(c, nccl_api()->AllGather(d + m->rank, d, 1, ncclUint64, m->comm, c->stream));
+    m->collectives++;
+  }
+  BIC_CUDA(c, cudaMemcpyAsync(m->nrows.data(), d, 8 * m->nranks, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  m->row0 = 0;
+  m->nglobal = 0;
+  for (int r = 0; r < m->nranks; ++r) { if (r < m->rank) m->row0 += m->nrows[r]; m->nglobal += m->nrows[r]; }
+  return BIC_OK;
+}
+
+bic_status bic_k_init_scratch(bic_ctx* c, uint64_t p, uint64_t wpr, InitWork* w);
+bic_status bic_k_init_gather(bic_ctx* c, const bic_mat* X, const uint64_t* host_pivots, InitWork* w);
+bic_status bic_k_init_stats(bic_ctx* c, const bic_mat* X, InitWork* w);
+bic_status bic_k_init_finalize(bic_ctx* c, InitWork* w, uint64_t m, bic_mat* D);
+bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, unsigned long long* d_changed);
+bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, DictWork* w);
+bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_mat* A, DictWork* w, uint32_t* Hc,
+                           unsigned long long* d_changed);
+bic_status bic_k_dict_cursor(bic_ctx* c, DictWork* w, uint32_t* cursor_out);
+bic_status bic_k_dict_commit(bic_ctx* c, bic_mat* D, DictWork* w);
+
+// ------------------------------------------------------------------ initialize_model_neighbor, sharded
+// src/bsvd.cpp:227-267 over the concatenation of all ranks' rows.
+extern "C" bic_status bic_dist_initialize_model_neighbor(bic_ctx* c, bic_comm* m, const bic_mat* X, bic_mat* D, bic_mat* A,
+                                                         uint64_t* rng_state) {
+  if (!c || !m || !X || !D || !A || !rng_state) return BIC_ERR_INVALID;
+  cudaSetDevice(c->device);
+  const uint64_t p = D->rows;
+  if (D->cols != X->cols || A->rows != X->rows || A->cols != p)
+    return bic_fail(c, BIC_ERR_INVALID, "init: shapes must be X n x m, D p x m, A n x p");
+  BIC_TRY(share_rows(c, m, X->rows));
+  BIC_TRY(bic_mat_clear(c, A));
+  BIC_TRY(bic_mat_clear(c, D));
+  if (p == 0 || m->nglobal == 0 || X->cols == 0) return BIC_OK;
+  // zero-row bitmaps of all ranks, padded to the largest shard
+  uint64_t maxn = 0;
+  for (uint64_t v : m->nrows) maxn = v > maxn ? v : maxn;
+  const uint64_t bw = div_up_u64(maxn, 32);
+  BIC_TRY(bic_scratch_reserve(c, &c->work[0], (size_t)bw * 4 * m->nranks + 16));
+  uint32_t* d_bm = (uint32_t*)c->work[0].p;
+  BIC_CUDA(c, cudaMemsetAsync(d_bm, 0, (size_t)bw * 4 * m->nranks, c->stream));
+  BIC_TRY(bic_k_row_nonzero_bitmap(c, X, d_bm + (size_t)m->rank * bw));
+  if (m->nranks > 1) {
+    BIC_NCCL(c, nccl_api()->AllGather(d_bm + (size_t)m->rank * bw, d_bm, bw, ncclUint32, m->comm, c->stream));
+    m->collectives++;
+  }
+  std::vector<uint32_t> bm((size_t)bw * m->nranks);
+  BIC_CUDA(c, cudaMemcpyAsync(bm.data(), d_bm, bm.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  bool any = false;
+  for (size_t i = 0; i < bm.size() && !any; ++i) any = bm[i] != 0;
+  if (!any) return bic_fail(c, BIC_ERR_INVALID, "init: X is all zero (the reference's draw loop never ends)");
+  // every rank replays the same draw over the global row index (src/bsvd.cpp:239-243)
+  std::vector<uint64_t> local_piv(p);
+  std::vector<uint64_t> start(m->nranks + 1, 0);
+  for (int r = 0; r < m->nranks; ++r) start[r + 1] = start[r] + m->nrows[r];
+  for (uint64_t k = 0; k < p;) {
+    const uint64_t g = bic_rand48_uniform_int(rng_state, m->nglobal);
+    int owner = 0;
+    while (g >= start[owner + 1]) owner++;
+    const uint64_t li = g - start[owner];
+    if (!((bm[(size_t)owner * bw + (li >> 5)] >> (li & 31)) & 1u)) continue;
+    local_piv[k++] = (owner == m->rank) ? li : ~0ull;
+  }
+  InitWork w;
+  BIC_TRY(bic_k_init_scratch(c, p, X->wpr, &w));
+  BIC_TRY(bic_k_init_gather(c, X, local_piv.data(), &w));
+  BIC_TRY(allreduce_u32(c, m, w.P, (size_t)p * X->wpr));          // each pivot row has exactly one owner
+  BIC_TRY(bic_k_init_stats(c, X, &w));
+  BIC_TRY(allreduce_u32(c, m, w.hist, (size_t)X->wpr * 32 + p));  // hist and usage are adjacent
+  return bic_k_init_finalize(c, &w, X->cols, D);
+}
+
+// H += Hd; Hd = 0
+__global__ void k_apply_corrections(uint32_t* __restrict__ H, uint32_t* __restrict__ Hd, uint64_t nwords) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t d = Hd[i];
+    if (d) { H[i] += d; Hd[i] = 0; }
+  }
+}
+
+// ------------------------------------------------------------------ update_dictionary_steepest, sharded
+// d_counts[0] (changed rows of the preceding coefficient update, local) is summed over ranks in the same
+// allreduce as H and U; d_counts[1] receives the changed atoms (identical on every rank).
+static bic_status dist_update_dictionary(bic_ctx* c, bic_comm* m, bic_mat* E, bic_mat* D, const bic_mat* A,
+                                         unsigned long long* d_counts) {
+  if (D->rows == 0 || E->cols == 0) return BIC_OK;
+  DictWork w;
+  BIC_TRY(bic_k_dict_prepare(c, E, D, A, &w));
+  // [H | U | extra]: extra[0..1] carries the 64-bit changed-rows count as two u32 halves
+  BIC_CUDA(c, cudaMemcpyAsync(w.extra, d_counts, 8, cudaMemcpyDeviceToDevice, c->stream));
+  BIC_TRY(allreduce_u32(c, m, w.H, (size_t)w.p * w.hs + w.p + 2));
+  uint32_t cursor = 0;
+  uint32_t batch = 1;  // most updates after the first iteration change no atom: one launch, one look at the cursor
+  const uint64_t hwords = w.p * w.hs;
+  for (;;) {
+    for (uint32_t i = 0; i < batch && w.launched < w.p; ++i) {
+      BIC_TRY(bic_k_dict_step(c, E, D, A, &w, w.Hd, d_counts + 1));
+      // an atom may have changed: combine the corrections its users produced on every rank
+      BIC_TRY(allreduce_u32(c, m, w.Hd, hwords));
+      k_apply_corrections<<<bic_grid_for(c, hwords, 256, 2), 256, 0, c->stream>>>(w.H, w.Hd, hwords);
+      BIC_LAUNCH_CHECK(c);
+    }
+    BIC_TRY(bic_k_dict_cursor(c, &w, &cursor));
+    if (cursor >= w.p || w.launched >= w.p) break;
+    batch = (batch * 2 < 32) ? batch * 2 : 32;
+  }
+  return bic_k_dict_commit(c, D, &w);
+}
+
+__global__ void k_join_u32_pair(const uint32_t* __restrict__ lohi, unsigned long long* __restrict__ out) {
+  // the two halves were summed separately: recombine with the carry
+  *out = (unsigned long long)lohi[0] + ((unsigned long long)lohi[1] << 32);
+}
+
+extern "C" bic_status bic_dist_update_dictionary_steepest(bic_ctx* c, bic_comm* m, bic_mat* E, bic_mat* D, const bic_mat* A,
+                                                          uint64_t* changed) {
+  if (!c || !m || !E || !D || !A) return BIC_ERR_INVALID;
+  cudaSetDevice(c->device);
+  BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, 16, c->stream));
+  BIC_TRY(dist_update_dictionary(c, m, E, D, A, (unsigned long long*)c->d_scalars));
+  BIC_TRY(bic_read_scalars(c, 2));
+  if (changed) *changed = c->h_scalars[1];
+  return BIC_OK;
+}
+
+// ------------------------------------------------------------------ learn_model_traditional, sharded
+extern "C" bic_status bic_dist_learn_model_traditional(bic_ctx* c, bic_comm* m, const bic_mat* X, bic_mat* E, bic_mat* D,
+                                                       bic_mat* A, uint64_t* iterations, uint64_t* trace, uint64_t trace_cap) {
+  if (!c || !m || !X || !E || !D || !A) return BIC_ERR_INVALID;
+  cudaSetDevice(c->device);
+  BIC_TRY(bic_residual(c, X, A, D, E));
+  uint64_t changed = 1, iter = 0;
+  unsigned long long* d_cc = (unsigned long long*)c->d_scalars;
+  while (changed > 0) {
+    iter++;
+    BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, 16, c->stream));
+    BIC_TRY(bic_k_update_coefficients(c, E, D, A, d_cc));
+    // global changed-rows: rides in the dictionary update's first allreduce (extra[0..1]); read it back
+    // from there after the update
+    BIC_TRY(dist_update_dictionary(c, m, E, D, A, d_cc));
+    // extra[] lives in work[3] right after H and U
+    {
+      const uint64_t p = D->rows, hs = E->wpr * 32;
+      const uint32_t* extra = (const uint32_t*)c->work[3].p + p * hs + p;
+      if (p && E->cols) {
+        k_join_u32_pair<<<1, 1, 0, c->stream>>>(extra, d_cc);
+        BIC_LAUNCH_CHECK(c);
+      } else if (m->nranks > 1) {
+        BIC_NCCL(c, nccl_api()->AllReduce(d_cc, d_cc, 1, ncclUint64, ncclSum, m->comm, c->stream));
+        m->collectives++;
+      }
+    }
+    BIC_TRY(bic_read_scalars(c, 2));
+    changed = c->h_scalars[0] + c->h_scalars[1];
+    if (trace && iter <= trace_cap) { trace[2 * (iter - 1)] = c->h_scalars[0]; trace[2 * (iter - 1) + 1] = c->h_scalars[1]; }
+  }
+  if (iterations) *iterations = iter;
+  return BIC_OK;
+}

@@ -140,7 +140,8 @@ __global__ void k_gather_rows(const uint32_t* __restrict__ X, uint64_t wpr, cons
   const uint64_t total = (uint64_t)np * wpr;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t k = i / wpr, w = i - k * wpr;
-    P[i] = X[pivots[k] * wpr + w];
+    const uint64_t r = pivots[k];
+    P[i] = (r == ~0ull) ? 0u : X[r * wpr + w];  // ~0: the row lives on another rank
   }
 }
 
@@ -175,51 +176,53 @@ static bic_status launch_usage(bic_ctx* c, const bic_mat* X, const uint32_t* P, 
   return BIC_OK;
 }
 
-extern "C" bic_status bic_initialize_model_neighbor_pivots(bic_ctx* c, const bic_mat* X, const uint64_t* pivots,
-                                                           uint64_t p, bic_mat* D, bic_mat* A) {
-  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
-  if (!c || !X || !D || !A || (!pivots && p)) return BIC_ERR_INVALID;
-  if (D->rows != p || D->cols != X->cols || A->rows != X->rows || A->cols != p)
-    return bic_fail(c, BIC_ERR_INVALID, "init: shapes must be X n x m, D p x m, A n x p");
-  for (uint64_t k = 0; k < p; ++k)
-    if (pivots[k] >= X->rows) return bic_fail(c, BIC_ERR_INVALID, "init: pivot out of range");
-  BIC_TRY(bic_mat_clear(c, A));  // A.clear(), src/bsvd.cpp:237
-  BIC_TRY(bic_mat_clear(c, D));  // D.clear(), :238
-  if (p == 0 || X->rows == 0 || X->cols == 0) return BIC_OK;
-  const uint64_t wpr = X->wpr, m = X->cols;
-  // work[1]: pivots (u64 p) | P rows (p*wpr u32) | hist (wpr*32 u32) | usage (p u32)
+// ---- stages, shared with the row-sharded driver (dist.cu) ------------------------------------------
+// scratch (work[1]): pivots (u64 p) | P rows (p*wpr u32) | hist (wpr*32 u32) | usage (p u32)
+bic_status bic_k_init_scratch(bic_ctx* c, uint64_t p, uint64_t wpr, InitWork* w) {
   const size_t off_P = (size_t)p * 8;
   const size_t off_h = off_P + (size_t)p * wpr * 4;
   const size_t off_u = off_h + (size_t)wpr * 32 * 4;
   const size_t total = off_u + (size_t)p * 4;
-  BIC_TRY(bic_scratch_reserve(c, &c->work[1], total));
+  BIC_TRY(bic_scratch_reserve(c, &c->work[1], total + 16));
   uint8_t* base = (uint8_t*)c->work[1].p;
-  uint64_t* d_piv = (uint64_t*)base;
-  uint32_t* d_P = (uint32_t*)(base + off_P);
-  uint32_t* d_hist = (uint32_t*)(base + off_h);
-  uint32_t* d_usage = (uint32_t*)(base + off_u);
-  BIC_CUDA(c, cudaMemcpyAsync(d_piv, pivots, (size_t)p * 8, cudaMemcpyHostToDevice, c->stream));
-  BIC_CUDA(c, cudaMemsetAsync(d_hist, 0, (size_t)wpr * 32 * 4 + (size_t)p * 4, c->stream));
+  w->piv = (uint64_t*)base;
+  w->P = (uint32_t*)(base + off_P);
+  w->hist = (uint32_t*)(base + off_h);
+  w->usage = (uint32_t*)(base + off_u);
+  w->p = p; w->wpr = wpr;
+  return BIC_OK;
+}
+
+// P[k] = X[pivots[k]] (zero row where pivots[k] == ~0, i.e. owned by another rank)
+bic_status bic_k_init_gather(bic_ctx* c, const bic_mat* X, const uint64_t* host_pivots, InitWork* w) {
+  BIC_CUDA(c, cudaMemcpyAsync(w->piv, host_pivots, (size_t)w->p * 8, cudaMemcpyHostToDevice, c->stream));
   BIC_PROF(c, KID_GATHER_ROWS);
-  k_gather_rows<<<bic_grid_for(c, p * wpr, 256, 4), 256, 0, c->stream>>>(X->d, wpr, d_piv, (uint32_t)p, d_P);
+  k_gather_rows<<<bic_grid_for(c, w->p * w->wpr, 256, 4), 256, 0, c->stream>>>(X->d, w->wpr, w->piv, (uint32_t)w->p, w->P);
   BIC_LAUNCH_CHECK(c);
-  // column histogram, 32 words of the row per launch
-  for (uint64_t w0 = 0; w0 < wpr; w0 += 32) {
+  return BIC_OK;
+}
+
+// local column histogram of X and, per pivot, the number of local rows that intersect it
+bic_status bic_k_init_stats(bic_ctx* c, const bic_mat* X, InitWork* w) {
+  const uint64_t wpr = w->wpr, p = w->p;
+  BIC_CUDA(c, cudaMemsetAsync(w->hist, 0, (size_t)wpr * 32 * 4 + (size_t)p * 4, c->stream));
+  if (X->rows == 0) return BIC_OK;
+  for (uint64_t w0 = 0; w0 < wpr; w0 += 32) {  // 32 words of the row per launch
     const uint64_t nw = (wpr - w0 < 32) ? wpr - w0 : 32;
     const int grid = bic_grid_for(c, X->rows * 32, 256, 8);
-    if (nw <= 2) { BIC_PROF(c, KID_COL_HIST); k_col_hist<2><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist); }
-    else if (nw <= 8) { BIC_PROF(c, KID_COL_HIST); k_col_hist<8><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist); }
-    else { BIC_PROF(c, KID_COL_HIST); k_col_hist<32><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, d_hist); }
+    BIC_PROF(c, KID_COL_HIST);
+    if (nw <= 2) k_col_hist<2><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, w->hist);
+    else if (nw <= 8) k_col_hist<8><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, w->hist);
+    else k_col_hist<32><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, w->hist);
     BIC_LAUNCH_CHECK(c);
   }
-  // pivot usage, in chunks of pivots whose rows fit in shared memory
-  if (wpr <= 32) {
+  if (wpr <= 32) {  // pivot usage, in chunks of pivots whose rows fit in shared memory
     const int WORDS = wpr <= 1 ? 1 : wpr <= 2 ? 2 : wpr <= 4 ? 4 : wpr <= 8 ? 8 : wpr <= 16 ? 16 : 32;
     const uint64_t max_np = (96 * 1024 / 4) / (WORDS + 1);
     for (uint64_t k0 = 0; k0 < p; k0 += max_np) {
       const uint32_t np = (uint32_t)((p - k0 < max_np) ? p - k0 : max_np);
-      const uint32_t* Pk = d_P + k0 * wpr;
-      uint32_t* uk = d_usage + k0;
+      const uint32_t* Pk = w->P + k0 * wpr;
+      uint32_t* uk = w->usage + k0;
       switch (WORDS) {
         case 1: BIC_TRY(launch_usage<1>(c, X, Pk, np, uk)); break;
         case 2: BIC_TRY(launch_usage<2>(c, X, Pk, np, uk)); break;
@@ -231,14 +234,35 @@ extern "C" bic_status bic_initialize_model_neighbor_pivots(bic_ctx* c, const bic
     }
   } else {
     BIC_PROF(c, KID_PIVOT_USAGE);
-    k_pivot_usage_wide<<<bic_grid_for(c, X->rows * 32, 256, 8), 256, 0, c->stream>>>(X->d, X->rows, wpr, d_P,
-                                                                                   (uint32_t)p, d_usage);
+    k_pivot_usage_wide<<<bic_grid_for(c, X->rows * 32, 256, 8), 256, 0, c->stream>>>(X->d, X->rows, wpr, w->P, (uint32_t)p, w->usage);
     BIC_LAUNCH_CHECK(c);
   }
+  return BIC_OK;
+}
+
+bic_status bic_k_init_finalize(bic_ctx* c, InitWork* w, uint64_t m, bic_mat* D) {
   BIC_PROF(c, KID_INIT_FINALIZE);
-  k_init_finalize<<<bic_grid_for(c, p * wpr, 256, 4), 256, 0, c->stream>>>(d_P, d_hist, d_usage, (uint32_t)p, wpr, m, D->d);
+  k_init_finalize<<<bic_grid_for(c, w->p * w->wpr, 256, 4), 256, 0, c->stream>>>(w->P, w->hist, w->usage, (uint32_t)w->p, w->wpr, m, D->d);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
+}
+
+extern "C" bic_status bic_initialize_model_neighbor_pivots(bic_ctx* c, const bic_mat* X, const uint64_t* pivots,
+                                                           uint64_t p, bic_mat* D, bic_mat* A) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
+  if (!c || !X || !D || !A || (!pivots && p)) return BIC_ERR_INVALID;
+  if (D->rows != p || D->cols != X->cols || A->rows != X->rows || A->cols != p)
+    return bic_fail(c, BIC_ERR_INVALID, "init: shapes must be X n x m, D p x m, A n x p");
+  for (uint64_t k = 0; k < p; ++k)
+    if (pivots[k] >= X->rows) return bic_fail(c, BIC_ERR_INVALID, "init: pivot out of range");
+  BIC_TRY(bic_mat_clear(c, A));  // A.clear(), src/bsvd.cpp:237
+  BIC_TRY(bic_mat_clear(c, D));  // D.clear(), :238
+  if (p == 0 || X->rows == 0 || X->cols == 0) return BIC_OK;
+  InitWork w;
+  BIC_TRY(bic_k_init_scratch(c, p, X->wpr, &w));
+  BIC_TRY(bic_k_init_gather(c, X, pivots, &w));
+  BIC_TRY(bic_k_init_stats(c, X, &w));
+  return bic_k_init_finalize(c, &w, X->cols, D);
 }
 
 extern "C" bic_status bic_initialize_model_neighbor(bic_ctx* c, const bic_mat* X, bic_mat* D, bic_mat* A,

@@ -146,6 +146,33 @@ bic_status bic_residual(bic_ctx* ctx, const bic_mat* X, const bic_mat* A, const 
 bic_status bic_learn_model_traditional(bic_ctx* ctx, const bic_mat* X, bic_mat* E, bic_mat* D, bic_mat* A,
                                        uint64_t* iterations, uint64_t* trace, uint64_t trace_cap);
 
+/* ---------------------------------------------------------------- several GPUs: rows sharded, D replicated
+ * One process per GPU. Every rank holds a contiguous block of the patch rows (its X, E, A); D is
+ * replicated. Integer statistics are combined with NCCL (loaded at run time: the libnccl.so.2 already in
+ * the process, else the system one), so the result equals the single-GPU fit of the concatenated rows
+ * bit for bit. The 128-byte id comes from bic_comm_unique_id on one rank and reaches the others through
+ * whatever the caller uses for plumbing (torch.distributed broadcast, a file, MPI ...). */
+typedef struct bic_comm bic_comm;
+bic_status bic_comm_unique_id(uint8_t id[128]);
+bic_status bic_comm_create(bic_ctx* ctx, int rank, int nranks, const uint8_t id[128], bic_comm** out);
+bic_status bic_comm_destroy(bic_ctx* ctx, bic_comm* comm);
+uint64_t bic_comm_collective_count(const bic_comm* comm);
+/* initialize_model_neighbor over all ranks' rows (src/bsvd.cpp:227-267): allgather of the zero-row
+ * bitmaps, the same rand48 replay on every rank (advance rng_state identically everywhere), pivot rows
+ * and [column histogram | intersect counts] by allreduce */
+bic_status bic_dist_initialize_model_neighbor(bic_ctx* ctx, bic_comm* comm, const bic_mat* X_local, bic_mat* D,
+                                              bic_mat* A_local, uint64_t* rng_state);
+/* update_dictionary_steepest over all ranks' rows (src/bsvd.cpp:463-527): one allreduce of the atom
+ * histograms, then the in-order resolve replicated on every rank with one more allreduce per atom that
+ * changes. *changed = changed atoms (same on every rank). */
+bic_status bic_dist_update_dictionary_steepest(bic_ctx* ctx, bic_comm* comm, bic_mat* E_local, bic_mat* D,
+                                               const bic_mat* A_local, uint64_t* changed);
+/* learn_model_traditional over all ranks' rows (src/bsvd.cpp:1215-1244); trace[2i] = changed rows summed
+ * over ranks, trace[2i+1] = changed atoms */
+bic_status bic_dist_learn_model_traditional(bic_ctx* ctx, bic_comm* comm, const bic_mat* X_local, bic_mat* E_local,
+                                            bic_mat* D, bic_mat* A_local, uint64_t* iterations, uint64_t* trace,
+                                            uint64_t trace_cap);
+
 /* ---------------------------------------------------------------- entropy coding
  * A coded stream is a byte string: stream bit t is in byte t/8 at mask 0x80 >> (t%8)
  * (writeBits / readBits order, src/GolombCoder.cpp:22-25, src/GolombDecoder.cpp:15-23). */

@@ -1,0 +1,62 @@
+"""Worker for tests/test_multi_gpu.py (launched with torch.distributed.run, one rank per GPU):
+row-sharded fit through the C ABI (NCCL inside libbic_b200.so) vs the oracle's single-process fit of
+the concatenated rows. Exits non-zero on any mismatch."""
+import importlib
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from oracle_bindings import Oracle
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    bic = importlib.import_module("binary-image-compression_b200")
+    synth, oracle = bic.synth, Oracle()
+    ctx = bic.Context(local)
+    uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+    dist.broadcast(uid, 0)
+    comm = ctx.comm_create(rank, world, uid.cpu().numpy())
+
+    for (rows, cols, W, K, seed) in [(512, 384, 8, 32, 1), (400, 512, 16, 64, 2), (300, 200, 12, 10, 3)]:
+        page = synth.structured_page(rows, cols, seed=seed, salt=0.01)
+        Xw = oracle.extract_patches(synth.pack_rows(page), rows, cols, W)
+        m, n = W * W, Xw.shape[0]
+        cuts = [int(n * r / world * (0.8 if r % 2 else 1.0)) if r < world else n for r in range(world + 1)]
+        cuts[0], cuts[-1] = 0, n
+        lo, hi = cuts[rank], cuts[rank + 1]
+        X = ctx.matrix(hi - lo, m, Xw[lo:hi])
+        D, A, E = ctx.matrix(K, m), ctx.matrix(hi - lo, K), ctx.matrix(hi - lo, m)
+        ctx.dist_initialize_model_neighbor(comm, X, D, A, ctx.rand48(500 + seed))
+        Do, Ao, _ = oracle.init_neighbor(Xw, m, K, 500 + seed)
+        assert np.array_equal(D.download(), Do), f"rank {rank}: sharded init differs"
+        it, tr = ctx.dist_learn_model_traditional(comm, X, E, D, A)
+        Eo, ito, tro = oracle.learn_traditional(Xw, Do, Ao, m, K)
+        assert it == ito and np.array_equal(tr, tro), f"rank {rank}: trace {tr.tolist()} vs {tro.tolist()}"
+        assert np.array_equal(D.download(), Do)
+        assert np.array_equal(A.download(), Ao[lo:hi]) and np.array_equal(E.download(), Eo[lo:hi])
+        # one dictionary update on its own: allreduces = 1 + changed atoms (+ rows exchange on first use)
+        c0 = ctx.comm_collectives(comm)
+        ch = ctx.dist_update_dictionary(comm, E, D, A)
+        assert ch == 0 and ctx.comm_collectives(comm) - c0 <= 2
+        for mm in (X, D, A, E):
+            mm.destroy()
+    if rank == 0:
+        print(f"dist ok world={world} collectives={ctx.comm_collectives(comm)}")
+    dist.barrier()
+    ctx.comm_destroy(comm)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
