@@ -393,12 +393,33 @@ class Context:
         return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
 
     # ---- several GPUs (rows sharded, D replicated)
+    @staticmethod
+    def _preload_nccl():
+        """Map the NCCL build torch ships (if any) before the library looks for one: a process must
+        not end up with two different libnccl.so.2."""
+        import importlib.util
+        import os
+        if os.environ.get("BIC_NCCL_LIB"):
+            return
+        try:
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for loc in (spec.submodule_search_locations or []) if spec else []:
+                cand = os.path.join(loc, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                    os.environ["BIC_NCCL_LIB"] = cand
+                    return
+        except Exception:
+            pass
+
     def comm_unique_id(self) -> np.ndarray:
+        self._preload_nccl()
         uid = np.zeros(128, np.uint8)
         self._ck(self.L.bic_comm_unique_id(uid.ctypes.data_as(_u8p)))
         return uid
 
     def comm_create(self, rank: int, nranks: int, uid: np.ndarray):
+        self._preload_nccl()
         h = _vp()
         u = np.ascontiguousarray(uid, np.uint8)
         self._ck(self.L.bic_comm_create(self.h, rank, nranks, u.ctypes.data_as(_u8p), C.byref(h)))

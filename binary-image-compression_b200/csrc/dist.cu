@@ -16,6 +16,7 @@
 #include "bic_internal.cuh"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <nccl.h>
 
 #include <vector>
@@ -35,7 +36,10 @@ static NcclApi* nccl_api() {
   static bool tried = false;
   if (tried) return api.ok ? &api : nullptr;
   tried = true;
-  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  // 1. a libnccl.so.2 some other component of the process (e.g. torch) already mapped; 2. the one
+  // BIC_NCCL_LIB names; 3. the system one. Two different NCCL builds in one process do not mix.
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) { const char* e = getenv("BIC_NCCL_LIB"); if (e && *e) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL); }
   if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!h) return nullptr;
