@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--atoms", type=int, default=32)
     ap.add_argument("--cpu-crop", type=int, default=2048, help="crop edge for the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="also time the row-sharded (NCCL) fit at N=1")
     ap.add_argument("--streams", type=int, default=16, help="contexts (CUDA streams) per GPU")
     return ap.parse_args()
 
@@ -407,6 +408,47 @@ def main():
         "kernel_time_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
     }
 
+    # ---- row-sharded fit (N > 1): the N bands are ONE image, one dictionary per plane over all ranks'
+    # patches, statistics combined by NCCL inside the library (csrc/dist.cu). One stream, planes in
+    # sequence; D/A/E shards are Golomb coded per rank (seam-exact global streams: not yet).
+    sharded = None
+    if world > 1 or args.sharded:
+        uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+        if dist is not None:
+            dist.broadcast(uid, 0)
+        w0 = workers[0]
+        comm = w0.ctx.comm_create(rank, world, uid.cpu().numpy())
+        sh_iters = [0] * P
+
+        def fit_sharded(b):
+            c = w0.ctx
+            c._ck(L.bic_extract_patches(c.h, rasters[b].h, W, w0.X.h))
+            rng = c.rand48(SEED)
+            c._ck(L.bic_dist_initialize_model_neighbor(c.h, comm, w0.X.h, w0.D.h, w0.A.h, C.byref(rng)))
+            it = C.c_uint64(0)
+            c._ck(L.bic_dist_learn_model_traditional(c.h, comm, w0.X.h, w0.E.h, w0.D.h, w0.A.h, C.byref(it), None, 0))
+            sh_iters[b] = int(it.value)
+            for M, s in zip((w0.D, w0.A, w0.E), w0.streams):
+                c._ck(L.bic_golomb_encode(c.h, M.h, 256, s.h))
+
+        for b in range(P):
+            fit_sharded(b)
+        barrier()
+        coll0 = w0.ctx.comm_collectives(comm)
+        w0.ctx.timer_start()
+        for _ in range(args.steps):
+            for b in range(P):
+                fit_sharded(b)
+        ms_sh = max_over_ranks(w0.ctx.timer_stop() / args.steps)
+        barrier()
+        sharded = {"value": world * px_step / (ms_sh / 1e3), "unit": UNIT, "ms_per_step": ms_sh,
+                   "collectives_per_step": (w0.ctx.comm_collectives(comm) - coll0) / args.steps,
+                   "iterations_per_plane": sh_iters,
+                   "what": f"each plane is ONE {world * S}x{S} image whose patch rows are sharded over {world} rank(s); one "
+                           "dictionary per plane; NCCL allreduce of atom statistics (1 per iteration + 1 per changed atom); "
+                           "one stream, planes in sequence"}
+        w0.ctx.comm_destroy(comm)
+
     # ---- CPU baseline (rank 0, N == 1): the reference's own code on a bounded crop
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -434,6 +476,8 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if sharded is not None:
+            line["row_sharded"] = sharded
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
