@@ -42,7 +42,7 @@ struct bic_stream {
 enum bic_kernel_id {
   KID_WORDS64_TO_DEV = 0, KID_DEV_TO_WORDS64, KID_PBM_TO_DEV, KID_DEV_TO_PBM, KID_WEIGHT, KID_XOR,
   KID_EXTRACT, KID_ASSEMBLE, KID_ROW_NONZERO, KID_GATHER_ROWS, KID_COL_HIST, KID_PIVOT_USAGE, KID_INIT_FINALIZE,
-  KID_UPDATE_COEF, KID_RESIDUAL, KID_TRANSPOSE_BITS, KID_UPDATE_DICT, KID_DICT_HIST, KID_DICT_RESOLVE,
+  KID_UPDATE_COEF, KID_RESIDUAL, KID_TRANSPOSE_BITS, KID_UPDATE_DICT, KID_DICT_HIST, KID_DICT_RESOLVE, KID_DICT_SCAN,
   KID_COMPACT_ROWS, KID_EXPAND_ROWS, KID_GOL_TILE_COUNTS, KID_GOL_SCAN_A, KID_GOL_LENGTHS, KID_GOL_SCAN_B,
   KID_GOL_SCATTER, KID_GOL_DECODE, KID_EG_FIRST, KID_EG_FILL, KID_EG_ENCODE, KID_EG_DECODE,
   KID_COUNT
@@ -128,8 +128,9 @@ static inline int bic_grid_for(const bic_ctx* ctx, uint64_t work_items, int per_
 // scratch layout of one dictionary update (dict2.cu), shared with the row-sharded driver (dist.cu)
 struct DictWork {
   uint64_t n, p, wpr, hs, wprN;
-  uint32_t *AT, *H, *U, *extra, *Hd, *Dnew, *cursor;
+  uint32_t *AT, *H, *U, *extra, *Hd, *Dnew, *cursor, *first;
   uint32_t launched;
+  bool use_scan;
 };
 
 // scratch layout of one neighbour initialisation (init.cu), shared with dist.cu

@@ -16,6 +16,7 @@
 #define TILE_THREADS 256
 #define TILE_WORDS_PER_THREAD 4
 #define TILE_WORDS (TILE_THREADS * TILE_WORDS_PER_THREAD)
+#define GOL_SMEM_WORDS 2560  // staged output range of one tile: 80 Kbit for 32 Kbit of input
 
 // ------------------------------------------------------------------ helpers
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
@@ -286,9 +287,23 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
     if (threadIdx.x == 0) g.bits[blockIdx.x] = tot;
     return;
   }
-  // pass 2: scatter
-  unsigned long long o = g.bits_before[blockIdx.x] + ex;
+  // pass 2: scatter. The tile's codewords are one contiguous bit range [o0, o0 + tot) of the stream.
+  // When it fits, the range is assembled in shared memory (shared-memory atomics, no L2 round trips)
+  // and flushed with coalesced stores; only its first and last word are shared with the neighbouring
+  // tiles and need a global atomic. Otherwise (very long unary runs) codewords go straight to global.
+  __shared__ uint32_t s_out[GOL_SMEM_WORDS];
+  const unsigned long long o0 = g.bits_before[blockIdx.x];
+  const unsigned long long base = o0 & ~31ull;                       // bit position of s_out[0]
+  const unsigned long long span_words = ((o0 - base) + tot + 31) >> 5;
+  const bool staged = span_words <= GOL_SMEM_WORDS;                  // uniform over the CTA
+  if (staged) {
+    for (unsigned i = threadIdx.x; i < (unsigned)span_words; i += blockDim.x) s_out[i] = 0;
+    __syncthreads();
+  }
+  unsigned long long o = o0 + ex;
   unsigned long long t = rank0;
+  const unsigned long long cmask = (unsigned long long)chunk - 1;  // chunk is a power of two
+  const int clog = 31 - __clz(chunk);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint32_t b = v[i];
@@ -298,13 +313,36 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
       const long long pos = (long long)((w0 + i) * 32 + p);
       const unsigned long long x = (unsigned long long)(pos - prev - 1);
       const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
-      if (t % chunk == 0) { index[2 * (t / chunk)] = o; index[2 * (t / chunk) + 1] = (unsigned long long)(prev + 1); }
-      put_bits(out, o, (uint32_t)(x & ((1ull << k) - 1)), k);  // k-bit remainder, MSB first
-      o += k + (x >> k);                                       // x>>k zeros (the buffer is zeroed)
-      put_one(out, o);                                         // closing one
-      o += 1;
+      if ((t & cmask) == 0) { index[2 * (t >> clog)] = o; index[2 * (t >> clog) + 1] = (unsigned long long)(prev + 1); }
+      const uint32_t rem = (uint32_t)(x & ((1ull << k) - 1));        // k-bit remainder, MSB first
+      const unsigned long long stop = o + k + (x >> k);              // x>>k zeros (the buffer is zeroed), then a one
+      if (staged) {
+        if (rem) {
+          const unsigned lo_bit = (unsigned)(o - base);
+          const unsigned long long v64 = (unsigned long long)rem << (64 - (lo_bit & 31) - k);
+          const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
+          if (hi) atomicOr(&s_out[lo_bit >> 5], hi);
+          if (lo) atomicOr(&s_out[(lo_bit >> 5) + 1], lo);
+        }
+        const unsigned sb = (unsigned)(stop - base);
+        atomicOr(&s_out[sb >> 5], 0x80000000u >> (sb & 31));
+      } else {
+        put_bits(out, o, rem, k);
+        put_one(out, stop);
+      }
+      o = stop + 1;
       prev = pos;
       ++t;
+    }
+  }
+  if (staged) {
+    __syncthreads();
+    uint32_t* gout = out + (base >> 5);
+    for (unsigned i = threadIdx.x; i < (unsigned)span_words; i += blockDim.x) {
+      const uint32_t w = s_out[i];
+      if (!w) continue;
+      if (i == 0 || i == (unsigned)span_words - 1) atomicOr(gout + i, bswap32(w));
+      else gout[i] = bswap32(w);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // the run closed by the virtual one
@@ -562,6 +600,7 @@ extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t c
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !M || !out) return BIC_ERR_INVALID;
   if (chunk_samples == 0) chunk_samples = 256;
+  while (chunk_samples & (chunk_samples - 1)) chunk_samples++;  // the kernels index chunks with shifts: round up to a power of two
   const uint64_t N = M->rows * M->cols;
   const uint32_t* S; uint64_t T, ntiles; GolTile g;
   BIC_TRY(golomb_prepare(c, M, &S, &T, &g, &ntiles));

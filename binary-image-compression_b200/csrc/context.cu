@@ -423,7 +423,7 @@ extern "C" uint64_t bic_rand48_uniform_int(uint64_t* state, uint64_t n) {
 static const char* const kKernelNames[KID_COUNT] = {
   "k_words64_to_dev", "k_dev_to_words64", "k_pbm_to_dev", "k_dev_to_pbm", "k_weight", "k_xor",
   "k_extract", "k_assemble", "k_row_nonzero", "k_gather_rows", "k_col_hist", "k_pivot_usage", "k_init_finalize",
-  "k_update_coefficients", "k_residual", "k_transpose_bits", "k_update_dictionary", "k_dict_hist_all", "k_dict_resolve",
+  "k_update_coefficients", "k_residual", "k_transpose_bits", "k_update_dictionary", "k_dict_hist_popc", "k_dict_resolve", "k_dict_scan",
   "k_compact_rows", "k_expand_rows", "k_gol_tile_counts", "k_gol_scan_tiles_a", "k_gol_walk<0>", "k_gol_scan_tiles_b",
   "k_gol_walk<1>", "k_gol_decode", "k_first_one/zero", "k_fill_ones", "k_eg_encode", "k_eg_decode"};
 

@@ -103,9 +103,119 @@ struct ResolveParams {
   const uint32_t* U;
   unsigned long long* changed;
   uint32_t* cursor;      // [2]: this launch reads [parity], writes [parity ^ 1]
+  uint32_t* first;       // [2]: scan/fix variant: first changing atom found by the scan of this parity
   uint64_t n, wprE, wprA, wprN, m, hs;
   uint32_t p, parity, win;  // win: histogram rows cached in shared memory per refill
 };
+
+// Atom k changes by s_delta = D_k ^ newD_k (shared memory, same in every CTA): patch its users'
+// residual rows, correct the histograms of the later atoms those rows use, publish newD_k and the cursor.
+__device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32_t k, const uint32_t* s_delta) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t* at = P.AT + (uint64_t)k * P.wprN;
+  if (P.wprE >= 8) {
+    // wide rows: a WARP per user row, lanes over the row's words (coalesced), so a 1024-bit row is 32
+    // lanes x 1 word instead of one lane x 32 words. AT words are spread over warps one by one.
+    for (uint64_t wi = gw; wi < P.wprN; wi += nwarps) {
+      uint32_t bits = __ldg(at + wi);
+      while (bits) {  // warp-uniform
+        const int pos = __clz(bits);
+        bits &= ~(0x80000000u >> pos);
+        const uint64_t i = wi * 32 + pos;
+        uint32_t* erow = P.E + i * P.wprE;
+        const uint32_t* arow = P.A + i * P.wprA;
+        for (uint64_t w0 = 0; w0 < P.wprE; w0 += 32) {
+          const uint64_t w = w0 + lane;
+          const uint32_t dl0 = (w < P.wprE) ? s_delta[w] : 0u;
+          const uint32_t e = (dl0 != 0) ? erow[w] : 0u;
+          if (__any_sync(0xffffffffu, dl0 != 0)) {
+            for (uint64_t aw = k >> 5; aw < P.wprA; ++aw) {   // later atoms used by this row (warp-uniform)
+              uint32_t ab = __ldg(arow + aw);
+              if (aw == (k >> 5)) ab &= (0x7FFFFFFFu >> (k & 31));
+              while (ab) {
+                const int ap = __clz(ab);
+                ab &= ~(0x80000000u >> ap);
+                uint32_t* hl = P.Hc + (aw * 32 + ap) * P.hs + w * 32;
+                uint32_t dl = dl0;
+                while (dl) {
+                  const int bp = __clz(dl);
+                  dl &= ~(0x80000000u >> bp);
+                  atomicAdd(hl + bp, ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u);
+                }
+              }
+            }
+          }
+          if (dl0) erow[w] = e ^ dl0;                         // E_i ^= Dk ^ newDk, :512-520
+        }
+      }
+    }
+  } else {
+    // narrow rows: a lane per user row. The users of a group of 32 AT words (1024 rows) are first listed
+    // in a per-warp shared-memory queue so the lanes get an even share (two or three rows each): the pass
+    // is a chain of dependent L2 round trips per row, so its duration is the LONGEST lane's chain.
+    __shared__ uint16_t s_q[8][1024];  // row index within the group
+    uint16_t* q = s_q[threadIdx.x >> 5];
+    const uint64_t ngroups = div_up_u64(P.wprN, 32);
+    for (uint64_t g = gw; g < ngroups; g += nwarps) {
+      const uint64_t wi = g * 32 + lane;
+      uint32_t bits = (wi < P.wprN) ? __ldg(at + wi) : 0u;
+      const uint32_t cnt = __popc(bits);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      uint32_t off = incl - cnt;
+      while (bits) {
+        const int pos = __clz(bits);
+        bits &= ~(0x80000000u >> pos);
+        q[off++] = (uint16_t)(lane * 32 + pos);
+      }
+      __syncwarp();
+      for (uint32_t t = lane; t < total; t += 32) {
+        const uint64_t i = g * 1024 + q[t];
+        uint32_t* erow = P.E + i * P.wprE;
+        const uint32_t* arow = P.A + i * P.wprA;
+        for (uint64_t aw = k >> 5; aw < P.wprA; ++aw) {   // later atoms used by this row
+          uint32_t ab = __ldg(arow + aw);
+          if (aw == (k >> 5)) ab &= (0x7FFFFFFFu >> (k & 31));  // strictly after k
+          while (ab) {
+            const int ap = __clz(ab);
+            ab &= ~(0x80000000u >> ap);
+            uint32_t* hl = P.Hc + (aw * 32 + ap) * P.hs;
+            for (uint64_t w = 0; w < P.wprE; ++w) {
+              uint32_t dl = s_delta[w];
+              if (!dl) continue;
+              const uint32_t e = erow[w];
+              while (dl) {
+                const int bp = __clz(dl);
+                dl &= ~(0x80000000u >> bp);
+                atomicAdd(hl + w * 32 + bp, ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u);
+              }
+            }
+          }
+        }
+        for (uint64_t w = 0; w < P.wprE; ++w) {           // E_i ^= Dk ^ newDk, :512-520
+          const uint32_t dl = s_delta[w];
+          if (dl) erow[w] ^= dl;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (uint64_t w = threadIdx.x; w < P.wprE; w += blockDim.x)
+      P.Dnew[(uint64_t)k * P.wprE + w] = __ldg(P.D + (uint64_t)k * P.wprE + w) ^ s_delta[w];  // :510
+    if (threadIdx.x == 0) {
+      atomicAdd(P.changed, 1ull);                       // :509
+      P.cursor[P.parity ^ 1] = k + 1;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(256) k_dict_resolve_step(ResolveParams P) {
   extern __shared__ uint32_t s_mem[];
@@ -162,54 +272,72 @@ __global__ void __launch_bounds__(256) k_dict_resolve_step(ResolveParams P) {
     if (blockIdx.x == 0 && threadIdx.x == 0) P.cursor[P.parity ^ 1] = P.p;
     return;
   }
-  // ---- atom k changes: patch its users' residuals and the histograms of the later atoms they use
+  dict_apply_change(P, k, s_delta);
+}
+
+// ------------------------------------------------------------------ pass 2 for large dictionaries
+// With many atoms the serial walk above (every CTA re-derives every atom) is the bottleneck. Instead:
+//   k_dict_scan : all atoms at or after the cursor are tested IN PARALLEL against the current H
+//                 ("would this atom change?"); atomicMin keeps the first one.
+//   k_dict_fix  : that atom is the next to change in the reference's order (every earlier one is
+//                 unchanged under the same H); the grid applies its corrections and advances the cursor.
+// Atoms after the first changing one are re-tested by the next scan, after the corrections landed.
+__global__ void __launch_bounds__(256) k_dict_scan(ResolveParams P) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t start = __ldcg(P.cursor + P.parity);
+  if (start >= P.p) return;
   const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint64_t nchunks = div_up_u64(P.wprN, 32);
-  const uint32_t* at = P.AT + (uint64_t)k * P.wprN;
-  for (uint64_t ch = gw; ch < nchunks; ch += nwarps) {
-    const uint64_t wi = ch * 32 + lane;
-    uint32_t bits = (wi < P.wprN) ? __ldg(at + wi) : 0u;
-    const uint64_t row0 = wi * 32;
-    while (bits) {
-      const int pos = __clz(bits);
-      bits &= ~(0x80000000u >> pos);
-      const uint64_t i = row0 + pos;
-      uint32_t* erow = P.E + i * P.wprE;
-      const uint32_t* arow = P.A + i * P.wprA;
-      for (uint64_t aw = k >> 5; aw < P.wprA; ++aw) {   // later atoms used by this row
-        uint32_t ab = __ldg(arow + aw);
-        if (aw == (k >> 5)) ab &= (0x7FFFFFFFu >> (k & 31));  // strictly after k
-        while (ab) {
-          const int ap = __clz(ab);
-          ab &= ~(0x80000000u >> ap);
-          uint32_t* hl = P.Hc + (aw * 32 + ap) * P.hs;
-          for (uint64_t w = 0; w < P.wprE; ++w) {
-            uint32_t dl = s_delta[w];
-            if (!dl) continue;
-            const uint32_t e = erow[w];
-            while (dl) {
-              const int bp = __clz(dl);
-              dl &= ~(0x80000000u >> bp);
-              atomicAdd(hl + w * 32 + bp, ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u);
-            }
-          }
-        }
+  for (uint64_t k = start + gw; k < P.p; k += nwarps) {
+    if (k >= __ldcg(P.first + P.parity)) break;  // an earlier atom already changes
+    const uint32_t usage = __ldg(P.U + k);
+    if (usage == 0) continue;
+    const uint32_t half = usage >> 1;
+    const uint32_t* hk = P.H + k * P.hs;
+    bool any = false;
+    for (uint64_t w = 0; w < P.wprE; ++w) {
+      const uint64_t j = w * 32 + lane;
+      const uint32_t dk = __ldg(P.D + k * P.wprE + w);
+      uint32_t bit = 0;
+      if (j < P.m) {
+        const uint32_t ce = __ldcg(hk + j);
+        const uint32_t weight = ((dk >> (31 - lane)) & 1u) ? usage - ce : ce;
+        bit = weight > half;
       }
-      for (uint64_t w = 0; w < P.wprE; ++w) {           // E_i ^= Dk ^ newDk, :512-520
-        const uint32_t dl = s_delta[w];
-        if (dl) erow[w] ^= dl;
-      }
+      const uint32_t nd = __brev(__ballot_sync(0xffffffffu, bit));
+      any |= (nd != dk);
     }
+    if (any && lane == 0) atomicMin(P.first + P.parity, (uint32_t)k);
   }
-  if (blockIdx.x == 0) {
-    for (uint64_t w = threadIdx.x; w < P.wprE; w += blockDim.x)
-      P.Dnew[(uint64_t)k * P.wprE + w] = __ldg(P.D + (uint64_t)k * P.wprE + w) ^ s_delta[w];  // :510
-    if (threadIdx.x == 0) {
-      atomicAdd(P.changed, 1ull);                       // :509
-      P.cursor[P.parity ^ 1] = k + 1;
+}
+
+__global__ void __launch_bounds__(256) k_dict_fix(ResolveParams P) {
+  extern __shared__ uint32_t s_delta[];  // wprE
+  const int lane = threadIdx.x & 31;
+  const uint32_t start = __ldcg(P.cursor + P.parity);
+  const uint32_t k = __ldcg(P.first + P.parity);
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.first[P.parity ^ 1] = P.p;  // arm the next scan
+  if (start >= P.p || k >= P.p) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.cursor[P.parity ^ 1] = P.p;
+    return;
+  }
+  const uint32_t usage = __ldg(P.U + k);
+  const uint32_t half = usage >> 1;
+  const uint32_t* hk = P.H + (uint64_t)k * P.hs;
+  for (uint64_t w = threadIdx.x >> 5; w < P.wprE; w += blockDim.x >> 5) {
+    const uint64_t j = w * 32 + lane;
+    const uint32_t dk = __ldg(P.D + (uint64_t)k * P.wprE + w);
+    uint32_t bit = 0;
+    if (j < P.m) {
+      const uint32_t ce = __ldcg(hk + j);
+      const uint32_t weight = ((dk >> (31 - lane)) & 1u) ? usage - ce : ce;
+      bit = weight > half;
     }
+    const uint32_t nd = __brev(__ballot_sync(0xffffffffu, bit));
+    if (lane == 0) s_delta[w] = nd ^ dk;
   }
+  __syncthreads();
+  dict_apply_change(P, k, s_delta);
 }
 
 static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs) {
@@ -250,10 +378,17 @@ bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat*
   w->Hd = w->extra + 64;
   w->Dnew = (uint32_t*)c->work[0].p;
   w->cursor = w->Dnew + p * wpr;
+  w->first = w->cursor + 2;
   w->launched = 0;
+  // a dictionary whose histogram fits one shared-memory window is walked serially inside one launch;
+  // larger ones use the parallel scan + fix pair
+  w->use_scan = (p * (w->hs + 1) * 4 > 32 * 1024);
   BIC_CUDA(c, cudaMemsetAsync(w->H, 0, (size_t)(2 * p * w->hs + p + 64) * 4, c->stream));
   BIC_CUDA(c, cudaMemcpyAsync(w->Dnew, D->d, (size_t)p * wpr * 4, cudaMemcpyDeviceToDevice, c->stream));
-  BIC_CUDA(c, cudaMemsetAsync(w->cursor, 0, 8, c->stream));
+  {
+    const uint32_t init[4] = {0u, 0u, (uint32_t)p, (uint32_t)p};  // cursor[2], first[2]
+    BIC_CUDA(c, cudaMemcpyAsync(w->cursor, init, 16, cudaMemcpyHostToDevice, c->stream));
+  }
   if (n) {
     BIC_TRY(bic_k_transpose_A(c, A, w->AT, w->wprN));
     BIC_TRY(launch_hist(c, E, A, w->H, w->U, w->hs));
@@ -266,18 +401,29 @@ bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_m
                            unsigned long long* d_changed) {
   ResolveParams P;
   P.E = E->d; P.D = D->d; P.Dnew = w->Dnew; P.A = A->d; P.AT = w->AT; P.H = w->H; P.Hc = Hc; P.U = w->U;
-  P.changed = d_changed; P.cursor = w->cursor;
+  P.changed = d_changed; P.cursor = w->cursor; P.first = w->first;
   P.n = w->n; P.wprE = w->wpr; P.wprA = A->wpr; P.wprN = w->wprN; P.m = E->cols; P.hs = w->hs; P.p = (uint32_t)w->p;
   uint64_t win = (32 * 1024 / 4) / (w->hs + 1);
   if (win < 1) win = 1;
   if (win > w->p) win = w->p;
   P.win = (uint32_t)win;
   const size_t smem = (size_t)(w->wpr + win * (w->hs + 1)) * 4;
-  const int grid = bic_grid_for(c, div_up_u64(w->wprN ? w->wprN : 1, 32) * 32, 256, 4);
+  const int grid = (w->wpr >= 8) ? bic_grid_for(c, (w->wprN ? w->wprN : 1) * 32, 256, 8)
+                                 : bic_grid_for(c, div_up_u64(w->wprN ? w->wprN : 1, 32) * 32, 256, 4);
   P.parity = w->launched & 1;
-  BIC_PROF(c, KID_DICT_RESOLVE);
-  k_dict_resolve_step<<<grid, 256, smem, c->stream>>>(P);
-  BIC_LAUNCH_CHECK(c);
+  if (w->use_scan) {
+    const int sgrid = bic_grid_for(c, w->p * 32, 256, 4);
+    BIC_PROF(c, KID_DICT_SCAN);
+    k_dict_scan<<<sgrid, 256, 0, c->stream>>>(P);
+    BIC_LAUNCH_CHECK(c);
+    BIC_PROF(c, KID_DICT_RESOLVE);
+    k_dict_fix<<<grid, 256, (size_t)w->wpr * 4, c->stream>>>(P);
+    BIC_LAUNCH_CHECK(c);
+  } else {
+    BIC_PROF(c, KID_DICT_RESOLVE);
+    k_dict_resolve_step<<<grid, 256, smem, c->stream>>>(P);
+    BIC_LAUNCH_CHECK(c);
+  }
   w->launched++;
   return BIC_OK;
 }
