@@ -175,6 +175,36 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
 #undef BIC_T32_STAGE
   return x;
 }
+// ---- TMA bulk copy (cp.async.bulk, 1-D) of a contiguous global block into shared memory, completion
+// signalled on an mbarrier. Used to stage the dictionary (the atom tile every row of a CTA is matched
+// against). bytes must be a multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_stage_begin(uint64_t* bar) {  // one thread, before the copies
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_stage_copy(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  while (done < bytes) {  // pieces of at most 32 KB
+    const uint32_t n = (bytes - done < 32768u) ? bytes - done : 32768u;
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared((char*)smem_dst + done);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"((const char*)gmem_src + done), "r"(n), "r"(b) : "memory");
+    done += n;
+  }
+}
+__device__ __forceinline__ void tma_stage_wait(uint64_t* bar) {  // every thread that reads the staged data
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(b) : "memory");
+    if (spin > (1u << 26)) __trap();  // never spin forever on a lost copy
+  }
+}
+
 // mask of the valid bits of the last word of a row with `cols` columns
 __host__ __device__ __forceinline__ uint32_t tail_mask32(uint64_t cols) {
   const unsigned r = (unsigned)(cols & 31);

@@ -29,12 +29,24 @@ __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restric
                                                              uint32_t* __restrict__ A, uint64_t n, uint64_t wprE,
                                                              uint32_t p, uint64_t wprA,
                                                              unsigned long long* __restrict__ changed) {
-  extern __shared__ uint32_t Ds[];  // p * WORDS, rows zero padded to WORDS
-  for (uint32_t i = threadIdx.x; i < p * WORDS; i += blockDim.x) {
-    const uint32_t k = i / WORDS, w = i - k * WORDS;
-    Ds[i] = (w < wprE) ? D[(uint64_t)k * wprE + w] : 0u;
+  extern __shared__ __align__(16) uint32_t Ds[];  // p * WORDS, rows zero padded to WORDS
+  __shared__ uint64_t tma_bar;
+  // The atom tile: when the rows need no padding (m = 64, 256, 1024 ...) the whole dictionary is one
+  // contiguous block and is staged by the TMA engine (cp.async.bulk) while the threads set up;
+  // otherwise it is re-strided with ordinary loads.
+  const bool bulk = (wprE == WORDS) && ((p * WORDS * 4u) % 16u == 0);
+  if (bulk) {
+    if (threadIdx.x == 0) tma_stage_begin(&tma_bar);
+    __syncthreads();
+    if (threadIdx.x == 0) tma_stage_copy(Ds, D, p * WORDS * 4u, &tma_bar);
+    tma_stage_wait(&tma_bar);
+  } else {
+    for (uint32_t i = threadIdx.x; i < p * WORDS; i += blockDim.x) {
+      const uint32_t k = i / WORDS, w = i - k * WORDS;
+      Ds[i] = (w < wprE) ? D[(uint64_t)k * wprE + w] : 0u;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   uint32_t nchanged = 0;
   for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t e[WORDS];
