@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--atoms", type=int, default=32)
     ap.add_argument("--cpu-crop", type=int, default=2048, help="crop edge for the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch", action="store_true", help="per-plane learner calls instead of the batched learner")
     ap.add_argument("--sharded", action="store_true", help="also time the row-sharded (NCCL) fit at N=1")
     ap.add_argument("--streams", type=int, default=16, help="contexts (CUDA streams) per GPU")
     return ap.parse_args()
@@ -262,7 +263,7 @@ def main():
             self.streams = [c.stream() for _ in range(3)]
             self.out = c.pinned(2 * plane_bytes + (1 << 20))
 
-    T = max(1, min(args.streams, P))
+    T = max(1, min(args.streams, P * max(1, args.steps)))  # tasks of all steps share one queue
     workers = [Worker() for _ in range(T)]
     stats = {"iters": [0] * P, "bits": [0] * P, "d2h": [0] * P}
 
@@ -338,30 +339,130 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- batched mode: per-plane matrices; extract+init and Golomb coding stay per plane on the worker
+    # streams, the learner runs ONCE for all planes (bic_learn_model_traditional_batched on the main context)
+    batched = not args.no_batch
+    if batched:
+        planes_m = [dict(X=ctx.matrix(n, m), E=ctx.matrix(n, m), D=ctx.matrix(K, m), A=ctx.matrix(n, K),
+                         streams=[ctx.stream() for _ in range(3)], out=ctx.pinned(2 * plane_bytes + (1 << 20)))
+                    for _ in range(P)]
+
+    def run_phase(fn, nworkers=T):
+        q = queue.Queue()
+        for b in order:
+            q.put(b)
+        errs = []
+
+        def loop(w):
+            try:
+                while True:
+                    try:
+                        b = q.get_nowait()
+                    except queue.Empty:
+                        return
+                    fn(w, b)
+            except Exception as ex:  # noqa: BLE001
+                errs.append(ex)
+        ths = [threading.Thread(target=loop, args=(w,)) for w in workers[:nworkers]]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def prep_resident(w, b):
+        c, pm = w.ctx, planes_m[b]
+        c._ck(L.bic_extract_patches(c.h, rasters[b].h, W, pm["X"].h))
+        rng = c.rand48(SEED)
+        c._ck(L.bic_initialize_model_neighbor(c.h, pm["X"].h, pm["D"].h, pm["A"].h, C.byref(rng)))
+
+    def prep_e2e(w, b):
+        c, pm = w.ctx, planes_m[b]
+        c._ck(L.bic_mat_upload_pbm(c.h, rasters[b].h, host_planes[b].ctypes.data_as(C.POINTER(C.c_uint8))))
+        prep_resident(w, b)
+
+    def code_resident(w, b, record=False):
+        c, pm = w.ctx, planes_m[b]
+        bits = 0
+        for M, s in zip((pm["D"], pm["A"], pm["E"]), pm["streams"]):
+            c._ck(L.bic_golomb_encode(c.h, M.h, 256, s.h))
+            if record:
+                bits += s.info.bitcount
+        if record:
+            stats["bits"][b] = bits
+
+    def code_e2e(w, b):
+        c, pm = w.ctx, planes_m[b]
+        off, total = 0, 0
+        out = pm["out"]
+        for M, s in zip((pm["D"], pm["A"], pm["E"]), pm["streams"]):
+            c._ck(L.bic_golomb_encode(c.h, M.h, 256, s.h))
+            si = s.info
+            nb, ni = (si.bitcount + 7) // 8, int(si.nchunks)
+            nbp = (nb + 7) & ~7
+            idx = out[off + nbp: off + nbp + ni * 16].view(np.uint64)
+            c._ck(L.bic_stream_download(c.h, s.h, out[off:].ctypes.data_as(C.POINTER(C.c_uint8)), nb,
+                                        idx.ctypes.data_as(C.POINTER(C.c_uint64)), ni))
+            off += nbp + ni * 16
+            total += nb + ni * 16
+        stats["d2h"][b] = total
+
+    def batched_steps(nsteps, e2e=False, record=False):
+        ctx.timer_start()
+        for _ in range(nsteps):
+            for w in workers:
+                w.ctx.wait_for(ctx)
+            run_phase(prep_e2e if e2e else prep_resident)
+            for w in workers:
+                ctx.wait_for(w.ctx)
+            its = ctx.learn_model_traditional_batched([pm["X"] for pm in planes_m], [pm["E"] for pm in planes_m],
+                                                      [pm["D"] for pm in planes_m], [pm["A"] for pm in planes_m])
+            if record:
+                stats["iters"] = its
+            for w in workers:
+                w.ctx.wait_for(ctx)
+            run_phase(code_e2e if e2e else (lambda w, b: code_resident(w, b, record)))
+            for w in workers:
+                ctx.wait_for(w.ctx)
+        return ctx.timer_stop()
+
+    def all_launches():
+        return ctx.launches + sum(w.ctx.launches for w in workers)
+
     # ---- resident timing
     run_steps(fit_resident, 1, record=True)
     order.sort(key=lambda b: -stats["iters"][b])
-    run_steps(fit_resident, max(args.warmup, 3))
+    if batched:
+        per_plane_iters = list(stats["iters"])
+        batched_steps(1, record=True)
+        assert stats["iters"] == per_plane_iters, "batched learner disagrees with the per-plane path"
+        batched_steps(max(args.warmup, 3))
+    else:
+        run_steps(fit_resident, max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    launches0 = ctx.launches + sum(w.ctx.launches for w in workers)
+    launches0 = all_launches()
     barrier()
     t_wall0 = time.time()
-    ms = run_steps(fit_resident, args.steps)
+    ms = batched_steps(args.steps) if batched else run_steps(fit_resident, args.steps)
     barrier()
     t_wall1 = time.time()
-    launches = ctx.launches + sum(w.ctx.launches for w in workers) - launches0
+    launches = all_launches() - launches0
     clocks = sampler.stop(t_wall0, t_wall1)
     ms_per_step = max_over_ranks(ms / args.steps)
     px_step = P * rows * cols / 1e6  # Mpixel per rank per step
     value = world * px_step / (ms_per_step / 1e3)
 
     # ---- e2e timing (host buffers, H2D + D2H inside)
-    run_steps(fit_e2e, 2)
+    if batched:
+        batched_steps(2, e2e=True)
+    else:
+        run_steps(fit_e2e, 2)
     barrier()
-    ms_e2e = run_steps(fit_e2e, args.steps)
+    ms_e2e = batched_steps(args.steps, e2e=True) if batched else run_steps(fit_e2e, args.steps)
     barrier()
     ms_e2e_step = max_over_ranks(ms_e2e / args.steps)
     e2e_value = world * px_step / (ms_e2e_step / 1e3)
@@ -465,7 +566,8 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args), "patch_width": W, "atoms": K, "patches_per_plane": n,
                        "parallelism": f"{world} rank(s), one 16-plane image per rank, no data-path collective; "
-                                      f"{T} contexts (CUDA streams) per rank keep independent planes in flight",
+                                      f"{T} contexts (CUDA streams) per rank keep independent planes in flight for extraction, "
+                                      f"initialisation and coding; learner: {'one batched call for all planes' if batched else 'per plane'}",
                        "l2_policy": f"inputs larger than L2: {P} planes x {plane_bytes >> 20} MiB rasters + X/E/A "
                                     f"({(2 * n * m + n * K) // 8 >> 20} MiB per plane) cycle through a 126 MB L2",
                        "iterations_per_plane": stats["iters"], "golomb_bits_per_step": stats["bits"]},

@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
         "bic_dist_initialize_model_neighbor": [_vp, _vp, _vp, _vp, _vp, _u64p],
         "bic_dist_update_dictionary_steepest": [_vp, _vp, _vp, _vp, _vp, _u64p],
         "bic_dist_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
+        "bic_learn_model_traditional_batched": [_vp, C.c_uint32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _u64p],
         "bic_stream_create": [_vp, C.POINTER(_vp)],
         "bic_stream_destroy": [_vp, _vp],
         "bic_stream_get_info": [_vp, C.POINTER(StreamInfo)],
@@ -391,6 +392,15 @@ class Context:
                                                     tr.ctypes.data_as(_u64p), trace_cap))
         n = int(it.value)
         return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
+
+    def learn_model_traditional_batched(self, Xs, Es, Ds, As) -> list[int]:
+        """independent fits of identical shape, every kernel launched once for the whole batch"""
+        n = len(Xs)
+        arr = lambda ms: (_vp * n)(*[m.h for m in ms])  # noqa: E731
+        its = np.zeros(n, np.uint64)
+        self._ck(self.L.bic_learn_model_traditional_batched(self.h, n, arr(Xs), arr(Es), arr(Ds), arr(As),
+                                                            its.ctypes.data_as(_u64p)))
+        return [int(v) for v in its]
 
     # ---- several GPUs (rows sharded, D replicated)
     @staticmethod

@@ -125,6 +125,13 @@ static inline int bic_grid_for(const bic_ctx* ctx, uint64_t work_items, int per_
   return (int)(need < cap ? need : cap);
 }
 
+// One problem of a batch of equally shaped fits (batch.cu): kernels launched with a problem table take
+// their pointers from probs[blockIdx.y or .z] and return at once for problems that already converged.
+struct ProbDev {
+  uint32_t *E, *D, *A, *AT, *H, *U, *Dnew, *cursor, *first;
+  unsigned long long* counts;  // [0] changed rows, [1] changed atoms of the current iteration
+};
+
 // scratch layout of one dictionary update (dict2.cu), shared with the row-sharded driver (dist.cu)
 struct DictWork {
   uint64_t n, p, wpr, hs, wprN;

@@ -28,7 +28,14 @@ template <int WORDS>
 __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restrict__ E, const uint32_t* __restrict__ D,
                                                              uint32_t* __restrict__ A, uint64_t n, uint64_t wprE,
                                                              uint32_t p, uint64_t wprA,
-                                                             unsigned long long* __restrict__ changed) {
+                                                             unsigned long long* __restrict__ changed,
+                                                             const ProbDev* __restrict__ probs,
+                                                             const uint32_t* __restrict__ active) {
+  if (probs) {  // batched launch: blockIdx.y selects the problem
+    if (!active[blockIdx.y]) return;
+    const ProbDev pr = probs[blockIdx.y];
+    E = pr.E; D = pr.D; A = pr.A; changed = pr.counts;
+  }
   extern __shared__ __align__(16) uint32_t Ds[];  // p * WORDS, rows zero padded to WORDS
   __shared__ uint64_t tma_bar;
   // The atom tile: when the rows need no padding (m = 64, 256, 1024 ...) the whole dictionary is one
@@ -138,9 +145,45 @@ static bic_status launch_coef(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat*
   const int grid = bic_grid_for(c, E->rows, 256, per_sm);
   BIC_PROF(c, KID_UPDATE_COEF);
   k_update_coefficients<WORDS><<<grid, 256, smem, c->stream>>>(E->d, D->d, A->d, E->rows, E->wpr, (uint32_t)D->rows,
-                                                              A->wpr, d_changed);
+                                                              A->wpr, d_changed, nullptr, nullptr);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
+}
+
+template <int WORDS>
+static bic_status launch_coef_batched(bic_ctx* c, uint64_t n, uint64_t wprE, uint64_t p, uint64_t wprA, const ProbDev* probs,
+                                      const uint32_t* active, uint32_t nprob) {
+  const size_t smem = (size_t)p * WORDS * 4;
+  if (smem > 48 * 1024)
+    BIC_CUDA(c, cudaFuncSetAttribute(k_update_coefficients<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = smem ? (int)((200 * 1024) / smem) : 8;
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  uint64_t gx = ((uint64_t)c->sm_count * per_sm + nprob - 1) / nprob;  // the whole batch fills the GPU once
+  const uint64_t need = div_up_u64(n, 256);
+  if (gx > need) gx = need;
+  if (gx < 1) gx = 1;
+  BIC_PROF(c, KID_UPDATE_COEF);
+  k_update_coefficients<WORDS><<<dim3((unsigned)gx, nprob), 256, smem, c->stream>>>(nullptr, nullptr, nullptr, n, wprE, (uint32_t)p,
+                                                                                   wprA, nullptr, probs, active);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+// all problems of a batch in one launch (same shapes); only rows up to 1024 bits and a dictionary that fits
+// in shared memory (the single-problem path has a fallback for the rest)
+bic_status bic_k_update_coefficients_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t p, const ProbDev* probs,
+                                             const uint32_t* active, uint32_t nprob) {
+  const uint64_t wpr = div_up_u64(m, 32), wprA = div_up_u64(p, 32);
+  const int WORDS = wpr <= 1 ? 1 : wpr <= 2 ? 2 : wpr <= 4 ? 4 : wpr <= 8 ? 8 : wpr <= 16 ? 16 : wpr <= 32 ? 32 : 0;
+  if (!WORDS || (size_t)p * WORDS * 4 > 200 * 1024 || p > 65535) return BIC_ERR_UNSUPPORTED;
+  switch (WORDS) {
+    case 1: return launch_coef_batched<1>(c, n, wpr, p, wprA, probs, active, nprob);
+    case 2: return launch_coef_batched<2>(c, n, wpr, p, wprA, probs, active, nprob);
+    case 4: return launch_coef_batched<4>(c, n, wpr, p, wprA, probs, active, nprob);
+    case 8: return launch_coef_batched<8>(c, n, wpr, p, wprA, probs, active, nprob);
+    case 16: return launch_coef_batched<16>(c, n, wpr, p, wprA, probs, active, nprob);
+    default: return launch_coef_batched<32>(c, n, wpr, p, wprA, probs, active, nprob);
+  }
 }
 
 // device-side entry used by the learner too: adds the changed-row count to *d_changed

@@ -27,7 +27,13 @@ namespace cg = cooperative_groups;
 // transposes the 32x32 bit tile with 32 ballots; the 32 tiles of a CTA give each of the slab's 32
 // atoms 32 consecutive words (128 B) of AT, written coalesced through shared memory.
 __global__ void __launch_bounds__(1024) k_transpose_bits(const uint32_t* __restrict__ A, uint64_t n, uint64_t wprA,
-                                                         uint32_t* __restrict__ AT, uint64_t wprN, uint64_t p) {
+                                                         uint32_t* __restrict__ AT, uint64_t wprN, uint64_t p,
+                                                         const ProbDev* __restrict__ probs, const uint32_t* __restrict__ active) {
+  if (probs) {  // batched launch: blockIdx.z selects the problem
+    if (!active[blockIdx.z]) return;
+    A = probs[blockIdx.z].A;
+    AT = probs[blockIdx.z].AT;
+  }
   __shared__ uint32_t tile[32][33];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint64_t cw = blockIdx.y;                    // column word of A (32 atoms)
@@ -196,7 +202,20 @@ bic_status bic_k_transpose_A(bic_ctx* c, const bic_mat* A, uint32_t* AT, uint64_
   const uint64_t gx = nblk < (uint64_t)c->sm_count * 2 ? nblk : (uint64_t)c->sm_count * 2;
   dim3 grid((unsigned)gx, (unsigned)A->wpr);
   BIC_PROF(c, KID_TRANSPOSE_BITS);
-  k_transpose_bits<<<grid, 1024, 0, c->stream>>>(A->d, n, A->wpr, AT, wprN, A->cols);
+  k_transpose_bits<<<grid, 1024, 0, c->stream>>>(A->d, n, A->wpr, AT, wprN, A->cols, nullptr, nullptr);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+bic_status bic_k_transpose_A_batched(bic_ctx* c, uint64_t n, uint64_t p, const ProbDev* probs, const uint32_t* active,
+                                     uint32_t nprob) {
+  const uint64_t wprA = div_up_u64(p, 32), wprN = div_up_u64(n, 32);
+  const uint64_t nblk = div_up_u64(n, 1024);
+  uint64_t gx = div_up_u64((uint64_t)c->sm_count * 2, wprA * nprob);
+  if (gx > nblk) gx = nblk;
+  if (gx < 1) gx = 1;
+  BIC_PROF(c, KID_TRANSPOSE_BITS);
+  k_transpose_bits<<<dim3((unsigned)gx, (unsigned)wprA, nprob), 1024, 0, c->stream>>>(nullptr, n, wprA, nullptr, wprN, p, probs, active);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }

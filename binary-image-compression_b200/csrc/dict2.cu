@@ -29,7 +29,13 @@
 template <int JW>
 __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restrict__ E, const uint32_t* __restrict__ A,
                                                         uint32_t* __restrict__ H, uint32_t* __restrict__ U, uint64_t n,
-                                                        uint64_t wprE, uint64_t wprA, uint64_t hs, uint32_t ntile_j) {
+                                                        uint64_t wprE, uint64_t wprA, uint64_t hs, uint32_t ntile_j,
+                                                        const ProbDev* __restrict__ probs, const uint32_t* __restrict__ active) {
+  if (probs) {  // batched launch: blockIdx.z selects the problem
+    if (!active[blockIdx.z]) return;
+    const ProbDev pr = probs[blockIdx.z];
+    E = pr.E; A = pr.A; H = pr.H; U = pr.U;
+  }
   __shared__ uint32_t s_acc[32 * JW * 32];
   __shared__ uint32_t s_u[32];
   const int lane = threadIdx.x & 31;
@@ -106,7 +112,19 @@ struct ResolveParams {
   uint32_t* first;       // [2]: scan/fix variant: first changing atom found by the scan of this parity
   uint64_t n, wprE, wprA, wprN, m, hs;
   uint32_t p, parity, win;  // win: histogram rows cached in shared memory per refill
+  const ProbDev* probs;     // batched launch: blockIdx.y selects the problem (else null)
+  const uint32_t* active;
 };
+
+// batched launch: swap in the problem's pointers; false = this problem already converged
+__device__ __forceinline__ bool resolve_select_problem(ResolveParams& P) {
+  if (!P.probs) return true;
+  if (!P.active[blockIdx.y]) return false;
+  const ProbDev pr = P.probs[blockIdx.y];
+  P.E = pr.E; P.D = pr.D; P.Dnew = pr.Dnew; P.A = pr.A; P.AT = pr.AT; P.H = pr.H; P.Hc = pr.H; P.U = pr.U;
+  P.changed = pr.counts + 1; P.cursor = pr.cursor; P.first = pr.first;
+  return true;
+}
 
 // Atom k changes by s_delta = D_k ^ newD_k (shared memory, same in every CTA): patch its users'
 // residual rows, correct the histograms of the later atoms those rows use, publish newD_k and the cursor.
@@ -218,6 +236,7 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
 }
 
 __global__ void __launch_bounds__(256) k_dict_resolve_step(ResolveParams P) {
+  if (!resolve_select_problem(P)) return;
   extern __shared__ uint32_t s_mem[];
   uint32_t* s_delta = s_mem;              // wprE
   uint32_t* s_U = s_delta + P.wprE;       // win
@@ -283,6 +302,7 @@ __global__ void __launch_bounds__(256) k_dict_resolve_step(ResolveParams P) {
 //                 unchanged under the same H); the grid applies its corrections and advances the cursor.
 // Atoms after the first changing one are re-tested by the next scan, after the corrections landed.
 __global__ void __launch_bounds__(256) k_dict_scan(ResolveParams P) {
+  if (!resolve_select_problem(P)) return;
   const int lane = threadIdx.x & 31;
   const uint32_t start = __ldcg(P.cursor + P.parity);
   if (start >= P.p) return;
@@ -312,6 +332,7 @@ __global__ void __launch_bounds__(256) k_dict_scan(ResolveParams P) {
 }
 
 __global__ void __launch_bounds__(256) k_dict_fix(ResolveParams P) {
+  if (!resolve_select_problem(P)) return;
   extern __shared__ uint32_t s_delta[];  // wprE
   const int lane = threadIdx.x & 31;
   const uint32_t start = __ldcg(P.cursor + P.parity);
@@ -352,8 +373,8 @@ static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, ui
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, ntiles);
   BIC_PROF(c, KID_DICT_HIST);
-  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j);
-  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j);
+  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr);
+  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }
@@ -401,7 +422,7 @@ bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_m
                            unsigned long long* d_changed) {
   ResolveParams P;
   P.E = E->d; P.D = D->d; P.Dnew = w->Dnew; P.A = A->d; P.AT = w->AT; P.H = w->H; P.Hc = Hc; P.U = w->U;
-  P.changed = d_changed; P.cursor = w->cursor; P.first = w->first;
+  P.changed = d_changed; P.cursor = w->cursor; P.first = w->first; P.probs = nullptr; P.active = nullptr;
   P.n = w->n; P.wprE = w->wpr; P.wprA = A->wpr; P.wprN = w->wprN; P.m = E->cols; P.hs = w->hs; P.p = (uint32_t)w->p;
   uint64_t win = (32 * 1024 / 4) / (w->hs + 1);
   if (win < 1) win = 1;
@@ -425,6 +446,56 @@ bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_m
     BIC_LAUNCH_CHECK(c);
   }
   w->launched++;
+  return BIC_OK;
+}
+
+// ---- batched variants (batch.cu): the same kernels over a problem table
+bic_status bic_k_dict_hist_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t p, const ProbDev* probs, const uint32_t* active,
+                                   uint32_t nprob) {
+  const uint64_t wprE = div_up_u64(m, 32), wprA = div_up_u64(p, 32), hs = wprE * 32;
+  const bool two = wprE >= 2;
+  const uint32_t ntile_j = (uint32_t)(two ? div_up_u64(wprE, 2) : 1);
+  const uint32_t ntiles = (uint32_t)wprA * ntile_j;
+  uint64_t gx = div_up_u64((uint64_t)c->sm_count * 2, (uint64_t)ntiles * nprob);
+  const uint64_t need = div_up_u64(div_up_u64(n, 32), 8);
+  if (gx > need) gx = need;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, ntiles, nprob);
+  BIC_PROF(c, KID_DICT_HIST);
+  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active);
+  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+bic_status bic_k_dict_step_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t p, const ProbDev* probs, const uint32_t* active,
+                                   uint32_t nprob, uint32_t launched) {
+  const uint64_t wpr = div_up_u64(m, 32), hs = wpr * 32, wprN = div_up_u64(n, 32);
+  ResolveParams P;
+  memset(&P, 0, sizeof(P));
+  P.n = n; P.wprE = wpr; P.wprA = div_up_u64(p, 32); P.wprN = wprN; P.m = m; P.hs = hs; P.p = (uint32_t)p;
+  P.probs = probs; P.active = active;
+  uint64_t win = (32 * 1024 / 4) / (hs + 1);
+  if (win < 1) win = 1;
+  if (win > p) win = p;
+  P.win = (uint32_t)win;
+  const size_t smem = (size_t)(wpr + win * (hs + 1)) * 4;
+  const int gx = (wpr >= 8) ? bic_grid_for(c, (wprN ? wprN : 1) * 32, 256, 8)
+                            : bic_grid_for(c, div_up_u64(wprN ? wprN : 1, 32) * 32, 256, 4);
+  P.parity = launched & 1;
+  if (p * (hs + 1) * 4 > 32 * 1024) {
+    const int sgrid = bic_grid_for(c, p * 32, 256, 4);
+    BIC_PROF(c, KID_DICT_SCAN);
+    k_dict_scan<<<dim3(sgrid, nprob), 256, 0, c->stream>>>(P);
+    BIC_LAUNCH_CHECK(c);
+    BIC_PROF(c, KID_DICT_RESOLVE);
+    k_dict_fix<<<dim3(gx, nprob), 256, (size_t)wpr * 4, c->stream>>>(P);
+    BIC_LAUNCH_CHECK(c);
+  } else {
+    BIC_PROF(c, KID_DICT_RESOLVE);
+    k_dict_resolve_step<<<dim3(gx, nprob), 256, smem, c->stream>>>(P);
+    BIC_LAUNCH_CHECK(c);
+  }
   return BIC_OK;
 }
 

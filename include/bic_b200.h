@@ -146,6 +146,15 @@ bic_status bic_residual(bic_ctx* ctx, const bic_mat* X, const bic_mat* A, const 
 bic_status bic_learn_model_traditional(bic_ctx* ctx, const bic_mat* X, bic_mat* E, bic_mat* D, bic_mat* A,
                                        uint64_t* iterations, uint64_t* trace, uint64_t trace_cap);
 
+/* learn_model_traditional for a batch of independent fits of identical shape (the bitplanes of one grey
+ * image, pages that each get their own dictionary, ...): each problem runs exactly the loop of
+ * src/bsvd.cpp:1215-1244 and stops when one of its iterations changes nothing, but every kernel of an
+ * iteration is launched once for all problems still running. iterations[b] = problem b's return value.
+ * Limits: rows up to 1024 bits and p * ceil32(m) / 8 <= 200 KB (else BIC_ERR_UNSUPPORTED; use the
+ * single-problem call). */
+bic_status bic_learn_model_traditional_batched(bic_ctx* ctx, uint32_t nprob, const bic_mat* const* X, bic_mat* const* E,
+                                               bic_mat* const* D, bic_mat* const* A, uint64_t* iterations);
+
 /* ---------------------------------------------------------------- several GPUs: rows sharded, D replicated
  * One process per GPU. Every rank holds a contiguous block of the patch rows (its X, E, A); D is
  * replicated. Integer statistics are combined with NCCL (loaded at run time: the libnccl.so.2 already in

@@ -192,6 +192,33 @@ def test_dense_coefficients_many_shared_rows(ctx, oracle, synth):
     ctx.set_option("dict_algo", 1)
 
 
+@pytest.mark.parametrize("W,K,rows,cols", [(8, 32, 320, 256), (16, 64, 256, 320), (32, 40, 256, 256), (8, 5, 200, 184)])
+def test_batched_learner_equals_oracle_per_problem(ctx, oracle, synth, W, K, rows, cols):
+    """six independent pages of one shape in one batched call: each must end exactly where the oracle's
+    single-problem loop ends (different pages converge after different numbers of iterations)"""
+    m = W * W
+    Xs, Es, Ds, As, want = [], [], [], [], []
+    for s in range(6):
+        page = synth.structured_page(rows, cols, seed=50 + s, salt=0.002 + 0.01 * s)
+        if s == 5:
+            page = (np.random.default_rng(s).random((rows, cols)) < 0.5).astype(np.uint8)  # noise: stops early
+        Xw = oracle.extract_patches(synth.pack_rows(page), rows, cols, W)
+        Do, Ao, _ = oracle.init_neighbor(Xw, m, K, 34503498)
+        n = Xw.shape[0]
+        Xs.append(ctx.matrix(n, m, Xw)); Es.append(ctx.matrix(n, m)); Ds.append(ctx.matrix(K, m, Do)); As.append(ctx.matrix(n, K))
+        Eo, ito, _ = oracle.learn_traditional(Xw, Do, Ao, m, K)
+        want.append((Do, Ao, Eo, ito))
+    its = ctx.learn_model_traditional_batched(Xs, Es, Ds, As)
+    assert its == [w[3] for w in want]
+    assert len(set(its)) > 1  # the batch really mixes problems that stop at different times
+    for b in range(6):
+        assert np.array_equal(Ds[b].download(), want[b][0]), b
+        assert np.array_equal(As[b].download(), want[b][1]), b
+        assert np.array_equal(Es[b].download(), want[b][2]), b
+    for mm in Xs + Es + Ds + As:
+        mm.destroy()
+
+
 # ---------------------------------------------------------------- coders
 CODER_SHAPES = [(1, 1, 0.0), (1, 1, 1.0), (1, 32, 0.0), (3, 64, 0.5), (17, 100, 0.05), (64, 32, 0.5), (5, 333, 0.0),
                 (3, 70, 1.0), (300, 256, 0.005), (1000, 64, 0.02), (2000, 1024, 0.1), (1, 200000, 0.001), (4096, 32, 0.3)]
