@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--atoms", type=int, default=32)
     ap.add_argument("--cpu-crop", type=int, default=2048, help="crop edge for the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-batch", action="store_true", help="per-plane learner calls instead of the batched learner")
+    ap.add_argument("--batch", action="store_true", help="one batched learner call for all planes instead of per-plane calls on the stream pool")
     ap.add_argument("--sharded", action="store_true", help="also time the row-sharded (NCCL) fit at N=1")
     ap.add_argument("--streams", type=int, default=16, help="contexts (CUDA streams) per GPU")
     return ap.parse_args()
@@ -341,7 +341,7 @@ def main():
 
     # ---- batched mode: per-plane matrices; extract+init and Golomb coding stay per plane on the worker
     # streams, the learner runs ONCE for all planes (bic_learn_model_traditional_batched on the main context)
-    batched = not args.no_batch
+    batched = args.batch
     if batched:
         planes_m = [dict(X=ctx.matrix(n, m), E=ctx.matrix(n, m), D=ctx.matrix(K, m), A=ctx.matrix(n, K),
                          streams=[ctx.stream() for _ in range(3)], out=ctx.pinned(2 * plane_bytes + (1 << 20)))

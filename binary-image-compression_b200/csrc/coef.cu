@@ -54,32 +54,64 @@ __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restric
     }
     __syncthreads();
   }
+  // Rows need different numbers of greedy passes (0 .. weight). A lane that finishes its row takes the
+  // next row of its warp's range at once instead of idling until the slowest lane of the warp is
+  // done: every trip of the loop below is ONE pass (all atoms) for each lane that holds a row, and
+  // lanes at different passes of different rows run the same instructions.
   uint32_t nchanged = 0;
-  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t e[WORDS];
-    uint32_t* erow = E + r * wprE;
+  const int lane = threadIdx.x & 31;
+  const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t chunk = div_up_u64(n, nwarps);
+  uint64_t next = gw * chunk;                       // warp-uniform: next unassigned row of this warp
+  const uint64_t w_end = (next + chunk < n) ? next + chunk : n;
+  bool have = false, row_changed = false;
+  uint64_t r = 0;
+  uint32_t e[WORDS];
 #pragma unroll
-    for (int w = 0; w < WORDS; ++w) e[w] = ((uint64_t)w < wprE) ? erow[w] : 0u;
-    bool row_changed = false;
-    for (;;) {
+  for (int w = 0; w < WORDS; ++w) e[w] = 0;
+  for (;;) {
+    const uint32_t need = __ballot_sync(0xffffffffu, !have);
+    if (need) {
+      const uint64_t cand = next + __popc(need & ((1u << lane) - 1u));
+      if (!have && cand < w_end) {
+        r = cand;
+        const uint32_t* erow = E + r * wprE;
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) e[w] = ((uint64_t)w < wprE) ? erow[w] : 0u;
+        have = true;
+        row_changed = false;
+      }
+      next += __popc(need);
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (have) {
       uint32_t wt = 0;  // w = Ei.weight(), src/bsvd.cpp:1065
 #pragma unroll
       for (int w = 0; w < WORDS; ++w) wt += __popc(e[w]);
-      if (wt == 0) break;  // no distance can be < 0
-      const uint32_t key = best_atom_key<WORDS>(e, Ds, p);  // :1067-1082
-      const uint32_t bestd = key >> 16, bestk = key & 0xFFFFu;
-      if (bestd >= wt) break;  // :1084, strict <
-      A[r * wprA + (bestk >> 5)] ^= 0x80000000u >> (bestk & 31);  // Ai.flip(0,bestk), :1086
-      const uint32_t* dk = Ds + bestk * WORDS;
+      bool again = false;
+      if (wt) {         // with weight 0 no distance can be smaller
+        const uint32_t key = best_atom_key<WORDS>(e, Ds, p);  // :1067-1082
+        const uint32_t bestd = key >> 16, bestk = key & 0xFFFFu;
+        if (bestd < wt) {  // :1084, strict <
+          A[r * wprA + (bestk >> 5)] ^= 0x80000000u >> (bestk & 31);  // Ai.flip(0,bestk), :1086
+          const uint32_t* dk = Ds + bestk * WORDS;
 #pragma unroll
-      for (int w = 0; w < WORDS; ++w) e[w] ^= dk[w];  // :1087
-      row_changed = true;
-    }
-    if (row_changed) {  // :1095-1099
-      nchanged++;
+          for (int w = 0; w < WORDS; ++w) e[w] ^= dk[w];  // :1087
+          row_changed = true;
+          again = true;
+        }
+      }
+      if (!again) {      // the row is finished (:1090-1099)
+        if (row_changed) {
+          nchanged++;
+          uint32_t* erow = E + r * wprE;
 #pragma unroll
-      for (int w = 0; w < WORDS; ++w)
-        if ((uint64_t)w < wprE) erow[w] = e[w];
+          for (int w = 0; w < WORDS; ++w)
+            if ((uint64_t)w < wprE) erow[w] = e[w];
+        }
+        have = false;
+      }
     }
   }
   nchanged = warp_sum_u32(nchanged);

@@ -53,16 +53,40 @@ __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restri
   const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const uint64_t nblocks = div_up_u64(n, 32);
-  for (uint64_t blk = gw; blk < nblocks; blk += nwarps) {
+  // software pipeline: the next block's words are requested before the current block is processed
+  uint64_t blk = gw;
+  uint32_t a_n = 0, e_n[JW];
+#pragma unroll
+  for (int w = 0; w < JW; ++w) e_n[w] = 0;
+  if (blk < nblocks) {
     const uint64_t row = blk * 32 + lane;
-    const uint32_t a = (row < n) ? __ldg(A + row * wprA + kw) : 0u;
+    if (row < n) {
+      a_n = __ldg(A + row * wprA + kw);
+#pragma unroll
+      for (int w = 0; w < JW; ++w) e_n[w] = (jw0 + w < wprE) ? __ldg(E + row * wprE + jw0 + w) : 0u;
+    }
+  }
+  while (blk < nblocks) {
+    const uint32_t a = a_n;
+    uint32_t e[JW];
+#pragma unroll
+    for (int w = 0; w < JW; ++w) e[w] = e_n[w];
+    blk += nwarps;
+    a_n = 0;
+#pragma unroll
+    for (int w = 0; w < JW; ++w) e_n[w] = 0;
+    if (blk < nblocks) {
+      const uint64_t row = blk * 32 + lane;
+      if (row < n) {
+        a_n = __ldg(A + row * wprA + kw);
+#pragma unroll
+        for (int w = 0; w < JW; ++w) e_n[w] = (jw0 + w < wprE) ? __ldg(E + row * wprE + jw0 + w) : 0u;
+      }
+    }
     if (!__any_sync(0xffffffffu, a != 0)) continue;  // none of these 32 rows uses these 32 atoms
     uint32_t et[JW];
 #pragma unroll
-    for (int w = 0; w < JW; ++w) {
-      const uint32_t e = (row < n && jw0 + w < wprE) ? __ldg(E + row * wprE + jw0 + w) : 0u;
-      et[w] = warp_transpose32(e);
-    }
+    for (int w = 0; w < JW; ++w) et[w] = warp_transpose32(e[w]);
     const uint32_t at = warp_transpose32(a);
     ucnt += __popc(at);
 #pragma unroll
@@ -519,7 +543,7 @@ bic_status bic_k_update_dictionary_v2(bic_ctx* c, bic_mat* E, bic_mat* D, const 
   BIC_TRY(bic_k_dict_prepare(c, E, D, A, &w));
   // Queue launches ahead; each returns at once when the cursor is already at p. The cursor is read
   // back and more launches follow only if atoms are still pending.
-  uint32_t batch = 8, cursor = 0;
+  uint32_t batch = 4, cursor = 0;
   for (;;) {
     for (uint32_t i = 0; i < batch && w.launched < w.p; ++i) BIC_TRY(bic_k_dict_step(c, E, D, A, &w, w.H, d_changed));
     BIC_TRY(bic_k_dict_cursor(c, &w, &cursor));
