@@ -191,8 +191,10 @@ def workload_name(args):
 # ---------------------------------------------------------------------------------------------
 # algorithmic bytes per launch, for the roofline of whichever kernel dominates
 # ---------------------------------------------------------------------------------------------
-def algorithmic_bytes(kernel: str, rows, cols, n, m, p):
+def algorithmic_bytes(kernel: str, rows, cols, n, m, p, users_per_atom=0.0):
     t = {
+        # one resolve launch = one changed atom: read A row + E row of each of its users, write the E row back
+        "k_dict_resolve": users_per_atom * ((m + p) / 8 + m / 8),
         "k_update_dictionary": n * (2 * m + p) / 8,        # read E, A once + write E once
         "k_update_coefficients": n * 2 * (m + p) / 8,      # read + write E row and A row
         "k_transpose_bits": 2 * n * p / 8,
@@ -265,7 +267,7 @@ def main():
 
     T = max(1, min(args.streams, P * max(1, args.steps)))  # tasks of all steps share one queue
     workers = [Worker() for _ in range(T)]
-    stats = {"iters": [0] * P, "bits": [0] * P, "d2h": [0] * P}
+    stats = {"iters": [0] * P, "bits": [0] * P, "d2h": [0] * P, "wA": [0] * P}
 
     def fit_resident(w, b, record=False):
         c = w.ctx
@@ -281,6 +283,7 @@ def main():
                 bits += s.info.bitcount
         if record:
             stats["iters"][b], stats["bits"][b] = int(it.value), bits
+            stats["wA"][b] = int(w.streams[1].info.nsamples) - 1   # ones of A = samples - 1
 
     def fit_e2e(w, b, record=False):
         _, info = w.ctx.encode_raster(host_planes[b], rows, cols, W, K, seed=SEED, out=w.out)
@@ -488,7 +491,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    ab = algorithmic_bytes(dom_name, rows, cols, n, m, K)
+    ab = algorithmic_bytes(dom_name, rows, cols, n, m, K, users_per_atom=float(np.mean(stats["wA"])) / K)
     avg_ms = dom_ms / dom_n
     achieved = (ab / (avg_ms / 1e3)) / 1e9 if ab else None
     traffic = None
