@@ -170,44 +170,83 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_tile_counts(const uint32_t
   if (threadIdx.x == 0) { g.ones[blockIdx.x] = (uint32_t)tot; g.last[blockIdx.x] = tlast; }
 }
 
-// single CTA: exclusive scans over the tiles
-__global__ void __launch_bounds__(TILE_THREADS) k_gol_scan_tiles_a(GolTile g, uint64_t ntiles) {
-  __shared__ unsigned long long s_a[8];
-  __shared__ long long s_b[8];
-  unsigned long long carry = 0;
-  long long carry_last = -1;
-  for (uint64_t base = 0; base < ntiles; base += TILE_THREADS) {
-    const uint64_t i = base + threadIdx.x;
-    const unsigned long long c = (i < ntiles) ? g.ones[i] : 0ull;
-    const long long l = (i < ntiles) ? g.last[i] : -1;
-    unsigned long long tot;
-    long long tlast;
-    const unsigned long long ex = block_excl_scan_u64(c, &tot, s_a);
-    const long long exl = block_excl_scan_max(l, &tlast, s_b);
-    if (i < ntiles) {
-      g.ones_before[i] = carry + ex;
-      g.last_before[i] = carry_last > exl ? carry_last : exl;
+// single CTA of 1024 threads: exclusive scans over the tiles. Each thread owns a contiguous run of tiles
+// (serial over its run, one block-wide scan over the 1024 run totals), so 65536 tiles (2^31 input bits)
+// cost one pass instead of 256 dependent block scans.
+#define SCAN_THREADS 1024
+__device__ __forceinline__ void scan1024_sum_max(unsigned long long& sum, long long& mx, unsigned long long* s_sum, long long* s_max,
+                                                 unsigned long long* tot_sum, long long* tot_max) {
+  // exclusive prefix over threads of (sum, max); totals returned to everyone
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned long long inc = sum;
+  long long incm = mx;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+    const long long ym = __shfl_up_sync(0xffffffffu, incm, o);
+    if (lane >= o) { inc += y; incm = incm > ym ? incm : ym; }
+  }
+  if (lane == 31) { s_sum[wib] = inc; s_max[wib] = incm; }
+  __syncthreads();
+  if (wib == 0) {
+    unsigned long long v = s_sum[lane];
+    long long vm = s_max[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, v, o);
+      const long long ym = __shfl_up_sync(0xffffffffu, vm, o);
+      if (lane >= o) { v += y; vm = vm > ym ? vm : ym; }
     }
-    carry += tot;
-    carry_last = carry_last > tlast ? carry_last : tlast;
-    __syncthreads();
+    s_sum[lane] = v;   // inclusive over warps
+    s_max[lane] = vm;
+  }
+  __syncthreads();
+  const unsigned long long wbase = wib ? s_sum[wib - 1] : 0ull;
+  const long long wbasem = wib ? s_max[wib - 1] : -1;
+  unsigned long long ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  long long exm = __shfl_up_sync(0xffffffffu, incm, 1);
+  if (lane == 0) { ex = 0; exm = -1; }
+  *tot_sum = s_sum[31];
+  *tot_max = s_max[31];
+  sum = wbase + ex;
+  mx = wbasem > exm ? wbasem : exm;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_gol_scan_tiles_a(GolTile g, uint64_t ntiles) {
+  __shared__ unsigned long long s_sum[32];
+  __shared__ long long s_max[32];
+  const uint64_t per = div_up_u64(ntiles, SCAN_THREADS);
+  const uint64_t t0 = threadIdx.x * per, t1 = (t0 + per < ntiles) ? t0 + per : ntiles;
+  unsigned long long sum = 0;
+  long long mx = -1;
+  for (uint64_t i = t0; i < t1; ++i) { sum += g.ones[i]; const long long l = g.last[i]; mx = mx > l ? mx : l; }
+  unsigned long long tot;
+  long long totm;
+  scan1024_sum_max(sum, mx, s_sum, s_max, &tot, &totm);  // now exclusive prefixes of this thread's run
+  for (uint64_t i = t0; i < t1; ++i) {
+    g.ones_before[i] = sum;
+    g.last_before[i] = mx;
+    sum += g.ones[i];
+    const long long l = g.last[i];
+    mx = mx > l ? mx : l;
   }
 }
 
 // scalars: [0] bitcount, [1] nsamples, [2] offset of the closing sample, [3] last one + 1
-__global__ void __launch_bounds__(TILE_THREADS) k_gol_scan_tiles_b(GolTile g, uint64_t ntiles, uint64_t N,
+__global__ void __launch_bounds__(SCAN_THREADS) k_gol_scan_tiles_b(GolTile g, uint64_t ntiles, uint64_t N,
                                                                    unsigned long long* scalars) {
-  __shared__ unsigned long long s_a[8];
-  unsigned long long carry = 0;
-  for (uint64_t base = 0; base < ntiles; base += TILE_THREADS) {
-    const uint64_t i = base + threadIdx.x;
-    const unsigned long long c = (i < ntiles) ? g.bits[i] : 0ull;
-    unsigned long long tot;
-    const unsigned long long ex = block_excl_scan_u64(c, &tot, s_a);
-    if (i < ntiles) g.bits_before[i] = carry + ex;
-    carry += tot;
-    __syncthreads();
-  }
+  __shared__ unsigned long long s_sum[32];
+  __shared__ long long s_max[32];
+  const uint64_t per = div_up_u64(ntiles, SCAN_THREADS);
+  const uint64_t t0 = threadIdx.x * per, t1 = (t0 + per < ntiles) ? t0 + per : ntiles;
+  unsigned long long sum = 0;
+  long long dummy = -1;
+  for (uint64_t i = t0; i < t1; ++i) sum += g.bits[i];
+  unsigned long long carry;
+  long long totm;
+  scan1024_sum_max(sum, dummy, s_sum, s_max, &carry, &totm);
+  for (uint64_t i = t0; i < t1; ++i) { g.bits_before[i] = sum; sum += g.bits[i]; }
   if (threadIdx.x == 0) {
     unsigned long long ones = 0;
     long long last = -1;
@@ -572,14 +611,14 @@ static bic_status golomb_prepare(bic_ctx* c, const bic_mat* M, const uint32_t** 
     k_gol_tile_counts<<<(unsigned)ntiles, TILE_THREADS, 0, c->stream>>>(S, T, *g);
     BIC_LAUNCH_CHECK(c);
     BIC_PROF(c, KID_GOL_SCAN_A);
-    k_gol_scan_tiles_a<<<1, TILE_THREADS, 0, c->stream>>>(*g, ntiles);
+    k_gol_scan_tiles_a<<<1, SCAN_THREADS, 0, c->stream>>>(*g, ntiles);
     BIC_LAUNCH_CHECK(c);
     BIC_PROF(c, KID_GOL_LENGTHS);
     k_gol_walk<0><<<(unsigned)ntiles, TILE_THREADS, 0, c->stream>>>(S, T, N, *g, nullptr, nullptr, 1, nullptr);
     BIC_LAUNCH_CHECK(c);
   }
   BIC_PROF(c, KID_GOL_SCAN_B);
-  k_gol_scan_tiles_b<<<1, TILE_THREADS, 0, c->stream>>>(*g, ntiles, N, (unsigned long long*)c->d_scalars);
+  k_gol_scan_tiles_b<<<1, SCAN_THREADS, 0, c->stream>>>(*g, ntiles, N, (unsigned long long*)c->d_scalars);
   BIC_LAUNCH_CHECK(c);
   BIC_TRY(bic_read_scalars(c, 4));
   *S_out = S; *T_out = T; *ntiles_out = ntiles;
