@@ -100,7 +100,7 @@ extern "C" bic_status bic_learn_model_traditional_batched(bic_ctx* c, uint32_t n
       // cursors of all problems: one strided copy per problem would be nprob copies; they are 16 B apart
       // inside each problem's scratch, so gather them with a 2-D copy
       BIC_CUDA(c, cudaMemcpy2DAsync(cur.data(), 16, d_pool + o_cur, per * 4, 16, nprob, cudaMemcpyDeviceToHost, c->stream));
-      BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+      BIC_CUDA(c, bic_wait_stream(c));
       bool done = true;
       for (uint32_t b = 0; b < nprob && done; ++b)
         if (active[b] && cur[b * 4 + (launched & 1)] < p) done = false;
@@ -110,7 +110,7 @@ extern "C" bic_status bic_learn_model_traditional_batched(bic_ctx* c, uint32_t n
     k_batch_commit<<<dim3(8, nprob), 256, 0, c->stream>>>(d_probs, d_active, p * wpr);
     BIC_LAUNCH_CHECK(c);
     BIC_CUDA(c, cudaMemcpy2DAsync(cnt.data(), 16, d_pool + o_cnt, per * 4, 16, nprob, cudaMemcpyDeviceToHost, c->stream));
-    BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    BIC_CUDA(c, bic_wait_stream(c));
     for (uint32_t b = 0; b < nprob; ++b) {
       if (!active[b]) continue;
       if (iterations) iterations[b]++;

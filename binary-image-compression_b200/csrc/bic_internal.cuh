@@ -66,6 +66,8 @@ struct bic_ctx {
   bic_scratch staging;    // host-layout staging for uploads/downloads
   bic_scratch work[6];    // per-algorithm work buffers
   // optional per-launch device timers
+  int wait_mode = 0;       // how host threads wait for the stream: 0 cudaStreamSynchronize, 1 poll + sched_yield, 2 blocking event
+  cudaEvent_t wait_ev = nullptr, wait_ev_blocking = nullptr;
   int dict_algo = 1;  // 0: per-atom walk (dict.cu), 1: histogram first, resolve in order (dict2.cu)
   bool prof_on = false;
   std::vector<bic_prof_rec> prof_recs;
@@ -105,6 +107,8 @@ static inline bic_status bic_fail(bic_ctx* ctx, bic_status s, const char* msg) {
   return s;
 }
 
+// wait until everything queued on the context's stream is done (honours wait_mode)
+cudaError_t bic_wait_stream(bic_ctx* ctx);
 // grow-only scratch; contents are undefined after growth
 bic_status bic_scratch_reserve(bic_ctx* ctx, bic_scratch* s, size_t bytes);
 // D2H of the first n scalar slots after the stream drained

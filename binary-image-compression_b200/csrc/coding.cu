@@ -532,7 +532,7 @@ extern "C" bic_status bic_stream_create(bic_ctx* c, bic_stream** out) {
 extern "C" bic_status bic_stream_destroy(bic_ctx* c, bic_stream* s) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !s) return BIC_ERR_INVALID;
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   if (s->d_bytes) cudaFree(s->d_bytes);
   if (s->d_index) cudaFree(s->d_index);
   delete s;
@@ -553,7 +553,7 @@ static bic_status stream_reserve(bic_ctx* c, bic_stream* s, uint64_t bitcount, u
   const size_t typical = (size_t)(src_bits / 8 + src_bits / 32) + 4096;
   if (need > s->cap_bytes && typical > need) need = typical;
   if (need > s->cap_bytes) {
-    BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    BIC_CUDA(c, bic_wait_stream(c));
     if (s->d_bytes) cudaFree(s->d_bytes);
     s->d_bytes = nullptr; s->cap_bytes = 0;
     const size_t want = (need + (need >> 3) + 255) & ~(size_t)255;
@@ -564,7 +564,7 @@ static bic_status stream_reserve(bic_ctx* c, bic_stream* s, uint64_t bitcount, u
   const size_t typicali = (size_t)(src_bits / 256 + 64) * 2;  // one chunk per 256 samples, <= 1 sample per bit... /2 on average
   if (needi > s->cap_index && typicali > needi) needi = typicali;
   if (needi > s->cap_index) {
-    BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    BIC_CUDA(c, bic_wait_stream(c));
     if (s->d_index) cudaFree(s->d_index);
     s->d_index = nullptr; s->cap_index = 0;
     if (cudaMalloc(&s->d_index, needi * 8) != cudaSuccess) { cudaGetLastError(); c->err = "index allocation failed"; return BIC_ERR_NOMEM; }
@@ -774,7 +774,7 @@ extern "C" bic_status bic_stream_download(bic_ctx* c, const bic_stream* s, uint8
     if (s->info.nchunks)
       BIC_CUDA(c, cudaMemcpyAsync(index, s->d_index, s->info.nchunks * 16, cudaMemcpyDeviceToHost, c->stream));
   }
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   return BIC_OK;
 }
 

@@ -25,6 +25,8 @@ static bic_status ctx_init(bic_ctx* c, int device, void* stream, bool own) {
   c->owns_stream = own;
   BIC_CUDA(c, cudaEventCreate(&c->ev0));
   BIC_CUDA(c, cudaEventCreate(&c->ev1));
+  BIC_CUDA(c, cudaEventCreateWithFlags(&c->wait_ev, cudaEventDisableTiming));
+  BIC_CUDA(c, cudaEventCreateWithFlags(&c->wait_ev_blocking, cudaEventDisableTiming | cudaEventBlockingSync));
   BIC_CUDA(c, cudaMallocHost(&c->h_scalars, 64 * sizeof(uint64_t)));
   BIC_CUDA(c, cudaMalloc(&c->d_scalars, 64 * sizeof(uint64_t)));
   BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, 64 * sizeof(uint64_t), c->stream));
@@ -74,6 +76,8 @@ extern "C" bic_status bic_ctx_destroy(bic_ctx* c) {
   if (c->d_scalars) cudaFree(c->d_scalars);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->wait_ev) cudaEventDestroy(c->wait_ev);
+  if (c->wait_ev_blocking) cudaEventDestroy(c->wait_ev_blocking);
   if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return BIC_OK;
@@ -82,7 +86,7 @@ extern "C" bic_status bic_ctx_destroy(bic_ctx* c) {
 extern "C" bic_status bic_ctx_sync(bic_ctx* c) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c) return BIC_ERR_INVALID;
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   return BIC_OK;
 }
 
@@ -129,10 +133,31 @@ extern "C" bic_status bic_host_free(void* p) {
   return cudaFreeHost(p) == cudaSuccess ? BIC_OK : BIC_ERR_CUDA;
 }
 
+#include <sched.h>
+// Many contexts per process (one per page in flight) and several processes per box (one per GPU) mean
+// many host threads waiting at once; spinning inside cudaStreamSynchronize then oversubscribes the cores.
+cudaError_t bic_wait_stream(bic_ctx* c) {
+  if (c->wait_mode == 1) {
+    cudaError_t e = cudaEventRecord(c->wait_ev, c->stream);
+    if (e != cudaSuccess) return e;
+    for (;;) {
+      e = cudaEventQuery(c->wait_ev);
+      if (e != cudaErrorNotReady) return e;
+      sched_yield();
+    }
+  }
+  if (c->wait_mode == 2) {
+    cudaError_t e = cudaEventRecord(c->wait_ev_blocking, c->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(c->wait_ev_blocking);
+  }
+  return cudaStreamSynchronize(c->stream);
+}
+
 bic_status bic_scratch_reserve(bic_ctx* c, bic_scratch* s, size_t bytes) {
   if (bytes <= s->bytes) return BIC_OK;
   // the old block may still be in use by queued kernels
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   if (s->p) { cudaFree(s->p); s->p = nullptr; s->bytes = 0; }
   size_t want = (bytes + (bytes >> 2) + 255) & ~(size_t)255;
   cudaError_t e = cudaMalloc(&s->p, want);
@@ -148,7 +173,7 @@ bic_status bic_scratch_reserve(bic_ctx* c, bic_scratch* s, size_t bytes) {
 
 bic_status bic_read_scalars(bic_ctx* c, int n) {
   BIC_CUDA(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   return BIC_OK;
 }
 bic_status bic_zero_scalars(bic_ctx* c) {
@@ -186,7 +211,7 @@ extern "C" bic_status bic_mat_create(bic_ctx* c, uint64_t rows, uint64_t cols, b
 extern "C" bic_status bic_mat_destroy(bic_ctx* c, bic_mat* m) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !m) return BIC_ERR_INVALID;
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   if (m->owns && m->d) cudaFree(m->d);
   delete m;
   return BIC_OK;
@@ -278,7 +303,7 @@ extern "C" bic_status bic_mat_download_words64(bic_ctx* c, const bic_mat* m, uin
                                                                          m->wpr, wpr64);
   BIC_LAUNCH_CHECK(c);
   BIC_CUDA(c, cudaMemcpyAsync(host, c->staging.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   return BIC_OK;
 }
 
@@ -308,7 +333,7 @@ extern "C" bic_status bic_mat_download_pbm(bic_ctx* c, const bic_mat* m, uint8_t
   k_dev_to_pbm<<<copy_grid(c, bytes), 256, 0, c->stream>>>(m->d, (uint8_t*)c->staging.p, m->rows, m->wpr, bpr);
   BIC_LAUNCH_CHECK(c);
   BIC_CUDA(c, cudaMemcpyAsync(payload, c->staging.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   return BIC_OK;
 }
 
@@ -494,6 +519,7 @@ extern "C" bic_status bic_prof_get(bic_ctx* c, int kid, const char** name, uint6
 extern "C" bic_status bic_ctx_set_option(bic_ctx* c, const char* name, int64_t value) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !name) return BIC_ERR_INVALID;
+  if (!strcmp(name, "wait_mode")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->wait_mode = (int)value; return BIC_OK; }
   if (!strcmp(name, "dict_algo")) { if (value < 0 || value > 1) return BIC_ERR_INVALID; c->dict_algo = (int)value; return BIC_OK; }
   return bic_fail(c, BIC_ERR_INVALID, "unknown option");
 }

@@ -527,7 +527,7 @@ bic_status bic_k_dict_step_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t 
 bic_status bic_k_dict_cursor(bic_ctx* c, DictWork* w, uint32_t* cursor_out) {
   uint32_t* h_cursor = (uint32_t*)(c->h_scalars + 32);
   BIC_CUDA(c, cudaMemcpyAsync(h_cursor, w->cursor + (w->launched & 1), 4, cudaMemcpyDeviceToHost, c->stream));
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   *cursor_out = *h_cursor;
   return BIC_OK;
 }

@@ -122,7 +122,7 @@ static bic_status share_rows(bic_ctx* c, bic_comm* m, uint64_t n_local) {
     m->collectives++;
   }
   BIC_CUDA(c, cudaMemcpyAsync(m->nrows.data(), d, 8 * m->nranks, cudaMemcpyDeviceToHost, c->stream));
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   m->row0 = 0;
   m->nglobal = 0;
   for (int r = 0; r < m->nranks; ++r) { if (r < m->rank) m->row0 += m->nrows[r]; m->nglobal += m->nrows[r]; }
@@ -167,7 +167,7 @@ extern "C" bic_status bic_dist_initialize_model_neighbor(bic_ctx* c, bic_comm* m
   }
   std::vector<uint32_t> bm((size_t)bw * m->nranks);
   BIC_CUDA(c, cudaMemcpyAsync(bm.data(), d_bm, bm.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   bool any = false;
   for (size_t i = 0; i < bm.size() && !any; ++i) any = bm[i] != 0;
   if (!any) return bic_fail(c, BIC_ERR_INVALID, "init: X is all zero (the reference's draw loop never ends)");

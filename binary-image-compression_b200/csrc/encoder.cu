@@ -161,7 +161,7 @@ extern "C" bic_status bic_decode_raster(bic_ctx* c, const uint8_t* cont, uint64_
     std::vector<uint64_t> idx(si.nchunks * 2 + 1);
     memcpy(idx.data(), cont + off + nbp, si.nchunks * 16);
     BIC_TRY(bic_stream_upload(c, w->st[i], &si, cont + off, idx.data()));
-    BIC_CUDA(c, cudaStreamSynchronize(c->stream));  // idx is a local
+    BIC_CUDA(c, bic_wait_stream(c));  // idx is a local
     if (si.coder == BIC_CODER_GOLOMB) BIC_TRY(bic_golomb_decode(c, w->st[i], mats[i]));
     else if (si.coder == BIC_CODER_EG) BIC_TRY(bic_eg_decode(c, w->st[i], mats[i]));
     else return bic_fail(c, BIC_ERR_CORRUPT, "container: unknown coder");

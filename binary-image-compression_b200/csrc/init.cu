@@ -48,7 +48,7 @@ extern "C" bic_status bic_draw_pivots(bic_ctx* c, const bic_mat* X, uint64_t p, 
   BIC_TRY(bic_k_row_nonzero_bitmap(c, X, (uint32_t*)c->work[0].p));
   std::vector<uint32_t> bm(nw);
   BIC_CUDA(c, cudaMemcpyAsync(bm.data(), c->work[0].p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
-  BIC_CUDA(c, cudaStreamSynchronize(c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   bool any = false;
   for (uint64_t i = 0; i < nw && !any; ++i) any = bm[i] != 0;
   if (!any) return bic_fail(c, BIC_ERR_INVALID, "draw_pivots: X is all zero (the reference's draw loop never ends)");

@@ -62,7 +62,9 @@ int bic_ctx_sm_count(bic_ctx* ctx);
  * that run several contexts -- one per independent page -- concurrently) */
 bic_status bic_ctx_wait_ctx(bic_ctx* waiter, bic_ctx* signal);
 /* tuning switches. "dict_algo": 1 (default) = all atom histograms in one pass, then an in-order
- * resolve with a grid barrier only for atoms that change; 0 = one barrier per atom. Same results. */
+ * resolve with a grid barrier only for atoms that change; 0 = one barrier per atom. Same results.
+ * "wait_mode": how the calling thread waits for results: 0 (default) cudaStreamSynchronize, 1 poll + sched_yield
+ * (many contexts / several ranks per box), 2 blocking event. */
 bic_status bic_ctx_set_option(bic_ctx* ctx, const char* name, int64_t value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t bic_ctx_launch_count(bic_ctx* ctx);
