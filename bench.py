@@ -516,7 +516,7 @@ def main():
 
     # ---- row-sharded fit (N > 1): the N bands are ONE image, one dictionary per plane over all ranks'
     # patches, statistics combined by NCCL inside the library (csrc/dist.cu). One stream, planes in
-    # sequence; D/A/E shards are Golomb coded per rank (seam-exact global streams: not yet).
+    # sequence; A and E shards are Golomb coded as exact substrings of the single global streams.
     sharded = None
     if world > 1 or args.sharded:
         uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
@@ -534,8 +534,11 @@ def main():
             it = C.c_uint64(0)
             c._ck(L.bic_dist_learn_model_traditional(c.h, comm, w0.X.h, w0.E.h, w0.D.h, w0.A.h, C.byref(it), None, 0))
             sh_iters[b] = int(it.value)
-            for M, s in zip((w0.D, w0.A, w0.E), w0.streams):
-                c._ck(L.bic_golomb_encode(c.h, M.h, 256, s.h))
+            # D is replicated (every rank codes the same stream); A and E are row-sharded: each rank writes its
+            # rows' codewords as the exact substring of the single global stream (bic_dist_golomb_encode)
+            c._ck(L.bic_golomb_encode(c.h, w0.D.h, 256, w0.streams[0].h))
+            for M, s in zip((w0.A, w0.E), w0.streams[1:]):
+                c._ck(L.bic_dist_golomb_encode(c.h, comm, M.h, 256, s.h, None))
 
         for b in range(P):
             fit_sharded(b)
@@ -551,7 +554,7 @@ def main():
                    "collectives_per_step": (w0.ctx.comm_collectives(comm) - coll0) / args.steps,
                    "iterations_per_plane": sh_iters,
                    "what": f"each plane is ONE {world * S}x{S} image whose patch rows are sharded over {world} rank(s); one "
-                           "dictionary per plane; NCCL allreduce of atom statistics (1 per iteration + 1 per changed atom); "
+                           "dictionary per plane; NCCL allreduce of atom statistics (1 per iteration + 1 per changed atom), seam-exact sharded Golomb coding; "
                            "one stream, planes in sequence"}
         w0.ctx.comm_destroy(comm)
 

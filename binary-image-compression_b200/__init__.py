@@ -44,6 +44,11 @@ class StreamInfo(C.Structure):
                 ("bitcount", _u64), ("nsamples", _u64), ("nchunks", _u64)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [(n, _u64) for n in ("global_bitcount", "global_nsamples", "code_bit_offset", "local_code_bits",
+                                    "first_chunk", "local_chunks")]
+
+
 class EncodeInfo(C.Structure):
     _fields_ = [(n, _u64) for n in ("rows", "cols", "W", "K", "n", "m", "iterations", "weight_E", "weight_A",
                                     "weight_D", "bits_D", "bits_A", "bits_E", "container_bytes")]
@@ -112,6 +117,7 @@ def lib() -> C.CDLL:
         "bic_dist_update_dictionary_steepest": [_vp, _vp, _vp, _vp, _vp, _u64p],
         "bic_dist_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
         "bic_learn_model_traditional_batched": [_vp, C.c_uint32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _u64p],
+        "bic_dist_golomb_encode": [_vp, _vp, _vp, C.c_uint32, _vp, C.POINTER(ShardInfo)],
         "bic_stream_create": [_vp, C.POINTER(_vp)],
         "bic_stream_destroy": [_vp, _vp],
         "bic_stream_get_info": [_vp, C.POINTER(StreamInfo)],
@@ -456,6 +462,13 @@ class Context:
                                                          tr.ctypes.data_as(_u64p), trace_cap))
         n = int(it.value)
         return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
+
+    def dist_golomb_encode(self, comm, M: Matrix, out: "Stream | None" = None, chunk_samples: int = 256):
+        """this rank's rows coded as a substring of the one global stream; returns (Stream, ShardInfo)"""
+        out = out or Stream(self)
+        si = ShardInfo()
+        self._ck(self.L.bic_dist_golomb_encode(self.h, comm, M.h, chunk_samples, out.h, C.byref(si)))
+        return out, si
 
     # ---- coding
     def golomb_encode(self, M: Matrix, out: Stream | None = None, chunk_samples: int = 256) -> Stream:

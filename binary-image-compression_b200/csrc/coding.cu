@@ -279,10 +279,23 @@ __device__ __forceinline__ void put_one(uint32_t* __restrict__ out, unsigned lon
 }
 
 // MODE 0: code lengths per tile; MODE 1: scatter codewords (+ chunk index)
+// Where a (shard of a) matrix sits in the global sample stream. Single GPU: all zero / -1. Row-sharded
+// coding (bic_dist_golomb_encode): the shard's codewords are an exact substring of the one global stream.
+struct GolBase {
+  unsigned long long t0;      // ones before this shard (global rank of its first sample)
+  long long pos0;             // global stream position of the shard's first bit
+  long long prev0;            // global position of the last one before the shard, -1 if none
+  unsigned long long out0;    // bit offset of the shard's first codeword inside its own output buffer (code0 & 31)
+  unsigned long long code0;   // global code-bit offset of the shard's first codeword
+  unsigned long long chunk0;  // first chunk-index entry this shard stores
+  int closing;                // this shard writes the run closed by the virtual one
+  unsigned long long close_t, close_consumed, close_off;  // its sample rank, bits consumed before it, local bit offset
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __restrict__ S, uint64_t T, uint64_t N, GolTile g,
                                                            uint32_t* __restrict__ out, unsigned long long* __restrict__ index,
-                                                           uint32_t chunk, const unsigned long long* __restrict__ scalars) {
+                                                           uint32_t chunk, GolBase gb) {
   __shared__ unsigned long long s_a[8];
   __shared__ long long s_b[8];
   const uint64_t w0 = (uint64_t)blockIdx.x * TILE_WORDS + threadIdx.x * TILE_WORDS_PER_THREAD;
@@ -295,10 +308,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
     c += __popc(v[i]);
     if (v[i]) last = (long long)((w0 + i) * 32 + (32 - __ffs(v[i])));
   }
-  const unsigned long long rank0 = g.ones_before[blockIdx.x] + block_excl_scan_u64(c, nullptr, s_a);
+  const unsigned long long rank0 = gb.t0 + g.ones_before[blockIdx.x] + block_excl_scan_u64(c, nullptr, s_a);
   const long long pl = block_excl_scan_max(last, nullptr, s_b);
   const long long lb = g.last_before[blockIdx.x];
-  long long prev = pl > lb ? pl : lb;  // position of the previous one, -1 if none
+  const long long pv_local = pl > lb ? pl : lb;                       // previous one inside this shard, -1 if none
+  long long prev = pv_local >= 0 ? pv_local + gb.pos0 : gb.prev0;     // GLOBAL position of the previous one, -1 if none
 
   // pass 1: my code bits
   unsigned long long mybits = 0;
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
       while (b) {
         const int p = __clz(b);
         b &= ~(0x80000000u >> p);
-        const long long pos = (long long)((w0 + i) * 32 + p);
+        const long long pos = (long long)((w0 + i) * 32 + p) + gb.pos0;
         const unsigned long long x = (unsigned long long)(pos - pv - 1);
         const uint32_t k = golomb_k(t, (unsigned long long)(pv + 1));
         mybits += k + (x >> k) + 1;
@@ -331,7 +345,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
   // and flushed with coalesced stores; only its first and last word are shared with the neighbouring
   // tiles and need a global atomic. Otherwise (very long unary runs) codewords go straight to global.
   __shared__ uint32_t s_out[GOL_SMEM_WORDS];
-  const unsigned long long o0 = g.bits_before[blockIdx.x];
+  const unsigned long long o0 = g.bits_before[blockIdx.x] + gb.out0;
   const unsigned long long base = o0 & ~31ull;                       // bit position of s_out[0]
   const unsigned long long span_words = ((o0 - base) + tot + 31) >> 5;
   const bool staged = span_words <= GOL_SMEM_WORDS;                  // uniform over the CTA
@@ -349,10 +363,14 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
     while (b) {
       const int p = __clz(b);
       b &= ~(0x80000000u >> p);
-      const long long pos = (long long)((w0 + i) * 32 + p);
+      const long long pos = (long long)((w0 + i) * 32 + p) + gb.pos0;
       const unsigned long long x = (unsigned long long)(pos - prev - 1);
       const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
-      if ((t & cmask) == 0) { index[2 * (t >> clog)] = o; index[2 * (t >> clog) + 1] = (unsigned long long)(prev + 1); }
+      if ((t & cmask) == 0) {
+        const unsigned long long slot = (t >> clog) - gb.chunk0;
+        index[2 * slot] = o - gb.out0 + gb.code0;  // global code-bit offset
+        index[2 * slot + 1] = (unsigned long long)(prev + 1);
+      }
       const uint32_t rem = (uint32_t)(x & ((1ull << k) - 1));        // k-bit remainder, MSB first
       const unsigned long long stop = o + k + (x >> k);              // x>>k zeros (the buffer is zeroed), then a one
       if (staged) {
@@ -384,12 +402,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
       else gout[i] = bswap32(w);
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // the run closed by the virtual one
-    const unsigned long long tt = scalars[1] - 1, consumed = scalars[3];
-    unsigned long long oo = scalars[2];
+  if (gb.closing && blockIdx.x == 0 && threadIdx.x == 0) {  // the run closed by the virtual one (N = global bit count)
+    const unsigned long long tt = gb.close_t, consumed = gb.close_consumed;
+    unsigned long long oo = gb.close_off + gb.out0;
     const unsigned long long x = N - consumed;
     const uint32_t k = golomb_k(tt, consumed);
-    if (tt % chunk == 0) { index[2 * (tt / chunk)] = oo; index[2 * (tt / chunk) + 1] = consumed; }
+    if ((tt & cmask) == 0) { index[2 * ((tt >> clog) - gb.chunk0)] = oo - gb.out0 + gb.code0; index[2 * ((tt >> clog) - gb.chunk0) + 1] = consumed; }
     put_bits(out, oo, (uint32_t)(x & ((1ull << k) - 1)), k);
     oo += k + (x >> k);
     put_one(out, oo);
@@ -588,48 +606,79 @@ static bic_status dense_stream(bic_ctx* c, const bic_mat* M, const uint32_t** S,
   return BIC_OK;
 }
 
-static bic_status golomb_prepare(bic_ctx* c, const bic_mat* M, const uint32_t** S_out, uint64_t* T_out, GolTile* g,
-                                 uint64_t* ntiles_out) {
-  const uint64_t N = M->rows * M->cols;
+static GolBase gol_base_single() {
+  GolBase b;
+  memset(&b, 0, sizeof(b));
+  b.prev0 = -1;
+  b.closing = 1;
+  return b;
+}
+
+struct GolWork {
   const uint32_t* S;
-  uint64_t T;
-  BIC_TRY(dense_stream(c, M, &S, &T));
-  const uint64_t ntiles = div_up_u64(T, TILE_WORDS);
-  // work[5]: per-tile arrays
-  const size_t per = (size_t)(ntiles ? ntiles : 1);
-  const size_t bytes = per * (8 * 5 + 8);  // ones kept in a u64 slot for alignment
-  BIC_TRY(bic_scratch_reserve(c, &c->work[5], bytes));
-  uint8_t* base = (uint8_t*)c->work[5].p;
-  g->last = (long long*)base;
-  g->ones_before = (unsigned long long*)(base + per * 8);
-  g->last_before = (long long*)(base + per * 16);
-  g->bits = (unsigned long long*)(base + per * 24);
-  g->bits_before = (unsigned long long*)(base + per * 32);
-  g->ones = (uint32_t*)(base + per * 40);
-  if (ntiles) {
+  uint64_t T, N, ntiles;
+  GolTile g;
+};
+
+// per-tile counts and their scans. Afterwards h_scalars[1] = ones + 1 and h_scalars[3] = position after the
+// matrix's last one (0 if none); [0] and [2] are not meaningful yet.
+static bic_status golomb_counts(bic_ctx* c, const bic_mat* M, GolWork* w) {
+  w->N = M->rows * M->cols;
+  BIC_TRY(dense_stream(c, M, &w->S, &w->T));
+  w->ntiles = div_up_u64(w->T, TILE_WORDS);
+  const size_t per = (size_t)(w->ntiles ? w->ntiles : 1);  // work[5]: per-tile arrays
+  BIC_TRY(bic_scratch_reserve(c, &c->work[5], per * (8 * 5 + 8)));
+  uint8_t* p = (uint8_t*)c->work[5].p;
+  GolTile* g = &w->g;
+  g->last = (long long*)p;
+  g->ones_before = (unsigned long long*)(p + per * 8);
+  g->last_before = (long long*)(p + per * 16);
+  g->bits = (unsigned long long*)(p + per * 24);
+  g->bits_before = (unsigned long long*)(p + per * 32);
+  g->ones = (uint32_t*)(p + per * 40);
+  BIC_CUDA(c, cudaMemsetAsync(g->bits, 0, per * 8, c->stream));
+  if (w->ntiles) {
     BIC_PROF(c, KID_GOL_TILE_COUNTS);
-    k_gol_tile_counts<<<(unsigned)ntiles, TILE_THREADS, 0, c->stream>>>(S, T, *g);
+    k_gol_tile_counts<<<(unsigned)w->ntiles, TILE_THREADS, 0, c->stream>>>(w->S, w->T, *g);
     BIC_LAUNCH_CHECK(c);
     BIC_PROF(c, KID_GOL_SCAN_A);
-    k_gol_scan_tiles_a<<<1, SCAN_THREADS, 0, c->stream>>>(*g, ntiles);
+    k_gol_scan_tiles_a<<<1, SCAN_THREADS, 0, c->stream>>>(*g, w->ntiles);
     BIC_LAUNCH_CHECK(c);
+  }
+  return BIC_OK;
+}
+
+// code length of every tile under `base`, then their scan. Afterwards h_scalars: [0] bit count including the
+// closing sample (only meaningful for the single-stream base), [1] ones + 1, [2] code bits of the matrix's own
+// ones, [3] position after its last one.
+static bic_status golomb_lengths(bic_ctx* c, GolWork* w, const GolBase& base) {
+  if (w->ntiles) {
     BIC_PROF(c, KID_GOL_LENGTHS);
-    k_gol_walk<0><<<(unsigned)ntiles, TILE_THREADS, 0, c->stream>>>(S, T, N, *g, nullptr, nullptr, 1, nullptr);
+    k_gol_walk<0><<<(unsigned)w->ntiles, TILE_THREADS, 0, c->stream>>>(w->S, w->T, w->N, w->g, nullptr, nullptr, 1, base);
     BIC_LAUNCH_CHECK(c);
   }
   BIC_PROF(c, KID_GOL_SCAN_B);
-  k_gol_scan_tiles_b<<<1, SCAN_THREADS, 0, c->stream>>>(*g, ntiles, N, (unsigned long long*)c->d_scalars);
+  k_gol_scan_tiles_b<<<1, SCAN_THREADS, 0, c->stream>>>(w->g, w->ntiles, w->N, (unsigned long long*)c->d_scalars);
   BIC_LAUNCH_CHECK(c);
-  BIC_TRY(bic_read_scalars(c, 4));
-  *S_out = S; *T_out = T; *ntiles_out = ntiles;
+  return bic_read_scalars(c, 4);
+}
+
+static bic_status golomb_scatter(bic_ctx* c, GolWork* w, const GolBase& base, uint64_t N_global, uint32_t chunk, bic_stream* out) {
+  // with no tile (empty matrix) one CTA still has to write the closing sample
+  const unsigned grid = (unsigned)(w->ntiles ? w->ntiles : 1);
+  BIC_PROF(c, KID_GOL_SCATTER);
+  k_gol_walk<1><<<grid, TILE_THREADS, 0, c->stream>>>(w->S, w->ntiles ? w->T : 0, N_global, w->g, (uint32_t*)out->d_bytes,
+                                                     (unsigned long long*)out->d_index, chunk, base);
+  BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }
 
 extern "C" bic_status bic_golomb_bitcount(bic_ctx* c, const bic_mat* M, uint64_t* bitcount, uint64_t* nsamples) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !M) return BIC_ERR_INVALID;
-  const uint32_t* S; uint64_t T, ntiles; GolTile g;
-  BIC_TRY(golomb_prepare(c, M, &S, &T, &g, &ntiles));
+  GolWork w;
+  BIC_TRY(golomb_counts(c, M, &w));
+  BIC_TRY(golomb_lengths(c, &w, gol_base_single()));
   if (bitcount) *bitcount = c->h_scalars[0];
   if (nsamples) *nsamples = c->h_scalars[1];
   return BIC_OK;
@@ -640,20 +689,18 @@ extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t c
   if (!c || !M || !out) return BIC_ERR_INVALID;
   if (chunk_samples == 0) chunk_samples = 256;
   while (chunk_samples & (chunk_samples - 1)) chunk_samples++;  // the kernels index chunks with shifts: round up to a power of two
-  const uint64_t N = M->rows * M->cols;
-  const uint32_t* S; uint64_t T, ntiles; GolTile g;
-  BIC_TRY(golomb_prepare(c, M, &S, &T, &g, &ntiles));
+  GolWork w;
+  BIC_TRY(golomb_counts(c, M, &w));
+  GolBase base = gol_base_single();
+  BIC_TRY(golomb_lengths(c, &w, base));
   const uint64_t bitcount = c->h_scalars[0], nsamples = c->h_scalars[1];
+  base.close_t = nsamples - 1;
+  base.close_off = c->h_scalars[2];
+  base.close_consumed = c->h_scalars[3];
   const uint64_t nchunks = div_up_u64(nsamples, chunk_samples);
-  BIC_TRY(stream_reserve(c, out, bitcount, nchunks, N));
+  BIC_TRY(stream_reserve(c, out, bitcount, nchunks, w.N));
   BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, (size_t)(div_up_u64(bitcount, 32) * 4 + 16), c->stream));
-  // with no tile (empty matrix) one CTA still has to write the closing sample
-  const unsigned grid = (unsigned)(ntiles ? ntiles : 1);
-  BIC_PROF(c, KID_GOL_SCATTER);
-  k_gol_walk<1><<<grid, TILE_THREADS, 0, c->stream>>>(S, ntiles ? T : 0, N, g, (uint32_t*)out->d_bytes,
-                                                     (unsigned long long*)out->d_index, chunk_samples,
-                                                     (const unsigned long long*)c->d_scalars);
-  BIC_LAUNCH_CHECK(c);
+  BIC_TRY(golomb_scatter(c, &w, base, w.N, chunk_samples, out));
   out->info.coder = BIC_CODER_GOLOMB;
   out->info.chunk_samples = chunk_samples;
   out->info.rows = M->rows;
@@ -661,6 +708,99 @@ extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t c
   out->info.bitcount = bitcount;
   out->info.nsamples = nsamples;
   out->info.nchunks = nchunks;
+  return BIC_OK;
+}
+
+// ------------------------------------------------------------------ row-sharded coding (several GPUs)
+struct bic_comm;
+bic_status bic_comm_allgather_u64(bic_ctx* c, bic_comm* m, const uint64_t* mine, int count, uint64_t* all);
+int bic_comm_rank(const bic_comm* m);
+int bic_comm_size(const bic_comm* m);
+
+static uint32_t golomb_k_host(uint64_t t64, uint64_t bits_consumed) {  // twin of the device golomb_k
+  if (t64 == 0) return 1;
+  const uint32_t t = (uint32_t)t64, acc = (uint32_t)(bits_consumed - t64);
+  if (acc <= t) return 0;
+  uint32_t k = 0;
+  while (k < 31 && (uint32_t)(t << k) < acc) k++;
+  return k;
+}
+
+// Each rank holds a contiguous block of rows of ONE matrix (rank order = row order). Every rank codes its rows
+// as the exact substring of the single global Golomb stream: the coder state at a shard boundary is a closed
+// form of (ones before the shard, position of the last one before it), which two tiny allgathers provide.
+// The shard's bits start at bit (code_bit_offset & 31) of its own buffer, so the global stream is the
+// word-wise OR of the shards placed at word (code_bit_offset >> 5).
+extern "C" bic_status bic_dist_golomb_encode(bic_ctx* c, bic_comm* m, const bic_mat* M, uint32_t chunk_samples, bic_stream* out,
+                                             bic_shard_info* shard) {
+  if (!c || !m || !M || !out) return BIC_ERR_INVALID;
+  cudaSetDevice(c->device);
+  if (chunk_samples == 0) chunk_samples = 256;
+  while (chunk_samples & (chunk_samples - 1)) chunk_samples++;
+  const int rank = bic_comm_rank(m), nr = bic_comm_size(m);
+  GolWork w;
+  BIC_TRY(golomb_counts(c, M, &w));
+  BIC_PROF(c, KID_GOL_SCAN_B);
+  k_gol_scan_tiles_b<<<1, SCAN_THREADS, 0, c->stream>>>(w.g, w.ntiles, w.N, (unsigned long long*)c->d_scalars);
+  BIC_LAUNCH_CHECK(c);
+  BIC_TRY(bic_read_scalars(c, 4));
+  uint64_t mine[3] = {c->h_scalars[1] - 1, c->h_scalars[3], w.N};  // ones, position after the last one (0 = none), bits
+  uint64_t all[8 * 3];
+  BIC_TRY(bic_comm_allgather_u64(c, m, mine, 3, all));
+  GolBase base = gol_base_single();
+  base.closing = 0;
+  uint64_t N_global = 0, ones_global = 0;
+  long long last_global = -1;
+  {
+    uint64_t pos = 0;
+    for (int r = 0; r < nr; ++r) {
+      if (r == rank) { base.t0 = ones_global; base.pos0 = (long long)pos; base.prev0 = last_global; }
+      if (all[r * 3 + 1]) last_global = (long long)(pos + all[r * 3 + 1] - 1);
+      ones_global += all[r * 3];
+      pos += all[r * 3 + 2];
+    }
+    N_global = pos;
+  }
+  BIC_TRY(golomb_lengths(c, &w, base));
+  uint64_t bits_mine = c->h_scalars[2], bits_all[8];
+  BIC_TRY(bic_comm_allgather_u64(c, m, &bits_mine, 1, bits_all));
+  uint64_t code0 = 0, code_total = 0;
+  for (int r = 0; r < nr; ++r) { if (r < rank) code0 += bits_all[r]; code_total += bits_all[r]; }
+  const uint64_t consumed = (uint64_t)(last_global + 1);
+  const uint32_t kc = golomb_k_host(ones_global, consumed);
+  const uint64_t closing_bits = kc + ((N_global - consumed) >> kc) + 1;
+  base.code0 = code0;
+  base.out0 = code0 & 31;
+  base.chunk0 = div_up_u64(base.t0, chunk_samples);
+  uint64_t local_bits = bits_mine, local_samples = mine[0];
+  if (rank == nr - 1) {  // the last rank also writes the run closed by the virtual one
+    base.closing = 1;
+    base.close_t = ones_global;
+    base.close_consumed = consumed;
+    base.close_off = bits_mine;
+    local_bits += closing_bits;
+    local_samples += 1;
+  }
+  const uint64_t chunk_end = div_up_u64(base.t0 + local_samples, chunk_samples);  // first chunk the NEXT shard stores
+  const uint64_t nchunks = chunk_end - base.chunk0;
+  BIC_TRY(stream_reserve(c, out, base.out0 + local_bits, nchunks, w.N));
+  BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, (size_t)(div_up_u64(base.out0 + local_bits, 32) * 4 + 16), c->stream));
+  BIC_TRY(golomb_scatter(c, &w, base, N_global, chunk_samples, out));
+  out->info.coder = BIC_CODER_GOLOMB;
+  out->info.chunk_samples = chunk_samples;
+  out->info.rows = M->rows;
+  out->info.cols = M->cols;
+  out->info.bitcount = base.out0 + local_bits;  // bits of the local buffer, incl. the (code0 & 31) leading pad
+  out->info.nsamples = local_samples;
+  out->info.nchunks = nchunks;
+  if (shard) {
+    shard->global_bitcount = code_total + closing_bits;
+    shard->global_nsamples = ones_global + 1;
+    shard->code_bit_offset = code0;
+    shard->local_code_bits = local_bits;
+    shard->first_chunk = base.chunk0;
+    shard->local_chunks = nchunks;
+  }
   return BIC_OK;
 }
 

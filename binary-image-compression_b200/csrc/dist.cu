@@ -110,6 +110,22 @@ static bic_status allreduce_u32(bic_ctx* c, bic_comm* m, uint32_t* buf, size_t c
   return BIC_OK;
 }
 
+// small host-visible allgather of `count` u64 per rank (count <= 4): all[r*count + i]
+bic_status bic_comm_allgather_u64(bic_ctx* c, bic_comm* m, const uint64_t* mine, int count, uint64_t* all) {
+  if (count < 1 || count > 4 || m->nranks > 8) return BIC_ERR_INVALID;
+  uint64_t* d = c->d_scalars + 16;  // [16, 16 + 8*4)
+  BIC_CUDA(c, cudaMemcpyAsync(d + (size_t)m->rank * count, mine, 8 * count, cudaMemcpyHostToDevice, c->stream));
+  if (m->nranks > 1) {
+    BIC_NCCL(c, nccl_api()->AllGather(d + (size_t)m->rank * count, d, count, ncclUint64, m->comm, c->stream));
+    m->collectives++;
+  }
+  BIC_CUDA(c, cudaMemcpyAsync(all, d, 8 * (size_t)count * m->nranks, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
+  return BIC_OK;
+}
+int bic_comm_rank(const bic_comm* m) { return m->rank; }
+int bic_comm_size(const bic_comm* m) { return m->nranks; }
+
 // rows per rank -> offsets (one tiny allgather, repeated when the local row count changes)
 static bic_status share_rows(bic_ctx* c, bic_comm* m, uint64_t n_local) {
   if ((int)m->nrows.size() == m->nranks && m->nrows[m->rank] == n_local) return BIC_OK;

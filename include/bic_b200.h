@@ -184,6 +184,20 @@ bic_status bic_dist_learn_model_traditional(bic_ctx* ctx, bic_comm* comm, const 
                                             bic_mat* D, bic_mat* A_local, uint64_t* iterations, uint64_t* trace,
                                             uint64_t trace_cap);
 
+/* Golomb coding of a row-sharded matrix (rank order = row order): every rank codes its rows as the exact
+ * substring of the ONE global stream the serial coder would write for the whole matrix. `out` receives the
+ * shard's bits starting at bit (code_bit_offset & 31) of its buffer, so the global stream is the word-wise OR
+ * of the shards placed at 32-bit word (code_bit_offset >> 5); chunk-index entries hold global offsets and
+ * `first_chunk` is the global number of the shard's first entry. */
+typedef struct {
+  uint64_t global_bitcount, global_nsamples;  /* of the whole matrix: GolombCoder::bitcount, popcount + 1 */
+  uint64_t code_bit_offset, local_code_bits;  /* where this shard's codewords sit in the global stream */
+  uint64_t first_chunk, local_chunks;
+} bic_shard_info;
+struct bic_stream;
+bic_status bic_dist_golomb_encode(bic_ctx* ctx, bic_comm* comm, const bic_mat* M_local, uint32_t chunk_samples,
+                                  struct bic_stream* out, bic_shard_info* shard);
+
 /* ---------------------------------------------------------------- entropy coding
  * A coded stream is a byte string: stream bit t is in byte t/8 at mask 0x80 >> (t%8)
  * (writeBits / readBits order, src/GolombCoder.cpp:22-25, src/GolombDecoder.cpp:15-23). */

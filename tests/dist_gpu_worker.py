@@ -48,6 +48,23 @@ def main():
         c0 = ctx.comm_collectives(comm)
         ch = ctx.dist_update_dictionary(comm, E, D, A)
         assert ch == 0 and ctx.comm_collectives(comm) - c0 <= 2
+        # seam-exact coding: my rows' codewords are a substring of the oracle's single global stream
+        for M, Mo, cols_ in ((E, Eo, m), (A, Ao, K)):
+            so, nbits, ns = oracle.golomb_encode(Mo, cols_)
+            st, si = ctx.dist_golomb_encode(comm, M, chunk_samples=64)
+            assert si.global_bitcount == nbits and si.global_nsamples == ns, (rank, si.global_bitcount, nbits)
+            by, idx = st.download()
+            gbits = np.unpackbits(so)[:nbits]
+            lo, ln = int(si.code_bit_offset), int(si.local_code_bits)
+            mine = np.unpackbits(by)[lo % 32: lo % 32 + ln]
+            assert np.array_equal(mine, gbits[lo: lo + ln]), f"rank {rank}: shard substring differs at bit offset {lo}"
+            assert not np.unpackbits(by)[: lo % 32].any()
+            if rank == world - 1:
+                assert lo + ln == nbits
+            # chunk index entries are global: decoding from any of my entries with the serial rule must land on ones
+            assert len(idx) == si.local_chunks
+            if len(idx):
+                assert int(idx[0][0]) >= lo and int(idx[-1][0]) < lo + ln
         for mm in (X, D, A, E):
             mm.destroy()
     if rank == 0:

@@ -38,6 +38,14 @@ def test_sharded_path_with_one_rank(oracle, synth):
     Eo, ito, tro = oracle.learn_traditional(Xw, Do, Ao, m, K)
     assert it == ito and np.array_equal(tr, tro)
     assert np.array_equal(D.download(), Do) and np.array_equal(A.download(), Ao) and np.array_equal(E.download(), Eo)
+    # sharded coder with one shard == the plain coder
+    s_plain = ctx.golomb_encode(E)
+    s_shard, si = ctx.dist_golomb_encode(comm, E)
+    assert si.code_bit_offset == 0 and si.global_bitcount == s_plain.info.bitcount == s_shard.info.bitcount
+    assert si.global_nsamples == s_plain.info.nsamples
+    b0, i0 = s_plain.download()
+    b1, i1 = s_shard.download()
+    assert np.array_equal(b0, b1) and np.array_equal(i0, i1)
     ctx.comm_destroy(comm)
     ctx.close()
 
