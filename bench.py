@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", action="store_true", help="one batched learner call for all planes instead of per-plane calls on the stream pool")
     ap.add_argument("--wait-mode", type=int, default=1, help="0 cudaStreamSynchronize, 1 poll+yield, 2 blocking event")
+    ap.add_argument("--gol-onepass", type=int, default=0, help="1 single-pass Golomb encoder, 0 three-kernel pipeline")
     ap.add_argument("--sharded", action="store_true", help="also time the row-sharded (NCCL) fit at N=1")
     ap.add_argument("--streams", type=int, default=16, help="contexts (CUDA streams) per GPU")
     return ap.parse_args()
@@ -262,6 +263,7 @@ def main():
             self.ctx = bic.Context(local_rank)
             c = self.ctx
             c.set_option("wait_mode", args.wait_mode)
+            c.set_option("gol_onepass", args.gol_onepass)
             self.X, self.E = c.matrix(n, m), c.matrix(n, m)
             self.D, self.A = c.matrix(K, m), c.matrix(n, K)
             self.streams = [c.stream() for _ in range(3)]

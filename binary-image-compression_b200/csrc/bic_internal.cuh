@@ -68,6 +68,7 @@ struct bic_ctx {
   // optional per-launch device timers
   int wait_mode = 0;       // how host threads wait for the stream: 0 cudaStreamSynchronize, 1 poll + sched_yield, 2 blocking event
   cudaEvent_t wait_ev = nullptr, wait_ev_blocking = nullptr;
+  int gol_onepass = 0;     // 1: single-pass Golomb encoder (decoupled look-back) when the buffer is pre-sized
   int dict_algo = 1;  // 0: per-atom walk (dict.cu), 1: histogram first, resolve in order (dict2.cu)
   bool prof_on = false;
   std::vector<bic_prof_rec> prof_recs;

@@ -414,6 +414,204 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
   }
 }
 
+// ------------------------------------------------------------------ single-pass encoder
+// The three-kernel pipeline above reads the input three times and needs the bit count on the host before
+// the scatter. When the output buffer is already large enough (stream objects are sized for 1.25 code bits
+// per input bit) everything runs in ONE kernel: tiles take tickets in order and obtain their two prefixes
+// -- (ones, last one) before the tile, then code bits before the tile -- by decoupled look-back over
+// per-tile status words; the last tile also writes the closing sample and the totals. If the code would not
+// fit, nothing past the capacity is written, the overflow flag is set and the caller falls back to the
+// three-kernel path with an exact allocation.
+struct GolLook {  // per tile, two chained scans
+  unsigned long long agg_ones, pre_ones;
+  long long agg_last, pre_last;
+  unsigned long long agg_bits, pre_bits;
+  volatile unsigned int flag_a;  // 0 none, 1 aggregate, 2 inclusive prefix  (ones/last)
+  volatile unsigned int flag_b;  // same for bits
+};
+
+__global__ void __launch_bounds__(TILE_THREADS) k_gol_onepass(const uint32_t* __restrict__ S, uint64_t T, uint64_t N, uint64_t ntiles,
+                                                              GolLook* __restrict__ look, unsigned int* __restrict__ ticket,
+                                                              uint32_t* __restrict__ out, unsigned long long cap_bits,
+                                                              unsigned long long* __restrict__ index, uint32_t chunk,
+                                                              unsigned long long* __restrict__ scalars /* [0] bits [1] samples [4] overflow */) {
+  __shared__ unsigned long long s_a[8];
+  __shared__ long long s_b[8];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_ones_before, s_bits_before;
+  __shared__ long long s_last_before;
+  __shared__ uint32_t s_out[GOL_SMEM_WORDS];
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint64_t tile = s_tile;
+  const uint64_t w0 = tile * TILE_WORDS + threadIdx.x * TILE_WORDS_PER_THREAD;
+  uint32_t v[4];
+  load_tile_words(S, T, w0, v);
+  unsigned long long c = 0;
+  long long last = -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    c += __popc(v[i]);
+    if (v[i]) last = (long long)((w0 + i) * 32 + (32 - __ffs(v[i])));
+  }
+  unsigned long long tot_c;
+  long long tot_last;
+  const unsigned long long ex_c = block_excl_scan_u64(c, &tot_c, s_a);
+  const long long pl = block_excl_scan_max(last, &tot_last, s_b);
+  if (threadIdx.x == 0) {  // look-back 1: ones and last one before this tile
+    GolLook* me = look + tile;
+    me->agg_ones = tot_c;
+    me->agg_last = tot_last;
+    __threadfence();
+    me->flag_a = 1;
+    unsigned long long ones = 0;
+    long long lb = -1;
+    for (long long j = (long long)tile - 1; j >= 0; --j) {
+      GolLook* q = look + j;
+      unsigned int f;
+      while ((f = q->flag_a) == 0) {}
+      __threadfence();
+      if (f == 2) {
+        ones += __ldcg(&q->pre_ones);
+        const long long pq = __ldcg(&q->pre_last);
+        lb = lb > pq ? lb : pq;
+        break;
+      }
+      ones += __ldcg(&q->agg_ones);
+      const long long aq = __ldcg(&q->agg_last);
+      lb = lb > aq ? lb : aq;
+    }
+    me->pre_ones = ones + tot_c;
+    me->pre_last = lb > tot_last ? lb : tot_last;
+    __threadfence();
+    me->flag_a = 2;
+    s_ones_before = ones;
+    s_last_before = lb;
+  }
+  __syncthreads();
+  const unsigned long long rank0 = s_ones_before + ex_c;
+  long long prev = pl > s_last_before ? pl : s_last_before;
+  unsigned long long mybits = 0;
+  {
+    unsigned long long t = rank0;
+    long long pv = prev;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t b = v[i];
+      while (b) {
+        const int p = __clz(b);
+        b &= ~(0x80000000u >> p);
+        const long long pos = (long long)((w0 + i) * 32 + p);
+        const unsigned long long x = (unsigned long long)(pos - pv - 1);
+        const uint32_t k = golomb_k(t, (unsigned long long)(pv + 1));
+        mybits += k + (x >> k) + 1;
+        pv = pos;
+        ++t;
+      }
+    }
+  }
+  unsigned long long tot;
+  const unsigned long long ex = block_excl_scan_u64(mybits, &tot, s_a);
+  if (threadIdx.x == 0) {  // look-back 2: code bits before this tile
+    GolLook* me = look + tile;
+    me->agg_bits = tot;
+    __threadfence();
+    me->flag_b = 1;
+    unsigned long long bits = 0;
+    for (long long j = (long long)tile - 1; j >= 0; --j) {
+      GolLook* q = look + j;
+      unsigned int f;
+      while ((f = q->flag_b) == 0) {}
+      __threadfence();
+      if (f == 2) { bits += __ldcg(&q->pre_bits); break; }
+      bits += __ldcg(&q->agg_bits);
+    }
+    me->pre_bits = bits + tot;
+    __threadfence();
+    me->flag_b = 2;
+    s_bits_before = bits;
+  }
+  __syncthreads();
+  const unsigned long long o0 = s_bits_before;
+  const bool fits = (o0 + tot + 64 <= cap_bits);  // uniform over the CTA
+  if (!fits && threadIdx.x == 0) scalars[4] = 1;
+  const unsigned long long base = o0 & ~31ull;
+  const unsigned long long span_words = ((o0 - base) + tot + 31) >> 5;
+  const bool staged = span_words <= GOL_SMEM_WORDS;
+  if (fits) {
+    if (staged) {
+      for (unsigned i = threadIdx.x; i < (unsigned)span_words; i += blockDim.x) s_out[i] = 0;
+      __syncthreads();
+    }
+    unsigned long long o = o0 + ex;
+    unsigned long long t = rank0;
+    const unsigned long long cmask = (unsigned long long)chunk - 1;
+    const int clog = 31 - __clz(chunk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t b = v[i];
+      while (b) {
+        const int p = __clz(b);
+        b &= ~(0x80000000u >> p);
+        const long long pos = (long long)((w0 + i) * 32 + p);
+        const unsigned long long x = (unsigned long long)(pos - prev - 1);
+        const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+        if ((t & cmask) == 0) { index[2 * (t >> clog)] = o; index[2 * (t >> clog) + 1] = (unsigned long long)(prev + 1); }
+        const uint32_t rem = (uint32_t)(x & ((1ull << k) - 1));
+        const unsigned long long stop = o + k + (x >> k);
+        if (staged) {
+          if (rem) {
+            const unsigned lo_bit = (unsigned)(o - base);
+            const unsigned long long v64 = (unsigned long long)rem << (64 - (lo_bit & 31) - k);
+            const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
+            if (hi) atomicOr(&s_out[lo_bit >> 5], hi);
+            if (lo) atomicOr(&s_out[(lo_bit >> 5) + 1], lo);
+          }
+          const unsigned sb = (unsigned)(stop - base);
+          atomicOr(&s_out[sb >> 5], 0x80000000u >> (sb & 31));
+        } else {
+          put_bits(out, o, rem, k);
+          put_one(out, stop);
+        }
+        o = stop + 1;
+        prev = pos;
+        ++t;
+      }
+    }
+    if (staged) {
+      __syncthreads();
+      uint32_t* gout = out + (base >> 5);
+      for (unsigned i = threadIdx.x; i < (unsigned)span_words; i += blockDim.x) {
+        const uint32_t w = s_out[i];
+        if (!w) continue;
+        if (i == 0 || i == (unsigned)span_words - 1) atomicOr(gout + i, bswap32(w));
+        else gout[i] = bswap32(w);
+      }
+    }
+  }
+  if (tile == ntiles - 1 && threadIdx.x == 0) {  // totals and the run closed by the virtual one
+    const unsigned long long ones = s_ones_before + tot_c;
+    const long long lastg = s_last_before > tot_last ? s_last_before : tot_last;
+    const unsigned long long consumed = (unsigned long long)(lastg + 1);
+    unsigned long long oo = o0 + tot;
+    const unsigned long long x = N - consumed;
+    const uint32_t k = golomb_k(ones, consumed);
+    const unsigned long long total = oo + k + (x >> k) + 1;
+    scalars[0] = total;
+    scalars[1] = ones + 1;
+    if (total + 64 <= cap_bits) {
+      const unsigned long long cmask = (unsigned long long)chunk - 1;
+      const int clog = 31 - __clz(chunk);
+      if ((ones & cmask) == 0) { index[2 * (ones >> clog)] = oo; index[2 * (ones >> clog) + 1] = consumed; }
+      put_bits(out, oo, (uint32_t)(x & ((1ull << k) - 1)), k);
+      oo += k + (x >> k);
+      put_one(out, oo);
+    } else {
+      scalars[4] = 1;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ Golomb decoder: a thread per chunk
 __device__ __forceinline__ uint32_t peek32(const uint32_t* __restrict__ in, unsigned long long o) {
   const unsigned long long wi = o >> 5;
@@ -690,6 +888,39 @@ extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t c
   if (chunk_samples == 0) chunk_samples = 256;
   while (chunk_samples & (chunk_samples - 1)) chunk_samples++;  // the kernels index chunks with shifts: round up to a power of two
   GolWork w;
+  {  // single pass into the pre-sized buffer (the common case); falls through to the exact path on overflow
+    const uint64_t N = M->rows * M->cols;
+    const uint64_t T = div_up_u64(N, 32), ntiles = div_up_u64(T, TILE_WORDS);
+    BIC_TRY(stream_reserve(c, out, 0, div_up_u64(N + 1, chunk_samples), N));  // worst case: every bit a sample
+    const uint64_t cap_bits = (uint64_t)(out->cap_bytes - 16) * 8;
+    if (ntiles && c->gol_onepass) {
+      const uint32_t* S;
+      uint64_t T2;
+      BIC_TRY(dense_stream(c, M, &S, &T2));
+      BIC_TRY(bic_scratch_reserve(c, &c->work[5], ntiles * sizeof(GolLook) + 64));
+      GolLook* look = (GolLook*)((uint8_t*)c->work[5].p + 64);
+      unsigned int* ticket = (unsigned int*)c->work[5].p;
+      BIC_CUDA(c, cudaMemsetAsync(c->work[5].p, 0, ntiles * sizeof(GolLook) + 64, c->stream));
+      BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, 5 * sizeof(uint64_t), c->stream));
+      BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, out->cap_bytes, c->stream));
+      BIC_PROF(c, KID_GOL_SCATTER);
+      k_gol_onepass<<<(unsigned)ntiles, TILE_THREADS, 0, c->stream>>>(S, T2, N, ntiles, look, ticket, (uint32_t*)out->d_bytes, cap_bits,
+                                                                    (unsigned long long*)out->d_index, chunk_samples,
+                                                                    (unsigned long long*)c->d_scalars);
+      BIC_LAUNCH_CHECK(c);
+      BIC_TRY(bic_read_scalars(c, 5));
+      if (!c->h_scalars[4]) {
+        out->info.coder = BIC_CODER_GOLOMB;
+        out->info.chunk_samples = chunk_samples;
+        out->info.rows = M->rows;
+        out->info.cols = M->cols;
+        out->info.bitcount = c->h_scalars[0];
+        out->info.nsamples = c->h_scalars[1];
+        out->info.nchunks = div_up_u64(c->h_scalars[1], chunk_samples);
+        return BIC_OK;
+      }
+    }
+  }
   BIC_TRY(golomb_counts(c, M, &w));
   GolBase base = gol_base_single();
   BIC_TRY(golomb_lengths(c, &w, base));

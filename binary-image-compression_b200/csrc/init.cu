@@ -64,27 +64,37 @@ extern "C" bic_status bic_draw_pivots(bic_ctx* c, const bic_mat* X, uint64_t p, 
 }
 
 // ------------------------------------------------------------------ column histogram c[b]
-// A warp walks rows; every lane loads the same word (broadcast) and counts its own bit.
-// WORDS = words of a row handled per launch (registers), word0 = first word.
+// A warp takes blocks of 32 consecutive rows: lane r loads word w of row r (coalesced across the block's rows),
+// the 32x32 bit tile is transposed in registers (shuffle butterfly), and lane b then holds column b of the tile:
+// one POPC per 32 rows per column instead of 32 bit extractions. WORDS = words of a row per launch.
 template <int WORDS>
-__global__ void k_col_hist(const uint32_t* __restrict__ X, uint64_t n, uint64_t wpr, uint64_t word0, uint64_t nwords,
-                           uint32_t* __restrict__ hist /* [wpr*32] */) {
+__global__ void __launch_bounds__(256) k_col_hist(const uint32_t* __restrict__ X, uint64_t n, uint64_t wpr, uint64_t word0,
+                                                  uint64_t nwords, uint32_t* __restrict__ hist /* [wpr*32] */) {
+  __shared__ uint32_t s_cnt[WORDS * 32];
+  for (int i = threadIdx.x; i < WORDS * 32; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t nblocks = div_up_u64(n, 32);
   uint32_t cnt[WORDS];
 #pragma unroll
   for (int w = 0; w < WORDS; ++w) cnt[w] = 0;
-  for (uint64_t r = gw; r < n; r += nwarps) {
+  for (uint64_t blk = gw; blk < nblocks; blk += nwarps) {
+    const uint64_t r = blk * 32 + lane;
     const uint32_t* row = X + r * wpr + word0;
 #pragma unroll
     for (int w = 0; w < WORDS; ++w) {
-      if ((uint64_t)w < nwords) cnt[w] += (__ldg(row + w) >> (31 - lane)) & 1u;
+      const uint32_t x = (r < n && (uint64_t)w < nwords) ? __ldg(row + w) : 0u;
+      cnt[w] += __popc(warp_transpose32(x));
     }
   }
 #pragma unroll
   for (int w = 0; w < WORDS; ++w)
-    if ((uint64_t)w < nwords && cnt[w]) atomicAdd(&hist[(word0 + w) * 32 + lane], cnt[w]);
+    if ((uint64_t)w < nwords && cnt[w]) atomicAdd(&s_cnt[w * 32 + lane], cnt[w]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < WORDS * 32; i += blockDim.x)
+    if (s_cnt[i] && (uint64_t)(i >> 5) < nwords) atomicAdd(&hist[word0 * 32 + i], s_cnt[i]);
 }
 
 // ------------------------------------------------------------------ u[k] = #{j : X[j] & P_k != 0}
@@ -209,7 +219,7 @@ bic_status bic_k_init_stats(bic_ctx* c, const bic_mat* X, InitWork* w) {
   if (X->rows == 0) return BIC_OK;
   for (uint64_t w0 = 0; w0 < wpr; w0 += 32) {  // 32 words of the row per launch
     const uint64_t nw = (wpr - w0 < 32) ? wpr - w0 : 32;
-    const int grid = bic_grid_for(c, X->rows * 32, 256, 8);
+    const int grid = bic_grid_for(c, X->rows, 256, 4);  // a warp per 32-row block, a few blocks per warp
     BIC_PROF(c, KID_COL_HIST);
     if (nw <= 2) k_col_hist<2><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, w->hist);
     else if (nw <= 8) k_col_hist<8><<<grid, 256, 0, c->stream>>>(X->d, X->rows, wpr, w0, nw, w->hist);

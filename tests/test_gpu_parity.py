@@ -224,8 +224,10 @@ CODER_SHAPES = [(1, 1, 0.0), (1, 1, 1.0), (1, 32, 0.0), (3, 64, 0.5), (17, 100, 
                 (3, 70, 1.0), (300, 256, 0.005), (1000, 64, 0.02), (2000, 1024, 0.1), (1, 200000, 0.001), (4096, 32, 0.3)]
 
 
+@pytest.mark.parametrize("onepass", [0, 1])
 @pytest.mark.parametrize("rows,cols,rho", CODER_SHAPES)
-def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho):
+def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho, onepass):
+    ctx.set_option("gol_onepass", onepass)  # 1: single kernel with decoupled look-back, 0: three-kernel pipeline
     rng = np.random.default_rng(rows * 31 + cols)
     bits = (rng.random((rows, cols)) < rho).astype(np.uint8)
     Mw = synth.pack_rows(bits)
@@ -247,6 +249,7 @@ def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, c
         assert np.array_equal(M2.download(), Mw)
         M2.destroy(); s.destroy()
     M.destroy()
+    ctx.set_option("gol_onepass", 0)
 
 
 @pytest.mark.parametrize("rows,cols,rho", CODER_SHAPES[:11])
