@@ -136,6 +136,7 @@ struct ResolveParams {
   uint32_t* first;       // [2]: scan/fix variant: first changing atom found by the scan of this parity
   uint64_t n, wprE, wprA, wprN, m, hs;
   uint32_t p, parity, win;  // win: histogram rows cached in shared memory per refill
+  uint32_t corr_smem;       // 1: k_dict_resolve_step sums the corrections per CTA in shared memory (p*hs words after the window)
   const ProbDev* probs;     // batched launch: blockIdx.y selects the problem (else null)
   const uint32_t* active;
 };
@@ -152,7 +153,7 @@ __device__ __forceinline__ bool resolve_select_problem(ResolveParams& P) {
 
 // Atom k changes by s_delta = D_k ^ newD_k (shared memory, same in every CTA): patch its users'
 // residual rows, correct the histograms of the later atoms those rows use, publish newD_k and the cursor.
-__device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32_t k, const uint32_t* s_delta) {
+__device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32_t k, const uint32_t* s_delta, uint32_t* s_corr) {
   const int lane = threadIdx.x & 31;
   const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -228,7 +229,9 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
           while (ab) {
             const int ap = __clz(ab);
             ab &= ~(0x80000000u >> ap);
-            uint32_t* hl = P.Hc + (aw * 32 + ap) * P.hs;
+            // corrections are summed per CTA in shared memory when the histogram fits there (one global
+            // atomic per touched counter per CTA instead of one per row and bit), else go straight to L2
+            uint32_t* hl = (s_corr ? s_corr : P.Hc) + (aw * 32 + ap) * P.hs;
             for (uint64_t w = 0; w < P.wprE; ++w) {
               uint32_t dl = s_delta[w];
               if (!dl) continue;
@@ -247,6 +250,14 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
         }
       }
       __syncwarp();
+    }
+    if (s_corr) {
+      __syncthreads();
+      const uint64_t lo = (uint64_t)(k + 1) * P.hs, hi = (uint64_t)P.p * P.hs;
+      for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const uint32_t v = s_corr[i];
+        if (v) atomicAdd(P.Hc + i, v);
+      }
     }
   }
   if (blockIdx.x == 0) {
@@ -315,7 +326,13 @@ __global__ void __launch_bounds__(256) k_dict_resolve_step(ResolveParams P) {
     if (blockIdx.x == 0 && threadIdx.x == 0) P.cursor[P.parity ^ 1] = P.p;
     return;
   }
-  dict_apply_change(P, k, s_delta);
+  uint32_t* s_corr = nullptr;
+  if (P.corr_smem) {  // zero the CTA's correction counters for the atoms after k
+    s_corr = s_H + (uint64_t)P.win * P.hs;
+    for (uint64_t i = (uint64_t)(k + 1) * P.hs + threadIdx.x; i < (uint64_t)P.p * P.hs; i += blockDim.x) s_corr[i] = 0;
+    __syncthreads();
+  }
+  dict_apply_change(P, k, s_delta, s_corr);
 }
 
 // ------------------------------------------------------------------ pass 2 for large dictionaries
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__(256) k_dict_fix(ResolveParams P) {
     if (lane == 0) s_delta[w] = nd ^ dk;
   }
   __syncthreads();
-  dict_apply_change(P, k, s_delta);
+  dict_apply_change(P, k, s_delta, nullptr);
 }
 
 static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs) {
@@ -452,7 +469,8 @@ bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_m
   if (win < 1) win = 1;
   if (win > w->p) win = w->p;
   P.win = (uint32_t)win;
-  const size_t smem = (size_t)(w->wpr + win * (w->hs + 1)) * 4;
+  P.corr_smem = (!w->use_scan && w->wpr < 8 && w->p * w->hs <= 4096) ? 1u : 0u;
+  const size_t smem = (size_t)(w->wpr + win * (w->hs + 1) + (P.corr_smem ? w->p * w->hs : 0)) * 4;
   const int grid = (w->wpr >= 8) ? bic_grid_for(c, (w->wprN ? w->wprN : 1) * 32, 256, 8)
                                  : bic_grid_for(c, div_up_u64(w->wprN ? w->wprN : 1, 32) * 32, 256, 4);
   P.parity = w->launched & 1;
@@ -503,7 +521,8 @@ bic_status bic_k_dict_step_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t 
   if (win < 1) win = 1;
   if (win > p) win = p;
   P.win = (uint32_t)win;
-  const size_t smem = (size_t)(wpr + win * (hs + 1)) * 4;
+  P.corr_smem = (p * (hs + 1) * 4 <= 32 * 1024 && wpr < 8 && p * hs <= 4096) ? 1u : 0u;
+  const size_t smem = (size_t)(wpr + win * (hs + 1) + (P.corr_smem ? p * hs : 0)) * 4;
   const int gx = (wpr >= 8) ? bic_grid_for(c, (wprN ? wprN : 1) * 32, 256, 8)
                             : bic_grid_for(c, div_up_u64(wprN ? wprN : 1, 32) * 32, 256, 4);
   P.parity = launched & 1;
