@@ -422,6 +422,15 @@ static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, ui
 
 bic_status bic_k_transpose_A(bic_ctx* c, const bic_mat* A, uint32_t* AT, uint64_t wprN);
 
+// window (<= 32 KB) + correction counters (<= 16 KB) + the static user queue (16 KB) can pass the 48 KB default
+static bic_status resolve_step_smem_optin(bic_ctx* c) {
+  static bool done[64] = {false};
+  if (c->device < 64 && done[c->device]) return BIC_OK;
+  BIC_CUDA(c, cudaFuncSetAttribute(k_dict_resolve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  if (c->device < 64) done[c->device] = true;
+  return BIC_OK;
+}
+
 // The update as three reusable stages, so the row-sharded driver (dist.cu) can put its collectives
 // between them: (1) prepare: AT, local H/U; (2) resolve steps; (3) commit Dnew -> D.
 bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, DictWork* w) {
@@ -483,6 +492,7 @@ bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_m
     k_dict_fix<<<grid, 256, (size_t)w->wpr * 4, c->stream>>>(P);
     BIC_LAUNCH_CHECK(c);
   } else {
+    BIC_TRY(resolve_step_smem_optin(c));
     BIC_PROF(c, KID_DICT_RESOLVE);
     k_dict_resolve_step<<<grid, 256, smem, c->stream>>>(P);
     BIC_LAUNCH_CHECK(c);
@@ -535,6 +545,7 @@ bic_status bic_k_dict_step_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t 
     k_dict_fix<<<dim3(gx, nprob), 256, (size_t)wpr * 4, c->stream>>>(P);
     BIC_LAUNCH_CHECK(c);
   } else {
+    BIC_TRY(resolve_step_smem_optin(c));
     BIC_PROF(c, KID_DICT_RESOLVE);
     k_dict_resolve_step<<<dim3(gx, nprob), 256, smem, c->stream>>>(P);
     BIC_LAUNCH_CHECK(c);
