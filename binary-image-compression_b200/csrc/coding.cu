@@ -138,6 +138,7 @@ struct GolTile {           // per 1024-word tile
   long long* last_before;  // last one before the tile, -1 if none
   unsigned long long* bits;         // code bits produced by the tile's ones
   unsigned long long* bits_before;  // exclusive prefix
+  unsigned long long* tbits;        // per thread (4 words of input): code bits of its ones, written by the length pass
 };
 
 __device__ __forceinline__ void load_tile_words(const uint32_t* __restrict__ S, uint64_t T, uint64_t w0, uint32_t (&v)[4]) {
@@ -314,9 +315,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
   const long long pv_local = pl > lb ? pl : lb;                       // previous one inside this shard, -1 if none
   long long prev = pv_local >= 0 ? pv_local + gb.pos0 : gb.prev0;     // GLOBAL position of the previous one, -1 if none
 
-  // pass 1: my code bits
+  // pass 1: my code bits -- computed by the length pass (MODE 0) and kept per thread; the scatter pass
+  // (MODE 1) reads them back instead of walking the samples twice
   unsigned long long mybits = 0;
-  {
+  const uint64_t tslot = (uint64_t)blockIdx.x * TILE_THREADS + threadIdx.x;
+  if (MODE == 0) {
     unsigned long long t = rank0;
     long long pv = prev;
 #pragma unroll
@@ -333,6 +336,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
         ++t;
       }
     }
+    g.tbits[tslot] = mybits;
+  } else {
+    mybits = g.tbits[tslot];
   }
   unsigned long long tot;
   const unsigned long long ex = block_excl_scan_u64(mybits, &tot, s_a);
@@ -825,7 +831,7 @@ static bic_status golomb_counts(bic_ctx* c, const bic_mat* M, GolWork* w) {
   BIC_TRY(dense_stream(c, M, &w->S, &w->T));
   w->ntiles = div_up_u64(w->T, TILE_WORDS);
   const size_t per = (size_t)(w->ntiles ? w->ntiles : 1);  // work[5]: per-tile arrays
-  BIC_TRY(bic_scratch_reserve(c, &c->work[5], per * (8 * 5 + 8)));
+  BIC_TRY(bic_scratch_reserve(c, &c->work[5], per * (8 * 5 + 8) + per * TILE_THREADS * 8));
   uint8_t* p = (uint8_t*)c->work[5].p;
   GolTile* g = &w->g;
   g->last = (long long*)p;
@@ -834,7 +840,9 @@ static bic_status golomb_counts(bic_ctx* c, const bic_mat* M, GolWork* w) {
   g->bits = (unsigned long long*)(p + per * 24);
   g->bits_before = (unsigned long long*)(p + per * 32);
   g->ones = (uint32_t*)(p + per * 40);
+  g->tbits = (unsigned long long*)(p + per * 48);
   BIC_CUDA(c, cudaMemsetAsync(g->bits, 0, per * 8, c->stream));
+  if (!w->ntiles) BIC_CUDA(c, cudaMemsetAsync(g->tbits, 0, per * TILE_THREADS * 8, c->stream));  // the lone CTA of an empty matrix reads them
   if (w->ntiles) {
     BIC_PROF(c, KID_GOL_TILE_COUNTS);
     k_gol_tile_counts<<<(unsigned)w->ntiles, TILE_THREADS, 0, c->stream>>>(w->S, w->T, *g);

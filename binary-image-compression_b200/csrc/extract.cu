@@ -51,6 +51,35 @@ __global__ void k_extract(const uint32_t* __restrict__ I, uint32_t* __restrict__
   }
 }
 
+// Fast path for W = 2^LW <= 32 (8, 16, 32: every config BASELINE.json names): a word of X is 32/W whole tile
+// rows, each W aligned bits of one raster word, so there is no division, no funnel shift and no edge wrap
+// (W divides 64). blockIdx.y = tile row; threads run over (tile column, word) pairs.
+template <int LW>
+__global__ void __launch_bounds__(256) k_extract_pow2(const uint32_t* __restrict__ I, uint32_t* __restrict__ X, uint32_t rows,
+                                                      uint32_t cols, uint32_t wprI, uint32_t Nx) {
+  constexpr uint32_t W = 1u << LW;
+  constexpr uint32_t SEG = 32u / W;          // tile rows per word of X
+  constexpr uint32_t WPX = (W * W) / 32u;    // words per patch (W >= 8) -- W*W is a multiple of 32 for W >= 8
+  const uint32_t ti = blockIdx.y;
+  const uint32_t per_row = Nx * WPX;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+    const uint32_t tj = i / WPX, q = i - tj * WPX;   // WPX is a power of two: shifts
+    const uint32_t c = tj << LW;                     // first raster column of the tile
+    uint32_t out = 0;
+    if (c < cols) {
+      const uint32_t wi = c >> 5, sh = 32u - W - (c & 31u);
+#pragma unroll
+      for (uint32_t s = 0; s < SEG; ++s) {
+        const uint32_t r = (ti << LW) + q * SEG + s;
+        uint32_t seg = 0;
+        if (r < rows) seg = (W == 32) ? __ldg(I + (uint64_t)r * wprI + wi) : ((__ldg(I + (uint64_t)r * wprI + wi) >> sh) & ((1u << (W & 31)) - 1u));
+        out |= seg << (32u - W * (s + 1u));
+      }
+    }
+    X[((uint64_t)ti * Nx + tj) * WPX + q] = out;
+  }
+}
+
 // Inverse: one thread per 32-bit word of the raster; gathers its bits from the patches.
 __global__ void k_assemble(const uint32_t* __restrict__ X, uint32_t* __restrict__ I, uint64_t rows, uint64_t cols,
                            uint64_t wprI, uint64_t W, uint64_t Nx, uint64_t wprX) {
@@ -88,6 +117,16 @@ extern "C" bic_status bic_extract_patches(bic_ctx* c, const bic_mat* raster, uin
   const uint64_t Ny = (W - 1 + raster->rows) / W, Nx = (W - 1 + raster->cols) / W;  // bsvd_test.cpp:82-83
   if (X->rows != Nx * Ny || X->cols != W * W) return bic_fail(c, BIC_ERR_INVALID, "extract: X must be Nx*Ny x W*W");
   if (X->rows == 0) return BIC_OK;
+  if ((W == 8 || W == 16 || W == 32) && raster->rows < (1ull << 31) && raster->cols < (1ull << 31) && Ny < 65536) {
+    const uint32_t per_row = (uint32_t)(Nx * (W * W / 32));
+    dim3 grid((unsigned)((per_row + 255) / 256 < 64 ? (per_row + 255) / 256 : 64), (unsigned)Ny);
+    BIC_PROF(c, KID_EXTRACT);
+    if (W == 8) k_extract_pow2<3><<<grid, 256, 0, c->stream>>>(raster->d, X->d, (uint32_t)raster->rows, (uint32_t)raster->cols, (uint32_t)raster->wpr, (uint32_t)Nx);
+    else if (W == 16) k_extract_pow2<4><<<grid, 256, 0, c->stream>>>(raster->d, X->d, (uint32_t)raster->rows, (uint32_t)raster->cols, (uint32_t)raster->wpr, (uint32_t)Nx);
+    else k_extract_pow2<5><<<grid, 256, 0, c->stream>>>(raster->d, X->d, (uint32_t)raster->rows, (uint32_t)raster->cols, (uint32_t)raster->wpr, (uint32_t)Nx);
+    BIC_LAUNCH_CHECK(c);
+    return BIC_OK;
+  }
   BIC_PROF(c, KID_EXTRACT);
   k_extract<<<bic_grid_for(c, X->words(), 256, 16), 256, 0, c->stream>>>(raster->d, X->d, raster->rows, raster->cols,
                                                                         raster->wpr, W, Nx, X->rows, X->wpr, X->cols);
