@@ -115,6 +115,13 @@ extern "C" bic_status bic_learn_model_traditional_batched(bic_ctx* c, uint32_t n
       if (!active[b]) continue;
       if (iterations) iterations[b]++;
       if (cnt[b * 2] + cnt[b * 2 + 1] == 0) { active[b] = 0; nactive--; }  // while (changed > 0), src/bsvd.cpp:1227
+      else if (cnt[b * 2 + 1] == 0) {
+        // no atom changed: the next iteration of this problem provably changes nothing (see
+        // bic_learn_model_traditional); it is counted without being run
+        if (iterations) iterations[b]++;
+        active[b] = 0;
+        nactive--;
+      }
     }
   }
   return BIC_OK;

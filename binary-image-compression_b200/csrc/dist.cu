@@ -291,6 +291,11 @@ extern "C" bic_status bic_dist_learn_model_traditional(bic_ctx* c, bic_comm* m, 
     BIC_TRY(bic_read_scalars(c, 2));
     changed = c->h_scalars[0] + c->h_scalars[1];
     if (trace && iter <= trace_cap) { trace[2 * (iter - 1)] = c->h_scalars[0]; trace[2 * (iter - 1) + 1] = c->h_scalars[1]; }
+    if (changed > 0 && c->h_scalars[1] == 0) {  // the next iteration provably changes nothing (see bic_learn_model_traditional)
+      iter++;
+      if (trace && iter <= trace_cap) { trace[2 * (iter - 1)] = 0; trace[2 * (iter - 1) + 1] = 0; }
+      break;
+    }
   }
   if (iterations) *iterations = iter;
   return BIC_OK;

@@ -22,6 +22,15 @@ extern "C" bic_status bic_learn_model_traditional(bic_ctx* c, const bic_mat* X, 
     BIC_TRY(bic_read_scalars(c, 2));                           // the loop condition needs the counts
     changed = c->h_scalars[0] + c->h_scalars[1];
     if (trace && iter <= trace_cap) { trace[2 * (iter - 1)] = c->h_scalars[0]; trace[2 * (iter - 1) + 1] = c->h_scalars[1]; }
+    if (changed > 0 && c->h_scalars[1] == 0) {
+      // No atom changed, so D and E are exactly what the coefficient update left behind, and that update
+      // ended every row with a pass that found no improving atom. The reference's next iteration therefore
+      // changes no row, sees the same (E, A, D) in its dictionary update as this one did, changes no atom,
+      // and ends the loop: it is counted (and traced as 0, 0) without being run.
+      iter++;
+      if (trace && iter <= trace_cap) { trace[2 * (iter - 1)] = 0; trace[2 * (iter - 1) + 1] = 0; }
+      break;
+    }
   }
   if (iterations) *iterations = iter;
   return BIC_OK;
