@@ -269,7 +269,14 @@ def main():
             self.streams = [c.stream() for _ in range(3)]
             self.out = c.pinned(2 * plane_bytes + (1 << 20))
 
-    T = max(1, min(args.streams, P * max(1, args.steps)))  # tasks of all steps share one queue
+    # one host thread per context: with several ranks per box the threads must fit the host cores
+    # (8 ranks x 17 threads on a 32-core box cost 20 % at N = 8), so the pool shrinks to ~1.5 threads per core
+    try:
+        host_cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        host_cores = os.cpu_count() or 16
+    T_fit = max(4, int(1.5 * host_cores / max(world, 1)))
+    T = max(1, min(args.streams, T_fit, P * max(1, args.steps)))  # tasks of all steps share one queue
     workers = [Worker() for _ in range(T)]
     stats = {"iters": [0] * P, "bits": [0] * P, "d2h": [0] * P, "wA": [0] * P}
 
