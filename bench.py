@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--batch", action="store_true", help="one batched learner call for all planes instead of per-plane calls on the stream pool")
     ap.add_argument("--wait-mode", type=int, default=1, help="0 cudaStreamSynchronize, 1 poll+yield, 2 blocking event")
     ap.add_argument("--gol-onepass", type=int, default=0, help="1 single-pass Golomb encoder, 0 three-kernel pipeline")
+    ap.add_argument("--dict-algo", type=int, default=2, help="2 cluster chain (dict3.cu), 1 launch-per-changed-atom resolve (dict2.cu), 0 per-atom walk")
+    ap.add_argument("--chain-cluster", type=int, default=16, help="CTAs per cluster of the chain kernel")
     ap.add_argument("--sharded", action="store_true", help="also time the row-sharded (NCCL) fit at N=1")
     ap.add_argument("--streams", type=int, default=16, help="contexts (CUDA streams) per GPU")
     return ap.parse_args()
@@ -200,6 +202,8 @@ def algorithmic_bytes(kernel: str, rows, cols, n, m, p, users_per_atom=0.0):
         "k_update_dictionary": n * (2 * m + p) / 8,        # read E, A once + write E once
         "k_update_coefficients": n * 2 * (m + p) / 8,      # read + write E row and A row
         "k_transpose_bits": 2 * n * p / 8,
+        "k_dict_hist_popc": n * (m + p) / 8,               # read E, A once (the counters stay on chip)
+        "k_dict_apply": n * (2 * m + p) / 8,               # read A, E + write E
         "k_extract": 2 * rows * cols / 8,
         "k_residual": n * (2 * m + p) / 8,
         "k_col_hist": n * m / 8,
@@ -264,6 +268,8 @@ def main():
             c = self.ctx
             c.set_option("wait_mode", args.wait_mode)
             c.set_option("gol_onepass", args.gol_onepass)
+            c.set_option("dict_algo", args.dict_algo)
+            c.set_option("chain_cluster", args.chain_cluster)
             self.X, self.E = c.matrix(n, m), c.matrix(n, m)
             self.D, self.A = c.matrix(K, m), c.matrix(n, K)
             self.streams = [c.stream() for _ in range(3)]

@@ -44,7 +44,7 @@ enum bic_kernel_id {
   KID_EXTRACT, KID_ASSEMBLE, KID_ROW_NONZERO, KID_GATHER_ROWS, KID_COL_HIST, KID_PIVOT_USAGE, KID_INIT_FINALIZE,
   KID_UPDATE_COEF, KID_RESIDUAL, KID_TRANSPOSE_BITS, KID_UPDATE_DICT, KID_DICT_HIST, KID_DICT_RESOLVE, KID_DICT_SCAN,
   KID_COMPACT_ROWS, KID_EXPAND_ROWS, KID_GOL_TILE_COUNTS, KID_GOL_SCAN_A, KID_GOL_LENGTHS, KID_GOL_SCAN_B,
-  KID_GOL_SCATTER, KID_GOL_DECODE, KID_EG_FIRST, KID_EG_FILL, KID_EG_ENCODE, KID_EG_DECODE,
+  KID_GOL_SCATTER, KID_GOL_DECODE, KID_EG_FIRST, KID_EG_FILL, KID_EG_ENCODE, KID_EG_DECODE, KID_DICT_CHAIN, KID_DICT_APPLY, KID_DICT_COMPACT, KID_DICT_BUCKET,
   KID_COUNT
 };
 
@@ -69,7 +69,9 @@ struct bic_ctx {
   int wait_mode = 0;       // how host threads wait for the stream: 0 cudaStreamSynchronize, 1 poll + sched_yield, 2 blocking event
   cudaEvent_t wait_ev = nullptr, wait_ev_blocking = nullptr;
   int gol_onepass = 0;     // 1: single-pass Golomb encoder (decoupled look-back) when the buffer is pre-sized
-  int dict_algo = 1;  // 0: per-atom walk (dict.cu), 1: histogram first, resolve in order (dict2.cu)
+  int dict_algo = 2;  // 0: per-atom walk (dict.cu), 1: histogram first, resolve in order (dict2.cu), 2: cluster chain (dict3.cu) where the shape allows, else 1
+  long long chain_bucket_cap = -1;  // entries of dict3.cu's per-atom buckets; -1 = 2 per row (0 forces the list-scan fallback)
+  int chain_cluster = 16;  // CTAs in the cluster of dict3.cu's chain kernel (1, 2, 4, 8 or 16)
   bool prof_on = false;
   std::vector<bic_prof_rec> prof_recs;
   std::vector<cudaEvent_t> prof_free;

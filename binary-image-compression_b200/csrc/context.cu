@@ -450,7 +450,8 @@ static const char* const kKernelNames[KID_COUNT] = {
   "k_extract", "k_assemble", "k_row_nonzero", "k_gather_rows", "k_col_hist", "k_pivot_usage", "k_init_finalize",
   "k_update_coefficients", "k_residual", "k_transpose_bits", "k_update_dictionary", "k_dict_hist_popc", "k_dict_resolve", "k_dict_scan",
   "k_compact_rows", "k_expand_rows", "k_gol_tile_counts", "k_gol_scan_tiles_a", "k_gol_walk<0>", "k_gol_scan_tiles_b",
-  "k_gol_walk<1>", "k_gol_decode", "k_first_one/zero", "k_fill_ones", "k_eg_encode", "k_eg_decode"};
+  "k_gol_walk<1>", "k_gol_decode", "k_first_one/zero", "k_fill_ones", "k_eg_encode", "k_eg_decode", "k_dict_chain", "k_dict_apply",
+  "k_dict_compact", "k_dict_bucket"};
 
 static cudaEvent_t prof_event(bic_ctx* c) {
   if (!c->prof_free.empty()) { cudaEvent_t e = c->prof_free.back(); c->prof_free.pop_back(); return e; }
@@ -521,7 +522,13 @@ extern "C" bic_status bic_ctx_set_option(bic_ctx* c, const char* name, int64_t v
   if (!c || !name) return BIC_ERR_INVALID;
   if (!strcmp(name, "wait_mode")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->wait_mode = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_onepass")) { c->gol_onepass = value != 0; return BIC_OK; }
-  if (!strcmp(name, "dict_algo")) { if (value < 0 || value > 1) return BIC_ERR_INVALID; c->dict_algo = (int)value; return BIC_OK; }
+  if (!strcmp(name, "dict_algo")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->dict_algo = (int)value; return BIC_OK; }
+  if (!strcmp(name, "chain_bucket_cap")) { c->chain_bucket_cap = value; return BIC_OK; }
+  if (!strcmp(name, "chain_cluster")) {
+    if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16) return BIC_ERR_INVALID;
+    c->chain_cluster = (int)value;
+    return BIC_OK;
+  }
   return bic_fail(c, BIC_ERR_INVALID, "unknown option");
 }
 

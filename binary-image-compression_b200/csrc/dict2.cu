@@ -30,7 +30,9 @@ template <int JW>
 __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restrict__ E, const uint32_t* __restrict__ A,
                                                         uint32_t* __restrict__ H, uint32_t* __restrict__ U, uint64_t n,
                                                         uint64_t wprE, uint64_t wprA, uint64_t hs, uint32_t ntile_j,
-                                                        const ProbDev* __restrict__ probs, const uint32_t* __restrict__ active) {
+                                                        const ProbDev* __restrict__ probs, const uint32_t* __restrict__ active,
+                                                        uint32_t* __restrict__ listA, uint32_t* __restrict__ listE,
+                                                        uint32_t* __restrict__ list_count) {
   if (probs) {  // batched launch: blockIdx.z selects the problem
     if (!active[blockIdx.z]) return;
     const ProbDev pr = probs[blockIdx.z];
@@ -81,6 +83,24 @@ __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restri
         a_n = __ldg(A + row * wprA + kw);
 #pragma unroll
         for (int w = 0; w < JW; ++w) e_n[w] = (jw0 + w < wprE) ? __ldg(E + row * wprE + jw0 + w) : 0u;
+      }
+    }
+    if (listA) {
+      // on the side (single-tile shapes only: this warp holds the whole rows): rows using two or more atoms
+      // are appended to the list the cluster chain of dict3.cu walks
+      const bool multi = __popc(a) >= 2;
+      const uint32_t bal = __ballot_sync(0xffffffffu, multi);
+      if (bal) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(list_count, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (multi) {
+          const uint64_t pos = base + __popc(bal & ((1u << lane) - 1));
+          listA[pos] = a;
+#pragma unroll
+          for (int w = 0; w < JW; ++w)
+            if ((uint64_t)w < wprE) listE[pos * wprE + w] = e[w];
+        }
       }
     }
     if (!__any_sync(0xffffffffu, a != 0)) continue;  // none of these 32 rows uses these 32 atoms
@@ -402,7 +422,8 @@ __global__ void __launch_bounds__(256) k_dict_fix(ResolveParams P) {
   dict_apply_change(P, k, s_delta, nullptr);
 }
 
-static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs) {
+static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs,
+                              uint32_t* listA = nullptr, uint32_t* listE = nullptr, uint32_t* count = nullptr) {
   const uint64_t n = E->rows;
   const bool two = E->wpr >= 2;
   const uint32_t ntile_j = (uint32_t)(two ? div_up_u64(E->wpr, 2) : 1);
@@ -414,10 +435,18 @@ static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, ui
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, ntiles);
   BIC_PROF(c, KID_DICT_HIST);
-  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr);
-  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr);
+  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count);
+  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
+}
+
+// histogram pass for dict3.cu; the multi-atom row list is built on the side when a warp sees whole rows
+bic_status bic_k_dict_hist_compact(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs,
+                                   uint32_t* listA, uint32_t* listE, uint32_t* count, bool* fused) {
+  *fused = (A->wpr == 1 && E->wpr <= 2);
+  if (*fused) return launch_hist(c, E, A, H, U, hs, listA, listE, count);
+  return launch_hist(c, E, A, H, U, hs);
 }
 
 bic_status bic_k_transpose_A(bic_ctx* c, const bic_mat* A, uint32_t* AT, uint64_t wprN);
@@ -514,8 +543,8 @@ bic_status bic_k_dict_hist_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t 
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, ntiles, nprob);
   BIC_PROF(c, KID_DICT_HIST);
-  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active);
-  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active);
+  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr);
+  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }

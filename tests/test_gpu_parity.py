@@ -96,13 +96,15 @@ FIT_SHAPES = [  # rows, cols, W, K, seed
     (130, 128, 24, 6, 7),       # edge tiles read through into the next raster row
     (64, 64, 4, 3, 8),
     (97, 45, 5, 4, 9),
+    (300, 280, 8, 40, 10),      # two coefficient words per row, still inside the cluster chain's shared-memory budget
+    (256, 256, 16, 48, 11),     # ditto with 8-word residual rows (list built by the separate compaction kernel)
 ]
 
 
-@pytest.mark.parametrize("dict_algo", [1, 0])
+@pytest.mark.parametrize("dict_algo", [2, 1, 0])
 @pytest.mark.parametrize("rows,cols,W,K,seed", FIT_SHAPES)
 def test_fit_vs_oracle(ctx, oracle, synth, rows, cols, W, K, seed, dict_algo):
-    ctx.set_option("dict_algo", dict_algo)  # 1: histogram-first resolve (default), 0: per-atom walk
+    ctx.set_option("dict_algo", dict_algo)  # 2: cluster chain (default), 1: histogram-first resolve, 0: per-atom walk
     page = synth.structured_page(rows, cols, seed=seed, salt=0.01)
     Iw = synth.pack_rows(page)
     m = W * W
@@ -147,10 +149,10 @@ def test_fit_vs_oracle(ctx, oracle, synth, rows, cols, W, K, seed, dict_algo):
     assert np.array_equal(R.download(), Iw)
     for mm in (I, X, D, A, E, R):
         mm.destroy()
-    ctx.set_option("dict_algo", 1)
+    ctx.set_option("dict_algo", 2)
 
 
-@pytest.mark.parametrize("dict_algo", [1, 0])
+@pytest.mark.parametrize("dict_algo", [2, 1, 0])
 def test_matrix_mode_wide_rows(ctx, oracle, synth, dict_algo):
     """-I 0 (rows are the samples, bsvd_test.cpp:101-106) with m = 1100 > 1024: wide-row kernels"""
     ctx.set_option("dict_algo", dict_algo)
@@ -167,7 +169,36 @@ def test_matrix_mode_wide_rows(ctx, oracle, synth, dict_algo):
     it, tr = ctx.learn_model_traditional(X, E, D, A)
     assert it == ito and np.array_equal(tr, tro)
     assert np.array_equal(D.download(), Do) and np.array_equal(A.download(), Ao) and np.array_equal(E.download(), Eo)
-    ctx.set_option("dict_algo", 1)
+    ctx.set_option("dict_algo", 2)
+
+
+@pytest.mark.parametrize("bucket_cap", [-1, 0, 30000])
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_cluster_chain_any_cluster_size(ctx, oracle, synth, cluster, bucket_cap):
+    """dict3.cu's chain kernel with 1..8 CTAs in the cluster (16 is the default), with per-atom buckets
+    (default capacity), without (capacity 0: the list-scan fallback) and with a capacity that some
+    iterations exceed and others do not: same bits"""
+    ctx.set_option("dict_algo", 2)
+    ctx.set_option("chain_cluster", cluster)
+    ctx.set_option("chain_bucket_cap", bucket_cap)
+    try:
+        rng = np.random.default_rng(21)
+        bits = (rng.random((20000, 64)) < 0.3).astype(np.uint8)
+        bits[:, 8:24] |= (rng.random((20000, 1)) < 0.4).astype(np.uint8)
+        Xo = synth.pack_rows(bits)
+        m, K = 64, 32
+        piv, _ = oracle.draw_pivots(Xo, m, K, oracle.rng(9))
+        Do, Ao = oracle.init_neighbor_pivots(Xo, m, K, piv)
+        X = ctx.matrix(20000, m, Xo)
+        D, A, E = ctx.matrix(K, m), ctx.matrix(20000, K), ctx.matrix(20000, m)
+        ctx.initialize_model_neighbor_pivots(X, piv, D, A)
+        Eo, ito, tro = oracle.learn_traditional(Xo, Do, Ao, m, K)
+        it, tr = ctx.learn_model_traditional(X, E, D, A)
+        assert it == ito and np.array_equal(tr, tro)
+        assert np.array_equal(D.download(), Do) and np.array_equal(A.download(), Ao) and np.array_equal(E.download(), Eo)
+    finally:
+        ctx.set_option("chain_cluster", 16)
+        ctx.set_option("chain_bucket_cap", -1)
 
 
 def test_dense_coefficients_many_shared_rows(ctx, oracle, synth):
@@ -179,7 +210,7 @@ def test_dense_coefficients_many_shared_rows(ctx, oracle, synth):
     Xo = synth.pack_rows(bits)
     m, K = 64, 6
     piv, _ = oracle.draw_pivots(Xo, m, K, oracle.rng(3))
-    for algo in (1, 0):
+    for algo in (2, 1, 0):
         ctx.set_option("dict_algo", algo)
         Do, Ao = oracle.init_neighbor_pivots(Xo, m, K, piv)
         X = ctx.matrix(4000, m, Xo)
@@ -189,7 +220,7 @@ def test_dense_coefficients_many_shared_rows(ctx, oracle, synth):
         it, tr = ctx.learn_model_traditional(X, E, D, A)
         assert it == ito and np.array_equal(tr, tro)
         assert np.array_equal(D.download(), Do) and np.array_equal(A.download(), Ao) and np.array_equal(E.download(), Eo)
-    ctx.set_option("dict_algo", 1)
+    ctx.set_option("dict_algo", 2)
 
 
 @pytest.mark.parametrize("W,K,rows,cols", [(8, 32, 320, 256), (16, 64, 256, 320), (32, 40, 256, 256), (8, 5, 200, 184)])
