@@ -39,6 +39,23 @@ __device__ __forceinline__ uint32_t golomb_k(uint64_t t64, uint64_t bits_consume
   return k;
 }
 
+// Is k the same for every sample of a 128-bit stretch? Sample ranks run over [t, t + 127] and the sums
+// over [acc, acc + 128] (acc = consumed - t never decreases and grows by the zeros passed). If
+// (t << k) >= acc + 128 and ((t + 127) << (k - 1)) < acc, with no 32-bit wrap anywhere, every sample of the
+// stretch takes the k of the first: the coder's adaptation is far slower than one thread's four words once
+// a few thousand samples are in, so the per-sample search runs once per thread instead of once per sample.
+__device__ __forceinline__ bool golomb_k_stable(uint64_t t, uint64_t consumed, uint32_t* kout) {
+  if (t == 0 || t + 128 >= (1ull << 31)) return false;
+  const uint64_t acc = consumed - t;
+  if (acc + 128 >= (1ull << 31)) return false;
+  const uint32_t k = golomb_k(t, consumed);
+  if (((t + 127) << k) >= (1ull << 32)) return false;
+  if ((t << k) < acc + 128) return false;
+  if (k > 0 && ((t + 127) << (k - 1)) >= acc) return false;
+  *kout = k;
+  return true;
+}
+
 __device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long* total,
                                                                   unsigned long long* s_warp /* 8 */) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -319,23 +336,39 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
   // (MODE 1) reads them back instead of walking the samples twice
   unsigned long long mybits = 0;
   const uint64_t tslot = (uint64_t)blockIdx.x * TILE_THREADS + threadIdx.x;
+  const long long tb = (long long)(w0 * 32) + gb.pos0;  // global position of this thread's first bit
   if (MODE == 0) {
     unsigned long long t = rank0;
     long long pv = prev;
+    bool first = true, fast = false;
+    uint32_t kc = 0, lpv = 0, fastbits = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t b = v[i];
       while (b) {
         const int p = __clz(b);
         b &= ~(0x80000000u >> p);
-        const long long pos = (long long)((w0 + i) * 32 + p) + gb.pos0;
+        const uint32_t lp = (uint32_t)(i * 32 + p);
+        if (fast) {                       // k is kc for the rest of this thread's samples (golomb_k_stable)
+          const uint32_t x = lp - lpv - 1;
+          fastbits += kc + 1 + (x >> kc);
+          lpv = lp;
+          continue;
+        }
+        const long long pos = tb + lp;
         const unsigned long long x = (unsigned long long)(pos - pv - 1);
         const uint32_t k = golomb_k(t, (unsigned long long)(pv + 1));
         mybits += k + (x >> k) + 1;
         pv = pos;
         ++t;
+        if (first) {
+          first = false;
+          fast = golomb_k_stable(t, (unsigned long long)(pv + 1), &kc);
+          lpv = lp;
+        }
       }
     }
+    mybits += fastbits;
     g.tbits[tslot] = mybits;
   } else {
     mybits = g.tbits[tslot];
@@ -363,13 +396,40 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
   unsigned long long t = rank0;
   const unsigned long long cmask = (unsigned long long)chunk - 1;  // chunk is a power of two
   const int clog = 31 - __clz(chunk);
+  bool first = true, fast = false;
+  uint32_t kc = 0, lpv = 0, ob = 0, tl = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint32_t b = v[i];
     while (b) {
       const int p = __clz(b);
       b &= ~(0x80000000u >> p);
-      const long long pos = (long long)((w0 + i) * 32 + p) + gb.pos0;
+      const uint32_t lp = (uint32_t)(i * 32 + p);
+      if (fast) {
+        // staged tile, k = kc for the rest of this thread's samples: 32-bit arithmetic relative to the
+        // thread's first bit (lp, lpv) and to the staged range (ob)
+        const uint32_t x = lp - lpv - 1;
+        if ((tl & (uint32_t)cmask) == 0) {
+          const unsigned long long slot = (t >> clog) - gb.chunk0;
+          index[2 * slot] = base + ob - gb.out0 + gb.code0;
+          index[2 * slot + 1] = (unsigned long long)(tb + lpv + 1);
+        }
+        const uint32_t rem = x & ((1u << kc) - 1);
+        if (rem) {
+          const unsigned long long v64 = (unsigned long long)rem << (64 - (ob & 31) - kc);
+          const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
+          if (hi) atomicOr(&s_out[ob >> 5], hi);
+          if (lo) atomicOr(&s_out[(ob >> 5) + 1], lo);
+        }
+        const uint32_t sb = ob + kc + (x >> kc);
+        atomicOr(&s_out[sb >> 5], 0x80000000u >> (sb & 31));
+        ob = sb + 1;
+        lpv = lp;
+        ++tl;
+        ++t;
+        continue;
+      }
+      const long long pos = tb + lp;
       const unsigned long long x = (unsigned long long)(pos - prev - 1);
       const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
       if ((t & cmask) == 0) {
@@ -396,6 +456,15 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
       o = stop + 1;
       prev = pos;
       ++t;
+      if (first) {
+        first = false;
+        if (staged) {
+          fast = golomb_k_stable(t, (unsigned long long)(prev + 1), &kc);
+          lpv = lp;
+          ob = (uint32_t)(o - base);
+          tl = (uint32_t)t;
+        }
+      }
     }
   }
   if (staged) {
