@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restri
                                                         uint64_t wprE, uint64_t wprA, uint64_t hs, uint32_t ntile_j,
                                                         const ProbDev* __restrict__ probs, const uint32_t* __restrict__ active,
                                                         uint32_t* __restrict__ listA, uint32_t* __restrict__ listE,
-                                                        uint32_t* __restrict__ list_count) {
+                                                        uint32_t* __restrict__ list_count, uint32_t* __restrict__ hcount) {
   if (probs) {  // batched launch: blockIdx.z selects the problem
     if (!active[blockIdx.z]) return;
     const ProbDev pr = probs[blockIdx.z];
@@ -40,11 +40,13 @@ __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restri
   }
   __shared__ uint32_t s_acc[32 * JW * 32];
   __shared__ uint32_t s_u[32];
+  __shared__ uint32_t s_h[32];
+  uint32_t hcnt = 0;
   const int lane = threadIdx.x & 31;
   const uint32_t kw = blockIdx.y / ntile_j, jt = blockIdx.y - kw * ntile_j;
   const uint64_t jw0 = (uint64_t)jt * JW;
   for (int i = threadIdx.x; i < 32 * JW * 32; i += blockDim.x) s_acc[i] = 0;
-  if (threadIdx.x < 32) s_u[threadIdx.x] = 0;
+  if (threadIdx.x < 32) { s_u[threadIdx.x] = 0; s_h[threadIdx.x] = 0; }
   __syncthreads();
   uint32_t acc[32][JW];
 #pragma unroll
@@ -101,6 +103,9 @@ __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restri
           for (int w = 0; w < JW; ++w)
             if ((uint64_t)w < wprE) listE[pos * wprE + w] = e[w];
         }
+        // bucket sizes of the chain: per atom, the rows that use it and a later atom (a & (a - 1) drops
+        // the row's last atom, the lowest-valued set bit in MSB-first order)
+        hcnt += __popc(warp_transpose32(a & (a - 1)));
       }
     }
     if (!__any_sync(0xffffffffu, a != 0)) continue;  // none of these 32 rows uses these 32 atoms
@@ -123,6 +128,7 @@ __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restri
     for (int w = 0; w < JW; ++w)
       if (acc[k][w]) atomicAdd(&s_acc[(k * JW + w) * 32 + lane], acc[k][w]);
   if (jt == 0 && ucnt) atomicAdd(&s_u[lane], ucnt);
+  if (hcnt) atomicAdd(&s_h[lane], hcnt);
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * JW * 32; i += blockDim.x) {
     const uint32_t v = s_acc[i];
@@ -132,6 +138,7 @@ __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restri
     }
   }
   if (jt == 0 && threadIdx.x < 32 && s_u[threadIdx.x]) atomicAdd(&U[kw * 32 + threadIdx.x], s_u[threadIdx.x]);
+  if (hcount && threadIdx.x < 32 && s_h[threadIdx.x]) atomicAdd(&hcount[threadIdx.x], s_h[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------ pass 2
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(256) k_dict_fix(ResolveParams P) {
 }
 
 static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs,
-                              uint32_t* listA = nullptr, uint32_t* listE = nullptr, uint32_t* count = nullptr) {
+                              uint32_t* listA = nullptr, uint32_t* listE = nullptr, uint32_t* count = nullptr, uint32_t* hcount = nullptr) {
   const uint64_t n = E->rows;
   const bool two = E->wpr >= 2;
   const uint32_t ntile_j = (uint32_t)(two ? div_up_u64(E->wpr, 2) : 1);
@@ -435,17 +442,17 @@ static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, ui
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, ntiles);
   BIC_PROF(c, KID_DICT_HIST);
-  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count);
-  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count);
+  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count, hcount);
+  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count, hcount);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }
 
 // histogram pass for dict3.cu; the multi-atom row list is built on the side when a warp sees whole rows
 bic_status bic_k_dict_hist_compact(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs,
-                                   uint32_t* listA, uint32_t* listE, uint32_t* count, bool* fused) {
+                                   uint32_t* listA, uint32_t* listE, uint32_t* count, uint32_t* hcount, bool* fused) {
   *fused = (A->wpr == 1 && E->wpr <= 2);
-  if (*fused) return launch_hist(c, E, A, H, U, hs, listA, listE, count);
+  if (*fused) return launch_hist(c, E, A, H, U, hs, listA, listE, count, hcount);
   return launch_hist(c, E, A, H, U, hs);
 }
 
@@ -543,8 +550,8 @@ bic_status bic_k_dict_hist_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t 
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, ntiles, nprob);
   BIC_PROF(c, KID_DICT_HIST);
-  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr);
-  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr);
+  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr, nullptr);
+  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr, nullptr);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }

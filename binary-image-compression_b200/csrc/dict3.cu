@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k_dict_bucket_count(const uint32_t* __res
 
 // bucket contents. A CTA takes chunks of the list; per chunk it counts its rows per atom in shared memory, reserves
 // its range of every bucket with one global atomic per atom, and writes the row indices.
-static const int FILL_CHUNK = 2048;
+static const int FILL_CHUNK = 1024;
 __global__ void __launch_bounds__(256) k_dict_bucket_fill(const uint32_t* __restrict__ listA, const uint32_t* __restrict__ count,
                                                           const uint32_t* __restrict__ hcount, uint32_t* __restrict__ cursor,
                                                           uint32_t* __restrict__ bucket, uint32_t bucket_cap, uint32_t wprA, uint32_t p) {
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256) k_dict_compact(const uint32_t* __restrict
 }
 
 bic_status bic_k_dict_hist_compact(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs,
-                                   uint32_t* listA, uint32_t* listE, uint32_t* count, bool* fused);
+                                   uint32_t* listA, uint32_t* listE, uint32_t* count, uint32_t* hcount, bool* fused);
 
 // cluster size to launch with: the context's choice, but 16 (a non-portable size) only where the device can
 // actually co-schedule such a cluster with the kernel's shared-memory footprint
@@ -488,18 +488,20 @@ bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const 
   uint32_t* bucket = listE + (size_t)n * wprE;
   BIC_CUDA(c, cudaMemsetAsync(H, 0, zero_words * 4, c->stream));
   bool fused = false;
-  BIC_TRY(bic_k_dict_hist_compact(c, E, A, H, U, hs, listA, listE, count, &fused));
+  BIC_TRY(bic_k_dict_hist_compact(c, E, A, H, U, hs, listA, listE, count, hcount, &fused));
   if (!fused) {
     const int grid = bic_grid_for(c, n, 256, 8);
     BIC_PROF(c, KID_DICT_COMPACT);
     k_dict_compact<<<grid, 256, 0, c->stream>>>(E->d, A->d, listA, listE, count, n, (uint32_t)wprE, (uint32_t)wprA);
     BIC_LAUNCH_CHECK(c);
   }
-  {
+  if (!fused) {  // the fused histogram pass counted the buckets as well
     const int grid = bic_grid_for(c, n, 256, 2);
     BIC_PROF(c, KID_DICT_BUCKET);
     k_dict_bucket_count<<<grid, 256, (size_t)wprA * 32 * 4, c->stream>>>(listA, count, hcount, (uint32_t)wprA, (uint32_t)p);
     BIC_LAUNCH_CHECK(c);
+  }
+  {
     const int grid2 = bic_grid_for(c, div_up_u64(n, FILL_CHUNK) * 256, 256, 4);
     BIC_PROF(c, KID_DICT_BUCKET);
     k_dict_bucket_fill<<<grid2, 256, (size_t)(p + 1 + 2 * wprA * 32) * 4, c->stream>>>(listA, count, hcount, cursor, bucket,

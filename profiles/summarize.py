@@ -49,8 +49,9 @@ if rep.exists():
     want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum",
             "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-            "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_alu.sum",
-            "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+            "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
             "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum"]
     idx = [(w, hdr.index(w)) for w in want if w in hdr]
     seen = collections.Counter()
@@ -65,3 +66,24 @@ if rep.exists():
                 continue  # a few launches per kernel are enough
             wr.writerow([(r[i].split("(")[0] if w == "Kernel Name" else r[i]) for w, i in idx])
     print("wrote", out / f"{tag}_top_kernels.csv")
+    # DRAM traffic per launch of the kernel with the largest summed duration (bench.py's roofline.traffic)
+    import json
+    ki = hdr.index("Kernel Name")
+    di, ri, wi = hdr.index("gpu__time_duration.sum"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = collections.defaultdict(lambda: [0.0, 0.0, 0])
+    for r in data:
+        name = r[ki].split("(")[0].replace("void ", "").split("<")[0]
+        if not name.startswith("k_"):
+            continue
+        tot[name][0] += float(r[di])
+        tot[name][1] += float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
+        tot[name][2] += 1
+    if tot:
+        dom = max(tot.items(), key=lambda kv: kv[1][0])
+        (out / "dominant_kernel_traffic.json").write_text(json.dumps({
+            "kernel": dom[0], "workload": "8192x8192/8/32", "dram_bytes_per_launch": dom[1][1] / dom[1][2],
+            "launches_captured": dom[1][2],
+            "source": f"profiles/{tag}_top_kernels.csv (ncu --set full of profiles/profile_target.py; dram__bytes_read.sum + "
+                      "dram__bytes_write.sum, mean over the captured launches of the kernel with the largest summed duration)"}, indent=1))
+        print("dominant", dom[0], dom[1])
