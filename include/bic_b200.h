@@ -61,10 +61,15 @@ int bic_ctx_sm_count(bic_ctx* ctx);
 /* make `waiter`'s stream wait for everything queued so far on `signal`'s stream (for callers
  * that run several contexts -- one per independent page -- concurrently) */
 bic_status bic_ctx_wait_ctx(bic_ctx* waiter, bic_ctx* signal);
-/* tuning switches. "dict_algo": 1 (default) = all atom histograms in one pass, then an in-order
- * resolve with a grid barrier only for atoms that change; 0 = one barrier per atom. Same results.
+/* tuning switches (every setting gives the same bits).
+ * "dict_algo": how update_dictionary_steepest walks the atoms. 2 (default) = all atom histograms in one pass, then the
+ *   in-order atom chain inside ONE thread-block cluster (dict3.cu) where the histograms fit shared memory, else 1;
+ *   1 = same histograms, one launch per atom that changes (dict2.cu); 0 = one grid barrier per atom (dict.cu).
+ * "chain_cluster": CTAs in dict3.cu's cluster, 1/2/4/8/16 (default 16, 8 where 16 cannot be co-scheduled).
+ * "chain_bucket_cap": entries of dict3.cu's per-atom row buckets, -1 (default) = 2 per row; 0 = always scan the list.
+ * "gol_onepass": 1 = single-pass Golomb encoder with decoupled look-back, 0 (default) = counts / lengths / scatter.
  * "wait_mode": how the calling thread waits for results: 0 (default) cudaStreamSynchronize, 1 poll + sched_yield
- * (many contexts / several ranks per box), 2 blocking event. */
+ *   (many contexts / several ranks per box), 2 blocking event. */
 bic_status bic_ctx_set_option(bic_ctx* ctx, const char* name, int64_t value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t bic_ctx_launch_count(bic_ctx* ctx);
