@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         "bic_mat_download_pbm": [_vp, _vp, _u8p],
         "bic_mat_clear": [_vp, _vp],
         "bic_mat_copy": [_vp, _vp, _vp],
+        "bic_mat_copy_rows": [_vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64],
         "bic_mat_weight": [_vp, _vp, _u64p],
         "bic_mat_dist": [_vp, _vp, _vp, _u64p],
         "bic_mat_xor": [_vp, _vp, _vp, _vp],
@@ -211,6 +212,9 @@ class Matrix:
 
     def copy_from(self, other: "Matrix"):
         self.ctx._ck(self.ctx.L.bic_mat_copy(self.ctx.h, other.h, self.h))
+
+    def copy_rows_from(self, other: "Matrix", src_row0: int, nrows: int, dst_row0: int):
+        self.ctx._ck(self.ctx.L.bic_mat_copy_rows(self.ctx.h, other.h, src_row0, nrows, self.h, dst_row0))
 
     def weight(self) -> int:
         w = _u64(0)
@@ -348,9 +352,9 @@ class Context:
         return Stream(self)
 
     # ---- bsvd path (names as in src/bsvd.h / src/bsvd_test.cpp)
-    def extract_patches(self, raster: Matrix, W: int) -> Matrix:
+    def extract_patches(self, raster: Matrix, W: int, out: "Matrix | None" = None) -> Matrix:
         n = ((raster.rows + W - 1) // W) * ((raster.cols + W - 1) // W)
-        X = Matrix(self, n, W * W)
+        X = out if out is not None else Matrix(self, n, W * W)
         self._ck(self.L.bic_extract_patches(self.h, raster.h, W, X.h))
         return X
 

@@ -351,6 +351,19 @@ extern "C" bic_status bic_mat_copy(bic_ctx* c, const bic_mat* src, bic_mat* dst)
   return BIC_OK;
 }
 
+// rows [src_row0, src_row0 + nrows) of src -> rows [dst_row0, ...) of dst (same number of columns): the row-wise half of
+// set_submatrix / copy_submatrix_to (src/binmat.cpp:267-298, 373-414) that stacking patch matrices needs
+extern "C" bic_status bic_mat_copy_rows(bic_ctx* c, const bic_mat* src, uint64_t src_row0, uint64_t nrows, bic_mat* dst,
+                                        uint64_t dst_row0) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
+  if (!c || !src || !dst || src->cols != dst->cols || src_row0 + nrows > src->rows || dst_row0 + nrows > dst->rows)
+    return BIC_ERR_INVALID;
+  if (nrows == 0) return BIC_OK;
+  BIC_CUDA(c, cudaMemcpyAsync(dst->d + dst_row0 * dst->wpr, src->d + src_row0 * src->wpr, (size_t)nrows * src->wpr * 4,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  return BIC_OK;
+}
+
 // popcount reductions: weight(A) and dist(A,B) = weight(A xor B)
 __global__ void k_weight(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint64_t nwords,
                          unsigned long long* out) {

@@ -103,6 +103,10 @@ bic_status bic_mat_upload_pbm(bic_ctx* ctx, bic_mat* m, const uint8_t* payload);
 bic_status bic_mat_download_pbm(bic_ctx* ctx, const bic_mat* m, uint8_t* payload);
 bic_status bic_mat_clear(bic_ctx* ctx, bic_mat* m);                       /* clear(), src/binmat.cpp:165-168 */
 bic_status bic_mat_copy(bic_ctx* ctx, const bic_mat* src, bic_mat* dst);  /* copy_to, src/binmat.cpp:195-197 */
+/* rows [src_row0, src_row0+nrows) of src -> rows [dst_row0, ...) of dst; equal column counts
+ * (row-wise set_submatrix / copy_submatrix_to, src/binmat.cpp:267-298, 373-414) */
+bic_status bic_mat_copy_rows(bic_ctx* ctx, const bic_mat* src, uint64_t src_row0, uint64_t nrows, bic_mat* dst,
+                             uint64_t dst_row0);
 bic_status bic_mat_weight(bic_ctx* ctx, const bic_mat* m, uint64_t* w);   /* weight(), src/binmat.cpp:57-67 */
 bic_status bic_mat_dist(bic_ctx* ctx, const bic_mat* a, const bic_mat* b, uint64_t* d); /* dist, :499-512 */
 bic_status bic_mat_xor(bic_ctx* ctx, const bic_mat* a, const bic_mat* b, bic_mat* c);   /* add, :463-478 */
