@@ -462,3 +462,257 @@ int bo_eg_decode_matrix(const uint8_t* in, uint64_t nbits_in, uint64_t rows, uin
   }
   return br.pos == nbits_in ? 0 : -3;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * MDL model selection: model_codelength src/bsvd.cpp:1438-1461 over
+ * universal_codelength src/coding.cpp:24-32; learn_model_mdl_forward_selection :1463-1546,
+ * learn_model_mdl_backward_selection :1548-1660, learn_model_mdl_full_search :1662-1717.
+ * The inner learner is learn_model_traditional and the initialiser initialize_model_neighbor
+ * (the reference's defaults, learn_model_setup(0,0,0,*,0)). The only floating point on the
+ * path: double log2 on the host, truncated into idx_t at every accumulation, as the reference
+ * does it.
+ * ------------------------------------------------------------------------------------------ */
+#include <math.h>
+
+/* src/coding.cpp:24-32; the parameters are `unsigned` there, so 64-bit counts wrap to 32 bits */
+double bo_universal_codelength(unsigned n, unsigned r) {
+  const double p1 = (double)r / (double)n;
+  if ((r > 0) && (r < n)) {
+    return (double)n * (-p1 * log2(p1) - (1.0 - p1) * log2(1.0 - p1)) + 0.5 * log2(n);
+  } else {
+    return 0.5 * log2(n);
+  }
+}
+
+static uint64_t col_weight(const bo_word* A, uint64_t n, uint64_t p, uint64_t k) {
+  const uint64_t apr = bo_wpr(p);
+  uint64_t w = 0;
+  for (uint64_t i = 0; i < n; ++i) w += (A[i * apr + (k >> 6)] >> (63 - (k & 63))) & 1u;
+  return w;
+}
+
+/* src/bsvd.cpp:1438-1461. LE, LD, LA are idx_t: `LD += double` converts the sum back to an
+ * integer (truncation) after every atom. */
+uint64_t bo_model_codelength(const bo_word* E, const bo_word* D, const bo_word* A,
+                             uint64_t n, uint64_t m, uint64_t p) {
+  const uint64_t wpr = bo_wpr(m);
+  uint64_t LE = (uint64_t)bo_universal_codelength((unsigned)(n * m), (unsigned)bo_weight(E, n, m));  /* :1449 */
+  uint64_t LD = 0, LA = 0;
+  for (uint64_t k = 0; k < p; ++k) {                                                                  /* :1451-1456 */
+    LD = (uint64_t)((double)LD + bo_universal_codelength((unsigned)m, (unsigned)bo_weight(D + k * wpr, 1, m)));
+    LA = (uint64_t)((double)LA + bo_universal_codelength((unsigned)n, (unsigned)col_weight(A, n, p, k)));
+  }
+  return LE + LD + LA;
+}
+
+struct bo_mdl_result { uint64_t p, n, m, bestL; bo_word *D, *A; };
+
+static bo_word* mat_alloc(uint64_t rows, uint64_t cols) {
+  const uint64_t w = rows * bo_wpr(cols);
+  return (bo_word*)calloc(w ? w : 1, sizeof(bo_word));
+}
+static bo_word* mat_dup(const bo_word* M, uint64_t rows, uint64_t cols) {
+  bo_word* r = mat_alloc(rows, cols);
+  memcpy(r, M, rows * bo_wpr(cols) * sizeof(bo_word));
+  return r;
+}
+static int mget(const bo_word* M, uint64_t cols, uint64_t i, uint64_t j) {
+  return (int)((M[i * bo_wpr(cols) + (j >> 6)] >> (63 - (j & 63))) & 1u);
+}
+static void mset(bo_word* M, uint64_t cols, uint64_t i, uint64_t j, int b) {
+  const bo_word mask = (bo_word)1 << (63 - (j & 63));
+  bo_word* w = M + i * bo_wpr(cols) + (j >> 6);
+  *w = b ? (*w | mask) : (*w & ~mask);
+}
+/* A (n x p) -> n x (p+1) with `col` (n x 1) appended (set_submatrix(0,0,A); set_submatrix(0,p,col), :1513-1516) */
+static bo_word* append_col(const bo_word* A, uint64_t n, uint64_t p, const bo_word* col) {
+  bo_word* R = mat_alloc(n, p + 1);
+  for (uint64_t i = 0; i < n; ++i) {
+    for (uint64_t j = 0; j < p; ++j) if (mget(A, p, i, j)) mset(R, p + 1, i, j, 1);
+    if (mget(col, 1, i, 0)) mset(R, p + 1, i, p, 1);
+  }
+  return R;
+}
+/* column k removed (:1605-1616) */
+static bo_word* delete_col(const bo_word* A, uint64_t n, uint64_t p, uint64_t k) {
+  bo_word* R = mat_alloc(n, p - 1);
+  for (uint64_t i = 0; i < n; ++i)
+    for (uint64_t j = 0, o = 0; j < p; ++j) {
+      if (j == k) continue;
+      if (mget(A, p, i, j)) mset(R, p - 1, i, o, 1);
+      ++o;
+    }
+  return R;
+}
+
+static struct bo_mdl_result* mdl_result(uint64_t n, uint64_t m, uint64_t p, uint64_t bestL, bo_word* D, bo_word* A) {
+  struct bo_mdl_result* r = (struct bo_mdl_result*)malloc(sizeof(*r));
+  r->p = p; r->n = n; r->m = m; r->bestL = bestL; r->D = D; r->A = A;
+  return r;
+}
+void bo_mdl_result_info(const struct bo_mdl_result* r, uint64_t* p, uint64_t* bestL) { *p = r->p; *bestL = r->bestL; }
+void bo_mdl_result_copy(const struct bo_mdl_result* r, bo_word* D, bo_word* A) {
+  if (r->p) {
+    memcpy(D, r->D, r->p * bo_wpr(r->m) * sizeof(bo_word));
+    memcpy(A, r->A, r->n * bo_wpr(r->p) * sizeof(bo_word));
+  }
+}
+void bo_mdl_result_free(struct bo_mdl_result* r) { free(r->D); free(r->A); free(r); }
+
+/* learn_model_mdl_forward_selection, src/bsvd.cpp:1463-1546. D, A: the initialised model with p atoms (left
+ * untouched; the result carries the selected model); E receives the residual of the selected model. */
+struct bo_mdl_result* bo_learn_mdl_forward(const bo_word* X, bo_word* E, const bo_word* D_in, const bo_word* A_in,
+                                           uint64_t n, uint64_t m, uint64_t p, bo_rand48* rng) {
+  const uint64_t wpr = bo_wpr(m);
+  uint64_t K = p;
+  bo_word* D = mat_dup(D_in, K, m);
+  bo_word* A = mat_dup(A_in, n, K);
+  bo_learn_traditional(X, E, D, A, n, m, K, NULL, 0);                 /* :1470 */
+  bo_word* nextAtom = mat_alloc(1, m);
+  bo_word* nextCoefs = mat_alloc(n, 1);
+  bo_word *currD = mat_dup(D, K, m), *currA = mat_dup(A, n, K), *currE = mat_dup(E, n, m);  /* :1473 */
+  uint64_t bestK = K;
+  uint64_t bestL = bo_model_codelength(E, D, A, n, m, K);             /* :1476 */
+  uint64_t stuck = 0, sumStuck = 0, allStuck = 0;
+  do {
+    const int dev = allStuck > 0 ? (int)(sumStuck / allStuck) : 0;    /* :1486 */
+    bo_init_neighbor(currE, n, m, 1, rng, nextAtom, nextCoefs);       /* initialize_model(currE,nextAtom,nextCoefs), :1488 */
+    bo_word* nD = mat_alloc(K + 1, m);                                /* :1499-1506 */
+    memcpy(nD, currD, K * wpr * sizeof(bo_word));
+    memcpy(nD + K * wpr, nextAtom, wpr * sizeof(bo_word));
+    free(currD);
+    currD = nD;
+    bo_word* nA = append_col(currA, n, K, nextCoefs);                 /* :1508-1516 */
+    free(currA);
+    currA = nA;
+    bo_learn_traditional(X, currE, currD, currA, n, m, K + 1, NULL, 0);  /* :1518 */
+    const uint64_t currL = bo_model_codelength(currE, currD, currA, n, m, K + 1);
+    if ((currL + (uint64_t)(int64_t)dev) < bestL) {                   /* :1520 */
+      stuck = 0;
+      bestL = currL;
+      free(D); free(A);
+      D = mat_dup(currD, K + 1, m);
+      A = mat_dup(currA, n, K + 1);
+      memcpy(E, currE, n * wpr * sizeof(bo_word));
+      bestK = K + 1;
+    } else {
+      stuck++;
+      allStuck++;
+      sumStuck += (currL - bestL);
+      if (stuck >= 10) break;                                         /* :1532-1535 */
+    }
+    K++;
+  } while (stuck < 10);
+  free(currD); free(currA); free(currE); free(nextAtom); free(nextCoefs);
+  return mdl_result(n, m, bestK, bestL, D, A);
+}
+
+/* learn_model_mdl_backward_selection, src/bsvd.cpp:1548-1660 */
+struct bo_mdl_result* bo_learn_mdl_backward(const bo_word* X, bo_word* E, const bo_word* D_in, const bo_word* A_in,
+                                            uint64_t n, uint64_t m, uint64_t p) {
+  const uint64_t wpr = bo_wpr(m);
+  uint64_t K = p;
+  bo_word* D = mat_dup(D_in, K, m);
+  bo_word* A = mat_dup(A_in, n, K);
+  uint64_t outK = K;                                                  /* atoms of (D, A) as handed back */
+  bo_learn_traditional(X, E, D, A, n, m, K, NULL, 0);                 /* :1555 */
+  uint64_t bestL = bo_model_codelength(E, D, A, n, m, K);
+  uint64_t currL = bestL;
+  bo_word *currD = mat_dup(D, K, m), *currA = mat_dup(A, n, K);
+  bo_word *nextD = NULL, *nextA = NULL;
+  bo_word* nextE = mat_alloc(n, m);
+  uint64_t stuck = 0, sumStuck = 0, allStuck = 0;
+  (void)currL;
+  for (; K > 0; K--) {
+    const int dev = allStuck > 0 ? (int)(sumStuck / allStuck) : 0;    /* :1575 */
+    uint64_t nextk = 0;
+    uint64_t nextL = ~(1UL << (sizeof(uint64_t) - 1));                /* :1578 */
+    for (uint64_t k = 0; k < K; k++) {                                /* :1579-1592 */
+      const bo_word* Dk = currD + k * wpr;
+      for (uint64_t i = 0; i < n; ++i) {                              /* nextE = Ak' * Dk xor E */
+        const int a = mget(currA, K, i, k);
+        for (uint64_t b = 0; b < wpr; ++b) nextE[i * wpr + b] = E[i * wpr + b] ^ (a ? Dk[b] : 0);
+      }
+      uint64_t tmpL = bo_model_codelength(nextE, currD, currA, n, m, K);
+      tmpL = (uint64_t)((double)tmpL - bo_universal_codelength((unsigned)m, (unsigned)bo_weight(Dk, 1, m)));
+      tmpL = (uint64_t)((double)tmpL - bo_universal_codelength((unsigned)n, (unsigned)col_weight(currA, n, K, k)));
+      if (tmpL < nextL) { nextL = tmpL; nextk = k; }
+    }
+    free(nextD); free(nextA);
+    nextD = NULL; nextA = NULL;
+    if (K > 1) {                                                      /* :1598-1616 */
+      nextD = mat_alloc(K - 1, m);
+      for (uint64_t k = 0, o = 0; k < K; ++k) {
+        if (k == nextk) continue;
+        memcpy(nextD + o * wpr, currD + k * wpr, wpr * sizeof(bo_word));
+        ++o;
+      }
+      nextA = delete_col(currA, n, K, nextk);
+      bo_learn_traditional(X, nextE, nextD, nextA, n, m, K - 1, NULL, 0);
+      nextL = bo_model_codelength(nextE, nextD, nextA, n, m, K - 1);
+    } else {
+      nextL = bo_model_codelength(nextE, NULL, NULL, n, m, 0);        /* :1618, destroyed (0 x 0) D and A */
+    }
+    if (nextL + (uint64_t)(int64_t)dev < bestL) {                     /* :1621 */
+      if (K == 1) {                                                   /* "Resulted in empty model!", :1623-1629 */
+        free(D); free(A);
+        D = NULL; A = NULL;
+        outK = 0;
+        memcpy(E, X, n * wpr * sizeof(bo_word));
+        break;
+      }
+      stuck = 0;
+      bestL = nextL;
+      free(D); free(A);
+      D = mat_dup(nextD, K - 1, m);
+      A = mat_dup(nextA, n, K - 1);
+      outK = K - 1;
+      memcpy(E, nextE, n * wpr * sizeof(bo_word));
+    } else {
+      stuck++;
+      allStuck++;
+      sumStuck += (nextL - bestL);
+      if (stuck >= 10) break;
+    }
+    free(currD); free(currA);                                         /* :1649-1655 */
+    currD = (K > 1) ? mat_dup(nextD, K - 1, m) : mat_alloc(0, m);
+    currA = (K > 1) ? mat_dup(nextA, n, K - 1) : mat_alloc(n, 0);
+    currL = nextL;
+  }
+  free(currD); free(currA); free(nextD); free(nextA); free(nextE);
+  return mdl_result(n, m, outK, bestL, D, A);
+}
+
+/* learn_model_mdl_full_search, src/bsvd.cpp:1662-1717: dictionary sizes 20, 40, ... <= Kmax, eleven fits each (the
+ * RNG stream simply continues: random_seed is rewritten at :1680 but the generator was seeded on first use). The
+ * matrices kept for a size are those of its LAST fit, the length recorded is the minimum over the last ten. */
+struct bo_mdl_result* bo_learn_mdl_full_search(const bo_word* X, bo_word* E, uint64_t n, uint64_t m, uint64_t Kmax,
+                                               bo_rand48* rng) {
+  const uint64_t wpr = bo_wpr(m);
+  bo_word* candE = mat_alloc(n, m);
+  uint64_t bestL = 1UL << 30, bestk = 0;
+  bo_word *D = NULL, *A = NULL;
+  for (uint64_t k = 20; k <= Kmax; k += 20) {
+    bo_word *candD = mat_alloc(k, m), *candA = mat_alloc(n, k);
+    bo_init_neighbor(X, n, m, k, rng, candD, candA);
+    bo_learn_traditional(X, candE, candD, candA, n, m, k, NULL, 0);
+    uint64_t candL = ~0ull;
+    for (int rep = 0; rep < 10; ++rep) {
+      bo_init_neighbor(X, n, m, k, rng, candD, candA);
+      bo_learn_traditional(X, candE, candD, candA, n, m, k, NULL, 0);
+      const uint64_t L = bo_model_codelength(candE, candD, candA, n, m, k);
+      if (L < candL) candL = L;
+    }
+    if (candL < bestL) {
+      bestL = candL;
+      bestk = k;
+      memcpy(E, candE, n * wpr * sizeof(bo_word));
+      free(D); free(A);
+      D = candD; A = candA;
+    } else {
+      free(candD); free(candA);
+    }
+  }
+  free(candE);
+  return mdl_result(n, m, bestk, bestL, D, A);
+}

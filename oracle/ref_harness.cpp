@@ -32,11 +32,15 @@
 #include "bsvd.h"
 #include "GolombCoder.h"
 #include "eg.h"
+#include "coding.h"
 #undef private
 #undef protected
 #include "gsl/gsl_rng.h"
 
 typedef unsigned long u64;
+
+/* defined in bsvd.cpp:1438 but not declared in bsvd.h */
+idx_t model_codelength(const binary_matrix& E, const binary_matrix& D, const binary_matrix& A);
 
 static void load(binary_matrix& M, const u64* w) {
   if (M.data_blocks) std::memcpy(M.data, w, sizeof(u64) * M.data_blocks);
@@ -282,6 +286,62 @@ u64 ref_fit_timed(const u64* I_words, u64 rows, u64 cols, u64 W, u64 K, long see
   if (E_words) store(E, E_words);
   I.destroy(); X.destroy(); D.destroy(); A.destroy(); E.destroy();
   return iter;
+}
+
+/* universal_codelength: coding.cpp:24-32 */
+double ref_universal_codelength(unsigned n, unsigned r) { return universal_codelength(n, r); }
+
+/* model_codelength: bsvd.cpp:1438-1461 */
+u64 ref_model_codelength(const u64* E_words, const u64* D_words, const u64* A_words, u64 n, u64 m, u64 p) {
+  binary_matrix E(n, m), D(p, m), A(n, p);
+  load(E, E_words); load(D, D_words); load(A, A_words);
+  const u64 L = model_codelength(E, D, A);
+  E.destroy(); D.destroy(); A.destroy();
+  return L;
+}
+
+/* The MDL learners: learn_model_mdl_forward_selection bsvd.cpp:1463-1546 (lm = 4), _backward_selection :1548-1660
+ * (lm = 5), _full_search :1662-1717 (lm = 6), with the reference's default plug points (ensure_setup). They resize
+ * D and A, so the result stays in a handle until the caller has sized its buffers. */
+struct ref_mdl_result { binary_matrix D, A; u64 bestL; };
+
+void* ref_learn_mdl(int lm, const u64* X_words, u64* E_words, const u64* D_words, const u64* A_words,
+                    u64 n, u64 m, u64 p, long seed, int reseed) {
+  ensure_setup();
+  binary_matrix X(n, m), E(n, m);
+  load(X, X_words);
+  if (E_words) load(E, E_words);
+  ref_mdl_result* r = new ref_mdl_result;
+  r->D.allocate(p, m);
+  r->A.allocate(n, p);
+  if (D_words) load(r->D, D_words); else r->D.clear();
+  if (A_words) load(r->A, A_words); else r->A.clear();
+  if (reseed) ref_reseed(seed);
+  std::streambuf* old = std::cout.rdbuf();
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf());
+  if (lm == 4) r->bestL = learn_model_mdl_forward_selection(X, E, r->D, r->A);
+  else if (lm == 5) r->bestL = learn_model_mdl_backward_selection(X, E, r->D, r->A);
+  else r->bestL = learn_model_mdl_full_search(X, E, r->D, r->A);
+  std::cout.rdbuf(old);
+  store(E, E_words);
+  X.destroy(); E.destroy();
+  return r;
+}
+void ref_mdl_result_info(void* h, u64* p, u64* bestL) {
+  ref_mdl_result* r = (ref_mdl_result*)h;
+  *p = r->D.get_rows();
+  *bestL = r->bestL;
+}
+void ref_mdl_result_copy(void* h, u64* D_words, u64* A_words) {
+  ref_mdl_result* r = (ref_mdl_result*)h;
+  if (r->D.get_rows()) { store(r->D, D_words); store(r->A, A_words); }
+}
+void ref_mdl_result_free(void* h) {
+  ref_mdl_result* r = (ref_mdl_result*)h;
+  if (r->D.data) r->D.destroy();
+  if (r->A.data) r->A.destroy();
+  delete r;
 }
 
 } /* extern "C" */

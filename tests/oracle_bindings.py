@@ -78,6 +78,52 @@ class Oracle:
         L.bo_eg_encode_matrix.argtypes = [u64p, u64, u64, u8p, u64]
         L.bo_eg_decode_matrix.restype = C.c_int
         L.bo_eg_decode_matrix.argtypes = [u8p, u64, u64, u64, u64p]
+        L.bo_universal_codelength.restype = C.c_double
+        L.bo_universal_codelength.argtypes = [C.c_uint, C.c_uint]
+        L.bo_model_codelength.restype = u64
+        L.bo_model_codelength.argtypes = [u64p, u64p, u64p, u64, u64, u64]
+        L.bo_learn_mdl_forward.restype = C.c_void_p
+        L.bo_learn_mdl_forward.argtypes = [u64p, u64p, u64p, u64p, u64, u64, u64, C.POINTER(Rand48)]
+        L.bo_learn_mdl_backward.restype = C.c_void_p
+        L.bo_learn_mdl_backward.argtypes = [u64p, u64p, u64p, u64p, u64, u64, u64]
+        L.bo_learn_mdl_full_search.restype = C.c_void_p
+        L.bo_learn_mdl_full_search.argtypes = [u64p, u64p, u64, u64, u64, C.POINTER(Rand48)]
+        L.bo_mdl_result_info.argtypes = [C.c_void_p, u64p, u64p]
+        L.bo_mdl_result_copy.argtypes = [C.c_void_p, u64p, u64p]
+        L.bo_mdl_result_free.argtypes = [C.c_void_p]
+
+    # ---- MDL model selection
+    def universal_codelength(self, n, r):
+        return float(self.lib.bo_universal_codelength(n & 0xFFFFFFFF, r & 0xFFFFFFFF))
+
+    def model_codelength(self, E, D, A, m, p):
+        E, D, A = (np.ascontiguousarray(M, np.uint64) for M in (E, D, A))
+        return int(self.lib.bo_model_codelength(_p64(E), _p64(D), _p64(A), E.shape[0], m, p))
+
+    def _mdl_out(self, h, n, m):
+        p, L = u64(0), u64(0)
+        self.lib.bo_mdl_result_info(h, C.byref(p), C.byref(L))
+        p = int(p.value)
+        D = np.zeros((p, wpr(m)), np.uint64)
+        A = np.zeros((n, wpr(p) if p else 0), np.uint64)
+        if p:
+            self.lib.bo_mdl_result_copy(h, _p64(D), _p64(A))
+        self.lib.bo_mdl_result_free(h)
+        return p, int(L.value), D, A
+
+    def learn_mdl(self, lm, X, D, A, m, p, rng):
+        """lm = 4 forward selection, 5 backward selection, 6 full search (the reference's catalog numbers).
+        Returns (E, p_out, bestL, D_out, A_out); D, A (the initialised model) are not modified."""
+        X = np.ascontiguousarray(X, np.uint64)
+        n = X.shape[0]
+        E = np.zeros_like(X)
+        if lm == 4:
+            h = self.lib.bo_learn_mdl_forward(_p64(X), _p64(E), _p64(D), _p64(A), n, m, p, C.byref(rng))
+        elif lm == 5:
+            h = self.lib.bo_learn_mdl_backward(_p64(X), _p64(E), _p64(D), _p64(A), n, m, p)
+        else:
+            h = self.lib.bo_learn_mdl_full_search(_p64(X), _p64(E), n, m, p, C.byref(rng))
+        return (E,) + self._mdl_out(h, n, m)
 
     # ---- fit path -------------------------------------------------------------------------
     def weight(self, M, cols):
@@ -218,6 +264,42 @@ class Reference:
         L.ref_eg.argtypes = [C.POINTER(C.c_int), u8p, u64, u64p]
         L.ref_fit_timed.restype = u64
         L.ref_fit_timed.argtypes = [u64p, u64, u64, u64, u64, C.c_long, C.POINTER(C.c_double), u64p, u64p, u64p]
+        self.has_mdl = hasattr(L, "ref_learn_mdl")
+        if self.has_mdl:
+            L.ref_universal_codelength.restype = C.c_double
+            L.ref_universal_codelength.argtypes = [C.c_uint, C.c_uint]
+            L.ref_model_codelength.restype = u64
+            L.ref_model_codelength.argtypes = [u64p, u64p, u64p, u64, u64, u64]
+            L.ref_learn_mdl.restype = C.c_void_p
+            L.ref_learn_mdl.argtypes = [C.c_int, u64p, u64p, u64p, u64p, u64, u64, u64, C.c_long, C.c_int]
+            L.ref_mdl_result_info.argtypes = [C.c_void_p, u64p, u64p]
+            L.ref_mdl_result_copy.argtypes = [C.c_void_p, u64p, u64p]
+            L.ref_mdl_result_free.argtypes = [C.c_void_p]
+
+    def universal_codelength(self, n, r):
+        return float(self.lib.ref_universal_codelength(n & 0xFFFFFFFF, r & 0xFFFFFFFF))
+
+    def model_codelength(self, E, D, A, m, p):
+        E, D, A = (np.ascontiguousarray(M, np.uint64) for M in (E, D, A))
+        return int(self.lib.ref_model_codelength(_p64(E), _p64(D), _p64(A), E.shape[0], m, p))
+
+    def learn_mdl(self, lm, X, D, A, m, p, seed):
+        """the reference's MDL learner number lm (4, 5, 6) from the initialised model (D, A); the function-static
+        generator is re-seeded with `seed` first. Returns (E, p_out, bestL, D_out, A_out)."""
+        X = np.ascontiguousarray(X, np.uint64)
+        n = X.shape[0]
+        E = np.zeros_like(X)
+        h = self.lib.ref_learn_mdl(lm, _p64(X), _p64(E), _p64(D) if D is not None else None,
+                                   _p64(A) if A is not None else None, n, m, p, seed, 1)
+        pk, L = u64(0), u64(0)
+        self.lib.ref_mdl_result_info(h, C.byref(pk), C.byref(L))
+        pk = int(pk.value)
+        Do = np.zeros((pk, wpr(m)), np.uint64)
+        Ao = np.zeros((n, wpr(pk) if pk else 0), np.uint64)
+        if pk:
+            self.lib.ref_mdl_result_copy(h, _p64(Do), _p64(Ao))
+        self.lib.ref_mdl_result_free(h)
+        return E, pk, int(L.value), Do, Ao
 
     def max_threads(self):
         return int(self.lib.ref_max_threads())
