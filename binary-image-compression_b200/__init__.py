@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
         "bic_update_dictionary_steepest": [_vp, _vp, _vp, _vp, _u64p],
         "bic_residual": [_vp, _vp, _vp, _vp, _vp],
         "bic_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
+        "bic_model_codelength": [_vp, _vp, _vp, _vp, _u64p],
+        "bic_learn_model_mdl": [_vp, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _u64p, _u64p],
         "bic_comm_unique_id": [_u8p],
         "bic_comm_create": [_vp, C.c_int, C.c_int, _u8p, C.POINTER(_vp)],
         "bic_comm_destroy": [_vp, _vp],
@@ -402,6 +404,28 @@ class Context:
                                                     tr.ctypes.data_as(_u64p), trace_cap))
         n = int(it.value)
         return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
+
+    # ---- MDL model selection (src/bsvd.cpp:1438-1717)
+    def model_codelength(self, E: Matrix, D: "Matrix | None", A: "Matrix | None") -> int:
+        L = _u64(0)
+        self._ck(self.L.bic_model_codelength(self.h, E.h, D.h if D is not None else None, A.h if A is not None else None, C.byref(L)))
+        return int(L.value)
+
+    def learn_model_mdl(self, lm: int, X: Matrix, E: Matrix, D: Matrix, A: Matrix, rng_state=None):
+        """lm = 4 forward selection, 5 backward selection, 6 full search. D and A are consumed: their handles are
+        replaced by the selected model's matrices (None, None for the empty model). Returns (bestL, D, A)."""
+        L = _u64(0)
+        dh, ah = _vp(D.h.value), _vp(A.h.value)
+        D.h = A.h = None  # ownership moves into the call
+        self._ck(self.L.bic_learn_model_mdl(self.h, lm, X.h, E.h, C.byref(dh), C.byref(ah),
+                                            C.byref(rng_state) if rng_state is not None else None, C.byref(L)))
+        if not dh.value:
+            return int(L.value), None, None
+        Dn, An = Matrix.__new__(Matrix), Matrix.__new__(Matrix)
+        for M, h in ((Dn, dh), (An, ah)):
+            M.ctx, M.h = self, h
+            M.rows, M.cols = int(self.L.bic_mat_rows(h)), int(self.L.bic_mat_cols(h))
+        return int(L.value), Dn, An
 
     def learn_model_traditional_batched(self, Xs, Es, Ds, As) -> list[int]:
         """independent fits of identical shape, every kernel launched once for the whole batch"""

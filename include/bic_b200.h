@@ -166,6 +166,22 @@ bic_status bic_learn_model_traditional(bic_ctx* ctx, const bic_mat* X, bic_mat* 
 bic_status bic_learn_model_traditional_batched(bic_ctx* ctx, uint32_t nprob, const bic_mat* const* X, bic_mat* const* E,
                                                bic_mat* const* D, bic_mat* const* A, uint64_t* iterations);
 
+/* ---- MDL model selection (the learners that call the fit repeatedly) -----------------------
+ * universal_codelength, src/coding.cpp:24-32 (host arithmetic: double log2 over integer counts) */
+double bic_universal_codelength(unsigned n, unsigned r);
+/* model_codelength, src/bsvd.cpp:1438-1461: |E|, the row weights of D and the column weights of A are reduced on
+ * the device, the description length is the reference's host expression over them. D = A = NULL: the empty model. */
+bic_status bic_model_codelength(bic_ctx* ctx, const bic_mat* E, const bic_mat* D, const bic_mat* A, uint64_t* L);
+/* lm = 4: learn_model_mdl_forward_selection (src/bsvd.cpp:1463-1546), 5: learn_model_mdl_backward_selection (:1548-1660),
+ * 6: learn_model_mdl_full_search (:1662-1717), with initialize_model_neighbor and learn_model_traditional as the
+ * initialiser and inner learner (learn_model_setup(0,0,0,lm,0)). *D (p x m) and *A (n x p) hold the initialised model
+ * on entry (for lm = 6 only the row count of *D is used: the largest dictionary tried) and are REPLACED by newly
+ * created matrices of the selected size (the old ones are destroyed, as the reference destroy()s and allocate()s
+ * them); both are NULL after a backward selection that ends with the empty model. E receives the selected model's
+ * residual. rng_state: the rand48 stream the reference keeps in a function-static (may be NULL for lm = 5). */
+bic_status bic_learn_model_mdl(bic_ctx* ctx, int lm, const bic_mat* X, bic_mat* E, bic_mat** D, bic_mat** A,
+                               uint64_t* rng_state, uint64_t* best_codelength);
+
 /* ---------------------------------------------------------------- several GPUs: rows sharded, D replicated
  * One process per GPU. Every rank holds a contiguous block of the patch rows (its X, E, A); D is
  * replicated. Integer statistics are combined with NCCL (loaded at run time: the libnccl.so.2 already in
