@@ -110,6 +110,22 @@ bic_mat* binary_matrix::device() const {
   return mirror;
 }
 
+bic_mat* binary_matrix::release_device() {
+  bic_mat* m = device();
+  mirror = nullptr;
+  destroy();
+  return m;
+}
+
+void binary_matrix::adopt_device(bic_mat* m) {
+  destroy();
+  if (!m) return;
+  allocate(bic_mat_rows(m), bic_mat_cols(m));
+  mirror = m;
+  dev_newer = true;
+  host_newer = false;
+}
+
 void binary_matrix::pull() const {
   if (mirror) die(bic_mat_download_words64(bic_host_context(), mirror, data), "bic_mat_download_words64");
   dev_newer = false;

@@ -115,6 +115,10 @@ class binary_matrix {
   bic_mat* device() const;
   /** the device copy was written by a kernel: the host words are stale until next read */
   void device_written() const { dev_newer = true; host_newer = false; }
+  /** give up the device mirror (made current first): the caller owns the handle; this matrix is destroy()ed */
+  bic_mat* release_device();
+  /** destroy() + allocate(rows, cols of m) with m as the (newer) device copy; m = nullptr leaves the 0 x 0 matrix */
+  void adopt_device(bic_mat* m);
   /** raw host words in the reference layout (pulls the mirror first) */
   const block_t* host_words() const { want_host(); return data; }
 

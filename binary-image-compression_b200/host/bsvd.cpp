@@ -93,6 +93,40 @@ idx_t learn_model_traditional(binary_matrix& X, binary_matrix& E, binary_matrix&
   return iter;
 }
 
+// ---- MDL model selection (src/bsvd.cpp:1438-1717): the loops run in the library next to the data; D and A change size
+static idx_t learn_mdl(int lm, binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A, const char* what) {
+  if (initialize_model != initialize_model_neighbor || learn_model_inner != learn_model_traditional) {
+    std::cerr << what << ": the B200 build runs it with the neighbor initialisation and the traditional inner learner only" << std::endl;
+    std::exit(-1);
+  }
+  bic_mat* x = X.device();
+  bic_mat* e = E.device();
+  bic_mat* d = D.release_device();
+  bic_mat* a = A.release_device();
+  uint64_t bestL = 0;
+  ck(bic_learn_model_mdl(bic_host_context(), lm, x, e, &d, &a, get_rng(), &bestL), what);
+  E.device_written();
+  D.adopt_device(d);
+  A.adopt_device(a);
+  return bestL;
+}
+idx_t learn_model_mdl_forward_selection(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A) {
+  return learn_mdl(4, X, E, D, A, "learn_model_mdl_forward_selection");
+}
+idx_t learn_model_mdl_backward_selection(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A) {
+  return learn_mdl(5, X, E, D, A, "learn_model_mdl_backward_selection");
+}
+idx_t learn_model_mdl_full_search(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A) {
+  return learn_mdl(6, X, E, D, A, "learn_model_mdl_full_search");
+}
+idx_t model_codelength(const binary_matrix& E, const binary_matrix& D, const binary_matrix& A) {
+  uint64_t L = 0;
+  const bool empty = D.get_rows() == 0;
+  ck(bic_model_codelength(bic_host_context(), E.device(), empty ? nullptr : D.device(), empty ? nullptr : A.device(), &L), "model_codelength");
+  return L;
+}
+double universal_codelength(const unsigned n, const unsigned r) { return bic_universal_codelength(n, r); }
+
 // ---- catalog: same positions and names as src/bsvd.cpp:25-77; null = not provided by this build
 static mi_algorithm_t mi_catalog[] = {initialize_model_neighbor, 0, 0, 0, 0, 0};
 const char* mi_algorithm_names[] = {"Neighbor initialization", "Partition initialization", "Random centroids initialization",
@@ -104,7 +138,8 @@ static du_algorithm_t du_catalog[] = {update_dictionary_steepest, 0, update_dict
 const char* du_algorithm_names[] = {"Steepest descent (a la MOD)  dictionary update", "Proximus-like dictionary update",
                                     "Steepest descent (a la MOD)  dictionary update (OMP)",
                                     "Proximus-like dictionary update (OMP)", 0};
-static ml_algorithm_t lm_catalog[] = {learn_model_traditional, 0, 0, 0, 0, 0, 0, 0};
+static ml_algorithm_t lm_catalog[] = {learn_model_traditional, 0, 0, 0, learn_model_mdl_forward_selection,
+                                      learn_model_mdl_backward_selection, learn_model_mdl_full_search, 0};
 const char* lm_algorithm_names[] = {"Model learning by traditional alternate descent",
                                     "Role-switching learning 1: at each iteration, the role of A and D are switched",
                                     "Role-switched learning 2: after convergence, the role of A and D are switched and traditional model is applied again",
@@ -115,7 +150,7 @@ template <typename T>
 static T pick(T* catalog, int idx, const char* what, const char* const* names) {
   if (!catalog[idx]) {
     std::cerr << what << " '" << names[idx] << "' is not provided by the B200 build (only the reference's deterministic "
-              << "configuration -i 0 -c 0|1 -d 0|2 -l 0 -L 0 is)" << std::endl;
+              << "configuration -i 0 -c 0|1 -d 0|2 -l 0|4|5|6 -L 0 is)" << std::endl;
     std::exit(-1);
   }
   return catalog[idx];

@@ -20,6 +20,15 @@ idx_t update_coefficients_omp(binary_matrix& E, const binary_matrix& D, binary_m
 // src/bsvd.h:71-74 / src/bsvd.cpp:1215-1244
 idx_t learn_model_traditional(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A);
 
+// src/bsvd.h:100-118 / src/bsvd.cpp:1463-1717: MDL model selection around the fit. They resize D and A (destroy + allocate)
+// to the selected number of atoms and return the best description length; an empty model leaves D and A 0 x 0.
+idx_t learn_model_mdl_forward_selection(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A);
+idx_t learn_model_mdl_backward_selection(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A);
+idx_t learn_model_mdl_full_search(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A);
+// src/bsvd.cpp:1438-1461 and src/coding.h / coding.cpp:24-32
+idx_t model_codelength(const binary_matrix& E, const binary_matrix& D, const binary_matrix& A);
+double universal_codelength(const unsigned n, const unsigned r);
+
 typedef void (*mi_algorithm_t)(const binary_matrix& E, binary_matrix& D, binary_matrix& A);
 typedef idx_t (*cu_algorithm_t)(binary_matrix& E, const binary_matrix& D, binary_matrix& A);
 typedef idx_t (*du_algorithm_t)(binary_matrix& E, binary_matrix& D, binary_matrix& A);

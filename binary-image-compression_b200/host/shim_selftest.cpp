@@ -120,6 +120,33 @@ int main() {
     T.destroy();
     X.destroy(); Dd.destroy(); A.destroy(); E.destroy(); E2.destroy();
   }
+  // --- MDL learners through the catalog (src/bsvd.cpp:1463-1660): D and A are resized to the selected model
+  for (int lm : {4, 5}) {
+    learn_model_setup(0, 0, 0, lm, 0);
+    const idx_t W = 8, K = 6, Ny = (W - 1 + rows) / W, Nx = (W - 1 + cols) / W;
+    binary_matrix X(Nx * Ny, W * W), Dd(K, W * W), A(Nx * Ny, K), E(Nx * Ny, W * W), E2(Nx * Ny, W * W);
+    extract_patches(I, W, X);
+    initialize_model(X, Dd, A);
+    const idx_t bestL = learn_model(X, E, Dd, A);
+    CHECK(Dd.get_rows() == A.get_cols());
+    CHECK(Dd.get_rows() == 0 ? A.get_rows() == 0 : A.get_rows() == X.get_rows());  // the empty model is 0 x 0 (src/bsvd.cpp:1623-1629)
+    CHECK(lm == 4 ? Dd.get_rows() >= K : Dd.get_rows() <= K);
+    if (Dd.get_rows() > 0) {
+      CHECK(bestL == model_codelength(E, Dd, A));
+      CHECK(update_coefficients(E, Dd, A) == 0 && update_dictionary(E, Dd, A) == 0);
+      residual(X, A, Dd, E2);
+      CHECK(dist(E, E2) == 0);
+      // the description length from host-side weights (the reference's own loop, src/bsvd.cpp:1449-1456)
+      idx_t LE = universal_codelength(E.get_rows() * E.get_cols(), E.weight()), LD = 0, LA = 0;
+      for (idx_t k = 0; k < Dd.get_rows(); k++) {
+        LD += universal_codelength(Dd.get_cols(), Dd.row_weight(k));
+        LA += universal_codelength(A.get_rows(), A.col_weight(k));
+      }
+      CHECK(bestL == LE + LD + LA);
+    }
+    X.destroy(); Dd.destroy(); A.destroy(); E.destroy(); E2.destroy();
+  }
+  learn_model_setup(0, 0, 0, 0, 0);
   std::cout << "shim selftest ok" << std::endl;
   return 0;
 }

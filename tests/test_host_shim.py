@@ -28,7 +28,9 @@ def test_shim_builds_and_keeps_the_reference_names():
                 "add(binary_matrix const&, binary_matrix const&, binary_matrix&)", "dist(binary_matrix const&, binary_matrix const&)",
                 "mul(binary_matrix const&, bool, binary_matrix const&, bool, binary_matrix&)", "learn_model_setup(int, int, int, int, int)",
                 "initialize_model_neighbor", "update_coefficients_omp", "update_dictionary_steepest", "learn_model_traditional",
-                "initialize_model", "update_coefficients", "update_dictionary", "learn_model", "random_seed", "set_grid_width"]:
+                "initialize_model", "update_coefficients", "update_dictionary", "learn_model", "random_seed", "set_grid_width",
+                "learn_model_mdl_forward_selection", "learn_model_mdl_backward_selection", "learn_model_mdl_full_search",
+                "model_codelength(binary_matrix const&, binary_matrix const&, binary_matrix const&)", "universal_codelength"]:
         assert sym in out, sym
 
 
@@ -48,9 +50,11 @@ def test_shim_selftest_binary():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,W,K,rows,cols", [(1, 8, 32, 400, 328), (1, 16, 24, 300, 260), (0, 0, 12, 200, 150)])
-def test_driver_matches_reference_driver(tmp_path, synth, mode, W, K, rows, cols):
-    """same flags, same PBM -> same dictionary.pbm / coefficients.pbm / residual.pbm bytes"""
+@pytest.mark.parametrize("mode,W,K,rows,cols,lm", [(1, 8, 32, 400, 328, 0), (1, 16, 24, 300, 260, 0), (0, 0, 12, 200, 150, 0),
+                                                    (1, 8, 6, 200, 168, 4), (1, 8, 10, 200, 168, 5), (1, 8, 45, 160, 128, 6)])
+def test_driver_matches_reference_driver(tmp_path, synth, mode, W, K, rows, cols, lm):
+    """same flags, same PBM -> same dictionary.pbm / coefficients.pbm / residual.pbm bytes (-l 4/5/6: the MDL learners,
+    which change the number of atoms)"""
     ref_bin = ROOT / "oracle" / "_ref" / "bsvd_test"
     if not ref_bin.exists():
         pytest.skip("oracle/_ref/bsvd_test not built")
@@ -58,7 +62,7 @@ def test_driver_matches_reference_driver(tmp_path, synth, mode, W, K, rows, cols
     page = synth.structured_page(rows, cols, seed=5, salt=0.01)
     pbm = tmp_path / "in.pbm"
     _write_pbm(pbm, page)
-    flags = ["-I", str(mode), "-k", str(K), "-r", "777", "-m", "0", "-M", "0"] + (["-w", str(W)] if mode else [])
+    flags = ["-I", str(mode), "-k", str(K), "-r", "777", "-m", "0", "-M", "0", "-l", str(lm)] + (["-w", str(W)] if mode else [])
     outs = {}
     for name, exe in (("ref", ref_bin), ("b200", HOST / "bsvd_test_b200")):
         d = tmp_path / name
