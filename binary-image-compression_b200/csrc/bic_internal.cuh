@@ -22,6 +22,7 @@ struct bic_mat {
   uint32_t* d = nullptr;    // device words
   size_t alloc_bytes = 0;
   bool owns = true;
+  bool pooled = false;      // allocated with cudaMallocAsync on its context's stream (library-internal temporaries)
   uint64_t words() const { return rows * wpr; }
 };
 
@@ -153,6 +154,10 @@ struct InitWork {
   uint64_t* piv;
   uint32_t *P, *hist, *usage;
 };
+
+// a matrix from the stream-ordered pool: create and destroy cost no device synchronisation. Only for temporaries that are
+// used and destroyed on ONE context (the one passed here).
+bic_status bic_mat_create_pooled(bic_ctx* ctx, uint64_t rows, uint64_t cols, bic_mat** out);
 
 // ---- cross-TU entry points (implemented next to their kernels) -------------------------------
 bic_status bic_k_row_nonzero_bitmap(bic_ctx* ctx, const bic_mat* X, uint32_t* d_bitmap);

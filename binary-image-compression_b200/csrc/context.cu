@@ -208,9 +208,46 @@ extern "C" bic_status bic_mat_create(bic_ctx* c, uint64_t rows, uint64_t cols, b
   return BIC_OK;
 }
 
+bic_status bic_mat_create_pooled(bic_ctx* c, uint64_t rows, uint64_t cols, bic_mat** out) {
+  *out = nullptr;
+  static bool threshold_set[64] = {false};
+  if (c->device < 64 && !threshold_set[c->device]) {  // keep freed blocks in the pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    threshold_set[c->device] = true;
+  }
+  bic_mat* m = new (std::nothrow) bic_mat();
+  if (!m) return BIC_ERR_NOMEM;
+  m->rows = rows;
+  m->cols = cols;
+  m->wpr = div_up_u64(cols, 32);
+  m->pooled = true;
+  const size_t bytes = (size_t)(m->rows * m->wpr) * 4;
+  m->alloc_bytes = ((bytes + 255) & ~(size_t)255) + 256;
+  if (cudaMallocAsync((void**)&m->d, m->alloc_bytes, c->stream) != cudaSuccess) {
+    cudaGetLastError();
+    delete m;
+    c->err = "cudaMallocAsync failed for matrix";
+    return BIC_ERR_NOMEM;
+  }
+  cudaError_t e = cudaMemsetAsync(m->d, 0, m->alloc_bytes, c->stream);
+  if (e != cudaSuccess) { cudaFreeAsync(m->d, c->stream); delete m; c->err = cudaGetErrorString(e); return BIC_ERR_CUDA; }
+  *out = m;
+  return BIC_OK;
+}
+
 extern "C" bic_status bic_mat_destroy(bic_ctx* c, bic_mat* m) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !m) return BIC_ERR_INVALID;
+  if (m->pooled) {  // stream ordered: everything queued so far on this stream may still use it
+    if (m->d) BIC_CUDA(c, cudaFreeAsync(m->d, c->stream));
+    delete m;
+    return BIC_OK;
+  }
   BIC_CUDA(c, bic_wait_stream(c));
   if (m->owns && m->d) cudaFree(m->d);
   delete m;

@@ -192,8 +192,10 @@ extern "C" bic_status bic_model_codelength(bic_ctx* c, const bic_mat* E, const b
 }
 
 // ------------------------------------------------------------------ growing / shrinking a model
+// The learners' working matrices come from the stream-ordered pool (no device synchronisation per create / destroy);
+// what is handed back to the caller is copied into ordinary allocations at the end (unpool).
 static bic_status reshape_cols(bic_ctx* c, const bic_mat* Ain, uint64_t pout, uint64_t drop, bic_mat** out) {
-  BIC_TRY(bic_mat_create(c, Ain->rows, pout, out));
+  BIC_TRY(bic_mat_create_pooled(c, Ain->rows, pout, out));
   if (Ain->rows && pout) {
     k_reshape_cols<<<bic_grid_for(c, Ain->rows * (*out)->wpr, 256, 8), 256, 0, c->stream>>>(Ain->d, (*out)->d, Ain->rows, Ain->wpr,
                                                                                          (*out)->wpr, Ain->cols, drop);
@@ -203,8 +205,18 @@ static bic_status reshape_cols(bic_ctx* c, const bic_mat* Ain, uint64_t pout, ui
 }
 
 static bic_status clone_mat(bic_ctx* c, const bic_mat* M, bic_mat** out) {
-  BIC_TRY(bic_mat_create(c, M->rows, M->cols, out));
+  BIC_TRY(bic_mat_create_pooled(c, M->rows, M->cols, out));
   return bic_mat_copy(c, M, *out);
+}
+
+static bic_status unpool(bic_ctx* c, bic_mat** M) {
+  if (!*M || !(*M)->pooled) return BIC_OK;
+  bic_mat* r = nullptr;
+  BIC_TRY(bic_mat_create(c, (*M)->rows, (*M)->cols, &r));
+  BIC_TRY(bic_mat_copy(c, *M, r));
+  bic_mat_destroy(c, *M);
+  *M = r;
+  return BIC_OK;
 }
 
 static void drop_mat(bic_ctx* c, bic_mat** M) {
@@ -223,8 +235,8 @@ static bic_status mdl_forward(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat*
   uint64_t K = (*Dp)->rows;
   BIC_TRY(inner_learn(c, X, E, *Dp, *Ap));                                 // :1470
   bic_mat *nextAtom = nullptr, *nextCoefs = nullptr, *currD = nullptr, *currA = nullptr, *currE = nullptr;
-  BIC_TRY(bic_mat_create(c, 1, m, &nextAtom));
-  BIC_TRY(bic_mat_create(c, n, 1, &nextCoefs));
+  BIC_TRY(bic_mat_create_pooled(c, 1, m, &nextAtom));
+  BIC_TRY(bic_mat_create_pooled(c, n, 1, &nextCoefs));
   BIC_TRY(clone_mat(c, *Dp, &currD));
   BIC_TRY(clone_mat(c, *Ap, &currA));
   BIC_TRY(clone_mat(c, E, &currE));
@@ -237,7 +249,7 @@ static bic_status mdl_forward(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat*
     // one new atom from the current residual; its coefficient column starts at zero (initialize_model, :1488)
     if ((st = bic_initialize_model_neighbor(c, currE, nextAtom, nextCoefs, rng)) != BIC_OK) break;
     bic_mat *nD = nullptr, *nA = nullptr;
-    if ((st = bic_mat_create(c, K + 1, m, &nD)) != BIC_OK) break;          // :1499-1506
+    if ((st = bic_mat_create_pooled(c, K + 1, m, &nD)) != BIC_OK) break;          // :1499-1506
     if ((st = bic_mat_copy_rows(c, currD, 0, K, nD, 0)) != BIC_OK) break;
     if ((st = bic_mat_copy_rows(c, nextAtom, 0, 1, nD, K)) != BIC_OK) break;
     if ((st = reshape_cols(c, currA, K + 1, ~0ull, &nA)) != BIC_OK) break;  // :1508-1516 (the new column is all zero)
@@ -279,7 +291,7 @@ static bic_status mdl_backward(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat
   bic_mat *currD = nullptr, *currA = nullptr, *nextD = nullptr, *nextA = nullptr, *nextE = nullptr;
   BIC_TRY(clone_mat(c, *Dp, &currD));
   BIC_TRY(clone_mat(c, *Ap, &currA));
-  BIC_TRY(bic_mat_create(c, n, m, &nextE));
+  BIC_TRY(bic_mat_create_pooled(c, n, m, &nextE));
   uint64_t stuck = 0, sumStuck = 0, allStuck = 0;
   bic_status st = BIC_OK;
   for (; K > 0; K--) {
@@ -307,7 +319,7 @@ static bic_status mdl_backward(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat
     drop_mat(c, &nextD);
     drop_mat(c, &nextA);
     if (K > 1) {                                                           // :1598-1616
-      if ((st = bic_mat_create(c, K - 1, m, &nextD)) != BIC_OK) break;
+      if ((st = bic_mat_create_pooled(c, K - 1, m, &nextD)) != BIC_OK) break;
       if ((st = bic_mat_copy_rows(c, currD, 0, nextk, nextD, 0)) != BIC_OK) break;
       if ((st = bic_mat_copy_rows(c, currD, nextk + 1, K - 1 - nextk, nextD, nextk)) != BIC_OK) break;
       if ((st = reshape_cols(c, currA, K - 1, nextk, &nextA)) != BIC_OK) break;
@@ -343,8 +355,8 @@ static bic_status mdl_backward(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat
       if ((st = clone_mat(c, nextD, &currD)) != BIC_OK) break;
       if ((st = clone_mat(c, nextA, &currA)) != BIC_OK) break;
     } else {
-      if ((st = bic_mat_create(c, 0, m, &currD)) != BIC_OK) break;
-      if ((st = bic_mat_create(c, n, 0, &currA)) != BIC_OK) break;
+      if ((st = bic_mat_create_pooled(c, 0, m, &currD)) != BIC_OK) break;
+      if ((st = bic_mat_create_pooled(c, n, 0, &currA)) != BIC_OK) break;
     }
   }
   drop_mat(c, &currD); drop_mat(c, &currA); drop_mat(c, &nextD); drop_mat(c, &nextA); drop_mat(c, &nextE);
@@ -358,13 +370,13 @@ static bic_status mdl_backward(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat
 static bic_status mdl_full_search(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat** Dp, bic_mat** Ap, uint64_t* rng, uint64_t* bestL_out) {
   const uint64_t n = E->rows, m = E->cols, Kmax = (*Dp)->rows;
   bic_mat* candE = nullptr;
-  BIC_TRY(bic_mat_create(c, n, m, &candE));
+  BIC_TRY(bic_mat_create_pooled(c, n, m, &candE));
   uint64_t bestL = 1UL << 30;
   bic_status st = BIC_OK;
   for (uint64_t k = 20; k <= Kmax && st == BIC_OK; k += 20) {
     bic_mat *candD = nullptr, *candA = nullptr;
-    if ((st = bic_mat_create(c, k, m, &candD)) != BIC_OK) break;
-    if ((st = bic_mat_create(c, n, k, &candA)) != BIC_OK) { drop_mat(c, &candD); break; }
+    if ((st = bic_mat_create_pooled(c, k, m, &candD)) != BIC_OK) break;
+    if ((st = bic_mat_create_pooled(c, n, k, &candA)) != BIC_OK) { drop_mat(c, &candD); break; }
     uint64_t candL = ~0ull;
     for (int rep = 0; rep < 11 && st == BIC_OK; ++rep) {
       if ((st = bic_initialize_model_neighbor(c, X, candD, candA, rng)) != BIC_OK) break;
@@ -397,8 +409,11 @@ extern "C" bic_status bic_learn_model_mdl(bic_ctx* c, int lm, const bic_mat* X, 
   if (!c || !X || !E || !D || !A || !*D || !*A || !best_codelength) return BIC_ERR_INVALID;
   if (X->rows != E->rows || X->cols != E->cols || (*D)->cols != E->cols || (*A)->rows != E->rows || (*A)->cols != (*D)->rows)
     return bic_fail(c, BIC_ERR_INVALID, "learn_model_mdl: shapes must be X, E n x m, D p x m, A n x p");
-  if (lm == 4) return rng_state ? mdl_forward(c, X, E, D, A, rng_state, best_codelength) : BIC_ERR_INVALID;
-  if (lm == 5) return mdl_backward(c, X, E, D, A, best_codelength);
-  if (lm == 6) return rng_state ? mdl_full_search(c, X, E, D, A, rng_state, best_codelength) : BIC_ERR_INVALID;
-  return bic_fail(c, BIC_ERR_INVALID, "learn_model_mdl: lm must be 4 (forward), 5 (backward) or 6 (full search)");
+  bic_status st;
+  if (lm == 4) st = rng_state ? mdl_forward(c, X, E, D, A, rng_state, best_codelength) : BIC_ERR_INVALID;
+  else if (lm == 5) st = mdl_backward(c, X, E, D, A, best_codelength);
+  else if (lm == 6) st = rng_state ? mdl_full_search(c, X, E, D, A, rng_state, best_codelength) : BIC_ERR_INVALID;
+  else return bic_fail(c, BIC_ERR_INVALID, "learn_model_mdl: lm must be 4 (forward), 5 (backward) or 6 (full search)");
+  const bic_status s1 = unpool(c, D), s2 = unpool(c, A);
+  return st != BIC_OK ? st : (s1 != BIC_OK ? s1 : s2);
 }
