@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         "bic_residual": [_vp, _vp, _vp, _vp, _vp],
         "bic_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
         "bic_model_codelength": [_vp, _vp, _vp, _vp, _u64p],
+        "bic_split_bitplanes": [_vp, _u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_vp), C.c_uint32],
         "bic_learn_model_mdl": [_vp, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _u64p, _u64p],
         "bic_comm_unique_id": [_u8p],
         "bic_comm_create": [_vp, C.c_int, C.c_int, _u8p, C.POINTER(_vp)],
@@ -404,6 +405,22 @@ class Context:
                                                     tr.ctypes.data_as(_u64p), trace_cap))
         n = int(it.value)
         return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
+
+    # ---- bit planes of a grey image (src/bitplane_tool.cpp:24-39)
+    def split_bitplanes(self, p5_payload: np.ndarray, rows: int, cols: int, maxval: int, planes=None):
+        """P5 payload bytes (1 byte per pixel if maxval < 256 else 2, high byte first) -> list of rows x cols planes, LSB first"""
+        n = 0
+        b = 1
+        while b < maxval:
+            n += 1
+            b <<= 1
+        planes = planes or [Matrix(self, rows, cols) for _ in range(n)]
+        pay = np.ascontiguousarray(p5_payload, np.uint8)
+        assert pay.size == rows * cols * (2 if maxval >= 256 else 1)
+        arr = (_vp * n)(*[m.h for m in planes])
+        self._ck(self.L.bic_split_bitplanes(self.h, pay.ctypes.data_as(_u8p), rows, cols, maxval, arr, n))
+        self.sync()  # pay may be a temporary
+        return planes
 
     # ---- MDL model selection (src/bsvd.cpp:1438-1717)
     def model_codelength(self, E: Matrix, D: "Matrix | None", A: "Matrix | None") -> int:

@@ -166,6 +166,14 @@ bic_status bic_learn_model_traditional(bic_ctx* ctx, const bic_mat* X, bic_mat* 
 bic_status bic_learn_model_traditional_batched(bic_ctx* ctx, uint32_t nprob, const bic_mat* const* X, bic_mat* const* E,
                                                bic_mat* const* D, bic_mat* const* A, uint64_t* iterations);
 
+/* ---- bit planes of a grey image (bitplane_tool, src/bitplane_tool.cpp:24-39) -------------------------------
+ * planes[bi](i, j) = gray(i, j) & (1 << bi) for every mask 1 << bi < maxval (bic_bitplane_count of them); the input is
+ * the P5 payload as read_pgm_p5_data reads it (src/pnm.cpp:54-78): one byte per pixel if maxval < 256, else two, high
+ * byte first. Header parsing and file I/O stay on the host. */
+uint32_t bic_bitplane_count(uint32_t maxval);
+bic_status bic_split_bitplanes(bic_ctx* ctx, const uint8_t* p5_payload, uint64_t rows, uint64_t cols, uint32_t maxval,
+                               bic_mat* const* planes, uint32_t nplanes);
+
 /* ---- MDL model selection (the learners that call the fit repeatedly) -----------------------
  * universal_codelength, src/coding.cpp:24-32 (host arithmetic: double log2 over integer counts) */
 double bic_universal_codelength(unsigned n, unsigned r);

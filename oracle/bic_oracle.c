@@ -716,3 +716,24 @@ struct bo_mdl_result* bo_learn_mdl_full_search(const bo_word* X, bo_word* E, uin
   free(candE);
   return mdl_result(n, m, bestk, bestL, D, A);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Bit planes of a grey image: the loop of bitplane_tool (src/bitplane_tool.cpp:24-39) over pixels read as
+ * read_pgm_p5_data reads them (src/pnm.cpp:54-78): one byte per pixel when maxval < 256, else two, high byte
+ * first. planes: nplanes consecutive rows x cols matrices, plane bi for mask 1 << bi, for every mask < maxval.
+ * Returns the number of planes.
+ * ------------------------------------------------------------------------------------------ */
+uint32_t bo_split_bitplanes(const uint8_t* payload, uint64_t rows, uint64_t cols, uint32_t maxval, bo_word* planes) {
+  const uint64_t wpr = bo_wpr(cols);
+  uint32_t bi = 0;
+  for (uint64_t b = 1; b < maxval; b <<= 1, bi++) {           /* :24 */
+    bo_word* A = planes + (uint64_t)bi * rows * wpr;
+    memset(A, 0, rows * wpr * sizeof(bo_word));
+    for (uint64_t i = 0, li = 0; i < rows; i++)
+      for (uint64_t j = 0; j < cols; j++, li++) {
+        const uint32_t pix = maxval < 256 ? payload[li] : (((uint32_t)payload[2 * li] << 8) + payload[2 * li + 1]);  /* pnm.cpp:62,71 */
+        if (pix & b) A[i * wpr + (j >> 6)] |= (bo_word)1 << (63 - (j & 63));   /* A.set(i,j,gray_img[li] & b), :28 */
+      }
+  }
+  return bi;
+}

@@ -78,6 +78,8 @@ class Oracle:
         L.bo_eg_encode_matrix.argtypes = [u64p, u64, u64, u8p, u64]
         L.bo_eg_decode_matrix.restype = C.c_int
         L.bo_eg_decode_matrix.argtypes = [u8p, u64, u64, u64, u64p]
+        L.bo_split_bitplanes.restype = C.c_uint32
+        L.bo_split_bitplanes.argtypes = [u8p, u64, u64, C.c_uint32, u64p]
         L.bo_universal_codelength.restype = C.c_double
         L.bo_universal_codelength.argtypes = [C.c_uint, C.c_uint]
         L.bo_model_codelength.restype = u64
@@ -91,6 +93,19 @@ class Oracle:
         L.bo_mdl_result_info.argtypes = [C.c_void_p, u64p, u64p]
         L.bo_mdl_result_copy.argtypes = [C.c_void_p, u64p, u64p]
         L.bo_mdl_result_free.argtypes = [C.c_void_p]
+
+    def split_bitplanes(self, payload, rows, cols, maxval):
+        """P5 payload -> (nplanes, rows, wpr) uint64, plane bi for mask 1 << bi"""
+        pay = np.ascontiguousarray(payload, np.uint8)
+        n = 0
+        b = 1
+        while b < maxval:
+            n += 1
+            b <<= 1
+        out = np.zeros((max(n, 1), rows, wpr(cols)), np.uint64)
+        got = int(self.lib.bo_split_bitplanes(pay.ctypes.data_as(u8p), rows, cols, maxval, _p64(out)))
+        assert got == n
+        return out[:n]
 
     # ---- MDL model selection (SURVEY 8f row 3)
     def universal_codelength(self, n, r):
