@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
         "bic_eg_encode": [_vp, _vp, _vp],
         "bic_eg_decode": [_vp, _vp, _vp],
         "bic_encode_raster": [_vp, _u8p, _u64, _u64, _u64, _u64, C.c_ulong, _u8p, _u64, C.POINTER(EncodeInfo)],
+        "bic_encode_raster_resident": [_vp, _vp, _u64, _u64, C.c_ulong, _u8p, _u64, C.POINTER(EncodeInfo)],
         "bic_decode_raster": [_vp, _u8p, _u64, _u8p, _u64, _u64p, _u64p],
     }
     for name, args in sig.items():
@@ -552,6 +553,14 @@ class Context:
             st = self.L.bic_encode_raster(self.h, b.ctypes.data_as(_u8p), rows, cols, W, K, seed,
                                           out.ctypes.data_as(_u8p), out.size, C.byref(info))
         self._ck(st)
+        return out[: int(info.container_bytes)], info
+
+    def encode_raster_resident(self, raster: Matrix, W: int, K: int, seed: int = 34503498, out: np.ndarray | None = None):
+        """the same container from a raster already in device memory (e.g. a plane of split_bitplanes)"""
+        info = EncodeInfo()
+        if out is None:
+            out = np.zeros(max(64 * 1024, 2 * raster.rows * ((raster.cols + 7) // 8) + 64 * 1024), np.uint8)
+        self._ck(self.L.bic_encode_raster_resident(self.h, raster.h, W, K, seed, out.ctypes.data_as(_u8p), out.size, C.byref(info)))
         return out[: int(info.container_bytes)], info
 
     def decode_raster(self, container: np.ndarray):

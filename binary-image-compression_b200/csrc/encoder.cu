@@ -90,6 +90,9 @@ static bic_status ws_prepare(bic_ctx* c, EncWorkspace* w, uint64_t rows, uint64_
   return BIC_OK;
 }
 
+static bic_status encode_from_raster(bic_ctx* c, EncWorkspace* w, const bic_mat* raster, uint64_t W, uint64_t K, unsigned long seed,
+                                     uint8_t* out, uint64_t cap_bytes, bic_encode_info* info);
+
 extern "C" bic_status bic_encode_raster(bic_ctx* c, const uint8_t* pbm_payload, uint64_t rows, uint64_t cols, uint64_t W,
                                         uint64_t K, unsigned long seed, uint8_t* out, uint64_t cap_bytes,
                                         bic_encode_info* info) {
@@ -98,7 +101,23 @@ extern "C" bic_status bic_encode_raster(bic_ctx* c, const uint8_t* pbm_payload, 
   EncWorkspace* w = ws_of(c);
   BIC_TRY(ws_prepare(c, w, rows, cols, W, K));
   BIC_TRY(bic_mat_upload_pbm(c, w->raster, pbm_payload));
-  BIC_TRY(bic_extract_patches(c, w->raster, W, w->X));       // src/bsvd_test.cpp:80-99
+  return encode_from_raster(c, w, w->raster, W, K, seed, out, cap_bytes, info);
+}
+
+// the same encoder for a raster that already sits in device memory (e.g. one of bic_split_bitplanes' planes)
+extern "C" bic_status bic_encode_raster_resident(bic_ctx* c, const bic_mat* raster, uint64_t W, uint64_t K, unsigned long seed,
+                                                 uint8_t* out, uint64_t cap_bytes, bic_encode_info* info) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
+  if (!c || !raster || W == 0 || K == 0 || raster->rows == 0 || raster->cols == 0) return BIC_ERR_INVALID;
+  EncWorkspace* w = ws_of(c);
+  BIC_TRY(ws_prepare(c, w, raster->rows, raster->cols, W, K));
+  return encode_from_raster(c, w, raster, W, K, seed, out, cap_bytes, info);
+}
+
+static bic_status encode_from_raster(bic_ctx* c, EncWorkspace* w, const bic_mat* raster, uint64_t W, uint64_t K, unsigned long seed,
+                                     uint8_t* out, uint64_t cap_bytes, bic_encode_info* info) {
+  const uint64_t rows = raster->rows, cols = raster->cols;
+  BIC_TRY(bic_extract_patches(c, raster, W, w->X));          // src/bsvd_test.cpp:80-99
   uint64_t rng;
   bic_rand48_seed(&rng, seed);                               // -r / random_seed, src/bsvd.cpp:12
   BIC_TRY(bic_initialize_model_neighbor(c, w->X, w->D, w->A, &rng));  // :114

@@ -284,6 +284,9 @@ typedef struct {
 bic_status bic_encode_raster(bic_ctx* ctx, const uint8_t* pbm_payload, uint64_t rows, uint64_t cols,
                              uint64_t W, uint64_t K, unsigned long seed,
                              uint8_t* out, uint64_t cap_bytes, bic_encode_info* info);
+/* bic_encode_raster for a raster that is already in device memory (one of bic_split_bitplanes' planes): same container */
+bic_status bic_encode_raster_resident(bic_ctx* ctx, const bic_mat* raster, uint64_t W, uint64_t K, unsigned long seed,
+                                      uint8_t* out, uint64_t cap_bytes, bic_encode_info* info);
 /* inverse: container -> P4 payload (decode D, A, E; X = A*D xor E; patches -> raster) */
 bic_status bic_decode_raster(bic_ctx* ctx, const uint8_t* container, uint64_t container_bytes,
                              uint8_t* pbm_payload, uint64_t cap_bytes, uint64_t* rows, uint64_t* cols);

@@ -91,3 +91,27 @@ def test_split_bitplanes_full_size_matches_the_bench_generator(synth):
         want = synth.pbm_bytes_torch(synth.bitplane(img, b)).cpu().numpy()
         assert np.array_equal(planes[b].download_pbm(), want)
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_pgm_to_containers_equals_plane_by_plane(synth):
+    """configs[1] end to end: P5 payload -> bic_split_bitplanes -> bic_encode_raster_resident gives, plane for plane, the
+    container bic_encode_raster makes of that plane's P4 payload, and the containers decode back to the planes"""
+    import importlib
+    bic = importlib.import_module("binary-image-compression_b200")
+    ctx = bic.Context(0)
+    S = 512
+    img = synth.smooth_pgm16(S, S, seed=2)
+    pay = p5_payload(img.astype(np.int64), 65535)
+    planes = ctx.split_bitplanes(pay, S, S, 65535)
+    assert len(planes) == 16
+    for b in (0, 7, 12, 15):
+        p4 = synth.pbm_bytes(synth.bitplane(img, b))
+        if not p4.any():
+            continue  # an all-zero plane has no pivot (the reference's initialiser never returns on it)
+        c1, i1 = ctx.encode_raster(p4, S, S, 8, 32)
+        c2, i2 = ctx.encode_raster_resident(planes[b], 8, 32)
+        assert i1.container_bytes == i2.container_bytes and np.array_equal(np.array(c1), np.array(c2))
+        back, r, c_ = ctx.decode_raster(np.array(c2))
+        assert (r, c_) == (S, S) and np.array_equal(back, p4)
+    ctx.close()
