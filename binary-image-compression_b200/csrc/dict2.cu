@@ -163,6 +163,7 @@ struct ResolveParams {
   uint32_t* first;       // [2]: scan/fix variant: first changing atom found by the scan of this parity
   uint64_t n, wprE, wprA, wprN, m, hs;
   uint32_t p, parity, win;  // win: histogram rows cached in shared memory per refill
+  uint32_t dmax;            // k_dict_fix: bits of the delta whose corrections a CTA sums in shared memory (p * dmax counters)
   uint32_t corr_smem;       // 1: k_dict_resolve_step sums the corrections per CTA in shared memory (p*hs words after the window)
   const ProbDev* probs;     // batched launch: blockIdx.y selects the problem (else null)
   const uint32_t* active;
@@ -180,12 +181,17 @@ __device__ __forceinline__ bool resolve_select_problem(ResolveParams& P) {
 
 // Atom k changes by s_delta = D_k ^ newD_k (shared memory, same in every CTA): patch its users'
 // residual rows, correct the histograms of the later atoms those rows use, publish newD_k and the cursor.
-__device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32_t k, const uint32_t* s_delta, uint32_t* s_corr) {
+// s_cc / s_rank / s_pos (k_dict_fix, large dictionaries): the histogram does not fit shared memory, but only the bits of
+// the delta are ever corrected. They are numbered 0..nd-1 (s_rank[w] = bits before word w, s_pos[r] = bit position) and the
+// first P.dmax of them get per-CTA counters s_cc[l * dmax + r]; one global atomic per touched counter and CTA at the end.
+__device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32_t k, const uint32_t* s_delta, uint32_t* s_corr,
+                                                  uint32_t* s_cc = nullptr, const uint32_t* s_rank = nullptr,
+                                                  const uint32_t* s_pos = nullptr) {
   const int lane = threadIdx.x & 31;
   const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const uint32_t* at = P.AT + (uint64_t)k * P.wprN;
-  if (P.wprE >= 8) {
+  if (P.wprE > 8) {
     // wide rows: a WARP per user row, lanes over the row's words (coalesced), so a 1024-bit row is 32
     // lanes x 1 word instead of one lane x 32 words. AT words are spread over warps one by one.
     for (uint64_t wi = gw; wi < P.wprN; wi += nwarps) {
@@ -212,7 +218,10 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
                 while (dl) {
                   const int bp = __clz(dl);
                   dl &= ~(0x80000000u >> bp);
-                  atomicAdd(hl + bp, ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u);
+                  const uint32_t v = ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u;
+                  const uint32_t r = s_cc ? s_rank[w] + __popc(dl0 & ~(0xFFFFFFFFu >> bp)) : 0xFFFFFFFFu;
+                  if (r < P.dmax) atomicAdd(&s_cc[(aw * 32 + ap) * P.dmax + r], v);
+                  else atomicAdd(hl + bp, v);
                 }
               }
             }
@@ -260,13 +269,17 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
             // atomic per touched counter per CTA instead of one per row and bit), else go straight to L2
             uint32_t* hl = (s_corr ? s_corr : P.Hc) + (aw * 32 + ap) * P.hs;
             for (uint64_t w = 0; w < P.wprE; ++w) {
-              uint32_t dl = s_delta[w];
+              const uint32_t dl0 = s_delta[w];
+              uint32_t dl = dl0;
               if (!dl) continue;
               const uint32_t e = erow[w];
               while (dl) {
                 const int bp = __clz(dl);
                 dl &= ~(0x80000000u >> bp);
-                atomicAdd(hl + w * 32 + bp, ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u);
+                const uint32_t v = ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u;
+                const uint32_t r = s_cc ? s_rank[w] + __popc(dl0 & ~(0xFFFFFFFFu >> bp)) : 0xFFFFFFFFu;
+                if (r < P.dmax) atomicAdd(&s_cc[(aw * 32 + ap) * P.dmax + r], v);
+                else atomicAdd(hl + w * 32 + bp, v);
               }
             }
           }
@@ -285,6 +298,13 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
         const uint32_t v = s_corr[i];
         if (v) atomicAdd(P.Hc + i, v);
       }
+    }
+  }
+  if (s_cc) {
+    __syncthreads();
+    for (uint32_t i = (k + 1) * P.dmax + threadIdx.x; i < P.p * P.dmax; i += blockDim.x) {
+      const uint32_t v = s_cc[i];
+      if (v) atomicAdd(P.Hc + (uint64_t)(i / P.dmax) * P.hs + s_pos[i % P.dmax], v);
     }
   }
   if (blockIdx.x == 0) {
@@ -426,7 +446,38 @@ __global__ void __launch_bounds__(256) k_dict_fix(ResolveParams P) {
     if (lane == 0) s_delta[w] = nd ^ dk;
   }
   __syncthreads();
-  dict_apply_change(P, k, s_delta, nullptr);
+  uint32_t* s_rank = s_delta + P.wprE;      // wprE
+  uint32_t* s_pos = s_rank + P.wprE;        // dmax
+  uint32_t* s_cc = s_pos + P.dmax;          // p * dmax
+  if (P.dmax) {
+    if (threadIdx.x == 0) {
+      uint32_t r = 0;
+      for (uint64_t w = 0; w < P.wprE; ++w) {
+        s_rank[w] = r;
+        uint32_t dl = s_delta[w];
+        while (dl) {
+          const int bp = __clz(dl);
+          dl &= ~(0x80000000u >> bp);
+          if (r < P.dmax) s_pos[r] = (uint32_t)w * 32 + bp;
+          ++r;
+        }
+      }
+    }
+    for (uint32_t i = (k + 1) * P.dmax + threadIdx.x; i < P.p * P.dmax; i += blockDim.x) s_cc[i] = 0;
+    __syncthreads();
+    dict_apply_change(P, k, s_delta, nullptr, s_cc, s_rank, s_pos);
+  } else {
+    dict_apply_change(P, k, s_delta, nullptr);
+  }
+}
+
+// k_dict_fix's shared memory: delta, rank per word, positions, and p * dmax correction counters (at most ~40 KB)
+static void fix_set_dmax(ResolveParams& P) {
+  uint64_t d = 10240 / (P.p ? P.p : 1);
+  P.dmax = (uint32_t)(d > 64 ? 64 : d);
+}
+static size_t fix_smem_bytes(const ResolveParams& P) {
+  return (size_t)(2 * P.wprE + P.dmax + (uint64_t)P.p * P.dmax) * 4;
 }
 
 static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, uint32_t* H, uint32_t* U, uint64_t hs,
@@ -463,6 +514,7 @@ static bic_status resolve_step_smem_optin(bic_ctx* c) {
   static bool done[64] = {false};
   if (c->device < 64 && done[c->device]) return BIC_OK;
   BIC_CUDA(c, cudaFuncSetAttribute(k_dict_resolve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  BIC_CUDA(c, cudaFuncSetAttribute(k_dict_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));  // + 16 KB static
   if (c->device < 64) done[c->device] = true;
   return BIC_OK;
 }
@@ -514,18 +566,20 @@ bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_m
   if (win < 1) win = 1;
   if (win > w->p) win = w->p;
   P.win = (uint32_t)win;
+  fix_set_dmax(P);
   P.corr_smem = (!w->use_scan && w->wpr < 8 && w->p * w->hs <= 4096) ? 1u : 0u;
   const size_t smem = (size_t)(w->wpr + win * (w->hs + 1) + (P.corr_smem ? w->p * w->hs : 0)) * 4;
-  const int grid = (w->wpr >= 8) ? bic_grid_for(c, (w->wprN ? w->wprN : 1) * 32, 256, 8)
+  const int grid = (w->wpr > 8) ? bic_grid_for(c, (w->wprN ? w->wprN : 1) * 32, 256, 8)
                                  : bic_grid_for(c, div_up_u64(w->wprN ? w->wprN : 1, 32) * 32, 256, 4);
   P.parity = w->launched & 1;
   if (w->use_scan) {
+    BIC_TRY(resolve_step_smem_optin(c));
     const int sgrid = bic_grid_for(c, w->p * 32, 256, 4);
     BIC_PROF(c, KID_DICT_SCAN);
     k_dict_scan<<<sgrid, 256, 0, c->stream>>>(P);
     BIC_LAUNCH_CHECK(c);
     BIC_PROF(c, KID_DICT_RESOLVE);
-    k_dict_fix<<<grid, 256, (size_t)w->wpr * 4, c->stream>>>(P);
+    k_dict_fix<<<grid, 256, fix_smem_bytes(P), c->stream>>>(P);
     BIC_LAUNCH_CHECK(c);
   } else {
     BIC_TRY(resolve_step_smem_optin(c));
@@ -567,18 +621,20 @@ bic_status bic_k_dict_step_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t 
   if (win < 1) win = 1;
   if (win > p) win = p;
   P.win = (uint32_t)win;
+  fix_set_dmax(P);
   P.corr_smem = (p * (hs + 1) * 4 <= 32 * 1024 && wpr < 8 && p * hs <= 4096) ? 1u : 0u;
   const size_t smem = (size_t)(wpr + win * (hs + 1) + (P.corr_smem ? p * hs : 0)) * 4;
-  const int gx = (wpr >= 8) ? bic_grid_for(c, (wprN ? wprN : 1) * 32, 256, 8)
+  const int gx = (wpr > 8) ? bic_grid_for(c, (wprN ? wprN : 1) * 32, 256, 8)
                             : bic_grid_for(c, div_up_u64(wprN ? wprN : 1, 32) * 32, 256, 4);
   P.parity = launched & 1;
   if (p * (hs + 1) * 4 > 32 * 1024) {
+    BIC_TRY(resolve_step_smem_optin(c));
     const int sgrid = bic_grid_for(c, p * 32, 256, 4);
     BIC_PROF(c, KID_DICT_SCAN);
     k_dict_scan<<<dim3(sgrid, nprob), 256, 0, c->stream>>>(P);
     BIC_LAUNCH_CHECK(c);
     BIC_PROF(c, KID_DICT_RESOLVE);
-    k_dict_fix<<<dim3(gx, nprob), 256, (size_t)wpr * 4, c->stream>>>(P);
+    k_dict_fix<<<dim3(gx, nprob), 256, fix_smem_bytes(P), c->stream>>>(P);
     BIC_LAUNCH_CHECK(c);
   } else {
     BIC_TRY(resolve_step_smem_optin(c));

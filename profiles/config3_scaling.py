@@ -89,6 +89,13 @@ def main():
     ctx.timer_start()
     it, tr, bits = step()
     ms = ctx.timer_stop()
+    kernel_ms = None
+    if os.environ.get("BIC_C3_PROF"):   # a second, untimed pass with per-launch device timers: where the time goes
+        ctx.prof_reset()
+        ctx.prof_enable(True)
+        step()
+        ctx.prof_enable(False)
+        kernel_ms = {k: [int(v[0]), round(v[1], 2)] for k, v in sorted(ctx.prof_stats().items(), key=lambda kv: -kv[1][1])}
     coll = ctx.comm_collectives(comm) - c0
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -112,7 +119,7 @@ def main():
             "n_gpus": world, "pages": world * pages, "patches": world * n, "iterations": int(it),
             "changed_atoms_per_iteration": [int(x) for x in tr[:, 1]][:16], "collectives": int(coll),
             "device_ms": ms, "Mpixel_per_s": px / (ms / 1e3), "golomb_bits_D_A_E": [int(b) for b in bits],
-            "raw_bits": int(px * 1e6), "checks_all_ranks": bool(ok.item() == 1.0), "page_generation_s": round(t_gen, 1),
+            "raw_bits": int(px * 1e6), "kernel_launches_ms": kernel_ms, "checks_all_ranks": bool(ok.item() == 1.0), "page_generation_s": round(t_gen, 1),
             "scaling": "weak"}), flush=True)
     barrier()
     ctx.comm_destroy(comm)
