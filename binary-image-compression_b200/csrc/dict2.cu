@@ -114,6 +114,23 @@ __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restri
     for (int w = 0; w < JW; ++w) et[w] = warp_transpose32(e[w]);
     const uint32_t at = warp_transpose32(a);
     ucnt += __popc(at);
+    // With a large dictionary a block of 32 rows uses only a handful of these 32 atoms (rows are sparse codes): then
+    // only the atoms present are visited and their counts go straight to the CTA's shared-memory counters (lane-distinct
+    // banks); otherwise all 32 atoms are accumulated in registers.
+    uint32_t present = __ballot_sync(0xffffffffu, at != 0);
+    if (__popc(present) <= 12) {
+      while (present) {
+        const int k = __ffs(present) - 1;
+        present &= present - 1;
+        const uint32_t ak = __shfl_sync(0xffffffffu, at, k);
+#pragma unroll
+        for (int w = 0; w < JW; ++w) {
+          const uint32_t cnt = __popc(ak & et[w]);
+          if (cnt) atomicAdd(&s_acc[(k * JW + w) * 32 + lane], cnt);
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
       const uint32_t ak = __shfl_sync(0xffffffffu, at, k);
