@@ -140,12 +140,24 @@ struct ProbDev {
   unsigned long long* counts;  // [0] changed rows, [1] changed atoms of the current iteration
 };
 
+// Peers of a row-sharded fit, for kernels that exchange over NVLink peer memory (dist.cu): every rank maps every other
+// rank's window with cudaIpc; all pointers are valid on THIS device. Window layout in u32 words: [0, 64) flags (flags[r] =
+// the last barrier rank r has reached), [64] arrival counter of the local grid, [XWIN_DATA, ...) data.
+#define XWIN_DATA 128
+struct XPeers {
+  uint32_t* const* win = nullptr;  // [nranks] window of every rank (own included)
+  uint32_t nranks = 0, rank = 0;
+  uint32_t epoch = 0;              // number of this launch's barrier: strictly increasing, identical on every rank
+  uint64_t h_off = 0;              // word offset of the histograms H inside a window
+};
+
 // scratch layout of one dictionary update (dict2.cu), shared with the row-sharded driver (dist.cu)
 struct DictWork {
   uint64_t n, p, wpr, hs, wprN;
   uint32_t *AT, *H, *U, *extra, *Hd, *Dnew, *cursor, *first;
   uint32_t launched;
   bool use_scan;
+  XPeers x;                        // nranks > 1: corrections are pushed into every rank's H by the fix kernel itself
 };
 
 // scratch layout of one neighbour initialisation (init.cu), shared with dist.cu

@@ -184,6 +184,7 @@ struct ResolveParams {
   uint32_t corr_smem;       // 1: k_dict_resolve_step sums the corrections per CTA in shared memory (p*hs words after the window)
   const ProbDev* probs;     // batched launch: blockIdx.y selects the problem (else null)
   const uint32_t* active;
+  XPeers x;                 // row-sharded fit with peer-memory exchange: corrections go to EVERY rank's H (else nranks <= 1)
 };
 
 // batched launch: swap in the problem's pointers; false = this problem already converged
@@ -198,6 +199,44 @@ __device__ __forceinline__ bool resolve_select_problem(ResolveParams& P) {
 
 // Atom k changes by s_delta = D_k ^ newD_k (shared memory, same in every CTA): patch its users'
 // residual rows, correct the histograms of the later atoms those rows use, publish newD_k and the cursor.
+// one correction: to the local buffer, or -- row-sharded fit with peer windows -- straight into every rank's histograms
+// (remote atomics over NVLink; integer sums, so the order in which the ranks' contributions land does not matter)
+__device__ __forceinline__ void hc_add(const ResolveParams& P, uint64_t idx, uint32_t v) {
+  if (P.x.nranks > 1) {
+    for (uint32_t r = 0; r < P.x.nranks; ++r) atomicAdd(P.x.win[r] + P.x.h_off + idx, v);
+  } else {
+    atomicAdd(P.Hc + idx, v);
+  }
+}
+
+// Barrier over the ranks at the end of a kernel that pushed into the peers' windows: every thread fences its remote atomics,
+// the LAST CTA of the local grid tells every peer "rank r reached barrier e" and waits until every peer has said the same.
+// When the kernel ends, every rank's contributions to this rank's window have landed. One spinning thread per GPU; the wait is
+// bounded (about a second) and traps instead of hanging if a peer never arrives.
+__device__ __forceinline__ void xgpu_barrier(const XPeers& x) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* me = x.win[x.rank];
+    const uint32_t ncta = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(me + 64, 1u) == ncta - 1) {
+      atomicExch(me + 64, 0u);
+      __threadfence_system();
+      for (uint32_t r = 0; r < x.nranks; ++r)
+        if (r != x.rank) *(volatile uint32_t*)(x.win[r] + x.rank) = x.epoch;
+      for (uint32_t r = 0; r < x.nranks; ++r) {
+        if (r == x.rank) continue;
+        uint32_t spins = 0;
+        while ((int32_t)(*(volatile uint32_t*)(me + r) - x.epoch) < 0) {
+          __nanosleep(200);
+          if (++spins > (1u << 23)) __trap();
+        }
+      }
+      __threadfence_system();
+    }
+  }
+}
+
 // s_cc / s_rank / s_pos (k_dict_fix, large dictionaries): the histogram does not fit shared memory, but only the bits of
 // the delta are ever corrected. They are numbered 0..nd-1 (s_rank[w] = bits before word w, s_pos[r] = bit position) and the
 // first P.dmax of them get per-CTA counters s_cc[l * dmax + r]; one global atomic per touched counter and CTA at the end.
@@ -238,7 +277,7 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
                   const uint32_t v = ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u;
                   const uint32_t r = s_cc ? s_rank[w] + __popc(dl0 & ~(0xFFFFFFFFu >> bp)) : 0xFFFFFFFFu;
                   if (r < P.dmax) atomicAdd(&s_cc[(aw * 32 + ap) * P.dmax + r], v);
-                  else atomicAdd(hl + bp, v);
+                  else hc_add(P, (uint64_t)(hl - P.Hc) + bp, v);
                 }
               }
             }
@@ -296,7 +335,8 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
                 const uint32_t v = ((e >> (31 - bp)) & 1u) ? 0xFFFFFFFFu : 1u;
                 const uint32_t r = s_cc ? s_rank[w] + __popc(dl0 & ~(0xFFFFFFFFu >> bp)) : 0xFFFFFFFFu;
                 if (r < P.dmax) atomicAdd(&s_cc[(aw * 32 + ap) * P.dmax + r], v);
-                else atomicAdd(hl + w * 32 + bp, v);
+                else if (s_corr) atomicAdd(hl + w * 32 + bp, v);
+                else hc_add(P, (aw * 32 + ap) * P.hs + w * 32 + bp, v);
               }
             }
           }
@@ -313,7 +353,7 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
       const uint64_t lo = (uint64_t)(k + 1) * P.hs, hi = (uint64_t)P.p * P.hs;
       for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         const uint32_t v = s_corr[i];
-        if (v) atomicAdd(P.Hc + i, v);
+        if (v) hc_add(P, i, v);
       }
     }
   }
@@ -321,7 +361,7 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
     __syncthreads();
     for (uint32_t i = (k + 1) * P.dmax + threadIdx.x; i < P.p * P.dmax; i += blockDim.x) {
       const uint32_t v = s_cc[i];
-      if (v) atomicAdd(P.Hc + (uint64_t)(i / P.dmax) * P.hs + s_pos[i % P.dmax], v);
+      if (v) hc_add(P, (uint64_t)(i / P.dmax) * P.hs + s_pos[i % P.dmax], v);
     }
   }
   if (blockIdx.x == 0) {
@@ -332,6 +372,7 @@ __device__ __forceinline__ void dict_apply_change(const ResolveParams& P, uint32
       P.cursor[P.parity ^ 1] = k + 1;
     }
   }
+  if (P.x.nranks > 1) xgpu_barrier(P.x);                // every rank's corrections for atom k are in this rank's H
 }
 
 __global__ void __launch_bounds__(256) k_dict_resolve_step(ResolveParams P) {
@@ -538,7 +579,7 @@ static bic_status resolve_step_smem_optin(bic_ctx* c) {
 
 // The update as three reusable stages, so the row-sharded driver (dist.cu) can put its collectives
 // between them: (1) prepare: AT, local H/U; (2) resolve steps; (3) commit Dnew -> D.
-bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, DictWork* w) {
+bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, DictWork* w, uint32_t* hbase) {
   if (E->rows != A->rows || E->cols != D->cols || A->cols != D->rows)
     return bic_fail(c, BIC_ERR_INVALID, "update_dictionary: shapes must be E n x m, D p x m, A n x p");
   const uint64_t n = E->rows, p = D->rows, wpr = E->wpr;
@@ -548,10 +589,18 @@ bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat*
   BIC_TRY(bic_scratch_reserve(c, &c->work[3], (size_t)(2 * p * w->hs + p + 64) * 4));
   BIC_TRY(bic_scratch_reserve(c, &c->work[0], (size_t)p * wpr * 4 + 64));
   w->AT = (uint32_t*)c->work[2].p;
-  w->H = (uint32_t*)c->work[3].p;
-  w->U = w->H + p * w->hs;
-  w->extra = w->U + p;
-  w->Hd = w->extra + 64;
+  w->x = XPeers();
+  if (hbase) {  // the caller's buffer (a peer window) holds [H | U | extra]; the delta buffer stays in the scratch
+    w->H = hbase;
+    w->U = w->H + p * w->hs;
+    w->extra = w->U + p;
+    w->Hd = (uint32_t*)c->work[3].p;
+  } else {
+    w->H = (uint32_t*)c->work[3].p;
+    w->U = w->H + p * w->hs;
+    w->extra = w->U + p;
+    w->Hd = w->extra + 64;
+  }
   w->Dnew = (uint32_t*)c->work[0].p;
   w->cursor = w->Dnew + p * wpr;
   w->first = w->cursor + 2;
@@ -559,7 +608,11 @@ bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat*
   // a dictionary whose histogram fits one shared-memory window is walked serially inside one launch;
   // larger ones use the parallel scan + fix pair
   w->use_scan = (p * (w->hs + 1) * 4 > 32 * 1024);
-  BIC_CUDA(c, cudaMemsetAsync(w->H, 0, (size_t)(2 * p * w->hs + p + 64) * 4, c->stream));
+  if (hbase) {
+    BIC_CUDA(c, cudaMemsetAsync(w->H, 0, (size_t)(p * w->hs + p + 64) * 4, c->stream));
+  } else {
+    BIC_CUDA(c, cudaMemsetAsync(w->H, 0, (size_t)(2 * p * w->hs + p + 64) * 4, c->stream));
+  }
   BIC_CUDA(c, cudaMemcpyAsync(w->Dnew, D->d, (size_t)p * wpr * 4, cudaMemcpyDeviceToDevice, c->stream));
   {
     const uint32_t init[4] = {0u, 0u, (uint32_t)p, (uint32_t)p};  // cursor[2], first[2]
@@ -578,6 +631,8 @@ bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_m
   ResolveParams P;
   P.E = E->d; P.D = D->d; P.Dnew = w->Dnew; P.A = A->d; P.AT = w->AT; P.H = w->H; P.Hc = Hc; P.U = w->U;
   P.changed = d_changed; P.cursor = w->cursor; P.first = w->first; P.probs = nullptr; P.active = nullptr;
+  P.x = w->x;
+  if (P.x.nranks > 1) P.x.epoch += w->launched + 1;  // one barrier number per launch (a launch that changes no atom skips its barrier)
   P.n = w->n; P.wprE = w->wpr; P.wprA = A->wpr; P.wprN = w->wprN; P.m = E->cols; P.hs = w->hs; P.p = (uint32_t)w->p;
   uint64_t win = (32 * 1024 / 4) / (w->hs + 1);
   if (win < 1) win = 1;
@@ -679,7 +734,7 @@ bic_status bic_k_dict_commit(bic_ctx* c, bic_mat* D, DictWork* w) {
 bic_status bic_k_update_dictionary_v2(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
   if (E->rows == 0 || D->rows == 0 || E->cols == 0) return BIC_OK;
   DictWork w;
-  BIC_TRY(bic_k_dict_prepare(c, E, D, A, &w));
+  BIC_TRY(bic_k_dict_prepare(c, E, D, A, &w, nullptr));
   // Queue launches ahead; each returns at once when the cursor is already at p. The cursor is read
   // back and more launches follow only if atoms are still pending.
   uint32_t batch = 4, cursor = 0;

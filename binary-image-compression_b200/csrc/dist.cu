@@ -56,6 +56,14 @@ struct bic_comm {
   std::vector<uint64_t> nrows;    // rows per rank (set by the first collective that needs them)
   uint64_t row0 = 0, nglobal = 0;
   uint64_t collectives = 0;
+  // peer windows (cudaIpc) for the dictionary update's per-atom exchange: see XPeers in bic_internal.cuh
+  int fused = -1;                        // -1 not tried yet, 0 unavailable (NCCL path), 1 windows mapped
+  uint32_t* win = nullptr;               // this rank's window
+  size_t win_words = 0;
+  std::vector<uint32_t*> peer_win;       // every rank's window as mapped here (own = win)
+  uint32_t** d_peer_win = nullptr;       // the same table in device memory
+  uint32_t epoch = 0;                    // barriers used so far
+  const uint32_t* last_extra = nullptr;  // where the last dictionary update left the summed changed-rows count (two u32 halves)
 };
 
 #define BIC_NCCL(ctx, expr)                                                                   \
@@ -92,10 +100,22 @@ extern "C" bic_status bic_comm_create(bic_ctx* c, int rank, int nranks, const ui
   return BIC_OK;
 }
 
+static void window_release(bic_comm* m) {
+  for (int r = 0; r < (int)m->peer_win.size(); ++r)
+    if (r != m->rank && m->peer_win[r]) cudaIpcCloseMemHandle(m->peer_win[r]);
+  m->peer_win.clear();
+  if (m->win) cudaFree(m->win);
+  if (m->d_peer_win) cudaFree(m->d_peer_win);
+  m->win = nullptr;
+  m->d_peer_win = nullptr;
+  m->win_words = 0;
+}
+
 extern "C" bic_status bic_comm_destroy(bic_ctx* c, bic_comm* m) {
   if (!c || !m) return BIC_ERR_INVALID;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  window_release(m);
   if (m->comm) nccl_api()->CommDestroy(m->comm);
   delete m;
   return BIC_OK;
@@ -150,7 +170,7 @@ bic_status bic_k_init_gather(bic_ctx* c, const bic_mat* X, const uint64_t* host_
 bic_status bic_k_init_stats(bic_ctx* c, const bic_mat* X, InitWork* w);
 bic_status bic_k_init_finalize(bic_ctx* c, InitWork* w, uint64_t m, bic_mat* D);
 bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, unsigned long long* d_changed);
-bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, DictWork* w);
+bic_status bic_k_dict_prepare(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, DictWork* w, uint32_t* hbase);
 bic_status bic_k_dict_step(bic_ctx* c, bic_mat* E, const bic_mat* D, const bic_mat* A, DictWork* w, uint32_t* Hc,
                            unsigned long long* d_changed);
 bic_status bic_k_dict_cursor(bic_ctx* c, DictWork* w, uint32_t* cursor_out);
@@ -216,6 +236,94 @@ __global__ void k_apply_corrections(uint32_t* __restrict__ H, uint32_t* __restri
   }
 }
 
+// ------------------------------------------------------------------ peer windows
+// Every rank allocates a window of the same size, the cudaIpc handles go round with one NCCL allgather, and every rank
+// maps the others' windows. Collective: every rank must call it with the same size at the same point. BIC_DIST_FUSED=0
+// (or any failure to map a peer) keeps the NCCL-only path.
+static bic_status window_reserve(bic_ctx* c, bic_comm* m, size_t data_words) {
+  if (m->fused == 0 || m->nranks == 1) return BIC_OK;
+  if (m->fused == -1) {
+    const char* e = getenv("BIC_DIST_FUSED");
+    if ((e && e[0] == '0') || m->nranks > 64) { m->fused = 0; return BIC_OK; }
+  }
+  const size_t need = XWIN_DATA + data_words;
+  if (m->win && m->win_words >= need) return BIC_OK;
+  BIC_CUDA(c, bic_wait_stream(c));
+  window_release(m);
+  const size_t words = need + (need >> 2);
+  int ok = 1;
+  if (cudaMalloc((void**)&m->win, words * 4) != cudaSuccess) { cudaGetLastError(); m->win = nullptr; ok = 0; }
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    cudaMemset(m->win, 0, words * 4);
+    if (cudaIpcGetMemHandle(&mine, m->win) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  }
+  // handles (64 bytes each) + an "ok" byte per rank through NCCL; staged in a small device buffer
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+  uint8_t* d_rec = nullptr;
+  BIC_CUDA(c, cudaMalloc((void**)&d_rec, rec * m->nranks));
+  std::vector<uint8_t> h_rec(rec * m->nranks, 0);
+  memcpy(h_rec.data() + rec * m->rank, &mine, sizeof(mine));
+  h_rec[rec * m->rank + sizeof(mine)] = (uint8_t)ok;
+  BIC_CUDA(c, cudaMemcpyAsync(d_rec + rec * m->rank, h_rec.data() + rec * m->rank, rec, cudaMemcpyHostToDevice, c->stream));
+  BIC_NCCL(c, nccl_api()->AllGather(d_rec + rec * m->rank, d_rec, rec, ncclUint8, m->comm, c->stream));
+  m->collectives++;
+  BIC_CUDA(c, cudaMemcpyAsync(h_rec.data(), d_rec, rec * m->nranks, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
+  cudaFree(d_rec);
+  for (int r = 0; r < m->nranks; ++r) ok &= h_rec[rec * r + sizeof(mine)];
+  m->peer_win.assign(m->nranks, nullptr);
+  if (ok) {
+    for (int r = 0; r < m->nranks && ok; ++r) {
+      if (r == m->rank) { m->peer_win[r] = m->win; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, h_rec.data() + rec * r, sizeof(h));
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+      m->peer_win[r] = (uint32_t*)ptr;
+    }
+  }
+  // every rank must take the same path: agree on the outcome
+  uint64_t mine_ok = (uint64_t)ok, all_ok[16] = {0};
+  if (m->nranks <= 8) {
+    BIC_TRY(bic_comm_allgather_u64(c, m, &mine_ok, 1, all_ok));
+    for (int r = 0; r < m->nranks; ++r) ok &= (int)all_ok[r];
+  } else {
+    ok = 0;
+  }
+  if (!ok) {
+    window_release(m);
+    m->fused = 0;
+    return BIC_OK;
+  }
+  BIC_CUDA(c, cudaMalloc((void**)&m->d_peer_win, sizeof(uint32_t*) * m->nranks));
+  BIC_CUDA(c, cudaMemcpy(m->d_peer_win, m->peer_win.data(), sizeof(uint32_t*) * m->nranks, cudaMemcpyHostToDevice));
+  m->win_words = words;
+  m->fused = 1;
+  m->epoch = 0;
+  return BIC_OK;
+}
+
+// barrier over the ranks as a kernel of its own (after a collective whose result the peers are about to add to)
+__global__ void k_xgpu_barrier(XPeers x) {
+  __threadfence_system();
+  if (threadIdx.x == 0) {
+    uint32_t* me = x.win[x.rank];
+    for (uint32_t r = 0; r < x.nranks; ++r)
+      if (r != x.rank) *(volatile uint32_t*)(x.win[r] + x.rank) = x.epoch;
+    for (uint32_t r = 0; r < x.nranks; ++r) {
+      if (r == x.rank) continue;
+      uint32_t spins = 0;
+      while ((int32_t)(*(volatile uint32_t*)(me + r) - x.epoch) < 0) {
+        __nanosleep(200);
+        if (++spins > (1u << 23)) __trap();
+      }
+    }
+    __threadfence_system();
+  }
+}
+
 // ------------------------------------------------------------------ update_dictionary_steepest, sharded
 // d_counts[0] (changed rows of the preceding coefficient update, local) is summed over ranks in the same
 // allreduce as H and U; d_counts[1] receives the changed atoms (identical on every rank).
@@ -223,25 +331,49 @@ static bic_status dist_update_dictionary(bic_ctx* c, bic_comm* m, bic_mat* E, bi
                                          unsigned long long* d_counts) {
   if (D->rows == 0 || E->cols == 0) return BIC_OK;
   DictWork w;
-  BIC_TRY(bic_k_dict_prepare(c, E, D, A, &w));
+  // With peer windows the histograms live in the window: the fix kernel of an atom that changes adds its corrections
+  // straight into EVERY rank's H over NVLink and ends with a barrier over the ranks (dict2.cu: hc_add, xgpu_barrier) --
+  // compute and exchange are one kernel, there is no per-atom collective call. Without (BIC_DIST_FUSED=0, no peer
+  // access) the corrections go to a delta buffer that is allreduced with NCCL after every step.
+  const uint64_t hwords = D->rows * E->wpr * 32;
+  BIC_TRY(window_reserve(c, m, hwords + D->rows + 64));
+  const bool fused = (m->fused == 1);
+  BIC_TRY(bic_k_dict_prepare(c, E, D, A, &w, fused ? m->win + XWIN_DATA : nullptr));
   // [H | U | extra]: extra[0..1] carries the 64-bit changed-rows count as two u32 halves
   BIC_CUDA(c, cudaMemcpyAsync(w.extra, d_counts, 8, cudaMemcpyDeviceToDevice, c->stream));
+  m->last_extra = w.extra;
   BIC_TRY(allreduce_u32(c, m, w.H, (size_t)w.p * w.hs + w.p + 2));
+  if (fused) {
+    w.x.win = m->d_peer_win;
+    w.x.nranks = (uint32_t)m->nranks;
+    w.x.rank = (uint32_t)m->rank;
+    w.x.h_off = XWIN_DATA;
+    // no rank may add to a peer's H before that peer's allreduce has delivered it
+    XPeers b = w.x;
+    b.epoch = ++m->epoch;
+    k_xgpu_barrier<<<1, 32, 0, c->stream>>>(b);
+    BIC_LAUNCH_CHECK(c);
+    w.x.epoch = m->epoch;  // launch i of this update uses barrier number epoch + i + 1
+  }
   uint32_t cursor = 0;
   uint32_t batch = 1;  // most updates after the first iteration change no atom: one launch, one look at the cursor
-  const uint64_t hwords = w.p * w.hs;
   for (;;) {
     for (uint32_t i = 0; i < batch && w.launched < w.p; ++i) {
-      BIC_TRY(bic_k_dict_step(c, E, D, A, &w, w.Hd, d_counts + 1));
-      // an atom may have changed: combine the corrections its users produced on every rank
-      BIC_TRY(allreduce_u32(c, m, w.Hd, hwords));
-      k_apply_corrections<<<bic_grid_for(c, hwords, 256, 2), 256, 0, c->stream>>>(w.H, w.Hd, hwords);
-      BIC_LAUNCH_CHECK(c);
+      if (fused) {
+        BIC_TRY(bic_k_dict_step(c, E, D, A, &w, w.H, d_counts + 1));
+      } else {
+        BIC_TRY(bic_k_dict_step(c, E, D, A, &w, w.Hd, d_counts + 1));
+        // an atom may have changed: combine the corrections its users produced on every rank
+        BIC_TRY(allreduce_u32(c, m, w.Hd, hwords));
+        k_apply_corrections<<<bic_grid_for(c, hwords, 256, 2), 256, 0, c->stream>>>(w.H, w.Hd, hwords);
+        BIC_LAUNCH_CHECK(c);
+      }
     }
     BIC_TRY(bic_k_dict_cursor(c, &w, &cursor));
     if (cursor >= w.p || w.launched >= w.p) break;
     batch = (batch * 2 < 32) ? batch * 2 : 32;
   }
+  if (fused) m->epoch += w.launched + 1;
   return bic_k_dict_commit(c, D, &w);
 }
 
@@ -276,10 +408,10 @@ extern "C" bic_status bic_dist_learn_model_traditional(bic_ctx* c, bic_comm* m, 
     // global changed-rows: rides in the dictionary update's first allreduce (extra[0..1]); read it back
     // from there after the update
     BIC_TRY(dist_update_dictionary(c, m, E, D, A, d_cc));
-    // extra[] lives in work[3] right after H and U
+    // extra[] sits right after H and U, wherever the update put them (scratch or peer window)
     {
-      const uint64_t p = D->rows, hs = E->wpr * 32;
-      const uint32_t* extra = (const uint32_t*)c->work[3].p + p * hs + p;
+      const uint64_t p = D->rows;
+      const uint32_t* extra = m->last_extra;
       if (p && E->cols) {
         k_join_u32_pair<<<1, 1, 0, c->stream>>>(extra, d_cc);
         BIC_LAUNCH_CHECK(c);
