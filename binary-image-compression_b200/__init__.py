@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
         "bic_residual": [_vp, _vp, _vp, _vp, _vp],
         "bic_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
         "bic_model_codelength": [_vp, _vp, _vp, _vp, _u64p],
+        "bic_mat_transpose": [_vp, _vp, _vp],
+        "bic_learn_model_alter": [_vp, C.c_int, _vp, _vp, _vp, _vp, _u64p],
         "bic_split_bitplanes": [_vp, _u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_vp), C.c_uint32],
         "bic_learn_model_mdl": [_vp, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _u64p, _u64p],
         "bic_comm_unique_id": [_u8p],
@@ -406,6 +408,17 @@ class Context:
                                                     tr.ctypes.data_as(_u64p), trace_cap))
         n = int(it.value)
         return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
+
+    # ---- role-switched learners (src/bsvd.cpp:1245-1434)
+    def transpose(self, M: Matrix) -> Matrix:
+        T = Matrix(self, M.cols, M.rows)
+        self._ck(self.L.bic_mat_transpose(self.h, M.h, T.h))
+        return T
+
+    def learn_model_alter(self, variant: int, X: Matrix, E: Matrix, D: Matrix, A: Matrix) -> int:
+        it = _u64(0)
+        self._ck(self.L.bic_learn_model_alter(self.h, variant, X.h, E.h, D.h, A.h, C.byref(it)))
+        return int(it.value)
 
     # ---- bit planes of a grey image (src/bitplane_tool.cpp:24-39)
     def split_bitplanes(self, p5_payload: np.ndarray, rows: int, cols: int, maxval: int, planes=None):

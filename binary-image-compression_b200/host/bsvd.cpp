@@ -93,6 +93,23 @@ idx_t learn_model_traditional(binary_matrix& X, binary_matrix& E, binary_matrix&
   return iter;
 }
 
+// ---- role-switched learners (src/bsvd.cpp:1245-1434): loops, transposes and updates all run in the library
+static idx_t learn_alter(int variant, binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A, const char* what) {
+  const bool cu_ok = update_coefficients == update_coefficients_omp || update_coefficients == update_coefficients_basic;
+  const bool du_ok = update_dictionary == update_dictionary_steepest || update_dictionary == update_dictionary_steepest_omp;
+  if (!cu_ok || !du_ok) {
+    std::cerr << what << ": the B200 build runs it with its own coefficient and dictionary updates only" << std::endl;
+    std::exit(-1);
+  }
+  uint64_t iters = 0;
+  ck(bic_learn_model_alter(bic_host_context(), variant, X.device(), E.device(), D.device(), A.device(), &iters), what);
+  E.device_written(); D.device_written(); A.device_written();
+  return iters;
+}
+idx_t learn_model_alter1(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A) { return learn_alter(1, X, E, D, A, "learn_model_alter1"); }
+idx_t learn_model_alter2(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A) { return learn_alter(2, X, E, D, A, "learn_model_alter2"); }
+idx_t learn_model_alter3(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A) { return learn_alter(3, X, E, D, A, "learn_model_alter3"); }
+
 // ---- MDL model selection (src/bsvd.cpp:1438-1717): the loops run in the library next to the data; D and A change size
 static idx_t learn_mdl(int lm, binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A, const char* what) {
   if (initialize_model != initialize_model_neighbor || learn_model_inner != learn_model_traditional) {
@@ -138,7 +155,8 @@ static du_algorithm_t du_catalog[] = {update_dictionary_steepest, 0, update_dict
 const char* du_algorithm_names[] = {"Steepest descent (a la MOD)  dictionary update", "Proximus-like dictionary update",
                                     "Steepest descent (a la MOD)  dictionary update (OMP)",
                                     "Proximus-like dictionary update (OMP)", 0};
-static ml_algorithm_t lm_catalog[] = {learn_model_traditional, 0, 0, 0, learn_model_mdl_forward_selection,
+static ml_algorithm_t lm_catalog[] = {learn_model_traditional, learn_model_alter1, learn_model_alter2, learn_model_alter3,
+                                      learn_model_mdl_forward_selection,
                                       learn_model_mdl_backward_selection, learn_model_mdl_full_search, 0};
 const char* lm_algorithm_names[] = {"Model learning by traditional alternate descent",
                                     "Role-switching learning 1: at each iteration, the role of A and D are switched",
@@ -150,7 +168,7 @@ template <typename T>
 static T pick(T* catalog, int idx, const char* what, const char* const* names) {
   if (!catalog[idx]) {
     std::cerr << what << " '" << names[idx] << "' is not provided by the B200 build (only the reference's deterministic "
-              << "configuration -i 0 -c 0|1 -d 0|2 -l 0|4|5|6 -L 0 is)" << std::endl;
+              << "configuration -i 0 -c 0|1 -d 0|2 -l 0..6 -L 0 is)" << std::endl;
     std::exit(-1);
   }
   return catalog[idx];

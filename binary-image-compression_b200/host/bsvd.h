@@ -20,6 +20,11 @@ idx_t update_coefficients_omp(binary_matrix& E, const binary_matrix& D, binary_m
 // src/bsvd.h:71-74 / src/bsvd.cpp:1215-1244
 idx_t learn_model_traditional(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A);
 
+// src/bsvd.h:76-98 / src/bsvd.cpp:1245-1434: the role-switched learners (the fit's updates alternate with the same updates
+// on the transposed problem)
+idx_t learn_model_alter1(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A);
+idx_t learn_model_alter2(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A);
+idx_t learn_model_alter3(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A);
 // src/bsvd.h:100-118 / src/bsvd.cpp:1463-1717: MDL model selection around the fit. They resize D and A (destroy + allocate)
 // to the selected number of atoms and return the best description length; an empty model leaves D and A 0 x 0.
 idx_t learn_model_mdl_forward_selection(binary_matrix& X, binary_matrix& E, binary_matrix& D, binary_matrix& A);

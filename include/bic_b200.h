@@ -166,6 +166,15 @@ bic_status bic_learn_model_traditional(bic_ctx* ctx, const bic_mat* X, bic_mat* 
 bic_status bic_learn_model_traditional_batched(bic_ctx* ctx, uint32_t nprob, const bic_mat* const* X, bic_mat* const* E,
                                                bic_mat* const* D, bic_mat* const* A, uint64_t* iterations);
 
+/* ---- role-switched learners --------------------------------------------------------------
+ * binary_matrix::transpose_to, src/binmat.cpp:199-208: dst (cols x rows) = src' */
+bic_status bic_mat_transpose(bic_ctx* ctx, const bic_mat* src, bic_mat* dst);
+/* variant 1 / 2 / 3: learn_model_alter1 (src/bsvd.cpp:1245-1311), learn_model_alter2 (:1314-1388), learn_model_alter3
+ * (:1391-1434) with the default plug points: the fit's updates alternate with the same updates on the transposed problem
+ * (E' = Et, D' = At, A' = Dt). D, A in/out, E out; returns the reference's iteration count. */
+bic_status bic_learn_model_alter(bic_ctx* ctx, int variant, const bic_mat* X, bic_mat* E, bic_mat* D, bic_mat* A,
+                                 uint64_t* iterations);
+
 /* ---- bit planes of a grey image (bitplane_tool, src/bitplane_tool.cpp:24-39) -------------------------------
  * planes[bi](i, j) = gray(i, j) & (1 << bi) for every mask 1 << bi < maxval (bic_bitplane_count of them); the input is
  * the P5 payload as read_pgm_p5_data reads it (src/pnm.cpp:54-78): one byte per pixel if maxval < 256, else two, high

@@ -737,3 +737,70 @@ uint32_t bo_split_bitplanes(const uint8_t* payload, uint64_t rows, uint64_t cols
   }
   return bi;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Role-switched learners: learn_model_alter1 src/bsvd.cpp:1245-1311, learn_model_alter2
+ * :1314-1388, learn_model_alter3 :1391-1434, over binary_matrix::transpose_to (src/binmat.cpp:199-208) and the
+ * default update_coefficients / update_dictionary plug points. In the transposed calls the roles are
+ * E' = Et (m x n), D' = At (p x n), A' = Dt (m x p).
+ * ------------------------------------------------------------------------------------------ */
+void bo_transpose(const bo_word* M, uint64_t rows, uint64_t cols, bo_word* T) {
+  const uint64_t wi = bo_wpr(cols), wo = bo_wpr(rows);
+  memset(T, 0, cols * wo * sizeof(bo_word));
+  for (uint64_t i = 0; i < rows; ++i)
+    for (uint64_t j = 0; j < cols; ++j)
+      if ((M[i * wi + (j >> 6)] >> (63 - (j & 63))) & 1u) T[j * wo + (i >> 6)] |= (bo_word)1 << (63 - (i & 63));
+}
+
+uint64_t bo_learn_alter(int variant, const bo_word* X, bo_word* E, bo_word* D, bo_word* A, uint64_t n, uint64_t m, uint64_t p) {
+  bo_residual(X, A, D, E, n, m, p);                                   /* :1254-1255 / :1323-1324 / :1399-1400 */
+  bo_word* Dt = mat_alloc(m, p);
+  bo_word* At = mat_alloc(p, n);
+  bo_word* Et = mat_alloc(m, n);
+  uint64_t iter = 0;
+  if (variant == 1) {                                                 /* :1264-1307 */
+    uint64_t changed = 1;
+    while (changed > 0) {
+      iter++;
+      uint64_t cc = bo_update_coefficients(E, D, A, n, m, p);
+      changed = cc + bo_update_dictionary(E, D, A, n, m, p);
+      bo_transpose(A, n, p, At); bo_transpose(D, p, m, Dt); bo_transpose(E, n, m, Et);
+      cc = bo_update_coefficients(Et, At, Dt, m, n, p);
+      (void)cc;
+      changed = bo_update_dictionary(Et, At, Dt, m, n, p);            /* :1297: only this count drives the loop */
+      bo_transpose(At, p, n, A); bo_transpose(Dt, m, p, D); bo_transpose(Et, m, n, E);
+    }
+  } else if (variant == 2) {                                          /* :1331-1383 */
+    uint64_t changed = 1, outer_changed = 1;
+    while (outer_changed > 0) {
+      outer_changed = 0;
+      while (changed > 0) {
+        iter++;
+        const uint64_t cc = bo_update_coefficients(E, D, A, n, m, p);
+        changed = cc + bo_update_dictionary(E, D, A, n, m, p);
+        outer_changed += changed;
+      }
+      bo_transpose(A, n, p, At); bo_transpose(D, p, m, Dt); bo_transpose(E, n, m, Et);
+      changed = 1;
+      iter = 0;                                                       /* :1361 */
+      while (changed > 0) {
+        iter++;
+        const uint64_t cc = bo_update_coefficients(Et, At, Dt, m, n, p);
+        changed = cc + bo_update_dictionary(Et, At, Dt, m, n, p);
+        outer_changed += changed;
+      }
+      bo_transpose(At, p, n, A); bo_transpose(Dt, m, p, D); bo_transpose(Et, m, n, E);
+    }
+  } else {                                                            /* :1407-1429 */
+    uint64_t changed = p + 1;
+    while (changed > 0) {
+      iter++;
+      bo_transpose(A, n, p, At); bo_transpose(D, p, m, Dt); bo_transpose(E, n, m, Et);
+      changed = bo_update_dictionary(Et, At, Dt, m, n, p);
+      bo_transpose(At, p, n, A); bo_transpose(Dt, m, p, D); bo_transpose(Et, m, n, E);
+      changed = bo_update_dictionary(E, D, A, n, m, p);               /* :1423: overwrites the transposed count */
+    }
+  }
+  free(Dt); free(At); free(Et);
+  return iter;
+}

@@ -344,4 +344,19 @@ void ref_mdl_result_free(void* h) {
   delete r;
 }
 
+/* learn_model_alter1 / 2 / 3: bsvd.cpp:1245-1311, :1314-1388, :1391-1434 (default plug points). D, A in/out; E out. */
+u64 ref_learn_alter(int variant, const u64* X_words, u64* E_words, u64* D_words, u64* A_words, u64 n, u64 m, u64 p) {
+  ensure_setup();
+  binary_matrix X(n, m), D(p, m), A(n, p), E(n, m);
+  load(X, X_words); load(D, D_words); load(A, A_words);
+  E.clear();
+  u64 iters;
+  if (variant == 1) iters = learn_model_alter1(X, E, D, A);
+  else if (variant == 2) iters = learn_model_alter2(X, E, D, A);
+  else iters = learn_model_alter3(X, E, D, A);
+  store(E, E_words); store(D, D_words); store(A, A_words);
+  E.destroy(); D.destroy(); A.destroy(); X.destroy();
+  return iters;
+}
+
 } /* extern "C" */

@@ -78,6 +78,9 @@ class Oracle:
         L.bo_eg_encode_matrix.argtypes = [u64p, u64, u64, u8p, u64]
         L.bo_eg_decode_matrix.restype = C.c_int
         L.bo_eg_decode_matrix.argtypes = [u8p, u64, u64, u64, u64p]
+        L.bo_transpose.argtypes = [u64p, u64, u64, u64p]
+        L.bo_learn_alter.restype = u64
+        L.bo_learn_alter.argtypes = [C.c_int, u64p, u64p, u64p, u64p, u64, u64, u64]
         L.bo_split_bitplanes.restype = C.c_uint32
         L.bo_split_bitplanes.argtypes = [u8p, u64, u64, C.c_uint32, u64p]
         L.bo_universal_codelength.restype = C.c_double
@@ -93,6 +96,19 @@ class Oracle:
         L.bo_mdl_result_info.argtypes = [C.c_void_p, u64p, u64p]
         L.bo_mdl_result_copy.argtypes = [C.c_void_p, u64p, u64p]
         L.bo_mdl_result_free.argtypes = [C.c_void_p]
+
+    def transpose(self, M, cols):
+        M = np.ascontiguousarray(M, np.uint64)
+        T = np.zeros((cols, wpr(M.shape[0])), np.uint64)
+        self.lib.bo_transpose(_p64(M), M.shape[0], cols, _p64(T))
+        return T
+
+    def learn_alter(self, variant, X, D, A, m, p):
+        """learn_model_alter1/2/3; D, A updated in place; returns (E, iterations)"""
+        X = np.ascontiguousarray(X, np.uint64)
+        E = np.zeros_like(X)
+        it = int(self.lib.bo_learn_alter(variant, _p64(X), _p64(E), _p64(D), _p64(A), X.shape[0], m, p))
+        return E, it
 
     def split_bitplanes(self, payload, rows, cols, maxval):
         """P5 payload -> (nplanes, rows, wpr) uint64, plane bi for mask 1 << bi"""
@@ -279,6 +295,10 @@ class Reference:
         L.ref_eg.argtypes = [C.POINTER(C.c_int), u8p, u64, u64p]
         L.ref_fit_timed.restype = u64
         L.ref_fit_timed.argtypes = [u64p, u64, u64, u64, u64, C.c_long, C.POINTER(C.c_double), u64p, u64p, u64p]
+        self.has_alter = hasattr(L, "ref_learn_alter")
+        if self.has_alter:
+            L.ref_learn_alter.restype = u64
+            L.ref_learn_alter.argtypes = [C.c_int, u64p, u64p, u64p, u64p, u64, u64, u64]
         self.has_mdl = hasattr(L, "ref_learn_mdl")
         if self.has_mdl:
             L.ref_universal_codelength.restype = C.c_double
@@ -290,6 +310,12 @@ class Reference:
             L.ref_mdl_result_info.argtypes = [C.c_void_p, u64p, u64p]
             L.ref_mdl_result_copy.argtypes = [C.c_void_p, u64p, u64p]
             L.ref_mdl_result_free.argtypes = [C.c_void_p]
+
+    def learn_alter(self, variant, X, D, A, m, p):
+        X = np.ascontiguousarray(X, np.uint64)
+        E = np.zeros_like(X)
+        it = int(self.lib.ref_learn_alter(variant, _p64(X), _p64(E), _p64(D), _p64(A), X.shape[0], m, p))
+        return E, it
 
     def universal_codelength(self, n, r):
         return float(self.lib.ref_universal_codelength(n & 0xFFFFFFFF, r & 0xFFFFFFFF))

@@ -30,6 +30,7 @@ def test_shim_builds_and_keeps_the_reference_names():
                 "initialize_model_neighbor", "update_coefficients_omp", "update_dictionary_steepest", "learn_model_traditional",
                 "initialize_model", "update_coefficients", "update_dictionary", "learn_model", "random_seed", "set_grid_width",
                 "learn_model_mdl_forward_selection", "learn_model_mdl_backward_selection", "learn_model_mdl_full_search",
+                "learn_model_alter1", "learn_model_alter2", "learn_model_alter3",
                 "model_codelength(binary_matrix const&, binary_matrix const&, binary_matrix const&)", "universal_codelength"]:
         assert sym in out, sym
 
@@ -51,9 +52,10 @@ def test_shim_selftest_binary():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode,W,K,rows,cols,lm", [(1, 8, 32, 400, 328, 0), (1, 16, 24, 300, 260, 0), (0, 0, 12, 200, 150, 0),
-                                                    (1, 8, 6, 200, 168, 4), (1, 8, 10, 200, 168, 5), (1, 8, 45, 160, 128, 6)])
+                                                    (1, 8, 6, 200, 168, 4), (1, 8, 10, 200, 168, 5), (1, 8, 45, 160, 128, 6),
+                                                    (1, 8, 12, 200, 168, 1), (1, 8, 12, 200, 168, 2), (1, 16, 10, 160, 160, 3)])
 def test_driver_matches_reference_driver(tmp_path, synth, mode, W, K, rows, cols, lm):
-    """same flags, same PBM -> same dictionary.pbm / coefficients.pbm / residual.pbm bytes (-l 4/5/6: the MDL learners,
+    """same flags, same PBM -> same dictionary.pbm / coefficients.pbm / residual.pbm bytes (-l 1/2/3: the role-switched learners; -l 4/5/6: the MDL learners,
     which change the number of atoms)"""
     ref_bin = ROOT / "oracle" / "_ref" / "bsvd_test"
     if not ref_bin.exists():
