@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "bic_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
         "bic_model_codelength": [_vp, _vp, _vp, _vp, _u64p],
         "bic_mat_transpose": [_vp, _vp, _vp],
+        "bic_update_dictionary_proximus": [_vp, _vp, _vp, _vp, _u64p],
         "bic_learn_model_alter": [_vp, C.c_int, _vp, _vp, _vp, _vp, _u64p],
         "bic_split_bitplanes": [_vp, _u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_vp), C.c_uint32],
         "bic_learn_model_mdl": [_vp, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _u64p, _u64p],
@@ -408,6 +409,11 @@ class Context:
                                                     tr.ctypes.data_as(_u64p), trace_cap))
         n = int(it.value)
         return n, tr[: 2 * min(n, trace_cap)].reshape(-1, 2)
+
+    def update_dictionary_proximus(self, E: Matrix, D: Matrix, A: Matrix) -> int:
+        ch = _u64(0)
+        self._ck(self.L.bic_update_dictionary_proximus(self.h, E.h, D.h, A.h, C.byref(ch)))
+        return int(ch.value)
 
     # ---- role-switched learners (src/bsvd.cpp:1245-1434)
     def transpose(self, M: Matrix) -> Matrix:

@@ -50,6 +50,14 @@ idx_t update_dictionary_steepest(binary_matrix& E, binary_matrix& D, binary_matr
 idx_t update_dictionary_steepest_omp(binary_matrix& E, binary_matrix& D, binary_matrix& A) {
   return update_dictionary_steepest(E, D, A);
 }
+idx_t update_dictionary_proximus(binary_matrix& E, binary_matrix& D, binary_matrix& A) {
+  uint64_t changed = 0;
+  ck(bic_update_dictionary_proximus(bic_host_context(), E.device(), D.device(), A.device(), &changed), "update_dictionary_proximus");
+  E.device_written();
+  D.device_written();
+  A.device_written();
+  return changed;
+}
 
 void residual(const binary_matrix& X, const binary_matrix& A, const binary_matrix& D, binary_matrix& E) {
   ck(bic_residual(bic_host_context(), X.device(), A.device(), D.device(), E.device()), "residual");
@@ -151,7 +159,7 @@ const char* mi_algorithm_names[] = {"Neighbor initialization", "Partition initia
 static cu_algorithm_t cu_catalog[] = {update_coefficients_omp, update_coefficients_basic, 0, 0};
 const char* cu_algorithm_names[] = {"OpenMP basic coefficients update", "Basic coefficients update",
                                     "Fast coefficients update (broken!)", 0};
-static du_algorithm_t du_catalog[] = {update_dictionary_steepest, 0, update_dictionary_steepest_omp, 0, 0};
+static du_algorithm_t du_catalog[] = {update_dictionary_steepest, update_dictionary_proximus, update_dictionary_steepest_omp, 0, 0};
 const char* du_algorithm_names[] = {"Steepest descent (a la MOD)  dictionary update", "Proximus-like dictionary update",
                                     "Steepest descent (a la MOD)  dictionary update (OMP)",
                                     "Proximus-like dictionary update (OMP)", 0};
@@ -168,7 +176,7 @@ template <typename T>
 static T pick(T* catalog, int idx, const char* what, const char* const* names) {
   if (!catalog[idx]) {
     std::cerr << what << " '" << names[idx] << "' is not provided by the B200 build (only the reference's deterministic "
-              << "configuration -i 0 -c 0|1 -d 0|2 -l 0..6 -L 0 is)" << std::endl;
+              << "configuration -i 0 -c 0|1 -d 0|1|2 -l 0..6 -L 0 is)" << std::endl;
     std::exit(-1);
   }
   return catalog[idx];

@@ -11,6 +11,8 @@
 void initialize_model_neighbor(const binary_matrix& E, binary_matrix& D, binary_matrix& A);
 // src/bsvd.h:39 / src/bsvd.cpp:463-527 (atoms strictly in order)
 idx_t update_dictionary_steepest(binary_matrix& E, binary_matrix& D, binary_matrix& A);
+// src/bsvd.h:41 / src/bsvd.cpp:528-729: per atom, the atom's vote alternates with a vote for its coefficient column
+idx_t update_dictionary_proximus(binary_matrix& E, binary_matrix& D, binary_matrix& A);
 // src/bsvd.h:40: the reference's OpenMP variant races (src/bsvd.cpp:770-787); here it is the same
 // deterministic kernel as update_dictionary_steepest
 idx_t update_dictionary_steepest_omp(binary_matrix& E, binary_matrix& D, binary_matrix& A);

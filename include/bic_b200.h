@@ -166,6 +166,12 @@ bic_status bic_learn_model_traditional(bic_ctx* ctx, const bic_mat* X, bic_mat* 
 bic_status bic_learn_model_traditional_batched(bic_ctx* ctx, uint32_t nprob, const bic_mat* const* X, bic_mat* const* E,
                                                bic_mat* const* D, bic_mat* const* A, uint64_t* iterations);
 
+/* update_dictionary_proximus (du_algorithm_t, catalog slot 1), src/bsvd.cpp:528-729: per atom, in order, a majority vote for
+ * the atom over its users alternates with a majority vote for its coefficient column until neither changes. E, D and A are
+ * updated in place; *changed = atoms whose row changed. A chain of small launches (parity path; the throughput path is the
+ * steepest update). */
+bic_status bic_update_dictionary_proximus(bic_ctx* ctx, bic_mat* E, bic_mat* D, bic_mat* A, uint64_t* changed);
+
 /* ---- role-switched learners --------------------------------------------------------------
  * binary_matrix::transpose_to, src/binmat.cpp:199-208: dst (cols x rows) = src' */
 bic_status bic_mat_transpose(bic_ctx* ctx, const bic_mat* src, bic_mat* dst);

@@ -804,3 +804,70 @@ uint64_t bo_learn_alter(int variant, const bo_word* X, bo_word* E, bo_word* D, b
   free(Dt); free(At); free(Et);
   return iter;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * update_dictionary_proximus, src/bsvd.cpp:528-729 (the `#if 0` initialisation block :563-620 is dead code).
+ * Per atom, in order: alternate a majority vote for the atom over its users (as the steepest update does) and a
+ * majority vote for the atom's coefficient column over the atom's set bits, patching E after each, until neither
+ * changes. Counts the atoms whose D row changed (:655, :711 keeps coefficient-only changes out of the count).
+ * ------------------------------------------------------------------------------------------ */
+uint64_t bo_update_dictionary_proximus(bo_word* E, bo_word* D, bo_word* A, uint64_t n, uint64_t m, uint64_t p) {
+  const uint64_t wpr = bo_wpr(m), apr = bo_wpr(p);
+  uint64_t changed = 0;
+  uint64_t* Dw = (uint64_t*)malloc(sizeof(uint64_t) * (m ? m : 1));
+  bo_word* newDk = (bo_word*)malloc(sizeof(bo_word) * (wpr ? wpr : 1));
+  for (uint64_t k = 0; k < p; k++) {
+    bo_word* Dk = D + k * wpr;
+    int kchanged = 0, converged;
+    do {
+      converged = 1;
+      /* ---- the atom: :627-668 */
+      uint64_t u = 0;
+      memset(Dw, 0, sizeof(uint64_t) * m);
+      for (uint64_t i = 0; i < n; i++) {
+        if (!mget(A, p, i, k)) continue;
+        u++;
+        for (uint64_t j = 0; j < m; j++)
+          if (mget(E, m, i, j) ^ mget(Dk, m, 0, j)) Dw[j]++;          /* add-back old atom, :637-643 */
+      }
+      if (u) {
+        u /= 2;                                                       /* :649 */
+        memcpy(newDk, Dk, sizeof(bo_word) * wpr);
+        for (uint64_t j = 0; j < m; j++) mset(newDk, m, 0, j, Dw[j] > u);
+        int dd = 0;
+        for (uint64_t b = 0; b < wpr; ++b) dd |= (newDk[b] != Dk[b]);
+        if (dd) {
+          for (uint64_t i = 0; i < n; i++) {                          /* :659-666 */
+            if (!mget(A, p, i, k)) continue;
+            for (uint64_t b = 0; b < wpr; ++b) E[i * wpr + b] ^= Dk[b] ^ newDk[b];
+          }
+          memcpy(Dk, newDk, sizeof(bo_word) * wpr);                   /* :655 */
+          converged = 0;
+          kchanged = 1;
+        }
+      }
+      /* ---- the coefficient column: :673-715. u = bits of the (updated) atom; Aw[i] = sum over them of E[i][j] xor A[i][k] */
+      u = 0;
+      for (uint64_t j = 0; j < m; j++) u += (uint64_t)mget(Dk, m, 0, j);
+      if (u) {
+        const uint64_t half = u / 2;
+        for (uint64_t i = 0; i < n; i++) {
+          const int a = mget(A, p, i, k);
+          uint64_t Aw = 0;
+          for (uint64_t j = 0; j < m; j++)
+            if (mget(Dk, m, 0, j) && (mget(E, m, i, j) ^ a)) Aw++;
+          const int na = Aw > half;
+          if (na != a) {                                              /* rows are independent: each patches its own E row */
+            mset(A, p, i, k, na);
+            for (uint64_t b = 0; b < wpr; ++b) E[i * wpr + b] ^= Dk[b];
+            converged = 0;
+          }
+        }
+      }
+    } while (!converged);
+    if (kchanged) changed++;
+  }
+  free(Dw); free(newDk);
+  (void)apr;
+  return changed;
+}

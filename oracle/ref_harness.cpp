@@ -359,4 +359,14 @@ u64 ref_learn_alter(int variant, const u64* X_words, u64* E_words, u64* D_words,
   return iters;
 }
 
+/* update_dictionary_proximus: bsvd.cpp:528-729 (E, D, A updated in place). */
+u64 ref_update_dictionary_proximus(u64* E_words, u64* D_words, u64* A_words, u64 n, u64 m, u64 p) {
+  binary_matrix E(n, m), D(p, m), A(n, p);
+  load(E, E_words); load(D, D_words); load(A, A_words);
+  const u64 changed = update_dictionary_proximus(E, D, A);
+  store(E, E_words); store(D, D_words); store(A, A_words);
+  E.destroy(); D.destroy(); A.destroy();
+  return changed;
+}
+
 } /* extern "C" */

@@ -78,6 +78,8 @@ class Oracle:
         L.bo_eg_encode_matrix.argtypes = [u64p, u64, u64, u8p, u64]
         L.bo_eg_decode_matrix.restype = C.c_int
         L.bo_eg_decode_matrix.argtypes = [u8p, u64, u64, u64, u64p]
+        L.bo_update_dictionary_proximus.restype = u64
+        L.bo_update_dictionary_proximus.argtypes = [u64p, u64p, u64p, u64, u64, u64]
         L.bo_transpose.argtypes = [u64p, u64, u64, u64p]
         L.bo_learn_alter.restype = u64
         L.bo_learn_alter.argtypes = [C.c_int, u64p, u64p, u64p, u64p, u64, u64, u64]
@@ -96,6 +98,11 @@ class Oracle:
         L.bo_mdl_result_info.argtypes = [C.c_void_p, u64p, u64p]
         L.bo_mdl_result_copy.argtypes = [C.c_void_p, u64p, u64p]
         L.bo_mdl_result_free.argtypes = [C.c_void_p]
+
+    def update_dictionary_proximus(self, E, D, A, m, p):
+        """in place on E, D, A; returns changed atoms"""
+        assert E.flags.c_contiguous and A.flags.c_contiguous and D.flags.c_contiguous
+        return int(self.lib.bo_update_dictionary_proximus(_p64(E), _p64(D), _p64(A), E.shape[0], m, p))
 
     def transpose(self, M, cols):
         M = np.ascontiguousarray(M, np.uint64)
@@ -295,6 +302,10 @@ class Reference:
         L.ref_eg.argtypes = [C.POINTER(C.c_int), u8p, u64, u64p]
         L.ref_fit_timed.restype = u64
         L.ref_fit_timed.argtypes = [u64p, u64, u64, u64, u64, C.c_long, C.POINTER(C.c_double), u64p, u64p, u64p]
+        self.has_proximus = hasattr(L, "ref_update_dictionary_proximus")
+        if self.has_proximus:
+            L.ref_update_dictionary_proximus.restype = u64
+            L.ref_update_dictionary_proximus.argtypes = [u64p, u64p, u64p, u64, u64, u64]
         self.has_alter = hasattr(L, "ref_learn_alter")
         if self.has_alter:
             L.ref_learn_alter.restype = u64
@@ -310,6 +321,9 @@ class Reference:
             L.ref_mdl_result_info.argtypes = [C.c_void_p, u64p, u64p]
             L.ref_mdl_result_copy.argtypes = [C.c_void_p, u64p, u64p]
             L.ref_mdl_result_free.argtypes = [C.c_void_p]
+
+    def update_dictionary_proximus(self, E, D, A, m, p):
+        return int(self.lib.ref_update_dictionary_proximus(_p64(E), _p64(D), _p64(A), E.shape[0], m, p))
 
     def learn_alter(self, variant, X, D, A, m, p):
         X = np.ascontiguousarray(X, np.uint64)

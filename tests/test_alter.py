@@ -66,3 +66,42 @@ def test_alter_vs_oracle(oracle, synth, rows, cols, W, K, seed, variant):
     assert it == ito
     assert np.array_equal(D.download(), Do) and np.array_equal(A.download(), Ao) and np.array_equal(E.download(), Eo)
     ctx.close()
+
+
+# ---------------------------------------------------------------- update_dictionary_proximus (src/bsvd.cpp:528-729)
+@pytest.mark.parametrize("rows,cols,W,K,seed", SHAPES[:4])
+def test_oracle_proximus_vs_reference(oracle, ref, synth, rows, cols, W, K, seed):
+    if not getattr(ref, "has_proximus", False):
+        pytest.skip("oracle/_ref built without the proximus wrapper")
+    m = W * W
+    X, D, A = inputs(oracle, synth, rows, cols, W, K, seed)
+    E = oracle.residual(X, A, D, m, K)
+    for it in range(3):
+        oracle.update_coefficients(E, D, A, m, K)
+        Er, Dr, Ar = E.copy(), D.copy(), A.copy()
+        cr = ref.update_dictionary_proximus(Er, Dr, Ar, m, K)
+        co = oracle.update_dictionary_proximus(E, D, A, m, K)
+        assert co == cr, f"iteration {it}"
+        assert np.array_equal(Er, E) and np.array_equal(Dr, D) and np.array_equal(Ar, A)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,W,K,seed", SHAPES)
+def test_proximus_vs_oracle(oracle, synth, rows, cols, W, K, seed):
+    import importlib
+    bic = importlib.import_module("binary-image-compression_b200")
+    ctx = bic.Context(0)
+    m = W * W
+    Xo, Do, Ao = inputs(oracle, synth, rows, cols, W, K, seed)
+    Eo = oracle.residual(Xo, Ao, Do, m, K)
+    n = Xo.shape[0]
+    X, E, D, A = ctx.matrix(n, m, Xo), ctx.matrix(n, m, Eo), ctx.matrix(K, m, Do), ctx.matrix(n, K, Ao)
+    for it in range(4):
+        assert ctx.update_coefficients(E, D, A) == oracle.update_coefficients(Eo, Do, Ao, m, K)
+        co = oracle.update_dictionary_proximus(Eo, Do, Ao, m, K)
+        assert ctx.update_dictionary_proximus(E, D, A) == co, f"iteration {it}"
+        assert np.array_equal(E.download(), Eo) and np.array_equal(D.download(), Do) and np.array_equal(A.download(), Ao)
+    E2 = ctx.matrix(n, m)
+    ctx.residual(X, A, D, E2)
+    assert np.array_equal(E2.download(), Eo)   # E is still A*D xor X
+    ctx.close()

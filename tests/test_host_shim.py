@@ -30,7 +30,7 @@ def test_shim_builds_and_keeps_the_reference_names():
                 "initialize_model_neighbor", "update_coefficients_omp", "update_dictionary_steepest", "learn_model_traditional",
                 "initialize_model", "update_coefficients", "update_dictionary", "learn_model", "random_seed", "set_grid_width",
                 "learn_model_mdl_forward_selection", "learn_model_mdl_backward_selection", "learn_model_mdl_full_search",
-                "learn_model_alter1", "learn_model_alter2", "learn_model_alter3",
+                "learn_model_alter1", "learn_model_alter2", "learn_model_alter3", "update_dictionary_proximus",
                 "model_codelength(binary_matrix const&, binary_matrix const&, binary_matrix const&)", "universal_codelength"]:
         assert sym in out, sym
 
@@ -48,6 +48,27 @@ def test_shim_selftest_binary():
     r = subprocess.run([str(HOST / "shim_selftest")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "shim selftest ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_driver_proximus_matches_reference_driver(tmp_path, synth):
+    """-d 1 (update_dictionary_proximus inside the traditional learner): same output files as the reference's driver"""
+    ref_bin = ROOT / "oracle" / "_ref" / "bsvd_test"
+    if not ref_bin.exists():
+        pytest.skip("oracle/_ref/bsvd_test not built")
+    _build()
+    page = synth.structured_page(200, 168, seed=5, salt=0.01)
+    pbm = tmp_path / "in.pbm"
+    _write_pbm(pbm, page)
+    flags = ["-I", "1", "-k", "12", "-r", "777", "-m", "0", "-M", "0", "-d", "1", "-w", "8"]
+    outs = {}
+    for name, exe in (("ref", ref_bin), ("b200", HOST / "bsvd_test_b200")):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([str(exe)] + flags + [str(pbm)], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+        outs[name] = {f: hashlib.md5((d / f).read_bytes()).hexdigest() for f in ("dictionary.pbm", "coefficients.pbm", "residual.pbm")}
+    assert outs["ref"] == outs["b200"]
 
 
 @pytest.mark.gpu
