@@ -212,7 +212,7 @@ __device__ __forceinline__ void hc_add(const ResolveParams& P, uint64_t idx, uin
 // Barrier over the ranks at the end of a kernel that pushed into the peers' windows: every thread fences its remote atomics,
 // the LAST CTA of the local grid tells every peer "rank r reached barrier e" and waits until every peer has said the same.
 // When the kernel ends, every rank's contributions to this rank's window have landed. One spinning thread per GPU; the wait is
-// bounded (about a second) and traps instead of hanging if a peer never arrives.
+// bounded (about half a minute) and traps instead of hanging if a peer never arrives.
 __device__ __forceinline__ void xgpu_barrier(const XPeers& x) {
   __threadfence_system();
   __syncthreads();
@@ -229,7 +229,7 @@ __device__ __forceinline__ void xgpu_barrier(const XPeers& x) {
         uint32_t spins = 0;
         while ((int32_t)(*(volatile uint32_t*)(me + r) - x.epoch) < 0) {
           __nanosleep(200);
-          if (++spins > (1u << 23)) __trap();
+          if (++spins > (1u << 27)) __trap();  // ~30 s: a peer that never arrives ends in an error, not a hang
         }
       }
       __threadfence_system();

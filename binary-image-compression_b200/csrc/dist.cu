@@ -317,7 +317,7 @@ __global__ void k_xgpu_barrier(XPeers x) {
       uint32_t spins = 0;
       while ((int32_t)(*(volatile uint32_t*)(me + r) - x.epoch) < 0) {
         __nanosleep(200);
-        if (++spins > (1u << 23)) __trap();
+        if (++spins > (1u << 27)) __trap();  // ~30 s: a peer that never arrives ends in an error, not a hang
       }
     }
     __threadfence_system();
