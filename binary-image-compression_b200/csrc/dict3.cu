@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
   if (warp == 0) warp_offsets(sCnt, sOff, P.p);
   cluster.sync();                          // every CTA of the cluster runs before any remote shared-memory access
   const bool bucketed = sOff[P.p] <= P.bucket_cap;
-  uint32_t cursor = 0, nchanged = 0;
+  uint32_t cursor = 0, nchanged = 0, nx = 0;  // nx: changes that needed an exchange (the sum buffers rotate on it)
   for (;;) {
     // first atom at or after the cursor that changes under the current histograms: it is the next one
     // to change in the reference's order (every earlier one is unchanged under the same H)
@@ -270,14 +270,23 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
     const uint32_t k = sFirst;
     if (k >= P.p) break;
     if (warp == 0) chain_decide(sH, sU, sD, k, P, sDelta + k * P.wprE);
+    if (bucketed && sCnt[k] == 0) {
+      // no row uses atom k together with a later atom: the change reaches no other histogram (same decision in every
+      // CTA, so nobody waits at a barrier)
+      __syncthreads();                       // sDelta[k] is complete before anyone moves on
+      if (tid == 0) sCh[k >> 5] |= 0x80000000u >> (k & 31);
+      nchanged++;
+      cursor = k + 1;
+      continue;
+    }
     for (uint32_t i = (k + 1) * hsC + tid; i < nC; i += CHAIN_THREADS) sCorr[i] = 0;
-    // Buffer rotation of the cluster-wide sums: change number c uses buffer c % 3. The buffer of change c + 1 is
+    // Buffer rotation of the cluster-wide sums: exchange number c (nx) uses buffer c % 3. The buffer of change c + 1 is
     // cleared here: it was last read after the barrier of change c - 2, and every CTA finished those reads before
     // it arrived at the barrier of change c - 1, which we have passed; nobody adds to it before the barrier of
     // change c, which we have not reached.
-    uint32_t* acc = sAcc + (nchanged % 3) * slice;
+    uint32_t* acc = sAcc + (nx % 3) * slice;
     {
-      uint32_t* nxt = sAcc + ((nchanged + 1) % 3) * slice;
+      uint32_t* nxt = sAcc + ((nx + 1) % 3) * slice;
       for (uint32_t i = tid; i < slice; i += CHAIN_THREADS) nxt[i] = 0;
     }
     __syncthreads();
@@ -332,6 +341,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
     }
     if (tid == 0) sCh[kw] |= kbit;
     nchanged++;
+    nx++;
     cursor = k + 1;
     // the __syncthreads at the top of the loop orders these writes before the next decisions
   }
