@@ -70,6 +70,7 @@ struct bic_ctx {
   int wait_mode = 0;       // how host threads wait for the stream: 0 cudaStreamSynchronize, 1 poll + sched_yield, 2 blocking event
   cudaEvent_t wait_ev = nullptr, wait_ev_blocking = nullptr;
   int gol_onepass = 0;     // 1: single-pass Golomb encoder (decoupled look-back) when the buffer is pre-sized
+  int coef_algo = 1;  // 1: dictionaries of >= 64 atoms use the weight-sorted warp-per-row coefficient kernel; 0: always lane per row
   int dict_algo = 2;  // 0: per-atom walk (dict.cu), 1: histogram first, resolve in order (dict2.cu), 2: cluster chain (dict3.cu) where the shape allows, else 1
   long long chain_bucket_cap = -1;  // entries of dict3.cu's per-atom buckets; -1 = 2 per row (0 forces the list-scan fallback)
   int chain_cluster = 16;  // CTAs in the cluster of dict3.cu's chain kernel (1, 2, 4, 8 or 16)

@@ -118,6 +118,138 @@ __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restric
   if ((threadIdx.x & 31) == 0 && nchanged) atomicAdd(changed, (unsigned long long)nchanged);
 }
 
+// ------------------------------------------------------------------ large dictionaries: a warp per row, atoms pruned by weight
+// With many atoms (p >= 64) most of them cannot win a pass: |E_i xor D_k| >= | |E_i| - |D_k| |. The CTA keeps the dictionary
+// in shared memory SORTED BY WEIGHT (with the original indices); a warp takes one row and visits atoms outward from the
+// row's own weight, 16 lighter and 16 heavier ones per round (one atom per lane), tightening the bound after every round:
+// an atom can only win, or tie with the current best, if | |E_i| - |D_k| | <= T = min(|E_i| - 1, best distance so far).
+// The sort makes the survivors two contiguous runs, so a round is skipped for ALL lanes at once -- which a lane-per-row
+// kernel cannot do. Exactness: every atom that could beat or tie the final best is evaluated (the bound is inclusive),
+// and the key (distance << 16 | original index) keeps the reference's lowest-index tie-break whatever the visiting order.
+template <int WORDS>
+__global__ void __launch_bounds__(256) k_update_coefficients_sorted(uint32_t* __restrict__ E, const uint32_t* __restrict__ D,
+                                                                    uint32_t* __restrict__ A, uint64_t n, uint64_t wprE, uint32_t p,
+                                                                    uint64_t wprA, unsigned long long* __restrict__ changed,
+                                                                    unsigned long long* __restrict__ next_row, uint32_t grab) {
+  constexpr int STR = WORDS + 1;                 // row stride of the sorted dictionary: consecutive atoms hit distinct banks
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint32_t* Ds = sm;                             // p * STR, sorted by (weight, original index)
+  uint32_t* ws = Ds + (size_t)p * STR;           // p weights, ascending
+  uint16_t* ks = (uint16_t*)(ws + p);            // p original indices
+  uint16_t* pos = ks + p;                        // p: sorted position of original atom k
+  uint32_t* wraw = (uint32_t*)(pos + p);         // p: weights in original order (scratch for the rank sort); ks + pos = 4p bytes
+  for (uint32_t k = threadIdx.x; k < p; k += blockDim.x) {
+    uint32_t w = 0;
+    for (uint32_t j = 0; j < (uint32_t)wprE; ++j) w += __popc(__ldg(D + (uint64_t)k * wprE + j));
+    wraw[k] = w;
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < p; k += blockDim.x) {  // rank sort, stable in the original index
+    const uint32_t w = wraw[k];
+    uint32_t r = 0;
+    for (uint32_t j = 0; j < p; ++j) r += (wraw[j] < w) || (wraw[j] == w && j < k);
+    ws[r] = w;
+    ks[r] = (uint16_t)k;
+    pos[k] = (uint16_t)r;
+    for (int j = 0; j < WORDS; ++j) Ds[(size_t)r * STR + j] = ((uint64_t)j < wprE) ? __ldg(D + (uint64_t)k * wprE + j) : 0u;
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t nchanged = 0;
+  for (;;) {
+    // rows are handed out `grab` at a time (blank rows cost almost nothing, text rows many rounds)
+    unsigned long long r0 = 0;
+    if (lane == 0) r0 = atomicAdd(next_row, (unsigned long long)grab);
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    if (r0 >= n) break;
+    const uint64_t r1 = (r0 + grab < n) ? r0 + grab : n;
+    for (uint64_t r = r0; r < r1; ++r) {
+      uint32_t e[WORDS];
+      uint32_t wt = 0;
+#pragma unroll
+      for (int j = 0; j < WORDS; ++j) {
+        e[j] = ((uint64_t)j < wprE) ? __ldg(E + r * wprE + j) : 0u;   // the same address in every lane: a broadcast
+        wt += __popc(e[j]);
+      }
+      bool row_changed = false;
+      while (wt) {                               // one greedy pass per trip (src/bsvd.cpp:1063-1099)
+        uint32_t T = wt - 1;                     // a winner needs distance < wt
+        uint32_t best = 0xFFFFFFFFu;             // distance << 16 | original index
+        // first position whose weight is >= wt (all lanes the same search)
+        uint32_t lo = 0, hi = p;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (ws[mid] < wt) lo = mid + 1; else hi = mid;
+        }
+        uint32_t left = lo, right = lo;          // atoms [left, right) have been visited
+        for (;;) {
+          // the nearest unvisited atom on either side decides whether that side still has candidates
+          const bool more_l = left > 0 && (wt - ws[left - 1]) <= T;
+          const bool more_r = right < p && (ws[right] - wt) <= T;
+          if (!more_l && !more_r) break;
+          uint32_t idx = 0xFFFFFFFFu;
+          if (lane < 16) { if (left > lane) idx = left - 1 - lane; }
+          else { if (right + (lane - 16) < p) idx = right + (lane - 16); }
+          uint32_t key = 0xFFFFFFFFu;
+          if (idx != 0xFFFFFFFFu) {
+            const uint32_t wk = ws[idx];
+            const uint32_t lb = wk > wt ? wk - wt : wt - wk;
+            if (lb <= T) {
+              const uint32_t* dk = Ds + (size_t)idx * STR;
+              uint32_t d = 0;
+#pragma unroll
+              for (int j = 0; j < WORDS; ++j) d += __popc(e[j] ^ dk[j]);
+              key = (d << 16) | ks[idx];
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+          best = min(best, key);
+          if ((best >> 16) < T) T = best >> 16;  // ties with the best so far must still be evaluated: inclusive bound
+          left = left > 16 ? left - 16 : 0;
+          right = right + 16 < p ? right + 16 : p;
+        }
+        const uint32_t bestd = best >> 16, bestk = best & 0xFFFFu;
+        if (best == 0xFFFFFFFFu || bestd >= wt) break;   // :1084, strict <
+        if (lane == 0) A[r * wprA + (bestk >> 5)] ^= 0x80000000u >> (bestk & 31);  // :1086
+        const uint32_t* dk = Ds + (size_t)pos[bestk] * STR;
+        wt = 0;
+#pragma unroll
+        for (int j = 0; j < WORDS; ++j) { e[j] ^= dk[j]; wt += __popc(e[j]); }     // :1087
+        row_changed = true;
+      }
+      if (row_changed) {
+        nchanged++;
+#pragma unroll
+        for (int j = 0; j < WORDS; ++j)
+          if (lane == (uint32_t)j && (uint64_t)j < wprE) E[r * wprE + j] = e[j];
+      }
+    }
+  }
+  if (lane == 0 && nchanged) atomicAdd(changed, (unsigned long long)nchanged);
+}
+
+template <int WORDS>
+static bic_status launch_coef_sorted(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, unsigned long long* d_changed) {
+  const uint64_t p = D->rows;
+  const size_t smem = (size_t)p * (WORDS + 1) * 4 + p * 12 + 16;
+  if (smem > 48 * 1024)
+    BIC_CUDA(c, cudaFuncSetAttribute(k_update_coefficients_sorted<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((200 * 1024) / smem);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  const int grid = bic_grid_for(c, E->rows * 4, 256, per_sm);   // a warp per row
+  // rows per grab: about four grabs per warp, between 8 and 128 (one global atomic each)
+  uint64_t grab = E->rows / ((uint64_t)grid * 8 * 4);
+  grab = grab < 8 ? 8 : (grab > 128 ? 128 : grab);
+  unsigned long long* next_row = (unsigned long long*)(c->d_scalars + 8);
+  BIC_CUDA(c, cudaMemsetAsync(next_row, 0, 8, c->stream));
+  BIC_PROF(c, KID_UPDATE_COEF);
+  k_update_coefficients_sorted<WORDS><<<grid, 256, smem, c->stream>>>(E->d, D->d, A->d, E->rows, E->wpr, (uint32_t)p, A->wpr, d_changed,
+                                                                     next_row, (uint32_t)grab);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
 // Fallback for rows wider than 32 words (m > 1024) or a dictionary that does not fit in shared
 // memory: one warp per row, the row staged in shared memory, D read through L1/L2.
 __global__ void __launch_bounds__(256) k_update_coefficients_wide(uint32_t* __restrict__ E, const uint32_t* __restrict__ D,
@@ -226,6 +358,15 @@ bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, b
   if (D->rows > 65535) return bic_fail(c, BIC_ERR_UNSUPPORTED, "update_coefficients: more than 65535 atoms");
   const uint64_t wpr = E->wpr;
   const int WORDS = wpr <= 1 ? 1 : wpr <= 2 ? 2 : wpr <= 4 ? 4 : wpr <= 8 ? 8 : wpr <= 16 ? 16 : wpr <= 32 ? 32 : 0;
+  // many atoms, rows of 4..32 words: the weight-sorted warp-per-row kernel ("coef_algo" 0 keeps the lane-per-row kernel)
+  if (c->coef_algo != 0 && WORDS >= 4 && D->rows >= 64 && (size_t)D->rows * (WORDS + 4) * 4 + 64 <= 200 * 1024) {
+    switch (WORDS) {
+      case 4: return launch_coef_sorted<4>(c, E, D, A, d_changed);
+      case 8: return launch_coef_sorted<8>(c, E, D, A, d_changed);
+      case 16: return launch_coef_sorted<16>(c, E, D, A, d_changed);
+      default: return launch_coef_sorted<32>(c, E, D, A, d_changed);
+    }
+  }
   if (WORDS && (size_t)D->rows * WORDS * 4 <= 200 * 1024) {
     switch (WORDS) {
       case 1: return launch_coef<1>(c, E, D, A, d_changed);

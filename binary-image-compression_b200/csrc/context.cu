@@ -573,6 +573,7 @@ extern "C" bic_status bic_ctx_set_option(bic_ctx* c, const char* name, int64_t v
   if (!strcmp(name, "wait_mode")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->wait_mode = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_onepass")) { c->gol_onepass = value != 0; return BIC_OK; }
   if (!strcmp(name, "dict_algo")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->dict_algo = (int)value; return BIC_OK; }
+  if (!strcmp(name, "coef_algo")) { if (value < 0 || value > 1) return BIC_ERR_INVALID; c->coef_algo = (int)value; return BIC_OK; }
   if (!strcmp(name, "chain_bucket_cap")) { c->chain_bucket_cap = value; return BIC_OK; }
   if (!strcmp(name, "chain_cluster")) {
     if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16) return BIC_ERR_INVALID;

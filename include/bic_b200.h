@@ -65,6 +65,8 @@ bic_status bic_ctx_wait_ctx(bic_ctx* waiter, bic_ctx* signal);
  * "dict_algo": how update_dictionary_steepest walks the atoms. 2 (default) = all atom histograms in one pass, then the
  *   in-order atom chain inside ONE thread-block cluster (dict3.cu) where the histograms fit shared memory, else 1;
  *   1 = same histograms, one launch per atom that changes (dict2.cu); 0 = one grid barrier per atom (dict.cu).
+ * "coef_algo": 1 (default) = dictionaries of >= 64 atoms use the weight-sorted warp-per-row coefficient kernel; 0 = always a
+ *   lane per row.
  * "chain_cluster": CTAs in dict3.cu's cluster, 1/2/4/8/16 (default 16, 8 where 16 cannot be co-scheduled).
  * "chain_bucket_cap": entries of dict3.cu's per-atom row buckets, -1 (default) = 2 per row; 0 = always scan the list.
  * "gol_onepass": 1 = single-pass Golomb encoder with decoupled look-back, 0 (default) = counts / lengths / scatter.
