@@ -363,3 +363,28 @@ def test_a4_page_properties(ctx, synth):
     assert info.iterations == iters and info.weight_E == E.weight()
     out, r, c = ctx.decode_raster(cont)
     assert np.array_equal(out, payload)
+
+
+@pytest.mark.parametrize("coef_algo", [1, 0])
+@pytest.mark.parametrize("rows,cols,W,K,seed", [(300, 280, 16, 64, 31), (256, 256, 16, 200, 32), (200, 320, 32, 96, 33), (260, 300, 12, 70, 34)])
+def test_coefficient_kernels_large_dictionary(ctx, oracle, synth, rows, cols, W, K, seed, coef_algo):
+    """dictionaries of >= 64 atoms: the weight-sorted warp-per-row coefficient kernel (coef_algo 1, default) and the
+    lane-per-row kernel (0) against the oracle, update by update (ties between atoms included: structured pages give many)"""
+    ctx.set_option("coef_algo", coef_algo)
+    try:
+        m = W * W
+        page = synth.structured_page(rows, cols, seed=seed, salt=0.02)
+        Xo = oracle.extract_patches(synth.pack_rows(page), rows, cols, W)
+        n = Xo.shape[0]
+        Do, Ao, _ = oracle.init_neighbor(Xo, m, K, 900 + seed)
+        Eo = oracle.residual(Xo, Ao, Do, m, K)
+        X, E, D, A = ctx.matrix(n, m, Xo), ctx.matrix(n, m, Eo), ctx.matrix(K, m, Do), ctx.matrix(n, K, Ao)
+        for it in range(3):
+            assert ctx.update_coefficients(E, D, A) == oracle.update_coefficients(Eo, Do, Ao, m, K), f"iteration {it}"
+            assert np.array_equal(E.download(), Eo) and np.array_equal(A.download(), Ao)
+            assert ctx.update_dictionary(E, D, A) == oracle.update_dictionary(Eo, Do, Ao, m, K)
+            assert np.array_equal(D.download(), Do) and np.array_equal(E.download(), Eo)
+        for M in (X, E, D, A):
+            M.destroy()
+    finally:
+        ctx.set_option("coef_algo", 1)
