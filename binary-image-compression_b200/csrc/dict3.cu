@@ -470,7 +470,8 @@ static int bic_chain_cluster_size(bic_ctx* c) {
 bool bic_dict_chain_eligible(bic_ctx* c, uint64_t n, uint64_t p, uint64_t wprE) {
   const uint64_t hs = wprE * 32, csize = (uint64_t)bic_chain_cluster_size(c);
   const uint64_t smem = (p * hs + p * (hs + 1) + 3 * div_up_u64(p * hs, csize) + 2 * p * wprE + 3 * p + div_up_u64(p, 32) + 8) * 4 + 8 * 1024 + 64;
-  return n < (1ull << 32) - 8 && smem + 1024 <= c->smem_optin && smem <= 200 * 1024;
+  return n < (1ull << 30) &&  // list indices and bucket offsets are 32-bit (a row sits in at most p - 1 buckets; the capacity is 2n)
+         smem + 1024 <= c->smem_optin && smem <= 200 * 1024;
 }
 
 bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
