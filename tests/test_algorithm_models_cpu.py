@@ -129,3 +129,74 @@ def test_weight_window_argmin_equals_brute_force():
         seen += ev
         total += p
     assert seen < total                                                   # the bound does prune
+
+
+# ---------------------------------------------------------------- coding.cu: closed-form coder state and the constant-k stretch
+def serial_golomb_ks(bits):
+    """k used for every sample by the serial coder (src/GolombCoder.cpp:29-34, src/Golomb.h:14-24), samples = zero runs
+    closed by the ones of `bits`"""
+    k, samples, acc, run, out = 1, 0, 0, 0, []
+    for b in bits:
+        if b:
+            out.append(k)
+            samples = (samples + 1) & 0xFFFFFFFF
+            acc = (acc + run) & 0xFFFFFFFF
+            k = 0
+            while ((samples << k) & 0xFFFFFFFF) < acc:
+                k += 1
+            run = 0
+        else:
+            run += 1
+    return out
+
+
+def closed_form_k(t, consumed):
+    """k of sample number t when `consumed` stream bits precede it (csrc/coding.cu golomb_k)"""
+    if t == 0:
+        return 1
+    acc = (consumed - t) & 0xFFFFFFFF
+    k = 0
+    while k < 31 and ((t << k) & 0xFFFFFFFF) < acc:
+        k += 1
+    return k
+
+
+def k_stable(t, consumed):
+    """csrc/coding.cu golomb_k_stable: k is the same for every sample of the next 128 bits"""
+    if t == 0 or t + 128 >= (1 << 31):
+        return None
+    acc = consumed - t
+    if acc + 128 >= (1 << 31):
+        return None
+    k = closed_form_k(t, consumed)
+    if ((t + 127) << k) >= (1 << 32) or (t << k) < acc + 128 or (k > 0 and ((t + 127) << (k - 1)) >= acc):
+        return None
+    return k
+
+
+@pytest.mark.parametrize("rho", [0.5, 0.2, 0.03, 0.004])
+def test_golomb_closed_form_and_constant_k_stretch(rho):
+    rng = np.random.default_rng(int(rho * 1000))
+    bits = (rng.random(60000 if rho >= 0.2 else 600000) < rho).astype(np.uint8)
+    ks = serial_golomb_ks(bits)
+    ones = np.nonzero(bits)[0]
+    # closed form: sample t starts after its predecessor's one, i.e. ones[t-1] + 1 bits are consumed
+    for t in range(len(ones)):
+        consumed = int(ones[t - 1]) + 1 if t else 0
+        assert closed_form_k(t, consumed) == ks[t]
+    # the fast path: a "thread" owns 128 consecutive bits; after its first one, if the stretch is certified stable every later
+    # one of the thread uses the certified k
+    certified = 0
+    for start in range(0, len(bits) - 128, 128):
+        a, b = np.searchsorted(ones, [start, start + 128])
+        mine = list(range(int(a), int(b)))
+        if len(mine) < 2:
+            continue
+        t1 = mine[0] + 1                                     # rank of the second sample of the thread
+        k = k_stable(t1, int(ones[mine[0]]) + 1)
+        if k is None:
+            continue
+        certified += 1
+        assert all(ks[t] == k for t in mine[1:])
+    if rho >= 0.03:
+        assert certified > 0                                 # the certificate needs a few thousand samples of history
