@@ -116,7 +116,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU reference arm (oracle/_ref = the reference's own code)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_sample(synth, args, planes, crop, seed_img, budget_s=30.0):
+def cpu_reference_sample(synth, args, planes, crop, seed_img, budget_s=30.0, keep_outputs=False):
     """Runs the reference fit (bsvd_test.cpp's sequence via ref_fit_timed) + its serial GolombCoder
     over D, A, E on `crop` x `crop` crops of the given planes. Returns (Mpixel/s, dict)."""
     from oracle_bindings import load_reference, Oracle
@@ -126,35 +126,71 @@ def cpu_reference_sample(synth, args, planes, crop, seed_img, budget_s=30.0):
         kind = "port"
         orc = Oracle()
     W, K = args.patch_width, args.atoms
-    cores = ref.max_threads() if ref is not None else 1
+    cores = 1
+    if ref is not None:
+        # all the host cores this process may use, set explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers,
+        # which would silently make this a one-thread baseline
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        ref.set_threads(cores)
+        cores = ref.max_threads()
     img = synth.smooth_pgm16(crop, crop, seed=seed_img)
     t_total, px, done = 0.0, 0, 0
     phases = np.zeros(6)
+    outputs = []
     for b in planes:
         I = synth.pack_rows(synth.bitplane(img, b))
         t0 = time.perf_counter()
         if ref is not None:
             it, times, (D, A, E) = ref.fit_timed(I, crop, crop, W, K, SEED, want_outputs=True)
             phases += np.array(times)
-            for M, c in ((D, W * W), (A, K), (E, W * W)):
-                ref.golomb_matrix(M, c)
+            bits = [ref.golomb_matrix(M, c) for M, c in ((D, W * W), (A, K), (E, W * W))]
         else:
             X = orc.extract_patches(I, crop, crop, W)
             D, A, _ = orc.init_neighbor(X, W * W, K, SEED)
             E, it, _ = orc.learn_traditional(X, D, A, W * W, K)
-            for M, c in ((D, W * W), (A, K), (E, W * W)):
-                orc.golomb_encode(M, c)
+            bits = [orc.golomb_encode(M, c)[1] for M, c in ((D, W * W), (A, K), (E, W * W))]
         t_total += time.perf_counter() - t0
+        if keep_outputs:
+            outputs.append({"plane": b, "I": I, "D": D, "A": A, "E": E, "iters": int(it), "bits": [int(x) for x in bits]})
         px += crop * crop
         done += 1
         if t_total > budget_s:
             break
+    frac = (crop * crop) / float(args.size * args.size)
     return px / 1e6 / t_total, {
         "kind": kind, "cores": cores,
-        "sample": f"{done} bitplanes of a {crop}x{crop} crop of the same synthetic PGM, {W}x{W} patches, {K} atoms, "
-                  f"fit to convergence + serial GolombCoder over D,A,E ({t_total:.1f} s of CPU)",
-        "seconds": t_total,
+        "sample": f"{done} of {args.planes} bitplanes, each a {crop}x{crop} crop (the top-left {frac:.4f} of the area) of the same "
+                  f"synthetic {args.size}x{args.size} PGM, {W}x{W} patches, {K} atoms, fit to convergence + serial GolombCoder "
+                  f"over D,A,E ({t_total:.1f} s of CPU on {cores} threads)",
+        "seconds": t_total, "crop_fraction_of_plane": frac, "planes_done": done, "outputs": outputs,
     }
+
+
+def gpu_parity_on_crops(ctx, outputs, crop, W, K):
+    """a number counts only if the bits match the CPU reference on that input. The GPU path (C ABI:
+    upload -> extract -> init -> learn -> Golomb) runs on exactly the crops the CPU leg just fitted and D, A, E, the
+    iteration count and the three Golomb bit counts are compared with what the reference returned. Raises on a mismatch."""
+    checked = 0
+    for o in outputs:
+        I = ctx.matrix(crop, crop, o["I"])
+        X = ctx.extract_patches(I, W)
+        n, m = X.rows, W * W
+        D, A, E = ctx.matrix(K, m), ctx.matrix(n, K), ctx.matrix(n, m)
+        ctx.initialize_model_neighbor(X, D, A, ctx.rand48(SEED))
+        it, _ = ctx.learn_model_traditional(X, E, D, A)
+        bits = [ctx.golomb_bitcount(M)[0] for M in (D, A, E)]
+        ok = (it == o["iters"] and bits == o["bits"] and np.array_equal(D.download(), o["D"])
+              and np.array_equal(A.download(), o["A"]) and np.array_equal(E.download(), o["E"]))
+        for M in (I, X, D, A, E):
+            M.destroy()
+        if not ok:
+            raise SystemExit(f"PARITY FAILURE on bitplane {o['plane']} of the {crop}x{crop} crop: GPU iterations {it} vs {o['iters']}, "
+                             f"Golomb bits {bits} vs {o['bits']}")
+        checked += 1
+    return checked
 
 
 def run_reference_arm(args):
@@ -652,8 +688,9 @@ def main():
             w0 = workers[0]
             comm = w0.ctx.comm_create(rank, world, uid.cpu().numpy())
             sh_iters = [0] * P
+            sh_rec = {}
 
-            def fit_sharded(b):
+            def fit_sharded(b, record=False):
                 c = w0.ctx
                 c._ck(L.bic_extract_patches(c.h, rasters[b].h, W, w0.X.h))
                 rng = c.rand48(SEED)
@@ -664,11 +701,45 @@ def main():
                 # D is replicated (every rank codes the same stream); A and E are row-sharded: each rank writes its
                 # rows' codewords as the exact substring of the single global stream (bic_dist_golomb_encode)
                 c._ck(L.bic_golomb_encode(c.h, w0.D.h, 256, w0.streams[0].h))
-                for M, s in zip((w0.A, w0.E), w0.streams[1:]):
-                    c._ck(L.bic_dist_golomb_encode(c.h, comm, M.h, 256, s.h, None))
+                shi = [bic.ShardInfo(), bic.ShardInfo()]
+                for M, s, si in zip((w0.A, w0.E), w0.streams[1:], shi):
+                    c._ck(L.bic_dist_golomb_encode(c.h, comm, M.h, 256, s.h, C.byref(si)))
+                if record:
+                    sh_rec[b] = {"D": w0.D.download(), "iters": int(it.value),
+                                 "bits": [int(w0.streams[0].info.bitcount), int(shi[0].global_bitcount), int(shi[1].global_bitcount)]}
 
             for b in range(P):
-                fit_sharded(b)
+                fit_sharded(b, record=True)
+            barrier()
+            # ---- correctness of the sharded path, in the bench itself: the dictionary, the iteration count and the GLOBAL Golomb
+            # bit counts of D, A, E must equal the single-GPU fit of the concatenated rows (rank 0 gathers the N bands)
+            sh_checked = 0
+            for b in range(P):
+                band = torch.from_numpy(host_planes[b]).to(dev)
+                if dist is not None:
+                    bands = [torch.empty_like(band) for _ in range(world)]
+                    dist.all_gather(bands, band)
+                else:
+                    bands = [band]
+                if rank == 0:
+                    whole = torch.cat(bands, dim=0).cpu().numpy()
+                    c = ctx
+                    Iall = c.matrix(world * rows, cols)
+                    Iall.upload_pbm(whole)
+                    Xall = c.extract_patches(Iall, W)
+                    Dall, Aall, Eall = c.matrix(K, m), c.matrix(Xall.rows, K), c.matrix(Xall.rows, m)
+                    c.initialize_model_neighbor(Xall, Dall, Aall, c.rand48(SEED))
+                    it1, _ = c.learn_model_traditional(Xall, Eall, Dall, Aall)
+                    bits1 = [c.golomb_bitcount(M)[0] for M in (Dall, Aall, Eall)]
+                    rec = sh_rec[b]
+                    ok = it1 == rec["iters"] and bits1 == rec["bits"] and np.array_equal(Dall.download(), rec["D"])
+                    for M in (Iall, Xall, Dall, Aall, Eall):
+                        M.destroy()
+                    if not ok:
+                        raise SystemExit(f"PARITY FAILURE: row-sharded fit of bitplane {b} over {world} rank(s) differs from the single-GPU fit of the "
+                                         f"concatenated rows (iterations {rec['iters']} vs {it1}, Golomb bits {rec['bits']} vs {bits1})")
+                    sh_checked += 1
+                del band, bands
             barrier()
             coll0 = w0.ctx.comm_collectives(comm)
             w0.ctx.timer_start()
@@ -680,22 +751,34 @@ def main():
             sharded = {"value": world * px_step / (ms_sh / 1e3), "unit": UNIT, "ms_per_step": ms_sh,
                        "collectives_per_step": (w0.ctx.comm_collectives(comm) - coll0) / args.steps,
                        "iterations_per_plane": sh_iters,
+                       "parity_checked": bool(sh_checked == P) if rank == 0 else None, "parity_planes": sh_checked,
+                       "parity_how": "D, the iteration count and the global Golomb bit counts of D, A, E of every plane equal the single-GPU "
+                                     "fit of the concatenated rows (run on rank 0 inside this bench)",
                        "what": f"each plane is ONE {world * S}x{S} image whose patch rows are sharded over {world} rank(s); one "
                                "dictionary per plane; one NCCL allreduce of atom statistics per iteration, the corrections of an atom that changes pushed into every "
                                "rank's histograms by the fix kernel over NVLink peer memory (BIC_DIST_FUSED=0: one more allreduce per changed atom); seam-exact sharded Golomb coding; "
                                "one stream, planes in sequence"}
             w0.ctx.comm_destroy(comm)
+        except SystemExit:
+            raise
         except Exception as ex:  # the extra measurement must not void the main numbers
             sharded = {"value": None, "unit": UNIT, "error": f"{type(ex).__name__}: {ex}"}
 
     # ---- CPU baseline (rank 0, N == 1): the reference's own code on a bounded crop
     cpu = None
+    parity_planes = 0
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, info = cpu_reference_sample(synth, args, list(range(P)), args.cpu_crop, 2)
-            cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+            v, info = cpu_reference_sample(synth, args, list(range(P)), args.cpu_crop, 2, keep_outputs=True)
+            cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
+                   "crop_fraction_of_plane": info["crop_fraction_of_plane"]}
         except Exception as ex:  # the checker missing must not void the GPU number
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"{type(ex).__name__}: {ex}"}
+            info = None
+        if info is not None and info["outputs"]:
+            # the same crops through the GPU path, bit for bit against what the reference just produced (a mismatch ends
+            # the run with a non-zero exit code: no line is printed)
+            parity_planes = gpu_parity_on_crops(ctx, info["outputs"], args.cpu_crop, W, K)
 
     if rank == 0:
         line = {
@@ -715,6 +798,10 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity_checked": parity_planes > 0, "parity_planes": parity_planes,
+            "parity_how": (f"D, A, E, iteration count and the Golomb bit counts of D, A, E of {parity_planes} bitplane crops "
+                           f"({args.cpu_crop}x{args.cpu_crop}) compared bit for bit with the CPU reference's outputs of the cpu_baseline leg"
+                           if parity_planes else "not run (no cpu_baseline leg in this invocation)"),
         }
         if sharded is not None:
             line["row_sharded"] = sharded

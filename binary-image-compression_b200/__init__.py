@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
         "bic_dist_learn_model_traditional": [_vp, _vp, _vp, _vp, _vp, _vp, _u64p, _u64p, _u64],
         "bic_learn_model_traditional_batched": [_vp, C.c_uint32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _u64p],
         "bic_dist_golomb_encode": [_vp, _vp, _vp, C.c_uint32, _vp, C.POINTER(ShardInfo)],
+        "bic_golomb_encode_shard": [_vp, _vp, C.c_uint32, _u64, _u64, C.c_int64, _u64, C.c_int, _u64, _vp, C.POINTER(ShardInfo)],
         "bic_stream_create": [_vp, C.POINTER(_vp)],
         "bic_stream_destroy": [_vp, _vp],
         "bic_stream_get_info": [_vp, C.POINTER(StreamInfo)],
@@ -533,6 +534,16 @@ class Context:
         out = out or Stream(self)
         si = ShardInfo()
         self._ck(self.L.bic_dist_golomb_encode(self.h, comm, M.h, chunk_samples, out.h, C.byref(si)))
+        return out, si
+
+    def golomb_encode_shard(self, M: Matrix, ones_before: int, bits_before: int, last_one_before: int, code_bits_before: int,
+                            closing: bool, total_bits: int, out: "Stream | None" = None, chunk_samples: int = 256, lengths_only=False):
+        """M's rows coded as a substring of the one global stream, the prefix state given explicitly; returns (Stream, ShardInfo)"""
+        if not lengths_only:
+            out = out or Stream(self)
+        si = ShardInfo()
+        self._ck(self.L.bic_golomb_encode_shard(self.h, M.h, chunk_samples, ones_before, bits_before, last_one_before, code_bits_before,
+                                                int(closing), total_bits, None if lengths_only else out.h, C.byref(si)))
         return out, si
 
     # ---- coding

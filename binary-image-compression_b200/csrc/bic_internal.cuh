@@ -49,6 +49,8 @@ enum bic_kernel_id {
   KID_COUNT
 };
 
+#define BIC_SCALARS 512
+
 struct bic_prof_rec { int kid; cudaEvent_t e0, e1; };
 
 struct bic_ctx {
@@ -61,8 +63,8 @@ struct bic_ctx {
   std::string err;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // pinned host scalars for results read back after a kernel
-  uint64_t* h_scalars = nullptr;  // 64 entries
-  uint64_t* d_scalars = nullptr;  // 64 entries
+  uint64_t* h_scalars = nullptr;  // BIC_SCALARS entries
+  uint64_t* d_scalars = nullptr;  // BIC_SCALARS entries; [0, 64) per-call results, [128, 512) staging of small collectives
   // grow-only scratch areas
   bic_scratch staging;    // host-layout staging for uploads/downloads
   bic_scratch work[6];    // per-algorithm work buffers
@@ -71,6 +73,7 @@ struct bic_ctx {
   cudaEvent_t wait_ev = nullptr, wait_ev_blocking = nullptr;
   int gol_onepass = 0;     // 1: single-pass Golomb encoder (decoupled look-back) when the buffer is pre-sized
   int coef_algo = 1;  // 1: dictionaries of >= 64 atoms use the weight-sorted warp-per-row coefficient kernel; 0: always lane per row
+  int dict_update = 0;  // which dictionary update the learners call: 0 update_dictionary_steepest, 1 update_dictionary_proximus (the reference's -d 1)
   int dict_algo = 2;  // 0: per-atom walk (dict.cu), 1: histogram first, resolve in order (dict2.cu), 2: cluster chain (dict3.cu) where the shape allows, else 1
   long long chain_bucket_cap = -1;  // entries of dict3.cu's per-atom buckets; -1 = 2 per row (0 forces the list-scan fallback)
   int chain_cluster = 16;  // CTAs in the cluster of dict3.cu's chain kernel (1, 2, 4, 8 or 16)
@@ -126,6 +129,15 @@ bic_status bic_zero_scalars(bic_ctx* ctx);
 #define BIC_HD
 #endif
 BIC_HD static inline uint64_t div_up_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// rows * ceil(cols / 32) * 4 bytes and rows * cols bits must fit comfortably in 64 bits (and in what a device can hold:
+// 2^44 bytes = 16 TB is far beyond any HBM, so anything larger is a corrupt header or a caller bug, not a request)
+static inline bool bic_shape_ok(uint64_t rows, uint64_t cols) {
+  if (cols > (1ull << 40) || rows > (1ull << 40)) return false;
+  const uint64_t wpr = div_up_u64(cols, 32);
+  if (rows && wpr > (1ull << 42) / rows) return false;
+  return true;
+}
 
 // persistent-grid sizing: a multiple of the SM count
 static inline int bic_grid_for(const bic_ctx* ctx, uint64_t work_items, int per_block, int blocks_per_sm) {

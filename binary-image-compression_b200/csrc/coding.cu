@@ -702,7 +702,7 @@ __global__ void k_gol_decode(const uint32_t* __restrict__ in, unsigned long long
     unsigned long long o = index[2 * ch], pos = index[2 * ch + 1];
     unsigned long long t = ch * chunk;
     const unsigned long long tend = (t + chunk < nsamples) ? t + chunk : nsamples;
-    bool bad = (o > bitcount) || (pos > N);
+    bool bad = (o >= bitcount) || (pos > N);  // every chunk holds at least one codeword (>= 1 bit)
     for (; t < tend && !bad; ++t) {
       const uint32_t k = golomb_k(t, pos);
       const uint32_t rem = k ? (peek32(in, o) >> (32 - k)) : 0u;  // readBits(k), GolombDecoder.cpp:17
@@ -794,11 +794,27 @@ __global__ void k_first_zero(const uint32_t* __restrict__ in, unsigned long long
 }
 
 __global__ void k_eg_decode(const uint32_t* __restrict__ in, uint64_t rows, uint64_t cols, uint64_t wpr,
-                            const unsigned long long* __restrict__ first_zero, uint32_t* __restrict__ M) {
+                            const unsigned long long* __restrict__ first_zero, uint32_t* __restrict__ M,
+                            unsigned long long bitcount, unsigned long long* __restrict__ err) {
   const unsigned long long z = *first_zero;  // code position; ~0 if the matrix is all zero
   const uint64_t total = rows * wpr;
+  // what the coder always writes must be there: the extra zero right after the first input one's zero, the one that
+  // ends every row, and a length that says whether the extra bit exists
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    bool bad = (z == ~0ull) ? (bitcount != rows * (cols + 1)) : (bitcount != rows * (cols + 1) + 1);
+    if (!bad && z != ~0ull) {
+      const unsigned long long o = z + 1;
+      bad = (bswap32(__ldg(in + (o >> 5))) >> (31 - (unsigned)(o & 31))) & 1u;
+    }
+    if (bad) atomicAdd(err, 1ull);
+  }
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t r = i / wpr, w = i - r * wpr;
+    if (w == wpr - 1) {  // end-of-row one
+      unsigned long long o = r * (cols + 1) + cols;
+      if (o > z) o += 1;
+      if (o >= bitcount || !((bswap32(__ldg(in + (o >> 5))) >> (31 - (unsigned)(o & 31))) & 1u)) atomicAdd(err, 1ull);
+    }
     uint32_t v = 0;
     for (int b = 0; b < 32; ++b) {
       const uint64_t cc = w * 32 + b;
@@ -837,6 +853,7 @@ extern "C" bic_status bic_stream_get_info(const bic_stream* s, bic_stream_info* 
 }
 
 static bic_status stream_reserve(bic_ctx* c, bic_stream* s, uint64_t bitcount, uint64_t nchunks, uint64_t src_bits = 0) {
+  if (bitcount > (1ull << 45) || nchunks > (1ull << 40)) return bic_fail(c, BIC_ERR_INVALID, "stream size overflows");
   // whole 32-bit words plus slack so peek32 / put_bits may touch one word past the end
   size_t need = (size_t)(div_up_u64(bitcount, 32) * 4 + 16);
   // cudaMalloc/cudaFree stall every stream of the device, so a stream object is sized once for
@@ -1112,6 +1129,66 @@ extern "C" bic_status bic_dist_golomb_encode(bic_ctx* c, bic_comm* m, const bic_
   return BIC_OK;
 }
 
+// The same for a caller that does its own plumbing (MPI, files, a second process ...): the prefix state of the shard is an
+// explicit input. ones_before / bits_before / last_one_before describe the rows that precede M in the one global matrix,
+// code_bits_before the code bits their ones produced (0 is fine when only the shard's own length is wanted: pass out = NULL).
+extern "C" bic_status bic_golomb_encode_shard(bic_ctx* c, const bic_mat* M, uint32_t chunk_samples, uint64_t ones_before,
+                                              uint64_t bits_before, int64_t last_one_before, uint64_t code_bits_before, int closing,
+                                              uint64_t total_bits, bic_stream* out, bic_shard_info* shard) {
+  if (!c || !M) return BIC_ERR_INVALID;
+  cudaSetDevice(c->device);
+  if (last_one_before < -1 || (last_one_before >= 0 && (uint64_t)last_one_before >= bits_before) ||
+      (closing && total_bits < bits_before + M->rows * M->cols))
+    return bic_fail(c, BIC_ERR_INVALID, "golomb_encode_shard: inconsistent prefix state");
+  if (chunk_samples == 0) chunk_samples = 256;
+  while (chunk_samples & (chunk_samples - 1)) chunk_samples++;
+  GolWork w;
+  BIC_TRY(golomb_counts(c, M, &w));
+  GolBase base = gol_base_single();
+  base.closing = 0;
+  base.t0 = ones_before; base.pos0 = (long long)bits_before; base.prev0 = (long long)last_one_before;
+  BIC_TRY(golomb_lengths(c, &w, base));
+  const uint64_t ones = c->h_scalars[1] - 1, bits_mine = c->h_scalars[2];
+  const long long last_global = c->h_scalars[3] ? (long long)(bits_before + c->h_scalars[3] - 1) : (long long)last_one_before;
+  uint64_t local_bits = bits_mine, local_samples = ones, closing_bits = 0;
+  base.code0 = code_bits_before;
+  base.out0 = code_bits_before & 31;
+  base.chunk0 = div_up_u64(base.t0, chunk_samples);
+  if (closing) {
+    const uint64_t consumed = (uint64_t)(last_global + 1);
+    const uint32_t kc = golomb_k_host(ones_before + ones, consumed);
+    closing_bits = kc + ((total_bits - consumed) >> kc) + 1;
+    base.closing = 1;
+    base.close_t = ones_before + ones;
+    base.close_consumed = consumed;
+    base.close_off = bits_mine;
+    local_bits += closing_bits;
+    local_samples += 1;
+  }
+  const uint64_t nchunks = div_up_u64(base.t0 + local_samples, chunk_samples) - base.chunk0;
+  if (shard) {
+    memset(shard, 0, sizeof(*shard));
+    shard->global_bitcount = closing ? code_bits_before + local_bits : 0;   // only the last shard knows it
+    shard->global_nsamples = closing ? ones_before + ones + 1 : 0;
+    shard->code_bit_offset = code_bits_before;
+    shard->local_code_bits = local_bits;
+    shard->first_chunk = base.chunk0;
+    shard->local_chunks = nchunks;
+  }
+  if (!out) return BIC_OK;
+  BIC_TRY(stream_reserve(c, out, base.out0 + local_bits, nchunks, w.N));
+  BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, (size_t)(div_up_u64(base.out0 + local_bits, 32) * 4 + 16), c->stream));
+  BIC_TRY(golomb_scatter(c, &w, base, closing ? total_bits : 0, chunk_samples, out));
+  out->info.coder = BIC_CODER_GOLOMB;
+  out->info.chunk_samples = chunk_samples;
+  out->info.rows = M->rows;
+  out->info.cols = M->cols;
+  out->info.bitcount = base.out0 + local_bits;
+  out->info.nsamples = local_samples;
+  out->info.nchunks = nchunks;
+  return BIC_OK;
+}
+
 extern "C" bic_status bic_golomb_decode(bic_ctx* c, const bic_stream* s, bic_mat* M) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !s || !M) return BIC_ERR_INVALID;
@@ -1193,6 +1270,7 @@ extern "C" bic_status bic_eg_decode(bic_ctx* c, const bic_stream* s, bic_mat* M)
   if (s->info.bitcount != N + M->rows && s->info.bitcount != N + M->rows + 1)
     return bic_fail(c, BIC_ERR_CORRUPT, "eg_decode: bit count does not match the shape");
   BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0xFF, 8, c->stream));
+  BIC_CUDA(c, cudaMemsetAsync(c->d_scalars + 1, 0, 8, c->stream));
   if (s->info.bitcount) {
     BIC_PROF(c, KID_EG_FIRST);
     k_first_zero<<<bic_grid_for(c, div_up_u64(s->info.bitcount, 32), 256, 8), 256, 0, c->stream>>>(
@@ -1202,9 +1280,12 @@ extern "C" bic_status bic_eg_decode(bic_ctx* c, const bic_stream* s, bic_mat* M)
   if (M->words()) {
     BIC_PROF(c, KID_EG_DECODE);
     k_eg_decode<<<bic_grid_for(c, M->words(), 256, 8), 256, 0, c->stream>>>((const uint32_t*)s->d_bytes, M->rows, M->cols,
-                                                                          M->wpr, (const unsigned long long*)c->d_scalars, M->d);
+                                                                          M->wpr, (const unsigned long long*)c->d_scalars, M->d,
+                                                                          s->info.bitcount, (unsigned long long*)c->d_scalars + 1);
     BIC_LAUNCH_CHECK(c);
   }
+  BIC_TRY(bic_read_scalars(c, 2));
+  if (c->h_scalars[1]) return bic_fail(c, BIC_ERR_CORRUPT, "eg_decode: stream is not an EG code of the stated shape");
   return BIC_OK;
 }
 

@@ -2,6 +2,8 @@
 // reductions (weight / dist / xor). Reference interfaces: src/binmat.h:29-232.
 #include "bic_internal.cuh"
 
+#include <mutex>
+
 #include <new>
 
 // ---------------------------------------------------------------------------------------------
@@ -27,9 +29,9 @@ static bic_status ctx_init(bic_ctx* c, int device, void* stream, bool own) {
   BIC_CUDA(c, cudaEventCreate(&c->ev1));
   BIC_CUDA(c, cudaEventCreateWithFlags(&c->wait_ev, cudaEventDisableTiming));
   BIC_CUDA(c, cudaEventCreateWithFlags(&c->wait_ev_blocking, cudaEventDisableTiming | cudaEventBlockingSync));
-  BIC_CUDA(c, cudaMallocHost(&c->h_scalars, 64 * sizeof(uint64_t)));
-  BIC_CUDA(c, cudaMalloc(&c->d_scalars, 64 * sizeof(uint64_t)));
-  BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, 64 * sizeof(uint64_t), c->stream));
+  BIC_CUDA(c, cudaMallocHost(&c->h_scalars, BIC_SCALARS * sizeof(uint64_t)));
+  BIC_CUDA(c, cudaMalloc(&c->d_scalars, BIC_SCALARS * sizeof(uint64_t)));
+  BIC_CUDA(c, cudaMemsetAsync(c->d_scalars, 0, BIC_SCALARS * sizeof(uint64_t), c->stream));
   return BIC_OK;
 }
 
@@ -193,6 +195,7 @@ extern "C" bic_status bic_mat_create(bic_ctx* c, uint64_t rows, uint64_t cols, b
   m->rows = rows;
   m->cols = cols;
   m->wpr = div_up_u64(cols, 32);
+  if (!bic_shape_ok(rows, cols)) { delete m; c->err = "matrix shape overflows"; return BIC_ERR_INVALID; }
   size_t bytes = (size_t)(m->rows * m->wpr) * 4;
   m->alloc_bytes = ((bytes + 255) & ~(size_t)255) + 256;
   cudaSetDevice(c->device);
@@ -211,6 +214,8 @@ extern "C" bic_status bic_mat_create(bic_ctx* c, uint64_t rows, uint64_t cols, b
 bic_status bic_mat_create_pooled(bic_ctx* c, uint64_t rows, uint64_t cols, bic_mat** out) {
   *out = nullptr;
   static bool threshold_set[64] = {false};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
   if (c->device < 64 && !threshold_set[c->device]) {  // keep freed blocks in the pool instead of returning them to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
@@ -226,6 +231,7 @@ bic_status bic_mat_create_pooled(bic_ctx* c, uint64_t rows, uint64_t cols, bic_m
   m->cols = cols;
   m->wpr = div_up_u64(cols, 32);
   m->pooled = true;
+  if (!bic_shape_ok(rows, cols)) { delete m; c->err = "matrix shape overflows"; return BIC_ERR_INVALID; }
   const size_t bytes = (size_t)(m->rows * m->wpr) * 4;
   m->alloc_bytes = ((bytes + 255) & ~(size_t)255) + 256;
   if (cudaMallocAsync((void**)&m->d, m->alloc_bytes, c->stream) != cudaSuccess) {
@@ -573,6 +579,7 @@ extern "C" bic_status bic_ctx_set_option(bic_ctx* c, const char* name, int64_t v
   if (!strcmp(name, "wait_mode")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->wait_mode = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_onepass")) { c->gol_onepass = value != 0; return BIC_OK; }
   if (!strcmp(name, "dict_algo")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->dict_algo = (int)value; return BIC_OK; }
+  if (!strcmp(name, "dict_update")) { if (value < 0 || value > 1) return BIC_ERR_INVALID; c->dict_update = (int)value; return BIC_OK; }
   if (!strcmp(name, "coef_algo")) { if (value < 0 || value > 1) return BIC_ERR_INVALID; c->coef_algo = (int)value; return BIC_OK; }
   if (!strcmp(name, "chain_bucket_cap")) { c->chain_bucket_cap = value; return BIC_OK; }
   if (!strcmp(name, "chain_cluster")) {

@@ -17,6 +17,8 @@
 // Integer atomics are order independent, so the result is deterministic and bit exact.
 #include "bic_internal.cuh"
 
+#include <mutex>
+
 
 // ------------------------------------------------------------------ pass 1
 // H = A^T * E as integer counts: H[k][j] = sum_i A[i][k] * E[i][j] = popc(column k of A AND column j
@@ -570,6 +572,8 @@ bic_status bic_k_transpose_A(bic_ctx* c, const bic_mat* A, uint32_t* AT, uint64_
 // window (<= 32 KB) + correction counters (<= 16 KB) + the static user queue (16 KB) can pass the 48 KB default
 static bic_status resolve_step_smem_optin(bic_ctx* c) {
   static bool done[64] = {false};
+  static std::mutex mu;  // contexts of several host threads come through here at once
+  std::lock_guard<std::mutex> lk(mu);
   if (c->device < 64 && done[c->device]) return BIC_OK;
   BIC_CUDA(c, cudaFuncSetAttribute(k_dict_resolve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   BIC_CUDA(c, cudaFuncSetAttribute(k_dict_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));  // + 16 KB static

@@ -22,6 +22,8 @@
 #include "bic_internal.cuh"
 
 #include <cooperative_groups.h>
+
+#include <mutex>
 namespace cg = cooperative_groups;
 
 static const int CHAIN_THREADS = 1024;
@@ -444,6 +446,8 @@ bic_status bic_k_dict_hist_compact(bic_ctx* c, const bic_mat* E, const bic_mat* 
 static int bic_chain_cluster_size(bic_ctx* c) {
   if (c->chain_cluster != 16) return c->chain_cluster;
   static int ok16[64] = {0};  // 0 unknown, 1 yes, -1 no
+  static std::mutex mu;       // contexts of several host threads come through here at once
+  std::lock_guard<std::mutex> lk(mu);
   const int d = c->device < 64 ? c->device : 63;
   if (ok16[d] == 0) {
     cudaFuncSetAttribute(k_dict_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
@@ -525,11 +529,15 @@ bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const 
   P.changed = d_changed; P.p = (uint32_t)p; P.wprE = (uint32_t)wprE; P.wprA = (uint32_t)wprA; P.hs = (uint32_t)hs; P.m = E->cols;
   const unsigned csize = (unsigned)bic_chain_cluster_size(c);
   const size_t smem = (size_t)(p * hs + p * (hs + 1) + 2 * p * wprE + 3 * p + 1 + wprA + 3 * div_up_u64(p * hs, csize)) * 4;
-  static size_t optin_done[64] = {0};
-  if (c->device >= 64 || optin_done[c->device] < smem) {
-    BIC_CUDA(c, cudaFuncSetAttribute(k_dict_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    BIC_CUDA(c, cudaFuncSetAttribute(k_dict_chain, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));  // chain_cluster = 16
-    if (c->device < 64) optin_done[c->device] = 200 * 1024;
+  {
+    static size_t optin_done[64] = {0};
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (c->device >= 64 || optin_done[c->device] < smem) {
+      BIC_CUDA(c, cudaFuncSetAttribute(k_dict_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+      BIC_CUDA(c, cudaFuncSetAttribute(k_dict_chain, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));  // chain_cluster = 16
+      if (c->device < 64) optin_done[c->device] = 200 * 1024;
+    }
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

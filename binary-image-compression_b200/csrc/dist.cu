@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <nccl.h>
 
+#include <mutex>
 #include <vector>
 
 struct NcclApi {
@@ -31,11 +32,14 @@ struct NcclApi {
   bool ok = false;
 };
 
+static NcclApi* nccl_load(NcclApi& api);
 static NcclApi* nccl_api() {
   static NcclApi api;
-  static bool tried = false;
-  if (tried) return api.ok ? &api : nullptr;
-  tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] { nccl_load(api); });
+  return api.ok ? &api : nullptr;
+}
+static NcclApi* nccl_load(NcclApi& api) {
   // 1. a libnccl.so.2 some other component of the process (e.g. torch) already mapped; 2. the one
   // BIC_NCCL_LIB names; 3. the system one. Two different NCCL builds in one process do not mix.
   void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
@@ -63,7 +67,7 @@ struct bic_comm {
   std::vector<uint32_t*> peer_win;       // every rank's window as mapped here (own = win)
   uint32_t** d_peer_win = nullptr;       // the same table in device memory
   uint32_t epoch = 0;                    // barriers used so far
-  const uint32_t* last_extra = nullptr;  // where the last dictionary update left the summed changed-rows count (two u32 halves)
+  const uint32_t* last_extra = nullptr;  // where the last dictionary update left the summed changed-rows count (three 22-bit limbs)
 };
 
 #define BIC_NCCL(ctx, expr)                                                                   \
@@ -261,8 +265,10 @@ static bic_status window_reserve(bic_ctx* c, bic_comm* m, size_t data_words) {
   }
   // handles (64 bytes each) + an "ok" byte per rank through NCCL; staged in a small device buffer
   const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
-  uint8_t* d_rec = nullptr;
-  BIC_CUDA(c, cudaMalloc((void**)&d_rec, rec * m->nranks));
+  // the staging record lives in the context's scalar area: no allocation here that could fail on one rank only -- a rank that
+  // returned early would leave the others hanging in the allgather below
+  if (rec * m->nranks > (BIC_SCALARS - 128) * 8) return bic_fail(c, BIC_ERR_UNSUPPORTED, "too many ranks for the peer-window exchange");
+  uint8_t* d_rec = (uint8_t*)(c->d_scalars + 128);
   std::vector<uint8_t> h_rec(rec * m->nranks, 0);
   memcpy(h_rec.data() + rec * m->rank, &mine, sizeof(mine));
   h_rec[rec * m->rank + sizeof(mine)] = (uint8_t)ok;
@@ -271,7 +277,6 @@ static bic_status window_reserve(bic_ctx* c, bic_comm* m, size_t data_words) {
   m->collectives++;
   BIC_CUDA(c, cudaMemcpyAsync(h_rec.data(), d_rec, rec * m->nranks, cudaMemcpyDeviceToHost, c->stream));
   BIC_CUDA(c, bic_wait_stream(c));
-  cudaFree(d_rec);
   for (int r = 0; r < m->nranks; ++r) ok &= h_rec[rec * r + sizeof(mine)];
   m->peer_win.assign(m->nranks, nullptr);
   if (ok) {
@@ -324,6 +329,13 @@ __global__ void k_xgpu_barrier(XPeers x) {
   }
 }
 
+__global__ void k_split_u64_limbs(const unsigned long long* __restrict__ in, uint32_t* __restrict__ limbs) {
+  const unsigned long long v = *in;
+  limbs[0] = (uint32_t)(v & 0x3FFFFFu);
+  limbs[1] = (uint32_t)((v >> 22) & 0x3FFFFFu);
+  limbs[2] = (uint32_t)(v >> 44);   // < 2^20
+}
+
 // ------------------------------------------------------------------ update_dictionary_steepest, sharded
 // d_counts[0] (changed rows of the preceding coefficient update, local) is summed over ranks in the same
 // allreduce as H and U; d_counts[1] receives the changed atoms (identical on every rank).
@@ -339,10 +351,12 @@ static bic_status dist_update_dictionary(bic_ctx* c, bic_comm* m, bic_mat* E, bi
   BIC_TRY(window_reserve(c, m, hwords + D->rows + 64));
   const bool fused = (m->fused == 1);
   BIC_TRY(bic_k_dict_prepare(c, E, D, A, &w, fused ? m->win + XWIN_DATA : nullptr));
-  // [H | U | extra]: extra[0..1] carries the 64-bit changed-rows count as two u32 halves
-  BIC_CUDA(c, cudaMemcpyAsync(w.extra, d_counts, 8, cudaMemcpyDeviceToDevice, c->stream));
+  // [H | U | extra]: extra[0..2] carries the 64-bit changed-rows count as three 22-bit limbs, so the u32 sums over the
+  // ranks cannot overflow (<= 1024 ranks) and no carry between the limbs is lost
+  k_split_u64_limbs<<<1, 1, 0, c->stream>>>(d_counts, w.extra);
+  BIC_LAUNCH_CHECK(c);
   m->last_extra = w.extra;
-  BIC_TRY(allreduce_u32(c, m, w.H, (size_t)w.p * w.hs + w.p + 2));
+  BIC_TRY(allreduce_u32(c, m, w.H, (size_t)w.p * w.hs + w.p + 3));
   if (fused) {
     w.x.win = m->d_peer_win;
     w.x.nranks = (uint32_t)m->nranks;
@@ -377,9 +391,9 @@ static bic_status dist_update_dictionary(bic_ctx* c, bic_comm* m, bic_mat* E, bi
   return bic_k_dict_commit(c, D, &w);
 }
 
-__global__ void k_join_u32_pair(const uint32_t* __restrict__ lohi, unsigned long long* __restrict__ out) {
-  // the two halves were summed separately: recombine with the carry
-  *out = (unsigned long long)lohi[0] + ((unsigned long long)lohi[1] << 32);
+__global__ void k_join_u64_limbs(const uint32_t* __restrict__ limbs, unsigned long long* __restrict__ out) {
+  // each limb is a sum over the ranks of a 22-bit piece: the pieces overlap after the sum, plain 64-bit adds recombine them
+  *out = (unsigned long long)limbs[0] + ((unsigned long long)limbs[1] << 22) + ((unsigned long long)limbs[2] << 44);
 }
 
 extern "C" bic_status bic_dist_update_dictionary_steepest(bic_ctx* c, bic_comm* m, bic_mat* E, bic_mat* D, const bic_mat* A,
@@ -413,7 +427,7 @@ extern "C" bic_status bic_dist_learn_model_traditional(bic_ctx* c, bic_comm* m, 
       const uint64_t p = D->rows;
       const uint32_t* extra = m->last_extra;
       if (p && E->cols) {
-        k_join_u32_pair<<<1, 1, 0, c->stream>>>(extra, d_cc);
+        k_join_u64_limbs<<<1, 1, 0, c->stream>>>(extra, d_cc);
         BIC_LAUNCH_CHECK(c);
       } else if (m->nranks > 1) {
         BIC_NCCL(c, nccl_api()->AllReduce(d_cc, d_cc, 1, ncclUint64, ncclSum, m->comm, c->stream));

@@ -2,6 +2,7 @@
 // Reference: learn_model_traditional src/bsvd.cpp:1215-1244; driver src/bsvd_test.cpp:56-155.
 #include "bic_internal.cuh"
 
+#include <new>
 #include <vector>
 
 bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, unsigned long long* d_changed);
@@ -13,6 +14,19 @@ extern "C" bic_status bic_learn_model_traditional(bic_ctx* c, const bic_mat* X, 
   if (!c || !X || !E || !D || !A) return BIC_ERR_INVALID;
   BIC_TRY(bic_residual(c, X, A, D, E));  // mul(A,false,D,false,E); add(E,X,E)  src/bsvd.cpp:1219-1220
   uint64_t changed = 1, iter = 0;
+  if (c->dict_update == 1) {
+    // update_dictionary points at update_dictionary_proximus (-d 1): the reference's loop over its plug points, :1227-1243
+    while (changed > 0) {
+      iter++;
+      uint64_t cc = 0, ca = 0;
+      BIC_TRY(bic_update_coefficients(c, E, D, A, &cc));
+      BIC_TRY(bic_update_dictionary_proximus(c, E, D, A, &ca));
+      changed = cc + ca;
+      if (trace && iter <= trace_cap) { trace[2 * (iter - 1)] = cc; trace[2 * (iter - 1) + 1] = ca; }
+    }
+    if (iterations) *iterations = iter;
+    return BIC_OK;
+  }
   unsigned long long* d_cc = (unsigned long long*)c->d_scalars;
   while (changed > 0) {  // :1227
     iter++;
@@ -156,48 +170,93 @@ static bic_status encode_from_raster(bic_ctx* c, EncWorkspace* w, const bic_mat*
   return BIC_OK;
 }
 
-extern "C" bic_status bic_decode_raster(bic_ctx* c, const uint8_t* cont, uint64_t nbytes, uint8_t* pbm_payload,
+static bic_status decode_raster_checked(bic_ctx* c, const uint8_t* cont, uint64_t nbytes, uint8_t* pbm_payload,
                                         uint64_t cap_bytes, uint64_t* rows_out, uint64_t* cols_out) {
-  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
-  if (!c || !cont) return BIC_ERR_INVALID;
   const uint64_t hdr = (HDR_FIELDS + 3 * STREAM_FIELDS) * 8;
   if (nbytes < hdr) return bic_fail(c, BIC_ERR_CORRUPT, "container: truncated header");
   std::vector<uint64_t> h((HDR_FIELDS + 3 * STREAM_FIELDS));
   memcpy(h.data(), cont, hdr);
   if (h[0] != BIC_MAGIC || h[1] != 1) return bic_fail(c, BIC_ERR_CORRUPT, "container: bad magic/version");
   const uint64_t rows = h[2], cols = h[3], W = h[4], K = h[5], n = h[6], m = h[7];
-  if (W == 0 || rows == 0 || cols == 0 || m != W * W || n != ((W - 1 + rows) / W) * ((W - 1 + cols) / W))
+  // Every field is bounded BEFORE it enters any arithmetic: the file controls them all. A raster cannot have more pixels
+  // than 64 x the container's bits can possibly describe... there is no such bound for a compressor, so the limits are
+  // absolute: sides < 2^31, W <= 2^12, 1 <= K <= 65535 (the coefficient kernels' key packs the atom index in 16 bits).
+  const uint64_t SIDE_MAX = 1ull << 31, W_MAX = 1ull << 12;
+  if (W == 0 || W > W_MAX || rows == 0 || cols == 0 || rows >= SIDE_MAX || cols >= SIDE_MAX || K == 0 || K > 65535)
+    return bic_fail(c, BIC_ERR_CORRUPT, "container: field out of range");
+  if (m != W * W || n != ((W - 1 + rows) / W) * ((W - 1 + cols) / W))   // both products < 2^62
     return bic_fail(c, BIC_ERR_CORRUPT, "container: inconsistent shape");
+  if (!bic_shape_ok(n, m) || !bic_shape_ok(n, K) || !bic_shape_ok(rows, cols))
+    return bic_fail(c, BIC_ERR_CORRUPT, "container: shape too large");
   if (rows_out) *rows_out = rows;
   if (cols_out) *cols_out = cols;
   const uint64_t payload = rows * div_up_u64(cols, 8);
   if (!pbm_payload) return BIC_OK;
   if (cap_bytes < payload) return BIC_ERR_CAPACITY;
-  EncWorkspace* w = ws_of(c);
-  BIC_TRY(ws_prepare(c, w, rows, cols, W, K));
-  bic_mat* mats[3] = {w->D, w->A, w->E};
+  // validate all three stream headers against the bytes that are really there before touching the device
   const uint64_t shp[3][2] = {{K, m}, {n, K}, {n, m}};
+  bic_stream_info sis[3];
+  uint64_t offs[3];
   uint64_t off = hdr;
   for (int i = 0; i < 3; ++i) {
     const uint64_t* f = h.data() + HDR_FIELDS + i * STREAM_FIELDS;
-    bic_stream_info si;
-    si.coder = (uint32_t)f[0]; si.chunk_samples = (uint32_t)f[1]; si.rows = f[2]; si.cols = f[3];
+    bic_stream_info& si = sis[i];
+    if (f[0] != BIC_CODER_GOLOMB && f[0] != BIC_CODER_EG) return bic_fail(c, BIC_ERR_CORRUPT, "container: unknown coder");
+    si.coder = (uint32_t)f[0]; si.rows = f[2]; si.cols = f[3];
     si.bitcount = f[4]; si.nsamples = f[5]; si.nchunks = f[6];
     if (si.rows != shp[i][0] || si.cols != shp[i][1]) return bic_fail(c, BIC_ERR_CORRUPT, "container: stream shape mismatch");
+    const uint64_t left = nbytes - off, N = si.rows * si.cols;
+    if (si.bitcount > 8 * left) return bic_fail(c, BIC_ERR_CORRUPT, "container: truncated stream");   // left < 2^61
     const uint64_t nb = div_up_u64(si.bitcount, 8), nbp = div_up_u64(nb, 8) * 8;
-    if (off + nbp + si.nchunks * 16 > nbytes) return bic_fail(c, BIC_ERR_CORRUPT, "container: truncated stream");
+    if (nbp > left || si.nchunks > (left - nbp) / 16) return bic_fail(c, BIC_ERR_CORRUPT, "container: truncated stream");
+    if (si.coder == BIC_CODER_GOLOMB) {
+      if (f[1] == 0 || f[1] > (1ull << 30) || (f[1] & (f[1] - 1))) return bic_fail(c, BIC_ERR_CORRUPT, "container: bad chunk size");
+      si.chunk_samples = (uint32_t)f[1];
+      // popcount + 1 samples, each at least one code bit
+      if (si.nsamples == 0 || si.nsamples > N + 1 || si.nsamples > si.bitcount ||
+          si.nchunks != div_up_u64(si.nsamples, si.chunk_samples))
+        return bic_fail(c, BIC_ERR_CORRUPT, "container: inconsistent stream header");
+    } else {
+      si.chunk_samples = 0;
+      if (si.nchunks != 0 || si.nsamples != 0 || (si.bitcount != N + si.rows && si.bitcount != N + si.rows + 1))
+        return bic_fail(c, BIC_ERR_CORRUPT, "container: inconsistent stream header");
+    }
+    offs[i] = off;
+    off += nbp + si.nchunks * 16;
+  }
+  EncWorkspace* w = ws_of(c);
+  BIC_TRY(ws_prepare(c, w, rows, cols, W, K));
+  bic_mat* mats[3] = {w->D, w->A, w->E};
+  for (int i = 0; i < 3; ++i) {
+    const bic_stream_info& si = sis[i];
+    const uint64_t nb = div_up_u64(si.bitcount, 8), nbp = div_up_u64(nb, 8) * 8;
     std::vector<uint64_t> idx(si.nchunks * 2 + 1);
-    memcpy(idx.data(), cont + off + nbp, si.nchunks * 16);
-    BIC_TRY(bic_stream_upload(c, w->st[i], &si, cont + off, idx.data()));
+    memcpy(idx.data(), cont + offs[i] + nbp, si.nchunks * 16);
+    // chunk-index entries are offsets into the code and into the matrix: bound them here, the kernel re-checks
+    for (uint64_t j = 0; j < si.nchunks; ++j)
+      if (idx[2 * j] >= si.bitcount || idx[2 * j + 1] > si.rows * si.cols)
+        return bic_fail(c, BIC_ERR_CORRUPT, "container: chunk index out of range");
+    BIC_TRY(bic_stream_upload(c, w->st[i], &si, cont + offs[i], idx.data()));
     BIC_CUDA(c, bic_wait_stream(c));  // idx is a local
     if (si.coder == BIC_CODER_GOLOMB) BIC_TRY(bic_golomb_decode(c, w->st[i], mats[i]));
-    else if (si.coder == BIC_CODER_EG) BIC_TRY(bic_eg_decode(c, w->st[i], mats[i]));
-    else return bic_fail(c, BIC_ERR_CORRUPT, "container: unknown coder");
-    off += nbp + si.nchunks * 16;
+    else BIC_TRY(bic_eg_decode(c, w->st[i], mats[i]));
   }
   // X = A*D xor E  (the residual identity read backwards), then patches -> raster
   BIC_TRY(bic_residual(c, w->E, w->A, w->D, w->X));
   BIC_TRY(bic_assemble_patches(c, w->X, W, w->raster));
   BIC_TRY(bic_mat_download_pbm(c, w->raster, pbm_payload));
   return BIC_OK;
+}
+
+extern "C" bic_status bic_decode_raster(bic_ctx* c, const uint8_t* cont, uint64_t nbytes, uint8_t* pbm_payload,
+                                        uint64_t cap_bytes, uint64_t* rows_out, uint64_t* cols_out) {
+  if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
+  if (!c || !cont) return BIC_ERR_INVALID;
+  try {  // nothing may unwind through the C boundary
+    return decode_raster_checked(c, cont, nbytes, pbm_payload, cap_bytes, rows_out, cols_out);
+  } catch (const std::bad_alloc&) {
+    return bic_fail(c, BIC_ERR_NOMEM, "decode_raster: host allocation failed");
+  } catch (...) {
+    return bic_fail(c, BIC_ERR_CORRUPT, "decode_raster: container rejected");
+  }
 }

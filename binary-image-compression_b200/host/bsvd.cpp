@@ -124,12 +124,23 @@ static idx_t learn_mdl(int lm, binary_matrix& X, binary_matrix& E, binary_matrix
     std::cerr << what << ": the B200 build runs it with the neighbor initialisation and the traditional inner learner only" << std::endl;
     std::exit(-1);
   }
+  // the inner learner goes through the global update pointers (src/bsvd.cpp:1229,1235): -d 1 runs PROXIMUS inside the search
+  const bool cu_ok = update_coefficients == update_coefficients_omp || update_coefficients == update_coefficients_basic;
+  const bool du_steepest = update_dictionary == update_dictionary_steepest || update_dictionary == update_dictionary_steepest_omp;
+  const bool du_proximus = update_dictionary == update_dictionary_proximus;
+  if (!cu_ok || !(du_steepest || du_proximus)) {
+    std::cerr << what << ": the B200 build runs it with its own coefficient and dictionary updates only" << std::endl;
+    std::exit(-1);
+  }
   bic_mat* x = X.device();
   bic_mat* e = E.device();
   bic_mat* d = D.release_device();
   bic_mat* a = A.release_device();
   uint64_t bestL = 0;
-  ck(bic_learn_model_mdl(bic_host_context(), lm, x, e, &d, &a, get_rng(), &bestL), what);
+  ck(bic_ctx_set_option(bic_host_context(), "dict_update", du_proximus ? 1 : 0), what);
+  const bic_status st = bic_learn_model_mdl(bic_host_context(), lm, x, e, &d, &a, get_rng(), &bestL);
+  bic_ctx_set_option(bic_host_context(), "dict_update", 0);
+  ck(st, what);
   E.device_written();
   D.adopt_device(d);
   A.adopt_device(a);

@@ -65,6 +65,9 @@ bic_status bic_ctx_wait_ctx(bic_ctx* waiter, bic_ctx* signal);
  * "dict_algo": how update_dictionary_steepest walks the atoms. 2 (default) = all atom histograms in one pass, then the
  *   in-order atom chain inside ONE thread-block cluster (dict3.cu) where the histograms fit shared memory, else 1;
  *   1 = same histograms, one launch per atom that changes (dict2.cu); 0 = one grid barrier per atom (dict.cu).
+ * "dict_update": which dictionary update bic_learn_model_traditional (and the MDL learners through it) calls: 0 (default)
+ *   update_dictionary_steepest, 1 update_dictionary_proximus -- the reference's global update_dictionary pointer (-d 0 / -d 1,
+ *   src/bsvd.cpp:1235). This one DOES change the result, exactly as the flag does in the reference.
  * "coef_algo": 1 (default) = dictionaries of >= 64 atoms use the weight-sorted warp-per-row coefficient kernel; 0 = always a
  *   lane per row.
  * "chain_cluster": CTAs in dict3.cu's cluster, 1/2/4/8/16 (default 16, 8 where 16 cannot be co-scheduled).
@@ -247,6 +250,16 @@ typedef struct {
 struct bic_stream;
 bic_status bic_dist_golomb_encode(bic_ctx* ctx, bic_comm* comm, const bic_mat* M_local, uint32_t chunk_samples,
                                   struct bic_stream* out, bic_shard_info* shard);
+
+/* The same coder for callers with their own plumbing: the prefix state of the shard is an explicit input (what the two
+ * allgathers of bic_dist_golomb_encode provide). The rows of M follow `bits_before` bits of the one global matrix that hold
+ * `ones_before` ones, the last of them at global bit `last_one_before` (-1: none), and produced `code_bits_before` code bits.
+ * closing != 0: M holds the last rows, so the run closed by the virtual one at `total_bits` is written too. out may be NULL
+ * (lengths only: shard->local_code_bits). The coder state at the seam is GolombCoder's (src/Golomb.h:12-29,
+ * src/GolombCoder.cpp:29-34): samples = ones_before, accumulatedError = last_one_before + 1 - ones_before in uint32. */
+bic_status bic_golomb_encode_shard(bic_ctx* ctx, const bic_mat* M_local, uint32_t chunk_samples, uint64_t ones_before,
+                                   uint64_t bits_before, int64_t last_one_before, uint64_t code_bits_before, int closing,
+                                   uint64_t total_bits, struct bic_stream* out, bic_shard_info* shard);
 
 /* ---------------------------------------------------------------- entropy coding
  * A coded stream is a byte string: stream bit t is in byte t/8 at mask 0x80 >> (t%8)

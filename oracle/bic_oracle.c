@@ -366,6 +366,47 @@ uint64_t bo_golomb_encode_matrix(const bo_word* M, uint64_t rows, uint64_t cols,
   return (uint64_t)g.bitcount;
 }
 
+/* The serial coder started in the middle of a stream: the rows of M are a contiguous block of a bigger matrix.
+ * State of GolombCoder (Golomb.h:12-29) after the `ones_before` samples that precede the block: samples = ones_before,
+ * accumulatedError = sum of those samples = (last_one_before + 1) - ones_before (both uint32, wrapping as the reference's
+ * unsigned members do), k re-derived by GolombCoder.cpp:33 (k = 1 before the first sample, Golomb.h:18). The run in
+ * progress at the block's first bit is bits_before - (last_one_before + 1) zeros long. Codes the block's ones; with
+ * `closing` also the run closed by the virtual one at total_bits. Returns the bits written; out may be NULL. */
+uint64_t bo_golomb_encode_shard(const bo_word* M, uint64_t rows, uint64_t cols, uint64_t ones_before, uint64_t bits_before,
+                                int64_t last_one_before, int closing, uint64_t total_bits, uint8_t* out, uint64_t cap_bytes,
+                                uint64_t* nsamples) {
+  const uint64_t wpr = bo_wpr(cols);
+  bo_golomb g;
+  bo_golomb_init(&g);
+  if (ones_before) {
+    g.samples = (uint32_t)ones_before;
+    g.accumulatedError = (uint32_t)((uint64_t)(last_one_before + 1) - ones_before);
+    uint32_t k;
+    for (k = 0; k < 31 && (uint32_t)(g.samples << k) < g.accumulatedError; k++) {} /* GolombCoder.cpp:33 */
+    g.k = k;
+  }
+  bo_bitwriter bw = {out, cap_bytes * 8, 0};
+  if (out) memset(out, 0, cap_bytes);
+  uint64_t count = 0, run = bits_before - (uint64_t)(last_one_before + 1);
+  for (uint64_t i = 0; i < rows; ++i)
+    for (uint64_t j = 0; j < cols; ++j) {
+      if (get_bit(M + i * wpr, j)) {
+        bo_golomb_code_sample(&g, out ? &bw : NULL, (uint32_t)run);
+        count++;
+        run = 0;
+      } else {
+        run++;
+      }
+    }
+  if (closing) {
+    run += total_bits - (bits_before + rows * cols);
+    bo_golomb_code_sample(&g, out ? &bw : NULL, (uint32_t)run);
+    count++;
+  }
+  if (nsamples) *nsamples = count;
+  return (uint64_t)g.bitcount;
+}
+
 int bo_golomb_decode_matrix(const uint8_t* in, uint64_t nbits_in, uint64_t rows, uint64_t cols, bo_word* M) {
   const uint64_t wpr = bo_wpr(cols), N = rows * cols;
   memset(M, 0, sizeof(bo_word) * rows * wpr);

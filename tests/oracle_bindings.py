@@ -72,6 +72,8 @@ class Oracle:
         L.bo_zero_runs.argtypes = [u64p, u64, u64, u32p, u64]
         L.bo_golomb_encode_matrix.restype = u64
         L.bo_golomb_encode_matrix.argtypes = [u64p, u64, u64, u8p, u64, u64p]
+        L.bo_golomb_encode_shard.restype = u64
+        L.bo_golomb_encode_shard.argtypes = [u64p, u64, u64, u64, u64, C.c_int64, C.c_int, u64, u8p, u64, u64p]
         L.bo_golomb_decode_matrix.restype = C.c_int
         L.bo_golomb_decode_matrix.argtypes = [u8p, u64, u64, u64, u64p]
         L.bo_eg_encode_matrix.restype = u64
@@ -248,6 +250,16 @@ class Oracle:
         bits2 = int(self.lib.bo_golomb_encode_matrix(_p64(M), M.shape[0], cols, out.ctypes.data_as(u8p),
                                                       out.size, C.byref(ns)))
         assert bits == bits2
+        return out, bits, int(ns.value)
+
+    def golomb_encode_shard(self, M, cols, ones_before, bits_before, last_one_before, closing, total_bits):
+        """the serial coder started mid-stream (see bo_golomb_encode_shard): returns (bytes, bitcount, nsamples)"""
+        M = np.ascontiguousarray(M, np.uint64)
+        ns = u64(0)
+        args = (_p64(M), M.shape[0], cols, ones_before, bits_before, last_one_before, int(closing), total_bits)
+        bits = int(self.lib.bo_golomb_encode_shard(*args, None, 0, C.byref(ns)))
+        out = np.zeros((bits + 7) // 8, np.uint8)
+        self.lib.bo_golomb_encode_shard(*args, out.ctypes.data_as(u8p), out.size, C.byref(ns))
         return out, bits, int(ns.value)
 
     def golomb_decode(self, stream, nbits, rows, cols):

@@ -72,6 +72,29 @@ def test_driver_proximus_matches_reference_driver(tmp_path, synth):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lm,K", [(4, 6), (5, 10)])
+def test_driver_mdl_with_proximus_matches_reference_driver(tmp_path, synth, lm, K):
+    """-d 1 -l 4/5: the MDL learners' inner fit goes through the global update pointers (src/bsvd.cpp:1229,1235), so the
+    reference runs PROXIMUS inside the search; so must we"""
+    ref_bin = ROOT / "oracle" / "_ref" / "bsvd_test"
+    if not ref_bin.exists():
+        pytest.skip("oracle/_ref/bsvd_test not built")
+    _build()
+    page = synth.structured_page(200, 168, seed=5, salt=0.01)
+    pbm = tmp_path / "in.pbm"
+    _write_pbm(pbm, page)
+    flags = ["-I", "1", "-k", str(K), "-r", "777", "-m", "0", "-M", "0", "-d", "1", "-l", str(lm), "-w", "8"]
+    outs = {}
+    for name, exe in (("ref", ref_bin), ("b200", HOST / "bsvd_test_b200")):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([str(exe)] + flags + [str(pbm)], cwd=d, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+        outs[name] = {f: hashlib.md5((d / f).read_bytes()).hexdigest() for f in ("dictionary.pbm", "coefficients.pbm", "residual.pbm")}
+    assert outs["ref"] == outs["b200"]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode,W,K,rows,cols,lm", [(1, 8, 32, 400, 328, 0), (1, 16, 24, 300, 260, 0), (0, 0, 12, 200, 150, 0),
                                                     (1, 8, 6, 200, 168, 4), (1, 8, 10, 200, 168, 5), (1, 8, 45, 160, 128, 6),
                                                     (1, 8, 12, 200, 168, 1), (1, 8, 12, 200, 168, 2), (1, 16, 10, 160, 160, 3)])
