@@ -49,6 +49,13 @@ class ShardInfo(C.Structure):
                                     "first_chunk", "local_chunks")]
 
 
+class MatchTotals(C.Structure):
+    _fields_ = [("matches", _u64), ("weight_sum", _u64), ("bits_match", _u64), ("bits_nomatch", _u64), ("L", C.c_double)]
+
+
+MATCH_DTYPE = np.dtype([(n, np.uint64) for n in ("besti", "bestj", "bestd", "weight", "match_len", "nomatch_len", "use_match")])
+
+
 class EncodeInfo(C.Structure):
     _fields_ = [(n, _u64) for n in ("rows", "cols", "W", "K", "n", "m", "iterations", "weight_E", "weight_A",
                                     "weight_D", "bits_D", "bits_A", "bits_E", "container_bytes")]
@@ -126,6 +133,8 @@ def lib() -> C.CDLL:
         "bic_learn_model_traditional_batched": [_vp, C.c_uint32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _u64p],
         "bic_dist_golomb_encode": [_vp, _vp, _vp, C.c_uint32, _vp, C.POINTER(ShardInfo)],
         "bic_golomb_encode_shard": [_vp, _vp, C.c_uint32, _u64, _u64, C.c_int64, _u64, C.c_int, _u64, _vp, C.POINTER(ShardInfo)],
+        "bic_match_patches_v1": [_vp, _vp, _u64, _vp, C.POINTER(MatchTotals)],
+        "bic_match_patches_v4": [_vp, _vp, _u64, _u64, _u64, _vp, C.POINTER(MatchTotals)],
         "bic_stream_create": [_vp, C.POINTER(_vp)],
         "bic_stream_destroy": [_vp, _vp],
         "bic_stream_get_info": [_vp, C.POINTER(StreamInfo)],
@@ -144,6 +153,8 @@ def lib() -> C.CDLL:
         f = getattr(L, name)
         f.argtypes = args
         f.restype = C.c_int
+    L.bic_enumL.argtypes = [_u64, _u64]
+    L.bic_enumL.restype = C.c_double
     L.bic_prof_kernel_count.argtypes = []
     L.bic_prof_kernel_count.restype = C.c_int
     L.bic_comm_collective_count.argtypes = [_vp]
@@ -545,6 +556,19 @@ class Context:
         self._ck(self.L.bic_golomb_encode_shard(self.h, M.h, chunk_samples, ones_before, bits_before, last_one_before, code_bits_before,
                                                 int(closing), total_bits, None if lengths_only else out.h, C.byref(si)))
         return out, si
+
+    # ---- template matching (compress*_test)
+    def match_patches(self, raster: Matrix, W: int, version: int = 1, T: int = 0, R: int = 10000):
+        """version 1: compress_test.cpp's search over the unmodified image; 4: compress4_test.cpp's windowed search with the
+        in-place residual replacement (raster is rewritten). Returns (records structured array, MatchTotals)."""
+        n = ((raster.rows + W - 1) // W) * ((raster.cols + W - 1) // W)
+        recs = np.zeros(n, MATCH_DTYPE)
+        tot = MatchTotals()
+        if version == 1:
+            self._ck(self.L.bic_match_patches_v1(self.h, raster.h, W, recs.ctypes.data_as(_vp), C.byref(tot)))
+        else:
+            self._ck(self.L.bic_match_patches_v4(self.h, raster.h, W, T, R, recs.ctypes.data_as(_vp), C.byref(tot)))
+        return recs, tot
 
     # ---- coding
     def golomb_encode(self, M: Matrix, out: Stream | None = None, chunk_samples: int = 256) -> Stream:

@@ -45,7 +45,7 @@ enum bic_kernel_id {
   KID_EXTRACT, KID_ASSEMBLE, KID_ROW_NONZERO, KID_GATHER_ROWS, KID_COL_HIST, KID_PIVOT_USAGE, KID_INIT_FINALIZE,
   KID_UPDATE_COEF, KID_RESIDUAL, KID_TRANSPOSE_BITS, KID_UPDATE_DICT, KID_DICT_HIST, KID_DICT_RESOLVE, KID_DICT_SCAN,
   KID_COMPACT_ROWS, KID_EXPAND_ROWS, KID_GOL_TILE_COUNTS, KID_GOL_SCAN_A, KID_GOL_LENGTHS, KID_GOL_SCAN_B,
-  KID_GOL_SCATTER, KID_GOL_DECODE, KID_EG_FIRST, KID_EG_FILL, KID_EG_ENCODE, KID_EG_DECODE, KID_DICT_CHAIN, KID_DICT_APPLY, KID_DICT_COMPACT, KID_DICT_BUCKET, KID_BITPLANES, KID_PROXIMUS,
+  KID_GOL_SCATTER, KID_GOL_DECODE, KID_EG_FIRST, KID_EG_FILL, KID_EG_ENCODE, KID_EG_DECODE, KID_DICT_CHAIN, KID_DICT_APPLY, KID_DICT_COMPACT, KID_DICT_BUCKET, KID_BITPLANES, KID_PROXIMUS, KID_MATCH, KID_MATCH_DECIDE,
   KID_COUNT
 };
 

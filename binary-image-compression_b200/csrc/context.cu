@@ -507,7 +507,7 @@ static const char* const kKernelNames[KID_COUNT] = {
   "k_update_coefficients", "k_residual", "k_transpose_bits", "k_update_dictionary", "k_dict_hist_popc", "k_dict_resolve", "k_dict_scan",
   "k_compact_rows", "k_expand_rows", "k_gol_tile_counts", "k_gol_scan_tiles_a", "k_gol_walk<0>", "k_gol_scan_tiles_b",
   "k_gol_walk<1>", "k_gol_decode", "k_first_one/zero", "k_fill_ones", "k_eg_encode", "k_eg_decode", "k_dict_chain", "k_dict_apply",
-  "k_dict_compact", "k_dict_bucket", "k_bitplanes", "k_proximus"};
+  "k_dict_compact", "k_dict_bucket", "k_bitplanes", "k_proximus", "k_match", "k_match_decide"};
 
 static cudaEvent_t prof_event(bic_ctx* c) {
   if (!c->prof_free.empty()) { cudaEvent_t e = c->prof_free.back(); c->prof_free.pop_back(); return e; }

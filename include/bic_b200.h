@@ -210,6 +210,33 @@ bic_status bic_model_codelength(bic_ctx* ctx, const bic_mat* E, const bic_mat* D
 bic_status bic_learn_model_mdl(bic_ctx* ctx, int lm, const bic_mat* X, bic_mat* E, bic_mat** D, bic_mat** A,
                                uint64_t* rng_state, uint64_t* best_codelength);
 
+/* ---- template matching of the compress*_test experiments -----------------------------------
+ * For every W x W patch of a raster (row-major patch order, as the drivers walk them): the earlier window of the image that is
+ * closest in Hamming distance (dist(), src/binmat.cpp:499-512, over get_submatrix windows), and the drivers' costing of
+ * "difference to that window" against "the patch itself": enumL (enumerative code length, src/compress_test.cpp:37-40) plus
+ * one GolombCoder per branch over the weights (src/GolombCoder.cpp:13-34). 1 <= W <= 32. recs: one record per patch (host
+ * memory, ceil(rows/W) * ceil(cols/W) entries). */
+typedef struct {
+  uint64_t besti, bestj, bestd;      /* top-left pixel of the best window and its distance ("besti= bestj= bestd=") */
+  uint64_t weight;                   /* P.weight() */
+  uint64_t match_len, nomatch_len;   /* "nomatch len= match_len=" */
+  uint64_t use_match;                /* 1: the "USE MATCH!" branch */
+} bic_match_rec;
+typedef struct {
+  uint64_t matches, weight_sum;      /* "MATCHES:", sum of bestd over the matches (average_weight before the division) */
+  uint64_t bits_match, bits_nomatch; /* golomb_match.bitcount, golomb_nomatch.bitcount */
+  double L;                          /* sum of the chosen lengths; the drivers print (L + both bit counts) / 8 */
+} bic_match_totals;
+double bic_enumL(uint64_t n, uint64_t r);
+/* main loop of src/compress_test.cpp:73-141: every patch searches all earlier positions of the (unmodified) image; the
+ * first smallest distance in scan order wins. Patches are independent. */
+bic_status bic_match_patches_v1(bic_ctx* ctx, const bic_mat* raster, uint64_t W, bic_match_rec* recs, bic_match_totals* totals);
+/* main loop of src/compress4_test.cpp:89-171 (flags W T R): window of radius R behind / above the patch scanned backwards,
+ * stop at the first distance <= T, and a matched patch is replaced by its residual IN the raster (the driver's diff.pbm), so
+ * later patches search the coded image. W must divide 32 and the number of columns. */
+bic_status bic_match_patches_v4(bic_ctx* ctx, bic_mat* raster, uint64_t W, uint64_t T, uint64_t R, bic_match_rec* recs,
+                                bic_match_totals* totals);
+
 /* ---------------------------------------------------------------- several GPUs: rows sharded, D replicated
  * One process per GPU. Every rank holds a contiguous block of the patch rows (its X, E, A); D is
  * replicated. Integer statistics are combined with NCCL (loaded at run time: the libnccl.so.2 already in

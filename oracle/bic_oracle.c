@@ -912,3 +912,147 @@ uint64_t bo_update_dictionary_proximus(bo_word* E, bo_word* D, bo_word* A, uint6
   (void)apr;
   return changed;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * compress*_test: template matching with enumerative + Golomb costing.
+ * src/compress_test.cpp:37-141 (v1) and src/compress4_test.cpp:35-171 (v4).
+ * ------------------------------------------------------------------------------------------ */
+double bo_enumL(uint64_t n, uint64_t r) { /* compress_test.cpp:37-40; lnchoose as oracle/gsl_shim/gsl/gsl_sf_gamma.h */
+  if (r == 0 || r >= n) return 0.0;
+  const double ln = lgamma((double)n + 1.0) - lgamma((double)r + 1.0) - lgamma((double)(n - r) + 1.0);
+  return ln * 1.442695040888963387004650940070860087872;
+}
+
+/* W bits (W <= 64, left aligned in the result) of image row r starting at column j, as get_submatrix sees them
+ * (binmat.cpp:267-298): the words of the matrix are one flat array, rows are ceil(cols/64) blocks long with zero pad bits
+ * (read_pbm_data clears the matrix, pbm.cpp:31), a read that runs past the last block of a row continues in the next row,
+ * and blocks past the end of the array read as zero. */
+static bo_word flat_bits(const bo_word* I, uint64_t rows, uint64_t cols, uint64_t r, uint64_t j, uint64_t W) {
+  const uint64_t bpr = bo_wpr(cols), nblk = rows * bpr;
+  const uint64_t k1 = r * bpr + j / 64, off = j % 64;
+  const bo_word s1 = k1 < nblk ? I[k1] : 0, s2 = (k1 + 1) < nblk ? I[k1 + 1] : 0;
+  const bo_word v = off ? ((s1 << off) | (s2 >> (64 - off))) : s1;
+  return W >= 64 ? v : (v & ~(~(bo_word)0 >> W));  /* get_block's trail mask of the W-column patch, binmat.h:188-190 */
+}
+
+static uint64_t patch_dist(const bo_word* I, uint64_t rows, uint64_t cols, const bo_word* P, uint64_t i2, uint64_t j2, uint64_t W) {
+  uint64_t d = 0;                               /* dist(P, P2), binmat.cpp:499-512 */
+  for (uint64_t di = 0; di < W; ++di) d += (uint64_t)popc64(P[di] ^ flat_bits(I, rows, cols, i2 + di, j2, W));
+  return d;
+}
+
+static uint64_t ceil_log2_u64(uint64_t li) {    /* ceil(log2(li)) for li >= 1 */
+  uint64_t k = 0;
+  while (((uint64_t)1 << k) < li) k++;
+  return k;
+}
+
+static void match_account(bo_match_rec* rec, bo_golomb* gm, bo_golomb* gn, bo_match_totals* tot) {
+  if (rec->use_match) {                         /* compress_test.cpp:130-136 */
+    bo_golomb_code_sample(gm, NULL, (uint32_t)rec->bestd);
+    tot->weight_sum += rec->bestd;
+    tot->matches++;
+    tot->L += (double)rec->match_len;
+  } else {                                      /* :137-140 */
+    bo_golomb_code_sample(gn, NULL, (uint32_t)rec->weight);
+    tot->L += (double)rec->nomatch_len;
+  }
+}
+
+void bo_compress_v1(const bo_word* I, uint64_t rows, uint64_t cols, uint64_t W, bo_match_rec* recs, bo_match_totals* tot) {
+  const uint64_t Ny = (W - 1 + rows) / W, Nx = (W - 1 + cols) / W, M = W * W;
+  bo_golomb gm, gn;
+  bo_golomb_init(&gm); bo_golomb_init(&gn);
+  memset(tot, 0, sizeof(*tot));
+  bo_word P[64];
+  uint64_t li = 0;
+  for (uint64_t i = 0; i < Ny; ++i)
+    for (uint64_t j = 0; j < Nx; ++j, ++li) {
+      const uint64_t i0 = i * W, j0 = j * W;
+      uint64_t w = 0;
+      for (uint64_t di = 0; di < W; ++di) { P[di] = flat_bits(I, rows, cols, i0 + di, j0, W); w += (uint64_t)popc64(P[di]); }
+      uint64_t besti = 0, bestj = 0, bestd = M;  /* :78 */
+      int perfect = 0;
+      int64_t i2 = 0;
+      for (; i2 <= (int64_t)i0 - (int64_t)W && !perfect; ++i2)       /* :81-96 rows fully above: every column */
+        for (uint64_t j2 = 0; j2 < cols; ++j2) {
+          const uint64_t d = patch_dist(I, rows, cols, P, (uint64_t)i2, j2, W);
+          if (d < bestd) { bestd = d; besti = (uint64_t)i2; bestj = j2; }
+          if (bestd == 0) { perfect = 1; break; }
+        }
+      for (; i2 <= (int64_t)i0 && !perfect; ++i2)                     /* :97-111 the patch's own band: columns to its left */
+        for (int64_t j2 = 0; j2 <= (int64_t)j0 - (int64_t)W; ++j2) {
+          const uint64_t d = patch_dist(I, rows, cols, P, (uint64_t)i2, (uint64_t)j2, W);
+          if (d < bestd) { bestd = d; besti = (uint64_t)i2; bestj = (uint64_t)j2; }
+          if (bestd == 0) { perfect = 1; break; }
+        }
+      bo_match_rec* rec = recs + li;
+      rec->besti = besti; rec->bestj = bestj; rec->bestd = bestd; rec->weight = w;
+      rec->nomatch_len = (uint64_t)(1 + bo_enumL(M, w));              /* :126 */
+      if (li == 0) {
+        /* ceil(log2(0)) = -inf converted to idx_t is undefined; on x86-64 it comes out as 2^63, so the first patch
+         * (which has no candidate anyway) never takes the match branch */
+        rec->match_len = (uint64_t)1 << 63;
+        rec->use_match = 0;
+      } else {
+        rec->match_len = (uint64_t)(1 + ceil_log2_u64(li) + bo_enumL(M, bestd));  /* :120,127 */
+        rec->use_match = rec->nomatch_len > rec->match_len;            /* :129 */
+      }
+      match_account(rec, &gm, &gn, tot);
+    }
+  tot->bits_match = (uint64_t)gm.bitcount;
+  tot->bits_nomatch = (uint64_t)gn.bitcount;
+}
+
+void bo_compress_v4(bo_word* I, uint64_t rows, uint64_t cols, uint64_t W, uint64_t T, uint64_t R, bo_match_rec* recs,
+                    bo_match_totals* tot) {
+  const uint64_t Ny = (W - 1 + rows) / W, Nx = (W - 1 + cols) / W, M = W * W, bpr = bo_wpr(cols);
+  bo_golomb gm, gn;
+  bo_golomb_init(&gm); bo_golomb_init(&gn);
+  memset(tot, 0, sizeof(*tot));
+  bo_word P[64];
+  uint64_t li = 0;
+  for (uint64_t i = 0; i < Ny; ++i)
+    for (uint64_t j = 0; j < Nx; ++j, ++li) {
+      const int64_t i0 = (int64_t)(i * W), j0 = (int64_t)(j * W), Wi = (int64_t)W, Ri = (int64_t)R;
+      uint64_t w = 0;
+      for (uint64_t di = 0; di < W; ++di) { P[di] = flat_bits(I, rows, cols, (uint64_t)i0 + di, (uint64_t)j0, W); w += (uint64_t)popc64(P[di]); }
+      uint64_t besti = 0, bestj = 0, bestd = M + 1;                  /* compress4_test.cpp:94 */
+      int perfect = 0;
+      const int64_t mini = i0 > Ri ? i0 - Ri : 0, mini2 = i0 > Wi ? i0 - Wi : 0;     /* :97-98 */
+      const int64_t minj = j0 > Ri ? j0 - Ri : 0;
+      const int64_t maxj = (j0 + Ri) > ((int64_t)cols - Wi) ? (int64_t)cols - Wi : j0 + Ri;
+      for (int64_t i2 = i0; i2 >= mini2 && !perfect; --i2)            /* :103-119 behind the patch, backwards */
+        for (int64_t j2 = j0 - Wi; j2 >= minj; --j2) {
+          const uint64_t d = patch_dist(I, rows, cols, P, (uint64_t)i2, (uint64_t)j2, W);
+          if (d < bestd) { bestd = d; besti = (uint64_t)i2; bestj = (uint64_t)j2; }
+          if (bestd <= T) { perfect = 1; break; }
+        }
+      for (int64_t i2 = i0 - Wi; i2 >= mini && !perfect; --i2)        /* :120-135 everything above, backwards */
+        for (int64_t j2 = maxj; j2 >= minj; --j2) {
+          const uint64_t d = patch_dist(I, rows, cols, P, (uint64_t)i2, (uint64_t)j2, W);
+          if (d < bestd) { bestd = d; besti = (uint64_t)i2; bestj = (uint64_t)j2; }
+          if (bestd <= T) { perfect = 1; break; }
+        }
+      bo_match_rec* rec = recs + li;
+      rec->besti = besti; rec->bestj = bestj; rec->bestd = bestd; rec->weight = w;
+      rec->nomatch_len = (uint64_t)(1 + bo_enumL(M, w));              /* :153 */
+      /* :154; with bestd > W*W (no candidate: only the first patch) the constant 100000 keeps the undefined
+       * ceil(log2(0)) out of the comparison */
+      rec->match_len = bestd <= M ? (uint64_t)(1 + (li ? ceil_log2_u64(li) : 0) + bo_enumL(M, bestd)) : 100000;
+      rec->use_match = rec->nomatch_len > rec->match_len;             /* :157 */
+      match_account(rec, &gm, &gn, tot);
+      if (rec->use_match) {                                           /* :164 I.set_submatrix(i0,j0,P3), P3 = P xor P2 */
+        for (uint64_t di = 0; di < W && (uint64_t)i0 + di < rows; ++di) {
+          const bo_word p3 = P[di] ^ flat_bits(I, rows, cols, besti + di, bestj, W);
+          bo_word* blk = I + ((uint64_t)i0 + di) * bpr + (uint64_t)j0 / 64;
+          const uint64_t off = (uint64_t)j0 % 64;                      /* W | 64 and W | cols: the patch sits inside one block */
+          const bo_word mask = (W >= 64 ? ~(bo_word)0 : ~(~(bo_word)0 >> W)) >> off;
+          *blk = (*blk & ~mask) | ((p3 >> off) & mask);
+        }
+      }
+    }
+  tot->bits_match = (uint64_t)gm.bitcount;
+  tot->bits_nomatch = (uint64_t)gn.bitcount;
+}

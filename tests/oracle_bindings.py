@@ -40,6 +40,48 @@ def _build_oracle():
     return so
 
 
+class MatchRec(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("besti", "bestj", "bestd", "weight", "match_len", "nomatch_len", "use_match")]
+
+
+class MatchTotals(C.Structure):
+    _fields_ = [("matches", C.c_uint64), ("weight_sum", C.c_uint64), ("bits_match", C.c_uint64), ("bits_nomatch", C.c_uint64),
+                ("L", C.c_double)]
+
+
+MATCH_DTYPE = np.dtype([(n, np.uint64) for n in ("besti", "bestj", "bestd", "weight", "match_len", "nomatch_len", "use_match")])
+
+
+def run_reference_compress(version, page_bits, W, T=None, R=None, workdir=None):
+    """run the UNMODIFIED compress_test (version 1) / compress4_test (version 4) binary of oracle/_ref on a page and parse what
+    it prints: per patch (besti, bestj, bestd, nomatch_len, match_len, use_match), the totals, and (v4) the rewritten image.
+    Returns None if the binary is not there."""
+    import re
+    import tempfile
+    exe = ORACLE_DIR / "_ref" / ("compress_test" if version == 1 else "compress4_test")
+    if not exe.exists():
+        return None
+    d = workdir or tempfile.mkdtemp()
+    rows, cols = page_bits.shape
+    with open(os.path.join(d, "in.pbm"), "wb") as f:
+        f.write(f"P4\n{cols} {rows}\n".encode())
+        f.write(np.packbits(page_bits, axis=1, bitorder="big").tobytes())
+    args = [str(exe), "in.pbm", str(W)] + ([str(T), str(R)] if version == 4 else [])
+    r = subprocess.run(args, cwd=d, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stderr[-500:]
+    recs = []
+    for mm in re.finditer(r"besti=(\d+) bestj=(\d+) bestd=(\d+)\nnomatch len=(\d+) match_len=(\d+)( USE MATCH!)?", r.stdout):
+        recs.append(tuple(int(x) for x in mm.groups()[:5]) + (1 if mm.group(6) else 0,))
+    out = {"recs": recs, "matches": int(re.search(r"MATCHES: (\d+)", r.stdout).group(1)),
+           "comp_bytes": float(re.search(r"COMP CODELENGTH \(bytes\): ([0-9.e+]+)", r.stdout).group(1))}
+    if version == 4:
+        with open(os.path.join(d, "diff.pbm"), "rb") as f:
+            raw = f.read()
+        hdr_end = raw.index(b"\n", raw.index(b"\n") + 1) + 1
+        out["diff"] = np.unpackbits(np.frombuffer(raw[hdr_end:], np.uint8).reshape(rows, -1), axis=1)[:, :cols]
+    return out
+
+
 class Rand48(C.Structure):
     _fields_ = [("x0", C.c_uint16), ("x1", C.c_uint16), ("x2", C.c_uint16)]
 
@@ -74,6 +116,10 @@ class Oracle:
         L.bo_golomb_encode_matrix.argtypes = [u64p, u64, u64, u8p, u64, u64p]
         L.bo_golomb_encode_shard.restype = u64
         L.bo_golomb_encode_shard.argtypes = [u64p, u64, u64, u64, u64, C.c_int64, C.c_int, u64, u8p, u64, u64p]
+        L.bo_enumL.restype = C.c_double
+        L.bo_enumL.argtypes = [u64, u64]
+        L.bo_compress_v1.argtypes = [u64p, u64, u64, u64, C.c_void_p, C.POINTER(MatchTotals)]
+        L.bo_compress_v4.argtypes = [u64p, u64, u64, u64, u64, u64, C.c_void_p, C.POINTER(MatchTotals)]
         L.bo_golomb_decode_matrix.restype = C.c_int
         L.bo_golomb_decode_matrix.argtypes = [u8p, u64, u64, u64, u64p]
         L.bo_eg_encode_matrix.restype = u64
@@ -251,6 +297,24 @@ class Oracle:
                                                       out.size, C.byref(ns)))
         assert bits == bits2
         return out, bits, int(ns.value)
+
+    def compress_v1(self, I, rows, cols, W):
+        """compress_test.cpp's main loop; returns (records as a structured array, MatchTotals)"""
+        I = np.ascontiguousarray(I, np.uint64)
+        n = ((rows + W - 1) // W) * ((cols + W - 1) // W)
+        recs = np.zeros(n, MATCH_DTYPE)
+        tot = MatchTotals()
+        self.lib.bo_compress_v1(_p64(I), rows, cols, W, recs.ctypes.data_as(C.c_void_p), C.byref(tot))
+        return recs, tot
+
+    def compress_v4(self, I, rows, cols, W, T, R):
+        """compress4_test.cpp's main loop; returns (records, MatchTotals, rewritten image words)"""
+        I = np.array(I, np.uint64, copy=True)
+        n = ((rows + W - 1) // W) * ((cols + W - 1) // W)
+        recs = np.zeros(n, MATCH_DTYPE)
+        tot = MatchTotals()
+        self.lib.bo_compress_v4(_p64(I), rows, cols, W, T, R, recs.ctypes.data_as(C.c_void_p), C.byref(tot))
+        return recs, tot, I
 
     def golomb_encode_shard(self, M, cols, ones_before, bits_before, last_one_before, closing, total_bits):
         """the serial coder started mid-stream (see bo_golomb_encode_shard): returns (bytes, bitcount, nsamples)"""
