@@ -135,6 +135,18 @@ def lib() -> C.CDLL:
         "bic_golomb_encode_shard": [_vp, _vp, C.c_uint32, _u64, _u64, C.c_int64, _u64, C.c_int, _u64, _vp, C.POINTER(ShardInfo)],
         "bic_match_patches_v1": [_vp, _vp, _u64, _vp, C.POINTER(MatchTotals)],
         "bic_match_patches_v4": [_vp, _vp, _u64, _u64, _u64, _vp, C.POINTER(MatchTotals)],
+        "bic_pipeline_create": [C.c_int, C.c_int, C.POINTER(_vp)],
+        "bic_pipeline_destroy": [_vp],
+        "bic_pipeline_set_option": [_vp, C.c_char_p, C.c_int64],
+        "bic_pipeline_submit": [_vp, _u8p, _u64, _u64, _u64, _u64, C.c_ulong, _u8p, _u64, C.POINTER(EncodeInfo), _u64p],
+        "bic_pipeline_submit_resident": [_vp, _vp, _vp, _u64, _u64, C.c_ulong, _u8p, _u64, C.POINTER(EncodeInfo), _u64p],
+        "bic_pipeline_poll": [_vp, _u64p],
+        "bic_pipeline_wait": [_vp, _u64],
+        "bic_pipeline_job_status": [_vp, _u64, C.POINTER(C.c_int), C.POINTER(C.c_char_p)],
+        "bic_pipeline_forget_finished": [_vp],
+        "bic_pipeline_stats": [_vp, _u64p, _u64p, _u64p, _u64p, _u64p],
+        "bic_pipeline_wait_ctx": [_vp, _vp],
+        "bic_ctx_wait_pipeline": [_vp, _vp],
         "bic_stream_create": [_vp, C.POINTER(_vp)],
         "bic_stream_destroy": [_vp, _vp],
         "bic_stream_get_info": [_vp, C.POINTER(StreamInfo)],
@@ -281,6 +293,93 @@ class Stream:
             self.h = None
 
 
+class Pipeline:
+    """bic_pipeline: a pool of encoder slots driven by the calling thread; rasters are queued and polled, nothing blocks on the
+    device (see include/bic_b200.h)."""
+
+    def __init__(self, device: int = 0, nslots: int = 16):
+        self.L = lib()
+        h = _vp()
+        st = self.L.bic_pipeline_create(device, nslots, C.byref(h))
+        if st != 0:
+            raise BicError(st, "bic_pipeline_create")
+        self.h = h
+        self.nslots = nslots
+        self._keep = {}
+
+    def _ck(self, st, what=""):
+        if st != 0:
+            raise BicError(st, what)
+
+    def set_option(self, name: str, value: int):
+        self._ck(self.L.bic_pipeline_set_option(self.h, name.encode(), int(value)), name)
+
+    def submit(self, payload: np.ndarray, rows: int, cols: int, W: int, K: int, seed: int = 34503498, out: np.ndarray | None = None):
+        """queue a host P4 payload; returns (job id, EncodeInfo that is filled when the job is done)"""
+        info = EncodeInfo()
+        job = _u64(0)
+        outp = out.ctypes.data_as(_u8p) if out is not None else None
+        self._ck(self.L.bic_pipeline_submit(self.h, payload.ctypes.data_as(_u8p), rows, cols, W, K, seed, outp,
+                                            out.size if out is not None else 0, C.byref(info), C.byref(job)))
+        self._keep[int(job.value)] = (payload, out, info)
+        return int(job.value), info
+
+    def submit_resident(self, raster: "Matrix", W: int, K: int, seed: int = 34503498, out: np.ndarray | None = None, producer: "Context | None" = None):
+        info = EncodeInfo()
+        job = _u64(0)
+        outp = out.ctypes.data_as(_u8p) if out is not None else None
+        self._ck(self.L.bic_pipeline_submit_resident(self.h, raster.h, producer.h if producer is not None else None, W, K, seed, outp,
+                                                     out.size if out is not None else 0, C.byref(info), C.byref(job)))
+        self._keep[int(job.value)] = (raster, out, info)
+        return int(job.value), info
+
+    def poll(self) -> int:
+        left = _u64(0)
+        self._ck(self.L.bic_pipeline_poll(self.h, C.byref(left)))
+        return int(left.value)
+
+    def wait(self, job: int = 0):
+        self._ck(self.L.bic_pipeline_wait(self.h, job))
+
+    def status(self, job: int):
+        """(done, status code, message)"""
+        done = C.c_int(0)
+        msg = C.c_char_p()
+        st = self.L.bic_pipeline_job_status(self.h, job, C.byref(done), C.byref(msg))
+        return bool(done.value), st, (msg.value or b"").decode()
+
+    def result(self, job: int):
+        """wait for the job; raises on failure; returns its EncodeInfo"""
+        self.wait(job)
+        done, st, msg = self.status(job)
+        if st != 0:
+            raise BicError(st, msg)
+        return self._keep[job][2]
+
+    def forget_finished(self):
+        self._ck(self.L.bic_pipeline_forget_finished(self.h))
+        self._keep = {j: v for j, v in self._keep.items() if not self.status_safe(j)}
+
+    def status_safe(self, job):
+        try:
+            return self.status(job)[0]
+        except BicError:
+            return True
+
+    def stats(self) -> dict:
+        v = [_u64(0) for _ in range(5)]
+        self._ck(self.L.bic_pipeline_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("launches", "polls", "batches", "sync_fallbacks", "recodes"), (int(x.value) for x in v)))
+
+    def wait_for(self, ctx: "Context"):
+        self._ck(self.L.bic_pipeline_wait_ctx(self.h, ctx.h))
+
+    def close(self):
+        if self.h:
+            self.L.bic_pipeline_destroy(self.h)
+            self.h = None
+
+
 class Context:
     """One device context (one CUDA stream). Method names follow the reference's plug points."""
 
@@ -322,6 +421,9 @@ class Context:
         ms = C.c_float(0)
         self._ck(self.L.bic_timer_stop(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def wait_for_pipeline(self, pipe: "Pipeline"):
+        self._ck(self.L.bic_ctx_wait_pipeline(self.h, pipe.h))
 
     def wait_for(self, other: "Context"):
         """order this context's stream after everything queued so far on `other`'s stream"""

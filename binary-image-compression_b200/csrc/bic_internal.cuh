@@ -77,6 +77,9 @@ struct bic_ctx {
   int dict_algo = 2;  // 0: per-atom walk (dict.cu), 1: histogram first, resolve in order (dict2.cu), 2: cluster chain (dict3.cu) where the shape allows, else 1
   long long chain_bucket_cap = -1;  // entries of dict3.cu's per-atom buckets; -1 = 2 per row (0 forces the list-scan fallback)
   int chain_cluster = 16;  // CTAs in the cluster of dict3.cu's chain kernel (1, 2, 4, 8 or 16)
+  // device flag of a learner loop that runs ahead of the host (pipeline.cu): non-null while iterations are queued without
+  // waiting for the previous one's counts; the iteration's kernels return at once when *loop_skip != 0
+  const uint32_t* loop_skip = nullptr;
   bool prof_on = false;
   std::vector<bic_prof_rec> prof_recs;
   std::vector<cudaEvent_t> prof_free;
@@ -179,6 +182,28 @@ struct InitWork {
   uint64_t* piv;
   uint32_t *P, *hist, *usage;
 };
+
+// ---- container (encoder.cu writes it synchronously, pipeline.cu asynchronously): little-endian u64 fields
+//   [0] magic "BICB200\0"  [1] version  [2] rows [3] cols [4] W [5] K [6] n [7] m [8] iterations [9] seed
+//   then per stream (D, A, E) 7 fields: coder, chunk_samples, rows, cols, bitcount, nsamples, nchunks
+//   then per stream: code bytes padded to 8, chunk index (nchunks * 2 u64)
+static const uint64_t BIC_MAGIC = 0x0030303242434942ull;  // "BICB200\0"
+static const uint64_t BIC_HDR_FIELDS = 10, BIC_STREAM_FIELDS = 7;
+static inline uint64_t bic_container_bytes(const bic_stream_info si[3]) {
+  uint64_t need = (BIC_HDR_FIELDS + 3 * BIC_STREAM_FIELDS) * 8;
+  for (int i = 0; i < 3; ++i) need += div_up_u64(div_up_u64(si[i].bitcount, 8), 8) * 8 + si[i].nchunks * 16;
+  return need;
+}
+static inline void bic_container_header(uint8_t* out, uint64_t rows, uint64_t cols, uint64_t W, uint64_t K, uint64_t n, uint64_t m,
+                                        uint64_t iters, uint64_t seed, const bic_stream_info si[3]) {
+  uint64_t* h = (uint64_t*)out;
+  h[0] = BIC_MAGIC; h[1] = 1; h[2] = rows; h[3] = cols; h[4] = W; h[5] = K; h[6] = n; h[7] = m; h[8] = iters; h[9] = seed;
+  for (int i = 0; i < 3; ++i) {
+    uint64_t* f = h + BIC_HDR_FIELDS + i * BIC_STREAM_FIELDS;
+    f[0] = si[i].coder; f[1] = si[i].chunk_samples; f[2] = si[i].rows; f[3] = si[i].cols; f[4] = si[i].bitcount; f[5] = si[i].nsamples;
+    f[6] = si[i].nchunks;
+  }
+}
 
 // a matrix from the stream-ordered pool: create and destroy cost no device synchronisation. Only for temporaries that are
 // used and destroyed on ONE context (the one passed here).

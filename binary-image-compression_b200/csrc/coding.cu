@@ -252,8 +252,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_gol_scan_tiles_a(GolTile g, ui
 }
 
 // scalars: [0] bitcount, [1] nsamples, [2] offset of the closing sample, [3] last one + 1
+// cap_bits != 0: scalars[4] = 1 if the code does not fit a buffer of cap_bits (the asynchronous encoder sizes its buffer
+// before it knows the bit count; the scatter pass then does nothing and the caller re-encodes with an exact allocation)
 __global__ void __launch_bounds__(SCAN_THREADS) k_gol_scan_tiles_b(GolTile g, uint64_t ntiles, uint64_t N,
-                                                                   unsigned long long* scalars) {
+                                                                   unsigned long long* scalars, unsigned long long cap_bits) {
   __shared__ unsigned long long s_sum[32];
   __shared__ long long s_max[32];
   const uint64_t per = div_up_u64(ntiles, SCAN_THREADS);
@@ -280,7 +282,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_gol_scan_tiles_b(GolTile g, ui
     scalars[1] = ones + 1;
     scalars[2] = carry;
     scalars[3] = consumed;
+    scalars[4] = (cap_bits && scalars[0] + 64 > cap_bits) ? 1ull : 0ull;
   }
+}
+
+// zero the words the code will occupy (the scatter ORs into a zeroed buffer); the bit count is only known on the device
+__global__ void k_gol_zero_code(uint32_t* __restrict__ out, const unsigned long long* __restrict__ scalars) {
+  if (scalars[4]) return;
+  const unsigned long long nw = ((scalars[0] + 31) >> 5) + 4;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nw; i += (unsigned long long)gridDim.x * blockDim.x)
+    out[i] = 0u;
 }
 
 __device__ __forceinline__ void put_bits(uint32_t* __restrict__ out, unsigned long long o, uint32_t value, uint32_t nb) {
@@ -313,7 +324,10 @@ struct GolBase {
 template <int MODE>
 __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __restrict__ S, uint64_t T, uint64_t N, GolTile g,
                                                            uint32_t* __restrict__ out, unsigned long long* __restrict__ index,
-                                                           uint32_t chunk, GolBase gb) {
+                                                           uint32_t chunk, GolBase gb, const unsigned long long* __restrict__ dyn) {
+  // dyn (MODE 1, asynchronous encoder): k_gol_scan_tiles_b's scalars, still on the device -- the closing sample's rank,
+  // offset and position come from there instead of gb, and a code that does not fit the buffer is not written at all
+  if (MODE == 1 && dyn && dyn[4]) return;
   __shared__ unsigned long long s_a[8];
   __shared__ long long s_b[8];
   const uint64_t w0 = (uint64_t)blockIdx.x * TILE_WORDS + threadIdx.x * TILE_WORDS_PER_THREAD;
@@ -478,8 +492,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_gol_walk(const uint32_t* __res
     }
   }
   if (gb.closing && blockIdx.x == 0 && threadIdx.x == 0) {  // the run closed by the virtual one (N = global bit count)
-    const unsigned long long tt = gb.close_t, consumed = gb.close_consumed;
-    unsigned long long oo = gb.close_off + gb.out0;
+    const unsigned long long tt = dyn ? dyn[1] - 1 : gb.close_t, consumed = dyn ? dyn[3] : gb.close_consumed;
+    unsigned long long oo = (dyn ? dyn[2] : gb.close_off) + gb.out0;
     const unsigned long long x = N - consumed;
     const uint32_t k = golomb_k(tt, consumed);
     if ((tt & cmask) == 0) { index[2 * ((tt >> clog) - gb.chunk0)] = oo - gb.out0 + gb.code0; index[2 * ((tt >> clog) - gb.chunk0) + 1] = consumed; }
@@ -946,22 +960,64 @@ static bic_status golomb_counts(bic_ctx* c, const bic_mat* M, GolWork* w) {
 static bic_status golomb_lengths(bic_ctx* c, GolWork* w, const GolBase& base) {
   if (w->ntiles) {
     BIC_PROF(c, KID_GOL_LENGTHS);
-    k_gol_walk<0><<<(unsigned)w->ntiles, TILE_THREADS, 0, c->stream>>>(w->S, w->T, w->N, w->g, nullptr, nullptr, 1, base);
+    k_gol_walk<0><<<(unsigned)w->ntiles, TILE_THREADS, 0, c->stream>>>(w->S, w->T, w->N, w->g, nullptr, nullptr, 1, base, nullptr);
     BIC_LAUNCH_CHECK(c);
   }
   BIC_PROF(c, KID_GOL_SCAN_B);
-  k_gol_scan_tiles_b<<<1, SCAN_THREADS, 0, c->stream>>>(w->g, w->ntiles, w->N, (unsigned long long*)c->d_scalars);
+  k_gol_scan_tiles_b<<<1, SCAN_THREADS, 0, c->stream>>>(w->g, w->ntiles, w->N, (unsigned long long*)c->d_scalars, 0ull);
   BIC_LAUNCH_CHECK(c);
   return bic_read_scalars(c, 4);
 }
 
-static bic_status golomb_scatter(bic_ctx* c, GolWork* w, const GolBase& base, uint64_t N_global, uint32_t chunk, bic_stream* out) {
+static bic_status golomb_scatter(bic_ctx* c, GolWork* w, const GolBase& base, uint64_t N_global, uint32_t chunk, bic_stream* out,
+                                 const unsigned long long* dyn = nullptr) {
   // with no tile (empty matrix) one CTA still has to write the closing sample
   const unsigned grid = (unsigned)(w->ntiles ? w->ntiles : 1);
   BIC_PROF(c, KID_GOL_SCATTER);
   k_gol_walk<1><<<grid, TILE_THREADS, 0, c->stream>>>(w->S, w->ntiles ? w->T : 0, N_global, w->g, (uint32_t*)out->d_bytes,
-                                                     (unsigned long long*)out->d_index, chunk, base);
+                                                     (unsigned long long*)out->d_index, chunk, base, dyn);
   BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+// The encoder with nothing waiting for the host (pipeline.cu): counts, lengths, scans, clear and scatter are queued back to
+// back. The output buffer is sized for what its source can plausibly produce (stream_reserve: 1.25 code bits per input bit);
+// d_info (device, 8 u64) receives [0] bit count, [1] samples, [2] offset of the closing sample, [3] position after the last
+// one, [4] 1 if the code did not fit (nothing was written: re-encode with bic_golomb_encode). out->info is NOT filled in:
+// the caller completes it from d_info once it has been copied to the host (bic_golomb_async_finish).
+bic_status bic_k_golomb_encode_async(bic_ctx* c, const bic_mat* M, uint32_t chunk_samples, bic_stream* out, unsigned long long* d_info) {
+  const uint64_t N = M->rows * M->cols;
+  BIC_TRY(stream_reserve(c, out, N + N / 4 + 32768, div_up_u64(N + 1, chunk_samples), N));  // index: worst case, every bit a sample
+  const uint64_t cap_bits = (uint64_t)(out->cap_bytes - 32) * 8;
+  GolWork w;
+  BIC_TRY(golomb_counts(c, M, &w));
+  GolBase base = gol_base_single();
+  if (w.ntiles) {
+    BIC_PROF(c, KID_GOL_LENGTHS);
+    k_gol_walk<0><<<(unsigned)w.ntiles, TILE_THREADS, 0, c->stream>>>(w.S, w.T, w.N, w.g, nullptr, nullptr, 1, base, nullptr);
+    BIC_LAUNCH_CHECK(c);
+  }
+  BIC_PROF(c, KID_GOL_SCAN_B);
+  k_gol_scan_tiles_b<<<1, SCAN_THREADS, 0, c->stream>>>(w.g, w.ntiles, w.N, d_info, cap_bits);
+  BIC_LAUNCH_CHECK(c);
+  BIC_PROF(c, KID_GOL_SCAN_B);
+  k_gol_zero_code<<<bic_grid_for(c, div_up_u64(N, 32) + 4, 256, 4), 256, 0, c->stream>>>((uint32_t*)out->d_bytes, d_info);
+  BIC_LAUNCH_CHECK(c);
+  BIC_TRY(golomb_scatter(c, &w, base, w.N, chunk_samples, out, d_info));
+  out->info.coder = BIC_CODER_GOLOMB;
+  out->info.chunk_samples = chunk_samples;
+  out->info.rows = M->rows;
+  out->info.cols = M->cols;
+  out->info.bitcount = out->info.nsamples = out->info.nchunks = 0;
+  return BIC_OK;
+}
+
+// host_info: the 8 u64 of d_info after they reached the host. Returns BIC_ERR_CAPACITY if the code did not fit.
+bic_status bic_golomb_async_finish(bic_stream* out, const uint64_t* host_info) {
+  if (host_info[4]) return BIC_ERR_CAPACITY;
+  out->info.bitcount = host_info[0];
+  out->info.nsamples = host_info[1];
+  out->info.nchunks = div_up_u64(host_info[1], out->info.chunk_samples);
   return BIC_OK;
 }
 
@@ -1066,7 +1122,7 @@ extern "C" bic_status bic_dist_golomb_encode(bic_ctx* c, bic_comm* m, const bic_
   GolWork w;
   BIC_TRY(golomb_counts(c, M, &w));
   BIC_PROF(c, KID_GOL_SCAN_B);
-  k_gol_scan_tiles_b<<<1, SCAN_THREADS, 0, c->stream>>>(w.g, w.ntiles, w.N, (unsigned long long*)c->d_scalars);
+  k_gol_scan_tiles_b<<<1, SCAN_THREADS, 0, c->stream>>>(w.g, w.ntiles, w.N, (unsigned long long*)c->d_scalars, 0ull);
   BIC_LAUNCH_CHECK(c);
   BIC_TRY(bic_read_scalars(c, 4));
   uint64_t mine[3] = {c->h_scalars[1] - 1, c->h_scalars[3], w.N};  // ones, position after the last one (0 = none), bits

@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restric
                                                              uint32_t p, uint64_t wprA,
                                                              unsigned long long* __restrict__ changed,
                                                              const ProbDev* __restrict__ probs,
-                                                             const uint32_t* __restrict__ active) {
+                                                             const uint32_t* __restrict__ active,
+                                                             const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;  // the learner's loop already ended on the device (queued-ahead iteration)
   if (probs) {  // batched launch: blockIdx.y selects the problem
     if (!active[blockIdx.y]) return;
     const ProbDev pr = probs[blockIdx.y];
@@ -130,7 +132,9 @@ template <int WORDS>
 __global__ void __launch_bounds__(256) k_update_coefficients_sorted(uint32_t* __restrict__ E, const uint32_t* __restrict__ D,
                                                                     uint32_t* __restrict__ A, uint64_t n, uint64_t wprE, uint32_t p,
                                                                     uint64_t wprA, unsigned long long* __restrict__ changed,
-                                                                    unsigned long long* __restrict__ next_row, uint32_t grab) {
+                                                                    unsigned long long* __restrict__ next_row, uint32_t grab,
+                                                                    const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   constexpr int STR = WORDS + 1;                 // row stride of the sorted dictionary: consecutive atoms hit distinct banks
   extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* Ds = sm;                             // p * STR, sorted by (weight, original index)
@@ -245,7 +249,7 @@ static bic_status launch_coef_sorted(bic_ctx* c, bic_mat* E, const bic_mat* D, b
   BIC_CUDA(c, cudaMemsetAsync(next_row, 0, 8, c->stream));
   BIC_PROF(c, KID_UPDATE_COEF);
   k_update_coefficients_sorted<WORDS><<<grid, 256, smem, c->stream>>>(E->d, D->d, A->d, E->rows, E->wpr, (uint32_t)p, A->wpr, d_changed,
-                                                                     next_row, (uint32_t)grab);
+                                                                     next_row, (uint32_t)grab, c->loop_skip);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }
@@ -255,7 +259,9 @@ static bic_status launch_coef_sorted(bic_ctx* c, bic_mat* E, const bic_mat* D, b
 __global__ void __launch_bounds__(256) k_update_coefficients_wide(uint32_t* __restrict__ E, const uint32_t* __restrict__ D,
                                                                   uint32_t* __restrict__ A, uint64_t n, uint64_t wprE,
                                                                   uint32_t p, uint64_t wprA,
-                                                                  unsigned long long* __restrict__ changed) {
+                                                                  unsigned long long* __restrict__ changed,
+                                                                  const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   extern __shared__ uint32_t es_all[];  // (blockDim/32) * wprE
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* es = es_all + (size_t)wib * wprE;
@@ -309,7 +315,7 @@ static bic_status launch_coef(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat*
   const int grid = bic_grid_for(c, E->rows, 256, per_sm);
   BIC_PROF(c, KID_UPDATE_COEF);
   k_update_coefficients<WORDS><<<grid, 256, smem, c->stream>>>(E->d, D->d, A->d, E->rows, E->wpr, (uint32_t)D->rows,
-                                                              A->wpr, d_changed, nullptr, nullptr);
+                                                              A->wpr, d_changed, nullptr, nullptr, c->loop_skip);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }
@@ -328,7 +334,7 @@ static bic_status launch_coef_batched(bic_ctx* c, uint64_t n, uint64_t wprE, uin
   if (gx < 1) gx = 1;
   BIC_PROF(c, KID_UPDATE_COEF);
   k_update_coefficients<WORDS><<<dim3((unsigned)gx, nprob), 256, smem, c->stream>>>(nullptr, nullptr, nullptr, n, wprE, (uint32_t)p,
-                                                                                   wprA, nullptr, probs, active);
+                                                                                   wprA, nullptr, probs, active, nullptr);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }
@@ -383,7 +389,7 @@ bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, b
     BIC_CUDA(c, cudaFuncSetAttribute(k_update_coefficients_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BIC_PROF(c, KID_UPDATE_COEF);
   k_update_coefficients_wide<<<bic_grid_for(c, E->rows * 32, 256, 4), 256, smem, c->stream>>>(
-      E->d, D->d, A->d, E->rows, wpr, (uint32_t)D->rows, A->wpr, d_changed);
+      E->d, D->d, A->d, E->rows, wpr, (uint32_t)D->rows, A->wpr, d_changed, c->loop_skip);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }

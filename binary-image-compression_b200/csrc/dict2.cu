@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(256) k_dict_hist_popc(const uint32_t* __restri
                                                         uint64_t wprE, uint64_t wprA, uint64_t hs, uint32_t ntile_j,
                                                         const ProbDev* __restrict__ probs, const uint32_t* __restrict__ active,
                                                         uint32_t* __restrict__ listA, uint32_t* __restrict__ listE,
-                                                        uint32_t* __restrict__ list_count, uint32_t* __restrict__ hcount) {
+                                                        uint32_t* __restrict__ list_count, uint32_t* __restrict__ hcount,
+                                                        const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;  // the learner's loop already ended on the device (queued-ahead iteration)
   if (probs) {  // batched launch: blockIdx.z selects the problem
     if (!active[blockIdx.z]) return;
     const ProbDev pr = probs[blockIdx.z];
@@ -553,8 +555,8 @@ static bic_status launch_hist(bic_ctx* c, const bic_mat* E, const bic_mat* A, ui
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, ntiles);
   BIC_PROF(c, KID_DICT_HIST);
-  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count, hcount);
-  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count, hcount);
+  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count, hcount, c->loop_skip);
+  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(E->d, A->d, H, U, n, E->wpr, A->wpr, hs, ntile_j, nullptr, nullptr, listA, listE, count, hcount, c->loop_skip);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }
@@ -680,8 +682,8 @@ bic_status bic_k_dict_hist_batched(bic_ctx* c, uint64_t n, uint64_t m, uint64_t 
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, ntiles, nprob);
   BIC_PROF(c, KID_DICT_HIST);
-  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr, nullptr);
-  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr, nullptr);
+  if (two) k_dict_hist_popc<2><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr, nullptr, nullptr);
+  else k_dict_hist_popc<1><<<grid, 256, 0, c->stream>>>(nullptr, nullptr, nullptr, nullptr, n, wprE, wprA, hs, ntile_j, probs, active, nullptr, nullptr, nullptr, nullptr, nullptr);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }

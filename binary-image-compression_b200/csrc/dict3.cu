@@ -43,6 +43,7 @@ struct ChainParams {
   const uint32_t* bucket;   // list indices grouped by atom (offsets = exclusive scan of hcount)
   uint32_t bucket_cap;      // capacity of `bucket`; when the buckets do not fit the chain scans the list instead
   uint64_t m;
+  const uint32_t* skip;     // non-null and nonzero: the learner's loop already ended on the device, do nothing
 };
 
 // vote of atom k from the histograms in shared memory (src/bsvd.cpp:499-507); one warp. Returns whether
@@ -146,7 +147,9 @@ __device__ __forceinline__ uint32_t hit_word(const uint32_t* __restrict__ a, uin
 
 // bucket sizes: hcount[k] = list rows using atom k and a later atom
 __global__ void __launch_bounds__(256) k_dict_bucket_count(const uint32_t* __restrict__ listA, const uint32_t* __restrict__ count,
-                                                           uint32_t* __restrict__ hcount, uint32_t wprA, uint32_t p) {
+                                                           uint32_t* __restrict__ hcount, uint32_t wprA, uint32_t p,
+                                                           const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   extern __shared__ uint32_t sCnt[];       // wprA * 32
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < wprA * 32; i += blockDim.x) sCnt[i] = 0;
@@ -173,7 +176,9 @@ __global__ void __launch_bounds__(256) k_dict_bucket_count(const uint32_t* __res
 static const int FILL_CHUNK = 1024;
 __global__ void __launch_bounds__(256) k_dict_bucket_fill(const uint32_t* __restrict__ listA, const uint32_t* __restrict__ count,
                                                           const uint32_t* __restrict__ hcount, uint32_t* __restrict__ cursor,
-                                                          uint32_t* __restrict__ bucket, uint32_t bucket_cap, uint32_t wprA, uint32_t p) {
+                                                          uint32_t* __restrict__ bucket, uint32_t bucket_cap, uint32_t wprA, uint32_t p,
+                                                          const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   extern __shared__ uint32_t s_mem[];
   uint32_t* sOff = s_mem;                  // p + 1
   uint32_t* sCnt = sOff + p + 1;           // wprA * 32
@@ -226,6 +231,7 @@ __global__ void __launch_bounds__(256) k_dict_bucket_fill(const uint32_t* __rest
 }
 
 __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) {
+  if (P.skip && *P.skip) return;           // every CTA of the cluster takes the same branch
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank(), csize = cluster.num_blocks();
   extern __shared__ __align__(16) uint32_t s_mem[];
@@ -365,7 +371,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
 // E_i ^= XOR{delta_k : k changed, k in S_i} for every row (src/bsvd.cpp:512-520 for all changed atoms at once)
 __global__ void __launch_bounds__(256) k_dict_apply(uint32_t* __restrict__ E, const uint32_t* __restrict__ A,
                                                     const uint32_t* __restrict__ delta, const uint32_t* __restrict__ chmask,
-                                                    uint64_t n, uint32_t wprE, uint32_t wprA, uint32_t p) {
+                                                    uint64_t n, uint32_t wprE, uint32_t wprA, uint32_t p,
+                                                    const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   if (__ldcg(chmask + wprA) == 0) return;  // no atom changed
   extern __shared__ uint32_t s_mem[];
   uint32_t* sDelta = s_mem;                // p*wprE
@@ -416,7 +424,9 @@ __global__ void __launch_bounds__(256) k_dict_apply(uint32_t* __restrict__ E, co
 // histogram pass cannot do it on the side (more than one tile per row).
 __global__ void __launch_bounds__(256) k_dict_compact(const uint32_t* __restrict__ E, const uint32_t* __restrict__ A,
                                                       uint32_t* __restrict__ listA, uint32_t* __restrict__ listE,
-                                                      uint32_t* __restrict__ count, uint64_t n, uint32_t wprE, uint32_t wprA) {
+                                                      uint32_t* __restrict__ count, uint64_t n, uint32_t wprE, uint32_t wprA,
+                                                      const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   const int lane = threadIdx.x & 31;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t nround = div_up_u64(n, stride);
@@ -507,26 +517,27 @@ bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const 
   if (!fused) {
     const int grid = bic_grid_for(c, n, 256, 8);
     BIC_PROF(c, KID_DICT_COMPACT);
-    k_dict_compact<<<grid, 256, 0, c->stream>>>(E->d, A->d, listA, listE, count, n, (uint32_t)wprE, (uint32_t)wprA);
+    k_dict_compact<<<grid, 256, 0, c->stream>>>(E->d, A->d, listA, listE, count, n, (uint32_t)wprE, (uint32_t)wprA, c->loop_skip);
     BIC_LAUNCH_CHECK(c);
   }
   if (!fused) {  // the fused histogram pass counted the buckets as well
     const int grid = bic_grid_for(c, n, 256, 2);
     BIC_PROF(c, KID_DICT_BUCKET);
-    k_dict_bucket_count<<<grid, 256, (size_t)wprA * 32 * 4, c->stream>>>(listA, count, hcount, (uint32_t)wprA, (uint32_t)p);
+    k_dict_bucket_count<<<grid, 256, (size_t)wprA * 32 * 4, c->stream>>>(listA, count, hcount, (uint32_t)wprA, (uint32_t)p, c->loop_skip);
     BIC_LAUNCH_CHECK(c);
   }
   {
     const int grid2 = bic_grid_for(c, div_up_u64(n, FILL_CHUNK) * 256, 256, 4);
     BIC_PROF(c, KID_DICT_BUCKET);
     k_dict_bucket_fill<<<grid2, 256, (size_t)(p + 1 + 2 * wprA * 32) * 4, c->stream>>>(listA, count, hcount, cursor, bucket,
-                                                                                     (uint32_t)bucket_cap, (uint32_t)wprA, (uint32_t)p);
+                                                                                     (uint32_t)bucket_cap, (uint32_t)wprA, (uint32_t)p, c->loop_skip);
     BIC_LAUNCH_CHECK(c);
   }
   ChainParams P;
   P.D = D->d; P.H = H; P.U = U; P.listA = listA; P.listE = listE; P.count = count; P.delta = delta; P.chmask = chmask;
   P.hcount = hcount; P.bucket = bucket; P.bucket_cap = (uint32_t)bucket_cap;
   P.changed = d_changed; P.p = (uint32_t)p; P.wprE = (uint32_t)wprE; P.wprA = (uint32_t)wprA; P.hs = (uint32_t)hs; P.m = E->cols;
+  P.skip = c->loop_skip;
   const unsigned csize = (unsigned)bic_chain_cluster_size(c);
   const size_t smem = (size_t)(p * hs + p * (hs + 1) + 2 * p * wprE + 3 * p + 1 + wprA + 3 * div_up_u64(p * hs, csize)) * 4;
   {
@@ -557,7 +568,7 @@ bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const 
     const int grid = bic_grid_for(c, n, 256, 8);
     BIC_PROF(c, KID_DICT_APPLY);
     k_dict_apply<<<grid, 256, (size_t)(p * wprE + wprA) * 4, c->stream>>>(E->d, A->d, delta, chmask, n, (uint32_t)wprE,
-                                                                        (uint32_t)wprA, (uint32_t)p);
+                                                                        (uint32_t)wprA, (uint32_t)p, c->loop_skip);
     BIC_LAUNCH_CHECK(c);
   }
   return BIC_OK;

@@ -50,14 +50,8 @@ extern "C" bic_status bic_learn_model_traditional(bic_ctx* c, const bic_mat* X, 
   return BIC_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// container: little-endian u64 fields
-//   [0] magic "BICB200\0"  [1] version  [2] rows [3] cols [4] W [5] K [6] n [7] m [8] iterations [9] seed
-//   then per stream (D, A, E) 7 fields: coder, chunk_samples, rows, cols, bitcount, nsamples, nchunks
-//   then per stream: code bytes padded to 8, chunk index (nchunks * 2 u64)
-// ---------------------------------------------------------------------------------------------
-static const uint64_t BIC_MAGIC = 0x0030303242434942ull;  // "BICB200\0"
-static const uint64_t HDR_FIELDS = 10, STREAM_FIELDS = 7;
+// container layout: bic_internal.cuh
+static const uint64_t HDR_FIELDS = BIC_HDR_FIELDS, STREAM_FIELDS = BIC_STREAM_FIELDS;
 
 struct EncWorkspace {
   uint64_t rows = 0, cols = 0, W = 0, K = 0;

@@ -36,6 +36,70 @@ bic_status bic_k_row_nonzero_bitmap(bic_ctx* c, const bic_mat* X, uint32_t* d_bi
   return BIC_OK;
 }
 
+// The draw itself on the device, for callers that must not wait for the host (pipeline.cu): one warp replays rand48 32
+// steps at a time. Lane l holds the affine map of l + 1 generator steps (s -> a_l * s + c_l mod 2^48), so a round costs one
+// multiply-add, one division (gsl_rng_uniform_int: k = (s >> 16) / scale, k >= n is drawn again, src/bsvd.cpp:241) and one
+// bitmap lookup per lane; accepted rows are taken in lane (= draw) order until p pivots exist, and the generator is left
+// exactly after the draw that produced the last one. status[0] = 1 if X has no nonzero row (the reference would never
+// return), status[1] = draws of the outer loop (accepted + rejected zero rows).
+__global__ void __launch_bounds__(256) k_draw_pivots(const uint32_t* __restrict__ bitmap, uint64_t n, uint32_t p,
+                                                     uint64_t* __restrict__ state, uint64_t* __restrict__ pivots,
+                                                     unsigned long long* __restrict__ status) {
+  const uint64_t nw = (n + 31) >> 5;
+  int any = 0;
+  for (uint64_t i = threadIdx.x; i < nw; i += blockDim.x) any |= (bitmap[i] != 0);
+  any = __syncthreads_or(any);
+  if (!any) {
+    for (uint32_t k = threadIdx.x; k < p; k += blockDim.x) pivots[k] = 0;
+    if (threadIdx.x == 0) { status[0] = 1; status[1] = 0; }
+    return;
+  }
+  if (threadIdx.x >= 32) return;
+  const unsigned lane = threadIdx.x;
+  const uint64_t M48 = 0xFFFFFFFFFFFFull, A = 0x5DEECE66Dull, C = 0xBull;
+  uint64_t a = 1, cc = 0;
+  for (unsigned i = 0; i <= lane; ++i) { cc = (cc * A + C) & M48; a = (a * A) & M48; }
+  const uint64_t scale = 0xFFFFFFFFull / n;
+  uint64_t base = *state, draws = 0;
+  uint32_t got = 0;
+  while (got < p) {
+    const uint64_t s = (base * a + cc) & M48;
+    const uint64_t k = (s >> 16) / scale;
+    const bool in_range = k < n;                       // else uniform_int draws again: a generator step, not a draw of the loop
+    const bool nz = in_range && ((bitmap[k >> 5] >> (k & 31)) & 1u);
+    const uint32_t vmask = __ballot_sync(0xffffffffu, nz), rmask = __ballot_sync(0xffffffffu, in_range);
+    const uint32_t need = p - got, cnt = (uint32_t)__popc(vmask);
+    const uint32_t rank = (uint32_t)__popc(vmask & ((1u << lane) - 1u));
+    if (nz && rank < need) pivots[got + rank] = k;
+    if (cnt >= need) {
+      const unsigned L = __fns(vmask, 0, (int)need);   // lane of the draw that gave the last pivot
+      base = __shfl_sync(0xffffffffu, s, L);
+      draws += (uint64_t)__popc(rmask & (L == 31 ? 0xFFFFFFFFu : ((2u << L) - 1u)));
+      got = p;
+    } else {
+      got += cnt;
+      base = __shfl_sync(0xffffffffu, s, 31);
+      draws += (uint64_t)__popc(rmask);
+    }
+  }
+  if (lane == 0) { *state = base; status[0] = 0; status[1] = draws; }
+}
+
+// bitmap + draw, all queued on the stream: pivots (device, p u64), the generator state (device u64, in/out) and status
+// (device, 2 u64) are ready when the stream gets there. n must be below 2^32 (gsl_rng_uniform_int's range).
+bic_status bic_k_draw_pivots_device(bic_ctx* c, const bic_mat* X, uint64_t p, uint64_t* d_state, uint64_t* d_pivots,
+                                    unsigned long long* d_status) {
+  const uint64_t n = X->rows;
+  if (n == 0 || n > 0xFFFFFFFFull) return bic_fail(c, BIC_ERR_INVALID, "draw_pivots: row count outside gsl_rng_uniform_int's range");
+  const uint64_t nw = div_up_u64(n, 32);
+  BIC_TRY(bic_scratch_reserve(c, &c->work[0], nw * 4));
+  BIC_TRY(bic_k_row_nonzero_bitmap(c, X, (uint32_t*)c->work[0].p));
+  BIC_PROF(c, KID_ROW_NONZERO);
+  k_draw_pivots<<<1, 256, 0, c->stream>>>((const uint32_t*)c->work[0].p, n, (uint32_t)p, d_state, d_pivots, d_status);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
 extern "C" bic_status bic_draw_pivots(bic_ctx* c, const bic_mat* X, uint64_t p, uint64_t* rng_state,
                                       uint64_t* pivots_out, uint64_t* ndraws_out) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
@@ -43,23 +107,19 @@ extern "C" bic_status bic_draw_pivots(bic_ctx* c, const bic_mat* X, uint64_t p, 
   const uint64_t n = X->rows;
   if (p == 0) { if (ndraws_out) *ndraws_out = 0; return BIC_OK; }
   if (n == 0) return bic_fail(c, BIC_ERR_INVALID, "draw_pivots: empty X");
-  const uint64_t nw = div_up_u64(n, 32);
-  BIC_TRY(bic_scratch_reserve(c, &c->work[0], nw * 4));
-  BIC_TRY(bic_k_row_nonzero_bitmap(c, X, (uint32_t*)c->work[0].p));
-  std::vector<uint32_t> bm(nw);
-  BIC_CUDA(c, cudaMemcpyAsync(bm.data(), c->work[0].p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
+  // the draw runs on the device (k_draw_pivots); the caller's generator state goes there and comes back
+  uint64_t* d_state = c->d_scalars + 48;                               // [48] state, [49..50] status
+  unsigned long long* d_status = (unsigned long long*)(c->d_scalars + 49);
+  BIC_TRY(bic_scratch_reserve(c, &c->work[1], p * 8 + 64));
+  uint64_t* d_piv = (uint64_t*)c->work[1].p;
+  BIC_CUDA(c, cudaMemcpyAsync(d_state, rng_state, 8, cudaMemcpyHostToDevice, c->stream));
+  BIC_TRY(bic_k_draw_pivots_device(c, X, p, d_state, d_piv, d_status));
+  BIC_CUDA(c, cudaMemcpyAsync(pivots_out, d_piv, p * 8, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, cudaMemcpyAsync(c->h_scalars + 48, d_state, 24, cudaMemcpyDeviceToHost, c->stream));
   BIC_CUDA(c, bic_wait_stream(c));
-  bool any = false;
-  for (uint64_t i = 0; i < nw && !any; ++i) any = bm[i] != 0;
-  if (!any) return bic_fail(c, BIC_ERR_INVALID, "draw_pivots: X is all zero (the reference's draw loop never ends)");
-  uint64_t draws = 0;
-  for (uint64_t k = 0; k < p;) {                     // src/bsvd.cpp:239
-    const uint64_t i = bic_rand48_uniform_int(rng_state, n);  // :241
-    ++draws;
-    if (!((bm[i >> 5] >> (i & 31)) & 1u)) continue;  // :243 (a rejected draw is consumed)
-    pivots_out[k++] = i;                             // u > 0 always holds for a non-zero pivot (:258)
-  }
-  if (ndraws_out) *ndraws_out = draws;
+  if (c->h_scalars[49]) return bic_fail(c, BIC_ERR_INVALID, "draw_pivots: X is all zero (the reference's draw loop never ends)");
+  *rng_state = c->h_scalars[48];
+  if (ndraws_out) *ndraws_out = c->h_scalars[50];
   return BIC_OK;
 }
 
@@ -210,6 +270,35 @@ bic_status bic_k_init_gather(bic_ctx* c, const bic_mat* X, const uint64_t* host_
   k_gather_rows<<<bic_grid_for(c, w->p * w->wpr, 256, 4), 256, 0, c->stream>>>(X->d, w->wpr, w->piv, (uint32_t)w->p, w->P);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
+}
+
+// the same with the pivot list already in device memory at w->piv (k_draw_pivots wrote it)
+bic_status bic_k_init_gather_dev(bic_ctx* c, const bic_mat* X, InitWork* w) {
+  BIC_PROF(c, KID_GATHER_ROWS);
+  k_gather_rows<<<bic_grid_for(c, w->p * w->wpr, 256, 4), 256, 0, c->stream>>>(X->d, w->wpr, w->piv, (uint32_t)w->p, w->P);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+bic_status bic_k_init_stats(bic_ctx* c, const bic_mat* X, InitWork* w);
+bic_status bic_k_init_finalize(bic_ctx* c, InitWork* w, uint64_t m, bic_mat* D);
+
+// initialize_model_neighbor with nothing waiting for the host: bitmap, draw, gather, statistics and thresholds are queued on
+// the stream. d_state: the rand48 state (device u64, in/out); d_status: 2 u64 ([0] != 0: X is all zero, D is garbage).
+bic_status bic_k_init_neighbor_async(bic_ctx* c, const bic_mat* X, bic_mat* D, bic_mat* A, uint64_t* d_state,
+                                     unsigned long long* d_status) {
+  const uint64_t p = D->rows;
+  if (D->cols != X->cols || A->rows != X->rows || A->cols != p)
+    return bic_fail(c, BIC_ERR_INVALID, "init: shapes must be X n x m, D p x m, A n x p");
+  BIC_TRY(bic_mat_clear(c, A));
+  BIC_TRY(bic_mat_clear(c, D));
+  if (p == 0 || X->rows == 0 || X->cols == 0) return BIC_OK;
+  InitWork w;
+  BIC_TRY(bic_k_init_scratch(c, p, X->wpr, &w));
+  BIC_TRY(bic_k_draw_pivots_device(c, X, p, d_state, w.piv, d_status));
+  BIC_TRY(bic_k_init_gather_dev(c, X, &w));
+  BIC_TRY(bic_k_init_stats(c, X, &w));
+  return bic_k_init_finalize(c, &w, X->cols, D);
 }
 
 // local column histogram of X and, per pivot, the number of local rows that intersect it

@@ -348,6 +348,40 @@ bic_status bic_encode_raster_resident(bic_ctx* ctx, const bic_mat* raster, uint6
 bic_status bic_decode_raster(bic_ctx* ctx, const uint8_t* container, uint64_t container_bytes,
                              uint8_t* pbm_payload, uint64_t cap_bytes, uint64_t* rows, uint64_t* cols);
 
+/* ---------------------------------------------------------------- the encoder as a pipeline (one host thread, many rasters in flight)
+ * A pool of `nslots` encoder slots (a CUDA stream and a workspace each) on one device. Rasters are queued with _submit and come
+ * out exactly as bic_encode_raster / bic_encode_raster_resident would produce them (same container bytes), but no call ever
+ * waits for the device: the pivot draw of initialize_model_neighbor (src/bsvd.cpp:239-243) runs on the device, the iterations of
+ * learn_model_traditional (src/bsvd.cpp:1227-1242) are queued in small batches and a device flag turns the ones queued past the
+ * loop's end into no-ops, and the stream sizes reach the host with one small copy. bic_pipeline_poll advances every slot whose
+ * last event has fired and starts queued rasters on free slots; it returns at once. All calls on one pipeline come from ONE
+ * thread. `out` / `info` of a job belong to the pipeline until the job is done; host buffers should be pinned (bic_host_alloc)
+ * or the copies serialise. */
+typedef struct bic_pipeline bic_pipeline;
+bic_status bic_pipeline_create(int device, int nslots, bic_pipeline** out);
+bic_status bic_pipeline_destroy(bic_pipeline* p);
+/* "first_batch" / "next_batch": iterations queued before the loop flag is looked at (default 2 / 2); any bic_ctx_set_option
+ * name is passed on to every slot */
+bic_status bic_pipeline_set_option(bic_pipeline* p, const char* name, int64_t value);
+/* bic_encode_raster, queued. *job (optional) receives the job's id (> 0). */
+bic_status bic_pipeline_submit(bic_pipeline* p, const uint8_t* pbm_payload, uint64_t rows, uint64_t cols, uint64_t W, uint64_t K,
+                               unsigned long seed, uint8_t* out, uint64_t cap_bytes, bic_encode_info* info, uint64_t* job);
+/* bic_encode_raster_resident, queued. producer (optional): the context on whose stream the raster is being written (e.g. by
+ * bic_split_bitplanes); the job is ordered after everything queued there so far. */
+bic_status bic_pipeline_submit_resident(bic_pipeline* p, const bic_mat* raster, bic_ctx* producer, uint64_t W, uint64_t K,
+                                        unsigned long seed, uint8_t* out, uint64_t cap_bytes, bic_encode_info* info, uint64_t* job);
+bic_status bic_pipeline_poll(bic_pipeline* p, uint64_t* unfinished);
+/* poll (yielding the core in between) until `job` is done; job = 0: until everything submitted is done */
+bic_status bic_pipeline_wait(bic_pipeline* p, uint64_t job);
+/* returns the job's own status once it is done (BIC_OK while it is still running); *error: its message */
+bic_status bic_pipeline_job_status(bic_pipeline* p, uint64_t job, int* done, const char** error);
+bic_status bic_pipeline_forget_finished(bic_pipeline* p);
+bic_status bic_pipeline_stats(bic_pipeline* p, uint64_t* launches, uint64_t* polls, uint64_t* batches, uint64_t* sync_fallbacks,
+                              uint64_t* recodes);
+/* stream ordering against a context outside the pool: every slot after `signal` / `waiter` after every slot */
+bic_status bic_pipeline_wait_ctx(bic_pipeline* p, bic_ctx* signal);
+bic_status bic_ctx_wait_pipeline(bic_ctx* waiter, bic_pipeline* p);
+
 #ifdef __cplusplus
 }
 #endif
