@@ -60,7 +60,10 @@ def parse():
     ap.add_argument("--chain-cluster", type=int, default=16, help="CTAs per cluster of the chain kernel")
     ap.add_argument("--e2e-planes", action="store_true", help="e2e from 16 host P4 planes (bic_encode_raster) instead of the 16-bit P5 payload")
     ap.add_argument("--sharded", action="store_true", help="also time the row-sharded (NCCL) fit at N=1")
-    ap.add_argument("--streams", type=int, default=24, help="contexts (CUDA streams) per GPU")
+    ap.add_argument("--streams", type=int, default=24, help="encoder slots (CUDA streams) per GPU")
+    ap.add_argument("--pool", action="store_true", help="round-1 driver: one host thread per context instead of the single-thread pipeline")
+    ap.add_argument("--first-batch", type=int, default=2, help="pipeline: iterations queued before the loop flag is first looked at")
+    ap.add_argument("--next-batch", type=int, default=2, help="pipeline: iterations per later batch")
     return ap.parse_args()
 
 
@@ -510,7 +513,30 @@ def main():
         return ctx.timer_stop()
 
     def all_launches():
-        return ctx.launches + sum(w.ctx.launches for w in workers)
+        return ctx.launches + sum(w.ctx.launches for w in workers) + (pipe.stats()["launches"] if pipe is not None else 0)
+
+    # ---- the pipeline: ONE host thread keeps `streams` rasters in flight (csrc/pipeline.cu)
+    use_pipe = not (args.pool or batched)
+    pipe = None
+    if use_pipe:
+        pipe = bic.Pipeline(local_rank, args.streams)
+        for name, val in (("first_batch", args.first_batch), ("next_batch", args.next_batch), ("dict_algo", args.dict_algo),
+                          ("chain_cluster", args.chain_cluster)):
+            pipe.set_option(name, val)
+
+    def pipe_steps_resident(nsteps):
+        """nsteps passes over the resident planes through the pipeline (no container copy: the streams stay on the device)"""
+        ctx.timer_start()
+        pipe.wait_for(ctx)
+        for _ in range(nsteps):
+            for b in order:
+                pipe.submit_resident(rasters[b], W, K, seed=SEED, out=None)
+            pipe.poll()
+        pipe.wait()
+        ctx.wait_for_pipeline(pipe)
+        ms = ctx.timer_stop()
+        pipe.forget_finished()
+        return ms
 
     # ---- resident timing
     run_steps(fit_resident, 1, record=True)
@@ -520,6 +546,14 @@ def main():
         batched_steps(1, record=True)
         assert stats["iters"] == per_plane_iters, "batched learner disagrees with the per-plane path"
         batched_steps(max(args.warmup, 3))
+    elif use_pipe:
+        # the pipeline must give what the per-plane calls gave (iteration counts and the three bit counts of every plane)
+        infos = [pipe.submit_resident(rasters[b], W, K, seed=SEED, out=None)[1] for b in range(P)]
+        pipe.wait()
+        assert [int(i.iterations) for i in infos] == stats["iters"], "pipeline disagrees with the per-plane path"
+        assert sum(int(i.bits_D + i.bits_A + i.bits_E) for i in infos) == sum(stats["bits"]), "pipeline disagrees with the per-plane path"
+        pipe.forget_finished()
+        pipe_steps_resident(max(args.warmup, 3))
     else:
         run_steps(fit_resident, max(args.warmup, 3))
     barrier()
@@ -529,7 +563,7 @@ def main():
     launches0 = all_launches()
     barrier()
     t_wall0 = time.time()
-    ms = batched_steps(args.steps) if batched else run_steps(fit_resident, args.steps)
+    ms = batched_steps(args.steps) if batched else (pipe_steps_resident(args.steps) if use_pipe else run_steps(fit_resident, args.steps))
     barrier()
     t_wall1 = time.time()
     launches = all_launches() - launches0
@@ -596,7 +630,73 @@ def main():
             raise errs[0]
         return ms
 
-    if pgm_mode and not batched:
+    def pipe_steps_e2e_pgm(nsteps):
+        """the 16-bit P5 payload in pinned host memory -> bic_split_bitplanes on the loader stream -> one pipeline job per plane
+        (ordered after the split) -> containers in pinned host memory; one host thread"""
+        jobs = []
+        ctx.timer_start()
+        loader.wait_for(ctx)
+        pipe.wait_for(ctx)
+        for s_ in range(nsteps):
+            if s_ >= NSETS:
+                for jb in jobs[s_ - NSETS]:
+                    pipe.wait(jb)
+            loader.split_bitplanes(host_pgm, rows, cols, 65535, plane_sets[s_ % NSETS], sync=False)
+            step_jobs = []
+            for b in order:
+                jb, info = pipe.submit_resident(plane_sets[s_ % NSETS][b], W, K, seed=SEED, out=e2e_outs[s_ % NSETS][b], producer=loader)
+                step_jobs.append(jb)
+                e2e_infos[b] = info
+            jobs.append(step_jobs)
+            pipe.poll()
+        pipe.wait()
+        ctx.wait_for(loader)
+        ctx.wait_for_pipeline(pipe)
+        ms = ctx.timer_stop()
+        for b in range(P):
+            stats["d2h"][b] = int(e2e_infos[b].container_bytes)
+        for step_jobs in jobs:
+            for jb in step_jobs:
+                done, st, msg = pipe.status(jb)
+                if st != 0:
+                    raise RuntimeError(f"pipeline job failed: {msg}")
+        pipe.forget_finished()
+        return ms
+
+    def pipe_steps_e2e_planes(nsteps):
+        ctx.timer_start()
+        pipe.wait_for(ctx)
+        infos = {}
+        for _ in range(nsteps):
+            for b in order:
+                infos[b] = pipe.submit(host_planes[b].reshape(-1), rows, cols, W, K, seed=SEED, out=e2e_outs[0][b])[1]
+            pipe.poll()
+        pipe.wait()
+        ctx.wait_for_pipeline(pipe)
+        ms = ctx.timer_stop()
+        for b in range(P):
+            stats["d2h"][b] = int(infos[b].container_bytes)
+        pipe.forget_finished()
+        return ms
+
+    if use_pipe:
+        NSETS = 3 if pgm_mode else 1
+        e2e_outs = [[ctx.pinned(2 * plane_bytes + (1 << 20)) for _ in range(P)] for _ in range(NSETS)]
+        e2e_infos = [None] * P
+        if pgm_mode:
+            loader = bic.Context(local_rank)
+            plane_sets = [[loader.matrix(rows, cols) for _ in range(P)] for _ in range(NSETS)]
+            pipe_steps_e2e_pgm(2)
+            barrier()
+            ms_e2e = pipe_steps_e2e_pgm(args.steps)
+            e2e_h2d, e2e_how = rows * cols * 2, ("16-bit P5 payload (pinned host) -> bic_split_bitplanes -> bic_pipeline_submit_resident per plane -> "
+                                                  "containers (pinned host); one host thread")
+        else:
+            pipe_steps_e2e_planes(2)
+            barrier()
+            ms_e2e = pipe_steps_e2e_planes(args.steps)
+            e2e_h2d, e2e_how = P * plane_bytes, "16 P4 planes (pinned host) -> bic_pipeline_submit per plane -> containers (pinned host); one host thread"
+    elif pgm_mode and not batched:
         loader = bic.Context(local_rank)
         loader.set_option("wait_mode", args.wait_mode)
         NSETS = 3  # images in flight: one being loaded and split, up to two being fitted and coded
@@ -787,8 +887,13 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args), "patch_width": W, "atoms": K, "patches_per_plane": n,
                        "parallelism": f"{world} rank(s), one 16-plane image per rank, no data-path collective; "
-                                      f"{T} contexts (CUDA streams) per rank keep independent planes in flight for extraction, "
-                                      f"initialisation and coding; learner: {'one batched call for all planes' if batched else 'per plane'}",
+                                      + (f"ONE host thread per rank drives a pipeline of {args.streams} encoder slots (CUDA streams): device-side pivot draw, "
+                                         f"learner iterations queued {args.first_batch}+{args.next_batch} at a time behind a device loop flag, asynchronous Golomb coder"
+                                         if use_pipe else
+                                         f"{T} contexts (CUDA streams, one host thread each) per rank keep independent planes in flight; learner: "
+                                         f"{'one batched call for all planes' if batched else 'per plane'}"),
+                       "host_threads_per_rank": 1 if use_pipe else T,
+                       "pipeline": pipe.stats() if pipe is not None else None,
                        "l2_policy": f"inputs larger than L2: {P} planes x {plane_bytes >> 20} MiB rasters + X/E/A "
                                     f"({(2 * n * m + n * K) // 8 >> 20} MiB per plane) cycle through a 126 MB L2",
                        "iterations_per_plane": stats["iters"], "golomb_bits_per_step": stats["bits"]},
@@ -809,6 +914,8 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if pipe is not None:
+        pipe.close()
     for w in workers:
         w.ctx.close()
     ctx.close()

@@ -541,7 +541,7 @@ class Context:
         return int(it.value)
 
     # ---- bit planes of a grey image (src/bitplane_tool.cpp:24-39)
-    def split_bitplanes(self, p5_payload: np.ndarray, rows: int, cols: int, maxval: int, planes=None):
+    def split_bitplanes(self, p5_payload: np.ndarray, rows: int, cols: int, maxval: int, planes=None, sync: bool = True):
         """P5 payload bytes (1 byte per pixel if maxval < 256 else 2, high byte first) -> list of rows x cols planes, LSB first"""
         n = 0
         b = 1
@@ -553,7 +553,8 @@ class Context:
         assert pay.size == rows * cols * (2 if maxval >= 256 else 1)
         arr = (_vp * n)(*[m.h for m in planes])
         self._ck(self.L.bic_split_bitplanes(self.h, pay.ctypes.data_as(_u8p), rows, cols, maxval, arr, n))
-        self.sync()  # pay may be a temporary
+        if sync:
+            self.sync()  # pay may be a temporary
         return planes
 
     # ---- MDL model selection (src/bsvd.cpp:1438-1717)

@@ -11,6 +11,15 @@
 
 #include "bic_b200.h"
 
+// NVTX ranges per phase of the path (tracing): visible in Nsight Systems / ncu --nvtx, free when no tool is attached
+// (nvtx3 is header-only and resolves its injection library lazily).
+#include <nvtx3/nvToolsExt.h>
+struct bic_nvtx_range {
+  explicit bic_nvtx_range(const char* name) { nvtxRangePushA(name); }
+  ~bic_nvtx_range() { nvtxRangePop(); }
+};
+#define BIC_RANGE(name) bic_nvtx_range _bic_range_(name)
+
 // ---------------------------------------------------------------------------------------------
 // Device layout of a bit matrix: uint32 words, MSB first (bit j of a row is bit 31-(j&31) of
 // word j>>5), stride = ceil(cols/32) words, pad bits zero. The allocation is rounded up to a
@@ -71,6 +80,8 @@ struct bic_ctx {
   // optional per-launch device timers
   int wait_mode = 0;       // how host threads wait for the stream: 0 cudaStreamSynchronize, 1 poll + sched_yield, 2 blocking event
   cudaEvent_t wait_ev = nullptr, wait_ev_blocking = nullptr;
+  int gol_algo = 2;        // 2: wide-tile encoder with fused scans (coding2.cu), 1: the first formulation (coding.cu)
+  int gol_presize_pct = 125;  // the asynchronous encoders size the code buffer to this percentage of the input bits (+ 4 KB)
   int gol_onepass = 0;     // 1: single-pass Golomb encoder (decoupled look-back) when the buffer is pre-sized
   int coef_algo = 1;  // 1: dictionaries of >= 64 atoms use the weight-sorted warp-per-row coefficient kernel; 0: always lane per row
   int dict_update = 0;  // which dictionary update the learners call: 0 update_dictionary_steepest, 1 update_dictionary_proximus (the reference's -d 1)

@@ -146,6 +146,7 @@ bic_status bic_k_split_bitplanes_dev(bic_ctx* c, const uint8_t* d_payload, uint6
 
 extern "C" bic_status bic_split_bitplanes(bic_ctx* c, const uint8_t* p5_payload, uint64_t rows, uint64_t cols, uint32_t maxval,
                                           bic_mat* const* planes, uint32_t nplanes) {
+  BIC_RANGE("bic:split_bitplanes");
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !p5_payload || !planes || maxval == 0 || maxval > 65535) return BIC_ERR_INVALID;
   if (nplanes != bic_bitplane_count(maxval) || nplanes > 16) return bic_fail(c, BIC_ERR_INVALID, "split_bitplanes: one matrix per b = 1, 2, 4, ... < maxval");

@@ -1,0 +1,506 @@
+// Golomb encoder, second formulation: the same bytes as coding.cu's (and as the serial coder implied by
+// src/GolombCoder.cpp:13-34), reorganised around what limited the first one (profiles/r1_coder_sweep.md):
+//
+//   * wide tiles: a thread takes 16 consecutive words (four independent 128-bit loads in flight), a CTA 4096 words, so the fixed
+//     cost per tile (two block scans, the tile's prefix) is spread over four times the input and the loads cover the latency;
+//   * no scan kernels: the LAST CTA to finish a pass (an arrival counter per stream) scans the per-tile totals itself, so a stream
+//     costs three launches (count, lengths, scatter) + one clear instead of seven, and nothing spins;
+//   * up to three streams per launch (the D, A and E of one raster): blockIdx selects the stream, each with its own coder state;
+//   * the scatter assembles every thread's codewords in registers (a thread's code is one contiguous bit range) and stores whole
+//     words into the tile's staged output: plain shared-memory stores for the words the thread owns outright, an atomic OR only
+//     for its first and last partial word, instead of two or three shared-memory atomics per codeword;
+//   * the output buffer is sized before the bit count is known (1.25 code bits per input bit + slack); the bit count, the sample
+//     count and an overflow flag stay on the device (info[]), so the encoder never waits for the host. A stream that does not fit
+//     is reported through the flag and re-encoded by the exact-size path of coding.cu.
+//
+// Coder state as in coding.cu: before sample t (the t-th one, at position pos_t, previous one at pos_{t-1}) the reference's
+// coder has samples = t, accumulatedError = pos_{t-1} + 1 - t (mod 2^32), k_t = min{k : (t << k) >= accumulatedError}.
+#include "gol_common.cuh"
+
+#define G2_THREADS 256
+#define G2_WPT 16
+#define G2_TILE_WORDS (G2_THREADS * G2_WPT)          // 4096 words = 131072 bits
+#define G2_TILE_BITS (G2_TILE_WORDS * 32)
+#define G2_STAGE_WORDS 6144                           // staged code words of one tile (1.5 x its input)
+#define G2_MAXSEG 3
+
+struct G2Seg {
+  const uint32_t* S;                 // dense bit stream of the matrix, MSB first
+  uint64_t T, N;                     // words, bits
+  uint32_t tile0, ntiles;            // block index of the stream's first tile, tiles
+  uint32_t* ones;                    // per tile: ones
+  long long* last;                   // per tile: position of the last one, -1 if none
+  unsigned long long* ones_before;   // exclusive prefixes, written by the last CTA of the count pass
+  long long* last_before;
+  unsigned long long* bits;          // per tile: code bits of its ones
+  unsigned long long* bits_before;   // exclusive prefix, written by the last CTA of the length pass
+  unsigned long long* tbits;         // per thread: code bits of its 16 words
+  unsigned int* done;                // [0] tiles that finished the count pass, [1] the length pass
+  unsigned long long* info;          // [0] bit count [1] samples [2] code bits of the ones [3] position after the last one [4] overflow
+  uint32_t* out;
+  unsigned long long* index;
+  unsigned long long cap_bits;
+  uint32_t chunk;                    // samples per chunk-index entry, a power of two
+};
+struct G2Params {
+  G2Seg s[G2_MAXSEG];
+  uint32_t nseg;
+};
+
+__device__ __forceinline__ const G2Seg& g2_segment(const G2Params& P, uint32_t* tile) {
+  uint32_t i = 0;
+  while (i + 1 < P.nseg && blockIdx.x >= P.s[i].tile0 + P.s[i].ntiles) ++i;
+  *tile = blockIdx.x - P.s[i].tile0;
+  return P.s[i];
+}
+
+// the thread's 16 words; words past the end of the stream read as zero
+__device__ __forceinline__ void g2_load(const G2Seg& g, uint64_t w0, uint32_t (&v)[G2_WPT]) {
+#pragma unroll
+  for (int j = 0; j < G2_WPT / 4; ++j) {
+    const uint64_t w = w0 + 4 * j;
+    if (w + 4 <= g.T) {
+      const uint4 q = *reinterpret_cast<const uint4*>(g.S + w);
+      v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[4 * j + i] = (w + i < g.T) ? g.S[w + i] : 0u;
+    }
+  }
+}
+
+// ones of the 16 words and the bit index (inside the tile) of the last one, -1 if none
+__device__ __forceinline__ void g2_count(const uint32_t (&v)[G2_WPT], uint32_t* c, int* last) {
+  uint32_t n = 0;
+  int l = -1;
+#pragma unroll
+  for (int i = 0; i < G2_WPT; ++i) {
+    n += __popc(v[i]);
+    if (v[i]) l = (int)(threadIdx.x * (G2_WPT * 32) + i * 32 + (32 - __ffs(v[i])));
+  }
+  *c = n;
+  *last = l;
+}
+
+// exclusive prefix sum and exclusive prefix max over the CTA's 256 threads (s_w: 16 words of shared memory)
+__device__ __forceinline__ void g2_scan(uint32_t c, int last, uint32_t* ex_c, int* ex_last, uint32_t* tot_c, int* tot_last, int* s_w) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t inc = c;
+  int incm = last;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    const int ym = __shfl_up_sync(0xffffffffu, incm, o);
+    if (lane >= o) { inc += y; incm = max(incm, ym); }
+  }
+  int exm = __shfl_up_sync(0xffffffffu, incm, 1);
+  if (lane == 0) exm = -1;
+  __syncthreads();                     // s_w may still be read from the previous use
+  if (lane == 31) { s_w[wib] = (int)inc; s_w[8 + wib] = incm; }
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+  int basem = -1, totm = -1;
+#pragma unroll
+  for (int w = 0; w < G2_THREADS / 32; ++w) {
+    const uint32_t x = (uint32_t)s_w[w];
+    const int xm = s_w[8 + w];
+    if (w < wib) { base += x; basem = max(basem, xm); }
+    tot += x;
+    totm = max(totm, xm);
+  }
+  *ex_c = base + inc - c;
+  *ex_last = max(basem, exm);
+  *tot_c = tot;
+  *tot_last = totm;
+}
+
+__device__ __forceinline__ unsigned long long g2_excl_sum_u64(unsigned long long v, unsigned long long* total, unsigned long long* s_w /* 8 */) {
+  return block_excl_scan_u64(v, total, s_w);
+}
+
+// k is the same for every sample of a stretch of `span` input bits that starts with sample rank t and consumed bits `consumed`
+// (coding.cu: golomb_k_stable, with the thread's stretch as a parameter)
+__device__ __forceinline__ bool g2_k_stable(uint64_t t, uint64_t consumed, uint32_t span, uint32_t* kout) {
+  if (t == 0 || t + span >= (1ull << 31)) return false;
+  const uint64_t acc = consumed - t;
+  if (acc + span >= (1ull << 31)) return false;
+  const uint32_t k = golomb_k(t, consumed);
+  if (((t + span - 1) << k) >= (1ull << 32)) return false;
+  if ((t << k) < acc + span) return false;
+  if (k > 0 && ((t + span - 1) << (k - 1)) >= acc) return false;
+  *kout = k;
+  return true;
+}
+
+// ------------------------------------------------------------------ pass 1: ones and last one per tile; the last CTA scans the tiles
+__global__ void __launch_bounds__(G2_THREADS) k_g2_count(G2Params P) {
+  __shared__ int s_w[16];
+  __shared__ unsigned long long s_a[8];
+  __shared__ long long s_b[8];
+  __shared__ int s_last_cta;
+  uint32_t tile;
+  const G2Seg& g = g2_segment(P, &tile);
+  uint32_t v[G2_WPT];
+  g2_load(g, (uint64_t)tile * G2_TILE_WORDS + threadIdx.x * G2_WPT, v);
+  uint32_t c, ex_c, tot_c;
+  int last, ex_last, tot_last;
+  g2_count(v, &c, &last);
+  g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
+  if (threadIdx.x == 0) {
+    g.ones[tile] = tot_c;
+    g.last[tile] = tot_last >= 0 ? (long long)tile * G2_TILE_BITS + tot_last : -1;
+    __threadfence();
+    s_last_cta = (atomicAdd(g.done, 1u) == g.ntiles - 1);
+  }
+  __syncthreads();
+  if (!s_last_cta) return;
+  __threadfence();
+  // exclusive scans over the stream's tiles: a contiguous run of tiles per thread, one block scan over the run totals
+  const uint64_t per = div_up_u64(g.ntiles, G2_THREADS);
+  const uint64_t t0 = threadIdx.x * per, t1 = (t0 + per < g.ntiles) ? t0 + per : g.ntiles;
+  unsigned long long sum = 0;
+  long long mx = -1;
+  for (uint64_t i = t0; i < t1; ++i) { sum += __ldcg(g.ones + i); const long long l = __ldcg(g.last + i); mx = mx > l ? mx : l; }
+  unsigned long long run = block_excl_scan_u64(sum, nullptr, s_a);
+  long long runm = block_excl_scan_max(mx, nullptr, s_b);
+  for (uint64_t i = t0; i < t1; ++i) {
+    g.ones_before[i] = run;
+    g.last_before[i] = runm;
+    run += __ldcg(g.ones + i);
+    const long long l = __ldcg(g.last + i);
+    runm = runm > l ? runm : l;
+  }
+}
+
+// ------------------------------------------------------------------ pass 2: code bits per thread and tile; the last CTA scans and totals
+__global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
+  __shared__ int s_w[16];
+  __shared__ unsigned long long s_a[8];
+  __shared__ int s_last_cta;
+  uint32_t tile;
+  const G2Seg& g = g2_segment(P, &tile);
+  uint32_t v[G2_WPT];
+  const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS + threadIdx.x * G2_WPT;
+  g2_load(g, w0, v);
+  uint32_t c, ex_c, tot_c;
+  int last, ex_last, tot_last;
+  g2_count(v, &c, &last);
+  g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
+  unsigned long long t = g.ones_before[tile] + ex_c;                                  // rank of my first sample
+  const long long lb = g.last_before[tile];
+  long long prev = ex_last >= 0 ? (long long)tile * G2_TILE_BITS + ex_last : lb;       // the one before my stretch, -1 if none
+  const long long tb = (long long)(w0 * 32);
+  unsigned long long mybits = 0;
+  if (c) {
+    bool first = true, fast = false;
+    uint32_t kc = 0, lpv = 0, fastbits = 0;
+#pragma unroll
+    for (int i = 0; i < G2_WPT; ++i) {
+      uint32_t b = v[i];
+      while (b) {
+        const int p = __clz(b);
+        b &= ~(0x80000000u >> p);
+        const uint32_t lp = (uint32_t)(i * 32 + p);
+        if (fast) {                                                                     // k = kc for the rest of my samples
+          fastbits += kc + 1 + ((lp - lpv - 1) >> kc);
+          lpv = lp;
+          continue;
+        }
+        const long long pos = tb + lp;
+        const unsigned long long x = (unsigned long long)(pos - prev - 1);
+        const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+        mybits += k + (x >> k) + 1;
+        prev = pos;
+        ++t;
+        if (first) {
+          first = false;
+          fast = g2_k_stable(t, (unsigned long long)(prev + 1), G2_WPT * 32, &kc);
+          lpv = lp;
+        }
+      }
+    }
+    mybits += fastbits;
+  }
+  g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x] = mybits;
+  unsigned long long tot;
+  g2_excl_sum_u64(mybits, &tot, s_a);
+  if (threadIdx.x == 0) {
+    g.bits[tile] = tot;
+    __threadfence();
+    s_last_cta = (atomicAdd(g.done + 1, 1u) == g.ntiles - 1);
+  }
+  __syncthreads();
+  if (!s_last_cta) return;
+  __threadfence();
+  const uint64_t per = div_up_u64(g.ntiles, G2_THREADS);
+  const uint64_t t0 = threadIdx.x * per, t1 = (t0 + per < g.ntiles) ? t0 + per : g.ntiles;
+  unsigned long long sum = 0;
+  for (uint64_t i = t0; i < t1; ++i) sum += __ldcg(g.bits + i);
+  unsigned long long carry;
+  unsigned long long run = block_excl_scan_u64(sum, &carry, s_a);
+  for (uint64_t i = t0; i < t1; ++i) { g.bits_before[i] = run; run += __ldcg(g.bits + i); }
+  if (threadIdx.x == 0) {
+    const uint64_t lt = g.ntiles - 1;
+    const unsigned long long ones = g.ones_before[lt] + g.ones[lt];
+    const long long lastg = g.last_before[lt] > g.last[lt] ? g.last_before[lt] : g.last[lt];
+    const unsigned long long consumed = (unsigned long long)(lastg + 1);
+    const unsigned long long x = g.N - consumed;                                        // the run closed by the virtual one
+    const uint32_t k = golomb_k(ones, consumed);
+    const unsigned long long total = carry + k + (x >> k) + 1;
+    g.info[0] = total;
+    g.info[1] = ones + 1;
+    g.info[2] = carry;
+    g.info[3] = consumed;
+    g.info[4] = (total + 64 > g.cap_bits) ? 1ull : 0ull;
+  }
+}
+
+// ------------------------------------------------------------------ clear: the words the codes will occupy
+__global__ void __launch_bounds__(256) k_g2_clear(G2Params P) {
+  for (uint32_t si = 0; si < P.nseg; ++si) {
+    const G2Seg& g = P.s[si];
+    if (g.info[4]) continue;
+    const unsigned long long nw = ((g.info[0] + 31) >> 5) + 4;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nw; i += (unsigned long long)gridDim.x * blockDim.x)
+      g.out[i] = 0u;
+  }
+}
+
+// ------------------------------------------------------------------ pass 3: scatter
+// A thread's codewords are the contiguous bit range [o, o + mybits) of the stream. They are built in a register (cur: the word
+// being filled, `fill` bits used from the top) and stored word by word into the tile's staged range.
+struct G2Out {
+  uint32_t* s_out;
+  uint32_t wp, fill, cur;
+  bool shared_word;      // the word being filled is shared with the previous thread (my range starts inside it)
+  __device__ __forceinline__ void store(uint32_t val) {
+    if (val) {
+      if (shared_word) atomicOr(&s_out[wp], val);
+      else s_out[wp] = val;
+    }
+    shared_word = false;
+    ++wp;
+  }
+  __device__ __forceinline__ void put(uint32_t cw, uint32_t L) {        // L <= 32 bits, right aligned in cw
+    const unsigned long long a = ((unsigned long long)cur << 32) | ((unsigned long long)cw << (64 - fill - L));
+    fill += L;
+    if (fill >= 32) { store((uint32_t)(a >> 32)); cur = (uint32_t)a; fill -= 32; }
+    else cur = (uint32_t)(a >> 32);
+  }
+  __device__ __forceinline__ void zeros(unsigned long long u) {         // u zero bits (the buffer is zeroed: just move on)
+    const unsigned long long total = fill + u;
+    if (total >= 32) {
+      store(cur);
+      wp += (uint32_t)(total >> 5) - 1;
+      cur = 0;
+      fill = (uint32_t)(total & 31);
+    } else {
+      fill = (uint32_t)total;
+    }
+  }
+  __device__ __forceinline__ void finish() {                            // my last partial word is shared with the next thread
+    if (fill && cur) atomicOr(&s_out[wp], cur);
+  }
+};
+
+__global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
+  __shared__ int s_w[16];
+  __shared__ unsigned long long s_a[8];
+  __shared__ uint32_t s_out[G2_STAGE_WORDS];
+  uint32_t tile;
+  const G2Seg& g = g2_segment(P, &tile);
+  if (g.info[4]) return;                                                 // the code does not fit: nothing is written
+  uint32_t v[G2_WPT];
+  const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS + threadIdx.x * G2_WPT;
+  g2_load(g, w0, v);
+  uint32_t c, ex_c, tot_c;
+  int last, ex_last, tot_last;
+  g2_count(v, &c, &last);
+  g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
+  unsigned long long t = g.ones_before[tile] + ex_c;
+  const long long lb = g.last_before[tile];
+  long long prev = ex_last >= 0 ? (long long)tile * G2_TILE_BITS + ex_last : lb;
+  const long long tb = (long long)(w0 * 32);
+  const unsigned long long mybits = g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x];
+  unsigned long long tot;
+  const unsigned long long ex = g2_excl_sum_u64(mybits, &tot, s_a);
+  const unsigned long long o0 = g.bits_before[tile];
+  const unsigned long long base = o0 & ~31ull;                           // stream bit position of s_out[0]
+  const unsigned long long span_words = ((o0 - base) + tot + 31) >> 5;
+  const bool staged = span_words <= G2_STAGE_WORDS;                      // uniform over the CTA
+  const unsigned long long cmask = (unsigned long long)g.chunk - 1;
+  const int clog = 31 - __clz(g.chunk);
+  if (staged) {
+    for (unsigned i = threadIdx.x; i < (unsigned)span_words; i += blockDim.x) s_out[i] = 0;
+    __syncthreads();
+    if (c) {
+      const uint32_t ob = (uint32_t)(o0 + ex - base);
+      G2Out w;
+      w.s_out = s_out; w.wp = ob >> 5; w.fill = ob & 31; w.cur = 0; w.shared_word = (ob & 31) != 0;
+      bool first = true, fast = false;
+      uint32_t kc = 0, lpv = 0;
+#pragma unroll
+      for (int i = 0; i < G2_WPT; ++i) {
+        uint32_t b = v[i];
+        while (b) {
+          const int p = __clz(b);
+          b &= ~(0x80000000u >> p);
+          const uint32_t lp = (uint32_t)(i * 32 + p);
+          uint32_t k;
+          unsigned long long x;
+          if (fast) { k = kc; x = lp - lpv - 1; }
+          else { k = golomb_k(t, (unsigned long long)(prev + 1)); x = (unsigned long long)(tb + lp - prev - 1); }
+          if ((t & cmask) == 0) {                                        // chunk index: where this sample's codeword and run start
+            const unsigned long long slot = t >> clog;
+            g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
+            g.index[2 * slot + 1] = fast ? (unsigned long long)(tb + lpv + 1) : (unsigned long long)(prev + 1);
+          }
+          const unsigned long long u = x >> k;
+          const uint32_t rem = (uint32_t)(x & ((1ull << k) - 1));
+          if (k + u + 1 <= 32) {
+            w.put((rem << (uint32_t)(u + 1)) | 1u, k + (uint32_t)u + 1);  // k remainder bits, u zeros, a one
+          } else {
+            if (k) w.put(rem, k);
+            w.zeros(u);
+            w.put(1u, 1);
+          }
+          lpv = lp;
+          ++t;
+          if (!fast) {
+            prev = tb + lp;
+            if (first) {
+              first = false;
+              fast = g2_k_stable(t, (unsigned long long)(prev + 1), G2_WPT * 32, &kc);
+            }
+          }
+        }
+      }
+      w.finish();
+    }
+    __syncthreads();
+    uint32_t* gout = g.out + (base >> 5);
+    for (unsigned i = threadIdx.x; i < (unsigned)span_words; i += blockDim.x) {
+      const uint32_t wv = s_out[i];
+      if (!wv) continue;
+      if (i == 0 || i == (unsigned)span_words - 1) atomicOr(gout + i, bswap32(wv));   // shared with the neighbouring tiles
+      else gout[i] = bswap32(wv);
+    }
+  } else if (c) {
+    // a tile whose code is far longer than its input (long unary parts): codewords go straight to global memory
+    unsigned long long o = o0 + ex;
+#pragma unroll
+    for (int i = 0; i < G2_WPT; ++i) {
+      uint32_t b = v[i];
+      while (b) {
+        const int p = __clz(b);
+        b &= ~(0x80000000u >> p);
+        const long long pos = tb + i * 32 + p;
+        const unsigned long long x = (unsigned long long)(pos - prev - 1);
+        const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+        if ((t & cmask) == 0) { g.index[2 * (t >> clog)] = o; g.index[2 * (t >> clog) + 1] = (unsigned long long)(prev + 1); }
+        put_bits(g.out, o, (uint32_t)(x & ((1ull << k) - 1)), k);
+        const unsigned long long stop = o + k + (x >> k);
+        put_one(g.out, stop);
+        o = stop + 1;
+        prev = pos;
+        ++t;
+      }
+    }
+  }
+  if (tile == 0 && threadIdx.x == 0) {                                   // the run closed by the virtual one
+    const unsigned long long tt = g.info[1] - 1, consumed = g.info[3];
+    unsigned long long oo = g.info[2];
+    const unsigned long long x = g.N - consumed;
+    const uint32_t k = golomb_k(tt, consumed);
+    if ((tt & cmask) == 0) { g.index[2 * (tt >> clog)] = oo; g.index[2 * (tt >> clog) + 1] = consumed; }
+    put_bits(g.out, oo, (uint32_t)(x & ((1ull << k) - 1)), k);
+    oo += k + (x >> k);
+    put_one(g.out, oo);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+bic_status bic_stream_reserve_for(bic_ctx* c, bic_stream* s, uint64_t bitcount, uint64_t nchunks, uint64_t src_bits);
+bic_status bic_dense_stream_into(bic_ctx* c, const bic_mat* M, uint32_t* scratch, const uint32_t** S, uint64_t* T);
+
+// Up to three matrices in one set of launches. outs[i] is sized here; d_info + 8 * i receives stream i's info words. Nothing
+// waits for the host. Every matrix must have at least one bit (the callers route empty ones to coding.cu).
+bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int nmat, uint32_t chunk_samples, bic_stream* const* outs,
+                                     unsigned long long* d_info) {
+  if (nmat < 1 || nmat > G2_MAXSEG) return BIC_ERR_INVALID;
+  G2Params P;
+  memset(&P, 0, sizeof(P));
+  P.nseg = (uint32_t)nmat;
+  // scratch: per stream, the compacted copy (only when cols is not a multiple of 32) and the per-tile arrays
+  uint64_t words_compact = 0, ntiles_total = 0;
+  uint64_t Ts[G2_MAXSEG], nts[G2_MAXSEG];
+  for (int i = 0; i < nmat; ++i) {
+    const uint64_t N = mats[i]->rows * mats[i]->cols;
+    if (N == 0) return BIC_ERR_INVALID;
+    Ts[i] = div_up_u64(N, 32);
+    nts[i] = div_up_u64(Ts[i], G2_TILE_WORDS);
+    if (mats[i]->cols & 31) words_compact += (Ts[i] + 7) & ~(uint64_t)3;
+    ntiles_total += nts[i];
+  }
+  if (ntiles_total >= (1ull << 31)) return bic_fail(c, BIC_ERR_UNSUPPORTED, "golomb: too many tiles for one launch");
+  if (words_compact) BIC_TRY(bic_scratch_reserve(c, &c->work[4], words_compact * 4 + 64));
+  const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8;   // last, ones_before, last_before, bits, bits_before | ones (padded to 8) | tbits
+  BIC_TRY(bic_scratch_reserve(c, &c->work[5], ntiles_total * per_tile + 64 * G2_MAXSEG + 64));
+  uint8_t* p = (uint8_t*)c->work[5].p;
+  unsigned int* done = (unsigned int*)p;                         // 2 counters per stream, 64 bytes apart
+  BIC_CUDA(c, cudaMemsetAsync(done, 0, 64 * G2_MAXSEG, c->stream));
+  p += 64 * G2_MAXSEG;
+  uint32_t* compact = (uint32_t*)c->work[4].p;
+  uint32_t tile0 = 0;
+  for (int i = 0; i < nmat; ++i) {
+    G2Seg& g = P.s[i];
+    const bic_mat* M = mats[i];
+    g.N = M->rows * M->cols;
+    // pre-sized for gol_presize_pct (default 125) % of the input bits + slack; the stream object's buffer only ever grows
+    const uint64_t want_bits = g.N / 100 * (uint64_t)c->gol_presize_pct + 32768;
+    BIC_TRY(bic_stream_reserve_for(c, outs[i], want_bits, div_up_u64(g.N + 1, chunk_samples), 0));
+    if (M->cols & 31) {
+      BIC_TRY(bic_dense_stream_into(c, M, compact, &g.S, &g.T));
+      compact += (Ts[i] + 7) & ~(uint64_t)3;
+    } else {
+      g.S = M->d; g.T = Ts[i];
+    }
+    g.tile0 = tile0; g.ntiles = (uint32_t)nts[i];
+    tile0 += g.ntiles;
+    const size_t nt = nts[i];
+    g.last = (long long*)p;                         p += nt * 8;
+    g.ones_before = (unsigned long long*)p;         p += nt * 8;
+    g.last_before = (long long*)p;                  p += nt * 8;
+    g.bits = (unsigned long long*)p;                p += nt * 8;
+    g.bits_before = (unsigned long long*)p;         p += nt * 8;
+    g.ones = (uint32_t*)p;                          p += nt * 8;
+    g.tbits = (unsigned long long*)p;               p += nt * (size_t)G2_THREADS * 8;
+    g.done = done + 16 * i;
+    g.info = d_info + 8 * i;
+    g.out = (uint32_t*)outs[i]->d_bytes;
+    g.index = (unsigned long long*)outs[i]->d_index;
+    g.cap_bits = (uint64_t)(outs[i]->cap_bytes - 32) * 8;
+    if (c->gol_presize_pct < 100 && g.cap_bits > want_bits) g.cap_bits = want_bits;   // a test setting: pretend the buffer is that small
+    g.chunk = chunk_samples;
+    outs[i]->info.coder = BIC_CODER_GOLOMB;
+    outs[i]->info.chunk_samples = chunk_samples;
+    outs[i]->info.rows = M->rows;
+    outs[i]->info.cols = M->cols;
+    outs[i]->info.bitcount = outs[i]->info.nsamples = outs[i]->info.nchunks = 0;
+  }
+  BIC_PROF(c, KID_GOL_TILE_COUNTS);
+  k_g2_count<<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  BIC_LAUNCH_CHECK(c);
+  BIC_PROF(c, KID_GOL_LENGTHS);
+  k_g2_lengths<<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  BIC_LAUNCH_CHECK(c);
+  uint64_t maxN = 0;
+  for (int i = 0; i < nmat; ++i) maxN = P.s[i].N > maxN ? P.s[i].N : maxN;
+  BIC_PROF(c, KID_GOL_SCAN_B);
+  k_g2_clear<<<bic_grid_for(c, div_up_u64(maxN, 32) + 4, 256, 4), 256, 0, c->stream>>>(P);
+  BIC_LAUNCH_CHECK(c);
+  BIC_PROF(c, KID_GOL_SCATTER);
+  k_g2_scatter<<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}

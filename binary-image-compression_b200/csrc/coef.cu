@@ -358,6 +358,7 @@ bic_status bic_k_update_coefficients_batched(bic_ctx* c, uint64_t n, uint64_t m,
 
 // device-side entry used by the learner too: adds the changed-row count to *d_changed
 bic_status bic_k_update_coefficients(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat* A, unsigned long long* d_changed) {
+  BIC_RANGE("bic:update_coefficients");
   if (E->rows != A->rows || E->cols != D->cols || A->cols != D->rows)
     return bic_fail(c, BIC_ERR_INVALID, "update_coefficients: shapes must be E n x m, D p x m, A n x p");
   if (E->rows == 0 || D->rows == 0) return BIC_OK;
@@ -480,6 +481,7 @@ static bic_status launch_residual(bic_ctx* c, const bic_mat* X, const bic_mat* A
 }
 
 extern "C" bic_status bic_residual(bic_ctx* c, const bic_mat* X, const bic_mat* A, const bic_mat* D, bic_mat* E) {
+  BIC_RANGE("bic:residual");
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !X || !A || !D || !E) return BIC_ERR_INVALID;
   if (X->rows != A->rows || X->cols != D->cols || A->cols != D->rows || E->rows != X->rows || E->cols != X->cols)

@@ -225,6 +225,7 @@ bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const 
 bool bic_dict_chain_eligible(bic_ctx* c, uint64_t n, uint64_t p, uint64_t wprE);
 
 bic_status bic_k_update_dictionary(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
+  BIC_RANGE("bic:update_dictionary_steepest");
   if (E->rows != A->rows || E->cols != D->cols || A->cols != D->rows)
     return bic_fail(c, BIC_ERR_INVALID, "update_dictionary: shapes must be E n x m, D p x m, A n x p");
   if (c->dict_algo == 2 && bic_dict_chain_eligible(c, E->rows, D->rows, E->wpr)) return bic_k_update_dictionary_v3(c, E, D, A, d_changed);

@@ -489,6 +489,7 @@ bool bic_dict_chain_eligible(bic_ctx* c, uint64_t n, uint64_t p, uint64_t wprE) 
 }
 
 bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
+  BIC_RANGE("bic:update_dictionary_steepest(cluster chain)");
   const uint64_t n = E->rows, p = D->rows, wprE = E->wpr, wprA = A->wpr, hs = wprE * 32;
   if (n == 0 || p == 0 || E->cols == 0) return BIC_OK;
   // work[3]: H (p*hs) | U (p) | count (4) | hcount (wprA*32) | cursor (wprA*32) | delta (p*wprE) | chmask (wprA + 1)

@@ -341,6 +341,7 @@ __global__ void k_split_u64_limbs(const unsigned long long* __restrict__ in, uin
 // allreduce as H and U; d_counts[1] receives the changed atoms (identical on every rank).
 static bic_status dist_update_dictionary(bic_ctx* c, bic_comm* m, bic_mat* E, bic_mat* D, const bic_mat* A,
                                          unsigned long long* d_counts) {
+  BIC_RANGE("bic:dist:update_dictionary");
   if (D->rows == 0 || E->cols == 0) return BIC_OK;
   DictWork w;
   // With peer windows the histograms live in the window: the fix kernel of an atom that changes adds its corrections

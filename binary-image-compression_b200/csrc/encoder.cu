@@ -10,6 +10,7 @@ bic_status bic_k_update_dictionary(bic_ctx* c, bic_mat* E, bic_mat* D, const bic
 
 extern "C" bic_status bic_learn_model_traditional(bic_ctx* c, const bic_mat* X, bic_mat* E, bic_mat* D, bic_mat* A,
                                                   uint64_t* iterations, uint64_t* trace, uint64_t trace_cap) {
+  BIC_RANGE("bic:learn_model_traditional");
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !X || !E || !D || !A) return BIC_ERR_INVALID;
   BIC_TRY(bic_residual(c, X, A, D, E));  // mul(A,false,D,false,E); add(E,X,E)  src/bsvd.cpp:1219-1220

@@ -112,6 +112,7 @@ __global__ void k_assemble(const uint32_t* __restrict__ X, uint32_t* __restrict_
 }
 
 extern "C" bic_status bic_extract_patches(bic_ctx* c, const bic_mat* raster, uint64_t W, bic_mat* X) {
+  BIC_RANGE("bic:extract_patches");
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !raster || !X || W == 0) return BIC_ERR_INVALID;
   const uint64_t Ny = (W - 1 + raster->rows) / W, Nx = (W - 1 + raster->cols) / W;  // bsvd_test.cpp:82-83

@@ -287,6 +287,7 @@ bic_status bic_k_init_finalize(bic_ctx* c, InitWork* w, uint64_t m, bic_mat* D);
 // the stream. d_state: the rand48 state (device u64, in/out); d_status: 2 u64 ([0] != 0: X is all zero, D is garbage).
 bic_status bic_k_init_neighbor_async(bic_ctx* c, const bic_mat* X, bic_mat* D, bic_mat* A, uint64_t* d_state,
                                      unsigned long long* d_status) {
+  BIC_RANGE("bic:initialize_model_neighbor(async)");
   const uint64_t p = D->rows;
   if (D->cols != X->cols || A->rows != X->rows || A->cols != p)
     return bic_fail(c, BIC_ERR_INVALID, "init: shapes must be X n x m, D p x m, A n x p");
@@ -366,6 +367,7 @@ extern "C" bic_status bic_initialize_model_neighbor_pivots(bic_ctx* c, const bic
 
 extern "C" bic_status bic_initialize_model_neighbor(bic_ctx* c, const bic_mat* X, bic_mat* D, bic_mat* A,
                                                     uint64_t* rng_state) {
+  BIC_RANGE("bic:initialize_model_neighbor");
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !X || !D || !A || !rng_state) return BIC_ERR_INVALID;
   const uint64_t p = D->rows;

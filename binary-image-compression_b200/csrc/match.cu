@@ -199,6 +199,7 @@ struct GolombCounter {  // GolombCoder as the reference ships it: a bit COUNTER 
 
 static bic_status match_run(bic_ctx* c, bic_mat* raster, uint32_t mode, uint64_t W, uint64_t T, uint64_t R, bic_match_rec* recs,
                             bic_match_totals* tot) {
+  BIC_RANGE("bic:match_patches");
   if (!c || !raster || !recs || !tot) return BIC_ERR_INVALID;
   cudaSetDevice(c->device);
   const uint64_t rows = raster->rows, cols = raster->cols;

@@ -26,6 +26,8 @@ bool bic_dict_chain_eligible(bic_ctx* c, uint64_t n, uint64_t p, uint64_t wprE);
 bic_status bic_k_init_neighbor_async(bic_ctx* c, const bic_mat* X, bic_mat* D, bic_mat* A, uint64_t* d_state, unsigned long long* d_status);
 bic_status bic_k_golomb_encode_async(bic_ctx* c, const bic_mat* M, uint32_t chunk_samples, bic_stream* out, unsigned long long* d_info);
 bic_status bic_golomb_async_finish(bic_stream* out, const uint64_t* host_info);
+bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int nmat, uint32_t chunk_samples, bic_stream* const* outs,
+                                     unsigned long long* d_info);
 
 #define LOOP_TRACE 64
 struct LoopState {
@@ -183,6 +185,7 @@ static bic_status mirror_and_mark(Slot& s, bool with_trace) {
 static bic_status encode_sync(Slot& s, Job* j, const bic_mat* rast);
 
 static void job_start(bic_pipeline* P, Slot& s, Job* j) {
+  BIC_RANGE("bic:pipeline:job_start");
   s.job = j;
   P->in_flight++;
   bic_ctx* c = s.c;
@@ -251,6 +254,7 @@ static bic_status encode_sync(Slot& s, Job* j, const bic_mat* rast) {
 }
 
 static void slot_advance(bic_pipeline* P, Slot& s) {
+  BIC_RANGE("bic:pipeline:advance");
   bic_ctx* c = s.c;
   Job* j = s.job;
   if (s.stage == ST_LEARN) {
@@ -264,8 +268,12 @@ static void slot_advance(bic_pipeline* P, Slot& s) {
       return;
     }
     const bic_mat* mats[3] = {s.D, s.A, s.E};
-    for (int i = 0; i < 3 && st == BIC_OK; ++i)
-      st = bic_k_golomb_encode_async(c, mats[i], 256, s.st[i], (unsigned long long*)(s.d_status + SW_INFO + 8 * i));
+    if (c->gol_algo == 2) {                      // D, A and E in one set of launches (coding2.cu)
+      st = bic_k_golomb_encode_multi(c, mats, 3, 256, s.st, (unsigned long long*)(s.d_status + SW_INFO));
+    } else {
+      for (int i = 0; i < 3 && st == BIC_OK; ++i)
+        st = bic_k_golomb_encode_async(c, mats[i], 256, s.st[i], (unsigned long long*)(s.d_status + SW_INFO + 8 * i));
+    }
     if (st == BIC_OK) st = mirror_and_mark(s, true);
     if (st != BIC_OK) return job_finish(P, s, st);
     s.stage = ST_CODE;

@@ -72,6 +72,10 @@ bic_status bic_ctx_wait_ctx(bic_ctx* waiter, bic_ctx* signal);
  *   lane per row.
  * "chain_cluster": CTAs in dict3.cu's cluster, 1/2/4/8/16 (default 16, 8 where 16 cannot be co-scheduled).
  * "chain_bucket_cap": entries of dict3.cu's per-atom row buckets, -1 (default) = 2 per row; 0 = always scan the list.
+ * "gol_algo": 2 (default) = Golomb encoder with wide tiles, scans fused into the passes and register-assembled codewords
+ *   (coding2.cu), 1 = the first formulation (coding.cu: counts / scan / lengths / scan / scatter).
+ * "gol_presize_pct": the encoders that do not wait for the bit count size the code buffer to this percentage of the input bits
+ *   (default 125); a code that does not fit is re-encoded by the exact-size path (values below 100 exist to test that).
  * "gol_onepass": 1 = single-pass Golomb encoder with decoupled look-back, 0 (default) = counts / lengths / scatter.
  * "wait_mode": how the calling thread waits for results: 0 (default) cudaStreamSynchronize, 1 poll + sched_yield
  *   (many contexts / several ranks per box), 2 blocking event. */

@@ -255,10 +255,16 @@ CODER_SHAPES = [(1, 1, 0.0), (1, 1, 1.0), (1, 32, 0.0), (3, 64, 0.5), (17, 100, 
                 (3, 70, 1.0), (300, 256, 0.005), (1000, 64, 0.02), (2000, 1024, 0.1), (1, 200000, 0.001), (4096, 32, 0.3)]
 
 
-@pytest.mark.parametrize("onepass", [0, 1])
-@pytest.mark.parametrize("rows,cols,rho", CODER_SHAPES)
-def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho, onepass):
-    ctx.set_option("gol_onepass", onepass)  # 1: single kernel with decoupled look-back, 0: three-kernel pipeline
+CODER_SHAPES_BIG = [(700, 1024, 0.5), (1200, 1024, 0.003), (640, 2048, 0.12), (300, 4100, 0.9), (2, 600000, 0.0005), (1500, 1000, 0.0)]
+
+
+@pytest.mark.parametrize("algo,onepass", [(2, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("rows,cols,rho", CODER_SHAPES + CODER_SHAPES_BIG)
+def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho, algo, onepass):
+    # algo 2: wide tiles, scans fused into the passes, register-assembled codewords (coding2.cu); 1: the first formulation
+    # (coding.cu), as three kernels + scans (onepass 0) or one kernel with decoupled look-back (onepass 1)
+    ctx.set_option("gol_algo", algo)
+    ctx.set_option("gol_onepass", onepass)
     rng = np.random.default_rng(rows * 31 + cols)
     bits = (rng.random((rows, cols)) < rho).astype(np.uint8)
     Mw = synth.pack_rows(bits)
@@ -281,6 +287,65 @@ def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, c
         M2.destroy(); s.destroy()
     M.destroy()
     ctx.set_option("gol_onepass", 0)
+    ctx.set_option("gol_algo", 2)
+
+
+@pytest.mark.parametrize("algo", [2, 1])
+@pytest.mark.parametrize("dense_rows", [40, 400])
+def test_golomb_sparse_then_dense(ctx, oracle, synth, algo, dense_rows):
+    """a long almost empty stretch (k adapts upwards) followed by dense rows: every one of the dense part costs k + 1 bits until
+    the coder has adapted back, so those tiles' codes are many times their input (the scatter's straight-to-global path) and,
+    with enough dense rows, the whole code outgrows the pre-sized buffer (the exact-size path takes over)"""
+    ctx.set_option("gol_algo", algo)
+    rows, cols = 2048 + dense_rows, 1024
+    rng = np.random.default_rng(dense_rows)
+    bits = np.zeros((rows, cols), np.uint8)
+    bits[::300, 17] = 1
+    bits[2048:] = (rng.random((dense_rows, cols)) < 0.5).astype(np.uint8)
+    Mw = synth.pack_rows(bits)
+    so, nbits_o, ns_o = oracle.golomb_encode(Mw, cols)
+    M = ctx.matrix(rows, cols, Mw)
+    s = ctx.golomb_encode(M)
+    assert s.info.bitcount == nbits_o and s.info.nsamples == ns_o
+    by, idx = s.download()
+    assert np.array_equal(by, so)
+    M2 = ctx.matrix(rows, cols)
+    ctx.golomb_decode(s, M2)
+    assert np.array_equal(M2.download(), Mw)
+    ctx.set_option("gol_algo", 2)
+
+
+def test_golomb_code_outgrows_the_presized_buffer(ctx, bic, oracle, synth):
+    """the encoders that do not wait for the bit count write into a pre-sized buffer; when the code does not fit nothing is
+    written, the overflow flag comes back and the exact-size path encodes again: same bytes (forced here with a 10 % buffer),
+    through bic_golomb_encode and through the pipeline"""
+    rows, cols = 900, 1024
+    bits = (np.random.default_rng(77).random((rows, cols)) < 0.3).astype(np.uint8)
+    Mw = synth.pack_rows(bits)
+    so, nbits_o, ns_o = oracle.golomb_encode(Mw, cols)
+    ctx.set_option("gol_presize_pct", 10)
+    try:
+        M = ctx.matrix(rows, cols, Mw)
+        s = ctx.stream()
+        ctx.golomb_encode(M, out=s)
+        assert s.info.bitcount == nbits_o
+        assert np.array_equal(s.download()[0], so)
+    finally:
+        ctx.set_option("gol_presize_pct", 125)
+    pipe = bic.Pipeline(0, 2)
+    try:
+        pipe.set_option("gol_presize_pct", 10)
+        page = (np.random.default_rng(5).random((1024, 1024)) < 0.4).astype(np.uint8)   # noise: the residual stays dense
+        pay = ctx.pinned(1024 * 128)
+        pay[:] = synth.pbm_bytes(page).reshape(-1)
+        out = ctx.pinned(1 << 20)
+        job, info = pipe.submit(pay, 1024, 1024, 8, 16, out=out)
+        pipe.result(job)
+        assert pipe.stats()["recodes"] >= 1
+        cont, info2 = ctx.encode_raster(synth.pbm_bytes(page), 1024, 1024, 8, 16)
+        assert np.array_equal(out[: len(cont)], cont)
+    finally:
+        pipe.close()
 
 
 @pytest.mark.parametrize("rows,cols,rho", CODER_SHAPES[:11])
