@@ -18,10 +18,11 @@
 #include "gol_common.cuh"
 
 #define G2_THREADS 256
-#define G2_WPT 16
-#define G2_TILE_WORDS (G2_THREADS * G2_WPT)          // 4096 words = 131072 bits
-#define G2_TILE_BITS (G2_TILE_WORDS * 32)
-#define G2_STAGE_WORDS 6144                           // staged code words of one tile (1.5 x its input)
+// words per thread: 16 for long streams (four 128-bit loads in flight per thread, 4096-word tiles), 4 for streams so short that
+// 4096-word tiles would not fill the SMs for several waves (a thread's codewords are a serial chain: few fat CTAs end in a tail)
+#define G2_TILE_WORDS(WPT) (G2_THREADS * (WPT))
+#define G2_TILE_BITS(WPT) (G2_TILE_WORDS(WPT) * 32)
+#define G2_STAGE_WORDS(WPT) (G2_TILE_WORDS(WPT) * 3 / 2)   // staged code words of one tile (1.5 x its input)
 #define G2_MAXSEG 3
 
 struct G2Seg {
@@ -55,9 +56,10 @@ __device__ __forceinline__ const G2Seg& g2_segment(const G2Params& P, uint32_t* 
 }
 
 // the thread's 16 words; words past the end of the stream read as zero
-__device__ __forceinline__ void g2_load(const G2Seg& g, uint64_t w0, uint32_t (&v)[G2_WPT]) {
+template <int WPT>
+__device__ __forceinline__ void g2_load(const G2Seg& g, uint64_t w0, uint32_t (&v)[WPT]) {
 #pragma unroll
-  for (int j = 0; j < G2_WPT / 4; ++j) {
+  for (int j = 0; j < WPT / 4; ++j) {
     const uint64_t w = w0 + 4 * j;
     if (w + 4 <= g.T) {
       const uint4 q = *reinterpret_cast<const uint4*>(g.S + w);
@@ -70,13 +72,14 @@ __device__ __forceinline__ void g2_load(const G2Seg& g, uint64_t w0, uint32_t (&
 }
 
 // ones of the 16 words and the bit index (inside the tile) of the last one, -1 if none
-__device__ __forceinline__ void g2_count(const uint32_t (&v)[G2_WPT], uint32_t* c, int* last) {
+template <int WPT>
+__device__ __forceinline__ void g2_count(const uint32_t (&v)[WPT], uint32_t* c, int* last) {
   uint32_t n = 0;
   int l = -1;
 #pragma unroll
-  for (int i = 0; i < G2_WPT; ++i) {
+  for (int i = 0; i < WPT; ++i) {
     n += __popc(v[i]);
-    if (v[i]) l = (int)(threadIdx.x * (G2_WPT * 32) + i * 32 + (32 - __ffs(v[i])));
+    if (v[i]) l = (int)(threadIdx.x * (WPT * 32) + i * 32 + (32 - __ffs(v[i])));
   }
   *c = n;
   *last = l;
@@ -133,6 +136,7 @@ __device__ __forceinline__ bool g2_k_stable(uint64_t t, uint64_t consumed, uint3
 }
 
 // ------------------------------------------------------------------ pass 1: ones and last one per tile; the last CTA scans the tiles
+template <int WPT>
 __global__ void __launch_bounds__(G2_THREADS) k_g2_count(G2Params P) {
   __shared__ int s_w[16];
   __shared__ unsigned long long s_a[8];
@@ -140,15 +144,15 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_count(G2Params P) {
   __shared__ int s_last_cta;
   uint32_t tile;
   const G2Seg& g = g2_segment(P, &tile);
-  uint32_t v[G2_WPT];
-  g2_load(g, (uint64_t)tile * G2_TILE_WORDS + threadIdx.x * G2_WPT, v);
+  uint32_t v[WPT];
+  g2_load(g, (uint64_t)tile * G2_TILE_WORDS(WPT) + threadIdx.x * WPT, v);
   uint32_t c, ex_c, tot_c;
   int last, ex_last, tot_last;
   g2_count(v, &c, &last);
   g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
   if (threadIdx.x == 0) {
     g.ones[tile] = tot_c;
-    g.last[tile] = tot_last >= 0 ? (long long)tile * G2_TILE_BITS + tot_last : -1;
+    g.last[tile] = tot_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + tot_last : -1;
     __threadfence();
     s_last_cta = (atomicAdd(g.done, 1u) == g.ntiles - 1);
   }
@@ -173,14 +177,15 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_count(G2Params P) {
 }
 
 // ------------------------------------------------------------------ pass 2: code bits per thread and tile; the last CTA scans and totals
+template <int WPT>
 __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   __shared__ int s_w[16];
   __shared__ unsigned long long s_a[8];
   __shared__ int s_last_cta;
   uint32_t tile;
   const G2Seg& g = g2_segment(P, &tile);
-  uint32_t v[G2_WPT];
-  const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS + threadIdx.x * G2_WPT;
+  uint32_t v[WPT];
+  const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS(WPT) + threadIdx.x * WPT;
   g2_load(g, w0, v);
   uint32_t c, ex_c, tot_c;
   int last, ex_last, tot_last;
@@ -188,14 +193,14 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
   unsigned long long t = g.ones_before[tile] + ex_c;                                  // rank of my first sample
   const long long lb = g.last_before[tile];
-  long long prev = ex_last >= 0 ? (long long)tile * G2_TILE_BITS + ex_last : lb;       // the one before my stretch, -1 if none
+  long long prev = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;       // the one before my stretch, -1 if none
   const long long tb = (long long)(w0 * 32);
   unsigned long long mybits = 0;
   if (c) {
     bool first = true, fast = false;
     uint32_t kc = 0, lpv = 0, fastbits = 0;
 #pragma unroll
-    for (int i = 0; i < G2_WPT; ++i) {
+    for (int i = 0; i < WPT; ++i) {
       uint32_t b = v[i];
       while (b) {
         const int p = __clz(b);
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
         ++t;
         if (first) {
           first = false;
-          fast = g2_k_stable(t, (unsigned long long)(prev + 1), G2_WPT * 32, &kc);
+          fast = g2_k_stable(t, (unsigned long long)(prev + 1), WPT * 32, &kc);
           lpv = lp;
         }
       }
@@ -303,15 +308,16 @@ struct G2Out {
   }
 };
 
+template <int WPT>
 __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
   __shared__ int s_w[16];
   __shared__ unsigned long long s_a[8];
-  __shared__ uint32_t s_out[G2_STAGE_WORDS];
+  __shared__ uint32_t s_out[G2_STAGE_WORDS(WPT)];
   uint32_t tile;
   const G2Seg& g = g2_segment(P, &tile);
   if (g.info[4]) return;                                                 // the code does not fit: nothing is written
-  uint32_t v[G2_WPT];
-  const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS + threadIdx.x * G2_WPT;
+  uint32_t v[WPT];
+  const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS(WPT) + threadIdx.x * WPT;
   g2_load(g, w0, v);
   uint32_t c, ex_c, tot_c;
   int last, ex_last, tot_last;
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
   g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
   unsigned long long t = g.ones_before[tile] + ex_c;
   const long long lb = g.last_before[tile];
-  long long prev = ex_last >= 0 ? (long long)tile * G2_TILE_BITS + ex_last : lb;
+  long long prev = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;
   const long long tb = (long long)(w0 * 32);
   const unsigned long long mybits = g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x];
   unsigned long long tot;
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
   const unsigned long long o0 = g.bits_before[tile];
   const unsigned long long base = o0 & ~31ull;                           // stream bit position of s_out[0]
   const unsigned long long span_words = ((o0 - base) + tot + 31) >> 5;
-  const bool staged = span_words <= G2_STAGE_WORDS;                      // uniform over the CTA
+  const bool staged = span_words <= G2_STAGE_WORDS(WPT);                      // uniform over the CTA
   const unsigned long long cmask = (unsigned long long)g.chunk - 1;
   const int clog = 31 - __clz(g.chunk);
   if (staged) {
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
       bool first = true, fast = false;
       uint32_t kc = 0, lpv = 0;
 #pragma unroll
-      for (int i = 0; i < G2_WPT; ++i) {
+      for (int i = 0; i < WPT; ++i) {
         uint32_t b = v[i];
         while (b) {
           const int p = __clz(b);
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
             prev = tb + lp;
             if (first) {
               first = false;
-              fast = g2_k_stable(t, (unsigned long long)(prev + 1), G2_WPT * 32, &kc);
+              fast = g2_k_stable(t, (unsigned long long)(prev + 1), WPT * 32, &kc);
             }
           }
         }
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
     // a tile whose code is far longer than its input (long unary parts): codewords go straight to global memory
     unsigned long long o = o0 + ex;
 #pragma unroll
-    for (int i = 0; i < G2_WPT; ++i) {
+    for (int i = 0; i < WPT; ++i) {
       uint32_t b = v[i];
       while (b) {
         const int p = __clz(b);
@@ -432,16 +438,18 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
   memset(&P, 0, sizeof(P));
   P.nseg = (uint32_t)nmat;
   // scratch: per stream, the compacted copy (only when cols is not a multiple of 32) and the per-tile arrays
-  uint64_t words_compact = 0, ntiles_total = 0;
+  uint64_t words_compact = 0, ntiles_total = 0, words_total = 0;
   uint64_t Ts[G2_MAXSEG], nts[G2_MAXSEG];
   for (int i = 0; i < nmat; ++i) {
     const uint64_t N = mats[i]->rows * mats[i]->cols;
     if (N == 0) return BIC_ERR_INVALID;
     Ts[i] = div_up_u64(N, 32);
-    nts[i] = div_up_u64(Ts[i], G2_TILE_WORDS);
+    words_total += Ts[i];
     if (mats[i]->cols & 31) words_compact += (Ts[i] + 7) & ~(uint64_t)3;
-    ntiles_total += nts[i];
   }
+  // wide tiles only when they still give every SM a few waves of CTAs
+  const int WPT = (words_total / G2_TILE_WORDS(16) >= (uint64_t)c->sm_count * 16) ? 16 : 4;
+  for (int i = 0; i < nmat; ++i) { nts[i] = div_up_u64(Ts[i], (uint64_t)G2_TILE_WORDS(WPT)); ntiles_total += nts[i]; }
   if (ntiles_total >= (1ull << 31)) return bic_fail(c, BIC_ERR_UNSUPPORTED, "golomb: too many tiles for one launch");
   if (words_compact) BIC_TRY(bic_scratch_reserve(c, &c->work[4], words_compact * 4 + 64));
   const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8;   // last, ones_before, last_before, bits, bits_before | ones (padded to 8) | tbits
@@ -489,10 +497,12 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
     outs[i]->info.bitcount = outs[i]->info.nsamples = outs[i]->info.nchunks = 0;
   }
   BIC_PROF(c, KID_GOL_TILE_COUNTS);
-  k_g2_count<<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  if (WPT == 16) k_g2_count<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  else k_g2_count<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   BIC_LAUNCH_CHECK(c);
   BIC_PROF(c, KID_GOL_LENGTHS);
-  k_g2_lengths<<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  if (WPT == 16) k_g2_lengths<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  else k_g2_lengths<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   BIC_LAUNCH_CHECK(c);
   uint64_t maxN = 0;
   for (int i = 0; i < nmat; ++i) maxN = P.s[i].N > maxN ? P.s[i].N : maxN;
@@ -500,7 +510,8 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
   k_g2_clear<<<bic_grid_for(c, div_up_u64(maxN, 32) + 4, 256, 4), 256, 0, c->stream>>>(P);
   BIC_LAUNCH_CHECK(c);
   BIC_PROF(c, KID_GOL_SCATTER);
-  k_g2_scatter<<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  if (WPT == 16) k_g2_scatter<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  else k_g2_scatter<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }

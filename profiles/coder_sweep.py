@@ -48,6 +48,13 @@ for rho in (0.001, 0.003, 0.01, 0.03, 0.1, 0.2, 0.5):
         ctx.golomb_decode(s, M2)
     ms_dec = ctx.timer_stop() / reps
     ok = bool(np.array_equal(M2.download_pbm(), host))
+    # per-kernel device times of one more encode + decode (event pairs around every launch)
+    ctx.prof_reset()
+    ctx.prof_enable(True)
+    ctx.golomb_encode(M, out=s)
+    ctx.golomb_decode(s, M2)
+    ctx.prof_enable(False)
+    kernels = {k: round(v[1], 4) for k, v in ctx.prof_stats().items()}
     info = s.info
     # serial reference coder on a 2^26-bit prefix (single core, bit counting only)
     sample_rows = (1 << 26) // cols
@@ -59,7 +66,7 @@ for rho in (0.001, 0.003, 0.01, 0.03, 0.1, 0.2, 0.5):
     rec = {"rho": rho, "input_bits": N, "bitcount": int(info.bitcount), "ratio": info.bitcount / N, "nsamples": int(info.nsamples),
            "encode_ms": ms_enc, "decode_ms": ms_dec, "encode_GBps_in": gb / (ms_enc / 1e3), "decode_GBps_out": gb / (ms_dec / 1e3),
            "encode_GBps_in_plus_out": (gb + info.bitcount / 8e9) / (ms_enc / 1e3), "roundtrip_ok": ok,
-           "ref_serial_GBps_in": ((1 << 26) / 8 / 1e9) / t_ref if ref else None, "ref_sample_bits": 1 << 26}
+           "ref_serial_GBps_in": ((1 << 26) / 8 / 1e9) / t_ref if ref else None, "ref_sample_bits": 1 << 26, "kernel_ms": kernels}
     out.append(rec)
     print(json.dumps(rec), flush=True)
     for x in (M, M2, s):
