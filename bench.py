@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--e2e-planes", action="store_true", help="e2e from 16 host P4 planes (bic_encode_raster) instead of the 16-bit P5 payload")
     ap.add_argument("--sharded", action="store_true", help="also time the row-sharded (NCCL) fit at N=1")
     ap.add_argument("--streams", type=int, default=24, help="encoder slots (CUDA streams) per GPU")
+    ap.add_argument("--sharded-streams", type=int, default=8, help="row-sharded fit: planes in flight per rank (one communicator + host thread each)")
+    ap.add_argument("--sharded-cluster", type=int, default=8, help="row-sharded fit: CTAs per cluster of the chain kernel (it waits for the peers inside)")
     ap.add_argument("--pool", action="store_true", help="round-1 driver: one host thread per context instead of the single-thread pipeline")
     ap.add_argument("--first-batch", type=int, default=2, help="pipeline: iterations queued before the loop flag is first looked at")
     ap.add_argument("--next-batch", type=int, default=2, help="pipeline: iterations per later batch")
@@ -276,6 +278,10 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # kernels that wait for a peer GPU (NCCL's, the chain's exchange) must never sit behind another stream's kernel in a shared
+        # hardware queue: one connection per stream (32 is the maximum; the default is 8)
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -776,93 +782,163 @@ def main():
         "per_kernel": per_kernel,
     }
 
-    # ---- row-sharded fit (N > 1): the N bands are ONE image, one dictionary per plane over all ranks'
-    # patches, statistics combined by NCCL inside the library (csrc/dist.cu). One stream, planes in
-    # sequence; A and E shards are Golomb coded as exact substrings of the single global streams.
+    # ---- row-sharded fit (N > 1): the N bands are ONE image, one dictionary per plane over all ranks' patches (the north
+    # star's multi-GPU path). Integer statistics are combined inside the library (csrc/dist.cu): NCCL allreduce of [H | U |
+    # bucket sizes | changed rows] once per bsvd iteration, the corrections of every atom that changes exchanged over NVLink peer
+    # memory from inside the cluster-chain kernel, seam-exact sharded Golomb coding. `sharded_streams` planes are in flight per
+    # rank (one context + one communicator + one host thread each; planes are dealt to them in the same order on every rank).
     sharded = None
     if world > 1 or args.sharded:
-        try:
-            uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
-            if dist is not None:
-                dist.broadcast(uid, 0)
-            w0 = workers[0]
-            comm = w0.ctx.comm_create(rank, world, uid.cpu().numpy())
-            sh_iters = [0] * P
-            sh_rec = {}
+        TS = max(1, min(args.sharded_streams, P))
 
-            def fit_sharded(b, record=False):
-                c = w0.ctx
-                c._ck(L.bic_extract_patches(c.h, rasters[b].h, W, w0.X.h))
-                rng = c.rand48(SEED)
-                c._ck(L.bic_dist_initialize_model_neighbor(c.h, comm, w0.X.h, w0.D.h, w0.A.h, C.byref(rng)))
-                it = C.c_uint64(0)
-                c._ck(L.bic_dist_learn_model_traditional(c.h, comm, w0.X.h, w0.E.h, w0.D.h, w0.A.h, C.byref(it), None, 0))
-                sh_iters[b] = int(it.value)
-                # D is replicated (every rank codes the same stream); A and E are row-sharded: each rank writes its
-                # rows' codewords as the exact substring of the single global stream (bic_dist_golomb_encode)
-                c._ck(L.bic_golomb_encode(c.h, w0.D.h, 256, w0.streams[0].h))
-                shi = [bic.ShardInfo(), bic.ShardInfo()]
-                for M, s, si in zip((w0.A, w0.E), w0.streams[1:], shi):
-                    c._ck(L.bic_dist_golomb_encode(c.h, comm, M.h, 256, s.h, C.byref(si)))
-                if record:
-                    sh_rec[b] = {"D": w0.D.download(), "iters": int(it.value),
-                                 "bits": [int(w0.streams[0].info.bitcount), int(shi[0].global_bitcount), int(shi[1].global_bitcount)]}
-
-            for b in range(P):
-                fit_sharded(b, record=True)
-            barrier()
-            # ---- correctness of the sharded path, in the bench itself: the dictionary, the iteration count and the GLOBAL Golomb
-            # bit counts of D, A, E must equal the single-GPU fit of the concatenated rows (rank 0 gathers the N bands)
-            sh_checked = 0
-            for b in range(P):
-                band = torch.from_numpy(host_planes[b]).to(dev)
+        class ShWorker:
+            def __init__(self, j):
+                self.j = j
+                self.ctx = bic.Context(local_rank)
+                c = self.ctx
+                c.set_option("wait_mode", args.wait_mode)
+                c.set_option("dict_algo", args.dict_algo)
+                c.set_option("chain_cluster", args.sharded_cluster)
+                uid = torch.from_numpy(c.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
                 if dist is not None:
-                    bands = [torch.empty_like(band) for _ in range(world)]
-                    dist.all_gather(bands, band)
-                else:
-                    bands = [band]
-                if rank == 0:
-                    whole = torch.cat(bands, dim=0).cpu().numpy()
-                    c = ctx
-                    Iall = c.matrix(world * rows, cols)
-                    Iall.upload_pbm(whole)
-                    Xall = c.extract_patches(Iall, W)
-                    Dall, Aall, Eall = c.matrix(K, m), c.matrix(Xall.rows, K), c.matrix(Xall.rows, m)
-                    c.initialize_model_neighbor(Xall, Dall, Aall, c.rand48(SEED))
-                    it1, _ = c.learn_model_traditional(Xall, Eall, Dall, Aall)
-                    bits1 = [c.golomb_bitcount(M)[0] for M in (Dall, Aall, Eall)]
-                    rec = sh_rec[b]
-                    ok = it1 == rec["iters"] and bits1 == rec["bits"] and np.array_equal(Dall.download(), rec["D"])
-                    for M in (Iall, Xall, Dall, Aall, Eall):
-                        M.destroy()
-                    if not ok:
-                        raise SystemExit(f"PARITY FAILURE: row-sharded fit of bitplane {b} over {world} rank(s) differs from the single-GPU fit of the "
-                                         f"concatenated rows (iterations {rec['iters']} vs {it1}, Golomb bits {rec['bits']} vs {bits1})")
-                    sh_checked += 1
-                del band, bands
-            barrier()
-            coll0 = w0.ctx.comm_collectives(comm)
-            w0.ctx.timer_start()
-            for _ in range(args.steps):
-                for b in range(P):
-                    fit_sharded(b)
-            ms_sh = max_over_ranks(w0.ctx.timer_stop() / args.steps)
-            barrier()
-            sharded = {"value": world * px_step / (ms_sh / 1e3), "unit": UNIT, "ms_per_step": ms_sh,
-                       "collectives_per_step": (w0.ctx.comm_collectives(comm) - coll0) / args.steps,
-                       "iterations_per_plane": sh_iters,
-                       "parity_checked": bool(sh_checked == P) if rank == 0 else None, "parity_planes": sh_checked,
-                       "parity_how": "D, the iteration count and the global Golomb bit counts of D, A, E of every plane equal the single-GPU "
-                                     "fit of the concatenated rows (run on rank 0 inside this bench)",
-                       "what": f"each plane is ONE {world * S}x{S} image whose patch rows are sharded over {world} rank(s); one "
-                               "dictionary per plane; one NCCL allreduce of atom statistics per iteration, the corrections of an atom that changes pushed into every "
-                               "rank's histograms by the fix kernel over NVLink peer memory (BIC_DIST_FUSED=0: one more allreduce per changed atom); seam-exact sharded Golomb coding; "
-                               "one stream, planes in sequence"}
-            w0.ctx.comm_destroy(comm)
-        except SystemExit:
-            raise
-        except Exception as ex:  # the extra measurement must not void the main numbers
-            sharded = {"value": None, "unit": UNIT, "error": f"{type(ex).__name__}: {ex}"}
+                    dist.broadcast(uid, 0)
+                self.comm = c.comm_create(rank, world, uid.cpu().numpy())
+                self.R = c.matrix(rows, cols)
+                self.X, self.E = c.matrix(n, m), c.matrix(n, m)
+                self.D, self.A = c.matrix(K, m), c.matrix(n, K)
+                self.streams = [c.stream() for _ in range(3)]
+                self.out = c.pinned(2 * plane_bytes + (1 << 20))
+                self.planes = [b for b in range(P) if b % TS == j]
+
+        shw = [ShWorker(j) for j in range(TS)]
+        sh_iters = [0] * P
+        sh_rec = {}
+        sh_d2h = [0] * P
+
+        def fit_sharded(w, b, record=False, e2e=False):
+            c = w.ctx
+            src = rasters[b]
+            if e2e:   # this rank's band of the plane from pinned host memory
+                c._ck(L.bic_mat_upload_pbm(c.h, w.R.h, host_planes[b].ctypes.data_as(C.POINTER(C.c_uint8))))
+                src = w.R
+            c._ck(L.bic_extract_patches(c.h, src.h, W, w.X.h))
+            rng = c.rand48(SEED)
+            c._ck(L.bic_dist_initialize_model_neighbor(c.h, w.comm, w.X.h, w.D.h, w.A.h, C.byref(rng)))
+            it = C.c_uint64(0)
+            c._ck(L.bic_dist_learn_model_traditional(c.h, w.comm, w.X.h, w.E.h, w.D.h, w.A.h, C.byref(it), None, 0))
+            sh_iters[b] = int(it.value)
+            # D is replicated (every rank codes the same stream); A and E are row-sharded: each rank writes its
+            # rows' codewords as the exact substring of the single global stream (bic_dist_golomb_encode)
+            c._ck(L.bic_golomb_encode(c.h, w.D.h, 256, w.streams[0].h))
+            shi = [bic.ShardInfo(), bic.ShardInfo()]
+            for M, s_, si in zip((w.A, w.E), w.streams[1:], shi):
+                c._ck(L.bic_dist_golomb_encode(c.h, w.comm, M.h, 256, s_.h, C.byref(si)))
+            if e2e:   # the shard's streams (and, on rank 0, the dictionary's) back to pinned host memory
+                off = 0
+                for s_ in (w.streams if rank == 0 else w.streams[1:]):
+                    si = s_.info
+                    nb, ni = (int(si.bitcount) + 7) // 8, int(si.nchunks)
+                    nbp = (nb + 7) & ~7
+                    idx = w.out[off + nbp: off + nbp + ni * 16].view(np.uint64)
+                    c._ck(L.bic_stream_download(c.h, s_.h, w.out[off:].ctypes.data_as(C.POINTER(C.c_uint8)), nb,
+                                                idx.ctypes.data_as(C.POINTER(C.c_uint64)), ni))
+                    off += nbp + ni * 16
+                sh_d2h[b] = off
+            if record:
+                sh_rec[b] = {"D": w.D.download(), "iters": int(it.value),
+                             "bits": [int(w.streams[0].info.bitcount), int(shi[0].global_bitcount), int(shi[1].global_bitcount)]}
+
+        def sh_steps(nsteps, record=False, e2e=False, one_at_a_time=False):
+            errs = []
+
+            def loop(w):
+                try:
+                    for _ in range(nsteps):
+                        for b in w.planes:
+                            fit_sharded(w, b, record, e2e)
+                except BaseException as ex:  # noqa: BLE001
+                    errs.append(ex)
+
+            ctx.timer_start()
+            for w in shw:
+                w.ctx.wait_for(ctx)
+            if one_at_a_time:   # first use: scratch areas and peer windows are allocated (device-wide synchronisations) -- one
+                for w in shw:   # communicator at a time, every rank in the same order
+                    loop(w)
+                    if dist is not None:
+                        dist.barrier()
+            else:
+                ths = [threading.Thread(target=loop, args=(w,)) for w in shw]
+                for t in ths:
+                    t.start()
+                for t in ths:
+                    t.join()
+            for w in shw:
+                ctx.wait_for(w.ctx)
+            ms = ctx.timer_stop()
+            if errs:
+                raise errs[0]
+            return ms
+
+        sh_steps(1, record=True, one_at_a_time=True)
+        barrier()
+        # ---- correctness of the sharded path, in the bench itself: the dictionary, the iteration count and the GLOBAL Golomb
+        # bit counts of D, A, E must equal the single-GPU fit of the concatenated rows (rank 0 gathers the N bands)
+        sh_checked = 0
+        for b in range(P):
+            band = torch.from_numpy(host_planes[b]).to(dev)
+            if dist is not None:
+                bands = [torch.empty_like(band) for _ in range(world)]
+                dist.all_gather(bands, band)
+            else:
+                bands = [band]
+            if rank == 0:
+                whole = torch.cat(bands, dim=0).cpu().numpy()
+                c = ctx
+                Iall = c.matrix(world * rows, cols)
+                Iall.upload_pbm(whole)
+                Xall = c.extract_patches(Iall, W)
+                Dall, Aall, Eall = c.matrix(K, m), c.matrix(Xall.rows, K), c.matrix(Xall.rows, m)
+                c.initialize_model_neighbor(Xall, Dall, Aall, c.rand48(SEED))
+                it1, _ = c.learn_model_traditional(Xall, Eall, Dall, Aall)
+                bits1 = [c.golomb_bitcount(M)[0] for M in (Dall, Aall, Eall)]
+                rec = sh_rec[b]
+                ok = it1 == rec["iters"] and bits1 == rec["bits"] and np.array_equal(Dall.download(), rec["D"])
+                for M in (Iall, Xall, Dall, Aall, Eall):
+                    M.destroy()
+                if not ok:
+                    raise SystemExit(f"PARITY FAILURE: row-sharded fit of bitplane {b} over {world} rank(s) differs from the single-GPU fit of the "
+                                     f"concatenated rows (iterations {rec['iters']} vs {it1}, Golomb bits {rec['bits']} vs {bits1})")
+                sh_checked += 1
+            del band, bands
+        barrier()
+        sh_steps(max(args.warmup, 3))
+        barrier()
+        coll0 = sum(w.ctx.comm_collectives(w.comm) for w in shw)
+        sh_launch0 = sum(w.ctx.launches for w in shw)
+        ms_sh = max_over_ranks(sh_steps(args.steps) / args.steps)
+        sh_launches = sum(w.ctx.launches for w in shw) - sh_launch0
+        coll1 = sum(w.ctx.comm_collectives(w.comm) for w in shw)
+        barrier()
+        sh_steps(1, e2e=True)
+        barrier()
+        ms_sh_e2e = max_over_ranks(sh_steps(args.steps, e2e=True) / args.steps)
+        barrier()
+        sharded = {"value": world * px_step / (ms_sh / 1e3), "unit": UNIT, "ms_per_step": ms_sh,
+                   "e2e": {"value": world * px_step / (ms_sh_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_sh_e2e,
+                           "h2d_bytes_per_step": P * plane_bytes, "d2h_bytes_per_step": int(sum(sh_d2h)),
+                           "path": "each rank: its band of every plane from pinned host memory -> sharded fit -> its shard of the A and E streams "
+                                   "(rank 0: D's too) back to pinned host memory"},
+                   "collectives_per_step": (coll1 - coll0) / args.steps, "gpu_launches": int(sh_launches),
+                   "iterations_per_plane": sh_iters, "planes_in_flight_per_rank": TS,
+                   "parity_checked": bool(sh_checked == P) if rank == 0 else None, "parity_planes": sh_checked,
+                   "parity_how": "D, the iteration count and the global Golomb bit counts of D, A, E of every plane equal the single-GPU "
+                                 "fit of the concatenated rows (run on rank 0 inside this bench)",
+                   "what": f"each plane is ONE {world * S}x{S} image whose patch rows are sharded over {world} rank(s); one dictionary per plane; one NCCL "
+                           "allreduce of the atom statistics per bsvd iteration; the corrections of every atom that changes are exchanged over NVLink peer "
+                           "memory inside the cluster-chain kernel; seam-exact sharded Golomb coding"}
+        for w in shw:
+            w.ctx.comm_destroy(w.comm)
 
     # ---- CPU baseline (rank 0, N == 1): the reference's own code on a bounded crop
     cpu = None
@@ -910,6 +986,25 @@ def main():
         }
         if sharded is not None:
             line["row_sharded"] = sharded
+        if world > 1 and sharded is not None and sharded.get("value"):
+            # N > 1: the headline is the north star's multi-GPU path -- ONE dictionary per plane over the patch rows of all ranks,
+            # statistics allreduced once per bsvd iteration -- not N independent replicas (those stay below as "replicas")
+            line["replicas"] = {"value": line["value"], "unit": UNIT, "ms_per_step": line["ms_per_step"], "e2e": line["e2e"],
+                                "gpu_launches": line["gpu_launches"],
+                                "what": "every rank encodes its own 16-plane image with its own dictionaries: no data-path collective"}
+            line["value"] = sharded["value"]
+            line["ms_per_step"] = sharded["ms_per_step"]
+            line["e2e"] = sharded["e2e"]
+            line["gpu_launches"] = sharded["gpu_launches"]
+            line["config"]["workload"] = (workload_name(args) + f"; the {world} ranks' {S}x{S} bands are ONE {world * S}x{S} image per plane: patch rows sharded "
+                                          "over the ranks, one dictionary per plane")
+            line["config"]["parallelism"] = (f"{world} ranks, patch rows sharded, D replicated; NCCL allreduce of [H | U | bucket sizes | changed rows] once per bsvd "
+                                             f"iteration, per-changed-atom corrections exchanged over NVLink peer memory inside the chain kernel; "
+                                             f"{sharded['planes_in_flight_per_rank']} planes in flight per rank")
+            line["config"]["host_threads_per_rank"] = sharded["planes_in_flight_per_rank"]
+            line["parity_checked"] = bool(sharded.get("parity_checked"))
+            line["parity_planes"] = sharded.get("parity_planes", 0)
+            line["parity_how"] = sharded.get("parity_how")
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -178,6 +178,26 @@ struct XPeers {
   uint64_t h_off = 0;              // word offset of the histograms H inside a window
 };
 
+// Row-sharded cluster chain (dict3.cu + dist.cu): the corrections of an atom that changes are exchanged between the ranks from
+// inside the chain kernel. Window words used (header, < XWIN_DATA): [XWIN_EPOCH2] this rank's exchange counter (local),
+// [XWIN_FLAGS2 + r] the last exchange rank r has pushed into this window. The exchange area holds 2 (parity) x nranks vectors of
+// p * hs counters at word offset xoff of every window.
+#define XWIN_EPOCH2 95
+#define XWIN_FLAGS2 96
+struct ChainDist {
+  uint32_t* const* win = nullptr;  // [nranks] every rank's window as mapped on this device
+  uint32_t nranks = 1, rank = 0;
+  uint64_t xoff = 0;
+};
+// what the sharded driver plugs into the update: `reduce` sums buf[0 .. words) over the ranks (it is called once, after the
+// local histograms, usage counts and bucket sizes are complete and `extra` -- 4 words at the end of buf -- may be filled in)
+struct V3Hook {
+  bic_status (*reduce)(void* user, bic_ctx* c, uint32_t* buf, size_t words, uint32_t* extra) = nullptr;
+  void* user = nullptr;
+  ChainDist x;
+  size_t (*window_words)(void* user, size_t need_words, uint32_t** base) = nullptr;  // reserve the peer window; returns words available
+};
+
 // scratch layout of one dictionary update (dict2.cu), shared with the row-sharded driver (dist.cu)
 struct DictWork {
   uint64_t n, p, wpr, hs, wprN;

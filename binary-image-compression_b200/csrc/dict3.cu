@@ -44,6 +44,8 @@ struct ChainParams {
   uint32_t bucket_cap;      // capacity of `bucket`; when the buckets do not fit the chain scans the list instead
   uint64_t m;
   const uint32_t* skip;     // non-null and nonzero: the learner's loop already ended on the device, do nothing
+  const uint32_t* gcount;   // p: bucket sizes summed over all ranks (== hcount on one GPU): decides whether a change needs an exchange
+  ChainDist x;              // nranks > 1: rows are sharded over several GPUs, corrections are exchanged over peer memory
 };
 
 // vote of atom k from the histograms in shared memory (src/bsvd.cpp:499-507); one warp. Returns whether
@@ -254,6 +256,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
   for (uint32_t i = tid; i < nH; i += CHAIN_THREADS) sH[i] = __ldcg(P.H + i);
   for (uint32_t i = tid; i < P.p * P.wprE; i += CHAIN_THREADS) { sDelta[i] = 0; sD[i] = __ldcg(P.D + i); }
   for (uint32_t i = tid; i < P.p; i += CHAIN_THREADS) { sU[i] = __ldcg(P.U + i); sCnt[i] = __ldcg(P.hcount + i); }
+  const bool multi = P.x.nranks > 1;
+  uint32_t* const my_win = multi ? P.x.win[P.x.rank] : nullptr;
+  const uint32_t epoch0 = multi ? __ldcg(my_win + XWIN_EPOCH2) : 0u;   // exchanges done so far (the same number on every rank)
   for (uint32_t i = tid; i < P.wprA; i += CHAIN_THREADS) sCh[i] = 0;
   for (uint32_t i = tid; i < 3 * slice; i += CHAIN_THREADS) sAcc[i] = 0;
   const uint32_t L = __ldcg(P.count);
@@ -278,9 +283,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
     const uint32_t k = sFirst;
     if (k >= P.p) break;
     if (warp == 0) chain_decide(sH, sU, sD, k, P, sDelta + k * P.wprE);
-    if (bucketed && sCnt[k] == 0) {
-      // no row uses atom k together with a later atom: the change reaches no other histogram (same decision in every
-      // CTA, so nobody waits at a barrier)
+    if (__ldcg(P.gcount + k) == 0) {
+      // no row (on any rank) uses atom k together with a later atom: the change reaches no other histogram (same decision in
+      // every CTA and on every rank, so nobody waits at a barrier)
       __syncthreads();                       // sDelta[k] is complete before anyone moves on
       if (tid == 0) sCh[k >> 5] |= 0x80000000u >> (k & 31);
       nchanged++;
@@ -343,9 +348,54 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
       if (v) atomicAdd(cluster.map_shared_rank(acc, i % csize) + i / csize, v);
     }
     cluster.sync();
-    for (uint32_t i = (k + 1) * P.hs + tid; i < nH; i += CHAIN_THREADS) {
-      const uint32_t j = i % P.hs;
-      if ((sDelta[k * P.wprE + (j >> 5)] >> (31 - (j & 31))) & 1u) sH[i] += cluster.map_shared_rank(acc, i % csize)[i / csize];
+    if (!multi) {
+      for (uint32_t i = (k + 1) * P.hs + tid; i < nH; i += CHAIN_THREADS) {
+        const uint32_t j = i % P.hs;
+        if ((sDelta[k * P.wprE + (j >> 5)] >> (31 - (j & 31))) & 1u) sH[i] += cluster.map_shared_rank(acc, i % csize)[i / csize];
+      }
+    } else {
+      // Several GPUs: the sums above are this rank's rows only. CTA 0 writes them into every peer's window (a contiguous vector
+      // per source rank, two areas alternating with the exchange number), publishes "rank r has pushed exchange e" and waits
+      // for the same from every peer; the other CTAs wait at the hardware cluster barrier. Then everybody adds the peers' vectors.
+      // A rank that runs ahead can be at most one exchange further (it needs this rank's flag to get past the next one), and
+      // that one goes to the other area.
+      const uint32_t e = epoch0 + nx + 1;
+      const uint64_t area = P.x.xoff + (uint64_t)(e & 1u) * P.x.nranks * nH;
+      for (uint32_t i = (k + 1) * P.hs + tid; i < nH; i += CHAIN_THREADS) {
+        const uint32_t j = i % P.hs;
+        const uint32_t tot = cluster.map_shared_rank(acc, i % csize)[i / csize];
+        if ((sDelta[k * P.wprE + (j >> 5)] >> (31 - (j & 31))) & 1u) sH[i] += tot;
+        if (rank == 0)
+          for (uint32_t r = 0; r < P.x.nranks; ++r)
+            if (r != P.x.rank) P.x.win[r][area + (uint64_t)P.x.rank * nH + i] = tot;
+      }
+      if (rank == 0) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+          for (uint32_t r = 0; r < P.x.nranks; ++r)
+            if (r != P.x.rank) *(volatile uint32_t*)(P.x.win[r] + XWIN_FLAGS2 + P.x.rank) = e;
+          for (uint32_t r = 0; r < P.x.nranks; ++r) {
+            if (r == P.x.rank) continue;
+            uint32_t spins = 0;
+            while ((int32_t)(*(volatile uint32_t*)(my_win + XWIN_FLAGS2 + r) - e) < 0) {
+              __nanosleep(100);
+              if (++spins > (1u << 27)) __trap();  // a peer that never arrives ends in an error, not a hang
+            }
+          }
+          __threadfence_system();
+        }
+        __syncthreads();
+      }
+      cluster.sync();
+      for (uint32_t i = (k + 1) * P.hs + tid; i < nH; i += CHAIN_THREADS) {
+        const uint32_t j = i % P.hs;
+        if (!((sDelta[k * P.wprE + (j >> 5)] >> (31 - (j & 31))) & 1u)) continue;
+        uint32_t add = 0;
+        for (uint32_t r = 0; r < P.x.nranks; ++r)
+          if (r != P.x.rank) add += __ldcg(my_win + area + (uint64_t)r * nH + i);
+        sH[i] += add;
+      }
     }
     if (tid == 0) sCh[kw] |= kbit;
     nchanged++;
@@ -354,6 +404,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
     // the __syncthreads at the top of the loop orders these writes before the next decisions
   }
   cluster.sync();                          // no CTA leaves while another may still access its shared memory
+  if (multi && rank == 0 && tid == 0) my_win[XWIN_EPOCH2] = epoch0 + nx;
   if (rank == 0) {
     for (uint32_t i = tid; i < P.p * P.wprE; i += CHAIN_THREADS) {
       const uint32_t d = sDelta[i];
@@ -488,23 +539,49 @@ bool bic_dict_chain_eligible(bic_ctx* c, uint64_t n, uint64_t p, uint64_t wprE) 
          smem + 1024 <= c->smem_optin && smem <= 200 * 1024;
 }
 
-bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
+__global__ void k_copy_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t n, const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// hook == nullptr: one GPU. Otherwise the rows are one rank's shard: hook->reduce sums [H | U | bucket sizes | extra] over the
+// ranks between the histogram pass and the chain, and the chain exchanges the corrections of every atom that changes through
+// the peer windows in hook->x.
+bic_status bic_k_update_dictionary_v3x(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed, V3Hook* hook) {
   BIC_RANGE("bic:update_dictionary_steepest(cluster chain)");
   const uint64_t n = E->rows, p = D->rows, wprE = E->wpr, wprA = A->wpr, hs = wprE * 32;
-  if (n == 0 || p == 0 || E->cols == 0) return BIC_OK;
-  // work[3]: H (p*hs) | U (p) | count (4) | hcount (wprA*32) | cursor (wprA*32) | delta (p*wprE) | chmask (wprA + 1)
+  if (p == 0 || E->cols == 0) return BIC_OK;
+  if (n == 0 && !hook) return BIC_OK;
+  // global part (summed over the ranks when sharded): H (p*hs) | U (p) | gcount (wprA*32) | extra (4)
+  // local part: count (4) | hcount (wprA*32) | cursor (wprA*32) | delta (p*wprE) | chmask (wprA + 1)
   // work[2]: listA (n*wprA + 4) | listE (n*wprE) | bucket (bucket_cap)
-  const size_t zero_words = (size_t)(p * hs + p + 4 + 2 * wprA * 32);
-  const size_t ctl_words = zero_words + (size_t)(p * wprE + wprA + 1);
-  BIC_TRY(bic_scratch_reserve(c, &c->work[3], ctl_words * 4 + 64));
+  const size_t glob_words = (size_t)(p * hs + p + wprA * 32 + 4);
+  const size_t zero_local = (size_t)(4 + 2 * wprA * 32);
+  const size_t local_words = zero_local + (size_t)(p * wprE + wprA + 1);
+  uint32_t* G = nullptr;
+  if (hook && hook->window_words) {
+    // sharded with peer windows: the global part lives in this rank's window (so a collective of the driver's choice can work
+    // in place), followed by the chain's exchange area
+    const size_t xwords = (size_t)2 * hook->x.nranks * p * hs;
+    uint32_t* base = nullptr;
+    const size_t got = hook->window_words(hook->user, glob_words + 64 + xwords, &base);
+    if (got < glob_words + 64 + xwords || !base) return bic_fail(c, BIC_ERR_NOMEM, "update_dictionary: peer window too small");
+    G = base;
+    hook->x.xoff = (uint64_t)(base - hook->x.win[hook->x.rank]) + ((glob_words + 63) & ~(size_t)63);
+  }
+  BIC_TRY(bic_scratch_reserve(c, &c->work[3], (glob_words + local_words) * 4 + 64));
+  if (!G) G = (uint32_t*)c->work[3].p;
+  uint32_t* Lc = (uint32_t*)c->work[3].p + glob_words;
   const size_t la_words = ((size_t)n * wprA + 7) & ~(size_t)3;  // listE stays 16-byte aligned
   // a row with s atoms sits in s - 1 buckets; 2 entries per row covers sparse codes, denser ones fall back to the scan
   uint64_t bucket_cap = c->chain_bucket_cap >= 0 ? (uint64_t)c->chain_bucket_cap : 2 * n;
   if (bucket_cap > 0xFFFFFFF0ull) bucket_cap = 0xFFFFFFF0ull;
   BIC_TRY(bic_scratch_reserve(c, &c->work[2], (la_words + (size_t)n * wprE + bucket_cap) * 4 + 64));
-  uint32_t* H = (uint32_t*)c->work[3].p;
+  uint32_t* H = G;
   uint32_t* U = H + p * hs;
-  uint32_t* count = U + p;
+  uint32_t* gcount = U + p;
+  uint32_t* extra = gcount + wprA * 32;
+  uint32_t* count = Lc;
   uint32_t* hcount = count + 4;
   uint32_t* cursor = hcount + wprA * 32;
   uint32_t* delta = cursor + wprA * 32;
@@ -512,22 +589,32 @@ bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const 
   uint32_t* listA = (uint32_t*)c->work[2].p;
   uint32_t* listE = listA + la_words;
   uint32_t* bucket = listE + (size_t)n * wprE;
-  BIC_CUDA(c, cudaMemsetAsync(H, 0, zero_words * 4, c->stream));
+  BIC_CUDA(c, cudaMemsetAsync(G, 0, glob_words * 4, c->stream));
+  BIC_CUDA(c, cudaMemsetAsync(Lc, 0, zero_local * 4, c->stream));
   bool fused = false;
-  BIC_TRY(bic_k_dict_hist_compact(c, E, A, H, U, hs, listA, listE, count, hcount, &fused));
-  if (!fused) {
-    const int grid = bic_grid_for(c, n, 256, 8);
-    BIC_PROF(c, KID_DICT_COMPACT);
-    k_dict_compact<<<grid, 256, 0, c->stream>>>(E->d, A->d, listA, listE, count, n, (uint32_t)wprE, (uint32_t)wprA, c->loop_skip);
-    BIC_LAUNCH_CHECK(c);
+  if (n) {
+    BIC_TRY(bic_k_dict_hist_compact(c, E, A, H, U, hs, listA, listE, count, hcount, &fused));
+    if (!fused) {
+      const int grid = bic_grid_for(c, n, 256, 8);
+      BIC_PROF(c, KID_DICT_COMPACT);
+      k_dict_compact<<<grid, 256, 0, c->stream>>>(E->d, A->d, listA, listE, count, n, (uint32_t)wprE, (uint32_t)wprA, c->loop_skip);
+      BIC_LAUNCH_CHECK(c);
+    }
+    if (!fused) {  // the fused histogram pass counted the buckets as well
+      const int grid = bic_grid_for(c, n, 256, 2);
+      BIC_PROF(c, KID_DICT_BUCKET);
+      k_dict_bucket_count<<<grid, 256, (size_t)wprA * 32 * 4, c->stream>>>(listA, count, hcount, (uint32_t)wprA, (uint32_t)p, c->loop_skip);
+      BIC_LAUNCH_CHECK(c);
+    }
   }
-  if (!fused) {  // the fused histogram pass counted the buckets as well
-    const int grid = bic_grid_for(c, n, 256, 2);
-    BIC_PROF(c, KID_DICT_BUCKET);
-    k_dict_bucket_count<<<grid, 256, (size_t)wprA * 32 * 4, c->stream>>>(listA, count, hcount, (uint32_t)wprA, (uint32_t)p, c->loop_skip);
+  const uint32_t* gc = hcount;
+  if (hook) {
+    k_copy_u32<<<1, 256, 0, c->stream>>>(gcount, hcount, (uint32_t)(wprA * 32), c->loop_skip);
     BIC_LAUNCH_CHECK(c);
+    BIC_TRY(hook->reduce(hook->user, c, G, glob_words, extra));
+    gc = gcount;
   }
-  {
+  if (n) {
     const int grid2 = bic_grid_for(c, div_up_u64(n, FILL_CHUNK) * 256, 256, 4);
     BIC_PROF(c, KID_DICT_BUCKET);
     k_dict_bucket_fill<<<grid2, 256, (size_t)(p + 1 + 2 * wprA * 32) * 4, c->stream>>>(listA, count, hcount, cursor, bucket,
@@ -539,6 +626,8 @@ bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const 
   P.hcount = hcount; P.bucket = bucket; P.bucket_cap = (uint32_t)bucket_cap;
   P.changed = d_changed; P.p = (uint32_t)p; P.wprE = (uint32_t)wprE; P.wprA = (uint32_t)wprA; P.hs = (uint32_t)hs; P.m = E->cols;
   P.skip = c->loop_skip;
+  P.gcount = gc;
+  if (hook) P.x = hook->x;
   const unsigned csize = (unsigned)bic_chain_cluster_size(c);
   const size_t smem = (size_t)(p * hs + p * (hs + 1) + 2 * p * wprE + 3 * p + 1 + wprA + 3 * div_up_u64(p * hs, csize)) * 4;
   {
@@ -565,7 +654,7 @@ bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const 
   BIC_PROF(c, KID_DICT_CHAIN);
   BIC_CUDA(c, cudaLaunchKernelEx(&cfg, k_dict_chain, P));
   BIC_LAUNCH_CHECK(c);
-  {
+  if (n) {
     const int grid = bic_grid_for(c, n, 256, 8);
     BIC_PROF(c, KID_DICT_APPLY);
     k_dict_apply<<<grid, 256, (size_t)(p * wprE + wprA) * 4, c->stream>>>(E->d, A->d, delta, chmask, n, (uint32_t)wprE,
@@ -573,4 +662,8 @@ bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const 
     BIC_LAUNCH_CHECK(c);
   }
   return BIC_OK;
+}
+
+bic_status bic_k_update_dictionary_v3(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed) {
+  return bic_k_update_dictionary_v3x(c, E, D, A, d_changed, nullptr);
 }

@@ -336,6 +336,29 @@ __global__ void k_split_u64_limbs(const unsigned long long* __restrict__ in, uin
   limbs[2] = (uint32_t)(v >> 44);   // < 2^20
 }
 
+bic_status bic_k_update_dictionary_v3x(bic_ctx* c, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_changed, V3Hook* hook);
+bool bic_dict_chain_eligible(bic_ctx* c, uint64_t n, uint64_t p, uint64_t wprE);
+
+// the sharded driver's side of dict3.cu's hook
+struct ChainHookUser {
+  bic_comm* m;
+  unsigned long long* d_counts;
+};
+static bic_status chain_reduce(void* user, bic_ctx* c, uint32_t* buf, size_t words, uint32_t* extra) {
+  ChainHookUser* u = (ChainHookUser*)user;
+  // extra[0..2]: the 64-bit changed-rows count of the preceding coefficient update as three 22-bit limbs (see below)
+  k_split_u64_limbs<<<1, 1, 0, c->stream>>>(u->d_counts, extra);
+  BIC_LAUNCH_CHECK(c);
+  u->m->last_extra = extra;
+  return allreduce_u32(c, u->m, buf, words);
+}
+static size_t chain_window(void* user, size_t need_words, uint32_t** base) {
+  ChainHookUser* u = (ChainHookUser*)user;
+  (void)need_words;
+  *base = u->m->win ? u->m->win + XWIN_DATA : nullptr;
+  return u->m->win_words > XWIN_DATA ? u->m->win_words - XWIN_DATA : 0;
+}
+
 // ------------------------------------------------------------------ update_dictionary_steepest, sharded
 // d_counts[0] (changed rows of the preceding coefficient update, local) is summed over ranks in the same
 // allreduce as H and U; d_counts[1] receives the changed atoms (identical on every rank).
@@ -343,6 +366,31 @@ static bic_status dist_update_dictionary(bic_ctx* c, bic_comm* m, bic_mat* E, bi
                                          unsigned long long* d_counts) {
   BIC_RANGE("bic:dist:update_dictionary");
   if (D->rows == 0 || E->cols == 0) return BIC_OK;
+  // Where the histograms fit shared memory: the cluster chain (dict3.cu), one launch per update; the corrections of an atom
+  // that changes go from rank to rank inside the chain kernel (peer windows). The row count that decides eligibility is the
+  // largest shard's, so every rank takes the same path.
+  {
+    uint64_t maxn = E->rows;
+    for (uint64_t v : m->nrows) maxn = v > maxn ? v : maxn;
+    if (c->dict_algo == 2 && bic_dict_chain_eligible(c, maxn, D->rows, E->wpr)) {
+      const size_t hwords = (size_t)D->rows * E->wpr * 32;
+      const size_t glob = hwords + D->rows + A->wpr * 32 + 4;
+      if (m->nranks > 1) BIC_TRY(window_reserve(c, m, glob + 128 + 2 * (size_t)m->nranks * hwords));
+      if (m->nranks == 1 || m->fused == 1) {
+        ChainHookUser u{m, d_counts};
+        V3Hook hook;
+        hook.reduce = chain_reduce;
+        hook.user = &u;
+        if (m->nranks > 1) {
+          hook.window_words = chain_window;
+          hook.x.win = m->d_peer_win;
+          hook.x.nranks = (uint32_t)m->nranks;
+          hook.x.rank = (uint32_t)m->rank;
+        }
+        return bic_k_update_dictionary_v3x(c, E, D, A, d_counts + 1, &hook);
+      }
+    }
+  }
   DictWork w;
   // With peer windows the histograms live in the window: the fix kernel of an atom that changes adds its corrections
   // straight into EVERY rank's H over NVLink and ends with a barrier over the ranks (dict2.cu: hc_add, xgpu_barrier) --

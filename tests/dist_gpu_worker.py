@@ -27,8 +27,10 @@ def main():
     dist.broadcast(uid, 0)
     comm = ctx.comm_create(rank, world, uid.cpu().numpy())
 
-    for (rows, cols, W, K, seed) in [(512, 384, 8, 32, 1), (400, 512, 16, 64, 2), (300, 200, 12, 10, 3)]:
+    for (rows, cols, W, K, seed) in [(512, 384, 8, 32, 1), (400, 512, 16, 64, 2), (300, 200, 12, 10, 3), (640, 640, 8, 6, 4), (1024, 768, 8, 32, 5)]:
         page = synth.structured_page(rows, cols, seed=seed, salt=0.01)
+        if seed >= 4:   # noise: most rows use several atoms and almost every atom changes in the first updates -- many exchanges
+            page = (np.random.default_rng(seed).random((rows, cols)) < (0.35 if seed == 4 else 0.5)).astype(np.uint8)
         Xw = oracle.extract_patches(synth.pack_rows(page), rows, cols, W)
         m, n = W * W, Xw.shape[0]
         cuts = [int(n * r / world * (0.8 if r % 2 else 1.0)) if r < world else n for r in range(world + 1)]
