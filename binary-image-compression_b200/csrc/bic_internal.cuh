@@ -195,7 +195,9 @@ struct V3Hook {
   bic_status (*reduce)(void* user, bic_ctx* c, uint32_t* buf, size_t words, uint32_t* extra) = nullptr;
   void* user = nullptr;
   ChainDist x;
-  size_t (*window_words)(void* user, size_t need_words, uint32_t** base) = nullptr;  // reserve the peer window; returns words available
+  // this rank's window: *base = the first usable word (a device pointer), *base_off = its word offset inside the window;
+  // returns the words available from there
+  size_t (*window_words)(void* user, size_t need_words, uint32_t** base, uint64_t* base_off) = nullptr;
 };
 
 // scratch layout of one dictionary update (dict2.cu), shared with the row-sharded driver (dist.cu)

@@ -564,10 +564,11 @@ bic_status bic_k_update_dictionary_v3x(bic_ctx* c, bic_mat* E, bic_mat* D, const
     // in place), followed by the chain's exchange area
     const size_t xwords = (size_t)2 * hook->x.nranks * p * hs;
     uint32_t* base = nullptr;
-    const size_t got = hook->window_words(hook->user, glob_words + 64 + xwords, &base);
+    uint64_t base_off = 0;
+    const size_t got = hook->window_words(hook->user, glob_words + 64 + xwords, &base, &base_off);
     if (got < glob_words + 64 + xwords || !base) return bic_fail(c, BIC_ERR_NOMEM, "update_dictionary: peer window too small");
     G = base;
-    hook->x.xoff = (uint64_t)(base - hook->x.win[hook->x.rank]) + ((glob_words + 63) & ~(size_t)63);
+    hook->x.xoff = base_off + ((glob_words + 63) & ~(size_t)63);   // (hook->x.win is a table in DEVICE memory: not for the host to read)
   }
   BIC_TRY(bic_scratch_reserve(c, &c->work[3], (glob_words + local_words) * 4 + 64));
   if (!G) G = (uint32_t*)c->work[3].p;

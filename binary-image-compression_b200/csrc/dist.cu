@@ -352,10 +352,11 @@ static bic_status chain_reduce(void* user, bic_ctx* c, uint32_t* buf, size_t wor
   u->m->last_extra = extra;
   return allreduce_u32(c, u->m, buf, words);
 }
-static size_t chain_window(void* user, size_t need_words, uint32_t** base) {
+static size_t chain_window(void* user, size_t need_words, uint32_t** base, uint64_t* base_off) {
   ChainHookUser* u = (ChainHookUser*)user;
   (void)need_words;
   *base = u->m->win ? u->m->win + XWIN_DATA : nullptr;
+  *base_off = XWIN_DATA;
   return u->m->win_words > XWIN_DATA ? u->m->win_words - XWIN_DATA : 0;
 }
 

@@ -1,0 +1,20 @@
+#!/bin/bash
+# 2 GPUs: sharded parity tests + the N=2 bench line
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi -L > gpurun_out/e_gpus.txt; nproc >> gpurun_out/e_gpus.txt
+( time timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q ) > gpurun_out/e_pytest.log 2>&1
+echo "pytest rc=$? $(tail -4 gpurun_out/e_pytest.log | head -1)"
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 ) > gpurun_out/e_bench2.json 2> gpurun_out/e_bench2.err
+echo "bench2 rc=$?"; tail -c 1500 gpurun_out/e_bench2.err
+python - <<'PY'
+import json
+try:
+    l=[x for x in open('gpurun_out/e_bench2.json') if x.startswith('{')][0]
+    d=json.loads(l)
+    print('N=2 value', round(d['value']), 'ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), 'parity', d.get('parity_checked'), d.get('parity_planes'))
+    print('replicas', d.get('replicas',{}).get('value'), d.get('replicas',{}).get('ms_per_step'))
+    rs=d.get('row_sharded',{}); print({k:rs.get(k) for k in ('value','ms_per_step','collectives_per_step','gpu_launches','planes_in_flight_per_rank','iterations_per_plane')})
+except Exception as ex:
+    print('no line', ex)
+PY
