@@ -352,6 +352,8 @@ def main():
         host_cores = os.cpu_count() or 16
     T_fit = max(4, int(1.5 * host_cores / max(world, 1)))
     T = max(1, min(args.streams, T_fit, P * max(1, args.steps)))  # tasks of all steps share one queue
+    if not (args.pool or args.batch):
+        T = 1   # the pipeline drives the timed regions; one context is kept for the first pass and the per-kernel profile
     workers = [Worker() for _ in range(T)]
     stats = {"iters": [0] * P, "bits": [0] * P, "d2h": [0] * P, "wA": [0] * P, "changed_atoms": [0] * P}
 
@@ -521,6 +523,173 @@ def main():
     def all_launches():
         return ctx.launches + sum(w.ctx.launches for w in workers) + (pipe.stats()["launches"] if pipe is not None else 0)
 
+    # ---- row-sharded fit (N > 1): the N bands are ONE image, one dictionary per plane over all ranks' patches (the north
+    # star's multi-GPU path). Integer statistics are combined inside the library (csrc/dist.cu): NCCL allreduce of [H | U |
+    # bucket sizes | changed rows] once per bsvd iteration, the corrections of every atom that changes exchanged over NVLink peer
+    # memory from inside the cluster-chain kernel, seam-exact sharded Golomb coding. `sharded_streams` planes are in flight per
+    # rank (one context + one communicator + one host thread each; planes are dealt to them in the same order on every rank).
+    # (This arm runs FIRST and creates its contexts first: a kernel that waits for a peer GPU must not share a hardware queue with
+    # another such kernel, and CUDA deals streams to its 32 connections in creation order.)
+    px_step = P * rows * cols / 1e6  # Mpixel per rank per step
+    sharded = None
+    if world > 1 or args.sharded:
+        TS = max(1, min(args.sharded_streams, P, max(2, host_cores // max(world, 1))))
+
+        class ShWorker:
+            def __init__(self, j):
+                self.j = j
+                self.ctx = bic.Context(local_rank)
+                c = self.ctx
+                c.set_option("wait_mode", args.wait_mode)
+                c.set_option("dict_algo", args.dict_algo)
+                c.set_option("chain_cluster", args.sharded_cluster)
+                uid = torch.from_numpy(c.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+                if dist is not None:
+                    dist.broadcast(uid, 0)
+                self.comm = c.comm_create(rank, world, uid.cpu().numpy())
+                self.R = c.matrix(rows, cols)
+                self.X, self.E = c.matrix(n, m), c.matrix(n, m)
+                self.D, self.A = c.matrix(K, m), c.matrix(n, K)
+                self.streams = [c.stream() for _ in range(3)]
+                self.out = c.pinned(2 * plane_bytes + (1 << 20))
+                self.planes = [b for b in range(P) if b % TS == j]
+
+        shw = [ShWorker(j) for j in range(TS)]
+        sh_iters = [0] * P
+        sh_rec = {}
+        sh_d2h = [0] * P
+
+        def fit_sharded(w, b, record=False, e2e=False):
+            c = w.ctx
+            src = rasters[b]
+            if e2e:   # this rank's band of the plane from pinned host memory
+                c._ck(L.bic_mat_upload_pbm(c.h, w.R.h, host_planes[b].ctypes.data_as(C.POINTER(C.c_uint8))))
+                src = w.R
+            c._ck(L.bic_extract_patches(c.h, src.h, W, w.X.h))
+            rng = c.rand48(SEED)
+            c._ck(L.bic_dist_initialize_model_neighbor(c.h, w.comm, w.X.h, w.D.h, w.A.h, C.byref(rng)))
+            it = C.c_uint64(0)
+            c._ck(L.bic_dist_learn_model_traditional(c.h, w.comm, w.X.h, w.E.h, w.D.h, w.A.h, C.byref(it), None, 0))
+            sh_iters[b] = int(it.value)
+            # D is replicated (every rank codes the same stream); A and E are row-sharded: each rank writes its
+            # rows' codewords as the exact substring of the single global stream (bic_dist_golomb_encode)
+            c._ck(L.bic_golomb_encode(c.h, w.D.h, 256, w.streams[0].h))
+            shi = [bic.ShardInfo(), bic.ShardInfo()]
+            for M, s_, si in zip((w.A, w.E), w.streams[1:], shi):
+                c._ck(L.bic_dist_golomb_encode(c.h, w.comm, M.h, 256, s_.h, C.byref(si)))
+            if e2e:   # the shard's streams (and, on rank 0, the dictionary's) back to pinned host memory
+                off = 0
+                for s_ in (w.streams if rank == 0 else w.streams[1:]):
+                    si = s_.info
+                    nb, ni = (int(si.bitcount) + 7) // 8, int(si.nchunks)
+                    nbp = (nb + 7) & ~7
+                    idx = w.out[off + nbp: off + nbp + ni * 16].view(np.uint64)
+                    c._ck(L.bic_stream_download(c.h, s_.h, w.out[off:].ctypes.data_as(C.POINTER(C.c_uint8)), nb,
+                                                idx.ctypes.data_as(C.POINTER(C.c_uint64)), ni))
+                    off += nbp + ni * 16
+                sh_d2h[b] = off
+            if record:
+                sh_rec[b] = {"D": w.D.download(), "iters": int(it.value),
+                             "bits": [int(w.streams[0].info.bitcount), int(shi[0].global_bitcount), int(shi[1].global_bitcount)]}
+
+        def sh_steps(nsteps, record=False, e2e=False, one_at_a_time=False):
+            errs = []
+
+            def loop(w):
+                try:
+                    for _ in range(nsteps):
+                        for b in w.planes:
+                            fit_sharded(w, b, record, e2e)
+                except BaseException as ex:  # noqa: BLE001
+                    errs.append(ex)
+
+            ctx.timer_start()
+            for w in shw:
+                w.ctx.wait_for(ctx)
+            if one_at_a_time:   # first use: scratch areas and peer windows are allocated (device-wide synchronisations) -- one
+                for w in shw:   # communicator at a time, every rank in the same order
+                    loop(w)
+                    if dist is not None:
+                        dist.barrier()
+            else:
+                ths = [threading.Thread(target=loop, args=(w,), daemon=True) for w in shw]
+                for t in ths:
+                    t.start()
+                deadline = time.time() + 90 + 20 * nsteps
+                for t in ths:
+                    t.join(max(0.0, deadline - time.time()))
+                if any(t.is_alive() for t in ths):
+                    # a rank that waits for a peer forever must end the run, not burn the GPU box until somebody's limit
+                    sys.stderr.write(f"rank {rank}: the row-sharded arm made no progress for {90 + 20 * nsteps} s -- giving up\n")
+                    sys.stderr.flush()
+                    os._exit(3)
+            for w in shw:
+                ctx.wait_for(w.ctx)
+            ms = ctx.timer_stop()
+            if errs:
+                raise errs[0]
+            return ms
+
+        sh_steps(1, record=True, one_at_a_time=True)
+        barrier()
+        # ---- correctness of the sharded path, in the bench itself: the dictionary, the iteration count and the GLOBAL Golomb
+        # bit counts of D, A, E must equal the single-GPU fit of the concatenated rows (rank 0 gathers the N bands)
+        sh_checked = 0
+        for b in range(P):
+            band = torch.from_numpy(host_planes[b]).to(dev)
+            if dist is not None:
+                bands = [torch.empty_like(band) for _ in range(world)]
+                dist.all_gather(bands, band)
+            else:
+                bands = [band]
+            if rank == 0:
+                whole = torch.cat(bands, dim=0).cpu().numpy()
+                c = ctx
+                Iall = c.matrix(world * rows, cols)
+                Iall.upload_pbm(whole)
+                Xall = c.extract_patches(Iall, W)
+                Dall, Aall, Eall = c.matrix(K, m), c.matrix(Xall.rows, K), c.matrix(Xall.rows, m)
+                c.initialize_model_neighbor(Xall, Dall, Aall, c.rand48(SEED))
+                it1, _ = c.learn_model_traditional(Xall, Eall, Dall, Aall)
+                bits1 = [c.golomb_bitcount(M)[0] for M in (Dall, Aall, Eall)]
+                rec = sh_rec[b]
+                ok = it1 == rec["iters"] and bits1 == rec["bits"] and np.array_equal(Dall.download(), rec["D"])
+                for M in (Iall, Xall, Dall, Aall, Eall):
+                    M.destroy()
+                if not ok:
+                    raise SystemExit(f"PARITY FAILURE: row-sharded fit of bitplane {b} over {world} rank(s) differs from the single-GPU fit of the "
+                                     f"concatenated rows (iterations {rec['iters']} vs {it1}, Golomb bits {rec['bits']} vs {bits1})")
+                sh_checked += 1
+            del band, bands
+        barrier()
+        sh_steps(max(args.warmup, 3))
+        barrier()
+        coll0 = sum(w.ctx.comm_collectives(w.comm) for w in shw)
+        sh_launch0 = sum(w.ctx.launches for w in shw)
+        ms_sh = max_over_ranks(sh_steps(args.steps) / args.steps)
+        sh_launches = sum(w.ctx.launches for w in shw) - sh_launch0
+        coll1 = sum(w.ctx.comm_collectives(w.comm) for w in shw)
+        barrier()
+        sh_steps(1, e2e=True, one_at_a_time=True)   # first use of the upload staging areas: allocations, one communicator at a time
+        barrier()
+        ms_sh_e2e = max_over_ranks(sh_steps(args.steps, e2e=True) / args.steps)
+        barrier()
+        sharded = {"value": world * px_step / (ms_sh / 1e3), "unit": UNIT, "ms_per_step": ms_sh,
+                   "e2e": {"value": world * px_step / (ms_sh_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_sh_e2e,
+                           "h2d_bytes_per_step": P * plane_bytes, "d2h_bytes_per_step": int(sum(sh_d2h)),
+                           "path": "each rank: its band of every plane from pinned host memory -> sharded fit -> its shard of the A and E streams "
+                                   "(rank 0: D's too) back to pinned host memory"},
+                   "collectives_per_step": (coll1 - coll0) / args.steps, "gpu_launches": int(sh_launches),
+                   "iterations_per_plane": sh_iters, "planes_in_flight_per_rank": TS,
+                   "parity_checked": bool(sh_checked == P) if rank == 0 else None, "parity_planes": sh_checked,
+                   "parity_how": "D, the iteration count and the global Golomb bit counts of D, A, E of every plane equal the single-GPU "
+                                 "fit of the concatenated rows (run on rank 0 inside this bench)",
+                   "what": f"each plane is ONE {world * S}x{S} image whose patch rows are sharded over {world} rank(s); one dictionary per plane; one NCCL "
+                           "allreduce of the atom statistics per bsvd iteration; the corrections of every atom that changes are exchanged over NVLink peer "
+                           "memory inside the cluster-chain kernel; seam-exact sharded Golomb coding"}
+        for w in shw:
+            w.ctx.comm_destroy(w.comm)
+
     # ---- the pipeline: ONE host thread keeps `streams` rasters in flight (csrc/pipeline.cu)
     use_pipe = not (args.pool or batched)
     pipe = None
@@ -575,7 +744,6 @@ def main():
     launches = all_launches() - launches0
     clocks = sampler.stop(t_wall0, t_wall1)
     ms_per_step = max_over_ranks(ms / args.steps)
-    px_step = P * rows * cols / 1e6  # Mpixel per rank per step
     value = world * px_step / (ms_per_step / 1e3)
 
     # ---- e2e timing (host buffers, H2D + D2H inside)
@@ -731,7 +899,9 @@ def main():
     w0 = workers[0]
     w0.ctx.prof_reset()
     w0.ctx.prof_enable(True)
+    w0.ctx.read_counter("coef_passes")
     ms_seq = run_steps(fit_resident, args.steps, nworkers=1)
+    coef_passes = w0.ctx.read_counter("coef_passes") / args.steps    # (row, pass) pairs per step, counted by the kernel
     w0.ctx.prof_enable(False)
     prof = w0.ctx.prof_stats()
     tot_ms = sum(v[1] for v in prof.values()) or 1.0
@@ -764,14 +934,36 @@ def main():
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
+    # what bounds each kernel (ncu: profiles/): the product kernels sit on the popcount (XU) pipe, the Golomb walks on the issue
+    # slots, the chain on dependent shared-memory / DSMEM round trips inside ONE cluster; only the streaming passes are HBM kernels
+    POPC_PEAK = 4619.6   # Gpopc32/s, measured on this pool's B200 (profiles/r2_microbench.json: 15.9 per clock and SM at 1965 MHz)
+    BOUND = {"k_update_coefficients": "popc", "k_dict_hist_popc": "popc", "k_pivot_usage": "popc/issue", "k_dict_chain": "latency",
+             "k_gol_walk<0>": "issue", "k_gol_walk<1>": "issue", "k_gol_tile_counts": "hbm", "k_dict_apply": "hbm", "k_extract": "issue",
+             "k_residual": "hbm", "k_col_hist": "issue", "k_row_nonzero": "hbm", "k_dict_bucket": "latency"}
+    wprE32 = (m + 31) // 32
     per_kernel = {}
     for kname, (kn, kms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         kab = alg(kname, kn / args.steps)
         gbs = (kab / (kms / kn / 1e3)) / 1e9 if kab else None
-        per_kernel[kname] = {"ms_per_step": round(kms / args.steps, 4), "launches_per_step": kn / args.steps,
+        per_kernel[kname] = {"ms_per_step": round(kms / args.steps, 4), "launches_per_step": kn / args.steps, "bound": BOUND.get(kname, "latency"),
                              "algorithmic_gbs": round(gbs, 1) if gbs else None, "frac_of_hbm_peak": round(gbs / peak, 4) if gbs else None}
+        if kname == "k_update_coefficients" and coef_passes:
+            # algorithmic popcount work: every pass of a row is p * ceil(m/32) XOR + POPC (+ the row's own weight)
+            gpopc = coef_passes * (K + 1) * wprE32 / (kms / args.steps / 1e3) / 1e9
+            per_kernel[kname].update({"row_passes_per_step": coef_passes, "algorithmic_gpopc32_per_s": round(gpopc, 1),
+                                      "popc_peak_gpopc32_per_s": POPC_PEAK, "frac_of_popc_peak": round(gpopc / POPC_PEAK, 4)})
+        if kname == "k_dict_hist_popc":
+            gpopc = (kn / args.steps) * n * K * wprE32 / (kms / args.steps / 1e3) / 1e9   # one AND + POPC per (row block, atom, word column)
+            per_kernel[kname].update({"algorithmic_gpopc32_per_s": round(gpopc, 1), "popc_peak_gpopc32_per_s": POPC_PEAK,
+                                      "frac_of_popc_peak": round(gpopc / POPC_PEAK, 4)})
+    coefk = per_kernel.get("k_update_coefficients", {})
     roofline = {
-        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": BOUND.get(dom_name, "latency"), "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound_note": ("bound is what limits the kernel (ncu); achieved / peak / frac are still its ALGORITHMIC bytes against the measured HBM copy "
+                       "peak, as the contract asks, whatever the bound"),
+        "largest_full_grid_kernel": {"kernel": "k_update_coefficients", "bound": "popc", "achieved": coefk.get("algorithmic_gpopc32_per_s"),
+                                     "peak": POPC_PEAK, "unit": "Gpopc32/s", "frac": coefk.get("frac_of_popc_peak"),
+                                     "peak_source": "measured: profiles/microbench.cu k_popc_peak, profiles/r2_microbench.json"},
         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": avg_ms,
         "launches_per_step": dom_n / args.steps, "share_of_kernel_time": dom_ms / tot_ms,
@@ -781,164 +973,6 @@ def main():
                  "per_kernel lists every kernel of the step against the same HBM peak"),
         "per_kernel": per_kernel,
     }
-
-    # ---- row-sharded fit (N > 1): the N bands are ONE image, one dictionary per plane over all ranks' patches (the north
-    # star's multi-GPU path). Integer statistics are combined inside the library (csrc/dist.cu): NCCL allreduce of [H | U |
-    # bucket sizes | changed rows] once per bsvd iteration, the corrections of every atom that changes exchanged over NVLink peer
-    # memory from inside the cluster-chain kernel, seam-exact sharded Golomb coding. `sharded_streams` planes are in flight per
-    # rank (one context + one communicator + one host thread each; planes are dealt to them in the same order on every rank).
-    sharded = None
-    if world > 1 or args.sharded:
-        TS = max(1, min(args.sharded_streams, P))
-
-        class ShWorker:
-            def __init__(self, j):
-                self.j = j
-                self.ctx = bic.Context(local_rank)
-                c = self.ctx
-                c.set_option("wait_mode", args.wait_mode)
-                c.set_option("dict_algo", args.dict_algo)
-                c.set_option("chain_cluster", args.sharded_cluster)
-                uid = torch.from_numpy(c.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
-                if dist is not None:
-                    dist.broadcast(uid, 0)
-                self.comm = c.comm_create(rank, world, uid.cpu().numpy())
-                self.R = c.matrix(rows, cols)
-                self.X, self.E = c.matrix(n, m), c.matrix(n, m)
-                self.D, self.A = c.matrix(K, m), c.matrix(n, K)
-                self.streams = [c.stream() for _ in range(3)]
-                self.out = c.pinned(2 * plane_bytes + (1 << 20))
-                self.planes = [b for b in range(P) if b % TS == j]
-
-        shw = [ShWorker(j) for j in range(TS)]
-        sh_iters = [0] * P
-        sh_rec = {}
-        sh_d2h = [0] * P
-
-        def fit_sharded(w, b, record=False, e2e=False):
-            c = w.ctx
-            src = rasters[b]
-            if e2e:   # this rank's band of the plane from pinned host memory
-                c._ck(L.bic_mat_upload_pbm(c.h, w.R.h, host_planes[b].ctypes.data_as(C.POINTER(C.c_uint8))))
-                src = w.R
-            c._ck(L.bic_extract_patches(c.h, src.h, W, w.X.h))
-            rng = c.rand48(SEED)
-            c._ck(L.bic_dist_initialize_model_neighbor(c.h, w.comm, w.X.h, w.D.h, w.A.h, C.byref(rng)))
-            it = C.c_uint64(0)
-            c._ck(L.bic_dist_learn_model_traditional(c.h, w.comm, w.X.h, w.E.h, w.D.h, w.A.h, C.byref(it), None, 0))
-            sh_iters[b] = int(it.value)
-            # D is replicated (every rank codes the same stream); A and E are row-sharded: each rank writes its
-            # rows' codewords as the exact substring of the single global stream (bic_dist_golomb_encode)
-            c._ck(L.bic_golomb_encode(c.h, w.D.h, 256, w.streams[0].h))
-            shi = [bic.ShardInfo(), bic.ShardInfo()]
-            for M, s_, si in zip((w.A, w.E), w.streams[1:], shi):
-                c._ck(L.bic_dist_golomb_encode(c.h, w.comm, M.h, 256, s_.h, C.byref(si)))
-            if e2e:   # the shard's streams (and, on rank 0, the dictionary's) back to pinned host memory
-                off = 0
-                for s_ in (w.streams if rank == 0 else w.streams[1:]):
-                    si = s_.info
-                    nb, ni = (int(si.bitcount) + 7) // 8, int(si.nchunks)
-                    nbp = (nb + 7) & ~7
-                    idx = w.out[off + nbp: off + nbp + ni * 16].view(np.uint64)
-                    c._ck(L.bic_stream_download(c.h, s_.h, w.out[off:].ctypes.data_as(C.POINTER(C.c_uint8)), nb,
-                                                idx.ctypes.data_as(C.POINTER(C.c_uint64)), ni))
-                    off += nbp + ni * 16
-                sh_d2h[b] = off
-            if record:
-                sh_rec[b] = {"D": w.D.download(), "iters": int(it.value),
-                             "bits": [int(w.streams[0].info.bitcount), int(shi[0].global_bitcount), int(shi[1].global_bitcount)]}
-
-        def sh_steps(nsteps, record=False, e2e=False, one_at_a_time=False):
-            errs = []
-
-            def loop(w):
-                try:
-                    for _ in range(nsteps):
-                        for b in w.planes:
-                            fit_sharded(w, b, record, e2e)
-                except BaseException as ex:  # noqa: BLE001
-                    errs.append(ex)
-
-            ctx.timer_start()
-            for w in shw:
-                w.ctx.wait_for(ctx)
-            if one_at_a_time:   # first use: scratch areas and peer windows are allocated (device-wide synchronisations) -- one
-                for w in shw:   # communicator at a time, every rank in the same order
-                    loop(w)
-                    if dist is not None:
-                        dist.barrier()
-            else:
-                ths = [threading.Thread(target=loop, args=(w,)) for w in shw]
-                for t in ths:
-                    t.start()
-                for t in ths:
-                    t.join()
-            for w in shw:
-                ctx.wait_for(w.ctx)
-            ms = ctx.timer_stop()
-            if errs:
-                raise errs[0]
-            return ms
-
-        sh_steps(1, record=True, one_at_a_time=True)
-        barrier()
-        # ---- correctness of the sharded path, in the bench itself: the dictionary, the iteration count and the GLOBAL Golomb
-        # bit counts of D, A, E must equal the single-GPU fit of the concatenated rows (rank 0 gathers the N bands)
-        sh_checked = 0
-        for b in range(P):
-            band = torch.from_numpy(host_planes[b]).to(dev)
-            if dist is not None:
-                bands = [torch.empty_like(band) for _ in range(world)]
-                dist.all_gather(bands, band)
-            else:
-                bands = [band]
-            if rank == 0:
-                whole = torch.cat(bands, dim=0).cpu().numpy()
-                c = ctx
-                Iall = c.matrix(world * rows, cols)
-                Iall.upload_pbm(whole)
-                Xall = c.extract_patches(Iall, W)
-                Dall, Aall, Eall = c.matrix(K, m), c.matrix(Xall.rows, K), c.matrix(Xall.rows, m)
-                c.initialize_model_neighbor(Xall, Dall, Aall, c.rand48(SEED))
-                it1, _ = c.learn_model_traditional(Xall, Eall, Dall, Aall)
-                bits1 = [c.golomb_bitcount(M)[0] for M in (Dall, Aall, Eall)]
-                rec = sh_rec[b]
-                ok = it1 == rec["iters"] and bits1 == rec["bits"] and np.array_equal(Dall.download(), rec["D"])
-                for M in (Iall, Xall, Dall, Aall, Eall):
-                    M.destroy()
-                if not ok:
-                    raise SystemExit(f"PARITY FAILURE: row-sharded fit of bitplane {b} over {world} rank(s) differs from the single-GPU fit of the "
-                                     f"concatenated rows (iterations {rec['iters']} vs {it1}, Golomb bits {rec['bits']} vs {bits1})")
-                sh_checked += 1
-            del band, bands
-        barrier()
-        sh_steps(max(args.warmup, 3))
-        barrier()
-        coll0 = sum(w.ctx.comm_collectives(w.comm) for w in shw)
-        sh_launch0 = sum(w.ctx.launches for w in shw)
-        ms_sh = max_over_ranks(sh_steps(args.steps) / args.steps)
-        sh_launches = sum(w.ctx.launches for w in shw) - sh_launch0
-        coll1 = sum(w.ctx.comm_collectives(w.comm) for w in shw)
-        barrier()
-        sh_steps(1, e2e=True)
-        barrier()
-        ms_sh_e2e = max_over_ranks(sh_steps(args.steps, e2e=True) / args.steps)
-        barrier()
-        sharded = {"value": world * px_step / (ms_sh / 1e3), "unit": UNIT, "ms_per_step": ms_sh,
-                   "e2e": {"value": world * px_step / (ms_sh_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_sh_e2e,
-                           "h2d_bytes_per_step": P * plane_bytes, "d2h_bytes_per_step": int(sum(sh_d2h)),
-                           "path": "each rank: its band of every plane from pinned host memory -> sharded fit -> its shard of the A and E streams "
-                                   "(rank 0: D's too) back to pinned host memory"},
-                   "collectives_per_step": (coll1 - coll0) / args.steps, "gpu_launches": int(sh_launches),
-                   "iterations_per_plane": sh_iters, "planes_in_flight_per_rank": TS,
-                   "parity_checked": bool(sh_checked == P) if rank == 0 else None, "parity_planes": sh_checked,
-                   "parity_how": "D, the iteration count and the global Golomb bit counts of D, A, E of every plane equal the single-GPU "
-                                 "fit of the concatenated rows (run on rank 0 inside this bench)",
-                   "what": f"each plane is ONE {world * S}x{S} image whose patch rows are sharded over {world} rank(s); one dictionary per plane; one NCCL "
-                           "allreduce of the atom statistics per bsvd iteration; the corrections of every atom that changes are exchanged over NVLink peer "
-                           "memory inside the cluster-chain kernel; seam-exact sharded Golomb coding"}
-        for w in shw:
-            w.ctx.comm_destroy(w.comm)
 
     # ---- CPU baseline (rank 0, N == 1): the reference's own code on a bounded crop
     cpu = None
@@ -955,6 +989,87 @@ def main():
             # the same crops through the GPU path, bit for bit against what the reference just produced (a mismatch ends
             # the run with a non-zero exit code: no line is printed)
             parity_planes = gpu_parity_on_crops(ctx, info["outputs"], args.cpu_crop, W, K)
+
+    # ---- configs[4]: Golomb residual-coding-only sweep (encode + decode GB/s of packed input vs the reference's serial GolombCoder),
+    # at a size that keeps the default run short; profiles/coder_sweep.py runs the same at 2^31 bits
+    coder_sweep = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle_bindings import load_reference
+            ref_lib = load_reference()
+            LOG2 = 28
+            Nb = 1 << LOG2
+            ccols = 1 << 15
+            crows = Nb // ccols
+            coder_sweep = []
+            Ms, M2 = ctx.matrix(crows, ccols), ctx.matrix(crows, ccols)
+            st = ctx.stream()
+            for rho in (0.001, 0.01, 0.1, 0.5):
+                g = torch.Generator(device=dev).manual_seed(5)
+                bits = (torch.rand((crows, ccols), device=dev, generator=g) < rho).to(torch.uint8)
+                host = synth.pbm_bytes_torch(bits).cpu().numpy()
+                del bits
+                Ms.upload_pbm(host)
+                ctx.golomb_encode(Ms, out=st)
+                ctx.golomb_decode(st, M2)
+                reps = 5
+                ctx.timer_start()
+                for _ in range(reps):
+                    ctx.golomb_encode(Ms, out=st)
+                ms_enc = ctx.timer_stop() / reps
+                ctx.timer_start()
+                for _ in range(reps):
+                    ctx.golomb_decode(st, M2)
+                ms_dec = ctx.timer_stop() / reps
+                ok = bool(np.array_equal(M2.download_pbm(), host))
+                sample_rows = (1 << 24) // ccols
+                words = synth.pack_rows(np.unpackbits(host[:sample_rows], axis=1))
+                t0 = time.perf_counter()
+                if ref_lib is not None:
+                    ref_lib.golomb_matrix(words, ccols)
+                t_ref = time.perf_counter() - t0
+                gb = Nb / 8 / 1e9
+                coder_sweep.append({"rho": rho, "input_bits": Nb, "code_bits_per_input_bit": st.info.bitcount / Nb,
+                                    "encode_GBps_in": gb / (ms_enc / 1e3), "decode_GBps_out": gb / (ms_dec / 1e3),
+                                    "encode_frac_of_hbm_peak": gb / (ms_enc / 1e3) / peak, "roundtrip_ok": ok,
+                                    "serial_reference_GBps_in": ((1 << 24) / 8 / 1e9) / t_ref if ref_lib is not None else None})
+                if not ok:
+                    raise SystemExit(f"PARITY FAILURE: Golomb round trip at density {rho}")
+            for x in (Ms, M2, st):
+                x.destroy()
+        except SystemExit:
+            raise
+        except Exception as ex:  # noqa: BLE001
+            coder_sweep = {"error": f"{type(ex).__name__}: {ex}"}
+
+    # ---- what the links alone allow for the e2e path: the same host buffers copied in and out, nothing computed
+    copy_floor = None
+    if use_pipe and pgm_mode:
+        try:
+            d_in = torch.empty(rows * cols * 2, dtype=torch.uint8, device=dev)
+            tot_out = int(e2e_stats["d2h"])
+            d_out = torch.empty(tot_out, dtype=torch.uint8, device=dev)
+            h_in = torch.from_numpy(host_pgm)
+            h_out = torch.from_numpy(e2e_outs[0][0]) if False else torch.empty(tot_out, dtype=torch.uint8).pin_memory()
+            s_in, s_out2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            s_in.wait_event(ev0); s_out2.wait_event(ev0)
+            for _ in range(args.steps):
+                with torch.cuda.stream(s_in):
+                    d_in.copy_(h_in, non_blocking=True)
+                with torch.cuda.stream(s_out2):
+                    h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s_in); torch.cuda.current_stream().wait_stream(s_out2)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms_copy = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+            copy_floor = {"ms_per_step": ms_copy, "h2d_GBps": rows * cols * 2 / 1e9 / (ms_copy / 1e3), "d2h_GBps": tot_out / 1e9 / (ms_copy / 1e3),
+                          "what": "the e2e step's H2D and D2H bytes copied concurrently on two streams (pinned host memory), no kernel: the PCIe floor of one step"}
+            del d_in, d_out, h_out
+        except Exception as ex:  # noqa: BLE001
+            copy_floor = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
         line = {
@@ -979,6 +1094,8 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "coder_sweep": coder_sweep,
+            "e2e_copy_floor": copy_floor,
             "parity_checked": parity_planes > 0, "parity_planes": parity_planes,
             "parity_how": (f"D, A, E, iteration count and the Golomb bit counts of D, A, E of {parity_planes} bitplane crops "
                            f"({args.cpu_crop}x{args.cpu_crop}) compared bit for bit with the CPU reference's outputs of the cpu_baseline leg"

@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
         "bic_prof_enable": [_vp, C.c_int],
         "bic_prof_reset": [_vp],
         "bic_prof_get": [_vp, C.c_int, C.POINTER(C.c_char_p), _u64p, C.POINTER(C.c_double)],
+        "bic_ctx_read_counter": [_vp, C.c_char_p, _u64p],
         "bic_host_alloc": [C.c_size_t, C.POINTER(_vp)],
         "bic_host_free": [_vp],
         "bic_mat_create": [_vp, _u64, _u64, C.POINTER(_vp)],
@@ -431,6 +432,11 @@ class Context:
 
     def set_option(self, name: str, value: int):
         self._ck(self.L.bic_ctx_set_option(self.h, name.encode(), int(value)))
+
+    def read_counter(self, name: str) -> int:
+        v = _u64(0)
+        self._ck(self.L.bic_ctx_read_counter(self.h, name.encode(), C.byref(v)))
+        return int(v.value)
 
     def prof_enable(self, on: bool):
         self._ck(self.L.bic_prof_enable(self.h, 1 if on else 0))

@@ -59,6 +59,7 @@ enum bic_kernel_id {
 };
 
 #define BIC_SCALARS 512
+#define BIC_SCALAR_COEF_PASSES 100   // d_scalars slot: greedy passes (row x pass) of the lane-per-row coefficient kernel since the counter was last read
 
 struct bic_prof_rec { int kid; cudaEvent_t e0, e1; };
 

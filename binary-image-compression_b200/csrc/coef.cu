@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restric
                                                              unsigned long long* __restrict__ changed,
                                                              const ProbDev* __restrict__ probs,
                                                              const uint32_t* __restrict__ active,
-                                                             const uint32_t* __restrict__ skip) {
+                                                             const uint32_t* __restrict__ skip,
+                                                             unsigned long long* __restrict__ passes) {
   if (skip && *skip) return;  // the learner's loop already ended on the device (queued-ahead iteration)
   if (probs) {  // batched launch: blockIdx.y selects the problem
     if (!active[blockIdx.y]) return;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restric
   // next row of its warp's range at once instead of idling until the slowest lane of the warp is
   // done: every trip of the loop below is ONE pass (all atoms) for each lane that holds a row, and
   // lanes at different passes of different rows run the same instructions.
-  uint32_t nchanged = 0;
+  uint32_t nchanged = 0, npasses = 0;   // npasses: greedy passes over the dictionary (the algorithmic popcount work: p * WORDS each)
   const int lane = threadIdx.x & 31;
   const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restric
       for (int w = 0; w < WORDS; ++w) wt += __popc(e[w]);
       bool again = false;
       if (wt) {         // with weight 0 no distance can be smaller
+        ++npasses;
         const uint32_t key = best_atom_key<WORDS>(e, Ds, p);  // :1067-1082
         const uint32_t bestd = key >> 16, bestk = key & 0xFFFFu;
         if (bestd < wt) {  // :1084, strict <
@@ -117,7 +119,9 @@ __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restric
     }
   }
   nchanged = warp_sum_u32(nchanged);
+  npasses = warp_sum_u32(npasses);
   if ((threadIdx.x & 31) == 0 && nchanged) atomicAdd(changed, (unsigned long long)nchanged);
+  if ((threadIdx.x & 31) == 0 && npasses && passes) atomicAdd(passes, (unsigned long long)npasses);
 }
 
 // ------------------------------------------------------------------ large dictionaries: a warp per row, atoms pruned by weight
@@ -315,7 +319,7 @@ static bic_status launch_coef(bic_ctx* c, bic_mat* E, const bic_mat* D, bic_mat*
   const int grid = bic_grid_for(c, E->rows, 256, per_sm);
   BIC_PROF(c, KID_UPDATE_COEF);
   k_update_coefficients<WORDS><<<grid, 256, smem, c->stream>>>(E->d, D->d, A->d, E->rows, E->wpr, (uint32_t)D->rows,
-                                                              A->wpr, d_changed, nullptr, nullptr, c->loop_skip);
+                                                              A->wpr, d_changed, nullptr, nullptr, c->loop_skip, (unsigned long long*)(c->d_scalars + BIC_SCALAR_COEF_PASSES));
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }
@@ -334,7 +338,7 @@ static bic_status launch_coef_batched(bic_ctx* c, uint64_t n, uint64_t wprE, uin
   if (gx < 1) gx = 1;
   BIC_PROF(c, KID_UPDATE_COEF);
   k_update_coefficients<WORDS><<<dim3((unsigned)gx, nprob), 256, smem, c->stream>>>(nullptr, nullptr, nullptr, n, wprE, (uint32_t)p,
-                                                                                   wprA, nullptr, probs, active, nullptr);
+                                                                                   wprA, nullptr, probs, active, nullptr, nullptr);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }

@@ -108,6 +108,20 @@ extern "C" const char* bic_status_string(bic_status s) {
   }
 }
 
+// counters the kernels keep on the device for the measurement harness; reading one waits for the stream and resets it
+extern "C" bic_status bic_ctx_read_counter(bic_ctx* c, const char* name, uint64_t* value) {
+  if (!c || !name || !value) return BIC_ERR_INVALID;
+  cudaSetDevice(c->device);
+  int slot = -1;
+  if (!strcmp(name, "coef_passes")) slot = BIC_SCALAR_COEF_PASSES;
+  if (slot < 0) return bic_fail(c, BIC_ERR_INVALID, "unknown counter");
+  BIC_CUDA(c, cudaMemcpyAsync(c->h_scalars + slot, c->d_scalars + slot, 8, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, cudaMemsetAsync(c->d_scalars + slot, 0, 8, c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
+  *value = c->h_scalars[slot];
+  return BIC_OK;
+}
+
 extern "C" void* bic_ctx_cuda_stream(bic_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" int bic_ctx_sm_count(bic_ctx* c) { return c ? c->sm_count : 0; }
 extern "C" uint64_t bic_ctx_launch_count(bic_ctx* c) { return c ? c->launches : 0; }

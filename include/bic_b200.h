@@ -91,6 +91,10 @@ bic_status bic_prof_enable(bic_ctx* ctx, int on);
 bic_status bic_prof_reset(bic_ctx* ctx);
 int bic_prof_kernel_count(void);
 bic_status bic_prof_get(bic_ctx* ctx, int kernel, const char** name, uint64_t* launches, double* total_ms);
+/* device-side work counters for the measurement harness (reading waits for the stream and resets the counter):
+ * "coef_passes" = row passes over the dictionary done by update_coefficients since the last read (each is p * ceil(m/32)
+ * XOR + POPC: the algorithmic popcount work of SURVEY 8d) */
+bic_status bic_ctx_read_counter(bic_ctx* ctx, const char* name, uint64_t* value);
 /* pinned host memory for callers that want async H2D/D2H */
 bic_status bic_host_alloc(size_t bytes, void** out);
 bic_status bic_host_free(void* p);

@@ -1,7 +1,7 @@
 """BASELINE.json configs[4]: Golomb residual-coding-only sweep over densities 0.1 % - 50 %.
 Device encode + decode GB/s (of packed input) vs the reference's serial GolombCoder on the host
 (oracle/_ref, bit counting only -- the reference writes no bits). i.i.d. Bernoulli(rho) bit arrays.
-Usage (GPU box): python profiles/coder_sweep.py [log2_bits=31] > gpurun_out/coder_sweep.json"""
+Usage (GPU box): python profiles/coder_sweep.py [log2_bits=31] [rho,rho,...] > gpurun_out/coder_sweep.json"""
 import importlib
 import json
 import sys
@@ -25,7 +25,8 @@ rows = N // cols
 ctx = bic.Context(0)
 ref = load_reference()
 out = []
-for rho in (0.001, 0.003, 0.01, 0.03, 0.1, 0.2, 0.5):
+RHOS = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0.001, 0.003, 0.01, 0.03, 0.1, 0.2, 0.5]
+for rho in RHOS:
     g = torch.Generator(device="cuda").manual_seed(5)
     M = ctx.matrix(rows, cols)
     chunk_rows = 4096

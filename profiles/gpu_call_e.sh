@@ -3,9 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/e_gpus.txt; nproc >> gpurun_out/e_gpus.txt
-( time timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q ) > gpurun_out/e_pytest.log 2>&1
-echo "pytest rc=$? $(tail -4 gpurun_out/e_pytest.log | head -1)"
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 ) > gpurun_out/e_bench2.json 2> gpurun_out/e_bench2.err
+( time timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 4 --warmup 3 --no-cpu-baseline ) > gpurun_out/e_bench2.json 2> gpurun_out/e_bench2.err
 echo "bench2 rc=$?"; tail -c 1500 gpurun_out/e_bench2.err
 python - <<'PY'
 import json
