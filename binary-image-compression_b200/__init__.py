@@ -13,6 +13,7 @@ The directory name has a hyphen, so import it with
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -21,7 +22,8 @@ import numpy as np
 from . import synth  # noqa: F401
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libbic_b200.so"
+# BIC_B200_LIB selects another build of the same library (e.g. libbic_b200_dbg.so: device-side bounds checks compiled in)
+LIB_PATH = Path(os.environ["BIC_B200_LIB"]).resolve() if os.environ.get("BIC_B200_LIB") else PKG_DIR / "libbic_b200.so"
 
 BIC_OK = 0
 STATUS_NAMES = {0: "ok", 1: "invalid", 2: "cuda", 3: "nomem", 4: "capacity", 5: "no_device", 6: "corrupt", 7: "unsupported"}
@@ -63,7 +65,7 @@ class EncodeInfo(C.Structure):
 
 def build(verbose: bool = False) -> Path:
     """Compile libbic_b200.so in-tree with nvcc for sm_100a (no GPU needed)."""
-    r = subprocess.run(["make", "-C", str(PKG_DIR / "csrc"), "-j8"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", str(PKG_DIR / "csrc"), "-j8", "all", "debug"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building libbic_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
     if verbose:

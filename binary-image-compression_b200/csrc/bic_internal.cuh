@@ -138,6 +138,21 @@ bic_status bic_scratch_reserve(bic_ctx* ctx, bic_scratch* s, size_t bytes);
 bic_status bic_read_scalars(bic_ctx* ctx, int n);
 bic_status bic_zero_scalars(bic_ctx* ctx);
 
+// device-side bounds checks of the debug build (make -C csrc debug): a violated check prints its place and traps, which the
+// host sees as a failed launch -- the memcheck of a pool where compute-sanitizer is not available
+#if defined(BIC_DEBUG_CHECKS) && defined(__CUDA_ARCH__)
+#define BIC_DCHECK(cond)                                                                          \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      printf("BIC_DCHECK failed: %s at %s:%d (block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+             (int)blockIdx.x, (int)threadIdx.x);                                                  \
+      __trap();                                                                                   \
+    }                                                                                             \
+  } while (0)
+#else
+#define BIC_DCHECK(cond) do { } while (0)
+#endif
+
 #ifdef __CUDACC__
 #define BIC_HD __host__ __device__
 #else

@@ -278,7 +278,9 @@ struct G2Out {
   uint32_t* s_out;
   uint32_t wp, fill, cur;
   bool shared_word;      // the word being filled is shared with the previous thread (my range starts inside it)
+  uint32_t limit;        // words of the staged range (debug build: every store is checked against it)
   __device__ __forceinline__ void store(uint32_t val) {
+    BIC_DCHECK(!val || wp < limit);
     if (val) {
       if (shared_word) atomicOr(&s_out[wp], val);
       else s_out[wp] = val;
@@ -304,6 +306,7 @@ struct G2Out {
     }
   }
   __device__ __forceinline__ void finish() {                            // my last partial word is shared with the next thread
+    BIC_DCHECK(!(fill && cur) || wp < limit);
     if (fill && cur) atomicOr(&s_out[wp], cur);
   }
 };
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
       const uint32_t ob = (uint32_t)(o0 + ex - base);
       G2Out w;
       w.s_out = s_out; w.wp = ob >> 5; w.fill = ob & 31; w.cur = 0; w.shared_word = (ob & 31) != 0;
+      w.limit = (uint32_t)span_words;
       bool first = true, fast = false;
       uint32_t kc = 0, lpv = 0;
 #pragma unroll
@@ -358,6 +362,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
           else { k = golomb_k(t, (unsigned long long)(prev + 1)); x = (unsigned long long)(tb + lp - prev - 1); }
           if ((t & cmask) == 0) {                                        // chunk index: where this sample's codeword and run start
             const unsigned long long slot = t >> clog;
+            BIC_DCHECK(slot <= (g.N >> clog));
             g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
             g.index[2 * slot + 1] = fast ? (unsigned long long)(tb + lpv + 1) : (unsigned long long)(prev + 1);
           }
@@ -382,6 +387,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
         }
       }
       w.finish();
+      BIC_DCHECK((unsigned long long)w.wp * 32 + w.fill == (o0 + ex - base) + mybits);   // I wrote exactly the bits the length pass counted
     }
     __syncthreads();
     uint32_t* gout = g.out + (base >> 5);

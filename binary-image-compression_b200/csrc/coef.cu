@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256) k_update_coefficients(uint32_t* __restric
         const uint32_t key = best_atom_key<WORDS>(e, Ds, p);  // :1067-1082
         const uint32_t bestd = key >> 16, bestk = key & 0xFFFFu;
         if (bestd < wt) {  // :1084, strict <
+          BIC_DCHECK(bestk < p && r < n);
           A[r * wprA + (bestk >> 5)] ^= 0x80000000u >> (bestk & 31);  // Ai.flip(0,bestk), :1086
           const uint32_t* dk = Ds + bestk * WORDS;
 #pragma unroll

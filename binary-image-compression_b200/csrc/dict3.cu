@@ -86,6 +86,7 @@ __device__ __forceinline__ void chain_batch(const ChainParams& P, uint32_t k, ui
                                             const uint32_t* sDelta, const uint32_t* sCh, uint32_t* corr, uint32_t hsC) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t kw = k >> 5;
+  BIC_DCHECK(!valid || idx < __ldcg(P.count));                       // a bucket / queue entry is an index into the list
   const uint32_t* a = P.listA + (uint64_t)idx * P.wprA;
   const uint32_t* e = P.listE + (uint64_t)idx * P.wprE;
   for (uint32_t w = 0; w < P.wprE; ++w) {
@@ -110,6 +111,7 @@ __device__ __forceinline__ void chain_batch(const ChainParams& P, uint32_t k, ui
       if (!__any_sync(0xffffffffu, ab != 0)) continue;
       const uint32_t ul = warp_transpose32(ab);       // lane l: which of the 32 rows use atom t*32+l
       const uint32_t pu = __popc(ul);
+      BIC_DCHECK(!ul || t * 32 + lane < P.p);                            // a user bit beyond the last atom would be a stray pad bit of A
       uint32_t* hl = corr + (t * 32 + lane) * hsC + w * 32;
       uint32_t dl = dl0;
       while (dl) {                                    // warp-uniform
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(256) k_dict_bucket_fill(const uint32_t* __rest
             while (rows) {
               const int r = __clz(rows);
               rows &= ~(0x80000000u >> r);
+              BIC_DCHECK(o < bucket_cap && o < sOff[k + 1]);               // stays inside bucket k's range
               bucket[o++] = idx0 + r;
             }
           }
@@ -311,6 +314,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
       for (uint32_t b = warp * csize + rank; b < nb; b += csize * nwarps) {
         const uint32_t e = b * 32 + lane;
         const bool valid = e < cnt;
+        BIC_DCHECK(!valid || off + e < P.bucket_cap);
         chain_batch(P, k, valid ? __ldg(P.bucket + off + e) : 0u, valid, sDelta, sCh, sCorr, hsC);
       }
     } else {
@@ -361,6 +365,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_dict_chain(ChainParams P) 
       // that one goes to the other area.
       const uint32_t e = epoch0 + nx + 1;
       const uint64_t area = P.x.xoff + (uint64_t)(e & 1u) * P.x.nranks * nH;
+      BIC_DCHECK(P.x.rank < P.x.nranks && P.x.xoff >= XWIN_DATA);
       for (uint32_t i = (k + 1) * P.hs + tid; i < nH; i += CHAIN_THREADS) {
         const uint32_t j = i % P.hs;
         const uint32_t tot = cluster.map_shared_rank(acc, i % csize)[i / csize];
