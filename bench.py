@@ -533,14 +533,16 @@ def main():
     px_step = P * rows * cols / 1e6  # Mpixel per rank per step
     sharded = None
     if world > 1 or args.sharded:
-        TS = max(1, min(args.sharded_streams, P, max(2, host_cores // max(world, 1))))
+        TS = max(1, min(args.sharded_streams, P))
+        # more host threads than cores (8 ranks on a 32-core box): they must sleep while they wait, not poll
+        sh_wait_mode = args.wait_mode if TS + 1 <= max(1, host_cores // max(world, 1)) else 2
 
         class ShWorker:
             def __init__(self, j):
                 self.j = j
                 self.ctx = bic.Context(local_rank)
                 c = self.ctx
-                c.set_option("wait_mode", args.wait_mode)
+                c.set_option("wait_mode", sh_wait_mode)
                 c.set_option("dict_algo", args.dict_algo)
                 c.set_option("chain_cluster", args.sharded_cluster)
                 uid = torch.from_numpy(c.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
