@@ -277,27 +277,31 @@ __global__ void __launch_bounds__(256) k_g2_clear(G2Params P) {
 struct G2Out {
   uint32_t* s_out;
   uint32_t wp, fill, cur;
-  bool shared_word;      // the word being filled is shared with the previous thread (my range starts inside it)
-  uint32_t limit;        // words of the staged range (debug build: every store is checked against it)
-  __device__ __forceinline__ void store(uint32_t val) {
-    BIC_DCHECK(!val || wp < limit);
-    if (val) {
-      if (shared_word) atomicOr(&s_out[wp], val);
-      else s_out[wp] = val;
-    }
-    shared_word = false;
-    ++wp;
+  uint32_t first_wp, first_val;  // my first word when my range starts inside it: shared with the previous thread, so its value is
+  bool first_pending;            // kept in a register and OR-ed in at the end (finish) instead of being stored
+  uint32_t limit;                // words of the staged range (debug build: every store is checked against it)
+  // Everything below is branch-free on purpose: lanes complete their words at different times, and a branch around the store
+  // would be taken by a few lanes on almost every codeword (ncu: the store block ran with 2.5 of 32 lanes active).
+  __device__ __forceinline__ void store_if(bool doit, uint32_t val) {
+    BIC_DCHECK(!doit || !val || wp < limit);
+    const bool cap = doit && first_pending;
+    first_val = cap ? val : first_val;
+    if (doit && !first_pending) s_out[wp] = val;                       // one predicated store: the word is mine alone
+    first_pending = first_pending && !doit;
+    wp += doit ? 1u : 0u;
   }
   __device__ __forceinline__ void put(uint32_t cw, uint32_t L) {        // L <= 32 bits, right aligned in cw
     const unsigned long long a = ((unsigned long long)cur << 32) | ((unsigned long long)cw << (64 - fill - L));
     fill += L;
-    if (fill >= 32) { store((uint32_t)(a >> 32)); cur = (uint32_t)a; fill -= 32; }
-    else cur = (uint32_t)(a >> 32);
+    const bool full = fill >= 32;
+    store_if(full, (uint32_t)(a >> 32));
+    cur = full ? (uint32_t)a : (uint32_t)(a >> 32);
+    fill -= full ? 32u : 0u;
   }
   __device__ __forceinline__ void zeros(unsigned long long u) {         // u zero bits (the buffer is zeroed: just move on)
     const unsigned long long total = fill + u;
     if (total >= 32) {
-      store(cur);
+      store_if(true, cur);
       wp += (uint32_t)(total >> 5) - 1;
       cur = 0;
       fill = (uint32_t)(total & 31);
@@ -305,9 +309,15 @@ struct G2Out {
       fill = (uint32_t)total;
     }
   }
-  __device__ __forceinline__ void finish() {                            // my last partial word is shared with the next thread
+  __device__ __forceinline__ void finish() {
+    if (first_pending) {            // never completed a word: everything I wrote is in `cur`, inside my (shared) first word
+      BIC_DCHECK(!cur || wp < limit);
+      if (cur) atomicOr(&s_out[wp], cur);
+      return;
+    }
+    if (first_val) atomicOr(&s_out[first_wp], first_val);
     BIC_DCHECK(!(fill && cur) || wp < limit);
-    if (fill && cur) atomicOr(&s_out[wp], cur);
+    if (fill && cur) atomicOr(&s_out[wp], cur);                         // my last partial word is shared with the next thread
   }
 };
 
@@ -345,10 +355,12 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
     if (c) {
       const uint32_t ob = (uint32_t)(o0 + ex - base);
       G2Out w;
-      w.s_out = s_out; w.wp = ob >> 5; w.fill = ob & 31; w.cur = 0; w.shared_word = (ob & 31) != 0;
+      w.s_out = s_out; w.wp = ob >> 5; w.fill = ob & 31; w.cur = 0;
+      w.first_wp = w.wp; w.first_val = 0; w.first_pending = (ob & 31) != 0;   // a range that starts on a word boundary shares nothing there
       w.limit = (uint32_t)span_words;
+      const uint32_t cmask32 = g.chunk - 1;
       bool first = true, fast = false;
-      uint32_t kc = 0, lpv = 0;
+      uint32_t kc = 0, kmask = 0, lpv = 0, tl = (uint32_t)t;
 #pragma unroll
       for (int i = 0; i < WPT; ++i) {
         uint32_t b = v[i];
@@ -356,20 +368,38 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
           const int p = __clz(b);
           b &= ~(0x80000000u >> p);
           const uint32_t lp = (uint32_t)(i * 32 + p);
-          uint32_t k;
-          unsigned long long x;
-          if (fast) { k = kc; x = lp - lpv - 1; }
-          else { k = golomb_k(t, (unsigned long long)(prev + 1)); x = (unsigned long long)(tb + lp - prev - 1); }
-          if ((t & cmask) == 0) {                                        // chunk index: where this sample's codeword and run start
+          if (fast) {
+            // k = kc for the rest of my samples (g2_k_stable): 32-bit arithmetic relative to my first bit
+            const uint32_t x = lp - lpv - 1, u = x >> kc, rem = x & kmask;
+            if ((tl & cmask32) == 0) {                                   // chunk index: where this sample's codeword and run start
+              const unsigned long long slot = (t + (tl - (uint32_t)t)) >> clog;
+              BIC_DCHECK(slot <= (g.N >> clog));
+              g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
+              g.index[2 * slot + 1] = (unsigned long long)(tb + lpv + 1);
+            }
+            if (kc + u + 1 <= 32) {
+              w.put((rem << (u + 1)) | 1u, kc + u + 1);                   // k remainder bits, u zeros, a one
+            } else {
+              if (kc) w.put(rem, kc);
+              w.zeros(u);
+              w.put(1u, 1);
+            }
+            lpv = lp;
+            ++tl;
+            continue;
+          }
+          const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+          const unsigned long long x = (unsigned long long)(tb + lp - prev - 1);
+          if ((t & cmask) == 0) {
             const unsigned long long slot = t >> clog;
             BIC_DCHECK(slot <= (g.N >> clog));
             g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
-            g.index[2 * slot + 1] = fast ? (unsigned long long)(tb + lpv + 1) : (unsigned long long)(prev + 1);
+            g.index[2 * slot + 1] = (unsigned long long)(prev + 1);
           }
           const unsigned long long u = x >> k;
           const uint32_t rem = (uint32_t)(x & ((1ull << k) - 1));
           if (k + u + 1 <= 32) {
-            w.put((rem << (uint32_t)(u + 1)) | 1u, k + (uint32_t)u + 1);  // k remainder bits, u zeros, a one
+            w.put((rem << (uint32_t)(u + 1)) | 1u, k + (uint32_t)u + 1);
           } else {
             if (k) w.put(rem, k);
             w.zeros(u);
@@ -377,12 +407,12 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
           }
           lpv = lp;
           ++t;
-          if (!fast) {
-            prev = tb + lp;
-            if (first) {
-              first = false;
-              fast = g2_k_stable(t, (unsigned long long)(prev + 1), WPT * 32, &kc);
-            }
+          tl = (uint32_t)t;
+          prev = tb + lp;
+          if (first) {
+            first = false;
+            fast = g2_k_stable(t, (unsigned long long)(prev + 1), WPT * 32, &kc);
+            kmask = (1u << kc) - 1u;
           }
         }
       }
