@@ -60,9 +60,7 @@ __device__ const uint2 g_gol_lut[4 * 256] = {
 #define G2_LUT_TZ(m) (((m) >> 3) & 7u)
 #define G2_LUT_NBITS(m) (((m) >> 6) & 31u)
 #define G2_LUT_NONES(m) (((m) >> 11) & 15u)
-__device__ __forceinline__ void g2_load_lut(uint2* s_lut) {
-  for (int i = threadIdx.x; i < 4 * 256; i += G2_THREADS) s_lut[i] = g_gol_lut[i];
-}
+// (read with __ldg straight from global memory: the 8 KB stay in L1; a per-CTA copy to shared memory cost more than the walk saved)
 
 __device__ __forceinline__ const G2Seg& g2_segment(const G2Params& P, uint32_t* tile) {
   uint32_t i = 0;
@@ -198,8 +196,6 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   __shared__ int s_w[16];
   __shared__ unsigned long long s_a[8];
   __shared__ int s_last_cta;
-  __shared__ uint2 s_lut[4 * 256];
-  g2_load_lut(s_lut);                      // visible after the barriers of g2_scan below
   uint32_t tile;
   const G2Seg& g = g2_segment(P, &tile);
   uint32_t v[WPT];
@@ -215,45 +211,64 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   const long long tb = (long long)(w0 * 32);
   unsigned long long mybits = 0;
   if (c) {
-    bool first = true, fast = false, lut = false;
-    uint32_t kc = 0, lpv = 0, fastbits = 0;
-    const uint2* lutk = s_lut;
+    // my first one closes a run that began before my stretch: full-width arithmetic, and the coder state it leaves decides how
+    // the rest of the stretch is walked (the three loops below are each uniform, so a warp only diverges where lanes differ in mode)
+    uint32_t fw = 0, fi = 0;
 #pragma unroll
-    for (int i = 0; i < WPT; ++i) {
-      uint32_t wv = v[i];
-      if (!wv) continue;
-      for (uint32_t bb = i * 32; wv; bb += 8, wv <<= 8) {          // byte by byte, MSB first
-        const uint32_t B = wv >> 24;
-        if (!B) continue;
-        if (lut) {                                                   // constant small k: the whole byte from the table
-          const uint32_t meta = lutk[B].y;
+    for (int i = WPT - 1; i >= 0; --i) if (v[i]) { fw = v[i]; fi = (uint32_t)i; }
+    const uint32_t p0 = (uint32_t)__clz(fw);
+    uint32_t lpv = fi * 32 + p0;
+#pragma unroll
+    for (int i = 0; i < WPT; ++i) if ((uint32_t)i == fi) v[i] &= ~(0x80000000u >> p0);
+    {
+      const long long pos = tb + lpv;
+      const unsigned long long x = (unsigned long long)(pos - prev - 1);
+      const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+      mybits += k + (x >> k) + 1;
+      prev = pos;
+      ++t;
+    }
+    uint32_t kc = 0, fastbits = 0;
+    const bool fast = g2_k_stable(t, (unsigned long long)(prev + 1), WPT * 32, &kc);
+    if (fast && kc <= 3) {
+      const uint2* lutk = g_gol_lut + kc * 256;
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        uint32_t wv = v[i];
+        for (uint32_t bb = i * 32; wv; bb += 8, wv <<= 8) {        // byte by byte, MSB first: the whole byte from the table
+          const uint32_t B = wv >> 24;
+          if (!B) continue;
+          const uint32_t meta = __ldg(&lutk[B].y);
           fastbits += kc + 1 + ((bb + G2_LUT_F(meta) - lpv - 1) >> kc) + G2_LUT_NBITS(meta);
           lpv = bb + 7 - G2_LUT_TZ(meta);
-          continue;
         }
-        uint32_t b = B << 24;
+      }
+    } else if (fast) {
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        uint32_t b = v[i];
         while (b) {
           const int p = __clz(b);
           b &= ~(0x80000000u >> p);
-          const uint32_t lp = bb + p;
-          if (fast) {                                                // k = kc for the rest of my samples
-            fastbits += kc + 1 + ((lp - lpv - 1) >> kc);
-            lpv = lp;
-            continue;
-          }
-          const long long pos = tb + lp;
+          const uint32_t lp = (uint32_t)(i * 32 + p);
+          fastbits += kc + 1 + ((lp - lpv - 1) >> kc);
+          lpv = lp;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        uint32_t b = v[i];
+        while (b) {
+          const int p = __clz(b);
+          b &= ~(0x80000000u >> p);
+          const long long pos = tb + i * 32 + p;
           const unsigned long long x = (unsigned long long)(pos - prev - 1);
           const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
           mybits += k + (x >> k) + 1;
           prev = pos;
           ++t;
-          if (first) {
-            first = false;
-            fast = g2_k_stable(t, (unsigned long long)(prev + 1), WPT * 32, &kc);
-            lpv = lp;
-          }
         }
-        if (fast && kc <= 3) { lut = true; lutk = s_lut + kc * 256; }   // from the next byte on
       }
     }
     mybits += fastbits;
@@ -358,11 +373,9 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
   __shared__ int s_w[16];
   __shared__ unsigned long long s_a[8];
   __shared__ uint32_t s_out[G2_STAGE_WORDS(WPT)];
-  __shared__ uint2 s_lut[4 * 256];
   uint32_t tile;
   const G2Seg& g = g2_segment(P, &tile);
   if (g.info[4]) return;                                                 // the code does not fit: nothing is written
-  g2_load_lut(s_lut);                                                    // visible after the barriers of g2_scan below
   uint32_t v[WPT];
   const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS(WPT) + threadIdx.x * WPT;
   g2_load(g, w0, v);
@@ -393,24 +406,82 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
       w.first_wp = w.wp; w.first_val = 0; w.first_pending = (ob & 31) != 0;   // a range that starts on a word boundary shares nothing there
       w.limit = (uint32_t)span_words;
       const uint32_t cmask32 = g.chunk - 1;
-      bool first = true, fast = false, lut = false;
-      uint32_t kc = 0, kmask = 0, lpv = 0, tl = (uint32_t)t;
-      const uint2* lutk = s_lut;
+      // my first one (see the length pass): codeword from the full-width run length, then the mode of the rest
+      uint32_t fw = 0, fi = 0;
 #pragma unroll
-      for (int i = 0; i < WPT; ++i) {
-        uint32_t wv = v[i];
-        if (!wv) continue;
-        for (uint32_t bb = i * 32; wv; bb += 8, wv <<= 8) {          // byte by byte, MSB first
-          const uint32_t B = wv >> 24;
-          if (!B) continue;
-          if (lut) {
-            // constant small k: the byte's first one closes the run in progress, its other ones come from the table as one
-            // bit pattern -- unless one of the byte's samples starts a chunk (its code position goes into the index): then
-            // the byte is walked one by one below
-            const uint2 en = lutk[B];
-            const uint32_t no = G2_LUT_NONES(en.y);
-            if (((tl + no - 1) >> clog) == ((tl - 1) >> clog)) {
-              const uint32_t x = bb + G2_LUT_F(en.y) - lpv - 1, u = x >> kc, rem = x & kmask;
+      for (int i = WPT - 1; i >= 0; --i) if (v[i]) { fw = v[i]; fi = (uint32_t)i; }
+      const uint32_t p0 = (uint32_t)__clz(fw);
+      uint32_t lpv = fi * 32 + p0;
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) if ((uint32_t)i == fi) v[i] &= ~(0x80000000u >> p0);
+      {
+        const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+        const unsigned long long x = (unsigned long long)(tb + lpv - prev - 1);
+        if ((t & cmask) == 0) {                                          // chunk index: where this sample's codeword and run start
+          const unsigned long long slot = t >> clog;
+          BIC_DCHECK(slot <= (g.N >> clog));
+          g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
+          g.index[2 * slot + 1] = (unsigned long long)(prev + 1);
+        }
+        const unsigned long long u = x >> k;
+        const uint32_t rem = (uint32_t)(x & ((1ull << k) - 1));
+        if (k + u + 1 <= 32) {
+          w.put((rem << (uint32_t)(u + 1)) | 1u, k + (uint32_t)u + 1);    // k remainder bits, u zeros, a one
+        } else {
+          if (k) w.put(rem, k);
+          w.zeros(u);
+          w.put(1u, 1);
+        }
+        ++t;
+        prev = tb + lpv;
+      }
+      uint32_t kc = 0;
+      const bool fast = g2_k_stable(t, (unsigned long long)(prev + 1), WPT * 32, &kc);
+      const uint32_t kmask = (1u << kc) - 1u;
+      uint32_t tl = (uint32_t)t;                                           // low bits of the running sample rank (fast modes)
+      if (fast) {
+        const bool lut = kc <= 3;
+        const uint2* lutk = g_gol_lut + (lut ? kc : 0) * 256;
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          uint32_t wv = v[i];
+          for (uint32_t bb = i * 32; wv; bb += 8, wv <<= 8) {            // byte by byte, MSB first
+            const uint32_t B = wv >> 24;
+            if (!B) continue;
+            if (lut) {
+              // constant small k: the byte's first one closes the run in progress, its other ones come from the table as one bit
+              // pattern -- unless one of the byte's samples starts a chunk (its code position goes into the index): then the byte
+              // is walked one by one below
+              const uint2 en = __ldg(&lutk[B]);
+              const uint32_t no = G2_LUT_NONES(en.y);
+              if (((tl + no - 1) >> clog) == ((tl - 1) >> clog)) {
+                const uint32_t x = bb + G2_LUT_F(en.y) - lpv - 1, u = x >> kc, rem = x & kmask;
+                if (kc + u + 1 <= 32) {
+                  w.put((rem << (u + 1)) | 1u, kc + u + 1);
+                } else {
+                  if (kc) w.put(rem, kc);
+                  w.zeros(u);
+                  w.put(1u, 1);
+                }
+                const uint32_t nb = G2_LUT_NBITS(en.y);
+                if (nb) w.put(en.x, nb);
+                lpv = bb + 7 - G2_LUT_TZ(en.y);
+                tl += no;
+                continue;
+              }
+            }
+            uint32_t b = B << 24;
+            while (b) {                                                  // k = kc, one sample at a time
+              const int p = __clz(b);
+              b &= ~(0x80000000u >> p);
+              const uint32_t lp = bb + p;
+              const uint32_t x = lp - lpv - 1, u = x >> kc, rem = x & kmask;
+              if ((tl & cmask32) == 0) {
+                const unsigned long long slot = (t + (tl - (uint32_t)t)) >> clog;
+                BIC_DCHECK(slot <= (g.N >> clog));
+                g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
+                g.index[2 * slot + 1] = (unsigned long long)(tb + lpv + 1);
+              }
               if (kc + u + 1 <= 32) {
                 w.put((rem << (u + 1)) | 1u, kc + u + 1);
               } else {
@@ -418,40 +489,21 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
                 w.zeros(u);
                 w.put(1u, 1);
               }
-              const uint32_t nb = G2_LUT_NBITS(en.y);
-              if (nb) w.put(en.x, nb);
-              lpv = bb + 7 - G2_LUT_TZ(en.y);
-              tl += no;
-              continue;
-            }
-          }
-          uint32_t b = B << 24;
-          while (b) {
-            const int p = __clz(b);
-            b &= ~(0x80000000u >> p);
-            const uint32_t lp = bb + p;
-            if (fast) {
-              // k = kc for the rest of my samples (g2_k_stable): 32-bit arithmetic relative to my first bit
-              const uint32_t x = lp - lpv - 1, u = x >> kc, rem = x & kmask;
-              if ((tl & cmask32) == 0) {                                 // chunk index: where this sample's codeword and run start
-                const unsigned long long slot = (t + (tl - (uint32_t)t)) >> clog;
-                BIC_DCHECK(slot <= (g.N >> clog));
-                g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
-                g.index[2 * slot + 1] = (unsigned long long)(tb + lpv + 1);
-              }
-              if (kc + u + 1 <= 32) {
-                w.put((rem << (u + 1)) | 1u, kc + u + 1);                 // k remainder bits, u zeros, a one
-              } else {
-                if (kc) w.put(rem, kc);
-                w.zeros(u);
-                w.put(1u, 1);
-              }
               lpv = lp;
               ++tl;
-              continue;
             }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          uint32_t b = v[i];
+          while (b) {                                                    // k re-derived for every sample
+            const int p = __clz(b);
+            b &= ~(0x80000000u >> p);
+            const long long pos = tb + i * 32 + p;
             const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
-            const unsigned long long x = (unsigned long long)(tb + lp - prev - 1);
+            const unsigned long long x = (unsigned long long)(pos - prev - 1);
             if ((t & cmask) == 0) {
               const unsigned long long slot = t >> clog;
               BIC_DCHECK(slot <= (g.N >> clog));
@@ -467,17 +519,9 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
               w.zeros(u);
               w.put(1u, 1);
             }
-            lpv = lp;
             ++t;
-            tl = (uint32_t)t;
-            prev = tb + lp;
-            if (first) {
-              first = false;
-              fast = g2_k_stable(t, (unsigned long long)(prev + 1), WPT * 32, &kc);
-              kmask = (1u << kc) - 1u;
-            }
+            prev = pos;
           }
-          if (fast && kc <= 3) { lut = true; lutk = s_lut + kc * 256; }   // from the next byte on
         }
       }
       w.finish();
