@@ -439,16 +439,42 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
       const bool fast = g2_k_stable(t, (unsigned long long)(prev + 1), WPT * 32, &kc);
       const uint32_t kmask = (1u << kc) - 1u;
       uint32_t tl = (uint32_t)t;                                           // low bits of the running sample rank (fast modes)
-      if (fast) {
-        const bool lut = kc <= 3;
-        const uint2* lutk = g_gol_lut + (lut ? kc : 0) * 256;
+      if (fast && kc > 3) {
+        // constant k, sparse data (at most a one or two per word): one sample at a time, word by word
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          uint32_t b = v[i];
+          while (b) {
+            const int p = __clz(b);
+            b &= ~(0x80000000u >> p);
+            const uint32_t lp = (uint32_t)(i * 32 + p);
+            const uint32_t x = lp - lpv - 1, u = x >> kc, rem = x & kmask;
+            if ((tl & cmask32) == 0) {
+              const unsigned long long slot = (t + (tl - (uint32_t)t)) >> clog;
+              BIC_DCHECK(slot <= (g.N >> clog));
+              g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
+              g.index[2 * slot + 1] = (unsigned long long)(tb + lpv + 1);
+            }
+            if (kc + u + 1 <= 32) {
+              w.put((rem << (u + 1)) | 1u, kc + u + 1);
+            } else {
+              w.put(rem, kc);
+              w.zeros(u);
+              w.put(1u, 1);
+            }
+            lpv = lp;
+            ++tl;
+          }
+        }
+      } else if (fast) {
+        const uint2* lutk = g_gol_lut + kc * 256;
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
           uint32_t wv = v[i];
           for (uint32_t bb = i * 32; wv; bb += 8, wv <<= 8) {            // byte by byte, MSB first
             const uint32_t B = wv >> 24;
             if (!B) continue;
-            if (lut) {
+            {
               // constant small k: the byte's first one closes the run in progress, its other ones come from the table as one bit
               // pattern -- unless one of the byte's samples starts a chunk (its code position goes into the index): then the byte
               // is walked one by one below
