@@ -1011,6 +1011,84 @@ extern "C" bic_status bic_golomb_encode(bic_ctx* c, const bic_mat* M, uint32_t c
   return BIC_OK;
 }
 
+// ------------------------------------------------------------------ a shard through the wide-tile encoder (coding2.cu)
+bic_status bic_g2_plan(bic_ctx* c, const bic_mat* M, void* plan_out, size_t plan_bytes);
+bic_status bic_g2_count(bic_ctx* c, void* plan, unsigned long long* d_tot);
+bic_status bic_g2_lengths(bic_ctx* c, void* plan, const GolBase* gb, unsigned long long** d_info);
+bic_status bic_g2_scatter(bic_ctx* c, void* plan, const GolBase* gb, uint32_t chunk, bic_stream* out);
+
+// what the caller knows about the rest of the matrix: called with this shard's own numbers, fills in the global ones
+struct ShardPrefix {   // after pass 1
+  uint64_t ones_before, bits_before, ones_global, bits_global;
+  long long last_before, last_global;   // global positions of the last one before this shard / of the whole matrix, -1 if none
+  int is_last;
+};
+typedef bic_status (*shard_prefix_fn)(void* user, bic_ctx* c, uint64_t ones, uint64_t lastpos1, uint64_t nbits, ShardPrefix* out);
+typedef bic_status (*shard_code0_fn)(void* user, bic_ctx* c, uint64_t my_code_bits, uint64_t* code_bits_before, uint64_t* code_bits_total);
+
+static uint32_t golomb_k_host(uint64_t t64, uint64_t bits_consumed);
+
+static bic_status golomb_shard_g2(bic_ctx* c, const bic_mat* M, uint32_t chunk_samples, bic_stream* out, bic_shard_info* shard,
+                                  shard_prefix_fn prefix, shard_code0_fn code0fn, void* user) {
+  alignas(16) unsigned char plan[4096];
+  BIC_TRY(bic_g2_plan(c, M, plan, sizeof(plan)));
+  unsigned long long* d_tot = (unsigned long long*)(c->d_scalars + 58);
+  BIC_TRY(bic_g2_count(c, plan, d_tot));
+  BIC_CUDA(c, cudaMemcpyAsync(c->h_scalars + 58, d_tot, 16, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
+  const uint64_t ones = c->h_scalars[58], lastpos1 = c->h_scalars[59], N = M->rows * M->cols;
+  ShardPrefix px;
+  BIC_TRY(prefix(user, c, ones, lastpos1, N, &px));
+  GolBase base = gol_base_single();
+  base.closing = 0;
+  base.t0 = px.ones_before; base.pos0 = (long long)px.bits_before; base.prev0 = px.last_before;
+  unsigned long long* d_info = nullptr;
+  BIC_TRY(bic_g2_lengths(c, plan, &base, &d_info));
+  BIC_CUDA(c, cudaMemcpyAsync(c->h_scalars + 56, d_info + 2, 8, cudaMemcpyDeviceToHost, c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
+  const uint64_t bits_mine = c->h_scalars[56];
+  uint64_t code0 = 0, code_total = 0;
+  BIC_TRY(code0fn(user, c, bits_mine, &code0, &code_total));
+  const uint64_t consumed = (uint64_t)(px.last_global + 1);
+  const uint32_t kc = golomb_k_host(px.ones_global, consumed);
+  const uint64_t closing_bits = kc + ((px.bits_global - consumed) >> kc) + 1;
+  base.code0 = code0;
+  base.out0 = code0 & 31;
+  base.chunk0 = div_up_u64(base.t0, chunk_samples);
+  uint64_t local_bits = bits_mine, local_samples = ones;
+  if (px.is_last) {  // the last shard also writes the run closed by the virtual one
+    base.closing = 1;
+    base.close_t = px.ones_global;
+    base.close_consumed = consumed;
+    base.close_off = bits_mine;
+    base.close_n = px.bits_global;
+    local_bits += closing_bits;
+    local_samples += 1;
+  }
+  const uint64_t nchunks = div_up_u64(base.t0 + local_samples, chunk_samples) - base.chunk0;
+  if (shard) {
+    // code_total == ~0: the caller does not know the other shards' lengths; then only the last shard can tell the global count
+    shard->global_bitcount = code_total != ~0ull ? code_total + closing_bits : (px.is_last ? code0 + local_bits : 0);
+    shard->global_nsamples = px.ones_global + 1;
+    shard->code_bit_offset = code0;
+    shard->local_code_bits = local_bits;
+    shard->first_chunk = base.chunk0;
+    shard->local_chunks = nchunks;
+  }
+  if (!out) return BIC_OK;
+  BIC_TRY(stream_reserve(c, out, base.out0 + local_bits, nchunks, N));
+  BIC_CUDA(c, cudaMemsetAsync(out->d_bytes, 0, (size_t)(div_up_u64(base.out0 + local_bits, 32) * 4 + 16), c->stream));
+  BIC_TRY(bic_g2_scatter(c, plan, &base, chunk_samples, out));
+  out->info.coder = BIC_CODER_GOLOMB;
+  out->info.chunk_samples = chunk_samples;
+  out->info.rows = M->rows;
+  out->info.cols = M->cols;
+  out->info.bitcount = base.out0 + local_bits;  // bits of the local buffer, incl. the (code0 & 31) leading pad
+  out->info.nsamples = local_samples;
+  out->info.nchunks = nchunks;
+  return BIC_OK;
+}
+
 // ------------------------------------------------------------------ row-sharded coding (several GPUs)
 struct bic_comm;
 bic_status bic_comm_allgather_u64(bic_ctx* c, bic_comm* m, const uint64_t* mine, int count, uint64_t* all);
@@ -1038,6 +1116,34 @@ extern "C" bic_status bic_dist_golomb_encode(bic_ctx* c, bic_comm* m, const bic_
   if (chunk_samples == 0) chunk_samples = 256;
   while (chunk_samples & (chunk_samples - 1)) chunk_samples++;
   const int rank = bic_comm_rank(m), nr = bic_comm_size(m);
+  if (c->gol_algo == 2 && M->rows * M->cols > 0) {
+    struct U { bic_comm* m; int rank, nr; } u{m, rank, nr};
+    auto prefix = [](void* user, bic_ctx* cc, uint64_t ones, uint64_t lastpos1, uint64_t nbits, ShardPrefix* px) -> bic_status {
+      U* uu = (U*)user;
+      uint64_t mine[3] = {ones, lastpos1, nbits}, all[8 * 3];
+      BIC_TRY(bic_comm_allgather_u64(cc, uu->m, mine, 3, all));
+      memset(px, 0, sizeof(*px));
+      px->last_before = -1; px->last_global = -1;
+      uint64_t pos = 0, og = 0;
+      for (int r = 0; r < uu->nr; ++r) {
+        if (r == uu->rank) { px->ones_before = og; px->bits_before = pos; px->last_before = px->last_global; }
+        if (all[r * 3 + 1]) px->last_global = (long long)(pos + all[r * 3 + 1] - 1);
+        og += all[r * 3];
+        pos += all[r * 3 + 2];
+      }
+      px->ones_global = og; px->bits_global = pos; px->is_last = uu->rank == uu->nr - 1;
+      return BIC_OK;
+    };
+    auto code0fn = [](void* user, bic_ctx* cc, uint64_t mybits, uint64_t* before, uint64_t* total) -> bic_status {
+      U* uu = (U*)user;
+      uint64_t all[8];
+      BIC_TRY(bic_comm_allgather_u64(cc, uu->m, &mybits, 1, all));
+      *before = 0; *total = 0;
+      for (int r = 0; r < uu->nr; ++r) { if (r < uu->rank) *before += all[r]; *total += all[r]; }
+      return BIC_OK;
+    };
+    return golomb_shard_g2(c, M, chunk_samples, out, shard, prefix, code0fn, &u);
+  }
   GolWork w;
   BIC_TRY(golomb_counts(c, M, &w));
   BIC_PROF(c, KID_GOL_SCAN_B);
@@ -1117,6 +1223,31 @@ extern "C" bic_status bic_golomb_encode_shard(bic_ctx* c, const bic_mat* M, uint
     return bic_fail(c, BIC_ERR_INVALID, "golomb_encode_shard: inconsistent prefix state");
   if (chunk_samples == 0) chunk_samples = 256;
   while (chunk_samples & (chunk_samples - 1)) chunk_samples++;
+  if (c->gol_algo == 2 && M->rows * M->cols > 0) {
+    struct U { uint64_t ones_before, bits_before, code_before, total_bits; long long last_before; int closing; }
+        u{ones_before, bits_before, code_bits_before, total_bits, (long long)last_one_before, closing};
+    auto prefix = [](void* user, bic_ctx*, uint64_t ones, uint64_t lastpos1, uint64_t nbits, ShardPrefix* px) -> bic_status {
+      U* uu = (U*)user;
+      memset(px, 0, sizeof(*px));
+      px->ones_before = uu->ones_before; px->bits_before = uu->bits_before; px->last_before = uu->last_before;
+      px->ones_global = uu->ones_before + ones;          // meaningful for the closing shard only (nothing follows it)
+      px->bits_global = uu->closing ? uu->total_bits : uu->bits_before + nbits;
+      px->last_global = lastpos1 ? (long long)(uu->bits_before + lastpos1 - 1) : uu->last_before;
+      px->is_last = uu->closing != 0;
+      return BIC_OK;
+    };
+    auto code0fn = [](void* user, bic_ctx*, uint64_t, uint64_t* before, uint64_t* total) -> bic_status {
+      U* uu = (U*)user;
+      *before = uu->code_before; *total = ~0ull;         // the total is only known to whoever holds every shard
+      return BIC_OK;
+    };
+    bic_shard_info si;
+    memset(&si, 0, sizeof(si));
+    BIC_TRY(golomb_shard_g2(c, M, chunk_samples, out, &si, prefix, code0fn, &u));
+    if (!closing) { si.global_bitcount = 0; si.global_nsamples = 0; }   // only the last shard knows them
+    if (shard) *shard = si;
+    return BIC_OK;
+  }
   GolWork w;
   BIC_TRY(golomb_counts(c, M, &w));
   GolBase base = gol_base_single();

@@ -42,6 +42,10 @@ struct G2Seg {
   unsigned long long* index;
   unsigned long long cap_bits;
   uint32_t chunk;                    // samples per chunk-index entry, a power of two
+  // where the matrix sits in the ONE global sample stream when it is a row shard of a bigger matrix (coding.cu: GolBase; all zero
+  // / prev0 = -1 for a whole matrix). closing: 0 = another shard writes the run closed by the virtual one, 1 = this one does, with
+  // the rank / position / offset in gb.close_* (known on the host), 2 = this one does, from info[] (the totals are still on the device)
+  GolBase gb;
 };
 struct G2Params {
   G2Seg s[G2_MAXSEG];
@@ -205,10 +209,11 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   int last, ex_last, tot_last;
   g2_count(v, &c, &last);
   g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
-  unsigned long long t = g.ones_before[tile] + ex_c;                                  // rank of my first sample
+  unsigned long long t = g.gb.t0 + g.ones_before[tile] + ex_c;                        // global rank of my first sample
   const long long lb = g.last_before[tile];
-  long long prev = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;       // the one before my stretch, -1 if none
-  const long long tb = (long long)(w0 * 32);
+  const long long pvl = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;  // the one before my stretch inside this matrix, -1 if none
+  long long prev = pvl >= 0 ? pvl + g.gb.pos0 : g.gb.prev0;                            // ... as a GLOBAL position
+  const long long tb = (long long)(w0 * 32) + g.gb.pos0;                               // global position of my first bit
   unsigned long long mybits = 0;
   if (c) {
     // my first one closes a run that began before my stretch: full-width arithmetic, and the coder state it leaves decides how
@@ -383,15 +388,17 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
   int last, ex_last, tot_last;
   g2_count(v, &c, &last);
   g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
-  unsigned long long t = g.ones_before[tile] + ex_c;
+  unsigned long long t = g.gb.t0 + g.ones_before[tile] + ex_c;
   const long long lb = g.last_before[tile];
-  long long prev = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;
-  const long long tb = (long long)(w0 * 32);
+  const long long pvl = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;
+  long long prev = pvl >= 0 ? pvl + g.gb.pos0 : g.gb.prev0;
+  const long long tb = (long long)(w0 * 32) + g.gb.pos0;
   const unsigned long long mybits = g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x];
   unsigned long long tot;
   const unsigned long long ex = g2_excl_sum_u64(mybits, &tot, s_a);
-  const unsigned long long o0 = g.bits_before[tile];
-  const unsigned long long base = o0 & ~31ull;                           // stream bit position of s_out[0]
+  const unsigned long long o0 = g.bits_before[tile] + g.gb.out0;         // bit offset inside this shard's own buffer
+  const unsigned long long base = o0 & ~31ull;                           // buffer bit position of s_out[0]
+  const unsigned long long goff = g.gb.code0 - g.gb.out0;                // buffer bit offset -> global code bit offset (chunk index)
   const unsigned long long span_words = ((o0 - base) + tot + 31) >> 5;
   const bool staged = span_words <= G2_STAGE_WORDS(WPT);                      // uniform over the CTA
   const unsigned long long cmask = (unsigned long long)g.chunk - 1;
@@ -418,9 +425,9 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
         const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
         const unsigned long long x = (unsigned long long)(tb + lpv - prev - 1);
         if ((t & cmask) == 0) {                                          // chunk index: where this sample's codeword and run start
-          const unsigned long long slot = t >> clog;
-          BIC_DCHECK(slot <= (g.N >> clog));
-          g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
+          const unsigned long long slot = (t >> clog) - g.gb.chunk0;
+          BIC_DCHECK(slot <= (g.N >> clog) + 1);
+          g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
           g.index[2 * slot + 1] = (unsigned long long)(prev + 1);
         }
         const unsigned long long u = x >> k;
@@ -450,9 +457,9 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
             const uint32_t lp = (uint32_t)(i * 32 + p);
             const uint32_t x = lp - lpv - 1, u = x >> kc, rem = x & kmask;
             if ((tl & cmask32) == 0) {
-              const unsigned long long slot = (t + (tl - (uint32_t)t)) >> clog;
-              BIC_DCHECK(slot <= (g.N >> clog));
-              g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
+              const unsigned long long slot = ((t + (tl - (uint32_t)t)) >> clog) - g.gb.chunk0;
+              BIC_DCHECK(slot <= (g.N >> clog) + 1);
+              g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
               g.index[2 * slot + 1] = (unsigned long long)(tb + lpv + 1);
             }
             if (kc + u + 1 <= 32) {
@@ -503,9 +510,9 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
               const uint32_t lp = bb + p;
               const uint32_t x = lp - lpv - 1, u = x >> kc, rem = x & kmask;
               if ((tl & cmask32) == 0) {
-                const unsigned long long slot = (t + (tl - (uint32_t)t)) >> clog;
-                BIC_DCHECK(slot <= (g.N >> clog));
-                g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
+                const unsigned long long slot = ((t + (tl - (uint32_t)t)) >> clog) - g.gb.chunk0;
+                BIC_DCHECK(slot <= (g.N >> clog) + 1);
+                g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
                 g.index[2 * slot + 1] = (unsigned long long)(tb + lpv + 1);
               }
               if (kc + u + 1 <= 32) {
@@ -531,9 +538,9 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
             const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
             const unsigned long long x = (unsigned long long)(pos - prev - 1);
             if ((t & cmask) == 0) {
-              const unsigned long long slot = t >> clog;
-              BIC_DCHECK(slot <= (g.N >> clog));
-              g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill;
+              const unsigned long long slot = (t >> clog) - g.gb.chunk0;
+              BIC_DCHECK(slot <= (g.N >> clog) + 1);
+              g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
               g.index[2 * slot + 1] = (unsigned long long)(prev + 1);
             }
             const unsigned long long u = x >> k;
@@ -573,7 +580,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
         const long long pos = tb + i * 32 + p;
         const unsigned long long x = (unsigned long long)(pos - prev - 1);
         const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
-        if ((t & cmask) == 0) { g.index[2 * (t >> clog)] = o; g.index[2 * (t >> clog) + 1] = (unsigned long long)(prev + 1); }
+        if ((t & cmask) == 0) { g.index[2 * ((t >> clog) - g.gb.chunk0)] = o + goff; g.index[2 * ((t >> clog) - g.gb.chunk0) + 1] = (unsigned long long)(prev + 1); }
         put_bits(g.out, o, (uint32_t)(x & ((1ull << k) - 1)), k);
         const unsigned long long stop = o + k + (x >> k);
         put_one(g.out, stop);
@@ -583,12 +590,13 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
       }
     }
   }
-  if (tile == 0 && threadIdx.x == 0) {                                   // the run closed by the virtual one
-    const unsigned long long tt = g.info[1] - 1, consumed = g.info[3];
-    unsigned long long oo = g.info[2];
-    const unsigned long long x = g.N - consumed;
+  if (g.gb.closing && tile == 0 && threadIdx.x == 0) {                   // the run closed by the virtual one
+    const bool dyn = g.gb.closing == 2;
+    const unsigned long long tt = dyn ? g.info[1] - 1 : g.gb.close_t, consumed = dyn ? g.info[3] : g.gb.close_consumed;
+    unsigned long long oo = (dyn ? g.info[2] : g.gb.close_off) + g.gb.out0;
+    const unsigned long long x = (dyn ? g.N : g.gb.close_n) - consumed;
     const uint32_t k = golomb_k(tt, consumed);
-    if ((tt & cmask) == 0) { g.index[2 * (tt >> clog)] = oo; g.index[2 * (tt >> clog) + 1] = consumed; }
+    if ((tt & cmask) == 0) { g.index[2 * ((tt >> clog) - g.gb.chunk0)] = oo + goff; g.index[2 * ((tt >> clog) - g.gb.chunk0) + 1] = consumed; }
     put_bits(g.out, oo, (uint32_t)(x & ((1ull << k) - 1)), k);
     oo += k + (x >> k);
     put_one(g.out, oo);
@@ -660,6 +668,9 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
     g.cap_bits = (uint64_t)(outs[i]->cap_bytes - 32) * 8;
     if (c->gol_presize_pct < 100 && g.cap_bits > want_bits) g.cap_bits = want_bits;   // a test setting: pretend the buffer is that small
     g.chunk = chunk_samples;
+    memset(&g.gb, 0, sizeof(g.gb));
+    g.gb.prev0 = -1;
+    g.gb.closing = 2;                                            // a whole matrix: the closing sample's state comes from info[]
     outs[i]->info.coder = BIC_CODER_GOLOMB;
     outs[i]->info.chunk_samples = chunk_samples;
     outs[i]->info.rows = M->rows;
@@ -682,6 +693,105 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
   BIC_PROF(c, KID_GOL_SCATTER);
   if (WPT == 16) k_g2_scatter<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   else k_g2_scatter<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+
+// ---- the three passes as separate calls, for the row-sharded coders of coding.cu: the prefix state of a shard (GolBase) only
+// exists after the ranks have exchanged their counts, and its code offset after they have exchanged their code lengths.
+struct G2Plan {
+  G2Params P;
+  int WPT;
+  uint32_t ntiles;
+};
+static G2Plan g_unused_plan;  // (keeps the type complete for the declarations in coding.cu)
+
+bic_status bic_g2_plan(bic_ctx* c, const bic_mat* M, void* plan_out, size_t plan_bytes) {
+  if (plan_bytes < sizeof(G2Plan)) return BIC_ERR_INVALID;
+  (void)g_unused_plan;
+  G2Plan* pl = (G2Plan*)plan_out;
+  memset(pl, 0, sizeof(*pl));
+  const uint64_t N = M->rows * M->cols;
+  if (N == 0) return BIC_ERR_INVALID;
+  const uint64_t T = div_up_u64(N, 32);
+  pl->WPT = (T / G2_TILE_WORDS(16) >= (uint64_t)c->sm_count * 16) ? 16 : 4;
+  const uint64_t nt = div_up_u64(T, (uint64_t)G2_TILE_WORDS(pl->WPT));
+  if (nt >= (1ull << 31)) return bic_fail(c, BIC_ERR_UNSUPPORTED, "golomb: too many tiles for one launch");
+  if (M->cols & 31) BIC_TRY(bic_scratch_reserve(c, &c->work[4], ((T + 7) & ~(uint64_t)3) * 4 + 64));
+  const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8;
+  BIC_TRY(bic_scratch_reserve(c, &c->work[5], nt * per_tile + 64 * G2_MAXSEG + 64 + 64));
+  uint8_t* p = (uint8_t*)c->work[5].p;
+  unsigned int* done = (unsigned int*)p;
+  BIC_CUDA(c, cudaMemsetAsync(done, 0, 64 * G2_MAXSEG, c->stream));
+  p += 64 * G2_MAXSEG;
+  G2Seg& g = pl->P.s[0];
+  pl->P.nseg = 1;
+  g.N = N;
+  if (M->cols & 31) BIC_TRY(bic_dense_stream_into(c, M, (uint32_t*)c->work[4].p, &g.S, &g.T));
+  else { g.S = M->d; g.T = T; }
+  g.tile0 = 0; g.ntiles = (uint32_t)nt;
+  pl->ntiles = (uint32_t)nt;
+  g.last = (long long*)p;                         p += nt * 8;
+  g.ones_before = (unsigned long long*)p;         p += nt * 8;
+  g.last_before = (long long*)p;                  p += nt * 8;
+  g.bits = (unsigned long long*)p;                p += nt * 8;
+  g.bits_before = (unsigned long long*)p;         p += nt * 8;
+  g.ones = (uint32_t*)p;                          p += nt * 8;
+  g.tbits = (unsigned long long*)p;               p += nt * (size_t)G2_THREADS * 8;
+  g.info = (unsigned long long*)p;                 // 8 words after the per-tile arrays
+  g.done = done;
+  g.cap_bits = ~0ull >> 1;
+  g.chunk = 256;
+  memset(&g.gb, 0, sizeof(g.gb));
+  g.gb.prev0 = -1;
+  return BIC_OK;
+}
+
+// pass 1; afterwards (stream order) the per-tile counts and their prefixes exist. ones / last-one position are returned through
+// d_tot (device, 2 u64: ones, position after the last one or 0), computed by a tiny kernel from the tile arrays.
+__global__ void k_g2_totals(G2Seg g, unsigned long long* tot) {
+  const uint64_t lt = g.ntiles - 1;
+  const long long lastg = g.last_before[lt] > g.last[lt] ? g.last_before[lt] : g.last[lt];
+  tot[0] = g.ones_before[lt] + g.ones[lt];
+  tot[1] = (unsigned long long)(lastg + 1);
+}
+
+bic_status bic_g2_count(bic_ctx* c, void* plan, unsigned long long* d_tot) {
+  G2Plan* pl = (G2Plan*)plan;
+  BIC_PROF(c, KID_GOL_TILE_COUNTS);
+  if (pl->WPT == 16) k_g2_count<16><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
+  else k_g2_count<4><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
+  BIC_LAUNCH_CHECK(c);
+  k_g2_totals<<<1, 1, 0, c->stream>>>(pl->P.s[0], d_tot);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+// pass 2 under the shard's prefix state; the shard's own code bits land in info[2] (device) = *d_bits
+bic_status bic_g2_lengths(bic_ctx* c, void* plan, const GolBase* gb, unsigned long long** d_info) {
+  G2Plan* pl = (G2Plan*)plan;
+  pl->P.s[0].gb = *gb;
+  BIC_PROF(c, KID_GOL_LENGTHS);
+  if (pl->WPT == 16) k_g2_lengths<16><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
+  else k_g2_lengths<4><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
+  BIC_LAUNCH_CHECK(c);
+  *d_info = pl->P.s[0].info;
+  return BIC_OK;
+}
+
+// pass 3 into `out` (already zeroed by the caller), with the complete base (code0 / out0 / chunk0 / closing now known)
+bic_status bic_g2_scatter(bic_ctx* c, void* plan, const GolBase* gb, uint32_t chunk, bic_stream* out) {
+  G2Plan* pl = (G2Plan*)plan;
+  G2Seg& g = pl->P.s[0];
+  g.gb = *gb;
+  g.chunk = chunk;
+  g.out = (uint32_t*)out->d_bytes;
+  g.index = (unsigned long long*)out->d_index;
+  BIC_CUDA(c, cudaMemsetAsync(g.info + 4, 0, 8, c->stream));   // the overflow flag of the single-stream path: the buffer is exact here
+  BIC_PROF(c, KID_GOL_SCATTER);
+  if (pl->WPT == 16) k_g2_scatter<16><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
+  else k_g2_scatter<4><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }

@@ -119,5 +119,6 @@ struct GolBase {
   unsigned long long chunk0;  // first chunk-index entry this shard stores
   int closing;                // this shard writes the run closed by the virtual one
   unsigned long long close_t, close_consumed, close_off;  // its sample rank, bits consumed before it, local bit offset
+  unsigned long long close_n;                             // bits of the whole (global) matrix: where the virtual one sits (coding2.cu)
 };
 
