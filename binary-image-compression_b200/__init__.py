@@ -148,6 +148,7 @@ def lib() -> C.CDLL:
         "bic_pipeline_job_status": [_vp, _u64, C.POINTER(C.c_int), C.POINTER(C.c_char_p)],
         "bic_pipeline_forget_finished": [_vp],
         "bic_pipeline_stats": [_vp, _u64p, _u64p, _u64p, _u64p, _u64p],
+        "bic_pipeline_attach_comms": [_vp, C.POINTER(_vp), C.c_int],
         "bic_pipeline_wait_ctx": [_vp, _vp],
         "bic_ctx_wait_pipeline": [_vp, _vp],
         "bic_stream_create": [_vp, C.POINTER(_vp)],
@@ -168,6 +169,8 @@ def lib() -> C.CDLL:
         f = getattr(L, name)
         f.argtypes = args
         f.restype = C.c_int
+    L.bic_pipeline_slot_ctx.argtypes = [_vp, C.c_int]
+    L.bic_pipeline_slot_ctx.restype = _vp
     L.bic_enumL.argtypes = [_u64, _u64]
     L.bic_enumL.restype = C.c_double
     L.bic_prof_kernel_count.argtypes = []
@@ -377,8 +380,54 @@ class Pipeline:
     def wait_for(self, ctx: "Context"):
         self._ck(self.L.bic_pipeline_wait_ctx(self.h, ctx.h))
 
+    # ---- sharded mode (several GPUs): one communicator per slot, the same slot index on every rank
+    def make_sharded(self, rank: int, world: int, share_id):
+        """share_id(id_or_None) -> id: the caller's plumbing that takes the 128-byte id generated on rank 0 (None elsewhere) to every
+        rank (e.g. a torch.distributed broadcast). Creates one communicator per slot and switches the pipeline to sharded jobs."""
+        Context._preload_nccl()
+        self._comms = []
+        for i in range(self.nslots):
+            uid = None
+            if rank == 0:
+                buf = np.zeros(128, np.uint8)
+                self._ck(self.L.bic_comm_unique_id(buf.ctypes.data_as(_u8p)), "comm_unique_id")
+                uid = buf
+            uid = np.ascontiguousarray(share_id(uid), np.uint8)
+            comm = _vp()
+            self._ck(self.L.bic_comm_create(self.L.bic_pipeline_slot_ctx(self.h, i), rank, world, uid.ctypes.data_as(_u8p), C.byref(comm)),
+                     "comm_create")
+            self._comms.append(comm)
+        arr = (_vp * self.nslots)(*self._comms)
+        self._ck(self.L.bic_pipeline_attach_comms(self.h, arr, self.nslots), "attach_comms")
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def parse_shard_container(buf: np.ndarray) -> dict:
+        """the fields and streams of a sharded job's output (layout: csrc/pipeline.cu)"""
+        h = buf[:48 * 8].view(np.uint64)
+        assert int(h[0]) == 0x0044524853434942, "not a shard container"
+        out = {"rank": int(h[2]), "ranks": int(h[3]), "rows": int(h[4]), "cols": int(h[5]), "W": int(h[6]), "K": int(h[7]), "n": int(h[8]),
+               "m": int(h[9]), "iterations": int(h[10]), "seed": int(h[11]), "streams": {}}
+        off = 48 * 8
+        for i, name in enumerate(("D", "A", "E")):
+            f = [int(x) for x in h[12 + 7 * i: 19 + 7 * i]]
+            nb, ni = (f[4] + 7) // 8, f[6]
+            nbp = (nb + 7) & ~7
+            st = {"chunk_samples": f[1], "rows": f[2], "cols": f[3], "local_bits": f[4], "local_samples": f[5], "local_chunks": f[6],
+                  "bytes": buf[off: off + nb], "index": buf[off + nbp: off + nbp + ni * 16].view(np.uint64).reshape(-1, 2)}
+            if i:
+                sh = [int(x) for x in h[33 + 6 * (i - 1): 39 + 6 * (i - 1)]]
+                st.update(dict(zip(("global_bitcount", "global_nsamples", "code_bit_offset", "local_code_bits", "first_chunk", "local_chunks_sh"), sh)))
+            out["streams"][name] = st
+            off += nbp + ni * 16
+        out["bytes"] = off
+        return out
+
     def close(self):
         if self.h:
+            for i, comm in enumerate(getattr(self, "_comms", [])):
+                self.L.bic_comm_destroy(self.L.bic_pipeline_slot_ctx(self.h, i), comm)
+            self._comms = []
             self.L.bic_pipeline_destroy(self.h)
             self.h = None
 

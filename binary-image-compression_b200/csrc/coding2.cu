@@ -46,6 +46,7 @@ struct G2Seg {
   // / prev0 = -1 for a whole matrix). closing: 0 = another shard writes the run closed by the virtual one, 1 = this one does, with
   // the rank / position / offset in gb.close_* (known on the host), 2 = this one does, from info[] (the totals are still on the device)
   GolBase gb;
+  const GolBase* gbp;                // non-null: the base is still being computed on the device (pipeline.cu's sharded jobs): read it from here
 };
 struct G2Params {
   G2Seg s[G2_MAXSEG];
@@ -209,11 +210,12 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   int last, ex_last, tot_last;
   g2_count(v, &c, &last);
   g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
-  unsigned long long t = g.gb.t0 + g.ones_before[tile] + ex_c;                        // global rank of my first sample
+  const GolBase gb = g.gbp ? *g.gbp : g.gb;
+  unsigned long long t = gb.t0 + g.ones_before[tile] + ex_c;                          // global rank of my first sample
   const long long lb = g.last_before[tile];
   const long long pvl = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;  // the one before my stretch inside this matrix, -1 if none
-  long long prev = pvl >= 0 ? pvl + g.gb.pos0 : g.gb.prev0;                            // ... as a GLOBAL position
-  const long long tb = (long long)(w0 * 32) + g.gb.pos0;                               // global position of my first bit
+  long long prev = pvl >= 0 ? pvl + gb.pos0 : gb.prev0;                                // ... as a GLOBAL position
+  const long long tb = (long long)(w0 * 32) + gb.pos0;                                 // global position of my first bit
   unsigned long long mybits = 0;
   if (c) {
     // my first one closes a run that began before my stretch: full-width arithmetic, and the coder state it leaves decides how
@@ -304,11 +306,15 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
     const unsigned long long x = g.N - consumed;                                        // the run closed by the virtual one
     const uint32_t k = golomb_k(ones, consumed);
     const unsigned long long total = carry + k + (x >> k) + 1;
-    g.info[0] = total;
-    g.info[1] = ones + 1;
-    g.info[2] = carry;
-    g.info[3] = consumed;
-    g.info[4] = (total + 64 > g.cap_bits) ? 1ull : 0ull;
+    if (g.gbp) {            // a shard: the stream's totals are the business of k_g2_shard_base2; this rank's code bits are all it needs
+      g.info[2] = carry;
+    } else {
+      g.info[0] = total;
+      g.info[1] = ones + 1;
+      g.info[2] = carry;
+      g.info[3] = consumed;
+      g.info[4] = (total + 64 > g.cap_bits) ? 1ull : 0ull;
+    }
   }
 }
 
@@ -388,17 +394,18 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
   int last, ex_last, tot_last;
   g2_count(v, &c, &last);
   g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
-  unsigned long long t = g.gb.t0 + g.ones_before[tile] + ex_c;
+  const GolBase gb = g.gbp ? *g.gbp : g.gb;
+  unsigned long long t = gb.t0 + g.ones_before[tile] + ex_c;
   const long long lb = g.last_before[tile];
   const long long pvl = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;
-  long long prev = pvl >= 0 ? pvl + g.gb.pos0 : g.gb.prev0;
-  const long long tb = (long long)(w0 * 32) + g.gb.pos0;
+  long long prev = pvl >= 0 ? pvl + gb.pos0 : gb.prev0;
+  const long long tb = (long long)(w0 * 32) + gb.pos0;
   const unsigned long long mybits = g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x];
   unsigned long long tot;
   const unsigned long long ex = g2_excl_sum_u64(mybits, &tot, s_a);
-  const unsigned long long o0 = g.bits_before[tile] + g.gb.out0;         // bit offset inside this shard's own buffer
+  const unsigned long long o0 = g.bits_before[tile] + gb.out0;         // bit offset inside this shard's own buffer
   const unsigned long long base = o0 & ~31ull;                           // buffer bit position of s_out[0]
-  const unsigned long long goff = g.gb.code0 - g.gb.out0;                // buffer bit offset -> global code bit offset (chunk index)
+  const unsigned long long goff = gb.code0 - gb.out0;                // buffer bit offset -> global code bit offset (chunk index)
   const unsigned long long span_words = ((o0 - base) + tot + 31) >> 5;
   const bool staged = span_words <= G2_STAGE_WORDS(WPT);                      // uniform over the CTA
   const unsigned long long cmask = (unsigned long long)g.chunk - 1;
@@ -425,7 +432,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
         const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
         const unsigned long long x = (unsigned long long)(tb + lpv - prev - 1);
         if ((t & cmask) == 0) {                                          // chunk index: where this sample's codeword and run start
-          const unsigned long long slot = (t >> clog) - g.gb.chunk0;
+          const unsigned long long slot = (t >> clog) - gb.chunk0;
           BIC_DCHECK(slot <= (g.N >> clog) + 1);
           g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
           g.index[2 * slot + 1] = (unsigned long long)(prev + 1);
@@ -457,7 +464,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
             const uint32_t lp = (uint32_t)(i * 32 + p);
             const uint32_t x = lp - lpv - 1, u = x >> kc, rem = x & kmask;
             if ((tl & cmask32) == 0) {
-              const unsigned long long slot = ((t + (tl - (uint32_t)t)) >> clog) - g.gb.chunk0;
+              const unsigned long long slot = ((t + (tl - (uint32_t)t)) >> clog) - gb.chunk0;
               BIC_DCHECK(slot <= (g.N >> clog) + 1);
               g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
               g.index[2 * slot + 1] = (unsigned long long)(tb + lpv + 1);
@@ -510,7 +517,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
               const uint32_t lp = bb + p;
               const uint32_t x = lp - lpv - 1, u = x >> kc, rem = x & kmask;
               if ((tl & cmask32) == 0) {
-                const unsigned long long slot = ((t + (tl - (uint32_t)t)) >> clog) - g.gb.chunk0;
+                const unsigned long long slot = ((t + (tl - (uint32_t)t)) >> clog) - gb.chunk0;
                 BIC_DCHECK(slot <= (g.N >> clog) + 1);
                 g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
                 g.index[2 * slot + 1] = (unsigned long long)(tb + lpv + 1);
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
             const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
             const unsigned long long x = (unsigned long long)(pos - prev - 1);
             if ((t & cmask) == 0) {
-              const unsigned long long slot = (t >> clog) - g.gb.chunk0;
+              const unsigned long long slot = (t >> clog) - gb.chunk0;
               BIC_DCHECK(slot <= (g.N >> clog) + 1);
               g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
               g.index[2 * slot + 1] = (unsigned long long)(prev + 1);
@@ -580,7 +587,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
         const long long pos = tb + i * 32 + p;
         const unsigned long long x = (unsigned long long)(pos - prev - 1);
         const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
-        if ((t & cmask) == 0) { g.index[2 * ((t >> clog) - g.gb.chunk0)] = o + goff; g.index[2 * ((t >> clog) - g.gb.chunk0) + 1] = (unsigned long long)(prev + 1); }
+        if ((t & cmask) == 0) { g.index[2 * ((t >> clog) - gb.chunk0)] = o + goff; g.index[2 * ((t >> clog) - gb.chunk0) + 1] = (unsigned long long)(prev + 1); }
         put_bits(g.out, o, (uint32_t)(x & ((1ull << k) - 1)), k);
         const unsigned long long stop = o + k + (x >> k);
         put_one(g.out, stop);
@@ -590,13 +597,13 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
       }
     }
   }
-  if (g.gb.closing && tile == 0 && threadIdx.x == 0) {                   // the run closed by the virtual one
-    const bool dyn = g.gb.closing == 2;
-    const unsigned long long tt = dyn ? g.info[1] - 1 : g.gb.close_t, consumed = dyn ? g.info[3] : g.gb.close_consumed;
-    unsigned long long oo = (dyn ? g.info[2] : g.gb.close_off) + g.gb.out0;
-    const unsigned long long x = (dyn ? g.N : g.gb.close_n) - consumed;
+  if (gb.closing && tile == 0 && threadIdx.x == 0) {                   // the run closed by the virtual one
+    const bool dyn = gb.closing == 2;
+    const unsigned long long tt = dyn ? g.info[1] - 1 : gb.close_t, consumed = dyn ? g.info[3] : gb.close_consumed;
+    unsigned long long oo = (dyn ? g.info[2] : gb.close_off) + gb.out0;
+    const unsigned long long x = (dyn ? g.N : gb.close_n) - consumed;
     const uint32_t k = golomb_k(tt, consumed);
-    if ((tt & cmask) == 0) { g.index[2 * ((tt >> clog) - g.gb.chunk0)] = oo + goff; g.index[2 * ((tt >> clog) - g.gb.chunk0) + 1] = consumed; }
+    if ((tt & cmask) == 0) { g.index[2 * ((tt >> clog) - gb.chunk0)] = oo + goff; g.index[2 * ((tt >> clog) - gb.chunk0) + 1] = consumed; }
     put_bits(g.out, oo, (uint32_t)(x & ((1ull << k) - 1)), k);
     oo += k + (x >> k);
     put_one(g.out, oo);
@@ -671,6 +678,7 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
     memset(&g.gb, 0, sizeof(g.gb));
     g.gb.prev0 = -1;
     g.gb.closing = 2;                                            // a whole matrix: the closing sample's state comes from info[]
+    g.gbp = nullptr;
     outs[i]->info.coder = BIC_CODER_GOLOMB;
     outs[i]->info.chunk_samples = chunk_samples;
     outs[i]->info.rows = M->rows;
@@ -745,6 +753,7 @@ bic_status bic_g2_plan(bic_ctx* c, const bic_mat* M, void* plan_out, size_t plan
   g.chunk = 256;
   memset(&g.gb, 0, sizeof(g.gb));
   g.gb.prev0 = -1;
+  g.gbp = nullptr;
   return BIC_OK;
 }
 
@@ -792,6 +801,204 @@ bic_status bic_g2_scatter(bic_ctx* c, void* plan, const GolBase* gb, uint32_t ch
   BIC_PROF(c, KID_GOL_SCATTER);
   if (pl->WPT == 16) k_g2_scatter<16><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
   else k_g2_scatter<4><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+
+// ------------------------------------------------------------------ row shards with nothing waiting for the host (pipeline.cu)
+// The prefix state of a shard is computed ON THE DEVICE from what the ranks exchange (two small all-gathers queued on the stream by
+// the caller's hook): base1 after the count pass -- ones / last one / bits of every rank -> t0, pos0, prev0 and the global totals;
+// base2 after the length pass -- every rank's code bits -> code0, out0, chunk0, the closing sample, this shard's info[] and
+// bic_shard_info. all1: [rank][matrix][3] = ones, position after the last one (0: none), bits. all2: [rank][matrix] code bits.
+struct G2ShardAux { unsigned long long ones_global, bits_global, consumed_global, ones_local; };
+
+__global__ void k_g2_shard_base1(const unsigned long long* __restrict__ all1, uint32_t nr, uint32_t rank, uint32_t nmat,
+                                 GolBase* __restrict__ base, G2ShardAux* __restrict__ aux) {
+  const uint32_t i = threadIdx.x;
+  if (i >= nmat) return;
+  GolBase b;
+  memset(&b, 0, sizeof(b));
+  b.prev0 = -1;
+  unsigned long long pos = 0, og = 0;
+  long long lastg = -1;
+  for (uint32_t r = 0; r < nr; ++r) {
+    const unsigned long long* e = all1 + ((size_t)r * nmat + i) * 3;
+    if (r == rank) { b.t0 = og; b.pos0 = (long long)pos; b.prev0 = lastg; aux[i].ones_local = e[0]; }
+    if (e[1]) lastg = (long long)(pos + e[1] - 1);
+    og += e[0];
+    pos += e[2];
+  }
+  aux[i].ones_global = og; aux[i].bits_global = pos; aux[i].consumed_global = (unsigned long long)(lastg + 1);
+  base[i] = b;
+}
+
+struct G2ShardOut { unsigned long long* info[G2_MAXSEG]; unsigned long long cap_bits[G2_MAXSEG]; };
+
+__global__ void k_g2_shard_base2(const unsigned long long* __restrict__ all2, uint32_t nr, uint32_t rank, uint32_t nmat, uint32_t chunk,
+                                 GolBase* __restrict__ base, const G2ShardAux* __restrict__ aux, G2ShardOut o,
+                                 unsigned long long* __restrict__ shard /* 6 per matrix: bic_shard_info */) {
+  const uint32_t i = threadIdx.x;
+  if (i >= nmat) return;
+  GolBase b = base[i];
+  unsigned long long code0 = 0, total = 0;
+  for (uint32_t r = 0; r < nr; ++r) { const unsigned long long v = all2[(size_t)r * nmat + i]; if (r < rank) code0 += v; total += v; }
+  const unsigned long long mine = all2[(size_t)rank * nmat + i];
+  const unsigned long long consumed = aux[i].consumed_global;
+  const uint32_t kc = golomb_k(aux[i].ones_global, consumed);
+  const unsigned long long closing_bits = kc + ((aux[i].bits_global - consumed) >> kc) + 1;
+  b.code0 = code0;
+  b.out0 = code0 & 31;
+  b.chunk0 = (b.t0 + chunk - 1) / chunk;
+  unsigned long long local_bits = mine, local_samples = aux[i].ones_local;
+  b.closing = 0;
+  if (rank == nr - 1) {
+    b.closing = 1;
+    b.close_t = aux[i].ones_global;
+    b.close_consumed = consumed;
+    b.close_off = mine;
+    b.close_n = aux[i].bits_global;
+    local_bits += closing_bits;
+    local_samples += 1;
+  }
+  base[i] = b;
+  const unsigned long long nchunks = (b.t0 + local_samples + chunk - 1) / chunk - b.chunk0;
+  unsigned long long* info = o.info[i];
+  info[0] = b.out0 + local_bits;       // bits of the local buffer, incl. the (code0 & 31) leading pad
+  info[1] = local_samples;
+  info[3] = nchunks;                   // (a shard's chunk count is not ceil(samples / chunk): the caller takes it from here)
+  info[4] = (info[0] + 64 > o.cap_bits[i]) ? 1ull : 0ull;
+  unsigned long long* sh = shard + 6 * i;
+  sh[0] = total + closing_bits;        // global_bitcount
+  sh[1] = aux[i].ones_global + 1;      // global_nsamples
+  sh[2] = code0;                       // code_bit_offset
+  sh[3] = local_bits;                  // local_code_bits
+  sh[4] = b.chunk0;                    // first_chunk
+  sh[5] = nchunks;                     // local_chunks
+}
+
+__global__ void k_g2_pack(const unsigned long long* a0, const unsigned long long* a1, const unsigned long long* a2, unsigned long long* dst, uint32_t n,
+                          uint32_t stride, uint32_t off, unsigned long long n0, unsigned long long n1, unsigned long long n2) {
+  // dst[i * stride + off] = a_i[0]; with stride 3 (pass 1) also the matrix's bit count at + 2 and a_i[1] at + 1
+  const unsigned long long* a[3] = {a0, a1, a2};
+  const unsigned long long nb[3] = {n0, n1, n2};
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    if (stride == 3) { dst[i * 3] = a[i][0]; dst[i * 3 + 1] = a[i][1]; dst[i * 3 + 2] = nb[i]; }
+    else dst[i] = a[i][off];
+  }
+}
+
+bic_status bic_k_golomb_encode_multi_sharded(bic_ctx* c, const bic_mat* const* mats, int nmat, uint32_t chunk_samples, bic_stream* const* outs,
+                                             unsigned long long* d_info, unsigned long long* d_shard, uint32_t nranks, uint32_t rank,
+                                             bic_status (*allgather)(void* user, bic_ctx* c, const unsigned long long* d_src, int count,
+                                                                     unsigned long long* d_dst),
+                                             void* user) {
+  if (nmat < 1 || nmat > G2_MAXSEG || nranks < 1 || nranks > 64) return BIC_ERR_INVALID;
+  G2Params P;
+  memset(&P, 0, sizeof(P));
+  P.nseg = (uint32_t)nmat;
+  uint64_t words_compact = 0, ntiles_total = 0, words_total = 0;
+  uint64_t Ts[G2_MAXSEG], nts[G2_MAXSEG];
+  for (int i = 0; i < nmat; ++i) {
+    const uint64_t N = mats[i]->rows * mats[i]->cols;
+    if (N == 0) return BIC_ERR_INVALID;
+    Ts[i] = div_up_u64(N, 32);
+    words_total += Ts[i];
+    if (mats[i]->cols & 31) words_compact += (Ts[i] + 7) & ~(uint64_t)3;
+  }
+  const int WPT = (words_total / G2_TILE_WORDS(16) >= (uint64_t)c->sm_count * 16) ? 16 : 4;
+  for (int i = 0; i < nmat; ++i) { nts[i] = div_up_u64(Ts[i], (uint64_t)G2_TILE_WORDS(WPT)); ntiles_total += nts[i]; }
+  if (ntiles_total >= (1ull << 31)) return bic_fail(c, BIC_ERR_UNSUPPORTED, "golomb: too many tiles for one launch");
+  if (words_compact) BIC_TRY(bic_scratch_reserve(c, &c->work[4], words_compact * 4 + 64));
+  const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8;
+  // tail of the scratch: counters | base[3] | aux[3] | tot[3][2] | pack1 (3*3) | all1 (nranks*3*3) | pack2 (3) | all2 (nranks*3)
+  const size_t tail = 64 * G2_MAXSEG + sizeof(GolBase) * G2_MAXSEG + sizeof(G2ShardAux) * G2_MAXSEG + 8 * (6 + 9 + 3) + 8 * (size_t)nranks * (9 + 3) + 256;
+  BIC_TRY(bic_scratch_reserve(c, &c->work[5], ntiles_total * per_tile + tail));
+  uint8_t* p = (uint8_t*)c->work[5].p;
+  unsigned int* done = (unsigned int*)p;                     p += 64 * G2_MAXSEG;
+  BIC_CUDA(c, cudaMemsetAsync(done, 0, 64 * G2_MAXSEG, c->stream));
+  GolBase* d_base = (GolBase*)p;                             p += (sizeof(GolBase) * G2_MAXSEG + 15) & ~(size_t)15;
+  G2ShardAux* d_aux = (G2ShardAux*)p;                        p += sizeof(G2ShardAux) * G2_MAXSEG;
+  unsigned long long* d_tot = (unsigned long long*)p;        p += 8 * 6;
+  unsigned long long* d_pack1 = (unsigned long long*)p;      p += 8 * 9;
+  unsigned long long* d_all1 = (unsigned long long*)p;       p += 8 * (size_t)nranks * 9;
+  unsigned long long* d_pack2 = (unsigned long long*)p;      p += 8 * 3;
+  unsigned long long* d_all2 = (unsigned long long*)p;       p += 8 * (size_t)nranks * 3;
+  p = (uint8_t*)(((uintptr_t)p + 63) & ~(uintptr_t)63);
+  uint32_t* compact = (uint32_t*)c->work[4].p;
+  uint32_t tile0 = 0;
+  G2ShardOut so;
+  memset(&so, 0, sizeof(so));
+  for (int i = 0; i < nmat; ++i) {
+    G2Seg& g = P.s[i];
+    const bic_mat* M = mats[i];
+    g.N = M->rows * M->cols;
+    const uint64_t want_bits = g.N / 100 * (uint64_t)c->gol_presize_pct + 32768;
+    BIC_TRY(bic_stream_reserve_for(c, outs[i], want_bits, div_up_u64(g.N + 1, chunk_samples) + 2, 0));
+    if (M->cols & 31) {
+      BIC_TRY(bic_dense_stream_into(c, M, compact, &g.S, &g.T));
+      compact += (Ts[i] + 7) & ~(uint64_t)3;
+    } else {
+      g.S = M->d; g.T = Ts[i];
+    }
+    g.tile0 = tile0; g.ntiles = (uint32_t)nts[i];
+    tile0 += g.ntiles;
+    const size_t nt = nts[i];
+    g.last = (long long*)p;                         p += nt * 8;
+    g.ones_before = (unsigned long long*)p;         p += nt * 8;
+    g.last_before = (long long*)p;                  p += nt * 8;
+    g.bits = (unsigned long long*)p;                p += nt * 8;
+    g.bits_before = (unsigned long long*)p;         p += nt * 8;
+    g.ones = (uint32_t*)p;                          p += nt * 8;
+    g.tbits = (unsigned long long*)p;               p += nt * (size_t)G2_THREADS * 8;
+    g.done = done + 16 * i;
+    g.info = d_info + 8 * i;
+    g.out = (uint32_t*)outs[i]->d_bytes;
+    g.index = (unsigned long long*)outs[i]->d_index;
+    g.cap_bits = (uint64_t)(outs[i]->cap_bytes - 32) * 8;
+    if (c->gol_presize_pct < 100 && g.cap_bits > want_bits) g.cap_bits = want_bits;
+    g.chunk = chunk_samples;
+    memset(&g.gb, 0, sizeof(g.gb));
+    g.gbp = d_base + i;
+    so.info[i] = g.info;
+    so.cap_bits[i] = g.cap_bits;
+    outs[i]->info.coder = BIC_CODER_GOLOMB;
+    outs[i]->info.chunk_samples = chunk_samples;
+    outs[i]->info.rows = M->rows;
+    outs[i]->info.cols = M->cols;
+    outs[i]->info.bitcount = outs[i]->info.nsamples = outs[i]->info.nchunks = 0;
+  }
+  BIC_CUDA(c, cudaMemsetAsync(d_info, 0, 8 * 8 * (size_t)nmat, c->stream));
+  BIC_PROF(c, KID_GOL_TILE_COUNTS);
+  if (WPT == 16) k_g2_count<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  else k_g2_count<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  BIC_LAUNCH_CHECK(c);
+  for (int i = 0; i < nmat; ++i) {
+    k_g2_totals<<<1, 1, 0, c->stream>>>(P.s[i], d_tot + 2 * i);
+    BIC_LAUNCH_CHECK(c);
+  }
+  k_g2_pack<<<1, 32, 0, c->stream>>>(d_tot, d_tot + 2, d_tot + 4, d_pack1, (uint32_t)nmat, 3, 0, P.s[0].N, P.s[1].N, P.s[2].N);
+  BIC_LAUNCH_CHECK(c);
+  BIC_TRY(allgather(user, c, d_pack1, 3 * nmat, d_all1));
+  k_g2_shard_base1<<<1, 32, 0, c->stream>>>(d_all1, nranks, rank, (uint32_t)nmat, d_base, d_aux);
+  BIC_LAUNCH_CHECK(c);
+  BIC_PROF(c, KID_GOL_LENGTHS);
+  if (WPT == 16) k_g2_lengths<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  else k_g2_lengths<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  BIC_LAUNCH_CHECK(c);
+  k_g2_pack<<<1, 32, 0, c->stream>>>(d_info, d_info + 8, d_info + 16, d_pack2, (uint32_t)nmat, 1, 2, 0, 0, 0);
+  BIC_LAUNCH_CHECK(c);
+  BIC_TRY(allgather(user, c, d_pack2, nmat, d_all2));
+  k_g2_shard_base2<<<1, 32, 0, c->stream>>>(d_all2, nranks, rank, (uint32_t)nmat, chunk_samples, d_base, d_aux, so, d_shard);
+  BIC_LAUNCH_CHECK(c);
+  uint64_t maxN = 0;
+  for (int i = 0; i < nmat; ++i) maxN = P.s[i].N > maxN ? P.s[i].N : maxN;
+  BIC_PROF(c, KID_GOL_SCAN_B);
+  k_g2_clear<<<bic_grid_for(c, div_up_u64(maxN, 32) + 4, 256, 4), 256, 0, c->stream>>>(P);
+  BIC_LAUNCH_CHECK(c);
+  BIC_PROF(c, KID_GOL_SCATTER);
+  if (WPT == 16) k_g2_scatter<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+  else k_g2_scatter<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   BIC_LAUNCH_CHECK(c);
   return BIC_OK;
 }

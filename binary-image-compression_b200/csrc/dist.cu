@@ -59,6 +59,7 @@ struct bic_comm {
   int rank = 0, nranks = 1;
   std::vector<uint64_t> nrows;    // rows per rank (set by the first collective that needs them)
   uint64_t row0 = 0, nglobal = 0;
+  uint64_t* d_starts = nullptr;          // device copy of the shard boundaries (nranks + 1 global row indices), for the device-side draw
   uint64_t collectives = 0;
   // peer windows (cudaIpc) for the dictionary update's per-atom exchange: see XPeers in bic_internal.cuh
   int fused = -1;                        // -1 not tried yet, 0 unavailable (NCCL path), 1 windows mapped
@@ -120,6 +121,7 @@ extern "C" bic_status bic_comm_destroy(bic_ctx* c, bic_comm* m) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   window_release(m);
+  if (m->d_starts) cudaFree(m->d_starts);
   if (m->comm) nccl_api()->CommDestroy(m->comm);
   delete m;
   return BIC_OK;
@@ -166,7 +168,18 @@ static bic_status share_rows(bic_ctx* c, bic_comm* m, uint64_t n_local) {
   m->row0 = 0;
   m->nglobal = 0;
   for (int r = 0; r < m->nranks; ++r) { if (r < m->rank) m->row0 += m->nrows[r]; m->nglobal += m->nrows[r]; }
+  std::vector<uint64_t> starts(m->nranks + 1, 0);
+  for (int r = 0; r < m->nranks; ++r) starts[r + 1] = starts[r] + m->nrows[r];
+  if (!m->d_starts) BIC_CUDA(c, cudaMalloc((void**)&m->d_starts, 8 * 65));
+  BIC_CUDA(c, cudaMemcpyAsync(m->d_starts, starts.data(), 8 * (m->nranks + 1), cudaMemcpyHostToDevice, c->stream));
+  BIC_CUDA(c, bic_wait_stream(c));
   return BIC_OK;
+}
+
+// the sharded calls of the pipeline (pipeline.cu) never wait for the host, so the shard boundaries must be known beforehand
+bic_status bic_comm_share_rows(bic_ctx* c, bic_comm* m, uint64_t n_local) { return share_rows(c, m, n_local); }
+bool bic_comm_rows_known(const bic_comm* m, uint64_t n_local) {
+  return (int)m->nrows.size() == m->nranks && m->nrows[m->rank] == n_local && m->d_starts != nullptr;
 }
 
 bic_status bic_k_init_scratch(bic_ctx* c, uint64_t p, uint64_t wpr, InitWork* w);
@@ -232,7 +245,75 @@ extern "C" bic_status bic_dist_initialize_model_neighbor(bic_ctx* c, bic_comm* m
   return bic_k_init_finalize(c, &w, X->cols, D);
 }
 
-// H += Hd; Hd = 0
+bic_status bic_k_init_gather_dev(bic_ctx* c, const bic_mat* X, InitWork* w);
+__global__ void k_draw_pivots(const uint32_t* bitmap, uint64_t n, uint32_t p, uint64_t* state, uint64_t* pivots, unsigned long long* status,
+                              const uint64_t* starts, uint32_t nranks, uint64_t bw, uint32_t my_rank);
+
+// The same with nothing waiting for the host (pipeline.cu): the bitmaps are gathered on the device, the draw runs there over the
+// global row index (init.cu: k_draw_pivots, sharded variant -- every rank replays the same generator), pivot rows and statistics
+// are combined with NCCL calls queued on the stream. d_state: the rand48 state (device u64, in/out, the same on every rank);
+// d_status[0] != 0 afterwards: the whole matrix is zero. bic_comm_share_rows must have been called for this shard size.
+bic_status bic_k_dist_init_async(bic_ctx* c, bic_comm* m, const bic_mat* X, bic_mat* D, bic_mat* A, uint64_t* d_state,
+                                 unsigned long long* d_status) {
+  const uint64_t p = D->rows;
+  if (D->cols != X->cols || A->rows != X->rows || A->cols != p)
+    return bic_fail(c, BIC_ERR_INVALID, "init: shapes must be X n x m, D p x m, A n x p");
+  if (!bic_comm_rows_known(m, X->rows)) return bic_fail(c, BIC_ERR_INVALID, "init: shard sizes not exchanged (bic_comm_share_rows)");
+  if (m->nglobal == 0 || m->nglobal > 0xFFFFFFFFull) return bic_fail(c, BIC_ERR_INVALID, "init: row count outside gsl_rng_uniform_int's range");
+  BIC_TRY(bic_mat_clear(c, A));
+  BIC_TRY(bic_mat_clear(c, D));
+  if (p == 0 || X->cols == 0) return BIC_OK;
+  uint64_t maxn = 0;
+  for (uint64_t v : m->nrows) maxn = v > maxn ? v : maxn;
+  const uint64_t bw = div_up_u64(maxn, 32);
+  BIC_TRY(bic_scratch_reserve(c, &c->work[0], (size_t)bw * 4 * m->nranks + 16));
+  uint32_t* d_bm = (uint32_t*)c->work[0].p;
+  BIC_CUDA(c, cudaMemsetAsync(d_bm, 0, (size_t)bw * 4 * m->nranks, c->stream));
+  BIC_TRY(bic_k_row_nonzero_bitmap(c, X, d_bm + (size_t)m->rank * bw));
+  if (m->nranks > 1) {
+    BIC_NCCL(c, nccl_api()->AllGather(d_bm + (size_t)m->rank * bw, d_bm, bw, ncclUint32, m->comm, c->stream));
+    m->collectives++;
+  }
+  InitWork w;
+  BIC_TRY(bic_k_init_scratch(c, p, X->wpr, &w));
+  k_draw_pivots<<<1, 256, 0, c->stream>>>(d_bm, m->nglobal, (uint32_t)p, d_state, w.piv, d_status, m->d_starts, (uint32_t)m->nranks, bw,
+                                          (uint32_t)m->rank);
+  BIC_LAUNCH_CHECK(c);
+  BIC_TRY(bic_k_init_gather_dev(c, X, &w));
+  BIC_TRY(allreduce_u32(c, m, w.P, (size_t)p * X->wpr));          // each pivot row has exactly one owner
+  BIC_TRY(bic_k_init_stats(c, X, &w));
+  BIC_TRY(allreduce_u32(c, m, w.hist, (size_t)X->wpr * 32 + p));  // hist and usage are adjacent
+  return bic_k_init_finalize(c, &w, X->cols, D);
+}
+
+// ---- sharded Golomb coding with nothing waiting for the host: coding2.cu runs the passes, the two exchanges are NCCL all-gathers
+// queued on the same stream
+bic_status bic_k_golomb_encode_multi_sharded(bic_ctx* c, const bic_mat* const* mats, int nmat, uint32_t chunk_samples, bic_stream* const* outs,
+                                             unsigned long long* d_info, unsigned long long* d_shard, uint32_t nranks, uint32_t rank,
+                                             bic_status (*allgather)(void* user, bic_ctx* c, const unsigned long long* d_src, int count,
+                                                                     unsigned long long* d_dst),
+                                             void* user);
+static bic_status allgather_u64_dev(void* user, bic_ctx* c, const unsigned long long* d_src, int count, unsigned long long* d_dst) {
+  bic_comm* m = (bic_comm*)user;
+  if (m->nranks == 1) {
+    BIC_CUDA(c, cudaMemcpyAsync(d_dst, d_src, 8 * (size_t)count, cudaMemcpyDeviceToDevice, c->stream));
+    return BIC_OK;
+  }
+  BIC_NCCL(c, nccl_api()->AllGather(d_src, d_dst, (size_t)count, ncclUint64, m->comm, c->stream));
+  m->collectives++;
+  return BIC_OK;
+}
+bic_status bic_k_dist_golomb_async(bic_ctx* c, bic_comm* m, const bic_mat* const* mats, int nmat, uint32_t chunk_samples,
+                                   bic_stream* const* outs, unsigned long long* d_info, unsigned long long* d_shard) {
+  return bic_k_golomb_encode_multi_sharded(c, mats, nmat, chunk_samples, outs, d_info, d_shard, (uint32_t)m->nranks, (uint32_t)m->rank,
+                                           allgather_u64_dev, m);
+}
+
+// ---- the dictionary update of a sharded learner iteration, queued (no host wait): dist_update_dictionary's chain path + the
+// global changed-rows count joined back into d_counts[0]
+bic_status bic_k_dist_iteration_dict(bic_ctx* c, bic_comm* m, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_counts);
+
+// H += Hd; Hd = 0// H += Hd; Hd = 0// H += Hd; Hd = 0
 __global__ void k_apply_corrections(uint32_t* __restrict__ H, uint32_t* __restrict__ Hd, uint64_t nwords) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t d = Hd[i];
@@ -496,3 +577,27 @@ extern "C" bic_status bic_dist_learn_model_traditional(bic_ctx* c, bic_comm* m, 
   if (iterations) *iterations = iter;
   return BIC_OK;
 }
+
+
+bic_status bic_k_dist_iteration_dict(bic_ctx* c, bic_comm* m, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_counts) {
+  uint64_t maxn = E->rows;
+  for (uint64_t v : m->nrows) maxn = v > maxn ? v : maxn;
+  if (!(c->dict_algo == 2 && bic_dict_chain_eligible(c, maxn, D->rows, E->wpr)) || (m->nranks > 1 && m->fused != 1))
+    return bic_fail(c, BIC_ERR_UNSUPPORTED, "sharded pipeline: the dictionary update must take the cluster-chain path with peer windows");
+  BIC_TRY(dist_update_dictionary(c, m, E, D, A, d_counts));
+  k_join_u64_limbs<<<1, 1, 0, c->stream>>>(m->last_extra, d_counts);   // the changed-rows count summed over the ranks
+  BIC_LAUNCH_CHECK(c);
+  return BIC_OK;
+}
+
+// first use of a shape on a communicator: shard sizes and the peer window (both block and are collective: every rank calls this
+// for its slots in the same order, before any job of that shape is queued)
+bic_status bic_k_dist_prepare(bic_ctx* c, bic_comm* m, uint64_t n_local, uint64_t p, uint64_t wprE, uint64_t wprA) {
+  BIC_TRY(share_rows(c, m, n_local));
+  if (m->nranks > 1) {
+    const size_t hwords = (size_t)p * wprE * 32;
+    BIC_TRY(window_reserve(c, m, hwords + p + wprA * 32 + 4 + 128 + 2 * (size_t)m->nranks * hwords));
+  }
+  return BIC_OK;
+}
+bool bic_k_dist_fused(const bic_comm* m) { return m->nranks == 1 || m->fused == 1; }

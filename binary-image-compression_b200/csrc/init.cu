@@ -42,10 +42,14 @@ bic_status bic_k_row_nonzero_bitmap(bic_ctx* c, const bic_mat* X, uint32_t* d_bi
 // bitmap lookup per lane; accepted rows are taken in lane (= draw) order until p pivots exist, and the generator is left
 // exactly after the draw that produced the last one. status[0] = 1 if X has no nonzero row (the reference would never
 // return), status[1] = draws of the outer loop (accepted + rejected zero rows).
+// Row-sharded variant (starts != nullptr): the draw runs over the GLOBAL row index of the concatenated shards; `bitmap` holds
+// every rank's zero-row bitmap, bw words each, and starts[r] is the global index of rank r's first row. Every rank replays the
+// same draw; pivots[k] receives the LOCAL row index where this rank owns the row and ~0 elsewhere.
 __global__ void __launch_bounds__(256) k_draw_pivots(const uint32_t* __restrict__ bitmap, uint64_t n, uint32_t p,
                                                      uint64_t* __restrict__ state, uint64_t* __restrict__ pivots,
-                                                     unsigned long long* __restrict__ status) {
-  const uint64_t nw = (n + 31) >> 5;
+                                                     unsigned long long* __restrict__ status, const uint64_t* __restrict__ starts = nullptr,
+                                                     uint32_t nranks = 1, uint64_t bw = 0, uint32_t my_rank = 0) {
+  const uint64_t nw = starts ? (uint64_t)nranks * bw : (n + 31) >> 5;
   int any = 0;
   for (uint64_t i = threadIdx.x; i < nw; i += blockDim.x) any |= (bitmap[i] != 0);
   any = __syncthreads_or(any);
@@ -66,11 +70,19 @@ __global__ void __launch_bounds__(256) k_draw_pivots(const uint32_t* __restrict_
     const uint64_t s = (base * a + cc) & M48;
     const uint64_t k = (s >> 16) / scale;
     const bool in_range = k < n;                       // else uniform_int draws again: a generator step, not a draw of the loop
-    const bool nz = in_range && ((bitmap[k >> 5] >> (k & 31)) & 1u);
+    uint64_t bit = k, local = k;                       // where row k's bit sits in `bitmap`, and the row's index on its owner
+    uint32_t owner = my_rank;
+    if (starts && in_range) {
+      owner = 0;
+      while (owner + 1 < nranks && k >= starts[owner + 1]) ++owner;
+      local = k - starts[owner];
+      bit = (uint64_t)owner * bw * 32 + local;
+    }
+    const bool nz = in_range && ((bitmap[bit >> 5] >> (bit & 31)) & 1u);
     const uint32_t vmask = __ballot_sync(0xffffffffu, nz), rmask = __ballot_sync(0xffffffffu, in_range);
     const uint32_t need = p - got, cnt = (uint32_t)__popc(vmask);
     const uint32_t rank = (uint32_t)__popc(vmask & ((1u << lane) - 1u));
-    if (nz && rank < need) pivots[got + rank] = k;
+    if (nz && rank < need) pivots[got + rank] = (owner == my_rank) ? local : ~0ull;
     if (cnt >= need) {
       const unsigned L = __fns(vmask, 0, (int)need);   // lane of the draw that gave the last pivot
       base = __shfl_sync(0xffffffffu, s, L);

@@ -29,6 +29,16 @@ bic_status bic_golomb_async_finish(bic_stream* out, const uint64_t* host_info);
 bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int nmat, uint32_t chunk_samples, bic_stream* const* outs,
                                      unsigned long long* d_info);
 
+struct bic_comm;
+bic_status bic_k_dist_prepare(bic_ctx* c, bic_comm* m, uint64_t n_local, uint64_t p, uint64_t wprE, uint64_t wprA);
+bool bic_k_dist_fused(const bic_comm* m);
+bic_status bic_k_dist_init_async(bic_ctx* c, bic_comm* m, const bic_mat* X, bic_mat* D, bic_mat* A, uint64_t* d_state, unsigned long long* d_status);
+bic_status bic_k_dist_iteration_dict(bic_ctx* c, bic_comm* m, bic_mat* E, bic_mat* D, const bic_mat* A, unsigned long long* d_counts);
+bic_status bic_k_dist_golomb_async(bic_ctx* c, bic_comm* m, const bic_mat* const* mats, int nmat, uint32_t chunk_samples,
+                                   bic_stream* const* outs, unsigned long long* d_info, unsigned long long* d_shard);
+int bic_comm_rank(const bic_comm* m);
+int bic_comm_size(const bic_comm* m);
+
 #define LOOP_TRACE 64
 struct LoopState {
   uint32_t done, iter;            // done: the loop has ended; iterations queued after that do nothing
@@ -78,7 +88,7 @@ struct Job {
 };
 
 // device words of a slot's status block
-enum { SW_RNG = 0, SW_ALLZERO = 1, SW_DRAWS = 2, SW_INFO = 8, SW_WORDS = 32 };
+enum { SW_RNG = 0, SW_ALLZERO = 1, SW_DRAWS = 2, SW_INFO = 8, SW_SHARD = 32, SW_WORDS = 48 };
 
 struct HostMirror {
   uint64_t status[SW_WORDS];
@@ -98,6 +108,8 @@ struct Slot {
   Job* job = nullptr;
   Stage stage = ST_IDLE;
   bool async_ok = false;
+  bic_comm* comm = nullptr;           // sharded mode: this slot's communicator (the same slot index on every rank)
+  std::deque<Job*> queue;             // sharded mode: jobs are dealt to slots by their sequence number, identically on every rank
 };
 
 }  // namespace
@@ -111,6 +123,8 @@ struct bic_pipeline {
   uint64_t in_flight = 0;
   int first_batch = 2, next_batch = 2;
   uint64_t polls = 0, batches = 0, sync_fallbacks = 0, recodes = 0;
+  bool sharded = false;               // every job is one rank's row shard of a matrix that all ranks fit together
+  uint64_t seq = 0;                   // jobs submitted so far (sharded mode: job q runs on slot q % nslots)
   std::string err;
 };
 
@@ -136,6 +150,13 @@ static bic_status slot_prepare(Slot& s, uint64_t rows, uint64_t cols, uint64_t W
   s.rows = rows; s.cols = cols; s.W = W; s.K = K;
   s.async_ok = c->dict_algo == 2 && c->dict_update == 0 && n > 0 && n <= 0xFFFFFFFFull && K > 0 && K <= 65535 &&
                bic_dict_chain_eligible(c, n, K, s.E->wpr);
+  if (s.comm) {
+    // first raster of this shape on this slot: shard sizes and the peer window are exchanged now (blocking, collective -- every
+    // rank gets here for the same slot in the same order, see bic_pipeline_attach_comms)
+    if (!s.async_ok) return bic_fail(c, BIC_ERR_UNSUPPORTED, "sharded pipeline: the shape must be one the cluster-chain update takes");
+    BIC_TRY(bic_k_dist_prepare(c, s.comm, n, K, s.E->wpr, s.A->wpr));
+    if (!bic_k_dist_fused(s.comm)) return bic_fail(c, BIC_ERR_UNSUPPORTED, "sharded pipeline: the ranks cannot map each other's memory");
+  }
   return BIC_OK;
 }
 
@@ -163,7 +184,10 @@ static bic_status learn_enqueue(Slot& s, bool first, int niter) {
   bic_status st = BIC_OK;
   for (int i = 0; i < niter && st == BIC_OK; ++i) {
     st = bic_k_update_coefficients(c, s.E, s.D, s.A, d_cc);                    // :1229
-    if (st == BIC_OK) st = bic_k_update_dictionary_v3(c, s.E, s.D, s.A, d_cc + 1);  // :1235
+    if (st == BIC_OK) {                                                        // :1235
+      if (s.comm) st = bic_k_dist_iteration_dict(c, s.comm, s.E, s.D, s.A, d_cc);   // statistics summed over the ranks, d_cc[0] made global
+      else st = bic_k_update_dictionary_v3(c, s.E, s.D, s.A, d_cc + 1);
+    }
     if (st == BIC_OK) {
       k_loop_end<<<1, 1, 0, c->stream>>>(s.d_loop, d_cc);
       c->launches++;
@@ -202,6 +226,7 @@ static void job_start(bic_pipeline* P, Slot& s, Job* j) {
   st = bic_extract_patches(c, rast, j->W, s.X);                                  // src/bsvd_test.cpp:80-99
   if (st != BIC_OK) return job_finish(P, s, st);
   if (!s.async_ok) {
+    if (s.comm) return job_finish(P, s, BIC_ERR_UNSUPPORTED, "sharded pipeline: shape outside the asynchronous path");
     P->sync_fallbacks++;
     st = encode_sync(s, j, rast);
     return job_finish(P, s, st);
@@ -209,7 +234,8 @@ static void job_start(bic_pipeline* P, Slot& s, Job* j) {
   bic_rand48_seed(&s.h->rng_in, j->seed);                                        // -r / random_seed, src/bsvd.cpp:12
   if (cudaMemcpyAsync(s.d_status + SW_RNG, &s.h->rng_in, 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
     return job_finish(P, s, BIC_ERR_CUDA, "cudaMemcpyAsync");
-  st = bic_k_init_neighbor_async(c, s.X, s.D, s.A, s.d_status + SW_RNG, (unsigned long long*)(s.d_status + SW_ALLZERO));  // :114
+  if (s.comm) st = bic_k_dist_init_async(c, s.comm, s.X, s.D, s.A, s.d_status + SW_RNG, (unsigned long long*)(s.d_status + SW_ALLZERO));
+  else st = bic_k_init_neighbor_async(c, s.X, s.D, s.A, s.d_status + SW_RNG, (unsigned long long*)(s.d_status + SW_ALLZERO));  // :114
   if (st == BIC_OK) st = learn_enqueue(s, true, P->first_batch);                 // :119
   if (st == BIC_OK) st = mirror_and_mark(s, false);
   if (st != BIC_OK) return job_finish(P, s, st);
@@ -253,6 +279,71 @@ static bic_status encode_sync(Slot& s, Job* j, const bic_mat* rast) {
   return BIC_OK;
 }
 
+// A sharded job's output ("shard container"), little-endian u64 fields:
+//   [0] magic "BICSHRD\0" [1] version [2] rank [3] ranks [4] rows (this rank's band) [5] cols [6] W [7] K [8] n (local patches) [9] m
+//   [10] iterations [11] seed, [12 + 7 i ...) per stream (D, A, E) coder, chunk_samples, rows, cols, bits of the local buffer,
+//   local samples, local chunk-index entries; [33 + 6 j ...) for A and E the bic_shard_info fields (global bit count, global samples,
+//   code bit offset, local code bits, first chunk, local chunks); then per stream the bytes padded to 8 and the chunk index.
+//   The global stream of A (of E) is the word-wise OR of the ranks' buffers placed at 32-bit word (code bit offset >> 5).
+static const uint64_t BIC_SHARD_MAGIC = 0x0044524853434942ull;  // "BICSHRD\0"
+static const uint64_t SHARD_HDR_U64 = 48;
+
+static void slot_finish_sharded(bic_pipeline* P, Slot& s) {
+  bic_ctx* c = s.c;
+  Job* j = s.job;
+  bic_status st = bic_golomb_async_finish(s.st[0], s.h->status + SW_INFO);
+  if (st != BIC_OK) return job_finish(P, s, st, "sharded pipeline: the dictionary's code did not fit its buffer");
+  for (int i = 1; i < 3; ++i) {
+    const uint64_t* info = s.h->status + SW_INFO + 8 * i;
+    if (info[4]) return job_finish(P, s, BIC_ERR_CAPACITY, "sharded pipeline: a shard's code did not fit its pre-sized buffer (raise gol_presize_pct)");
+    s.st[i]->info.bitcount = info[0];
+    s.st[i]->info.nsamples = info[1];
+    s.st[i]->info.nchunks = info[3];
+  }
+  const uint64_t* shA = s.h->status + SW_SHARD;
+  const uint64_t* shE = s.h->status + SW_SHARD + 6;
+  bic_stream_info si[3];
+  for (int i = 0; i < 3; ++i) si[i] = s.st[i]->info;
+  uint64_t need = SHARD_HDR_U64 * 8;
+  for (int i = 0; i < 3; ++i) need += div_up_u64(div_up_u64(si[i].bitcount, 8), 8) * 8 + si[i].nchunks * 16;
+  const bic_mat* rast = j->payload ? s.raster : j->raster;
+  if (j->info) {
+    bic_encode_info* info = j->info;
+    memset(info, 0, sizeof(*info));
+    info->rows = rast->rows; info->cols = rast->cols; info->W = j->W; info->K = j->K; info->n = s.X->rows; info->m = s.X->cols;
+    info->iterations = s.h->loop.iters;
+    info->bits_D = si[0].bitcount; info->bits_A = shA[0]; info->bits_E = shE[0];          // A, E: of the ONE global stream
+    info->weight_D = si[0].nsamples - 1; info->weight_A = shA[1] - 1; info->weight_E = shE[1] - 1;
+    info->container_bytes = need;
+  }
+  if (!j->out) return job_finish(P, s, BIC_OK);
+  if (j->cap < need) return job_finish(P, s, BIC_ERR_CAPACITY, "encode: container larger than the caller's buffer");
+  if (((uintptr_t)j->out & 7) != 0) return job_finish(P, s, BIC_ERR_INVALID, "encode: out must be 8-byte aligned");
+  uint64_t* h = (uint64_t*)j->out;
+  memset(h, 0, SHARD_HDR_U64 * 8);
+  h[0] = BIC_SHARD_MAGIC; h[1] = 1; h[2] = (uint64_t)bic_comm_rank(s.comm); h[3] = (uint64_t)bic_comm_size(s.comm);
+  h[4] = rast->rows; h[5] = rast->cols; h[6] = j->W; h[7] = j->K; h[8] = s.X->rows; h[9] = s.X->cols; h[10] = s.h->loop.iters; h[11] = (uint64_t)j->seed;
+  for (int i = 0; i < 3; ++i) {
+    uint64_t* f = h + 12 + 7 * i;
+    f[0] = si[i].coder; f[1] = si[i].chunk_samples; f[2] = si[i].rows; f[3] = si[i].cols; f[4] = si[i].bitcount; f[5] = si[i].nsamples; f[6] = si[i].nchunks;
+  }
+  memcpy(h + 33, shA, 6 * 8);
+  memcpy(h + 39, shE, 6 * 8);
+  uint64_t off = SHARD_HDR_U64 * 8;
+  for (int i = 0; i < 3; ++i) {
+    const uint64_t nb = div_up_u64(si[i].bitcount, 8), nbp = div_up_u64(nb, 8) * 8;
+    cudaError_t e = cudaSuccess;
+    if (nbp > nb) memset(j->out + off + nb, 0, nbp - nb);   // (the copy below never touches the pad bytes)
+    if (nb) e = cudaMemcpyAsync(j->out + off, s.st[i]->d_bytes, nb, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && si[i].nchunks)
+      e = cudaMemcpyAsync(j->out + off + nbp, s.st[i]->d_index, si[i].nchunks * 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) return job_finish(P, s, BIC_ERR_CUDA, cudaGetErrorString(e));
+    off += nbp + si[i].nchunks * 16;
+  }
+  if (cudaEventRecord(s.ev, c->stream) != cudaSuccess) return job_finish(P, s, BIC_ERR_CUDA, "cudaEventRecord");
+  s.stage = ST_COPY;
+}
+
 static void slot_advance(bic_pipeline* P, Slot& s) {
   BIC_RANGE("bic:pipeline:advance");
   bic_ctx* c = s.c;
@@ -268,7 +359,13 @@ static void slot_advance(bic_pipeline* P, Slot& s) {
       return;
     }
     const bic_mat* mats[3] = {s.D, s.A, s.E};
-    if (c->gol_algo == 2) {                      // D, A and E in one set of launches (coding2.cu)
+    if (s.comm) {
+      // D is replicated: every rank codes the same stream; A and E are row shards of ONE global stream each
+      st = bic_k_golomb_encode_multi(c, mats, 1, 256, s.st, (unsigned long long*)(s.d_status + SW_INFO));
+      if (st == BIC_OK)
+        st = bic_k_dist_golomb_async(c, s.comm, mats + 1, 2, 256, s.st + 1, (unsigned long long*)(s.d_status + SW_INFO + 8),
+                                     (unsigned long long*)(s.d_status + SW_SHARD));
+    } else if (c->gol_algo == 2) {               // D, A and E in one set of launches (coding2.cu)
       st = bic_k_golomb_encode_multi(c, mats, 3, 256, s.st, (unsigned long long*)(s.d_status + SW_INFO));
     } else {
       for (int i = 0; i < 3 && st == BIC_OK; ++i)
@@ -279,6 +376,7 @@ static void slot_advance(bic_pipeline* P, Slot& s) {
     s.stage = ST_CODE;
     return;
   }
+  if (s.stage == ST_CODE && s.comm) return slot_finish_sharded(P, s);
   if (s.stage == ST_CODE) {
     const bic_mat* mats[3] = {s.D, s.A, s.E};
     bic_stream_info si[3];
@@ -319,6 +417,7 @@ static void slot_advance(bic_pipeline* P, Slot& s) {
     s.stage = ST_COPY;
     return;
   }
+  if (s.stage == ST_COPY && s.comm) return job_finish(P, s, BIC_OK);   // the header was written before the copies were queued
   if (s.stage == ST_COPY) {
     bic_stream_info si[3];
     for (int i = 0; i < 3; ++i) si[i] = s.st[i]->info;
@@ -388,7 +487,9 @@ static bic_status submit(bic_pipeline* P, Job* j, uint64_t* id_out) {
   j->id = P->next_id++;
   if (id_out) *id_out = j->id;
   P->jobs.emplace_back(j);
-  P->pending.push_back(j);
+  if (P->sharded) P->slots[P->seq % P->slots.size()].queue.push_back(j);   // the same slot (= communicator) on every rank
+  else P->pending.push_back(j);
+  P->seq++;
   return BIC_OK;
 }
 
@@ -430,13 +531,16 @@ extern "C" bic_status bic_pipeline_poll(bic_pipeline* P, uint64_t* in_flight) {
       if (e != cudaSuccess) { job_finish(P, s, BIC_ERR_CUDA, cudaGetErrorString(e)); continue; }
       slot_advance(P, s);
     }
-    while (s.stage == ST_IDLE && !P->pending.empty()) {   // a job that finishes inside job_start (error, synchronous shape) frees the slot again
-      Job* j = P->pending.front();
-      P->pending.pop_front();
+    std::deque<Job*>& q = P->sharded ? s.queue : P->pending;
+    while (s.stage == ST_IDLE && !q.empty()) {   // a job that finishes inside job_start (error, synchronous shape) frees the slot again
+      Job* j = q.front();
+      q.pop_front();
       job_start(P, s, j);
     }
   }
-  if (in_flight) *in_flight = P->in_flight + P->pending.size();
+  uint64_t waiting = P->pending.size();
+  for (auto& s : P->slots) waiting += s.queue.size();
+  if (in_flight) *in_flight = P->in_flight + waiting;
   return BIC_OK;
 }
 
@@ -492,5 +596,26 @@ extern "C" bic_status bic_pipeline_wait_ctx(bic_pipeline* P, bic_ctx* signal) {
 extern "C" bic_status bic_ctx_wait_pipeline(bic_ctx* waiter, bic_pipeline* P) {
   if (!P || !waiter) return BIC_ERR_INVALID;
   for (auto& s : P->slots) BIC_TRY(bic_ctx_wait_ctx(waiter, s.c));
+  return BIC_OK;
+}
+
+
+// ---- sharded mode: every job is this rank's row shard (a band of the raster) of ONE matrix that all ranks fit together with one
+// dictionary (csrc/dist.cu). Slot i of every rank shares communicator i: create them with bic_comm_create on
+// bic_pipeline_slot_ctx(p, i) (ids exchanged by the caller's plumbing), attach them, and from then on submit the SAME jobs in the
+// SAME order on every rank -- job q runs on slot q % nslots everywhere. A job's output is a shard container (see above).
+extern "C" bic_ctx* bic_pipeline_slot_ctx(bic_pipeline* P, int slot) {
+  if (!P || slot < 0 || slot >= (int)P->slots.size()) return nullptr;
+  return P->slots[slot].c;
+}
+extern "C" bic_status bic_pipeline_attach_comms(bic_pipeline* P, bic_comm* const* comms, int n) {
+  if (!P || !comms || n != (int)P->slots.size()) return BIC_ERR_INVALID;
+  if (P->in_flight || !P->pending.empty()) return BIC_ERR_INVALID;
+  for (int i = 0; i < n; ++i) {
+    if (!comms[i]) return BIC_ERR_INVALID;
+    P->slots[i].comm = comms[i];
+  }
+  P->sharded = true;
+  P->seq = 0;
   return BIC_OK;
 }

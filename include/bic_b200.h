@@ -386,6 +386,18 @@ bic_status bic_pipeline_job_status(bic_pipeline* p, uint64_t job, int* done, con
 bic_status bic_pipeline_forget_finished(bic_pipeline* p);
 bic_status bic_pipeline_stats(bic_pipeline* p, uint64_t* launches, uint64_t* polls, uint64_t* batches, uint64_t* sync_fallbacks,
                               uint64_t* recodes);
+/* Sharded mode: every job is THIS RANK'S ROW SHARD (a band of the raster, rank order = row order) of one matrix that all ranks
+ * fit together with ONE dictionary: bic_dist_* semantics (src/bsvd.cpp:227-267, 463-527, 1215-1244 over the concatenated rows),
+ * with nothing waiting for the host -- the pivot draw replays rand48 on the device over the gathered zero-row bitmaps, the
+ * statistics are combined by NCCL calls queued on the slot's stream, the per-changed-atom corrections go over NVLink peer memory
+ * inside the chain kernel, the shard's Golomb prefix state is computed on the device from two small all-gathers. Slot i of every
+ * rank shares communicator i: create them with bic_comm_create(bic_pipeline_slot_ctx(p, i), ...), attach, then submit the SAME
+ * jobs in the SAME order on every rank (job q runs on slot q % nslots everywhere). Output per job: a "shard container" (header
+ * with the bic_shard_info of A and E, then this rank's D stream, A shard and E shard; layout in csrc/pipeline.cu);
+ * info->bits_A / bits_E / weight_* are those of the global streams, identical on every rank. */
+struct bic_comm;
+bic_ctx* bic_pipeline_slot_ctx(bic_pipeline* p, int slot);
+bic_status bic_pipeline_attach_comms(bic_pipeline* p, struct bic_comm* const* comms, int n);
 /* stream ordering against a context outside the pool: every slot after `signal` / `waiter` after every slot */
 bic_status bic_pipeline_wait_ctx(bic_pipeline* p, bic_ctx* signal);
 bic_status bic_ctx_wait_pipeline(bic_ctx* waiter, bic_pipeline* p);

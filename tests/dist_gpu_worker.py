@@ -69,6 +69,57 @@ def main():
                 assert int(idx[0][0]) >= lo and int(idx[-1][0]) < lo + ln
         for mm in (X, D, A, E):
             mm.destroy()
+    # ---- the sharded PIPELINE (csrc/pipeline.cu, sharded mode): several rasters in flight on one host thread per rank, every raster's
+    # patch rows sharded over the ranks; against the oracle's single-process fit + serial coder of the whole raster
+    def share(uid):
+        t = torch.from_numpy(uid if uid is not None else np.zeros(128, np.uint8)).cuda()
+        dist.broadcast(t, 0)
+        return t.cpu().numpy()
+
+    pipe = bic.Pipeline(local, 3)
+    pipe.make_sharded(rank, world, share)
+    W, K = 8, 16
+    cases = []
+    for s_ in range(7):
+        rows_band, cols = 96 + 8 * (s_ % 3), 128     # every rank's band of raster s_ (the same height on every rank)
+        if s_ % 3 == 2:
+            whole = (np.random.default_rng(100 + s_).random((rows_band * world, cols)) < 0.45).astype(np.uint8)
+        else:
+            whole = synth.structured_page(rows_band * world, cols, seed=60 + s_, salt=0.01)
+        cases.append((rows_band, cols, whole))
+    jobs = []
+    for rows_band, cols, whole in cases:
+        band = whole[rank * rows_band: (rank + 1) * rows_band]
+        pay = ctx.pinned(rows_band * cols // 8)
+        pay[:] = synth.pbm_bytes(band).reshape(-1)
+        out = ctx.pinned(1 << 18)
+        job, info = pipe.submit(pay, rows_band, cols, W, K, seed=900, out=out)
+        jobs.append((job, info, out, pay))
+    pipe.wait()
+    for (job, info, out, pay), (rows_band, cols, whole) in zip(jobs, cases):
+        done, st, msg = pipe.status(job)
+        assert done and st == 0, f"rank {rank}: sharded pipeline job failed: {msg}"
+        Xw = oracle.extract_patches(synth.pack_rows(whole), rows_band * world, cols, W)
+        m = W * W
+        Do, Ao, _ = oracle.init_neighbor(Xw, m, K, 900)
+        Eo, ito, _ = oracle.learn_traditional(Xw, Do, Ao, m, K)
+        sc = bic.Pipeline.parse_shard_container(out[: int(info.container_bytes)])
+        assert sc["iterations"] == ito == int(info.iterations), (rank, sc["iterations"], ito)
+        sD, nbD, _ = oracle.golomb_encode(Do, m)
+        assert sc["streams"]["D"]["local_bits"] == nbD and np.array_equal(sc["streams"]["D"]["bytes"], sD), f"rank {rank}: D stream differs"
+        for name, Mo, cols_ in (("A", Ao, K), ("E", Eo, m)):
+            so, nbits, ns = oracle.golomb_encode(Mo, cols_)
+            stt = sc["streams"][name]
+            assert stt["global_bitcount"] == nbits and stt["global_nsamples"] == ns, (rank, name, stt["global_bitcount"], nbits)
+            gbits = np.unpackbits(so)[:nbits]
+            lo, ln = stt["code_bit_offset"], stt["local_code_bits"]
+            mine = np.unpackbits(stt["bytes"])[lo % 32: lo % 32 + ln]
+            assert np.array_equal(mine, gbits[lo: lo + ln]), f"rank {rank}: {name} shard substring differs at bit offset {lo}"
+            assert stt["local_bits"] == lo % 32 + ln
+            if rank == world - 1:
+                assert lo + ln == nbits
+        assert int(info.bits_A) == oracle.golomb_encode(Ao, K)[1] and int(info.bits_E) == oracle.golomb_encode(Eo, m)[1]
+    pipe.close()
     if rank == 0:
         print(f"dist ok world={world} collectives={ctx.comm_collectives(comm)}")
     dist.barrier()
