@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--e2e-planes", action="store_true", help="e2e from 16 host P4 planes (bic_encode_raster) instead of the 16-bit P5 payload")
     ap.add_argument("--sharded", action="store_true", help="also time the row-sharded (NCCL) fit at N=1")
     ap.add_argument("--streams", type=int, default=24, help="encoder slots (CUDA streams) per GPU")
+    ap.add_argument("--sharded-slots", type=int, default=16, help="row-sharded fit: sharded planes in flight per rank in the pipeline (one host thread)")
+    ap.add_argument("--sharded-threads", action="store_true", help="row-sharded fit through the synchronous bic_dist_* calls, one host thread per plane in flight, instead of the sharded pipeline")
     ap.add_argument("--sharded-streams", type=int, default=8, help="row-sharded fit: planes in flight per rank (one communicator + host thread each)")
     ap.add_argument("--sharded-cluster", type=int, default=8, help="row-sharded fit: CTAs per cluster of the chain kernel (it waits for the peers inside)")
     ap.add_argument("--pool", action="store_true", help="round-1 driver: one host thread per context instead of the single-thread pipeline")
@@ -532,7 +534,115 @@ def main():
     # another such kernel, and CUDA deals streams to its 32 connections in creation order.)
     px_step = P * rows * cols / 1e6  # Mpixel per rank per step
     sharded = None
-    if world > 1 or args.sharded:
+    if (world > 1 or args.sharded) and not args.sharded_threads:
+        # ---- the sharded PIPELINE: ONE host thread per rank keeps `sharded_slots` sharded planes in flight (csrc/pipeline.cu, sharded
+        # mode): nothing waits for the host -- the pivot draw runs on the device over the gathered zero-row bitmaps, NCCL calls are
+        # queued on the slot streams, the Golomb shard base is computed on the device
+        def share(uid):
+            t = torch.from_numpy(uid if uid is not None else np.zeros(128, np.uint8)).to(dev)
+            if dist is not None:
+                dist.broadcast(t, 0)
+            return t.cpu().numpy()
+
+        NSL = max(1, min(args.sharded_slots, P))
+        shp = bic.Pipeline(local_rank, NSL)
+        for name, val in (("first_batch", args.first_batch), ("next_batch", args.next_batch), ("dict_algo", args.dict_algo),
+                          ("chain_cluster", args.sharded_cluster)):
+            shp.set_option(name, val)
+        shp.make_sharded(rank, world, share)
+        sh_outs = [ctx.pinned(2 * plane_bytes + (1 << 20)) for _ in range(P)]
+        sh_infos = [None] * P
+
+        def shp_steps(nsteps, e2e=False, keep=False):
+            """every rank submits the same planes in the same order; e2e: this rank's band from pinned host memory, shard containers out"""
+            ctx.timer_start()
+            shp.wait_for(ctx)
+            for _ in range(nsteps):
+                for b in range(P):
+                    if e2e or keep:
+                        if e2e:
+                            _, info = shp.submit(host_planes[b].reshape(-1), rows, cols, W, K, seed=SEED, out=sh_outs[b])
+                        else:
+                            _, info = shp.submit_resident(rasters[b], W, K, seed=SEED, out=sh_outs[b])
+                        sh_infos[b] = info
+                    else:
+                        shp.submit_resident(rasters[b], W, K, seed=SEED, out=None)
+                shp.poll()
+            deadline = time.time() + 90 + 20 * nsteps
+            while shp.poll():
+                if time.time() > deadline:   # a rank that waits for a peer forever must end the run, not burn the GPU box
+                    sys.stderr.write(f"rank {rank}: the sharded pipeline made no progress -- giving up\n")
+                    sys.stderr.flush()
+                    os._exit(3)
+            ctx.wait_for_pipeline(shp)
+            ms = ctx.timer_stop()
+            shp.forget_finished()
+            return ms
+
+        shp_steps(1, keep=True)     # first use: shard sizes, peer windows, scratch (collective, slot by slot in the same order everywhere)
+        barrier()
+        sh_parsed = [bic.Pipeline.parse_shard_container(sh_outs[b][: int(sh_infos[b].container_bytes)]) for b in range(P)]
+        sh_iters = [sp["iterations"] for sp in sh_parsed]
+        # ---- correctness in the bench itself: iteration count, the dictionary's coded stream (byte for byte) and the GLOBAL Golomb bit
+        # counts of A and E must equal the single-GPU fit of the concatenated rows (rank 0 gathers the N bands)
+        sh_checked = 0
+        for b in range(P):
+            band = torch.from_numpy(host_planes[b]).to(dev)
+            if dist is not None:
+                bands = [torch.empty_like(band) for _ in range(world)]
+                dist.all_gather(bands, band)
+            else:
+                bands = [band]
+            if rank == 0:
+                whole = torch.cat(bands, dim=0).cpu().numpy()
+                c = ctx
+                Iall = c.matrix(world * rows, cols)
+                Iall.upload_pbm(whole)
+                Xall = c.extract_patches(Iall, W)
+                Dall, Aall, Eall = c.matrix(K, m), c.matrix(Xall.rows, K), c.matrix(Xall.rows, m)
+                c.initialize_model_neighbor(Xall, Dall, Aall, c.rand48(SEED))
+                it1, _ = c.learn_model_traditional(Xall, Eall, Dall, Aall)
+                sD = c.golomb_encode(Dall)
+                bytesD, _ = sD.download()
+                bitsA, bitsE = c.golomb_bitcount(Aall)[0], c.golomb_bitcount(Eall)[0]
+                sp = sh_parsed[b]
+                ok = (it1 == sp["iterations"] and np.array_equal(bytesD, sp["streams"]["D"]["bytes"])
+                      and bitsA == sp["streams"]["A"]["global_bitcount"] and bitsE == sp["streams"]["E"]["global_bitcount"])
+                for M in (Iall, Xall, Dall, Aall, Eall, sD):
+                    M.destroy()
+                if not ok:
+                    raise SystemExit(f"PARITY FAILURE: row-sharded fit of bitplane {b} over {world} rank(s) differs from the single-GPU fit of the "
+                                     f"concatenated rows (iterations {sp['iterations']} vs {it1}, A bits {sp['streams']['A']['global_bitcount']} vs {bitsA}, "
+                                     f"E bits {sp['streams']['E']['global_bitcount']} vs {bitsE})")
+                sh_checked += 1
+            del band, bands
+        barrier()
+        shp_steps(max(args.warmup, 3))
+        barrier()
+        st0 = shp.stats()
+        ms_sh = max_over_ranks(shp_steps(args.steps) / args.steps)
+        st1 = shp.stats()
+        barrier()
+        shp_steps(2, e2e=True)
+        barrier()
+        ms_sh_e2e = max_over_ranks(shp_steps(args.steps, e2e=True) / args.steps)
+        barrier()
+        sharded = {"value": world * px_step / (ms_sh / 1e3), "unit": UNIT, "ms_per_step": ms_sh,
+                   "e2e": {"value": world * px_step / (ms_sh_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_sh_e2e,
+                           "h2d_bytes_per_step": P * plane_bytes, "d2h_bytes_per_step": int(sum(int(i.container_bytes) for i in sh_infos)),
+                           "path": "each rank: its band of every plane from pinned host memory -> bic_pipeline_submit (sharded mode) -> its shard container "
+                                   "(D stream, A shard, E shard + chunk indexes) in pinned host memory; one host thread per rank"},
+                   "gpu_launches": int(st1["launches"] - st0["launches"]), "pipeline": st1,
+                   "iterations_per_plane": sh_iters, "planes_in_flight_per_rank": NSL, "host_threads_per_rank": 1,
+                   "parity_checked": bool(sh_checked == P) if rank == 0 else None, "parity_planes": sh_checked,
+                   "parity_how": "iteration count, the dictionary's coded stream byte for byte and the global Golomb bit counts of A and E of every plane "
+                                 "equal the single-GPU fit of the concatenated rows (run on rank 0 inside this bench)",
+                   "what": f"each plane is ONE {world * S}x{S} image whose patch rows are sharded over {world} rank(s); one dictionary per plane; per bsvd "
+                           "iteration one NCCL allreduce of [H | U | bucket sizes | changed rows] queued on the slot's stream; the corrections of every atom "
+                           "that changes are exchanged over NVLink peer memory inside the cluster-chain kernel; seam-exact sharded Golomb coding with the "
+                           "shard's prefix state computed on the device from two small all-gathers; nothing waits for the host"}
+        shp.close()
+    elif world > 1 or args.sharded:
         # one polling host thread per plane in flight: as many as this rank's share of the host cores carries (sleeping waits --
         # wait_mode 2 -- were measured at 8 ranks x 8 threads: 81 ms per step against 13 ms with 4 polling threads)
         TS = max(1, min(args.sharded_streams, P, max(2, host_cores // max(world, 1))))
@@ -1120,8 +1230,9 @@ def main():
                                           "over the ranks, one dictionary per plane")
             line["config"]["parallelism"] = (f"{world} ranks, patch rows sharded, D replicated; NCCL allreduce of [H | U | bucket sizes | changed rows] once per bsvd "
                                              f"iteration, per-changed-atom corrections exchanged over NVLink peer memory inside the chain kernel; "
-                                             f"{sharded['planes_in_flight_per_rank']} planes in flight per rank")
-            line["config"]["host_threads_per_rank"] = sharded["planes_in_flight_per_rank"]
+                                             f"{sharded['planes_in_flight_per_rank']} planes in flight per rank on "
+                                             f"{sharded.get('host_threads_per_rank', sharded['planes_in_flight_per_rank'])} host thread(s)")
+            line["config"]["host_threads_per_rank"] = sharded.get("host_threads_per_rank", sharded["planes_in_flight_per_rank"])
             line["parity_checked"] = bool(sharded.get("parity_checked"))
             line["parity_planes"] = sharded.get("parity_planes", 0)
             line["parity_how"] = sharded.get("parity_how")

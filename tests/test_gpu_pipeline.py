@@ -155,3 +155,44 @@ def test_device_pivot_draw_equals_the_host_replay(ctx, oracle, synth, n, p, zero
     for _ in range(5):
         assert int(L.bic_rand48_uniform_int(C.byref(st), 1000)) == oracle.uniform_int(r, 1000)
     X.destroy()
+
+
+def test_sharded_pipeline_with_one_rank(bic, ctx, synth, oracle):
+    """the sharded mode of the pipeline on a one-rank communicator per slot: the whole asynchronous sharded path (device-side
+    draw over the gathered bitmap, the hooked cluster chain, the device-resident Golomb shard base, the shard container) must
+    reproduce the oracle's fit and the serial coder's streams; tests/dist_gpu_worker.py runs the same over several GPUs"""
+    pipe = bic.Pipeline(0, 3)
+    pipe.make_sharded(0, 1, lambda uid: uid)
+    try:
+        W, K = 8, 16
+        jobs = []
+        for s_ in range(7):
+            rows, cols = 96 + 8 * (s_ % 3), 128
+            if s_ % 3 == 2:
+                page = (np.random.default_rng(100 + s_).random((rows, cols)) < 0.45).astype(np.uint8)
+            else:
+                page = synth.structured_page(rows, cols, seed=60 + s_, salt=0.01)
+            pay = ctx.pinned(rows * cols // 8)
+            pay[:] = synth.pbm_bytes(page).reshape(-1)
+            out = ctx.pinned(1 << 18)
+            job, info = pipe.submit(pay, rows, cols, W, K, seed=900, out=out)
+            jobs.append((job, info, out, page, rows, cols))
+        pipe.wait()
+        m = W * W
+        for job, info, out, page, rows, cols in jobs:
+            done, st, msg = pipe.status(job)
+            assert done and st == 0, msg
+            Xw = oracle.extract_patches(synth.pack_rows(page), rows, cols, W)
+            Do, Ao, _ = oracle.init_neighbor(Xw, m, K, 900)
+            Eo, ito, _ = oracle.learn_traditional(Xw, Do, Ao, m, K)
+            sc = bic.Pipeline.parse_shard_container(out[: int(info.container_bytes)])
+            assert sc["iterations"] == ito == int(info.iterations)
+            for name, Mo, cols_ in (("D", Do, m), ("A", Ao, K), ("E", Eo, m)):
+                so, nbits, ns = oracle.golomb_encode(Mo, cols_)
+                stt = sc["streams"][name]
+                assert stt["local_bits"] == nbits and stt["local_samples"] == ns, (name, stt["local_bits"], nbits)
+                assert np.array_equal(stt["bytes"], so), name
+                if name != "D":
+                    assert stt["global_bitcount"] == nbits and stt["code_bit_offset"] == 0
+    finally:
+        pipe.close()
