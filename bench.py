@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--sharded-threads", action="store_true", help="row-sharded fit through the synchronous bic_dist_* calls, one host thread per plane in flight, instead of the sharded pipeline")
     ap.add_argument("--sharded-streams", type=int, default=8, help="row-sharded fit: planes in flight per rank (one communicator + host thread each)")
     ap.add_argument("--sharded-cluster", type=int, default=8, help="row-sharded fit: CTAs per cluster of the chain kernel (it waits for the peers inside)")
+    ap.add_argument("--sharded-only", action="store_true", help="tuning runs: time the row-sharded arm, print its object and stop")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the host cores of its GPU's NUMA node")
     ap.add_argument("--pool", action="store_true", help="round-1 driver: one host thread per context instead of the single-thread pipeline")
     ap.add_argument("--first-batch", type=int, default=2, help="pipeline: iterations queued before the loop flag is first looked at")
     ap.add_argument("--next-batch", type=int, default=2, help="pipeline: iterations per later batch")
@@ -275,6 +277,31 @@ def algorithmic_bytes(kernel: str, rows, cols, n, m, p, launches_per_step=1.0, u
     return None
 
 
+def bind_to_gpu_numa_node(torch, local_rank, world):
+    """N > 1: pinned host buffers and the rank's host thread belong on the NUMA node its GPU hangs off (first-touch places the pinned
+    pages where the allocating thread runs). Only when the node offers this rank at least its fair share of the allowed cores."""
+    if world <= 1:
+        return None
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"bdf": bdf, "node": node, "bound": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        mine = sorted(cpus & allowed)
+        if len(mine) < max(2, len(allowed) // world):
+            return {"bdf": bdf, "node": node, "bound": False, "node_cores_allowed": len(mine)}
+        os.sched_setaffinity(0, mine)
+        return {"bdf": bdf, "node": node, "bound": True, "cores": len(mine)}
+    except Exception as ex:  # no sysfs, no permission: run unbound
+        return {"bound": False, "why": str(ex)[:80]}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -291,7 +318,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback")
+    try:
+        host_cores = len(os.sched_getaffinity(0))   # before the NUMA binding below narrows it
+    except AttributeError:
+        host_cores = os.cpu_count() or 16
     torch.cuda.set_device(local_rank)
+    numa = None if args.no_numa else bind_to_gpu_numa_node(torch, local_rank, world)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -348,10 +380,6 @@ def main():
 
     # one host thread per context: with several ranks per box the threads must fit the host cores
     # (8 ranks x 17 threads on a 32-core box cost 20 % at N = 8), so the pool shrinks to ~1.5 threads per core
-    try:
-        host_cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        host_cores = os.cpu_count() or 16
     T_fit = max(4, int(1.5 * host_cores / max(world, 1)))
     T = max(1, min(args.streams, T_fit, P * max(1, args.steps)))  # tasks of all steps share one queue
     if not (args.pool or args.batch):
@@ -802,6 +830,16 @@ def main():
                            "memory inside the cluster-chain kernel; seam-exact sharded Golomb coding"}
         for w in shw:
             w.ctx.comm_destroy(w.comm)
+
+    if sharded is not None:
+        sharded["numa"] = numa
+    if args.sharded_only:
+        if rank == 0:
+            print(json.dumps({"sharded_only": True, "n_gpus": world, "row_sharded": sharded}))
+        if dist is not None:
+            dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
     # ---- the pipeline: ONE host thread keeps `streams` rasters in flight (csrc/pipeline.cu)
     use_pipe = not (args.pool or batched)
