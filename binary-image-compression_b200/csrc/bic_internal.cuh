@@ -82,6 +82,7 @@ struct bic_ctx {
   int wait_mode = 0;       // how host threads wait for the stream: 0 cudaStreamSynchronize, 1 poll + sched_yield, 2 blocking event
   cudaEvent_t wait_ev = nullptr, wait_ev_blocking = nullptr;
   int gol_algo = 2;        // 2: wide-tile encoder with fused scans (coding2.cu), 1: the first formulation (coding.cu)
+  int gol_list = 1;        // sparse tiles coded from a list of their ones (coding2.cu): 0 never, 1 for streams long enough for wide tiles, 2 always
   int gol_presize_pct = 125;  // the asynchronous encoders size the code buffer to this percentage of the input bits (+ 4 KB)
   int gol_onepass = 0;     // 1: single-pass Golomb encoder (decoupled look-back) when the buffer is pre-sized
   int coef_algo = 1;  // 1: dictionaries of >= 64 atoms use the weight-sorted warp-per-row coefficient kernel; 0: always lane per row
@@ -93,6 +94,11 @@ struct bic_ctx {
   // waiting for the previous one's counts; the iteration's kernels return at once when *loop_skip != 0
   const uint32_t* loop_skip = nullptr;
   bool prof_on = false;
+  // A context that is one slot of a SHARDED pipeline must never call cudaFree while jobs are in flight: cudaFree waits for every
+  // stream of the device, including other slots' kernels that are waiting for a peer GPU -- whose host may be waiting the same
+  // way for ours. Such contexts park outgrown blocks here until they are destroyed.
+  bool defer_free = false;
+  std::vector<void*> graveyard;
   std::vector<bic_prof_rec> prof_recs;
   std::vector<cudaEvent_t> prof_free;
   double prof_ms[KID_COUNT] = {0};
@@ -133,6 +139,11 @@ static inline bic_status bic_fail(bic_ctx* ctx, bic_status s, const char* msg) {
 // wait until everything queued on the context's stream is done (honours wait_mode)
 cudaError_t bic_wait_stream(bic_ctx* ctx);
 // grow-only scratch; contents are undefined after growth
+static inline void bic_free_device(bic_ctx* c, void* p) {
+  if (!p) return;
+  if (c && c->defer_free) c->graveyard.push_back(p);
+  else cudaFree(p);
+}
 bic_status bic_scratch_reserve(bic_ctx* ctx, bic_scratch* s, size_t bytes);
 // D2H of the first n scalar slots after the stream drained
 bic_status bic_read_scalars(bic_ctx* ctx, int n);

@@ -760,7 +760,7 @@ static bic_status stream_reserve(bic_ctx* c, bic_stream* s, uint64_t bitcount, u
   if (need > s->cap_bytes && typical > need) need = typical;
   if (need > s->cap_bytes) {
     BIC_CUDA(c, bic_wait_stream(c));
-    if (s->d_bytes) cudaFree(s->d_bytes);
+    bic_free_device(c, s->d_bytes);
     s->d_bytes = nullptr; s->cap_bytes = 0;
     const size_t want = (need + (need >> 3) + 255) & ~(size_t)255;
     if (cudaMalloc(&s->d_bytes, want) != cudaSuccess) { cudaGetLastError(); c->err = "stream allocation failed"; return BIC_ERR_NOMEM; }
@@ -771,7 +771,7 @@ static bic_status stream_reserve(bic_ctx* c, bic_stream* s, uint64_t bitcount, u
   if (needi > s->cap_index && typicali > needi) needi = typicali;
   if (needi > s->cap_index) {
     BIC_CUDA(c, bic_wait_stream(c));
-    if (s->d_index) cudaFree(s->d_index);
+    bic_free_device(c, s->d_index);
     s->d_index = nullptr; s->cap_index = 0;
     if (cudaMalloc(&s->d_index, needi * 8) != cudaSuccess) { cudaGetLastError(); c->err = "index allocation failed"; return BIC_ERR_NOMEM; }
     s->cap_index = needi;

@@ -24,12 +24,17 @@
 #define G2_TILE_BITS(WPT) (G2_TILE_WORDS(WPT) * 32)
 #define G2_STAGE_WORDS(WPT) (G2_TILE_WORDS(WPT) * 3 / 2)   // staged code words of one tile (1.5 x its input)
 #define G2_MAXSEG 3
+// Sparse tiles (at most one bit in 64 set): the count pass also writes the positions of the tile's ones as a list, and the length
+// and scatter passes of such a tile work from the list -- a thread per few SAMPLES instead of a thread per 16 words, and the
+// words are not read again. Decided tile by tile from the tile's own count, so a stream may mix both kinds.
+#define G2_LIST_CAP(WPT) (G2_TILE_WORDS(WPT) / 2)
 
 struct G2Seg {
   const uint32_t* S;                 // dense bit stream of the matrix, MSB first
   uint64_t T, N;                     // words, bits
   uint32_t tile0, ntiles;            // block index of the stream's first tile, tiles
   uint32_t* ones;                    // per tile: ones
+  uint32_t* list;                    // per tile: G2_LIST_CAP entries, bit index inside the tile of each one (tiles with <= CAP ones); null = off
   long long* last;                   // per tile: position of the last one, -1 if none
   unsigned long long* ones_before;   // exclusive prefixes, written by the last CTA of the count pass
   long long* last_before;
@@ -169,6 +174,18 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_count(G2Params P) {
   int last, ex_last, tot_last;
   g2_count(v, &c, &last);
   g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
+  if (g.list && c && tot_c <= G2_LIST_CAP(WPT)) {                       // a sparse tile: my ones go into the tile's list
+    uint32_t* L = g.list + (uint64_t)tile * G2_LIST_CAP(WPT) + ex_c;
+#pragma unroll
+    for (int i = 0; i < WPT; ++i) {
+      uint32_t b = v[i];
+      while (b) {
+        const int p = __clz(b);
+        b &= ~(0x80000000u >> p);
+        *L++ = threadIdx.x * (WPT * 32) + i * 32 + p;
+      }
+    }
+  }
   if (threadIdx.x == 0) {
     g.ones[tile] = tot_c;
     g.last[tile] = tot_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + tot_last : -1;
@@ -178,21 +195,55 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_count(G2Params P) {
   __syncthreads();
   if (!s_last_cta) return;
   __threadfence();
-  // exclusive scans over the stream's tiles: a contiguous run of tiles per thread, one block scan over the run totals
+  // exclusive scans over the stream's tiles: a contiguous run of tiles per thread, one block scan over the run totals. The loads
+  // of a run are issued eight at a time (restrict + unroll): this CTA is the kernel's tail and a dependent L2 round trip per tile
+  // would be most of a sparse stream's count pass
+  const uint32_t* __restrict__ ones = g.ones;
+  const long long* __restrict__ lastp = g.last;
+  unsigned long long* __restrict__ ob = g.ones_before;
+  long long* __restrict__ lbp = g.last_before;
   const uint64_t per = div_up_u64(g.ntiles, G2_THREADS);
   const uint64_t t0 = threadIdx.x * per, t1 = (t0 + per < g.ntiles) ? t0 + per : g.ntiles;
   unsigned long long sum = 0;
   long long mx = -1;
-  for (uint64_t i = t0; i < t1; ++i) { sum += __ldcg(g.ones + i); const long long l = __ldcg(g.last + i); mx = mx > l ? mx : l; }
+#pragma unroll 8
+  for (uint64_t i = t0; i < t1; ++i) { sum += __ldcg(ones + i); const long long l = __ldcg(lastp + i); mx = mx > l ? mx : l; }
   unsigned long long run = block_excl_scan_u64(sum, nullptr, s_a);
   long long runm = block_excl_scan_max(mx, nullptr, s_b);
+#pragma unroll 8
   for (uint64_t i = t0; i < t1; ++i) {
-    g.ones_before[i] = run;
-    g.last_before[i] = runm;
-    run += __ldcg(g.ones + i);
-    const long long l = __ldcg(g.last + i);
+    ob[i] = run;
+    lbp[i] = runm;
+    run += __ldcg(ones + i);
+    const long long l = __ldcg(lastp + i);
     runm = runm > l ? runm : l;
   }
+}
+
+// ------------------------------------------------------------------ sparse tiles: a thread's samples from the tile's list
+// Thread j of the CTA owns samples [i0, i1) of the tile (consecutive, so its codewords are one contiguous bit range, like a
+// thread's 16 words in the dense route). Returns their code bits; *t / *prev: global rank of sample i0 / global position of the
+// one before it (the state the first codeword is computed from).
+template <int WPT>
+__device__ __forceinline__ unsigned long long g2_list_span(const G2Seg& g, const GolBase& gb, uint32_t tile, uint32_t nones, long long lb,
+                                                           uint32_t* i0o, uint32_t* i1o, unsigned long long* t0o, long long* prev0o) {
+  const uint32_t q = (nones + G2_THREADS - 1) / G2_THREADS;
+  const uint32_t i0 = min(threadIdx.x * q, nones), i1 = min(i0 + q, nones);
+  const uint32_t* L = g.list + (uint64_t)tile * G2_LIST_CAP(WPT);
+  const long long tileb = (long long)tile * G2_TILE_BITS(WPT) + gb.pos0;
+  long long prev = i0 ? tileb + (long long)__ldcg(L + i0 - 1) : (lb >= 0 ? lb + gb.pos0 : gb.prev0);
+  unsigned long long t = gb.t0 + g.ones_before[tile] + i0;
+  *i0o = i0; *i1o = i1; *t0o = t; *prev0o = prev;
+  unsigned long long bits = 0;
+  for (uint32_t i = i0; i < i1; ++i) {
+    const long long pos = tileb + (long long)__ldcg(L + i);
+    const unsigned long long x = (unsigned long long)(pos - prev - 1);
+    const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+    bits += k + (x >> k) + 1;
+    prev = pos;
+    ++t;
+  }
+  return bits;
 }
 
 // ------------------------------------------------------------------ pass 2: code bits per thread and tile; the last CTA scans and totals
@@ -203,6 +254,16 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   __shared__ int s_last_cta;
   uint32_t tile;
   const G2Seg& g = g2_segment(P, &tile);
+  const GolBase gb = g.gbp ? *g.gbp : g.gb;
+  const long long lb = g.last_before[tile];
+  unsigned long long mybits = 0;
+  const uint32_t nones = g.list ? g.ones[tile] : 0xffffffffu;
+  if (nones <= G2_LIST_CAP(WPT)) {                                                     // sparse tile (uniform over the CTA): from the list
+    uint32_t i0, i1;
+    unsigned long long t;
+    long long prev;
+    mybits = g2_list_span<WPT>(g, gb, tile, nones, lb, &i0, &i1, &t, &prev);
+  } else {
   uint32_t v[WPT];
   const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS(WPT) + threadIdx.x * WPT;
   g2_load(g, w0, v);
@@ -210,13 +271,10 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   int last, ex_last, tot_last;
   g2_count(v, &c, &last);
   g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
-  const GolBase gb = g.gbp ? *g.gbp : g.gb;
   unsigned long long t = gb.t0 + g.ones_before[tile] + ex_c;                          // global rank of my first sample
-  const long long lb = g.last_before[tile];
   const long long pvl = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;  // the one before my stretch inside this matrix, -1 if none
   long long prev = pvl >= 0 ? pvl + gb.pos0 : gb.prev0;                                // ... as a GLOBAL position
   const long long tb = (long long)(w0 * 32) + gb.pos0;                                 // global position of my first bit
-  unsigned long long mybits = 0;
   if (c) {
     // my first one closes a run that began before my stretch: full-width arithmetic, and the coder state it leaves decides how
     // the rest of the stretch is walked (the three loops below are each uniform, so a warp only diverges where lanes differ in mode)
@@ -281,6 +339,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
     mybits += fastbits;
   }
   g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x] = mybits;
+  }
   unsigned long long tot;
   g2_excl_sum_u64(mybits, &tot, s_a);
   if (threadIdx.x == 0) {
@@ -293,11 +352,15 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   __threadfence();
   const uint64_t per = div_up_u64(g.ntiles, G2_THREADS);
   const uint64_t t0 = threadIdx.x * per, t1 = (t0 + per < g.ntiles) ? t0 + per : g.ntiles;
+  const unsigned long long* __restrict__ bitsp = g.bits;
+  unsigned long long* __restrict__ bbp = g.bits_before;
   unsigned long long sum = 0;
-  for (uint64_t i = t0; i < t1; ++i) sum += __ldcg(g.bits + i);
+#pragma unroll 8
+  for (uint64_t i = t0; i < t1; ++i) sum += __ldcg(bitsp + i);
   unsigned long long carry;
   unsigned long long run = block_excl_scan_u64(sum, &carry, s_a);
-  for (uint64_t i = t0; i < t1; ++i) { g.bits_before[i] = run; run += __ldcg(g.bits + i); }
+#pragma unroll 8
+  for (uint64_t i = t0; i < t1; ++i) { bbp[i] = run; run += __ldcg(bitsp + i); }
   if (threadIdx.x == 0) {
     const uint64_t lt = g.ntiles - 1;
     const unsigned long long ones = g.ones_before[lt] + g.ones[lt];
@@ -387,20 +450,32 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
   uint32_t tile;
   const G2Seg& g = g2_segment(P, &tile);
   if (g.info[4]) return;                                                 // the code does not fit: nothing is written
+  const GolBase gb = g.gbp ? *g.gbp : g.gb;
+  const long long lb = g.last_before[tile];
+  const uint32_t nones = g.list ? g.ones[tile] : 0xffffffffu;
+  const bool sparse = nones <= G2_LIST_CAP(WPT);                          // uniform over the CTA
   uint32_t v[WPT];
   const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS(WPT) + threadIdx.x * WPT;
-  g2_load(g, w0, v);
-  uint32_t c, ex_c, tot_c;
-  int last, ex_last, tot_last;
-  g2_count(v, &c, &last);
-  g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
-  const GolBase gb = g.gbp ? *g.gbp : g.gb;
-  unsigned long long t = gb.t0 + g.ones_before[tile] + ex_c;
-  const long long lb = g.last_before[tile];
-  const long long pvl = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;
-  long long prev = pvl >= 0 ? pvl + gb.pos0 : gb.prev0;
+  uint32_t c = 0, li0 = 0, li1 = 0;
+  unsigned long long t, mybits;
+  long long prev;
+  if (sparse) {
+    mybits = g2_list_span<WPT>(g, gb, tile, nones, lb, &li0, &li1, &t, &prev);
+    c = li1 - li0;
+  } else {
+    g2_load(g, w0, v);
+    uint32_t ex_c, tot_c;
+    int last, ex_last, tot_last;
+    g2_count(v, &c, &last);
+    g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
+    t = gb.t0 + g.ones_before[tile] + ex_c;
+    const long long pvl = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;
+    prev = pvl >= 0 ? pvl + gb.pos0 : gb.prev0;
+    mybits = g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x];
+  }
   const long long tb = (long long)(w0 * 32) + gb.pos0;
-  const unsigned long long mybits = g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x];
+  const uint32_t* const lst = sparse ? g.list + (uint64_t)tile * G2_LIST_CAP(WPT) : nullptr;
+  const long long tileb = (long long)tile * G2_TILE_BITS(WPT) + gb.pos0;
   unsigned long long tot;
   const unsigned long long ex = g2_excl_sum_u64(mybits, &tot, s_a);
   const unsigned long long o0 = g.bits_before[tile] + gb.out0;         // bit offset inside this shard's own buffer
@@ -420,6 +495,30 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
       w.first_wp = w.wp; w.first_val = 0; w.first_pending = (ob & 31) != 0;   // a range that starts on a word boundary shares nothing there
       w.limit = (uint32_t)span_words;
       const uint32_t cmask32 = g.chunk - 1;
+      if (sparse) {
+        for (uint32_t i = li0; i < li1; ++i) {                             // my samples from the tile's list, k re-derived for each
+          const long long pos = tileb + (long long)__ldcg(lst + i);
+          const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+          const unsigned long long x = (unsigned long long)(pos - prev - 1);
+          if ((t & cmask) == 0) {
+            const unsigned long long slot = (t >> clog) - gb.chunk0;
+            BIC_DCHECK(slot <= (g.N >> clog) + 1);
+            g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
+            g.index[2 * slot + 1] = (unsigned long long)(prev + 1);
+          }
+          const unsigned long long u = x >> k;
+          const uint32_t rem = (uint32_t)(x & ((1ull << k) - 1));
+          if (k + u + 1 <= 32) {
+            w.put((rem << (uint32_t)(u + 1)) | 1u, k + (uint32_t)u + 1);
+          } else {
+            if (k) w.put(rem, k);
+            w.zeros(u);
+            w.put(1u, 1);
+          }
+          ++t;
+          prev = pos;
+        }
+      } else {
       // my first one (see the length pass): codeword from the full-width run length, then the mode of the rest
       uint32_t fw = 0, fi = 0;
 #pragma unroll
@@ -564,6 +663,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
           }
         }
       }
+      }
       w.finish();
       BIC_DCHECK((unsigned long long)w.wp * 32 + w.fill == (o0 + ex - base) + mybits);   // I wrote exactly the bits the length pass counted
     }
@@ -578,6 +678,20 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
   } else if (c) {
     // a tile whose code is far longer than its input (long unary parts): codewords go straight to global memory
     unsigned long long o = o0 + ex;
+    if (sparse) {
+      for (uint32_t i = li0; i < li1; ++i) {
+        const long long pos = tileb + (long long)__ldcg(lst + i);
+        const unsigned long long x = (unsigned long long)(pos - prev - 1);
+        const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+        if ((t & cmask) == 0) { g.index[2 * ((t >> clog) - gb.chunk0)] = o + goff; g.index[2 * ((t >> clog) - gb.chunk0) + 1] = (unsigned long long)(prev + 1); }
+        put_bits(g.out, o, (uint32_t)(x & ((1ull << k) - 1)), k);
+        const unsigned long long stop = o + k + (x >> k);
+        put_one(g.out, stop);
+        o = stop + 1;
+        prev = pos;
+        ++t;
+      }
+    } else {
 #pragma unroll
     for (int i = 0; i < WPT; ++i) {
       uint32_t b = v[i];
@@ -595,6 +709,7 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
         prev = pos;
         ++t;
       }
+    }
     }
   }
   if (gb.closing && tile == 0 && threadIdx.x == 0) {                   // the run closed by the virtual one
@@ -637,7 +752,9 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
   for (int i = 0; i < nmat; ++i) { nts[i] = div_up_u64(Ts[i], (uint64_t)G2_TILE_WORDS(WPT)); ntiles_total += nts[i]; }
   if (ntiles_total >= (1ull << 31)) return bic_fail(c, BIC_ERR_UNSUPPORTED, "golomb: too many tiles for one launch");
   if (words_compact) BIC_TRY(bic_scratch_reserve(c, &c->work[4], words_compact * 4 + 64));
-  const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8;   // last, ones_before, last_before, bits, bits_before | ones (padded to 8) | tbits
+  const bool use_list = c->gol_list == 2 || (c->gol_list == 1 && WPT == 16);
+  const size_t list_tile = use_list ? (size_t)G2_TILE_WORDS(WPT) / 2 * 4 : 0;
+  const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8 + list_tile;   // last, ones_before, last_before, bits, bits_before | ones (padded to 8) | tbits | list
   BIC_TRY(bic_scratch_reserve(c, &c->work[5], ntiles_total * per_tile + 64 * G2_MAXSEG + 64));
   uint8_t* p = (uint8_t*)c->work[5].p;
   unsigned int* done = (unsigned int*)p;                         // 2 counters per stream, 64 bytes apart
@@ -668,6 +785,7 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
     g.bits_before = (unsigned long long*)p;         p += nt * 8;
     g.ones = (uint32_t*)p;                          p += nt * 8;
     g.tbits = (unsigned long long*)p;               p += nt * (size_t)G2_THREADS * 8;
+    g.list = use_list ? (uint32_t*)p : nullptr;     p += nt * list_tile;
     g.done = done + 16 * i;
     g.info = d_info + 8 * i;
     g.out = (uint32_t*)outs[i]->d_bytes;
@@ -727,7 +845,9 @@ bic_status bic_g2_plan(bic_ctx* c, const bic_mat* M, void* plan_out, size_t plan
   const uint64_t nt = div_up_u64(T, (uint64_t)G2_TILE_WORDS(pl->WPT));
   if (nt >= (1ull << 31)) return bic_fail(c, BIC_ERR_UNSUPPORTED, "golomb: too many tiles for one launch");
   if (M->cols & 31) BIC_TRY(bic_scratch_reserve(c, &c->work[4], ((T + 7) & ~(uint64_t)3) * 4 + 64));
-  const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8;
+  const bool use_list = c->gol_list == 2 || (c->gol_list == 1 && pl->WPT == 16);
+  const size_t list_tile = use_list ? (size_t)G2_TILE_WORDS(pl->WPT) / 2 * 4 : 0;
+  const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8 + list_tile;
   BIC_TRY(bic_scratch_reserve(c, &c->work[5], nt * per_tile + 64 * G2_MAXSEG + 64 + 64));
   uint8_t* p = (uint8_t*)c->work[5].p;
   unsigned int* done = (unsigned int*)p;
@@ -747,6 +867,7 @@ bic_status bic_g2_plan(bic_ctx* c, const bic_mat* M, void* plan_out, size_t plan
   g.bits_before = (unsigned long long*)p;         p += nt * 8;
   g.ones = (uint32_t*)p;                          p += nt * 8;
   g.tbits = (unsigned long long*)p;               p += nt * (size_t)G2_THREADS * 8;
+  g.list = use_list ? (uint32_t*)p : nullptr;     p += nt * list_tile;
   g.info = (unsigned long long*)p;                 // 8 words after the per-tile arrays
   g.done = done;
   g.cap_bits = ~0ull >> 1;
@@ -910,7 +1031,9 @@ bic_status bic_k_golomb_encode_multi_sharded(bic_ctx* c, const bic_mat* const* m
   for (int i = 0; i < nmat; ++i) { nts[i] = div_up_u64(Ts[i], (uint64_t)G2_TILE_WORDS(WPT)); ntiles_total += nts[i]; }
   if (ntiles_total >= (1ull << 31)) return bic_fail(c, BIC_ERR_UNSUPPORTED, "golomb: too many tiles for one launch");
   if (words_compact) BIC_TRY(bic_scratch_reserve(c, &c->work[4], words_compact * 4 + 64));
-  const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8;
+  const bool use_list = c->gol_list == 2 || (c->gol_list == 1 && WPT == 16);
+  const size_t list_tile = use_list ? (size_t)G2_TILE_WORDS(WPT) / 2 * 4 : 0;
+  const size_t per_tile = 8 * 5 + 8 + (size_t)G2_THREADS * 8 + list_tile;
   // tail of the scratch: counters | base[3] | aux[3] | tot[3][2] | pack1 (3*3) | all1 (nranks*3*3) | pack2 (3) | all2 (nranks*3)
   const size_t tail = 64 * G2_MAXSEG + sizeof(GolBase) * G2_MAXSEG + sizeof(G2ShardAux) * G2_MAXSEG + 8 * (6 + 9 + 3) + 8 * (size_t)nranks * (9 + 3) + 256;
   BIC_TRY(bic_scratch_reserve(c, &c->work[5], ntiles_total * per_tile + tail));
@@ -951,6 +1074,7 @@ bic_status bic_k_golomb_encode_multi_sharded(bic_ctx* c, const bic_mat* const* m
     g.bits_before = (unsigned long long*)p;         p += nt * 8;
     g.ones = (uint32_t*)p;                          p += nt * 8;
     g.tbits = (unsigned long long*)p;               p += nt * (size_t)G2_THREADS * 8;
+    g.list = use_list ? (uint32_t*)p : nullptr;     p += nt * list_tile;
     g.done = done + 16 * i;
     g.info = d_info + 8 * i;
     g.out = (uint32_t*)outs[i]->d_bytes;

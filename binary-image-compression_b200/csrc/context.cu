@@ -74,6 +74,8 @@ extern "C" bic_status bic_ctx_destroy(bic_ctx* c) {
   prof_collect_for_destroy(c);
   if (c->staging.p) cudaFree(c->staging.p);
   for (auto& w : c->work) if (w.p) cudaFree(w.p);
+  for (void* p : c->graveyard) cudaFree(p);
+  c->graveyard.clear();
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->d_scalars) cudaFree(c->d_scalars);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -174,7 +176,7 @@ bic_status bic_scratch_reserve(bic_ctx* c, bic_scratch* s, size_t bytes) {
   if (bytes <= s->bytes) return BIC_OK;
   // the old block may still be in use by queued kernels
   BIC_CUDA(c, bic_wait_stream(c));
-  if (s->p) { cudaFree(s->p); s->p = nullptr; s->bytes = 0; }
+  if (s->p) { bic_free_device(c, s->p); s->p = nullptr; s->bytes = 0; }
   size_t want = (bytes + (bytes >> 2) + 255) & ~(size_t)255;
   cudaError_t e = cudaMalloc(&s->p, want);
   if (e != cudaSuccess) {
@@ -592,6 +594,7 @@ extern "C" bic_status bic_ctx_set_option(bic_ctx* c, const char* name, int64_t v
   if (!c || !name) return BIC_ERR_INVALID;
   if (!strcmp(name, "wait_mode")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->wait_mode = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_algo")) { if (value < 1 || value > 2) return BIC_ERR_INVALID; c->gol_algo = (int)value; return BIC_OK; }
+  if (!strcmp(name, "gol_list")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->gol_list = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_presize_pct")) { if (value < 1 || value > 1000) return BIC_ERR_INVALID; c->gol_presize_pct = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_onepass")) { c->gol_onepass = value != 0; return BIC_OK; }
   if (!strcmp(name, "dict_algo")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->dict_algo = (int)value; return BIC_OK; }

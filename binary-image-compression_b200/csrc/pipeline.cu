@@ -614,6 +614,7 @@ extern "C" bic_status bic_pipeline_attach_comms(bic_pipeline* P, bic_comm* const
   for (int i = 0; i < n; ++i) {
     if (!comms[i]) return BIC_ERR_INVALID;
     P->slots[i].comm = comms[i];
+    P->slots[i].c->defer_free = true;      // no cudaFree (a device-wide wait) while peers may be waiting for this rank
   }
   P->sharded = true;
   P->seq = 0;

@@ -152,14 +152,16 @@ WRAP_CASES = [
 
 @pytest.mark.parametrize("ones_before,run,acc", WRAP_CASES)
 @pytest.mark.parametrize("closing", [False, True])
-def test_golomb_shard_state_wraps_like_the_serial_coder(ctx, oracle, synth, ones_before, run, acc, closing):
+@pytest.mark.parametrize("lst,rho", [(1, 0.04), (2, 0.01)])
+def test_golomb_shard_state_wraps_like_the_serial_coder(ctx, oracle, synth, ones_before, run, acc, closing, lst, rho):
     """bic_golomb_encode_shard (the seam arithmetic of bic_dist_golomb_encode with the prefix state given explicitly) against
     the oracle's serial coder started in the same state: GolombCoder's members are 32-bit unsigned (src/Golomb.h:21-24), so
     accumulatedError and samples wrap, and (samples << k) overflows, exactly as in the reference. configs[3]'s residual is
     2^32 bits long, so its tail runs in this regime."""
     rows, cols = 96, 256
+    ctx.set_option("gol_list", lst)                          # 2 with 1 % ones: the tile is coded from the list of its ones
     rng = np.random.default_rng(ones_before % 1000 + run)
-    bits = (rng.random((rows, cols)) < 0.04).astype(np.uint8)
+    bits = (rng.random((rows, cols)) < rho).astype(np.uint8)
     bits[:3] = 0                                             # > 300 zeros first, so case 1 wraps mid-shard
     Mw = synth.pack_rows(bits)
     # prefix state: sum of samples = (last_one + 1) - ones  =>  last_one = acc + ones - 1
@@ -179,6 +181,7 @@ def test_golomb_shard_state_wraps_like_the_serial_coder(ctx, oracle, synth, ones
         assert not np.unpackbits(by)[: code0 & 31].any()     # the leading pad stays zero: shards are OR-ed together
         s.destroy()
     M.destroy()
+    ctx.set_option("gol_list", 1)
 
 
 def test_golomb_two_shards_concatenate_to_the_whole_stream(ctx, oracle, synth):

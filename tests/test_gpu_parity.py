@@ -258,13 +258,15 @@ CODER_SHAPES = [(1, 1, 0.0), (1, 1, 1.0), (1, 32, 0.0), (3, 64, 0.5), (17, 100, 
 CODER_SHAPES_BIG = [(700, 1024, 0.5), (1200, 1024, 0.003), (640, 2048, 0.12), (300, 4100, 0.9), (2, 600000, 0.0005), (1500, 1000, 0.0)]
 
 
-@pytest.mark.parametrize("algo,onepass", [(2, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("algo,onepass,lst", [(2, 0, 1), (2, 0, 2), (1, 0, 1), (1, 1, 1)])
 @pytest.mark.parametrize("rows,cols,rho", CODER_SHAPES + CODER_SHAPES_BIG)
-def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho, algo, onepass):
+def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho, algo, onepass, lst):
     # algo 2: wide tiles, scans fused into the passes, register-assembled codewords (coding2.cu); 1: the first formulation
-    # (coding.cu), as three kernels + scans (onepass 0) or one kernel with decoupled look-back (onepass 1)
+    # (coding.cu), as three kernels + scans (onepass 0) or one kernel with decoupled look-back (onepass 1).
+    # lst 2: sparse tiles are coded from the list of their ones whatever the tile width (default: wide tiles only)
     ctx.set_option("gol_algo", algo)
     ctx.set_option("gol_onepass", onepass)
+    ctx.set_option("gol_list", lst)
     rng = np.random.default_rng(rows * 31 + cols)
     bits = (rng.random((rows, cols)) < rho).astype(np.uint8)
     Mw = synth.pack_rows(bits)
@@ -288,14 +290,80 @@ def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, c
     M.destroy()
     ctx.set_option("gol_onepass", 0)
     ctx.set_option("gol_algo", 2)
+    ctx.set_option("gol_list", 1)
 
 
-@pytest.mark.parametrize("algo", [2, 1])
+@pytest.mark.parametrize("lst", [2, 1, 0])
+def test_golomb_list_and_word_tiles_mixed(ctx, oracle, synth, lst):
+    """tiles with exactly the list capacity, one more, none, a single one, and dense tiles, in one stream: the route is chosen
+    tile by tile from the tile's own count (narrow tiles: 1024 words, capacity 512; lst 2 forces lists on them)"""
+    ctx.set_option("gol_list", lst)
+    tile_bits, cap = 1024 * 32, 512
+    rng = np.random.default_rng(5)
+    counts = [cap, cap + 1, 0, 1, 9000, cap - 1, 3, 0, 0, 20000, 2, cap, 700, 130]
+    n = len(counts) * tile_bits - 777                       # the last tile is ragged
+    bits = np.zeros(n, np.uint8)
+    for ti, cnt in enumerate(counts):
+        hi = min((ti + 1) * tile_bits, n)
+        pos = rng.choice(np.arange(ti * tile_bits, hi), size=min(cnt, hi - ti * tile_bits), replace=False)
+        bits[pos] = 1
+    bits[len(counts[:3]) * tile_bits - 1] = 1               # a one on a tile's last bit, the next tile starts with one too
+    bits[3 * tile_bits] = 1
+    cols = 911                                              # not a multiple of 32: the compacted copy is coded
+    rows = n // cols
+    bits = bits[: rows * cols].reshape(rows, cols)
+    Mw = synth.pack_rows(bits)
+    so, nbits_o, ns_o = oracle.golomb_encode(Mw, cols)
+    M = ctx.matrix(rows, cols, Mw)
+    try:
+        for chunk in (256, 16):
+            s = ctx.golomb_encode(M, chunk_samples=chunk)
+            assert s.info.bitcount == nbits_o and s.info.nsamples == ns_o
+            by, _ = s.download()
+            assert np.array_equal(by, so)
+            M2 = ctx.matrix(rows, cols)
+            ctx.golomb_decode(s, M2)
+            assert np.array_equal(M2.download(), Mw)
+            M2.destroy(); s.destroy()
+    finally:
+        ctx.set_option("gol_list", 1)
+        M.destroy()
+
+
+def test_golomb_wide_tiles_list_route(ctx, oracle, synth):
+    """a stream long enough for the wide tiles (4096 words, list capacity 2048): sparse with a few dense stretches, so both
+    routes run in one launch with the default options"""
+    nwords = 148 * 16 * 4096 + 12345
+    rng = np.random.default_rng(11)
+    words = np.zeros(nwords, np.uint32)
+    pos = rng.integers(0, nwords * 32, size=nwords * 32 // 700)
+    np.bitwise_or.at(words, pos >> 5, (np.uint32(1) << (31 - (pos & 31)).astype(np.uint32)))
+    for w0 in (0, 5 * 4096 + 100, nwords - 9000):
+        words[w0: w0 + 6000] = rng.integers(0, 1 << 32, size=6000, dtype=np.uint64).astype(np.uint32)
+    cols = 4096
+    rows = nwords * 32 // cols
+    Mw = words[: rows * cols // 32].reshape(rows, cols // 32)
+    so, nbits_o, ns_o = oracle.golomb_encode(Mw, cols)
+    M = ctx.matrix(rows, cols, Mw)
+    s = ctx.golomb_encode(M)
+    assert s.info.bitcount == nbits_o and s.info.nsamples == ns_o
+    by, _ = s.download()
+    assert np.array_equal(by, so)
+    M2 = ctx.matrix(rows, cols)
+    ctx.golomb_decode(s, M2)
+    assert np.array_equal(M2.download(), Mw)
+    for x in (M, M2, s):
+        x.destroy()
+
+
+@pytest.mark.parametrize("algo", [2, 3, 1])
 @pytest.mark.parametrize("dense_rows", [40, 400])
 def test_golomb_sparse_then_dense(ctx, oracle, synth, algo, dense_rows):
     """a long almost empty stretch (k adapts upwards) followed by dense rows: every one of the dense part costs k + 1 bits until
     the coder has adapted back, so those tiles' codes are many times their input (the scatter's straight-to-global path) and,
     with enough dense rows, the whole code outgrows the pre-sized buffer (the exact-size path takes over)"""
+    ctx.set_option("gol_list", 2 if algo == 3 else 1)      # "3": algo 2 with the sparse tiles coded from their lists
+    algo = min(algo, 2)
     ctx.set_option("gol_algo", algo)
     rows, cols = 2048 + dense_rows, 1024
     rng = np.random.default_rng(dense_rows)
@@ -313,6 +381,7 @@ def test_golomb_sparse_then_dense(ctx, oracle, synth, algo, dense_rows):
     ctx.golomb_decode(s, M2)
     assert np.array_equal(M2.download(), Mw)
     ctx.set_option("gol_algo", 2)
+    ctx.set_option("gol_list", 1)
 
 
 def test_golomb_code_outgrows_the_presized_buffer(ctx, bic, oracle, synth):
