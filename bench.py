@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--wait-mode", type=int, default=1, help="0 cudaStreamSynchronize, 1 poll+yield, 2 blocking event")
     ap.add_argument("--gol-onepass", type=int, default=0, help="1 single-pass Golomb encoder, 0 three-kernel pipeline")
     ap.add_argument("--gol-list", type=int, default=1, help="Golomb: sparse tiles coded from a list of their ones: 0 never, 1 wide tiles only, 2 always")
+    ap.add_argument("--gol-scan", type=int, default=1, help="Golomb: scans over the tiles 0 in the passes' last CTA, 1 as their own launch for long streams, 2 always")
     ap.add_argument("--dict-algo", type=int, default=2, help="2 cluster chain (dict3.cu), 1 launch-per-changed-atom resolve (dict2.cu), 0 per-atom walk")
     ap.add_argument("--chain-cluster", type=int, default=16, help="CTAs per cluster of the chain kernel")
     ap.add_argument("--e2e-planes", action="store_true", help="e2e from 16 host P4 planes (bic_encode_raster) instead of the 16-bit P5 payload")
@@ -373,6 +374,7 @@ def main():
             c.set_option("wait_mode", args.wait_mode)
             c.set_option("gol_onepass", args.gol_onepass)
             c.set_option("gol_list", args.gol_list)
+            c.set_option("gol_scan", args.gol_scan)
             c.set_option("dict_algo", args.dict_algo)
             c.set_option("chain_cluster", args.chain_cluster)
             self.X, self.E = c.matrix(n, m), c.matrix(n, m)
@@ -849,7 +851,7 @@ def main():
     if use_pipe:
         pipe = bic.Pipeline(local_rank, args.streams)
         for name, val in (("first_batch", args.first_batch), ("next_batch", args.next_batch), ("dict_algo", args.dict_algo),
-                          ("chain_cluster", args.chain_cluster), ("gol_list", args.gol_list)):
+                          ("chain_cluster", args.chain_cluster), ("gol_list", args.gol_list), ("gol_scan", args.gol_scan)):
             pipe.set_option(name, val)
 
     def pipe_steps_resident(nsteps):

@@ -83,6 +83,7 @@ struct bic_ctx {
   cudaEvent_t wait_ev = nullptr, wait_ev_blocking = nullptr;
   int gol_algo = 2;        // 2: wide-tile encoder with fused scans (coding2.cu), 1: the first formulation (coding.cu)
   int gol_list = 1;        // sparse tiles coded from a list of their ones (coding2.cu): 0 never, 1 for streams long enough for wide tiles, 2 always
+  int gol_scan = 1;        // tile scans of coding2.cu: 0 in the passes' last CTA, 1 as their own launch for long streams (>= 8192 tiles), 2 always
   int gol_presize_pct = 125;  // the asynchronous encoders size the code buffer to this percentage of the input bits (+ 4 KB)
   int gol_onepass = 0;     // 1: single-pass Golomb encoder (decoupled look-back) when the buffer is pre-sized
   int coef_algo = 1;  // 1: dictionaries of >= 64 atoms use the weight-sorted warp-per-row coefficient kernel; 0: always lane per row

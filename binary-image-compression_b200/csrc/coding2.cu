@@ -56,6 +56,7 @@ struct G2Seg {
 struct G2Params {
   G2Seg s[G2_MAXSEG];
   uint32_t nseg;
+  uint32_t sep_scan;                 // 1: the scans over the tiles run as their own launch (k_g2_scan_tiles), not in the passes' last CTA
 };
 
 // Byte-at-a-time fast path. Once a thread's k is known to be constant (g2_k_stable) and small (<= 3: dense data, where a byte holds
@@ -98,15 +99,41 @@ __device__ __forceinline__ void g2_load(const G2Seg& g, uint64_t w0, uint32_t (&
 // ones of the 16 words and the bit index (inside the tile) of the last one, -1 if none
 template <int WPT>
 __device__ __forceinline__ void g2_count(const uint32_t (&v)[WPT], uint32_t* c, int* last) {
-  uint32_t n = 0;
-  int l = -1;
+  uint32_t n = 0, lw = 0;
+  int li = 0;
 #pragma unroll
   for (int i = 0; i < WPT; ++i) {
     n += __popc(v[i]);
-    if (v[i]) l = (int)(threadIdx.x * (WPT * 32) + i * 32 + (32 - __ffs(v[i])));
+    if (v[i]) { lw = v[i]; li = i; }                 // two selects per word; the bit position is worked out once, below
   }
   *c = n;
-  *last = l;
+  *last = lw ? (int)(threadIdx.x * (WPT * 32) + li * 32 + (32 - __ffs(lw))) : -1;
+}
+
+// the count pass's own scan: exclusive prefix of the ones (list offsets) and only the MAXIMUM of the last-one positions
+__device__ __forceinline__ void g2_scan_count(uint32_t c, int last, uint32_t* ex_c, uint32_t* tot_c, int* tot_last, int* s_w) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  const int wmax = __reduce_max_sync(0xffffffffu, last);
+  if (lane == 31) { s_w[wib] = (int)inc; s_w[8 + wib] = wmax; }
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+  int totm = -1;
+#pragma unroll
+  for (int w = 0; w < G2_THREADS / 32; ++w) {
+    const uint32_t x = (uint32_t)s_w[w];
+    if (w < wib) base += x;
+    tot += x;
+    totm = max(totm, s_w[8 + w]);
+  }
+  *ex_c = base + inc - c;
+  *tot_c = tot;
+  *tot_last = totm;
 }
 
 // exclusive prefix sum and exclusive prefix max over the CTA's 256 threads (s_w: 16 words of shared memory)
@@ -171,9 +198,9 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_count(G2Params P) {
   uint32_t v[WPT];
   g2_load(g, (uint64_t)tile * G2_TILE_WORDS(WPT) + threadIdx.x * WPT, v);
   uint32_t c, ex_c, tot_c;
-  int last, ex_last, tot_last;
+  int last, tot_last;
   g2_count(v, &c, &last);
-  g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
+  g2_scan_count(c, last, &ex_c, &tot_c, &tot_last, s_w);
   if (g.list && c && tot_c <= G2_LIST_CAP(WPT)) {                       // a sparse tile: my ones go into the tile's list
     uint32_t* L = g.list + (uint64_t)tile * G2_LIST_CAP(WPT) + ex_c;
 #pragma unroll
@@ -189,9 +216,12 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_count(G2Params P) {
   if (threadIdx.x == 0) {
     g.ones[tile] = tot_c;
     g.last[tile] = tot_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + tot_last : -1;
-    __threadfence();
-    s_last_cta = (atomicAdd(g.done, 1u) == g.ntiles - 1);
+    if (!P.sep_scan) {
+      __threadfence();
+      s_last_cta = (atomicAdd(g.done, 1u) == g.ntiles - 1);
+    }
   }
+  if (P.sep_scan) return;
   __syncthreads();
   if (!s_last_cta) return;
   __threadfence();
@@ -344,9 +374,12 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
   g2_excl_sum_u64(mybits, &tot, s_a);
   if (threadIdx.x == 0) {
     g.bits[tile] = tot;
-    __threadfence();
-    s_last_cta = (atomicAdd(g.done + 1, 1u) == g.ntiles - 1);
+    if (!P.sep_scan) {
+      __threadfence();
+      s_last_cta = (atomicAdd(g.done + 1, 1u) == g.ntiles - 1);
+    }
   }
+  if (P.sep_scan) return;
   __syncthreads();
   if (!s_last_cta) return;
   __threadfence();
@@ -372,6 +405,88 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_lengths(G2Params P) {
     if (g.gbp) {            // a shard: the stream's totals are the business of k_g2_shard_base2; this rank's code bits are all it needs
       g.info[2] = carry;
     } else {
+      g.info[0] = total;
+      g.info[1] = ones + 1;
+      g.info[2] = carry;
+      g.info[3] = consumed;
+      g.info[4] = (total + 64 > g.cap_bits) ? 1ull : 0ull;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the scans over the tiles as their own launch (long streams)
+// One CTA of 1024 threads per stream. PASS 0 (after the count pass): ones / last -> ones_before / last_before. PASS 1 (after the
+// length pass): bits -> bits_before and the stream's totals in info[]. In the passes' last CTA the same scans are a serial tail
+// of 256 threads (ncu, 2^31 bits at 0.1 % ones: the SMs idle for 44 % of the count pass and 35 % of the length pass behind it).
+#define G2_SCAN_THREADS 1024
+template <typename T, bool MAX>
+__device__ __forceinline__ T g2_block_excl_1024(T v, T ident, T* total, T* s_w /* 32 */) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  T inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const T y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = MAX ? (inc > y ? inc : y) : inc + y;
+  }
+  T excl = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) excl = ident;
+  __syncthreads();
+  if (lane == 31) s_w[wib] = inc;
+  __syncthreads();
+  T base = ident, tot = ident;
+  for (int w = 0; w < G2_SCAN_THREADS / 32; ++w) {
+    const T x = s_w[w];
+    if (w < wib) base = MAX ? (base > x ? base : x) : base + x;
+    tot = MAX ? (tot > x ? tot : x) : tot + x;
+  }
+  if (total) *total = tot;
+  return MAX ? (base > excl ? base : excl) : base + excl;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(G2_SCAN_THREADS) k_g2_scan_tiles(G2Params P) {
+  __shared__ unsigned long long s_a[32];
+  __shared__ long long s_b[32];
+  const G2Seg& g = P.s[blockIdx.x];
+  const uint64_t per = div_up_u64(g.ntiles, G2_SCAN_THREADS);
+  const uint64_t t0 = min((uint64_t)threadIdx.x * per, (uint64_t)g.ntiles), t1 = min(t0 + per, (uint64_t)g.ntiles);
+  if (PASS == 0) {
+    const uint32_t* __restrict__ ones = g.ones;
+    const long long* __restrict__ lastp = g.last;
+    unsigned long long* __restrict__ ob = g.ones_before;
+    long long* __restrict__ lbp = g.last_before;
+    unsigned long long sum = 0;
+    long long mx = -1;
+#pragma unroll 4
+    for (uint64_t i = t0; i < t1; ++i) { sum += ones[i]; const long long l = lastp[i]; mx = mx > l ? mx : l; }
+    unsigned long long run = g2_block_excl_1024<unsigned long long, false>(sum, 0ull, nullptr, s_a);
+    long long runm = g2_block_excl_1024<long long, true>(mx, -1ll, nullptr, s_b);
+#pragma unroll 4
+    for (uint64_t i = t0; i < t1; ++i) {
+      ob[i] = run;
+      lbp[i] = runm;
+      run += ones[i];
+      const long long l = lastp[i];
+      runm = runm > l ? runm : l;
+    }
+  } else {
+    const unsigned long long* __restrict__ bitsp = g.bits;
+    unsigned long long* __restrict__ bbp = g.bits_before;
+    unsigned long long sum = 0;
+#pragma unroll 4
+    for (uint64_t i = t0; i < t1; ++i) sum += bitsp[i];
+    unsigned long long carry;
+    unsigned long long run = g2_block_excl_1024<unsigned long long, false>(sum, 0ull, &carry, s_a);
+#pragma unroll 4
+    for (uint64_t i = t0; i < t1; ++i) { bbp[i] = run; run += bitsp[i]; }
+    if (threadIdx.x == 0) {            // the stream's totals, as in the length pass's last CTA
+      const uint64_t lt = g.ntiles - 1;
+      const unsigned long long ones = g.ones_before[lt] + g.ones[lt];
+      const long long lastg = g.last_before[lt] > g.last[lt] ? g.last_before[lt] : g.last[lt];
+      const unsigned long long consumed = (unsigned long long)(lastg + 1);
+      const unsigned long long x = g.N - consumed;
+      const uint32_t k = golomb_k(ones, consumed);
+      const unsigned long long total = carry + k + (x >> k) + 1;
       g.info[0] = total;
       g.info[1] = ones + 1;
       g.info[2] = carry;
@@ -803,14 +918,18 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
     outs[i]->info.cols = M->cols;
     outs[i]->info.bitcount = outs[i]->info.nsamples = outs[i]->info.nchunks = 0;
   }
+  // gol_scan: 0 scans in the passes' last CTA, 2 always as their own launch, 1 (default) their own launch for long streams
+  P.sep_scan = (c->gol_scan == 2 || (c->gol_scan == 1 && ntiles_total >= 8192)) ? 1u : 0u;
   BIC_PROF(c, KID_GOL_TILE_COUNTS);
   if (WPT == 16) k_g2_count<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   else k_g2_count<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   BIC_LAUNCH_CHECK(c);
+  if (P.sep_scan) { k_g2_scan_tiles<0><<<nmat, G2_SCAN_THREADS, 0, c->stream>>>(P); BIC_LAUNCH_CHECK(c); }
   BIC_PROF(c, KID_GOL_LENGTHS);
   if (WPT == 16) k_g2_lengths<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   else k_g2_lengths<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   BIC_LAUNCH_CHECK(c);
+  if (P.sep_scan) { k_g2_scan_tiles<1><<<nmat, G2_SCAN_THREADS, 0, c->stream>>>(P); BIC_LAUNCH_CHECK(c); }
   uint64_t maxN = 0;
   for (int i = 0; i < nmat; ++i) maxN = P.s[i].N > maxN ? P.s[i].N : maxN;
   BIC_PROF(c, KID_GOL_SCAN_B);

@@ -594,6 +594,7 @@ extern "C" bic_status bic_ctx_set_option(bic_ctx* c, const char* name, int64_t v
   if (!c || !name) return BIC_ERR_INVALID;
   if (!strcmp(name, "wait_mode")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->wait_mode = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_algo")) { if (value < 1 || value > 2) return BIC_ERR_INVALID; c->gol_algo = (int)value; return BIC_OK; }
+  if (!strcmp(name, "gol_scan")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->gol_scan = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_list")) { if (value < 0 || value > 2) return BIC_ERR_INVALID; c->gol_list = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_presize_pct")) { if (value < 1 || value > 1000) return BIC_ERR_INVALID; c->gol_presize_pct = (int)value; return BIC_OK; }
   if (!strcmp(name, "gol_onepass")) { c->gol_onepass = value != 0; return BIC_OK; }

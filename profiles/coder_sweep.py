@@ -23,6 +23,10 @@ N = 1 << LOG2
 cols = 1 << 15
 rows = N // cols
 ctx = bic.Context(0)
+import os  # noqa: E402
+for kv in filter(None, os.environ.get("BIC_SWEEP_OPTS", "").split(",")):   # e.g. BIC_SWEEP_OPTS=gol_list=0,gol_scan=0
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 ref = load_reference()
 out = []
 RHOS = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0.001, 0.003, 0.01, 0.03, 0.1, 0.2, 0.5]

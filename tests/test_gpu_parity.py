@@ -258,15 +258,17 @@ CODER_SHAPES = [(1, 1, 0.0), (1, 1, 1.0), (1, 32, 0.0), (3, 64, 0.5), (17, 100, 
 CODER_SHAPES_BIG = [(700, 1024, 0.5), (1200, 1024, 0.003), (640, 2048, 0.12), (300, 4100, 0.9), (2, 600000, 0.0005), (1500, 1000, 0.0)]
 
 
-@pytest.mark.parametrize("algo,onepass,lst", [(2, 0, 1), (2, 0, 2), (1, 0, 1), (1, 1, 1)])
+@pytest.mark.parametrize("algo,onepass,lst,scan", [(2, 0, 1, 1), (2, 0, 2, 2), (2, 0, 2, 0), (1, 0, 1, 1), (1, 1, 1, 1)])
 @pytest.mark.parametrize("rows,cols,rho", CODER_SHAPES + CODER_SHAPES_BIG)
-def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho, algo, onepass, lst):
+def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, cols, rho, algo, onepass, lst, scan):
     # algo 2: wide tiles, scans fused into the passes, register-assembled codewords (coding2.cu); 1: the first formulation
     # (coding.cu), as three kernels + scans (onepass 0) or one kernel with decoupled look-back (onepass 1).
-    # lst 2: sparse tiles are coded from the list of their ones whatever the tile width (default: wide tiles only)
+    # lst 2: sparse tiles are coded from the list of their ones whatever the tile width (default: wide tiles only);
+    # scan 2 / 0: the scans over the tiles always / never as their own launch (default: for long streams)
     ctx.set_option("gol_algo", algo)
     ctx.set_option("gol_onepass", onepass)
     ctx.set_option("gol_list", lst)
+    ctx.set_option("gol_scan", scan)
     rng = np.random.default_rng(rows * 31 + cols)
     bits = (rng.random((rows, cols)) < rho).astype(np.uint8)
     Mw = synth.pack_rows(bits)
@@ -291,13 +293,16 @@ def test_golomb_stream_is_byte_identical_and_decodes(ctx, oracle, synth, rows, c
     ctx.set_option("gol_onepass", 0)
     ctx.set_option("gol_algo", 2)
     ctx.set_option("gol_list", 1)
+    ctx.set_option("gol_scan", 1)
 
 
+@pytest.mark.parametrize("scan", [2, 0])
 @pytest.mark.parametrize("lst", [2, 1, 0])
-def test_golomb_list_and_word_tiles_mixed(ctx, oracle, synth, lst):
+def test_golomb_list_and_word_tiles_mixed(ctx, oracle, synth, lst, scan):
     """tiles with exactly the list capacity, one more, none, a single one, and dense tiles, in one stream: the route is chosen
     tile by tile from the tile's own count (narrow tiles: 1024 words, capacity 512; lst 2 forces lists on them)"""
     ctx.set_option("gol_list", lst)
+    ctx.set_option("gol_scan", scan)
     tile_bits, cap = 1024 * 32, 512
     rng = np.random.default_rng(5)
     counts = [cap, cap + 1, 0, 1, 9000, cap - 1, 3, 0, 0, 20000, 2, cap, 700, 130]
@@ -327,10 +332,12 @@ def test_golomb_list_and_word_tiles_mixed(ctx, oracle, synth, lst):
             M2.destroy(); s.destroy()
     finally:
         ctx.set_option("gol_list", 1)
+        ctx.set_option("gol_scan", 1)
         M.destroy()
 
 
-def test_golomb_wide_tiles_list_route(ctx, oracle, synth):
+@pytest.mark.parametrize("scan", [2, 0])
+def test_golomb_wide_tiles_list_route(ctx, oracle, synth, scan):
     """a stream long enough for the wide tiles (4096 words, list capacity 2048): sparse with a few dense stretches, so both
     routes run in one launch with the default options"""
     nwords = 148 * 16 * 4096 + 12345
@@ -342,10 +349,13 @@ def test_golomb_wide_tiles_list_route(ctx, oracle, synth):
         words[w0: w0 + 6000] = rng.integers(0, 1 << 32, size=6000, dtype=np.uint64).astype(np.uint32)
     cols = 4096
     rows = nwords * 32 // cols
-    Mw = words[: rows * cols // 32].reshape(rows, cols // 32)
+    w32 = words[: rows * cols // 32].reshape(rows, cols // 32).astype(np.uint64)
+    Mw = (w32[:, 0::2] << np.uint64(32)) | w32[:, 1::2]       # reference layout: 64-bit blocks, first column in the top bit
     so, nbits_o, ns_o = oracle.golomb_encode(Mw, cols)
+    ctx.set_option("gol_scan", scan)
     M = ctx.matrix(rows, cols, Mw)
     s = ctx.golomb_encode(M)
+    ctx.set_option("gol_scan", 1)
     assert s.info.bitcount == nbits_o and s.info.nsamples == ns_o
     by, _ = s.download()
     assert np.array_equal(by, so)

@@ -33,7 +33,7 @@ def _pages(synth, n, rows, cols, noise_every=4):
     return out
 
 
-@pytest.mark.parametrize("first,nxt,slots", [(2, 2, 4), (1, 1, 3), (5, 3, 8), (64, 1, 2)])
+@pytest.mark.parametrize("first,nxt,slots", [(2, 2, 4), (1, 1, 3), (5, 3, 8), (64, 1, 2), (2, 2, 5)])
 def test_pipeline_containers_equal_the_synchronous_encoder(bic, ctx, synth, oracle, first, nxt, slots):
     rows, cols, W, K = 328, 264, 8, 32
     pages = _pages(synth, 10, rows, cols)
@@ -50,6 +50,9 @@ def test_pipeline_containers_equal_the_synchronous_encoder(bic, ctx, synth, orac
     pipe = bic.Pipeline(0, slots)
     pipe.set_option("first_batch", first)
     pipe.set_option("next_batch", nxt)
+    if slots == 5:      # the coder's other routes inside the pipeline: lists for sparse tiles, tile scans as their own launches
+        pipe.set_option("gol_list", 2)
+        pipe.set_option("gol_scan", 2)
     try:
         bufs, jobs = [], []
         for bits in pages:
