@@ -557,40 +557,22 @@ struct G2Out {
   }
 };
 
+// a tile coded from its words (the dense route): thread j owns words [16 j, 16 j + 16) of the tile
 template <int WPT>
-__global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
-  __shared__ int s_w[16];
-  __shared__ unsigned long long s_a[8];
-  __shared__ uint32_t s_out[G2_STAGE_WORDS(WPT)];
-  uint32_t tile;
-  const G2Seg& g = g2_segment(P, &tile);
-  if (g.info[4]) return;                                                 // the code does not fit: nothing is written
-  const GolBase gb = g.gbp ? *g.gbp : g.gb;
-  const long long lb = g.last_before[tile];
-  const uint32_t nones = g.list ? g.ones[tile] : 0xffffffffu;
-  const bool sparse = nones <= G2_LIST_CAP(WPT);                          // uniform over the CTA
+__device__ __forceinline__ void g2_scatter_word_tile(const G2Seg& g, const GolBase& gb, uint32_t tile, int* s_w, unsigned long long* s_a, uint32_t* s_out) {
   uint32_t v[WPT];
   const uint64_t w0 = (uint64_t)tile * G2_TILE_WORDS(WPT) + threadIdx.x * WPT;
-  uint32_t c = 0, li0 = 0, li1 = 0;
-  unsigned long long t, mybits;
-  long long prev;
-  if (sparse) {
-    mybits = g2_list_span<WPT>(g, gb, tile, nones, lb, &li0, &li1, &t, &prev);
-    c = li1 - li0;
-  } else {
-    g2_load(g, w0, v);
-    uint32_t ex_c, tot_c;
-    int last, ex_last, tot_last;
-    g2_count(v, &c, &last);
-    g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
-    t = gb.t0 + g.ones_before[tile] + ex_c;
-    const long long pvl = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;
-    prev = pvl >= 0 ? pvl + gb.pos0 : gb.prev0;
-    mybits = g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x];
-  }
+  g2_load(g, w0, v);
+  uint32_t c, ex_c, tot_c;
+  int last, ex_last, tot_last;
+  g2_count(v, &c, &last);
+  g2_scan(c, last, &ex_c, &ex_last, &tot_c, &tot_last, s_w);
+  unsigned long long t = gb.t0 + g.ones_before[tile] + ex_c;
+  const long long lb = g.last_before[tile];
+  const long long pvl = ex_last >= 0 ? (long long)tile * G2_TILE_BITS(WPT) + ex_last : lb;
+  long long prev = pvl >= 0 ? pvl + gb.pos0 : gb.prev0;
   const long long tb = (long long)(w0 * 32) + gb.pos0;
-  const uint32_t* const lst = sparse ? g.list + (uint64_t)tile * G2_LIST_CAP(WPT) : nullptr;
-  const long long tileb = (long long)tile * G2_TILE_BITS(WPT) + gb.pos0;
+  const unsigned long long mybits = g.tbits[(uint64_t)tile * G2_THREADS + threadIdx.x];
   unsigned long long tot;
   const unsigned long long ex = g2_excl_sum_u64(mybits, &tot, s_a);
   const unsigned long long o0 = g.bits_before[tile] + gb.out0;         // bit offset inside this shard's own buffer
@@ -610,30 +592,6 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
       w.first_wp = w.wp; w.first_val = 0; w.first_pending = (ob & 31) != 0;   // a range that starts on a word boundary shares nothing there
       w.limit = (uint32_t)span_words;
       const uint32_t cmask32 = g.chunk - 1;
-      if (sparse) {
-        for (uint32_t i = li0; i < li1; ++i) {                             // my samples from the tile's list, k re-derived for each
-          const long long pos = tileb + (long long)__ldcg(lst + i);
-          const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
-          const unsigned long long x = (unsigned long long)(pos - prev - 1);
-          if ((t & cmask) == 0) {
-            const unsigned long long slot = (t >> clog) - gb.chunk0;
-            BIC_DCHECK(slot <= (g.N >> clog) + 1);
-            g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
-            g.index[2 * slot + 1] = (unsigned long long)(prev + 1);
-          }
-          const unsigned long long u = x >> k;
-          const uint32_t rem = (uint32_t)(x & ((1ull << k) - 1));
-          if (k + u + 1 <= 32) {
-            w.put((rem << (uint32_t)(u + 1)) | 1u, k + (uint32_t)u + 1);
-          } else {
-            if (k) w.put(rem, k);
-            w.zeros(u);
-            w.put(1u, 1);
-          }
-          ++t;
-          prev = pos;
-        }
-      } else {
       // my first one (see the length pass): codeword from the full-width run length, then the mode of the rest
       uint32_t fw = 0, fi = 0;
 #pragma unroll
@@ -778,7 +736,6 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
           }
         }
       }
-      }
       w.finish();
       BIC_DCHECK((unsigned long long)w.wp * 32 + w.fill == (o0 + ex - base) + mybits);   // I wrote exactly the bits the length pass counted
     }
@@ -793,20 +750,6 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
   } else if (c) {
     // a tile whose code is far longer than its input (long unary parts): codewords go straight to global memory
     unsigned long long o = o0 + ex;
-    if (sparse) {
-      for (uint32_t i = li0; i < li1; ++i) {
-        const long long pos = tileb + (long long)__ldcg(lst + i);
-        const unsigned long long x = (unsigned long long)(pos - prev - 1);
-        const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
-        if ((t & cmask) == 0) { g.index[2 * ((t >> clog) - gb.chunk0)] = o + goff; g.index[2 * ((t >> clog) - gb.chunk0) + 1] = (unsigned long long)(prev + 1); }
-        put_bits(g.out, o, (uint32_t)(x & ((1ull << k) - 1)), k);
-        const unsigned long long stop = o + k + (x >> k);
-        put_one(g.out, stop);
-        o = stop + 1;
-        prev = pos;
-        ++t;
-      }
-    } else {
 #pragma unroll
     for (int i = 0; i < WPT; ++i) {
       uint32_t b = v[i];
@@ -825,8 +768,92 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
         ++t;
       }
     }
+  }
+}
+
+// a sparse tile coded from the list of its ones: thread j owns samples [i0, i1) (g2_list_span), k re-derived for every sample
+template <int WPT>
+__device__ __forceinline__ void g2_scatter_list_tile(const G2Seg& g, const GolBase& gb, uint32_t tile, uint32_t nones, unsigned long long* s_a, uint32_t* s_out) {
+  const long long lb = g.last_before[tile];
+  uint32_t li0, li1;
+  unsigned long long t;
+  long long prev;
+  const unsigned long long mybits = g2_list_span<WPT>(g, gb, tile, nones, lb, &li0, &li1, &t, &prev);
+  const uint32_t* const lst = g.list + (uint64_t)tile * G2_LIST_CAP(WPT);
+  const long long tileb = (long long)tile * G2_TILE_BITS(WPT) + gb.pos0;
+  unsigned long long tot;
+  const unsigned long long ex = g2_excl_sum_u64(mybits, &tot, s_a);
+  const unsigned long long o0 = g.bits_before[tile] + gb.out0;
+  const unsigned long long base = o0 & ~31ull;
+  const unsigned long long goff = gb.code0 - gb.out0;
+  const unsigned long long span_words = ((o0 - base) + tot + 31) >> 5;
+  const bool staged = span_words <= G2_STAGE_WORDS(WPT);
+  const unsigned long long cmask = (unsigned long long)g.chunk - 1;
+  const int clog = 31 - __clz(g.chunk);
+  if (staged) {
+    for (unsigned i = threadIdx.x; i < (unsigned)span_words; i += blockDim.x) s_out[i] = 0;
+    __syncthreads();
+    if (li1 > li0) {
+      const uint32_t ob = (uint32_t)(o0 + ex - base);
+      G2Out w;
+      w.s_out = s_out; w.wp = ob >> 5; w.fill = ob & 31; w.cur = 0;
+      w.first_wp = w.wp; w.first_val = 0; w.first_pending = (ob & 31) != 0;
+      w.limit = (uint32_t)span_words;
+      for (uint32_t i = li0; i < li1; ++i) {
+        const long long pos = tileb + (long long)__ldcg(lst + i);
+        const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+        const unsigned long long x = (unsigned long long)(pos - prev - 1);
+        if ((t & cmask) == 0) {                                          // chunk index: where this sample's codeword and run start
+          const unsigned long long slot = (t >> clog) - gb.chunk0;
+          BIC_DCHECK(slot <= (g.N >> clog) + 1);
+          g.index[2 * slot] = base + (unsigned long long)w.wp * 32 + w.fill + goff;
+          g.index[2 * slot + 1] = (unsigned long long)(prev + 1);
+        }
+        const unsigned long long u = x >> k;
+        const uint32_t rem = (uint32_t)(x & ((1ull << k) - 1));
+        if (k + u + 1 <= 32) {
+          w.put((rem << (uint32_t)(u + 1)) | 1u, k + (uint32_t)u + 1);
+        } else {
+          if (k) w.put(rem, k);
+          w.zeros(u);
+          w.put(1u, 1);
+        }
+        ++t;
+        prev = pos;
+      }
+      w.finish();
+      BIC_DCHECK((unsigned long long)w.wp * 32 + w.fill == (o0 + ex - base) + mybits);
+    }
+    __syncthreads();
+    uint32_t* gout = g.out + (base >> 5);
+    for (unsigned i = threadIdx.x; i < (unsigned)span_words; i += blockDim.x) {
+      const uint32_t wv = s_out[i];
+      if (!wv) continue;
+      if (i == 0 || i == (unsigned)span_words - 1) atomicOr(gout + i, bswap32(wv));
+      else gout[i] = bswap32(wv);
+    }
+  } else {
+    unsigned long long o = o0 + ex;                                      // codes far longer than the input: straight to global memory
+    for (uint32_t i = li0; i < li1; ++i) {
+      const long long pos = tileb + (long long)__ldcg(lst + i);
+      const unsigned long long x = (unsigned long long)(pos - prev - 1);
+      const uint32_t k = golomb_k(t, (unsigned long long)(prev + 1));
+      if ((t & cmask) == 0) { g.index[2 * ((t >> clog) - gb.chunk0)] = o + goff; g.index[2 * ((t >> clog) - gb.chunk0) + 1] = (unsigned long long)(prev + 1); }
+      put_bits(g.out, o, (uint32_t)(x & ((1ull << k) - 1)), k);
+      const unsigned long long stop = o + k + (x >> k);
+      put_one(g.out, stop);
+      o = stop + 1;
+      prev = pos;
+      ++t;
     }
   }
+}
+
+// the run closed by the virtual one after the matrix's last bit (one thread of the stream's first tile)
+__device__ __forceinline__ void g2_scatter_closing(const G2Seg& g, const GolBase& gb, uint32_t tile) {
+  const unsigned long long goff = gb.code0 - gb.out0;
+  const unsigned long long cmask = (unsigned long long)g.chunk - 1;
+  const int clog = 31 - __clz(g.chunk);
   if (gb.closing && tile == 0 && threadIdx.x == 0) {                   // the run closed by the virtual one
     const bool dyn = gb.closing == 2;
     const unsigned long long tt = dyn ? g.info[1] - 1 : gb.close_t, consumed = dyn ? g.info[3] : gb.close_consumed;
@@ -838,6 +865,35 @@ __global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
     oo += k + (x >> k);
     put_one(g.out, oo);
   }
+}
+
+// Two launches: the tiles coded from their words here (the closing run too), the tiles coded from their lists in
+// k_g2_scatter_list below; a CTA whose tile belongs to the other kernel leaves at once. (One kernel with both routes cost the
+// word route a quarter of its speed on dense wide-tile streams: 4.9 against 3.9 ms at 2^31 bits, 20 % ones.)
+template <int WPT>
+__global__ void __launch_bounds__(G2_THREADS) k_g2_scatter(G2Params P) {
+  __shared__ int s_w[16];
+  __shared__ unsigned long long s_a[8];
+  __shared__ uint32_t s_out[G2_STAGE_WORDS(WPT)];
+  uint32_t tile;
+  const G2Seg& g = g2_segment(P, &tile);
+  if (g.info[4]) return;                                                 // the code does not fit: nothing is written
+  const GolBase gb = g.gbp ? *g.gbp : g.gb;
+  if (!(g.list && g.ones[tile] <= G2_LIST_CAP(WPT))) g2_scatter_word_tile<WPT>(g, gb, tile, s_w, s_a, s_out);   // uniform over the CTA
+  g2_scatter_closing(g, gb, tile);
+}
+
+template <int WPT>
+__global__ void __launch_bounds__(G2_THREADS) k_g2_scatter_list(G2Params P) {
+  __shared__ unsigned long long s_a[8];
+  __shared__ uint32_t s_out[G2_STAGE_WORDS(WPT)];
+  uint32_t tile;
+  const G2Seg& g = g2_segment(P, &tile);
+  if (g.info[4] || !g.list) return;
+  const uint32_t nones = g.ones[tile];
+  if (nones > G2_LIST_CAP(WPT)) return;
+  const GolBase gb = g.gbp ? *g.gbp : g.gb;
+  g2_scatter_list_tile<WPT>(g, gb, tile, nones, s_a, s_out);
 }
 
 // ------------------------------------------------------------------ host side
@@ -939,6 +995,11 @@ bic_status bic_k_golomb_encode_multi(bic_ctx* c, const bic_mat* const* mats, int
   if (WPT == 16) k_g2_scatter<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   else k_g2_scatter<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   BIC_LAUNCH_CHECK(c);
+  if (use_list) {
+    if (WPT == 16) k_g2_scatter_list<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+    else k_g2_scatter_list<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+    BIC_LAUNCH_CHECK(c);
+  }
   return BIC_OK;
 }
 
@@ -1042,6 +1103,11 @@ bic_status bic_g2_scatter(bic_ctx* c, void* plan, const GolBase* gb, uint32_t ch
   if (pl->WPT == 16) k_g2_scatter<16><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
   else k_g2_scatter<4><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
   BIC_LAUNCH_CHECK(c);
+  if (g.list) {
+    if (pl->WPT == 16) k_g2_scatter_list<16><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
+    else k_g2_scatter_list<4><<<pl->ntiles, G2_THREADS, 0, c->stream>>>(pl->P);
+    BIC_LAUNCH_CHECK(c);
+  }
   return BIC_OK;
 }
 
@@ -1243,5 +1309,10 @@ bic_status bic_k_golomb_encode_multi_sharded(bic_ctx* c, const bic_mat* const* m
   if (WPT == 16) k_g2_scatter<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   else k_g2_scatter<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
   BIC_LAUNCH_CHECK(c);
+  if (use_list) {
+    if (WPT == 16) k_g2_scatter_list<16><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+    else k_g2_scatter_list<4><<<tile0, G2_THREADS, 0, c->stream>>>(P);
+    BIC_LAUNCH_CHECK(c);
+  }
   return BIC_OK;
 }
