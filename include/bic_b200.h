@@ -74,6 +74,10 @@ bic_status bic_ctx_wait_ctx(bic_ctx* waiter, bic_ctx* signal);
  * "chain_bucket_cap": entries of dict3.cu's per-atom row buckets, -1 (default) = 2 per row; 0 = always scan the list.
  * "gol_algo": 2 (default) = Golomb encoder with wide tiles, scans fused into the passes and register-assembled codewords
  *   (coding2.cu), 1 = the first formulation (coding.cu: counts / scan / lengths / scan / scatter).
+ * "gol_list": coding2.cu codes a sparse tile (at most one bit in 64 set) from a list of its ones written by the count pass
+ *   instead of re-reading its words: 0 never, 1 (default) for streams long enough for the wide tiles, 2 always.
+ * "gol_scan": coding2.cu's scans over the tiles: 0 in the last CTA of the count / length pass, 1 (default) as their own
+ *   1024-thread launch for long streams (>= 8192 tiles), 2 always.
  * "gol_presize_pct": the encoders that do not wait for the bit count size the code buffer to this percentage of the input bits
  *   (default 125); a code that does not fit is re-encoded by the exact-size path (values below 100 exist to test that).
  * "gol_onepass": 1 = single-pass Golomb encoder with decoupled look-back, 0 (default) = counts / lengths / scatter.

@@ -200,3 +200,115 @@ def test_golomb_closed_form_and_constant_k_stretch(rho):
         assert all(ks[t] == k for t in mine[1:])
     if rho >= 0.03:
         assert certified > 0                                 # the certificate needs a few thousand samples of history
+
+
+# ---------------------------------------------------------------- coding2.cu: tiles routed by their own count (list / words)
+def tiled_encoder_model(bits, tile_bits, cap, threads, base_t=0, base_pos=0, base_prev=-1):
+    """What coding2.cu computes, with its data flow: per-tile ones and last-one position (count pass), exclusive scans over the
+    tiles (k_g2_scan_tiles), then per tile either the LIST route (tile has <= cap ones: thread j owns samples [j q, (j + 1) q),
+    q = ceil(ones / threads), previous one from the list or from last_before) or the WORD route (thread j owns a fixed stretch
+    of the tile's bits, previous one from the prefix maximum inside the tile or last_before), each thread producing the code
+    bits of ITS samples from the closed form alone. Returns (per-tile code bits, concatenated codeword list, routes)."""
+    n = len(bits)
+    ntiles = (n + tile_bits - 1) // tile_bits
+    ones_t, last_t, lists = [], [], []
+    for ti in range(ntiles):
+        seg = bits[ti * tile_bits: (ti + 1) * tile_bits]
+        pos = np.nonzero(seg)[0]
+        ones_t.append(len(pos))
+        last_t.append(ti * tile_bits + int(pos[-1]) if len(pos) else -1)
+        lists.append(pos if len(pos) <= cap else None)            # the count pass writes a list only for sparse tiles
+    ones_before = np.concatenate([[0], np.cumsum(ones_t)[:-1]]).astype(np.int64)
+    last_before, m = [], -1
+    for l in last_t:
+        last_before.append(m)
+        m = max(m, l)
+
+    def code(t, prev, pos):                                        # (k, run) of the sample closed by the one at `pos`
+        return closed_form_k(t, prev + 1), pos - prev - 1
+
+    words, tile_bits_out, routes = [], [], []
+    for ti in range(ntiles):
+        lb = last_before[ti]
+        out_tile = []
+        if lists[ti] is not None:                                  # ---- list route
+            routes.append("list")
+            L, nones = lists[ti], ones_t[ti]
+            q = (nones + threads - 1) // threads if nones else 0
+            for j in range(threads):
+                i0 = min(j * q, nones)
+                i1 = min(i0 + q, nones)
+                if i1 <= i0:
+                    continue
+                prev = base_pos + ti * tile_bits + int(L[i0 - 1]) if i0 else (lb + base_pos if lb >= 0 else base_prev)
+                t = base_t + int(ones_before[ti]) + i0
+                for i in range(i0, i1):
+                    pos = base_pos + ti * tile_bits + int(L[i])
+                    out_tile.append(code(t, prev, pos))
+                    prev, t = pos, t + 1
+        else:                                                      # ---- word route
+            routes.append("words")
+            per = tile_bits // threads
+            seg = bits[ti * tile_bits: (ti + 1) * tile_bits]
+            ex_c, ex_last = 0, -1
+            for j in range(threads):
+                mine = np.nonzero(seg[j * per: (j + 1) * per])[0] + j * per
+                pvl = ti * tile_bits + ex_last if ex_last >= 0 else lb
+                prev = pvl + base_pos if pvl >= 0 else base_prev
+                t = base_t + int(ones_before[ti]) + ex_c
+                for p in mine:
+                    pos = base_pos + ti * tile_bits + int(p)
+                    out_tile.append(code(t, prev, pos))
+                    prev, t = pos, t + 1
+                if len(mine):
+                    ex_c += len(mine)
+                    ex_last = int(mine[-1])
+        words += out_tile
+        tile_bits_out.append(sum(k + (x >> k) + 1 for k, x in out_tile))
+    return tile_bits_out, words, routes
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_tile_routed_encoder_model_equals_the_serial_coder(oracle, synth, seed):
+    """the per-tile routing of coding2.cu (list of ones for sparse tiles, words for the others, separate scans over the tiles)
+    reproduces the serial coder sample for sample: k from the closed form, run length from the neighbouring one, wherever that
+    one lives (same thread, another thread of the tile, an earlier tile of either route, or nowhere)"""
+    rng = np.random.default_rng(seed)
+    tile_bits, cap, threads = 2048, 32, 16
+    dens = [0.001, 0.01, 0.3, 0.0, 0.012, 0.02, 0.5, 0.0, 0.0005, 0.015, 0.2, 0.004]
+    bits = np.concatenate([(rng.random(tile_bits) < d).astype(np.uint8) for d in dens])[: len(dens) * tile_bits - 333]
+    per_tile, words, routes = tiled_encoder_model(bits, tile_bits, cap, threads)
+    assert "list" in routes and "words" in routes
+    ks = serial_golomb_ks(bits)
+    ones = np.nonzero(bits)[0]
+    runs = np.diff(np.concatenate([[-1], ones])) - 1
+    assert [w[0] for w in words] == ks
+    assert [w[1] for w in words] == [int(r) for r in runs]
+    # and the total is the oracle's bit count minus the closing sample
+    cols = 64
+    rows = len(bits) // cols
+    b2 = bits[: rows * cols]
+    per_tile2, words2, _ = tiled_encoder_model(b2, tile_bits, cap, threads)
+    _, nbits, ns = oracle.golomb_encode(synth.pack_rows(b2.reshape(rows, cols)), cols)
+    t, last = len(words2), (int(np.nonzero(b2)[0][-1]) if b2.any() else -1)
+    k = closed_form_k(t, last + 1)
+    closing = k + ((len(b2) - (last + 1)) >> k) + 1
+    assert sum(per_tile2) + closing == nbits and ns == t + 1
+
+
+def test_tile_routed_encoder_model_as_a_row_shard(oracle, synth):
+    """the same with a GolBase: the shard's samples continue the global stream (rank t0, position pos0, previous one prev0)"""
+    rng = np.random.default_rng(9)
+    cols, rows_a, rows_b = 128, 40, 56
+    bits = (rng.random((rows_a + rows_b) * cols) < 0.01).astype(np.uint8)
+    bits[rows_a * cols - 300: rows_a * cols + 200] = 0           # the run in progress crosses the seam
+    top, bot = bits[: rows_a * cols], bits[rows_a * cols:]
+    t0 = int(top.sum())
+    prev0 = int(np.nonzero(top)[0][-1])
+    _, words, routes = tiled_encoder_model(bot, 1024, 16, 8, base_t=t0, base_pos=rows_a * cols, base_prev=prev0)
+    assert "list" in routes
+    ks = serial_golomb_ks(bits)
+    ones = np.nonzero(bits)[0]
+    runs = np.diff(np.concatenate([[-1], ones])) - 1
+    assert [w[0] for w in words] == ks[t0:]
+    assert [w[1] for w in words] == [int(r) for r in runs[t0:]]
