@@ -774,7 +774,11 @@ class Context:
         info = EncodeInfo()
         if out is None:
             out = np.zeros(max(64 * 1024, 2 * raster.rows * ((raster.cols + 7) // 8) + 64 * 1024), np.uint8)
-        self._ck(self.L.bic_encode_raster_resident(self.h, raster.h, W, K, seed, out.ctypes.data_as(_u8p), out.size, C.byref(info)))
+        st = self.L.bic_encode_raster_resident(self.h, raster.h, W, K, seed, out.ctypes.data_as(_u8p), out.size, C.byref(info))
+        if st == 4:  # capacity: retry once with the size the library reported, as encode_raster does
+            out = np.zeros(int(info.container_bytes) + 64, np.uint8)
+            st = self.L.bic_encode_raster_resident(self.h, raster.h, W, K, seed, out.ctypes.data_as(_u8p), out.size, C.byref(info))
+        self._ck(st)
         return out[: int(info.container_bytes)], info
 
     def decode_raster(self, container: np.ndarray):

@@ -107,6 +107,7 @@ extern "C" bic_status bic_encode_raster(bic_ctx* c, const uint8_t* pbm_payload, 
                                         bic_encode_info* info) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !pbm_payload || W == 0 || K == 0 || rows == 0 || cols == 0) return BIC_ERR_INVALID;
+  if (out && ((uintptr_t)out & 7) != 0) return bic_fail(c, BIC_ERR_INVALID, "encode_raster: out must be 8-byte aligned");   // before the fit, not after
   EncWorkspace* w = ws_of(c);
   BIC_TRY(ws_prepare(c, w, rows, cols, W, K));
   BIC_TRY(bic_mat_upload_pbm(c, w->raster, pbm_payload));
@@ -118,6 +119,7 @@ extern "C" bic_status bic_encode_raster_resident(bic_ctx* c, const bic_mat* rast
                                                  uint8_t* out, uint64_t cap_bytes, bic_encode_info* info) {
   if (c) cudaSetDevice(c->device);  // the calling thread may be new to this device
   if (!c || !raster || W == 0 || K == 0 || raster->rows == 0 || raster->cols == 0) return BIC_ERR_INVALID;
+  if (out && ((uintptr_t)out & 7) != 0) return bic_fail(c, BIC_ERR_INVALID, "encode_raster: out must be 8-byte aligned");
   EncWorkspace* w = ws_of(c);
   BIC_TRY(ws_prepare(c, w, raster->rows, raster->cols, W, K));
   return encode_from_raster(c, w, raster, W, K, seed, out, cap_bytes, info);
