@@ -63,3 +63,32 @@ def sharded_update_dictionary(El, D, Al, allreduce):
         H += allreduce(corr)
         ncoll += 1
     return newD, changed, ncoll
+
+
+def sharded_golomb(bits_l, rank, nranks, allgather, encode_shard):
+    """csrc/coding2.cu bic_k_golomb_encode_multi_sharded's message flow for ONE matrix whose rows are sharded (rank order = row
+    order): all-gather of (ones, position after the local last one or 0, local bits) -> this shard's prefix state
+    (k_g2_shard_base1: samples before it, global position of its first bit, global position of the last one before it); the
+    shard's code bits under that state; all-gather of the code bits -> its code offset, and for the last rank the closing run
+    (k_g2_shard_base2). `encode_shard(ones_before, bits_before, last_one_before, closing, total_bits)` is the serial coder
+    started in that state. Returns (bytes, local code bits, code bit offset, global bit count, global samples)."""
+    flat = np.asarray(bits_l, np.uint8).reshape(-1)
+    nz = np.flatnonzero(flat)
+    mine = (int(len(nz)), int(nz[-1]) + 1 if len(nz) else 0, int(flat.size))
+    all1 = allgather(mine)
+    t0 = pos0 = 0
+    prev0 = lastg = -1
+    og = pos = 0
+    for r, (ones, after_last, nbits) in enumerate(all1):
+        if r == rank:
+            t0, pos0, prev0 = og, pos, lastg
+        if after_last:
+            lastg = pos + after_last - 1
+        og += ones
+        pos += nbits
+    total_bits = pos
+    closing = rank == nranks - 1
+    by, nbits_local, ns = encode_shard(t0, pos0, prev0, closing, total_bits)
+    all2 = allgather(int(nbits_local))
+    code0 = sum(all2[:rank])
+    return by, nbits_local, code0, sum(all2), og + 1
