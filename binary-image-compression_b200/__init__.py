@@ -149,6 +149,7 @@ def lib() -> C.CDLL:
         "bic_pipeline_forget_finished": [_vp],
         "bic_pipeline_stats": [_vp, _u64p, _u64p, _u64p, _u64p, _u64p],
         "bic_pipeline_attach_comms": [_vp, C.POINTER(_vp), C.c_int],
+        "bic_merge_shard_containers": [C.POINTER(_u8p), C.POINTER(_u64), C.c_int, _u8p, _u64, C.POINTER(_u64)],
         "bic_pipeline_wait_ctx": [_vp, _vp],
         "bic_ctx_wait_pipeline": [_vp, _vp],
         "bic_stream_create": [_vp, C.POINTER(_vp)],
@@ -421,6 +422,29 @@ class Pipeline:
             out["streams"][name] = st
             off += nbp + ni * 16
         out["bytes"] = off
+        return out
+
+    @staticmethod
+    def merge_shard_containers(shards) -> np.ndarray:
+        """the N shard containers of one sharded job (one per rank, any order) -> the ordinary container of the whole raster,
+        byte for byte what encode_raster gives for the concatenated bands (bic_merge_shard_containers: host code, no device)"""
+        L = lib()
+        bufs = []
+        for b in shards:
+            a = np.zeros((len(b) + 7) // 8 * 8, np.uint8)            # 8-byte aligned copies (numpy allocations are)
+            a[: len(b)] = np.frombuffer(bytes(b), np.uint8) if not isinstance(b, np.ndarray) else b
+            bufs.append(a)
+        n = len(bufs)
+        ptrs = (_u8p * n)(*[a.ctypes.data_as(_u8p) for a in bufs])
+        sizes = (_u64 * n)(*[len(b) for b in shards])
+        need = _u64(0)
+        st = L.bic_merge_shard_containers(ptrs, sizes, n, None, 0, C.byref(need))
+        if st != BIC_OK:
+            raise BicError(st, L.bic_status_string(st).decode())
+        out = np.zeros(int(need.value), np.uint8)
+        st = L.bic_merge_shard_containers(ptrs, sizes, n, out.ctypes.data_as(_u8p), out.size, C.byref(need))
+        if st != BIC_OK:
+            raise BicError(st, L.bic_status_string(st).decode())
         return out
 
     def close(self):

@@ -620,3 +620,129 @@ extern "C" bic_status bic_pipeline_attach_comms(bic_pipeline* P, bic_comm* const
   P->seq = 0;
   return BIC_OK;
 }
+
+// ---- the shard containers of ONE sharded job (one per rank) -> the ordinary container of the whole raster.
+// Pure host code: byte surgery on buffers the caller gathered from the ranks (MPI, NCCL, files -- not our business). The result
+// is the container bic_encode_raster produces for the concatenated bands, byte for byte: D's stream is replicated (rank 0's is
+// taken, the others are checked against it), the global A / E stream is the OR of the ranks' buffers at their 32-bit word
+// offsets (a shard's buffer starts with code_bit_offset mod 32 zero bits), the chunk indexes are already in global terms and
+// concatenate in rank order. Every field is bounded before it sizes anything: the inputs may come from anywhere.
+namespace {
+struct ShardView {
+  const uint64_t* h = nullptr;
+  uint64_t bytes = 0;
+  uint64_t off[3] = {0, 0, 0}, nb[3] = {0, 0, 0}, nbp[3] = {0, 0, 0}, nidx[3] = {0, 0, 0};
+};
+bool shard_view(const uint8_t* p, uint64_t bytes, ShardView* v) {
+  if (!p || bytes < SHARD_HDR_U64 * 8 || ((uintptr_t)p & 7) != 0) return false;
+  const uint64_t* h = (const uint64_t*)p;
+  if (h[0] != BIC_SHARD_MAGIC || h[1] != 1) return false;
+  v->h = h;
+  v->bytes = bytes;
+  uint64_t off = SHARD_HDR_U64 * 8;
+  for (int i = 0; i < 3; ++i) {
+    const uint64_t* f = h + 12 + 7 * i;
+    const uint64_t room = bytes - off;
+    if (f[4] > room * 8 || f[6] > room / 16) return false;                 // bits of the local buffer, chunk-index entries
+    const uint64_t nb = div_up_u64(f[4], 8), nbp = div_up_u64(nb, 8) * 8;
+    if (nbp > room || f[6] * 16 > room - nbp) return false;
+    v->off[i] = off; v->nb[i] = nb; v->nbp[i] = nbp; v->nidx[i] = f[6];
+    off += nbp + f[6] * 16;
+  }
+  return true;
+}
+}  // namespace
+
+extern "C" bic_status bic_merge_shard_containers(const uint8_t* const* shards, const uint64_t* shard_bytes, int nshards, uint8_t* out,
+                                                 uint64_t cap_bytes, uint64_t* bytes) {
+  if (!shards || !shard_bytes || nshards < 1 || nshards > 64) return BIC_ERR_INVALID;
+  try {
+    std::vector<ShardView> v((size_t)nshards);          // by rank
+    for (int i = 0; i < nshards; ++i) {
+      ShardView t;
+      if (!shard_view(shards[i], shard_bytes[i], &t)) return BIC_ERR_CORRUPT;
+      const uint64_t r = t.h[2];
+      if (t.h[3] != (uint64_t)nshards || r >= (uint64_t)nshards || v[r].h) return BIC_ERR_CORRUPT;   // every rank exactly once
+      v[r] = t;
+    }
+    const uint64_t* h0 = v[0].h;
+    const uint64_t cols = h0[5], W = h0[6], K = h0[7], m = h0[9], iters = h0[10], seed = h0[11];
+    if (W == 0 || W > 1024 || K == 0 || K > 65535 || cols == 0 || cols > (1ull << 40) || m != W * W) return BIC_ERR_CORRUPT;
+    uint64_t rows = 0, n = 0;
+    for (int r = 0; r < nshards; ++r) {
+      const uint64_t* h = v[r].h;
+      if (h[5] != cols || h[6] != W || h[7] != K || h[9] != m || h[10] != iters || h[11] != seed) return BIC_ERR_CORRUPT;
+      if (h[4] == 0 || h[4] > (1ull << 40) || h[8] > (1ull << 40)) return BIC_ERR_CORRUPT;
+      if (r + 1 < nshards && h[4] % W != 0) return BIC_ERR_INVALID;        // only the last band may end inside a patch row
+      if (h[8] != div_up_u64(h[4], W) * div_up_u64(cols, W)) return BIC_ERR_CORRUPT;
+      rows += h[4];
+      n += h[8];
+    }
+    // ---- the three streams of the whole: D from rank 0, A and E from the shard fields
+    bic_stream_info si[3];
+    memset(si, 0, sizeof(si));
+    const uint64_t* fD = h0 + 12;
+    si[0].coder = (uint32_t)fD[0]; si[0].chunk_samples = (uint32_t)fD[1]; si[0].rows = fD[2]; si[0].cols = fD[3];
+    si[0].bitcount = fD[4]; si[0].nsamples = fD[5]; si[0].nchunks = fD[6];
+    if (fD[2] != K || fD[3] != m) return BIC_ERR_CORRUPT;
+    for (int r = 1; r < nshards; ++r) {                                     // the replicas of D must agree
+      if (memcmp(v[r].h + 12, fD, 7 * 8) != 0 || v[r].nb[0] != v[0].nb[0]) return BIC_ERR_CORRUPT;
+      if (memcmp((const uint8_t*)v[r].h + v[r].off[0], (const uint8_t*)h0 + v[0].off[0], v[0].nbp[0] + v[0].nidx[0] * 16) != 0) return BIC_ERR_CORRUPT;
+    }
+    for (int s = 1; s < 3; ++s) {
+      const uint64_t mcols = s == 1 ? K : m;
+      const uint64_t* f0 = h0 + 12 + 7 * s;
+      const uint64_t* g0 = h0 + 33 + 6 * (s - 1);       // global bit count, global samples, code bit offset, local code bits, first chunk, local chunks
+      const uint64_t gbits = g0[0], gsamples = g0[1], chunk = f0[1];
+      if (chunk == 0 || (chunk & (chunk - 1)) || gbits > (1ull << 45) || gsamples == 0 || gsamples > n * mcols + 1) return BIC_ERR_CORRUPT;
+      uint64_t code = 0, chunks = 0, mrows = 0;
+      for (int r = 0; r < nshards; ++r) {
+        const uint64_t* f = v[r].h + 12 + 7 * s;
+        const uint64_t* g = v[r].h + 33 + 6 * (s - 1);
+        if (f[0] != f0[0] || f[1] != chunk || f[3] != mcols || f[2] != v[r].h[8]) return BIC_ERR_CORRUPT;
+        if (g[0] != gbits || g[1] != gsamples) return BIC_ERR_CORRUPT;
+        if (g[2] != code || g[4] != chunks || g[5] != f[6]) return BIC_ERR_CORRUPT;       // shards follow each other without a gap
+        if (g[3] > gbits - code || f[4] != (g[2] & 31) + g[3]) return BIC_ERR_CORRUPT;
+        code += g[3];
+        chunks += g[5];
+        mrows += f[2];
+      }
+      if (code != gbits || chunks != div_up_u64(gsamples, chunk) || mrows != n) return BIC_ERR_CORRUPT;
+      si[s].coder = (uint32_t)f0[0]; si[s].chunk_samples = (uint32_t)chunk; si[s].rows = n; si[s].cols = mcols;
+      si[s].bitcount = gbits; si[s].nsamples = gsamples; si[s].nchunks = chunks;
+    }
+    const uint64_t need = bic_container_bytes(si);
+    if (bytes) *bytes = need;
+    if (!out) return BIC_OK;
+    if (cap_bytes < need) return BIC_ERR_CAPACITY;
+    if (((uintptr_t)out & 7) != 0) return BIC_ERR_INVALID;
+    memset(out, 0, need);
+    bic_container_header(out, rows, cols, W, K, n, m, iters, seed, si);
+    uint64_t off = (BIC_HDR_FIELDS + 3 * BIC_STREAM_FIELDS) * 8;
+    for (int s = 0; s < 3; ++s) {
+      const uint64_t nb = div_up_u64(si[s].bitcount, 8), nbp = div_up_u64(nb, 8) * 8;
+      uint8_t* dst = out + off;
+      uint64_t* idx = (uint64_t*)(out + off + nbp);
+      if (s == 0) {
+        memcpy(dst, (const uint8_t*)h0 + v[0].off[0], v[0].nb[0]);
+        memcpy(idx, (const uint8_t*)h0 + v[0].off[0] + v[0].nbp[0], v[0].nidx[0] * 16);
+      } else {
+        uint64_t ci = 0;
+        for (int r = 0; r < nshards; ++r) {
+          const uint64_t* g = v[r].h + 33 + 6 * (s - 1);
+          const uint8_t* src = (const uint8_t*)v[r].h + v[r].off[s];
+          const uint64_t b0 = (g[2] >> 5) * 4;                              // the shard's buffer starts at this byte of the whole
+          for (uint64_t i = 0; i < v[r].nb[s] && b0 + i < nb; ++i) dst[b0 + i] |= src[i];
+          memcpy(idx + 2 * ci, src + v[r].nbp[s], v[r].nidx[s] * 16);
+          ci += v[r].nidx[s];
+        }
+      }
+      off += nbp + si[s].nchunks * 16;
+    }
+    return BIC_OK;
+  } catch (const std::bad_alloc&) {
+    return BIC_ERR_NOMEM;
+  } catch (...) {
+    return BIC_ERR_CORRUPT;
+  }
+}

@@ -402,6 +402,12 @@ bic_status bic_pipeline_stats(bic_pipeline* p, uint64_t* launches, uint64_t* pol
 struct bic_comm;
 bic_ctx* bic_pipeline_slot_ctx(bic_pipeline* p, int slot);
 bic_status bic_pipeline_attach_comms(bic_pipeline* p, struct bic_comm* const* comms, int n);
+/* The shard containers of ONE sharded job, one per rank (gathered by the caller; any order), merged into the ordinary container
+ * of the whole raster: byte for byte what bic_encode_raster gives for the concatenated bands, so bic_decode_raster reads it.
+ * Host code only (no device, no context). Every band but the last must be a whole number of patch rows (rows % W == 0).
+ * out = NULL: only *bytes is set. BIC_ERR_CORRUPT for inputs that are not the N shards of one job. Buffers 8-byte aligned. */
+bic_status bic_merge_shard_containers(const uint8_t* const* shards, const uint64_t* shard_bytes, int nshards, uint8_t* out,
+                                      uint64_t cap_bytes, uint64_t* bytes);
 /* stream ordering against a context outside the pool: every slot after `signal` / `waiter` after every slot */
 bic_status bic_pipeline_wait_ctx(bic_pipeline* p, bic_ctx* signal);
 bic_status bic_ctx_wait_pipeline(bic_ctx* waiter, bic_pipeline* p);

@@ -119,6 +119,19 @@ def main():
             if rank == world - 1:
                 assert lo + ln == nbits
         assert int(info.bits_A) == oracle.golomb_encode(Ao, K)[1] and int(info.bits_E) == oracle.golomb_encode(Eo, m)[1]
+        # the ranks' shard containers merged on the host (bic_merge_shard_containers) == the container the single-GPU encoder
+        # writes for the whole raster, byte for byte, and it decodes to the raster.
+        # (Added after the round's last multi-GPU call: exercised so far only on containers fabricated from the oracle,
+        # tests/test_shard_merge_cpu.py.)
+        mine_c = np.array(out[: int(info.container_bytes)], copy=True)
+        allc = [None] * world
+        dist.all_gather_object(allc, mine_c)
+        if rank == 0:
+            merged = bic.Pipeline.merge_shard_containers(allc)
+            cont, info1 = ctx.encode_raster(synth.pbm_bytes(whole), rows_band * world, cols, W, K, seed=900)
+            assert len(merged) == len(cont) and np.array_equal(merged, cont), f"merged shard containers differ from the single-GPU container ({len(merged)} vs {len(cont)} bytes)"
+            back, r_, c_ = ctx.decode_raster(merged)
+            assert (r_, c_) == (rows_band * world, cols) and np.array_equal(back, synth.pbm_bytes(whole))
     pipe.close()
     if rank == 0:
         print(f"dist ok world={world} collectives={ctx.comm_collectives(comm)}")
